@@ -1,0 +1,224 @@
+"""Seeded synthetic dexel volumes / images in generic position.
+
+These stand in for `vor3d::create_dexels` output (src/vor3d/Dexelize.cpp:231-274): the grid follows
+the `CompressedVolume` constructor (CompressedVolume.cpp:11-23), column centres are
+`(i + 0.5) * spacing + origin` (Dexelize.cpp:166-225) and z is stored as `world_z / spacing`.
+All shapes are shifted by small irrational offsets so that no two interval endpoints coincide
+exactly (the reference's brute_force method is tie-unstable on degenerate inputs).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .volume import CompressedVolume, DexelImage, csr_from_lists
+
+_JX, _JY, _JZ = 0.0137, 0.0071, 0.0093  # generic-position jitter, in dexels
+
+
+def _grid(extent, n, padding, min_corner):
+    spacing = max(extent) / n
+    vol = CompressedVolume.from_box(min_corner, extent, spacing, padding)
+    xs = (np.arange(vol.nx) + 0.5) * spacing + vol.origin[0]
+    ys = (np.arange(vol.ny) + 0.5) * spacing + vol.origin[1]
+    return vol, xs, ys, spacing
+
+
+def _single_interval_volume(vol, lo, hi, mask):
+    """One interval [lo, hi] where mask, none elsewhere. lo/hi/mask are (ny, nx)."""
+    cnt = mask.reshape(-1).astype(np.int64)
+    off = np.zeros(cnt.size + 1, dtype=np.int64)
+    np.cumsum(cnt, out=off[1:])
+    spans = np.stack([lo.reshape(-1)[mask.reshape(-1)], hi.reshape(-1)[mask.reshape(-1)]], axis=1)
+    return vol.like(vol.nx, vol.ny, off, spans)
+
+
+def torus_z(n: int, padding: int = 0, major: float = 1.0, minor: float = 0.35) -> CompressedVolume:
+    """Torus with axis z (square footprint, at most one interval per column): configs C4 / C5."""
+    ext = (2 * (major + minor), 2 * (major + minor), 2 * minor)
+    corner = (-(major + minor), -(major + minor), -minor)
+    vol, xs, ys, sp = _grid(ext, n, padding, corner)
+    X, Y = np.meshgrid(xs + _JX * sp, ys + _JY * sp)
+    rho = np.sqrt(X * X + Y * Y)
+    d2 = minor * minor - (rho - major) ** 2
+    mask = d2 > 0
+    half = np.sqrt(np.where(mask, d2, 0.0))
+    zc = _JZ * sp
+    return _single_interval_volume(vol, (zc - half) / sp, (zc + half) / sp, mask)
+
+
+def torus_x(n: int, padding: int = 0, major: float = 1.0, minor: float = 0.35) -> CompressedVolume:
+    """Torus with axis x (up to two intervals per column): config C1 (grid 67 x 256 at n=256)."""
+    ext = (2 * minor, 2 * (major + minor), 2 * (major + minor))
+    corner = (-minor, -(major + minor), -(major + minor))
+    vol, xs, ys, sp = _grid(ext, n, padding, corner)
+    X, Y = np.meshgrid(xs + _JX * sp, ys + _JY * sp)
+    zc = _JZ * sp
+    # point (x, y, z) inside  <=>  (sqrt(y^2+z^2) - major)^2 + x^2 < minor^2
+    w2 = minor * minor - X * X
+    lists = []
+    flat_w2 = w2.reshape(-1)
+    flat_y = Y.reshape(-1)
+    for w2c, y in zip(flat_w2, flat_y):
+        if w2c <= 0:
+            lists.append(())
+            continue
+        w = math.sqrt(w2c)
+        ro, ri = major + w, major - w          # outer / inner radius of the annulus in the (y,z) plane
+        if abs(y) >= ro:
+            lists.append(())
+            continue
+        zo = math.sqrt(ro * ro - y * y)
+        if abs(y) >= ri:
+            lists.append(((zc - zo) / sp, (zc + zo) / sp))
+        else:
+            zi = math.sqrt(ri * ri - y * y)
+            lists.append(((zc - zo) / sp, (zc - zi) / sp, (zc + zi) / sp, (zc + zo) / sp))
+    off, spans = csr_from_lists(lists)
+    return vol.like(vol.nx, vol.ny, off, spans)
+
+
+def lattice(n: int, padding: int = 10, seed: int = 3) -> CompressedVolume:
+    """Filigree-like jittered lattice of axis-aligned bars (config C3: -n 512 -p 10).
+
+    Bars of width 5..8 dexels with period 16..24 along x, y and z; every bar edge is at
+    `k*period + eps*(1 + 0.37 k)` so no two endpoints coincide.
+    """
+    rng = np.random.RandomState(seed)
+    eps = 0.0137
+    ext = (1.0, 1.0, 1.0)
+    vol, xs, ys, sp = _grid(ext, n, padding, (0.0, 0.0, 0.0))
+
+    def bars(length):
+        out, k, pos = [], 0, 2.0 + rng.uniform(0, 4)
+        while pos < length - 10:
+            w = rng.uniform(5.0, 8.0)
+            a = pos + eps * (1 + 0.37 * k)
+            out.append((a, a + w))
+            pos += rng.uniform(16.0, 24.0)
+            k += 1
+        return out
+
+    bx, by, bz = bars(n), bars(n), bars(n)
+    p = padding
+
+    def inside(bs, coord):
+        m = np.zeros(coord.shape, dtype=bool)
+        for a, b in bs:
+            m |= (coord > a) & (coord < b)
+        return m
+
+    cx = np.arange(vol.nx) - p + 0.5 + _JX
+    cy = np.arange(vol.ny) - p + 0.5 + _JY
+    in_x = inside(bx, cx)
+    in_y = inside(by, cy)
+    grid_ok_x = (cx > 0) & (cx < n)
+    grid_ok_y = (cy > 0) & (cy < n)
+    z0, z1 = 1.0 + _JZ, n - 1.0 - _JZ * 0.7
+    lists = []
+    for j in range(vol.ny):
+        for i in range(vol.nx):
+            if not (grid_ok_x[i] and grid_ok_y[j]):
+                lists.append(())
+            elif in_x[i] and in_y[j]:
+                lists.append((z0 + 0.011 * ((i * 7 + j * 3) % 13), z1 - 0.013 * ((i * 5 + j * 11) % 17)))  # z-bar
+            elif in_x[i] or in_y[j]:
+                ev = []
+                for k, (a, b) in enumerate(bz):          # x- or y-bar seen end-on: one interval per z level
+                    ev += [a + 0.0021 * ((i + 2 * j + k) % 7), b + 0.0017 * ((2 * i + j + k) % 5)]
+                lists.append(ev)
+            else:
+                lists.append(())
+    off, spans = csr_from_lists(lists)
+    return vol.like(vol.nx, vol.ny, off, spans)
+
+
+def random_volume(nx: int, ny: int, kmax: int = 8, seed: int = 7, zrange: float = 64.0,
+                  fill: float = 1.0, padding: int = 0) -> CompressedVolume:
+    """Multi-interval stress volume: k ~ U{0..kmax} intervals per column, lengths U[0.3, 6].
+
+    `padding` behaves like offset3d's -p: `padding` empty columns on every side and `padding`
+    dexels of head-room below and above the data in z (CompressedVolume.cpp:17-20,
+    VoronoiVorPower.cpp:28-29), which closing / opening need to stay inside [zmin, zmax].
+    """
+    rng = np.random.RandomState(seed)
+    inner = {}
+    zhi = 1.0
+    for j in range(ny):
+        for i in range(nx):
+            k = rng.randint(0, kmax + 1) if rng.uniform() < fill else 0
+            ev, z = [], rng.uniform(0, 5)
+            for _ in range(k):
+                z += rng.uniform(0.05, zrange / max(kmax, 1))
+                a = z
+                z += rng.uniform(0.3, 6.0)
+                ev += [a, z]
+            inner[(i, j)] = ev
+            if ev:
+                zhi = max(zhi, ev[-1])
+    zhi = math.ceil(zhi) + 1.0
+    p = padding
+    gx, gy = nx + 2 * p, ny + 2 * p
+    lists = [inner.get((i - p, j - p), ()) for j in range(gy) for i in range(gx)]
+    off, spans = csr_from_lists(lists)
+    return CompressedVolume(gx, gy, off, spans, origin=(-float(p), -float(p), -float(p)),
+                            extent=(float(nx), float(ny), zhi), spacing=1.0, padding=p)
+
+
+def star_image(rows: int = 2048, width: int = 2048, n_polys: int = 64, seed: int = 1234) -> DexelImage:
+    """Config C2: star polygons (5..12 spikes) scan-converted at row centres, rows = sweep axis.
+
+    This plays the role of `DoubleCompressedImage::fromImage` (src/vor2d/DoubleCompressedImage.cpp:
+    25-111), which is upstream of the hot path; parity is pinned at the dexel-image boundary.
+    """
+    rng = np.random.RandomState(seed)
+    g = int(math.ceil(math.sqrt(n_polys)))
+    cell_r, cell_c = rows / g, width / g
+    per_row = [[] for _ in range(rows)]
+    for p in range(n_polys):
+        cy = (p // g + 0.5) * cell_r + rng.uniform(-0.1, 0.1) * cell_r
+        cx = (p % g + 0.5) * cell_c + rng.uniform(-0.1, 0.1) * cell_c
+        nv = rng.randint(5, 13)
+        ang0 = rng.uniform(0, 2 * math.pi)
+        pts = []
+        for v in range(2 * nv):
+            rad = min(cell_r, cell_c) * (rng.uniform(0.25, 0.35) if v % 2 == 0 else rng.uniform(0.09, 0.18))
+            a = ang0 + math.pi * v / nv
+            pts.append((cy + rad * math.sin(a), cx + rad * math.cos(a)))
+        pts = np.array(pts)
+        r0 = max(0, int(math.floor(pts[:, 0].min())) - 1)
+        r1 = min(rows - 1, int(math.ceil(pts[:, 0].max())) + 1)
+        q = np.roll(pts, -1, axis=0)
+        for i in range(r0, r1 + 1):
+            yy = i + 0.5 + 0.00173
+            crossing = (pts[:, 0] <= yy) != (q[:, 0] <= yy)
+            if not crossing.any():
+                continue
+            t = (yy - pts[crossing, 0]) / (q[crossing, 0] - pts[crossing, 0])
+            xs = np.sort(pts[crossing, 1] + t * (q[crossing, 1] - pts[crossing, 1]))
+            xs = np.clip(xs, 0.0, float(width))
+            for k in range(0, len(xs) - 1, 2):
+                if xs[k + 1] > xs[k]:
+                    per_row[i].append((xs[k], xs[k + 1]))
+    lists = []
+    for i in range(rows):
+        iv = sorted(per_row[i])
+        merged = []
+        for a, b in iv:
+            if merged and a <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], b)
+            else:
+                merged.append([a, b])
+        lists.append([v for ab in merged for v in ab])
+    return DexelImage.from_lists(width, lists)
+
+
+def random_image(rows: int, width: int, kmax: int = 6, seed: int = 11) -> DexelImage:
+    rng = np.random.RandomState(seed)
+    lists = []
+    for _ in range(rows):
+        k = rng.randint(0, kmax + 1)
+        pts = np.sort(rng.uniform(0.01, width - 0.01, size=2 * k))
+        lists.append(pts.tolist())
+    return DexelImage.from_lists(width, lists)
