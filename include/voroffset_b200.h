@@ -1,0 +1,137 @@
+/*
+ * voroffset_b200 - C ABI of the B200-native dexel-morphology hot path.
+ *
+ * This header is the drop-in boundary. Every entry point names the reference interface it replaces
+ * (paths relative to the geometryprocessing/voroffset tree). Only plain pointers and sizes cross it;
+ * there are no torch / C++ types in the signatures. The library (libvoroffset_b200.so) is CUDA-only:
+ * there is no CPU fallback, every compute entry point fails with VO_ERR_CUDA when no sm_100 device is
+ * usable.
+ *
+ * Data layout (same on host and in HBM): a dexel volume with nx*ny columns is a CSR pair
+ *   off   : uint32_t[nx*ny + 1]   column (x,y) is list c = x + nx*y  (CompressedVolume.h:28-29)
+ *   spans : double  [2 * off[nx*ny]]  (z1,z2) pairs, ascending and disjoint inside a column, in dexel
+ *           units (world z / spacing, Dexelize.cpp:204).   vo_span_bytes() == 16.
+ * A 2D dexel image (DoubleCompressedImage) is the same with one list per row.
+ *
+ * Threading: a vo_ctx owns one CUDA device, one stream and its scratch memory; it is not
+ * thread-safe. Use one context per calling thread / per GPU.
+ *
+ * Errors: every function returns VO_OK (0) or a VO_ERR_* code; vo_last_error(ctx) gives the text.
+ * The C++ adapters (voroffset_b200/cpp) turn a non-zero code into std::runtime_error, which is what
+ * the reference's vor_assert does (src/vor3d/Common.cpp:7-17).
+ */
+#ifndef VOROFFSET_B200_H
+#define VOROFFSET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VO_OK              0
+#define VO_ERR_ARG         1   /* invalid argument (bad op / method / sizes / unsorted offsets)        */
+#define VO_ERR_CUDA        2   /* CUDA runtime failure, or no usable device                            */
+#define VO_ERR_NOMEM       3   /* host or device allocation failed                                     */
+#define VO_ERR_OVERFLOW    4   /* interval count exceeds the uint32 CSR offsets / a list capacity      */
+
+/* op for the 3D entry points: app/cli3d/offset3d.cpp:116-136 (-x dilation|erosion|opening|closing). */
+#define VO_OP_DILATION     0
+#define VO_OP_EROSION      1
+#define VO_OP_OPENING      2
+#define VO_OP_CLOSING      3
+/* method: app/cli3d/offset3d.cpp:104-112 (-m ours|brute_force).                                      */
+#define VO_METHOD_OURS         0   /* VoronoiMorphoVorPower  (src/vor3d/VoronoiVorPower.cpp:24-96)   */
+#define VO_METHOD_BRUTE_FORCE  1   /* VoronoiMorphoBruteForce (src/vor3d/VoronoiBruteForce.cpp:16-100) */
+/* op for the 2D entry points: DoubleCompressedImage::dilate/erode/open/close/negate
+ * (src/vor2d/DoubleCompressedImage.h:96-111).                                                        */
+#define VO_OP2D_DILATE     0
+#define VO_OP2D_ERODE      1
+#define VO_OP2D_OPEN       2
+#define VO_OP2D_CLOSE      3
+#define VO_OP2D_NEGATE     4
+
+typedef struct vo_ctx  vo_ctx;
+typedef struct vo_dvol vo_dvol;   /* a dexel volume resident in HBM (device CSR)                      */
+typedef struct vo_dmid vo_dmid;   /* the intermediate volume between the two passes, resident in HBM:
+                                     replaces CompressedVolumeWithRadii (CompressedVolumeWithRadii.h:10-38) */
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+int         vo_create(int device, vo_ctx **out);
+void        vo_destroy(vo_ctx *ctx);
+const char *vo_last_error(const vo_ctx *ctx);   /* never NULL; "" when the last call succeeded         */
+const char *vo_version(void);
+int         vo_span_bytes(void);                /* 16: spans are (double z1, double z2)                */
+void        vo_free(void *host_ptr);            /* releases a host buffer returned by vo_morph3d/2d    */
+/* Stream the context launches on (a cudaStream_t), for callers that time with CUDA events.           */
+void       *vo_stream(const vo_ctx *ctx);
+/* Number of kernel launches issued by this context so far (bench.py's gpu_launches).                 */
+uint64_t    vo_launch_count(const vo_ctx *ctx);
+
+/* ---- host-buffer drop-in: one call = upload, operator, download -------------------------------- */
+/* Replaces  VoronoiMorpho::dilation / ::erosion  (src/vor3d/Voronoi.h:18,29; Voronoi.cpp:8-17) and the
+ * opening / closing compositions of app/cli3d/offset3d.cpp:124-133.
+ *   zmin, zmax : origin_z/spacing and zmin + 2*padding + extent_z/spacing (VoronoiVorPower.cpp:28-29);
+ *                only erosion (and therefore opening / closing) reads them (Voronoi.cpp:10-11).
+ *   radius     : in dexels (offset3d.cpp:73-75 has already divided by the spacing for -u).
+ *   out_off / out_spans : pinned host buffers owned by the caller afterwards, release with vo_free().
+ *                The output grid is nx*ny again (Voronoi.cpp:57-89 strips erosion's border).
+ *   ms_pass1 / ms_pass2 : device time of the two passes in milliseconds, the time_1 / time_2
+ *                out-parameters of the reference (VoronoiVorPower.cpp:66,95). For composites they hold
+ *                the last primitive, like offset3d.cpp:127-133. May be NULL.                          */
+int vo_morph3d(vo_ctx *ctx, int op, int method, int nx, int ny, double zmin, double zmax,
+               const uint32_t *off, const double *spans, double radius,
+               uint32_t **out_off, double **out_spans, uint64_t *out_nspans,
+               double *ms_pass1, double *ms_pass2);
+
+/* Replaces  DoubleCompressedImage::dilate / erode / open / close / negate
+ * (src/vor2d/DoubleCompressedImage.cpp:438-468,680-719). `r` is the argument of the member function,
+ * untouched: dilate sweeps with R = r*rows, erode with R = r (DoubleCompressedImage.cpp:685-686,698-699). */
+int vo_morph2d(vo_ctx *ctx, int op, int rows, int width, const uint32_t *off, const double *spans, double r,
+               uint32_t **out_off, double **out_spans, uint64_t *out_nspans, double *ms);
+
+/* Replaces  VoronoiMorpho::calculateXor (src/vor3d/Voronoi.cpp:91-111): symmetric difference of two
+ * same-grid volumes, slivers shorter than 1e-10 dropped (MorphologyOperators.cpp:354-374); *volume is
+ * spacing^3 * total length (CompressedVolume.cpp:61-73).                                              */
+int vo_xor3d(vo_ctx *ctx, int nx, int ny, double zmin, double zmax, double spacing,
+             const uint32_t *off_a, const double *spans_a, const uint32_t *off_b, const double *spans_b,
+             uint32_t **out_off, double **out_spans, uint64_t *out_nspans, double *volume);
+
+/* ---- device-resident API (inputs and results stay in HBM) --------------------------------------- */
+/* CompressedVolume storage (src/vor3d/CompressedVolume.h:14) converted to device CSR.                 */
+int  vo_dvol_upload(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans, vo_dvol **out);
+int  vo_dvol_download(vo_ctx *ctx, const vo_dvol *vol, uint32_t *off, double *spans);
+/* Shape and raw device pointers (uint32_t* / double*) of a resident volume.                           */
+int  vo_dvol_info(const vo_dvol *vol, int *nx, int *ny, uint64_t *nspans, const void **d_off, const void **d_spans);
+void vo_dvol_free(vo_ctx *ctx, vo_dvol *vol);
+/* Copy of rows [y0, y1) of a resident volume (a y-slab; rows are contiguous in the x-fastest layout). */
+int  vo_dvol_rows(vo_ctx *ctx, const vo_dvol *vol, int y0, int y1, vo_dvol **out);
+/* Concatenate up to three y-slabs of equal nx (NULL entries are skipped).                             */
+int  vo_dvol_concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const vo_dvol *c, vo_dvol **out);
+
+/* Same operators as vo_morph3d on resident volumes.                                                   */
+int  vo_morph3d_dev(vo_ctx *ctx, int op, int method, const vo_dvol *in, double zmin, double zmax,
+                    double radius, vo_dvol **out, double *ms_pass1, double *ms_pass2);
+int  vo_xor3d_dev(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, double zmin, double zmax, double spacing,
+                  vo_dvol **out, double *volume);
+
+/* The two passes of 'ours' separately (what a multi-GPU driver interleaves with its halo exchange).
+ * Pass 1 (x-direction): for every column and every radius class j = |dy| the union over |dx| <= reach(j)
+ * of the column's neighbours capped by sqrt(r1(j)^2 - dx^2)  - the work of
+ * VoronoiMorpho2D / halfDilate (Voronoi2D.cpp:591-739, HalfDilationOperator.cpp:6-29).
+ * Pass 2 (y-direction): out(x,y) = union over |dy| <= floor(R) of class |dy| of column (x, y+dy) - the work
+ * of SeparatePowerMorpho2D + unionMap (SeparatePower2D.cpp:215-341, HalfDilationOperator.hpp:5-16).
+ * Pass 2 produces rows [y0, y1) of the mid volume's grid.                                              */
+int  vo_pass1_dev(vo_ctx *ctx, const vo_dvol *in, double radius, vo_dmid **mid, double *ms);
+int  vo_pass2_dev(vo_ctx *ctx, const vo_dmid *mid, int y0, int y1, vo_dvol **out, double *ms);
+void vo_dmid_free(vo_ctx *ctx, vo_dmid *mid);
+int  vo_dmid_info(const vo_dmid *mid, int *nx, int *ny, int *classes, uint64_t *bytes);
+
+/* 2D on resident data (one list per row).                                                             */
+int  vo_morph2d_dev(vo_ctx *ctx, int op, const vo_dvol *rows_as_vol /* nx = rows, ny = 1 */, int width,
+                    double r, vo_dvol **out, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOROFFSET_B200_H */

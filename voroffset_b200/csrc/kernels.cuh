@@ -1,0 +1,485 @@
+// Gather kernels of the dexel-morphology hot path (sm_100a).
+//
+// Data layout in HBM
+//   dexel volume   : CSR, off[nx*ny+1] (uint32) + spans[M] (double2 = (z1,z2)), column (x,y) = x + nx*y.
+//   mid volume     : dense slots mid[(y*(J+1) + j)*nx + x] (double2), j = |dy| radius class, J = floor(R);
+//                    a slot is one interval, empty, or a reference into the mid pool (run_union.cuh).
+//   staged output  : cnt[c] + 2 inline slots per list + a pool for longer lists; k_compact turns it into
+//                    canonical CSR after the prefix sum over cnt.
+//   cap tables     : host-computed doubles (vo_lib.cu: make_tables) so that every cap height carries the
+//                    reference's exact fp64 operation order, independent of GPU sqrt / FMA behaviour.
+#pragma once
+#include "run_union.cuh"
+
+namespace vo {
+
+constexpr int CAP_FAST = 16;    // running-union capacity of the first launch
+constexpr int CAP_BIG = 512;    // capacity of the redo launch for lists that outgrew CAP_FAST
+constexpr int STAGE_INLINE = 2; // inline slots per staged list
+
+struct Stage {
+	uint32_t *cnt;                 // [nlists]
+	double2 *inl;                  // [nlists * STAGE_INLINE]
+	double2 *pool;                 // [pool_cap]
+	unsigned long long *cursor;    // pool allocation cursor (keeps counting past pool_cap)
+	unsigned long long pool_cap;
+};
+
+struct Redo {
+	unsigned long long *list;      // ids of lists whose running union overflowed CAP_FAST
+	unsigned int *count;
+	unsigned int cap;
+};
+
+template <int CAP>
+__device__ __forceinline__ void stage_emit(const Stage &st, size_t c, const RunUnion<CAP> &u)
+{
+	st.cnt[c] = (uint32_t)u.n;
+	if (u.n <= STAGE_INLINE) {
+		for (int k = 0; k < u.n; ++k) st.inl[c * STAGE_INLINE + k] = u.get(k);
+	} else {
+		unsigned long long base = atomicAdd(st.cursor, (unsigned long long)u.n);
+		if (base + u.n <= st.pool_cap)
+			for (int k = 0; k < u.n; ++k) st.pool[base + k] = u.L[k];
+		st.inl[c * STAGE_INLINE] = slot_pool(base, (unsigned int)u.n);
+	}
+}
+
+__device__ __forceinline__ void redo_push(const Redo &rd, unsigned long long id)
+{
+	unsigned int k = atomicAdd(rd.count, 1u);
+	if (k < rd.cap) rd.list[k] = id;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 'ours', pass 1 (x-direction). One thread per (x, y, j): the union over |dx| <= reach[j] of the
+// intervals of column (x+dx, y) grown by H[j][|dx|] = sqrt(r1(j)^2 - dx^2), r1(j) = sqrt(R^2 - j^2).
+// This is the per-slice 2D dilation the reference's VoronoiMorpho2D sweep computes
+// (src/vor3d/Voronoi2D.cpp:591-739 driven by halfDilate, HalfDilationOperator.cpp:6-29), evaluated
+// for every radius class so that pass 2 needs no arithmetic at all.
+// Lanes run along x: offsets and spans of neighbouring columns are read coalesced.
+// ---------------------------------------------------------------------------------------------------
+struct Pass1Args {
+	int nx, ny, J;
+	const uint32_t *off;
+	const double2 *spans;
+	const double *H;        // (J+1)*(J+1), [j][|dx|]
+	const int *reach;       // J+1
+	double2 *mid;
+	double2 *pool;
+	unsigned long long *cursor;
+	unsigned long long pool_cap;
+	Redo redo;
+	const unsigned long long *work; // NULL: all slots; else the redo list
+	unsigned long long nwork;
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(128) k_pass1(Pass1Args a)
+{
+	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= a.nwork) return;
+	const unsigned long long slot = a.work ? a.work[tid] : tid;
+	const int x = (int)(slot % (unsigned)a.nx);
+	const unsigned long long rest = slot / (unsigned)a.nx;
+	const int j = (int)(rest % (unsigned)(a.J + 1));
+	const int y = (int)(rest / (unsigned)(a.J + 1));
+
+	RunUnion<CAP> u;
+	u.init();
+	const int X = a.reach[j];
+	const int lo = max(-X, -x), hi = min(X, a.nx - 1 - x);
+	const double *Hrow = a.H + (size_t)j * (a.J + 1);
+	const size_t c0 = (size_t)y * a.nx + x;
+	uint32_t o0 = __ldg(a.off + c0 + lo);
+	for (int dx = lo; dx <= hi; ++dx) {
+		const uint32_t o1 = __ldg(a.off + c0 + dx + 1);
+		if (o1 > o0) {
+			const double h = __ldg(Hrow + abs(dx));
+			for (uint32_t k = o0; k < o1; ++k) {
+				const double2 v = __ldg(a.spans + k);
+				u.insert(v.x - h, v.y + h);
+			}
+		}
+		o0 = o1;
+	}
+	double2 out;
+	if (u.overflow) { redo_push(a.redo, slot); out = slot_empty(); }
+	else if (u.n == 0) out = slot_empty();
+	else if (u.n == 1) out = make_double2(u.s0, u.e0);
+	else {
+		unsigned long long base = atomicAdd(a.cursor, (unsigned long long)u.n);
+		if (base + u.n <= a.pool_cap)
+			for (int k = 0; k < u.n; ++k) a.pool[base + k] = u.L[k];
+		out = slot_pool(base, (unsigned int)u.n);
+	}
+	a.mid[slot] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 'ours', pass 2 (y-direction). One thread per output column (x, y): the plain union of class |dy| of
+// column (x, y+dy) for |dy| <= J. Replaces the SeparatePowerMorpho2D sweep + unionMap
+// (src/vor3d/SeparatePower2D.cpp:215-341, HalfDilationOperator.hpp:5-16). Lanes run along x, so each
+// (dy) step is one coalesced 512-byte row segment of the mid volume.
+// ---------------------------------------------------------------------------------------------------
+struct Pass2Args {
+	int nx, ny, J;          // grid of the mid volume
+	int y0, y1;             // rows produced
+	const double2 *mid;
+	const double2 *pool;
+	Stage st;
+	Redo redo;
+	const unsigned long long *work;
+	unsigned long long nwork;
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
+{
+	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= a.nwork) return;
+	const unsigned long long c = a.work ? a.work[tid] : tid;     // output list index, rows relative to y0
+	const int x = (int)(c % (unsigned)a.nx);
+	const int y = a.y0 + (int)(c / (unsigned)a.nx);
+
+	RunUnion<CAP> u;
+	u.init();
+	const int lo = max(-a.J, -y), hi = min(a.J, a.ny - 1 - y);
+	for (int dy = lo; dy <= hi; ++dy) {
+		const double2 s = __ldg(a.mid + ((size_t)(y + dy) * (a.J + 1) + abs(dy)) * a.nx + x);
+		if (s.x <= s.y) u.insert(s.x, s.y);
+		else if (slot_is_pool(s)) {
+			const unsigned long long base = slot_pool_base(s);
+			const unsigned int n = slot_pool_count(s);
+			for (unsigned int k = 0; k < n; ++k) {
+				const double2 v = __ldg(a.pool + base + k);
+				u.insert(v.x, v.y);
+			}
+		}
+	}
+	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
+	stage_emit(a.st, (size_t)c, u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// 'brute_force' (src/vor3d/VoronoiBruteForce.cpp:16-100): one thread per output column gathers the
+// whole disc. HB[|dy|][|dx|] = sqrt(R*R - dx^2 - dy^2) where dx^2 + dy^2 <= R*R, else -1.
+// ---------------------------------------------------------------------------------------------------
+struct BruteArgs {
+	int nx, ny, J;
+	const uint32_t *off;
+	const double2 *spans;
+	const double *HB;       // (J+1)*(J+1), [|dy|][|dx|]
+	Stage st;
+	Redo redo;
+	const unsigned long long *work;
+	unsigned long long nwork;
+};
+
+template <int CAP>
+__global__ void __launch_bounds__(128) k_brute(BruteArgs a)
+{
+	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= a.nwork) return;
+	const unsigned long long c = a.work ? a.work[tid] : tid;
+	const int x = (int)(c % (unsigned)a.nx);
+	const int y = (int)(c / (unsigned)a.nx);
+
+	RunUnion<CAP> u;
+	u.init();
+	const int ylo = max(-a.J, -y), yhi = min(a.J, a.ny - 1 - y);
+	const int xlo = max(-a.J, -x), xhi = min(a.J, a.nx - 1 - x);
+	for (int dy = ylo; dy <= yhi; ++dy) {
+		const double *Hrow = a.HB + (size_t)abs(dy) * (a.J + 1);
+		const size_t c0 = (size_t)(y + dy) * a.nx + x;
+		uint32_t o0 = __ldg(a.off + c0 + xlo);
+		for (int dx = xlo; dx <= xhi; ++dx) {
+			const uint32_t o1 = __ldg(a.off + c0 + dx + 1);
+			if (o1 > o0) {
+				const double h = __ldg(Hrow + abs(dx));
+				if (h >= 0.0)
+					for (uint32_t k = o0; k < o1; ++k) {
+						const double2 v = __ldg(a.spans + k);
+						u.insert(v.x - h, v.y + h);
+					}
+			}
+			o0 = o1;
+		}
+	}
+	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
+	stage_emit(a.st, (size_t)c, u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// vor2d (src/vor2d/DoubleCompressedImage.cpp:680-703, DoubleVoronoi.h:101-148, DoubleVoronoi.cpp:713-725):
+// one thread per row i gathers rows i+di, |di| <= J, caps h2[|di|] = sqrt(R*R - di*di), every candidate
+// clamped to [0, W] and dropped when it lies outside. complement != 0 is the erosion sweep: the seeds
+// are the gaps of each row with extremes -1 and W, and rows -1 and `rows` are full sentinels.
+// ---------------------------------------------------------------------------------------------------
+struct Dil2dArgs {
+	int rows, J, complement;
+	double W;
+	const uint32_t *off;
+	const double2 *spans;
+	const double *h2;       // J+1
+	Stage st;
+	Redo redo;
+	const unsigned long long *work;
+	unsigned long long nwork;
+};
+
+template <int CAP>
+__device__ __forceinline__ void clamp_insert(RunUnion<CAP> &u, double y1, double y2, double h, double W)
+{
+	const double a = (y1 - h > 0) ? y1 - h : 0;
+	const double b = (y2 + h < W) ? y2 + h : W;
+	if (a > W || b < 0) return;
+	u.insert(a, b);
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(64) k_dilate2d(Dil2dArgs a)
+{
+	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= a.nwork) return;
+	const unsigned long long c = a.work ? a.work[tid] : tid;
+	const int i = (int)c;
+	RunUnion<CAP> u;
+	u.init();
+	for (int di = -a.J; di <= a.J; ++di) {
+		const int r = i + di;
+		const double h = __ldg(a.h2 + abs(di));
+		if (!a.complement) {
+			if (r < 0 || r >= a.rows) continue;
+			for (uint32_t k = a.off[r]; k < a.off[r + 1]; ++k) {
+				const double2 v = __ldg(a.spans + k);
+				clamp_insert(u, v.x, v.y, h, a.W);
+			}
+		} else {
+			if (r < -1 || r > a.rows) continue;
+			if (r == -1 || r == a.rows) { clamp_insert(u, -1.0, a.W, h, a.W); continue; }
+			double j2 = a.W;
+			for (long long k = (long long)a.off[r + 1] - 1; k >= (long long)a.off[r]; --k) {
+				const double2 v = __ldg(a.spans + k);
+				clamp_insert(u, v.y, j2, h, a.W);
+				j2 = v.x;
+			}
+			clamp_insert(u, -1.0, j2, h, a.W);
+		}
+	}
+	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
+	stage_emit(a.st, (size_t)c, u);
+}
+
+// Staged lists -> canonical CSR (after the exclusive scan of cnt).
+__global__ void __launch_bounds__(256) k_compact(Stage st, unsigned long long nlists,
+                                                 const uint32_t *__restrict__ off, double2 *__restrict__ spans)
+{
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nlists) return;
+	const uint32_t n = st.cnt[c];
+	if (n == 0) return;
+	double2 *dst = spans + off[c];
+	if (n <= STAGE_INLINE) {
+		for (uint32_t k = 0; k < n; ++k) dst[k] = st.inl[c * STAGE_INLINE + k];
+	} else {
+		const unsigned long long base = slot_pool_base(st.inl[c * STAGE_INLINE]);
+		for (uint32_t k = 0; k < n; ++k) dst[k] = st.pool[base + k];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Complement kernels of the erosion composite (src/vor3d/Voronoi.cpp:18-89).
+// negate: output grid (nx+2*border)^2-ish with `border` empty lines added on every side, every column
+// complemented inside [lo, hi] with negate_ray's exact '==' tests (MorphologyOperators.cpp:230-259).
+// border = 1 for the 3D erosion, 0 for the vor2d negate() (DoubleCompressedImage.cpp:438-468).
+// ---------------------------------------------------------------------------------------------------
+struct NegArgs {
+	int nx, ny, border;     // source grid, border width
+	double lo, hi;
+	const uint32_t *off;
+	const double2 *spans;
+	uint32_t *cnt;          // count kernel output
+	const uint32_t *out_off;
+	double2 *out_spans;
+};
+
+__device__ __forceinline__ bool neg_src(const NegArgs &a, unsigned long long c, uint32_t &o0, uint32_t &o1)
+{
+	const int mx = a.nx + 2 * a.border;
+	const int x = (int)(c % (unsigned)mx) - a.border;
+	const int y = (int)(c / (unsigned)mx) - a.border;
+	if (x < 0 || x >= a.nx || y < 0 || y >= a.ny) { o0 = o1 = 0; return false; }
+	const size_t s = (size_t)y * a.nx + x;
+	o0 = a.off[s];
+	o1 = a.off[s + 1];
+	return true;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_negate(NegArgs a, unsigned long long nlists)
+{
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nlists) return;
+	uint32_t o0, o1;
+	neg_src(a, c, o0, o1);
+	const uint32_t k = o1 - o0;
+	if (k == 0) {
+		if (FILL) a.out_spans[a.out_off[c]] = make_double2(a.lo, a.hi);
+		else a.cnt[c] = 1;
+		return;
+	}
+	const bool f = (a.spans[o0].x == a.lo);          // first event == lo: erased
+	const bool l = (a.spans[o1 - 1].y == a.hi);      // last event == hi: popped
+	const uint32_t n = k + 1 - (f ? 1u : 0u) - (l ? 1u : 0u);
+	if (!FILL) { a.cnt[c] = n; return; }
+	double2 *dst = a.out_spans + a.out_off[c];
+	// event sequence: [lo if !f] z1_0? ... pairs re-formed from consecutive events
+	double start = f ? a.spans[o0].y : a.lo;
+	uint32_t w = 0;
+	if (f) {
+		// events after erasing the first: y_0, x_1, y_1, ...
+		for (uint32_t i = o0 + 1; i < o1; ++i) { dst[w++] = make_double2(start, a.spans[i].x); start = a.spans[i].y; }
+	} else {
+		for (uint32_t i = o0; i < o1; ++i) { dst[w++] = make_double2(start, a.spans[i].x); start = a.spans[i].y; }
+	}
+	if (!l) dst[w++] = make_double2(start, a.hi);
+}
+
+// negateInv: strip `border` lines on every side, then negate_ray_range (MorphologyOperators.cpp:282-315):
+// leading events <= lo and trailing events >= hi are dropped; a bound is re-inserted when an even
+// number of events was dropped on that side; an empty column becomes [lo, hi].
+struct NegInvArgs {
+	int mx, my, border;     // source (bordered) grid
+	double lo, hi;
+	const uint32_t *off;
+	const double2 *spans;
+	uint32_t *cnt;
+	const uint32_t *out_off;
+	double2 *out_spans;
+};
+
+__device__ __forceinline__ double ev_at(const double2 *sp, uint32_t base, uint32_t i)
+{
+	const double2 v = sp[base + (i >> 1)];
+	return (i & 1u) ? v.y : v.x;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_negate_inv(NegInvArgs a, unsigned long long nlists)
+{
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nlists) return;
+	const int nx = a.mx - 2 * a.border;
+	const int x = (int)(c % (unsigned)nx) + a.border;
+	const int y = (int)(c / (unsigned)nx) + a.border;
+	const size_t s = (size_t)y * a.mx + x;
+	const uint32_t o0 = a.off[s], o1 = a.off[s + 1];
+	const uint32_t n = 2 * (o1 - o0);               // events
+	if (n == 0) {
+		if (FILL) a.out_spans[a.out_off[c]] = make_double2(a.lo, a.hi);
+		else a.cnt[c] = 1;
+		return;
+	}
+	uint32_t cf = 0;
+	while (cf < n && ev_at(a.spans, o0, cf) <= a.lo) ++cf;
+	const uint32_t pre = (cf % 2 == 0) ? 1u : 0u;    // lo re-inserted in front
+	uint32_t k = pre + (n - cf);                     // length of the edited list
+	uint32_t cl = 0;
+	while (k > 0) {
+		const double last = (k - 1 >= pre) ? ev_at(a.spans, o0, cf + (k - 1 - pre)) : a.lo;
+		if (last >= a.hi) { --k; ++cl; } else break;
+	}
+	const uint32_t app = (cl % 2 == 0) ? 1u : 0u;    // hi re-appended
+	const uint32_t total = k + app;                  // events of the result
+	if (!FILL) { a.cnt[c] = total / 2; return; }
+	double2 *dst = a.out_spans + a.out_off[c];
+	// event t of the result: t < min(pre,k) -> lo ; t < k -> e[cf + t - pre] ; t == k (app) -> hi
+	const uint32_t npre = (pre < k) ? pre : k;
+	for (uint32_t t = 0; t + 1 < total + 0u; t += 2) {
+		double v[2];
+		for (uint32_t q = 0; q < 2; ++q) {
+			const uint32_t tt = t + q;
+			v[q] = (tt < npre) ? a.lo : (tt < k) ? ev_at(a.spans, o0, cf + tt - pre) : a.hi;
+		}
+		dst[t >> 1] = make_double2(v[0], v[1]);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// xor of two same-grid volumes (src/vor3d/Voronoi.cpp:91-111, MorphologyOperators.cpp:334-374):
+// symmetric difference inside [zmin, zmax], slivers shorter than 1e-10 dropped. One thread per column
+// walks both sorted event lists once. cnt pass and fill pass share the walk.
+// ---------------------------------------------------------------------------------------------------
+struct XorArgs {
+	const uint32_t *off_a; const double2 *sp_a;
+	const uint32_t *off_b; const double2 *sp_b;
+	double lo, hi;
+	uint32_t *cnt;
+	const uint32_t *out_off;
+	double2 *out_spans;
+	double *col_len;        // per-column summed length (fill pass)
+};
+
+// membership of z-range pieces: the reference computes (a \ b) u (b \ a) through negate_ray / unionSegs;
+// for sorted disjoint inputs inside [lo, hi] that is the set of maximal runs where exactly one of the
+// two lists covers, with touching runs coalesced (unionSegs merges start <= end) and both inputs
+// clipped the way negate_ray clips (events equal to the bounds vanish).
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_xor(XorArgs a, unsigned long long nlists)
+{
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nlists) return;
+	const uint32_t a0 = a.off_a[c], na = 2 * (a.off_a[c + 1] - a0);
+	const uint32_t b0 = a.off_b[c], nb = 2 * (a.off_b[c + 1] - b0);
+	uint32_t ia = 0, ib = 0, w = 0;
+	bool in_a = false, in_b = false, open = false;
+	double start = 0, len = 0, cur_s = 0, cur_e = 0;
+	bool have = false;
+	double2 *dst = FILL ? a.out_spans + a.out_off[c] : nullptr;
+	while (ia < na || ib < nb) {
+		const double za = (ia < na) ? ev_at(a.sp_a, a0, ia) : 0.0;
+		const double zb = (ib < nb) ? ev_at(a.sp_b, b0, ib) : 0.0;
+		double z;
+		if (ib >= nb || (ia < na && za <= zb)) { z = za; in_a = !in_a; ++ia; if (ib < nb && zb == z) { in_b = !in_b; ++ib; } }
+		else { z = zb; in_b = !in_b; ++ib; }
+		const bool x = (in_a != in_b);
+		if (x && !open) { open = true; start = z; }
+		else if (!x && open) {
+			open = false;
+			// piece [start, z]; coalesce with the previous piece when touching
+			if (have && start <= cur_e) { if (z > cur_e) cur_e = z; }
+			else {
+				if (have && !(cur_e - cur_s < 1e-10)) { if (FILL) dst[w] = make_double2(cur_s, cur_e); len += cur_e - cur_s; ++w; }
+				cur_s = start; cur_e = z; have = true;
+			}
+		}
+	}
+	if (have && !(cur_e - cur_s < 1e-10)) { if (FILL) dst[w] = make_double2(cur_s, cur_e); len += cur_e - cur_s; ++w; }
+	if (FILL) a.col_len[c] = len; else a.cnt[c] = w;
+}
+
+// Rebase a copied slice of offsets so that it starts at zero.
+__global__ void __launch_bounds__(256) k_rebase(uint32_t *off, unsigned long long n, uint32_t base, uint32_t add)
+{
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) off[i] = off[i] - base + add;
+}
+
+// Sum of (z2 - z1) per block, accumulated in double with a fixed tree order; host adds the partials.
+__global__ void __launch_bounds__(256) k_sum(const double *__restrict__ v, unsigned long long n, double *__restrict__ partial)
+{
+	__shared__ double sh[256];
+	double s = 0;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+		s += v[i];
+	sh[threadIdx.x] = s;
+	__syncthreads();
+	for (int d = 128; d > 0; d >>= 1) {
+		if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+} // namespace vo

@@ -1,0 +1,106 @@
+// Interval algebra on the device: the running union every gather kernel folds its candidates into.
+//
+// Replaces the reference's per-line interval helpers (src/vor3d/MorphologyOperators.cpp:15-34
+// appendSegment, :117-158 unionSegs, MorphologyOperators.hpp:7-19 addSegmentAtTheEnd): a sorted list of
+// disjoint CLOSED intervals; a candidate that touches or overlaps existing intervals coalesces with
+// them ("next.start <= prev.end" merges, exactly the reference's rule). Because the union of closed
+// intervals is associative and min/max are exact, the result does not depend on the order in which
+// candidates arrive - that is what lets a data-parallel gather reproduce the sweep bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vo {
+
+// Slot encoding shared by the intermediate volume and the staging buffers:
+//   x <= y            one interval [x, y]
+//   x = +inf, y = -inf   empty
+//   x = NaN-tagged    the list lives in a pool: low 48 bits of x = first index, bits of y = count
+__device__ __forceinline__ double2 slot_empty()
+{
+	return make_double2(__longlong_as_double(0x7FF0000000000000LL), __longlong_as_double((long long)0xFFF0000000000000ULL));
+}
+__device__ __forceinline__ double2 slot_pool(unsigned long long base, unsigned int n)
+{
+	return make_double2(__longlong_as_double((long long)(0x7FF8000000000000ULL | base)), __longlong_as_double((long long)n));
+}
+__device__ __forceinline__ bool slot_is_pool(double2 s)
+{
+	return (((unsigned int)__double2hiint(s.x)) & 0xFFFF0000u) == 0x7FF80000u;
+}
+__device__ __forceinline__ unsigned long long slot_pool_base(double2 s)
+{
+	return ((unsigned long long)__double_as_longlong(s.x)) & 0x0000FFFFFFFFFFFFULL;
+}
+__device__ __forceinline__ unsigned int slot_pool_count(double2 s)
+{
+	return (unsigned int)__double_as_longlong(s.y);
+}
+
+// Sorted disjoint closed intervals. One interval lives in registers (the overwhelmingly common case for
+// smooth solids); from two on the list lives in L[] (local memory).
+template <int CAP>
+struct RunUnion {
+	double s0, e0;
+	int n;
+	bool overflow;
+	double2 L[CAP];
+
+	__device__ __forceinline__ void init() { n = 0; overflow = false; s0 = 0; e0 = 0; }
+
+	__device__ __forceinline__ double2 get(int k) const { return n == 1 ? make_double2(s0, e0) : L[k]; }
+
+	__device__ __forceinline__ void insert(double s, double e)
+	{
+		if (n == 1) {
+			if (s <= e0 && e >= s0) {         // touches or overlaps: coalesce in registers
+				s0 = fmin(s0, s);
+				e0 = fmax(e0, e);
+				return;
+			}
+			insert_second(s, e);
+			return;
+		}
+		if (n == 0) { s0 = s; e0 = e; n = 1; return; }
+		insert_list(s, e);
+	}
+
+	__device__ __noinline__ void insert_second(double s, double e)
+	{
+		if (CAP < 2) { overflow = true; return; }
+		if (e < s0) { L[0] = make_double2(s, e); L[1] = make_double2(s0, e0); }
+		else        { L[0] = make_double2(s0, e0); L[1] = make_double2(s, e); }
+		n = 2;
+	}
+
+	__device__ __noinline__ void insert_list(double s, double e)
+	{
+		if (overflow) return;
+		int i = 0;
+		while (i < n && L[i].y < s) ++i;          // intervals entirely below the candidate
+		if (i == n) {                              // append
+			if (n == CAP) { overflow = true; return; }
+			L[n++] = make_double2(s, e);
+			return;
+		}
+		if (L[i].x > e) {                          // falls into a gap: open a new interval at i
+			if (n == CAP) { overflow = true; return; }
+			for (int k = n; k > i; --k) L[k] = L[k - 1];
+			L[i] = make_double2(s, e);
+			++n;
+			return;
+		}
+		double ns = fmin(s, L[i].x), ne = fmax(e, L[i].y);
+		int j = i + 1;
+		while (j < n && L[j].x <= e) { ne = fmax(ne, L[j].y); ++j; }
+		L[i] = make_double2(ns, ne);
+		const int drop = j - i - 1;
+		if (drop > 0) {
+			for (int k = j; k < n; ++k) L[k - drop] = L[k];
+			n -= drop;
+			if (n == 1) { s0 = L[0].x; e0 = L[0].y; }
+		}
+	}
+};
+
+} // namespace vo

@@ -1,0 +1,1039 @@
+// libvoroffset_b200.so - host side of the C ABI declared in include/voroffset_b200.h.
+// CUDA runtime only (no torch, no CPU fallback). Kernels are in kernels.cuh / scan.cuh.
+#include "voroffset_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.cuh"
+#include "scan.cuh"
+
+using namespace vo;
+
+// ---------------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------------
+struct vo_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+	std::string err;
+	uint64_t launches = 0;
+	// small persistent device scratch: [0] mid-pool cursor, [1] stage-pool cursor, [2] redo count
+	unsigned long long *d_ctr = nullptr;
+};
+
+struct vo_dvol {
+	int nx = 0, ny = 0;
+	uint64_t nspans = 0;
+	uint32_t *off = nullptr;
+	double2 *spans = nullptr;
+};
+
+struct vo_dmid {
+	int nx = 0, ny = 0, J = 0;
+	double R = 0;
+	double2 *slots = nullptr;
+	double2 *pool = nullptr;
+	uint64_t pool_cap = 0, pool_used = 0;
+};
+
+namespace {
+
+int fail(vo_ctx *ctx, int code, const std::string &msg)
+{
+	if (ctx) ctx->err = msg;
+	return code;
+}
+
+#define VO_CUDA(call)                                                                                   \
+	do {                                                                                                \
+		cudaError_t e_ = (call);                                                                        \
+		if (e_ != cudaSuccess) {                                                                        \
+			cudaGetLastError();                                                                         \
+			return fail(ctx, e_ == cudaErrorMemoryAllocation ? VO_ERR_NOMEM : VO_ERR_CUDA,              \
+			            std::string(#call) + ": " + cudaGetErrorString(e_));                            \
+		}                                                                                               \
+	} while (0)
+
+#define VO_TRY(expr)                                                                                    \
+	do {                                                                                                \
+		int rc_ = (expr);                                                                               \
+		if (rc_ != VO_OK) return rc_;                                                                   \
+	} while (0)
+
+inline unsigned int blocks_for(unsigned long long n, int threads)
+{
+	unsigned long long b = (n + threads - 1) / threads;
+	return (unsigned int)(b ? b : 1);
+}
+
+template <typename T> int dalloc(vo_ctx *ctx, T **p, unsigned long long count)
+{
+	*p = nullptr;
+	size_t bytes = (size_t)std::max<unsigned long long>(count, 1ull) * sizeof(T);
+	VO_CUDA(cudaMallocAsync((void **)p, bytes, ctx->stream));
+	return VO_OK;
+}
+
+template <typename T> void dfree(vo_ctx *ctx, T *p)
+{
+	if (p) cudaFreeAsync((void *)p, ctx->stream);
+}
+
+// RAII for temporaries allocated on the context stream
+template <typename T> struct Tmp {
+	vo_ctx *ctx;
+	T *p = nullptr;
+	explicit Tmp(vo_ctx *c) : ctx(c) {}
+	~Tmp() { dfree(ctx, p); }
+	Tmp(const Tmp &) = delete;
+	Tmp &operator=(const Tmp &) = delete;
+};
+
+// ---- pinned host blocks handed to the caller, recycled through vo_free -------------------------------
+std::mutex g_host_mu;
+std::unordered_map<void *, size_t> g_host_live;            // ptr -> capacity
+std::vector<std::pair<void *, size_t>> g_host_cache;       // released blocks kept for reuse
+
+void *host_block(size_t bytes)
+{
+	bytes = std::max<size_t>(bytes, 64);
+	{
+		std::lock_guard<std::mutex> lk(g_host_mu);
+		int best = -1;
+		for (int i = 0; i < (int)g_host_cache.size(); ++i)
+			if (g_host_cache[i].second >= bytes && g_host_cache[i].second <= 2 * bytes + (1u << 20) &&
+			    (best < 0 || g_host_cache[i].second < g_host_cache[best].second))
+				best = i;
+		if (best >= 0) {
+			auto blk = g_host_cache[best];
+			g_host_cache.erase(g_host_cache.begin() + best);
+			g_host_live[blk.first] = blk.second;
+			return blk.first;
+		}
+	}
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	std::lock_guard<std::mutex> lk(g_host_mu);
+	g_host_live[p] = bytes;
+	return p;
+}
+
+// ---- cap tables (the reference's exact fp64 operation order, computed once on the host) --------------
+struct Tables {
+	int J = 0;
+	std::vector<double> H;     // 'ours'  [j = |dy|][|dx|]
+	std::vector<int> reach;    // 'ours'  floor(r1(j))
+	std::vector<double> HB;    // 'brute_force' [|dy|][|dx|]
+};
+
+// 'ours': r1 = R (dy == 0) or sqrt(R*R - dy*dy) (Voronoi2D.cpp:704-716); a piece lives while
+// |dx| <= floor(r1) (SeparatePower2D.cpp:241,266); h = sqrt(r1*r1 - dx*dx) (SeparatePower2D.cpp:314).
+// 'brute_force': dx^2 + dy^2 <= R*R, dz = sqrt(R*R - dx^2 - dy^2) (VoronoiBruteForce.cpp:48-50).
+Tables make_tables(double R)
+{
+	Tables t;
+	t.J = (int)std::floor(R);
+	const int n = t.J + 1;
+	t.H.assign((size_t)n * n, -1.0);
+	t.HB.assign((size_t)n * n, -1.0);
+	t.reach.assign(n, 0);
+	for (int dy = 0; dy < n; ++dy) {
+		const double dyd = (double)dy;
+		volatile double r1 = (dy == 0) ? R : std::sqrt(R * R - dyd * dyd);
+		const int reach = (int)std::floor(r1);
+		t.reach[dy] = std::min(reach, t.J);
+		for (int dx = 0; dx < n; ++dx) {
+			const double dxd = (double)dx;
+			if (dx <= reach) {
+				volatile double a = r1 * r1;
+				volatile double b = dxd * dxd;
+				volatile double d = a - b;
+				t.H[(size_t)dy * n + dx] = std::sqrt(d);
+			}
+			volatile double p2 = std::pow(dxd, 2.0) + std::pow(dyd, 2.0);
+			volatile double rr = R * R;
+			if (p2 <= rr) {
+				volatile double q = rr - std::pow(dxd, 2.0);
+				volatile double q2 = q - std::pow(dyd, 2.0);
+				t.HB[(size_t)dy * n + dx] = std::sqrt(q2);
+			}
+		}
+	}
+	return t;
+}
+
+int check_dims(vo_ctx *ctx, int nx, int ny)
+{
+	if (nx < 0 || ny < 0) return fail(ctx, VO_ERR_ARG, "negative grid size");
+	if ((unsigned long long)nx * (unsigned long long)ny >= (1ull << 32) - 8) return fail(ctx, VO_ERR_OVERFLOW, "grid too large for uint32 CSR offsets");
+	return VO_OK;
+}
+
+// counts -> offsets; returns the grand total (checked against the uint32 range)
+int scan_counts(vo_ctx *ctx, const uint32_t *cnt, unsigned long long n, uint32_t *off, unsigned long long *total)
+{
+	if (n == 0) {
+		VO_CUDA(cudaMemsetAsync(off, 0, sizeof(uint32_t), ctx->stream));
+		*total = 0;
+		return VO_OK;
+	}
+	const unsigned int ntiles = blocks_for(n, SCAN_TILE);
+	Tmp<unsigned long long> sums(ctx);
+	VO_TRY(dalloc(ctx, &sums.p, (unsigned long long)ntiles + 1));
+	k_scan_reduce<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(cnt, n, sums.p);
+	k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(sums.p, ntiles);
+	k_scan_apply<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(cnt, n, sums.p, off);
+	ctx->launches += 3;
+	VO_CUDA(cudaGetLastError());
+	unsigned long long tot = 0;
+	VO_CUDA(cudaMemcpyAsync(&tot, sums.p + ntiles, sizeof(tot), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (tot >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
+	*total = tot;
+	return VO_OK;
+}
+
+int new_dvol(vo_ctx *ctx, int nx, int ny, vo_dvol **out)
+{
+	vo_dvol *v = new (std::nothrow) vo_dvol();
+	if (!v) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
+	v->nx = nx;
+	v->ny = ny;
+	int rc = dalloc(ctx, &v->off, (unsigned long long)nx * ny + 1);
+	if (rc) { delete v; return rc; }
+	*out = v;
+	return VO_OK;
+}
+
+void free_dvol(vo_ctx *ctx, vo_dvol *v)
+{
+	if (!v) return;
+	dfree(ctx, v->off);
+	dfree(ctx, v->spans);
+	delete v;
+}
+
+// Staged lists of `nlists` lists -> new device CSR volume of shape (nx, ny).
+struct StageBuf {
+	vo_ctx *ctx;
+	Stage st{};
+	explicit StageBuf(vo_ctx *c) : ctx(c) {}
+	~StageBuf() { dfree(ctx, st.cnt); dfree(ctx, st.inl); dfree(ctx, st.pool); }
+	int alloc(unsigned long long nlists, unsigned long long pool_cap)
+	{
+		VO_TRY(dalloc(ctx, &st.cnt, nlists));
+		VO_TRY(dalloc(ctx, &st.inl, nlists * STAGE_INLINE));
+		VO_TRY(dalloc(ctx, &st.pool, pool_cap));
+		st.pool_cap = pool_cap;
+		st.cursor = ctx->d_ctr + 1;
+		return VO_OK;
+	}
+	int regrow(unsigned long long pool_cap)
+	{
+		dfree(ctx, st.pool);
+		st.pool = nullptr;
+		VO_TRY(dalloc(ctx, &st.pool, pool_cap));
+		st.pool_cap = pool_cap;
+		return VO_OK;
+	}
+};
+
+struct RedoBuf {
+	vo_ctx *ctx;
+	Redo rd{};
+	explicit RedoBuf(vo_ctx *c) : ctx(c) {}
+	~RedoBuf() { dfree(ctx, rd.list); }
+	int alloc(unsigned int cap)
+	{
+		VO_TRY(dalloc(ctx, &rd.list, cap));
+		rd.cap = cap;
+		rd.count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 2);
+		return VO_OK;
+	}
+};
+
+int read_counters(vo_ctx *ctx, unsigned long long h[3])
+{
+	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	return VO_OK;
+}
+
+int finish_stage(vo_ctx *ctx, const Stage &st, int nx, int ny, vo_dvol **out)
+{
+	const unsigned long long nlists = (unsigned long long)nx * ny;
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &v));
+	unsigned long long total = 0;
+	int rc = scan_counts(ctx, st.cnt, nlists, v->off, &total);
+	if (rc == VO_OK) rc = dalloc(ctx, &v->spans, total);
+	if (rc != VO_OK) { free_dvol(ctx, v); return rc; }
+	v->nspans = total;
+	if (nlists) {
+		k_compact<<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(st, nlists, v->off, v->spans);
+		ctx->launches++;
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) { free_dvol(ctx, v); return fail(ctx, VO_ERR_CUDA, std::string("k_compact: ") + cudaGetErrorString(e)); }
+	}
+	*out = v;
+	return VO_OK;
+}
+
+// Generic driver for the staged gather kernels: first launch with CAP_FAST over all lists, then the
+// redo launch with CAP_BIG over the lists whose running union outgrew CAP_FAST; the staging pool is
+// regrown and the launch repeated if it was too small (the cursor keeps counting past the capacity).
+template <typename Args, typename LaunchFast, typename LaunchBig>
+int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long long pool_guess,
+               LaunchFast launch_fast, LaunchBig launch_big, int nx, int ny, vo_dvol **out)
+{
+	StageBuf sb(ctx);
+	RedoBuf rb(ctx);
+	VO_TRY(sb.alloc(nlists, pool_guess));
+	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nlists, 1ull), 1ull << 22);
+	VO_TRY(rb.alloc(redo_cap));
+	for (int attempt = 0; attempt < 3; ++attempt) {
+		VO_CUDA(cudaMemsetAsync(ctx->d_ctr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+		args.st = sb.st;
+		args.redo = rb.rd;
+		args.work = nullptr;
+		args.nwork = nlists;
+		if (nlists) { launch_fast(args); ctx->launches++; }
+		VO_CUDA(cudaGetLastError());
+		unsigned long long h[3];
+		VO_TRY(read_counters(ctx, h));
+		const unsigned int nredo = (unsigned int)h[2];
+		if (nredo > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
+		if (nredo) {
+			args.work = rb.rd.list;
+			args.nwork = nredo;
+			VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 2, 0, sizeof(unsigned long long), ctx->stream));
+			launch_big(args);
+			ctx->launches++;
+			VO_CUDA(cudaGetLastError());
+			VO_TRY(read_counters(ctx, h));
+			if (h[2]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
+		}
+		if (h[1] <= sb.st.pool_cap) return finish_stage(ctx, sb.st, nx, ny, out);
+		VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024));
+	}
+	return fail(ctx, VO_ERR_OVERFLOW, "staging pool did not converge");
+}
+
+struct DevTables {
+	vo_ctx *ctx;
+	double *H = nullptr, *HB = nullptr;
+	int *reach = nullptr;
+	int J = 0;
+	explicit DevTables(vo_ctx *c) : ctx(c) {}
+	~DevTables() { dfree(ctx, H); dfree(ctx, HB); dfree(ctx, reach); }
+	int upload(const Tables &t)
+	{
+		J = t.J;
+		const size_t n = (size_t)(J + 1) * (J + 1);
+		VO_TRY(dalloc(ctx, &H, n));
+		VO_TRY(dalloc(ctx, &HB, n));
+		VO_TRY(dalloc(ctx, &reach, (unsigned long long)J + 1));
+		VO_CUDA(cudaMemcpyAsync(H, t.H.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(HB, t.HB.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(reach, t.reach.data(), (size_t)(J + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors may go out of scope
+		return VO_OK;
+	}
+};
+
+int check_radius(vo_ctx *ctx, double R)
+{
+	if (!(R >= 0.0) || !(R < 4096.0)) return fail(ctx, VO_ERR_ARG, "radius must be in [0, 4096) dexels");
+	return VO_OK;
+}
+
+// ---- 'ours' pass 1 ------------------------------------------------------------------------------------
+int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
+{
+	VO_TRY(check_radius(ctx, R));
+	Tables t = make_tables(R);
+	DevTables dt(ctx);
+	VO_TRY(dt.upload(t));
+	vo_dmid *m = new (std::nothrow) vo_dmid();
+	if (!m) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
+	m->nx = in->nx; m->ny = in->ny; m->J = t.J; m->R = R;
+	const unsigned long long nslots = (unsigned long long)in->nx * in->ny * (t.J + 1);
+	int rc = dalloc(ctx, &m->slots, nslots);
+	unsigned long long pool_cap = 65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4);
+	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
+	RedoBuf rb(ctx);
+	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nslots, 1ull), 1ull << 22);
+	if (rc == VO_OK) rc = rb.alloc(redo_cap);
+	if (rc != VO_OK) { vo_dmid_free(ctx, m); return rc; }
+	m->pool_cap = pool_cap;
+	auto bail = [&](int code) { vo_dmid_free(ctx, m); return code; };
+	for (int attempt = 0; attempt < 3; ++attempt) {
+		cudaError_t e = cudaMemsetAsync(ctx->d_ctr, 0, 3 * sizeof(unsigned long long), ctx->stream);
+		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, cudaGetErrorString(e)));
+		Pass1Args a;
+		a.nx = in->nx; a.ny = in->ny; a.J = t.J;
+		a.off = in->off; a.spans = in->spans; a.H = dt.H; a.reach = dt.reach;
+		a.mid = m->slots; a.pool = m->pool; a.cursor = ctx->d_ctr; a.pool_cap = m->pool_cap;
+		a.redo = rb.rd; a.work = nullptr; a.nwork = nslots;
+		if (nslots) { k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a); ctx->launches++; }
+		e = cudaGetLastError();
+		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1: ") + cudaGetErrorString(e)));
+		unsigned long long h[3];
+		rc = read_counters(ctx, h);
+		if (rc) return bail(rc);
+		const unsigned int nredo = (unsigned int)h[2];
+		if (nredo > redo_cap) return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
+		if (nredo) {
+			a.work = rb.rd.list; a.nwork = nredo;
+			cudaMemsetAsync(ctx->d_ctr + 2, 0, sizeof(unsigned long long), ctx->stream);
+			k_pass1<CAP_BIG><<<blocks_for(nredo, 128), 128, 0, ctx->stream>>>(a);
+			ctx->launches++;
+			e = cudaGetLastError();
+			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1 redo: ") + cudaGetErrorString(e)));
+			rc = read_counters(ctx, h);
+			if (rc) return bail(rc);
+			if (h[2]) return bail(fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union"));
+		}
+		if (h[0] <= m->pool_cap) { m->pool_used = h[0]; *out = m; return VO_OK; }
+		dfree(ctx, m->pool);
+		m->pool = nullptr;
+		m->pool_cap = h[0] + h[0] / 8 + 1024;
+		rc = dalloc(ctx, &m->pool, m->pool_cap);
+		if (rc) return bail(rc);
+	}
+	return bail(fail(ctx, VO_ERR_OVERFLOW, "mid pool did not converge"));
+}
+
+int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
+{
+	if (y0 < 0 || y1 > m->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "pass 2 row range outside the mid volume");
+	Pass2Args a;
+	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = y0; a.y1 = y1;
+	a.mid = m->slots; a.pool = m->pool;
+	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
+	cudaStream_t s = ctx->stream;
+	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
+		[&](Pass2Args &g) { k_pass2<CAP_FAST><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
+		[&](Pass2Args &g) { k_pass2<CAP_BIG><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
+		m->nx, y1 - y0, out);
+}
+
+int brute(vo_ctx *ctx, const vo_dvol *in, double R, vo_dvol **out)
+{
+	VO_TRY(check_radius(ctx, R));
+	Tables t = make_tables(R);
+	DevTables dt(ctx);
+	VO_TRY(dt.upload(t));
+	BruteArgs a;
+	a.nx = in->nx; a.ny = in->ny; a.J = t.J;
+	a.off = in->off; a.spans = in->spans; a.HB = dt.HB;
+	const unsigned long long nlists = (unsigned long long)in->nx * in->ny;
+	cudaStream_t s = ctx->stream;
+	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
+		[&](BruteArgs &g) { k_brute<CAP_FAST><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
+		[&](BruteArgs &g) { k_brute<CAP_BIG><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
+		in->nx, in->ny, out);
+}
+
+struct PassTimes { double ms1 = 0, ms2 = 0; };
+
+// dilation of a resident volume; fills the per-pass device times
+int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, PassTimes *pt)
+{
+	float t1 = 0, t2 = 0;
+	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	if (method == VO_METHOD_OURS) {
+		vo_dmid *mid = nullptr;
+		VO_TRY(pass1(ctx, in, R, &mid));
+		cudaEventRecord(ctx->ev[1], ctx->stream);
+		int rc = pass2(ctx, mid, 0, mid->ny, out);
+		vo_dmid_free(ctx, mid);
+		VO_TRY(rc);
+		VO_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+		VO_CUDA(cudaEventSynchronize(ctx->ev[2]));
+		cudaEventElapsedTime(&t1, ctx->ev[0], ctx->ev[1]);
+		cudaEventElapsedTime(&t2, ctx->ev[1], ctx->ev[2]);
+	} else if (method == VO_METHOD_BRUTE_FORCE) {
+		VO_TRY(brute(ctx, in, R, out));
+		VO_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+		VO_CUDA(cudaEventSynchronize(ctx->ev[2]));
+		cudaEventElapsedTime(&t1, ctx->ev[0], ctx->ev[2]);
+	} else {
+		return fail(ctx, VO_ERR_ARG, "Invalid method");
+	}
+	if (pt) { pt->ms1 = t1; pt->ms2 = t2; }
+	return VO_OK;
+}
+
+// negate (Voronoi.cpp:18-55) / negateInv (Voronoi.cpp:57-89) / vor2d negate, all count -> scan -> fill
+int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out)
+{
+	const int mx = in->nx + 2 * border, my = in->ny + 2 * border;
+	VO_TRY(check_dims(ctx, mx, my));
+	const unsigned long long nlists = (unsigned long long)mx * my;
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, mx, my, &v));
+	Tmp<uint32_t> cnt(ctx);
+	int rc = dalloc(ctx, &cnt.p, nlists);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	NegArgs a;
+	a.nx = in->nx; a.ny = in->ny; a.border = border; a.lo = lo; a.hi = hi;
+	a.off = in->off; a.spans = in->spans; a.cnt = cnt.p; a.out_off = nullptr; a.out_spans = nullptr;
+	if (nlists) { k_negate<false><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
+	unsigned long long total = 0;
+	rc = scan_counts(ctx, cnt.p, nlists, v->off, &total);
+	if (rc == VO_OK) rc = dalloc(ctx, &v->spans, total);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	v->nspans = total;
+	a.out_off = v->off; a.out_spans = v->spans;
+	if (nlists) { k_negate<true><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { free_dvol(ctx, v); return fail(ctx, VO_ERR_CUDA, std::string("k_negate: ") + cudaGetErrorString(e)); }
+	*out = v;
+	return VO_OK;
+}
+
+int negate_inv(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out)
+{
+	const int nx = in->nx - 2 * border, ny = in->ny - 2 * border;
+	if (nx < 0 || ny < 0) return fail(ctx, VO_ERR_ARG, "negateInv on a grid smaller than its border");
+	const unsigned long long nlists = (unsigned long long)nx * ny;
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &v));
+	Tmp<uint32_t> cnt(ctx);
+	int rc = dalloc(ctx, &cnt.p, nlists);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	NegInvArgs a;
+	a.mx = in->nx; a.my = in->ny; a.border = border; a.lo = lo; a.hi = hi;
+	a.off = in->off; a.spans = in->spans; a.cnt = cnt.p; a.out_off = nullptr; a.out_spans = nullptr;
+	if (nlists) { k_negate_inv<false><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
+	unsigned long long total = 0;
+	rc = scan_counts(ctx, cnt.p, nlists, v->off, &total);
+	if (rc == VO_OK) rc = dalloc(ctx, &v->spans, total);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	v->nspans = total;
+	a.out_off = v->off; a.out_spans = v->spans;
+	if (nlists) { k_negate_inv<true><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { free_dvol(ctx, v); return fail(ctx, VO_ERR_CUDA, std::string("k_negate_inv: ") + cudaGetErrorString(e)); }
+	*out = v;
+	return VO_OK;
+}
+
+// erosion = negate, dilation, negateInv (Voronoi.cpp:8-17)
+int erode(vo_ctx *ctx, int method, const vo_dvol *in, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt)
+{
+	const double z_min = zmin - 1, z_max = zmax + 1;
+	vo_dvol *neg = nullptr, *dil = nullptr;
+	VO_TRY(negate(ctx, in, 1, z_min, z_max, &neg));
+	int rc = dilate(ctx, method, neg, R, &dil, pt);
+	free_dvol(ctx, neg);
+	VO_TRY(rc);
+	rc = negate_inv(ctx, dil, 1, z_min + 1, z_max - 1, out);
+	free_dvol(ctx, dil);
+	return rc;
+}
+
+int morph3d_dev(vo_ctx *ctx, int op, int method, const vo_dvol *in, double zmin, double zmax, double R,
+                vo_dvol **out, PassTimes *pt)
+{
+	if (method != VO_METHOD_OURS && method != VO_METHOD_BRUTE_FORCE) return fail(ctx, VO_ERR_ARG, "Invalid method");
+	switch (op) {
+	case VO_OP_DILATION: return dilate(ctx, method, in, R, out, pt);
+	case VO_OP_EROSION: return erode(ctx, method, in, zmin, zmax, R, out, pt);
+	case VO_OP_OPENING: {   // offset3d.cpp:129-133
+		vo_dvol *tmp = nullptr;
+		VO_TRY(erode(ctx, method, in, zmin, zmax, R, &tmp, pt));
+		int rc = dilate(ctx, method, tmp, R, out, pt);
+		free_dvol(ctx, tmp);
+		return rc;
+	}
+	case VO_OP_CLOSING: {   // offset3d.cpp:124-128
+		vo_dvol *tmp = nullptr;
+		VO_TRY(dilate(ctx, method, in, R, &tmp, pt));
+		int rc = erode(ctx, method, tmp, zmin, zmax, R, out, pt);
+		free_dvol(ctx, tmp);
+		return rc;
+	}
+	default: return fail(ctx, VO_ERR_ARG, "Operation");
+	}
+}
+
+// vor2d: rows live in a vo_dvol with nx = rows, ny = 1
+int dilate2d(vo_ctx *ctx, const vo_dvol *in, int width, double R, int complement, vo_dvol **out)
+{
+	VO_TRY(check_radius(ctx, R));
+	const int J = (int)std::floor(R);
+	std::vector<double> h2((size_t)J + 1);
+	for (int di = 0; di <= J; ++di) {
+		const double d = (double)di;
+		volatile double a = R * R;
+		volatile double b = d * d;
+		volatile double c = a - b;
+		h2[di] = std::sqrt(c);     // DoubleVoronoi.cpp:718
+	}
+	Tmp<double> dh(ctx);
+	VO_TRY(dalloc(ctx, &dh.p, (unsigned long long)J + 1));
+	VO_CUDA(cudaMemcpyAsync(dh.p, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	Dil2dArgs a;
+	a.rows = in->nx; a.J = J; a.complement = complement; a.W = (double)width;
+	a.off = in->off; a.spans = in->spans; a.h2 = dh.p;
+	const unsigned long long nlists = (unsigned long long)in->nx;
+	cudaStream_t s = ctx->stream;
+	return run_staged(ctx, a, nlists, 65536ull + 4 * in->nspans,
+		[&](Dil2dArgs &g) { k_dilate2d<CAP_FAST><<<blocks_for(g.nwork, 64), 64, 0, s>>>(g); },
+		[&](Dil2dArgs &g) { k_dilate2d<CAP_BIG><<<blocks_for(g.nwork, 64), 64, 0, s>>>(g); },
+		in->nx, 1, out);
+}
+
+int morph2d_dev(vo_ctx *ctx, int op, const vo_dvol *in, int width, double r, vo_dvol **out)
+{
+	if (in->ny != 1 && in->nx != 0) return fail(ctx, VO_ERR_ARG, "2D rows must be passed as an nx = rows, ny = 1 volume");
+	switch (op) {
+	case VO_OP2D_DILATE:   // DoubleCompressedImage.cpp:680-689: R = r * rows
+		return dilate2d(ctx, in, width, r * (double)(size_t)in->nx, 0, out);
+	case VO_OP2D_ERODE: {  // DoubleCompressedImage.cpp:693-703: R = r, then negate()
+		vo_dvol *tmp = nullptr;
+		VO_TRY(dilate2d(ctx, in, width, r, 1, &tmp));
+		int rc = negate(ctx, tmp, 0, 0.0, (double)width, out);
+		free_dvol(ctx, tmp);
+		return rc;
+	}
+	case VO_OP2D_NEGATE: return negate(ctx, in, 0, 0.0, (double)width, out);
+	case VO_OP2D_OPEN: {   // erode then dilate (DoubleCompressedImage.cpp:715-719)
+		vo_dvol *tmp = nullptr;
+		VO_TRY(morph2d_dev(ctx, VO_OP2D_ERODE, in, width, r, &tmp));
+		int rc = morph2d_dev(ctx, VO_OP2D_DILATE, tmp, width, r, out);
+		free_dvol(ctx, tmp);
+		return rc;
+	}
+	case VO_OP2D_CLOSE: {  // dilate then erode (DoubleCompressedImage.cpp:707-711)
+		vo_dvol *tmp = nullptr;
+		VO_TRY(morph2d_dev(ctx, VO_OP2D_DILATE, in, width, r, &tmp));
+		int rc = morph2d_dev(ctx, VO_OP2D_ERODE, tmp, width, r, out);
+		free_dvol(ctx, tmp);
+		return rc;
+	}
+	default: return fail(ctx, VO_ERR_ARG, "Operation");
+	}
+}
+
+int xor_dev(vo_ctx *ctx, const vo_dvol *A, const vo_dvol *B, double zmin, double zmax, double spacing,
+            vo_dvol **out, double *volume)
+{
+	if (A->nx != B->nx || A->ny != B->ny) return fail(ctx, VO_ERR_ARG, "xor needs two volumes on the same grid");
+	const unsigned long long nlists = (unsigned long long)A->nx * A->ny;
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, A->nx, A->ny, &v));
+	Tmp<uint32_t> cnt(ctx);
+	Tmp<double> len(ctx), part(ctx);
+	int rc = dalloc(ctx, &cnt.p, nlists);
+	if (rc == VO_OK) rc = dalloc(ctx, &len.p, nlists);
+	const unsigned int nb = 256;
+	if (rc == VO_OK) rc = dalloc(ctx, &part.p, nb);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	XorArgs a;
+	a.off_a = A->off; a.sp_a = A->spans; a.off_b = B->off; a.sp_b = B->spans; a.lo = zmin; a.hi = zmax;
+	a.cnt = cnt.p; a.out_off = nullptr; a.out_spans = nullptr; a.col_len = len.p;
+	if (nlists) { k_xor<false><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
+	unsigned long long total = 0;
+	rc = scan_counts(ctx, cnt.p, nlists, v->off, &total);
+	if (rc == VO_OK) rc = dalloc(ctx, &v->spans, total);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	v->nspans = total;
+	a.out_off = v->off; a.out_spans = v->spans;
+	double vol = 0;
+	if (nlists) {
+		k_xor<true><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists);
+		k_sum<<<nb, 256, 0, ctx->stream>>>(len.p, nlists, part.p);
+		ctx->launches += 2;
+		std::vector<double> hp(nb);
+		cudaError_t e = cudaMemcpyAsync(hp.data(), part.p, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+		if (e != cudaSuccess) { free_dvol(ctx, v); return fail(ctx, VO_ERR_CUDA, std::string("k_xor: ") + cudaGetErrorString(e)); }
+		for (double p : hp) vol += p;
+	}
+	if (volume) *volume = spacing * spacing * spacing * vol;
+	*out = v;
+	return VO_OK;
+}
+
+int upload(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans, vo_dvol **out)
+{
+	VO_TRY(check_dims(ctx, nx, ny));
+	const unsigned long long n = (unsigned long long)nx * ny;
+	if (!off) return fail(ctx, VO_ERR_ARG, "off is NULL");
+	if (off[0] != 0) return fail(ctx, VO_ERR_ARG, "off[0] must be 0");
+	const uint64_t m = off[n];
+	if (m && !spans) return fail(ctx, VO_ERR_ARG, "spans is NULL");
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &v));
+	int rc = dalloc(ctx, &v->spans, m);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	v->nspans = m;
+	cudaError_t e = cudaMemcpyAsync(v->off, off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess && m) e = cudaMemcpyAsync(v->spans, spans, m * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream);
+	if (e != cudaSuccess) { free_dvol(ctx, v); cudaGetLastError(); return fail(ctx, VO_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e)); }
+	*out = v;
+	return VO_OK;
+}
+
+int download_new(vo_ctx *ctx, const vo_dvol *v, uint32_t **out_off, double **out_spans, uint64_t *out_nspans)
+{
+	const unsigned long long n = (unsigned long long)v->nx * v->ny;
+	uint32_t *ho = (uint32_t *)host_block((n + 1) * sizeof(uint32_t));
+	double *hs = (double *)host_block(std::max<uint64_t>(v->nspans, 1) * sizeof(double2));
+	if (!ho || !hs) { vo_free(ho); vo_free(hs); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
+	cudaError_t e = cudaMemcpyAsync(ho, v->off, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess && v->nspans) e = cudaMemcpyAsync(hs, v->spans, v->nspans * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e != cudaSuccess) { vo_free(ho); vo_free(hs); cudaGetLastError(); return fail(ctx, VO_ERR_CUDA, std::string("download: ") + cudaGetErrorString(e)); }
+	*out_off = ho; *out_spans = hs;
+	if (out_nspans) *out_nspans = v->nspans;
+	return VO_OK;
+}
+
+struct DeviceGuard {
+	int prev = -1;
+	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *vo_version(void) { return "voroffset_b200 0.1 (sm_100a)"; }
+int vo_span_bytes(void) { return (int)sizeof(double2); }
+
+int vo_create(int device, vo_ctx **out)
+{
+	if (!out) return VO_ERR_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return VO_ERR_CUDA; }
+	if (device < 0 || device >= ndev) return VO_ERR_ARG;
+	vo_ctx *ctx = new (std::nothrow) vo_ctx();
+	if (!ctx) return VO_ERR_NOMEM;
+	ctx->device = device;
+	bool ok = cudaSetDevice(device) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+	for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&ctx->d_ctr, 4 * sizeof(unsigned long long)) == cudaSuccess;
+	if (ok) {
+		// keep freed blocks in the stream-ordered pool: steady-state calls then allocate without the driver
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			uint64_t thr = UINT64_MAX;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+		}
+	}
+	if (!ok) { cudaGetLastError(); vo_destroy(ctx); return VO_ERR_CUDA; }
+	*out = ctx;
+	return VO_OK;
+}
+
+void vo_destroy(vo_ctx *ctx)
+{
+	if (!ctx) return;
+	DeviceGuard g(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+	for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+const char *vo_last_error(const vo_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+void *vo_stream(const vo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t vo_launch_count(const vo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void vo_free(void *p)
+{
+	if (!p) return;
+	std::lock_guard<std::mutex> lk(g_host_mu);
+	auto it = g_host_live.find(p);
+	if (it == g_host_live.end()) return;
+	std::pair<void *, size_t> blk(it->first, it->second);
+	g_host_live.erase(it);
+	if (g_host_cache.size() < 8) g_host_cache.push_back(blk);
+	else cudaFreeHost(blk.first);
+}
+
+int vo_dvol_upload(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans, vo_dvol **out)
+{
+	if (!ctx || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	VO_TRY(upload(ctx, nx, ny, off, spans, out));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	return VO_OK;
+}
+
+int vo_dvol_download(vo_ctx *ctx, const vo_dvol *v, uint32_t *off, double *spans)
+{
+	if (!ctx || !v || !off) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	const unsigned long long n = (unsigned long long)v->nx * v->ny;
+	VO_CUDA(cudaMemcpyAsync(off, v->off, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	if (v->nspans) {
+		if (!spans) return fail(ctx, VO_ERR_ARG, "spans is NULL");
+		VO_CUDA(cudaMemcpyAsync(spans, v->spans, v->nspans * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	return VO_OK;
+}
+
+int vo_dvol_info(const vo_dvol *v, int *nx, int *ny, uint64_t *nspans, const void **d_off, const void **d_spans)
+{
+	if (!v) return VO_ERR_ARG;
+	if (nx) *nx = v->nx;
+	if (ny) *ny = v->ny;
+	if (nspans) *nspans = v->nspans;
+	if (d_off) *d_off = v->off;
+	if (d_spans) *d_spans = v->spans;
+	return VO_OK;
+}
+
+void vo_dvol_free(vo_ctx *ctx, vo_dvol *v)
+{
+	if (!ctx || !v) return;
+	DeviceGuard g(ctx->device);
+	free_dvol(ctx, v);
+}
+
+int vo_dvol_rows(vo_ctx *ctx, const vo_dvol *v, int y0, int y1, vo_dvol **out)
+{
+	if (!ctx || !v || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	if (y0 < 0 || y1 > v->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "row range outside the volume");
+	const unsigned long long c0 = (unsigned long long)y0 * v->nx, c1 = (unsigned long long)y1 * v->nx;
+	uint32_t ends[2] = {0, 0};
+	VO_CUDA(cudaMemcpyAsync(&ends[0], v->off + c0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaMemcpyAsync(&ends[1], v->off + c1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	vo_dvol *r = nullptr;
+	VO_TRY(new_dvol(ctx, v->nx, y1 - y0, &r));
+	r->nspans = ends[1] - ends[0];
+	int rc = dalloc(ctx, &r->spans, r->nspans);
+	if (rc) { free_dvol(ctx, r); return rc; }
+	cudaMemcpyAsync(r->off, v->off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+	if (r->nspans) cudaMemcpyAsync(r->spans, v->spans + ends[0], r->nspans * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream);
+	k_rebase<<<blocks_for(c1 - c0 + 1, 256), 256, 0, ctx->stream>>>(r->off, c1 - c0 + 1, ends[0], 0u);
+	ctx->launches++;
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { free_dvol(ctx, r); return fail(ctx, VO_ERR_CUDA, cudaGetErrorString(e)); }
+	*out = r;
+	return VO_OK;
+}
+
+int vo_dvol_concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const vo_dvol *c, vo_dvol **out)
+{
+	if (!ctx || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	const vo_dvol *parts[3] = {a, b, c};
+	int nx = -1, ny = 0;
+	uint64_t total = 0;
+	for (auto p : parts) {
+		if (!p) continue;
+		if (nx < 0) nx = p->nx;
+		if (p->nx != nx) return fail(ctx, VO_ERR_ARG, "slabs must share nx");
+		ny += p->ny;
+		total += p->nspans;
+	}
+	if (nx < 0) return fail(ctx, VO_ERR_ARG, "nothing to concatenate");
+	if (total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
+	vo_dvol *r = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &r));
+	r->nspans = total;
+	int rc = dalloc(ctx, &r->spans, total);
+	if (rc) { free_dvol(ctx, r); return rc; }
+	unsigned long long col = 0;
+	uint64_t sp = 0;
+	for (auto p : parts) {
+		if (!p) continue;
+		const unsigned long long n = (unsigned long long)p->nx * p->ny;
+		cudaMemcpyAsync(r->off + col, p->off, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+		if (sp) { k_rebase<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(r->off + col, n + 1, 0u, (uint32_t)sp); ctx->launches++; }
+		if (p->nspans) cudaMemcpyAsync(r->spans + sp, p->spans, p->nspans * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream);
+		col += n;
+		sp += p->nspans;
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { free_dvol(ctx, r); return fail(ctx, VO_ERR_CUDA, cudaGetErrorString(e)); }
+	*out = r;
+	return VO_OK;
+}
+
+int vo_morph3d_dev(vo_ctx *ctx, int op, int method, const vo_dvol *in, double zmin, double zmax, double radius,
+                   vo_dvol **out, double *ms_pass1, double *ms_pass2)
+{
+	if (!ctx || !in || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	PassTimes pt;
+	VO_TRY(morph3d_dev(ctx, op, method, in, zmin, zmax, radius, out, &pt));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (ms_pass1) *ms_pass1 = pt.ms1;
+	if (ms_pass2) *ms_pass2 = pt.ms2;
+	return VO_OK;
+}
+
+int vo_xor3d_dev(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, double zmin, double zmax, double spacing,
+                 vo_dvol **out, double *volume)
+{
+	if (!ctx || !a || !b || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	VO_TRY(xor_dev(ctx, a, b, zmin, zmax, spacing, out, volume));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	return VO_OK;
+}
+
+int vo_pass1_dev(vo_ctx *ctx, const vo_dvol *in, double radius, vo_dmid **mid, double *ms)
+{
+	if (!ctx || !in || !mid) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	VO_TRY(pass1(ctx, in, radius, mid));
+	VO_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	VO_CUDA(cudaEventSynchronize(ctx->ev[1]));
+	float t = 0;
+	cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+	if (ms) *ms = t;
+	return VO_OK;
+}
+
+int vo_pass2_dev(vo_ctx *ctx, const vo_dmid *mid, int y0, int y1, vo_dvol **out, double *ms)
+{
+	if (!ctx || !mid || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	VO_TRY(pass2(ctx, mid, y0, y1, out));
+	VO_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	VO_CUDA(cudaEventSynchronize(ctx->ev[1]));
+	float t = 0;
+	cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+	if (ms) *ms = t;
+	return VO_OK;
+}
+
+void vo_dmid_free(vo_ctx *ctx, vo_dmid *m)
+{
+	if (!ctx || !m) return;
+	DeviceGuard g(ctx->device);
+	dfree(ctx, m->slots);
+	dfree(ctx, m->pool);
+	delete m;
+}
+
+int vo_dmid_info(const vo_dmid *m, int *nx, int *ny, int *classes, uint64_t *bytes)
+{
+	if (!m) return VO_ERR_ARG;
+	if (nx) *nx = m->nx;
+	if (ny) *ny = m->ny;
+	if (classes) *classes = m->J + 1;
+	if (bytes) *bytes = ((uint64_t)m->nx * m->ny * (m->J + 1) + m->pool_used) * sizeof(double2);
+	return VO_OK;
+}
+
+int vo_morph2d_dev(vo_ctx *ctx, int op, const vo_dvol *rows, int width, double r, vo_dvol **out, double *ms)
+{
+	if (!ctx || !rows || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	VO_TRY(morph2d_dev(ctx, op, rows, width, r, out));
+	VO_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	VO_CUDA(cudaEventSynchronize(ctx->ev[1]));
+	float t = 0;
+	cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+	if (ms) *ms = t;
+	return VO_OK;
+}
+
+int vo_morph3d(vo_ctx *ctx, int op, int method, int nx, int ny, double zmin, double zmax,
+               const uint32_t *off, const double *spans, double radius,
+               uint32_t **out_off, double **out_spans, uint64_t *out_nspans, double *ms_pass1, double *ms_pass2)
+{
+	if (!ctx || !out_off || !out_spans) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	vo_dvol *in = nullptr, *res = nullptr;
+	VO_TRY(upload(ctx, nx, ny, off, spans, &in));
+	PassTimes pt;
+	int rc = morph3d_dev(ctx, op, method, in, zmin, zmax, radius, &res, &pt);
+	free_dvol(ctx, in);
+	VO_TRY(rc);
+	rc = download_new(ctx, res, out_off, out_spans, out_nspans);
+	free_dvol(ctx, res);
+	VO_TRY(rc);
+	if (ms_pass1) *ms_pass1 = pt.ms1;
+	if (ms_pass2) *ms_pass2 = pt.ms2;
+	return VO_OK;
+}
+
+int vo_morph2d(vo_ctx *ctx, int op, int rows, int width, const uint32_t *off, const double *spans, double r,
+               uint32_t **out_off, double **out_spans, uint64_t *out_nspans, double *ms)
+{
+	if (!ctx || !out_off || !out_spans) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	if (rows < 0 || width < 0) return fail(ctx, VO_ERR_ARG, "negative image size");
+	vo_dvol *in = nullptr, *res = nullptr;
+	VO_TRY(upload(ctx, rows, 1, off, spans, &in));
+	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	int rc = morph2d_dev(ctx, op, in, width, r, &res);
+	free_dvol(ctx, in);
+	VO_TRY(rc);
+	VO_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	rc = download_new(ctx, res, out_off, out_spans, out_nspans);
+	free_dvol(ctx, res);
+	VO_TRY(rc);
+	float t = 0;
+	cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+	if (ms) *ms = t;
+	return VO_OK;
+}
+
+int vo_xor3d(vo_ctx *ctx, int nx, int ny, double zmin, double zmax, double spacing,
+             const uint32_t *off_a, const double *spans_a, const uint32_t *off_b, const double *spans_b,
+             uint32_t **out_off, double **out_spans, uint64_t *out_nspans, double *volume)
+{
+	if (!ctx || !out_off || !out_spans) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	vo_dvol *a = nullptr, *b = nullptr, *res = nullptr;
+	VO_TRY(upload(ctx, nx, ny, off_a, spans_a, &a));
+	int rc = upload(ctx, nx, ny, off_b, spans_b, &b);
+	if (rc == VO_OK) rc = xor_dev(ctx, a, b, zmin, zmax, spacing, &res, volume);
+	free_dvol(ctx, a);
+	free_dvol(ctx, b);
+	VO_TRY(rc);
+	rc = download_new(ctx, res, out_off, out_spans, out_nspans);
+	free_dvol(ctx, res);
+	return rc;
+}
+
+} // extern "C"

@@ -166,6 +166,35 @@ def random_volume(nx: int, ny: int, kmax: int = 8, seed: int = 7, zrange: float 
                             extent=(float(nx), float(ny), zhi), spacing=1.0, padding=p)
 
 
+def blobs(n: int, count: int = 24, seed: int = 5, padding: int = 0, rmin: float = 0.06, rmax: float = 0.2) -> CompressedVolume:
+    """Union of random balls in the unit cube: smooth multi-interval columns (thick enough to survive
+    erosion / opening), used by the parity tests next to the tori."""
+    rng = np.random.RandomState(seed)
+    vol, xs, ys, sp = _grid((1.0, 1.0, 1.0), n, padding, (0.0, 0.0, 0.0))
+    cen = rng.uniform(0.2, 0.8, size=(count, 3))
+    rad = rng.uniform(rmin, rmax, size=count)
+    X, Y = np.meshgrid(xs + _JX * sp, ys + _JY * sp)
+    per = [[] for _ in range(vol.nx * vol.ny)]
+    for (cx, cy, cz), r in zip(cen, rad):
+        d2 = r * r - (X - cx) ** 2 - (Y - cy) ** 2
+        idx = np.nonzero(d2.reshape(-1) > 0)[0]
+        half = np.sqrt(d2.reshape(-1)[idx])
+        for c, h in zip(idx, half):
+            per[c].append(((cz - h) / sp, (cz + h) / sp))
+    lists = []
+    for iv in per:
+        iv.sort()
+        merged = []
+        for a, b in iv:
+            if merged and a <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], b)
+            else:
+                merged.append([a, b])
+        lists.append([v for ab in merged for v in ab])
+    off, spans = csr_from_lists(lists)
+    return vol.like(vol.nx, vol.ny, off, spans)
+
+
 def star_image(rows: int = 2048, width: int = 2048, n_polys: int = 64, seed: int = 1234) -> DexelImage:
     """Config C2: star polygons (5..12 spikes) scan-converted at row centres, rows = sweep axis.
 
