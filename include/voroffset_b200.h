@@ -68,6 +68,14 @@ void       *vo_stream(const vo_ctx *ctx);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches).                 */
 uint64_t    vo_launch_count(const vo_ctx *ctx);
 
+/* Timing on the context's own stream (torch.cuda.Event only sees torch's streams): vo_mark records event
+ * `slot` (0..7); vo_elapsed_ms waits for slot_b and returns the device time between the two marks.     */
+int         vo_mark(vo_ctx *ctx, int slot);
+int         vo_elapsed_ms(vo_ctx *ctx, int slot_a, int slot_b, double *ms);
+/* Device time of the two dominant kernels (k_pass1, k_pass2; first launch of each) of the most recent
+ * 'ours' dilation on this context, measured with CUDA events around the launches.                     */
+int         vo_last_profile(vo_ctx *ctx, double *k_pass1_ms, double *k_pass2_ms);
+
 /* ---- host-buffer drop-in: one call = upload, operator, download -------------------------------- */
 /* Replaces  VoronoiMorpho::dilation / ::erosion  (src/vor3d/Voronoi.h:18,29; Voronoi.cpp:8-17) and the
  * opening / closing compositions of app/cli3d/offset3d.cpp:124-133.
@@ -100,7 +108,11 @@ int vo_xor3d(vo_ctx *ctx, int nx, int ny, double zmin, double zmax, double spaci
 /* ---- device-resident API (inputs and results stay in HBM) --------------------------------------- */
 /* CompressedVolume storage (src/vor3d/CompressedVolume.h:14) converted to device CSR.                 */
 int  vo_dvol_upload(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans, vo_dvol **out);
+/* Destination buffers may be host or device memory (cudaMemcpyDefault).                               */
 int  vo_dvol_download(vo_ctx *ctx, const vo_dvol *vol, uint32_t *off, double *spans);
+/* Same as upload, from device pointers (e.g. buffers an NCCL halo exchange has just filled).           */
+int  vo_dvol_from_device(vo_ctx *ctx, int nx, int ny, const void *d_off, const void *d_spans, uint64_t nspans,
+                         vo_dvol **out);
 /* Shape and raw device pointers (uint32_t* / double*) of a resident volume.                           */
 int  vo_dvol_info(const vo_dvol *vol, int *nx, int *ny, uint64_t *nspans, const void **d_off, const void **d_spans);
 void vo_dvol_free(vo_ctx *ctx, vo_dvol *vol);

@@ -182,6 +182,22 @@ class Reference:
         o, s = _take(self._free, onx.value * ony.value, poff, pev)
         return vol.like(onx.value, ony.value, o, s)
 
+    def mid_count(self, vol: CompressedVolume, radius: float) -> int:
+        """Pieces in the reference's own intermediate volume (VoronoiVorPower.cpp:50-65) = N * k_mid."""
+        off, ev = _in_arrays(vol.off, vol.spans)
+        origin = (C.c_double * 3)(*vol.origin)
+        extent = (C.c_double * 3)(*vol.extent)
+        n = C.c_uint64(0)
+        err = C.create_string_buffer(1024)
+        self.lib.ref3d_mid_count.argtypes = [C.c_int, C.c_int, _f64p, _f64p, C.c_double, C.c_int, _u64p, _f64p,
+                                             C.c_double, C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
+        rc = self.lib.ref3d_mid_count(vol.nx, vol.ny, origin, extent, vol.spacing, vol.padding,
+                                      off.ctypes.data_as(_u64p), ev.ctypes.data_as(_f64p), float(radius),
+                                      C.byref(n), err, 1024)
+        if rc:
+            raise RuntimeError(err.value.decode(errors="replace"))
+        return int(n.value)
+
     def xor3d(self, a: CompressedVolume, b: CompressedVolume):
         oa, ea = _in_arrays(a.off, a.spans)
         ob, eb = _in_arrays(b.off, b.spans)

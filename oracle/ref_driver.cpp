@@ -13,6 +13,9 @@
 #include "vor3d/CompressedVolume.h"
 #include "vor3d/VoronoiVorPower.h"
 #include "vor3d/VoronoiBruteForce.h"
+#include "vor3d/MorphologyOperators.h"
+#include "vor3d/HalfDilationOperator.h"
+#include "vor3d/Voronoi2D.h"
 #include "vor2d/DoubleCompressedImage.h"
 #include "tbb/task_scheduler_init.h"
 
@@ -97,6 +100,38 @@ int ref3d_morph(int op, int method, int threads, int nx, int ny, const double *o
 		if (time_1) *time_1 = t1;
 		if (time_2) *time_2 = t2;
 		if (dump_volume(output, out_nx, out_ny, out_off, out_ev)) { set_err(err, errlen, "out of memory"); return 3; }
+		return 0;
+	} catch (const std::exception &e) {
+		set_err(err, errlen, e.what());
+		return 1;
+	}
+}
+
+// Number of pieces the reference's intermediate volume (`mid_output`, VoronoiVorPower.cpp:65) holds for
+// this input and radius: runs the reference's own first pass - the loop of VoronoiVorPower.cpp:50-57
+// (halfDilate forward + backward per x-slice with a VoronoiMorpho2D) followed by its unionMap - and counts.
+// This is the k_mid of SURVEY.md section 8(d) that the roofline's algorithmic bytes are defined on.
+int ref3d_mid_count(int nx, int ny, const double *origin, const double *extent, double spacing, int padding,
+	const uint64_t *off, const double *ev, double radius, uint64_t *pieces, char *err, int errlen)
+{
+	try {
+		vor3d::CompressedVolume input;
+		fill_volume(input, nx, ny, origin, extent, spacing, padding, off, ev);
+		double zmin = input.origin()(2) / input.spacing();
+		double zmax = zmin + 2 * input.padding() + input.extent()(2) / input.spacing();
+		vor3d::CompressedVolumeWithRadii o1, o2, mid;
+		o1.reshape(nx, ny); o2.reshape(nx, ny); mid.reshape(nx, ny);
+		vor3d::VoronoiMorpho2D op_x(ny, zmin, zmax, radius, input.spacing());
+		for (int x = 0; x < nx; x++) {
+			vor3d::halfDilate(op_x, true, input, o1, x, 0, 0, +1);
+			op_x.resetData();
+			vor3d::halfDilate(op_x, true, input, o2, x, ny - 1, 0, -1);
+			op_x.resetData();
+		}
+		vor3d::unionMap(o1, o2, mid);
+		uint64_t n = 0;
+		for (int y = 0; y < ny; ++y) for (int x = 0; x < nx; ++x) n += mid.at(x, y).size();
+		*pieces = n;
 		return 0;
 	} catch (const std::exception &e) {
 		set_err(err, errlen, e.what());

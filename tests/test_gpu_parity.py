@@ -1,0 +1,275 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (ctypes -> libvoroffset_b200.so).
+
+Bit-exact for dilation / erosion (both methods) and for every brute_force composite; opening / closing
+of 'ours' are compared with identical topology and |dz| <= util.COMPOSITE_TOL (see tests/util.py).
+"""
+import numpy as np
+import pytest
+
+import util
+from voroffset_b200 import _lib, image2d, morpho, synth
+from voroffset_b200.volume import CompressedVolume, DexelImage
+
+pytestmark = pytest.mark.gpu
+
+OPS = ("dilation", "erosion", "opening", "closing")
+
+
+# ---- golden vectors produced by the reference itself -----------------------------------------------
+@pytest.mark.parametrize("path", util.golden_3d(), ids=lambda p: p.split("vol3d_")[-1][:-4])
+@pytest.mark.parametrize("method", ["ours", "brute_force"])
+def test_golden_3d(ctx, path, method):
+    z, vol, radius, ops = util.load_3d(path)
+    op = morpho.make_operator(method, ctx)
+    for name in ops:
+        got, t1, t2 = morpho.apply_operation(op, name, vol, radius)
+        util.assert_same(got, util.expected_3d(z, vol, name, method), name, method, "cuda vs golden")
+        assert t1 >= 0 and t2 >= 0
+
+
+@pytest.mark.parametrize("path", util.golden_2d(), ids=lambda p: p.split("img2d_")[-1][:-4])
+def test_golden_2d(ctx, path):
+    z, img, ops = util.load_2d(path)
+    for i, (name, r) in enumerate(ops):
+        d = image2d.DoubleCompressedImage.from_image(img, ctx)
+        d.negate() if name == "negate" else getattr(d, name)(r)
+        want = DexelImage(img.rows, img.width, z[f"{i}__off"], z[f"{i}__spans"])
+        assert d.bit_equal(want), (name, r)
+
+
+# ---- seeded inputs against the oracle ---------------------------------------------------------------
+SEEDED = [
+    ("torus_x_n128_p8", lambda: synth.torus_x(128, padding=8), 5.5),
+    ("torus_z_n160_p12", lambda: synth.torus_z(160, padding=12), 10.0),
+    ("blobs_n96_p9", lambda: synth.blobs(96, padding=9), 8.0),
+    ("blobs_many_n80", lambda: synth.blobs(80, count=120, padding=5, rmin=0.02, rmax=0.07, seed=9), 3.3),
+    ("random_k8", lambda: synth.random_volume(40, 32, kmax=8, padding=6), 4.3),
+    ("random_sparse", lambda: synth.random_volume(33, 47, kmax=3, padding=9, seed=9, fill=0.3), 7.7),
+    ("lattice_n96", lambda: synth.lattice(96, padding=8), 5.0),
+    ("ragged_31x3", lambda: synth.random_volume(31, 3, kmax=5, padding=0, seed=4), 2.5),
+    ("one_row", lambda: synth.random_volume(50, 1, kmax=4, padding=0, seed=5), 6.0),
+    ("one_column", lambda: synth.random_volume(1, 1, kmax=3, padding=0, seed=6), 4.0),
+    ("radius_lt_1", lambda: synth.blobs(40, padding=2, seed=3), 0.75),
+    ("radius_integer", lambda: synth.blobs(48, padding=7, seed=2), 6.0),
+    ("all_empty", lambda: synth.random_volume(9, 7, kmax=0, padding=2), 3.0),
+]
+
+
+@pytest.mark.parametrize("name,gen,radius", SEEDED, ids=[c[0] for c in SEEDED])
+@pytest.mark.parametrize("method", ["ours", "brute_force"])
+def test_seeded_3d(ctx, oracle, name, gen, radius, method):
+    vol = gen()
+    op = morpho.make_operator(method, ctx)
+    for opn in OPS:
+        got, _, _ = morpho.apply_operation(op, opn, vol, radius)
+        util.assert_same(got, oracle.morph3d(vol, opn, radius, method), opn, method, f"cuda vs oracle [{name}]")
+
+
+def test_many_layers_use_the_redo_path(ctx, oracle):
+    # 40 thin layers per column: the running union outgrows the fast capacity (16) and is redone
+    rng = np.random.RandomState(0)
+    lists = []
+    for _ in range(12 * 10):
+        z = np.cumsum(rng.uniform(0.4, 0.9, size=80)) + rng.uniform(0, 0.3)
+        lists.append(z.tolist())
+    vol = CompressedVolume.from_lists(12, 10, lists, origin=(0, 0, -5.0), extent=(12.0, 10.0, 70.0), spacing=1.0, padding=0)
+    for method in ("ours", "brute_force"):
+        op = morpho.make_operator(method, ctx)
+        got, _, _ = op.dilation(vol, 0.3)
+        assert got.bit_equal(oracle.morph3d(vol, "dilation", 0.3, method))
+        assert got.counts().max() > 16
+    # with neighbours in reach (R = 1.3) the transient lists are long although the result is short
+    for method in ("ours", "brute_force"):
+        got, _, _ = morpho.make_operator(method, ctx).dilation(vol, 1.3)
+        assert got.bit_equal(oracle.morph3d(vol, "dilation", 1.3, method))
+
+
+def test_zero_radius_is_identity(ctx):
+    vol = synth.blobs(32, padding=2, seed=4)
+    got, _, _ = morpho.make_operator("ours", ctx).dilation(vol, 0.0)
+    assert got.bit_equal(vol)
+
+
+def test_single_point_column_dilates_to_a_ball(ctx):
+    # analytic check (SURVEY.md 8(c) pin 4): half-length at offset d is sqrt(R^2 - d^2)
+    R, n = 6.5, 21
+    lists = [[] for _ in range(n * n)]
+    lists[10 + n * 10] = [3.0, 3.0]
+    vol = CompressedVolume.from_lists(n, n, lists, origin=(0, 0, -10.0), extent=(float(n), float(n), 30.0), spacing=1.0)
+    got, _, _ = morpho.make_operator("ours", ctx).dilation(vol, R)
+    for y in range(n):
+        for x in range(n):
+            d2 = (x - 10) ** 2 + (y - 10) ** 2
+            col = got.at(x, y)
+            if d2 <= R * R and abs(x - 10) <= np.floor(np.sqrt(R * R - (y - 10) ** 2)):
+                assert col.size == 2
+                assert col[1] - 3.0 == pytest.approx(np.sqrt(R * R - d2), abs=1e-12)
+                assert 3.0 - col[0] == pytest.approx(np.sqrt(R * R - d2), abs=1e-12)
+            else:
+                assert col.size == 0
+
+
+# ---- error behaviour ----------------------------------------------------------------------------------
+def test_errors_are_reported_not_swallowed(ctx):
+    vol = synth.blobs(16, padding=1, seed=1)
+    op = morpho.make_operator("ours", ctx)
+    with pytest.raises(_lib.VoroffsetError):
+        op.dilation(vol, -1.0)
+    with pytest.raises(_lib.VoroffsetError):
+        op.dilation(vol, float("nan"))
+    with pytest.raises(ValueError):
+        morpho.make_operator("fancy", ctx)
+    with pytest.raises(ValueError):
+        morpho.apply_operation(op, "smoothing", vol, 1.0)
+    import ctypes as C
+    poff, pspans, n = _lib._u32p(), _lib._f64p(), C.c_uint64()
+    rc = ctx.lib.vo_morph3d(ctx.handle, 9, 0, vol.nx, vol.ny, 0.0, 1.0, _lib.ptr(vol.off), _lib.ptr(vol.spans), 2.0,
+                            C.byref(poff), C.byref(pspans), C.byref(n), None, None)
+    assert rc == 1 and ctx.lib.vo_last_error(ctx.handle) == b"Operation"
+    rc = ctx.lib.vo_morph3d(ctx.handle, 0, 7, vol.nx, vol.ny, 0.0, 1.0, _lib.ptr(vol.off), _lib.ptr(vol.spans), 2.0,
+                            C.byref(poff), C.byref(pspans), C.byref(n), None, None)
+    assert rc == 1 and ctx.lib.vo_last_error(ctx.handle) == b"Invalid method"
+
+
+# ---- resident API ---------------------------------------------------------------------------------------
+def test_resident_round_trip_rows_and_concat(ctx):
+    vol = synth.blobs(48, padding=3, seed=6)
+    d = morpho.DeviceVolume.upload(ctx, vol)
+    assert d.download().bit_equal(vol)
+    a, b, c = d.rows(0, 10), d.rows(10, 31), d.rows(31, vol.ny)
+    assert morpho.concat_rows(ctx, [a, b, c]).download().bit_equal(vol)
+    part = b.download()
+    assert part.ny == 21 and part.at(5, 0).tolist() == vol.at(5, 10).tolist()
+
+
+def test_split_passes_equal_fused_call(ctx):
+    import ctypes as C
+    vol = synth.blobs(64, padding=8, seed=7)
+    R = 7.3
+    op = morpho.make_operator("ours", ctx)
+    fused, _, _ = op.dilation(vol, R)
+    d = morpho.DeviceVolume.upload(ctx, vol)
+    mid = C.c_void_p()
+    ctx.check(ctx.lib.vo_pass1_dev(ctx.handle, d.handle, R, C.byref(mid), None))
+    pieces = []
+    for y0, y1 in [(0, 17), (17, 18), (18, vol.ny)]:
+        h = C.c_void_p()
+        ctx.check(ctx.lib.vo_pass2_dev(ctx.handle, mid, y0, y1, C.byref(h), None))
+        pieces.append(morpho.DeviceVolume(ctx, h, vol))
+    ctx.lib.vo_dmid_free(ctx.handle, mid)
+    assert morpho.concat_rows(ctx, pieces).download().bit_equal(fused)
+
+
+def test_resident_operator_matches_host_call(ctx):
+    vol = synth.torus_x(96, padding=6)
+    op = morpho.make_operator("ours", ctx)
+    d = morpho.DeviceVolume.upload(ctx, vol)
+    for opn in OPS:
+        r, _, _ = op.morph_dev(opn, d, 4.4)
+        h, _, _ = morpho.apply_operation(op, opn, vol, 4.4)
+        assert r.download().bit_equal(h)
+
+
+# ---- xor --------------------------------------------------------------------------------------------------
+def test_xor(ctx, oracle):
+    a, b = synth.blobs(64, padding=4, seed=1), synth.blobs(64, padding=4, seed=2)
+    op = morpho.make_operator("ours", ctx)
+    vol, x = op.calculateXor(a, b)
+    wvol, wx = oracle.xor3d(a, b)
+    assert x.bit_equal(wx)
+    assert vol == pytest.approx(wvol, rel=1e-12)
+    v0, x0 = op.calculateXor(a, a)
+    assert v0 == 0 and x0.numSegments() == 0
+    # the reference's own use: ours vs brute_force have zero xor volume
+    d1, _, _ = op.dilation(a, 5.5)
+    d2, _, _ = morpho.make_operator("brute_force", ctx).dilation(a, 5.5)
+    v, _ = op.calculateXor(d1, d2)
+    assert v == 0
+
+
+# ---- 2D ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [1, 2])
+def test_seeded_2d(ctx, oracle, seed):
+    img = synth.random_image(200, 300, kmax=5, seed=seed)
+    for op, r in [("dilate", 8.0 / 200), ("dilate", 5.5 / 200), ("erode", 4.0), ("erode", 2.5), ("open", 3.0 / 200),
+                  ("close", 3.0 / 200), ("negate", 0.0)]:
+        d = image2d.DoubleCompressedImage.from_image(img, ctx)
+        d.negate() if op == "negate" else getattr(d, op)(r)
+        assert d.bit_equal(oracle.morph2d(img, op, r)), (op, r)
+
+
+def test_config2_2048_rows(ctx, oracle):
+    # BASELINE config 2: 2048^2 grid, effective R = 16 dilation (call dilate(16/2048)), erode R = 4
+    img = synth.star_image(2048, 2048, 64)
+    for op, r in [("dilate", 16.0 / 2048), ("erode", 4.0)]:
+        d = image2d.DoubleCompressedImage.from_image(img, ctx)
+        getattr(d, op)(r)
+        assert d.bit_equal(oracle.morph2d(img, op, r)), op
+    empty = image2d.DoubleCompressedImage.from_image(DexelImage.from_lists(64, [[] for _ in range(5)]), ctx)
+    empty.erode(2.0)
+    assert empty.numSegments() == 0
+    empty.negate()
+    assert empty.numSegments() == 5
+
+
+# ---- BASELINE sizes ---------------------------------------------------------------------------------------
+def test_config3_lattice_ours_vs_brute_force(ctx, oracle):
+    # config 3: -n 512 -p 10 -r 5, dilation, 'ours' against the 'brute_force' oracle method, both on the GPU,
+    # plus the CPU oracle on the same input (283 k columns)
+    vol = synth.lattice(512, padding=10)
+    assert (vol.nx, vol.ny) == (532, 532)
+    a, _, _ = morpho.make_operator("ours", ctx).dilation(vol, 5.0)
+    b, _, _ = morpho.make_operator("brute_force", ctx).dilation(vol, 5.0)
+    assert a.same_topology(b)
+    assert np.abs(a.spans - b.spans).max() <= 1e-12
+    assert a.bit_equal(oracle.morph3d(vol, "dilation", 5.0, "ours"))
+
+
+def test_config4_opening_closing_1024(ctx, oracle):
+    # config 4: -n 1024 -r 16 opening and closing. Full-size oracle run on the CPU is ~10 s with threads.
+    vol = synth.torus_z(1024, padding=18)
+    op = morpho.make_operator("ours", ctx)
+    for opn in ("opening", "closing"):
+        got, _, _ = morpho.apply_operation(op, opn, vol, 16.0)
+        util.assert_same(got, oracle.morph3d(vol, opn, 16.0, "ours"), opn, "ours", "config 4")
+    # size-independent properties: closing is extensive, opening anti-extensive (single-interval columns)
+    cl, _, _ = op.closing(vol, 16.0)
+    opn_, _, _ = op.opening(vol, 16.0)
+    ci, cc, co = vol.counts(), cl.counts(), opn_.counts()
+    assert np.all(cc[ci > 0] >= 1) and np.all(ci[co > 0] >= 1)
+
+
+def test_config5_dilation_2048_properties(ctx, oracle):
+    # config 5 at full size (4.19 M columns, R = 32): the oracle checks a band of rows bit for bit, and
+    # size-independent properties hold over the whole result.
+    vol = synth.torus_z(2048)
+    R = 32.0
+    op = morpho.make_operator("ours", ctx)
+    got, t1, t2 = op.dilation(vol, R)
+    assert (got.nx, got.ny) == (2048, 2048)
+    # (1) band parity: rows [y0-R, y1+R) of the input determine rows [y0, y1) of the output exactly
+    y0, y1, J = 300, 316, 32
+    band = CompressedVolume(vol.nx, (y1 + J) - (y0 - J), *_rows(vol, y0 - J, y1 + J))
+    want = oracle.morph3d(band, "dilation", R, "ours")
+    g_off, g_sp = _rows(got, y0, y1)
+    w_off, w_sp = _rows(want, J, J + (y1 - y0))
+    assert np.array_equal(g_off, w_off) and np.array_equal(g_sp.view(np.uint64), w_sp.view(np.uint64))
+    # (2) extensive: every input interval is inside an output interval grown by exactly R at dx=dy=0
+    ci, co = vol.counts(), got.counts()
+    assert np.all(co[ci > 0] == 1)
+    cols = np.nonzero(ci > 0)[0]
+    lo_in, hi_in = vol.spans[vol.off[cols].astype(np.int64)].T
+    lo_out, hi_out = got.spans[got.off[cols].astype(np.int64)].T
+    assert np.all(lo_out <= lo_in - R) and np.all(hi_out >= hi_in + R)
+    # (3) a bigger radius gives a superset; (4) determinism (checksum of a second run)
+    again, _, _ = op.dilation(vol, R)
+    assert util.checksum(again) == util.checksum(got)
+    small, _, _ = op.dilation(vol, 20.0)
+    cs = small.counts()
+    assert np.all(co[cs > 0] >= 1)
+
+
+def _rows(vol, y0, y1):
+    c0, c1 = y0 * vol.nx, y1 * vol.nx
+    off = vol.off[c0:c1 + 1].astype(np.int64)
+    return (off - off[0]).astype(np.uint32), vol.spans[off[0]:off[-1]]

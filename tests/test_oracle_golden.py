@@ -1,0 +1,27 @@
+"""The plain-C restatement (oracle/oracle.c) against the committed outputs of the reference itself
+(tests/golden, produced by tests/golden/make_golden.py from oracle/_ref). CPU only."""
+import pytest
+
+import util
+
+
+@pytest.mark.parametrize("path", util.golden_3d(), ids=lambda p: p.split("vol3d_")[-1][:-4])
+def test_oracle_matches_reference_outputs_3d(oracle, path):
+    z, vol, radius, ops = util.load_3d(path)
+    for op in ops:
+        for method in ("ours", "brute_force"):
+            got = oracle.morph3d(vol, op, radius, method)
+            util.assert_same(got, util.expected_3d(z, vol, op, method), op, method, "oracle vs golden")
+
+
+@pytest.mark.parametrize("path", util.golden_2d(), ids=lambda p: p.split("img2d_")[-1][:-4])
+def test_oracle_matches_reference_outputs_2d(oracle, path):
+    z, img, ops = util.load_2d(path)
+    for i, (op, r) in enumerate(ops):
+        got = oracle.morph2d(img, op, r)
+        assert got.off.tolist() == z[f"{i}__off"].tolist(), (op, r)
+        assert (got.spans.view("u8") == z[f"{i}__spans"].view("u8")).all(), (op, r)
+
+
+def test_golden_set_is_present():
+    assert len(util.golden_3d()) >= 5 and len(util.golden_2d()) >= 2

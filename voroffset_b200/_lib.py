@@ -29,6 +29,7 @@ EXPORTS = [
     "vo_launch_count", "vo_morph3d", "vo_morph2d", "vo_xor3d", "vo_dvol_upload", "vo_dvol_download",
     "vo_dvol_info", "vo_dvol_free", "vo_dvol_rows", "vo_dvol_concat_rows", "vo_morph3d_dev", "vo_xor3d_dev",
     "vo_pass1_dev", "vo_pass2_dev", "vo_dmid_free", "vo_dmid_info", "vo_morph2d_dev",
+    "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device",
 ]
 
 _lib = None
@@ -84,6 +85,10 @@ def load() -> C.CDLL:
     L.vo_dmid_free.restype = None
     L.vo_dmid_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     L.vo_morph2d_dev.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double, C.POINTER(_vp), _f64p]
+    L.vo_mark.argtypes = [_vp, C.c_int]
+    L.vo_elapsed_ms.argtypes = [_vp, C.c_int, C.c_int, _f64p]
+    L.vo_last_profile.argtypes = [_vp, _f64p, _f64p]
+    L.vo_dvol_from_device.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp)]
     _lib = L
     return L
 
@@ -122,6 +127,19 @@ class Context:
     @property
     def stream(self) -> int:
         return int(self.lib.vo_stream(self.handle) or 0)
+
+    def mark(self, slot: int):
+        self.check(self.lib.vo_mark(self.handle, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double(0)
+        self.check(self.lib.vo_elapsed_ms(self.handle, a, b, C.byref(ms)))
+        return ms.value
+
+    def last_profile(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self.check(self.lib.vo_last_profile(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def take_host(self, poff, pspans, nlists: int, nspans: int):
         """Copy a (vo_free-able) result pair into numpy arrays and release the pinned blocks."""

@@ -31,6 +31,10 @@ struct vo_ctx {
 	uint64_t launches = 0;
 	// small persistent device scratch: [0] mid-pool cursor, [1] stage-pool cursor, [2] redo count
 	unsigned long long *d_ctr = nullptr;
+	// caller-visible timing marks (vo_mark / vo_elapsed_ms) and per-kernel profile of the last dilation
+	cudaEvent_t mark[8] = {};
+	cudaEvent_t kev[4] = {};          // [0,1] around k_pass1<CAP_FAST>, [2,3] around k_pass2<CAP_FAST>
+	bool kev_valid[2] = {false, false};
 };
 
 struct vo_dvol {
@@ -387,7 +391,13 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		a.off = in->off; a.spans = in->spans; a.H = dt.H; a.reach = dt.reach;
 		a.mid = m->slots; a.pool = m->pool; a.cursor = ctx->d_ctr; a.pool_cap = m->pool_cap;
 		a.redo = rb.rd; a.work = nullptr; a.nwork = nslots;
-		if (nslots) { k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a); ctx->launches++; }
+		if (nslots) {
+			cudaEventRecord(ctx->kev[0], ctx->stream);
+			k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a);
+			cudaEventRecord(ctx->kev[1], ctx->stream);
+			ctx->kev_valid[0] = true;
+			ctx->launches++;
+		}
 		e = cudaGetLastError();
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1: ") + cudaGetErrorString(e)));
 		unsigned long long h[3];
@@ -425,7 +435,12 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
 	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
-		[&](Pass2Args &g) { k_pass2<CAP_FAST><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
+		[&](Pass2Args &g) {
+			cudaEventRecord(ctx->kev[2], s);
+			k_pass2<CAP_FAST><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g);
+			cudaEventRecord(ctx->kev[3], s);
+			ctx->kev_valid[1] = true;
+		},
 		[&](Pass2Args &g) { k_pass2<CAP_BIG><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
 		m->nx, y1 - y0, out);
 }
@@ -735,6 +750,8 @@ int vo_create(int device, vo_ctx **out)
 	bool ok = cudaSetDevice(device) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
 	for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+	for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->mark[i]) == cudaSuccess;
+	for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&ctx->kev[i]) == cudaSuccess;
 	ok = ok && cudaMalloc((void **)&ctx->d_ctr, 4 * sizeof(unsigned long long)) == cudaSuccess;
 	if (ok) {
 		// keep freed blocks in the stream-ordered pool: steady-state calls then allocate without the driver
@@ -756,6 +773,8 @@ void vo_destroy(vo_ctx *ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	if (ctx->d_ctr) cudaFree(ctx->d_ctr);
 	for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+	for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
+	for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -763,6 +782,57 @@ void vo_destroy(vo_ctx *ctx)
 const char *vo_last_error(const vo_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 void *vo_stream(const vo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t vo_launch_count(const vo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vo_mark(vo_ctx *ctx, int slot)
+{
+	if (!ctx || slot < 0 || slot >= 8) return VO_ERR_ARG;
+	DeviceGuard g(ctx->device);
+	VO_CUDA(cudaEventRecord(ctx->mark[slot], ctx->stream));
+	return VO_OK;
+}
+
+int vo_elapsed_ms(vo_ctx *ctx, int slot_a, int slot_b, double *ms)
+{
+	if (!ctx || !ms || slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8) return VO_ERR_ARG;
+	DeviceGuard g(ctx->device);
+	VO_CUDA(cudaEventSynchronize(ctx->mark[slot_b]));
+	float t = 0;
+	VO_CUDA(cudaEventElapsedTime(&t, ctx->mark[slot_a], ctx->mark[slot_b]));
+	*ms = t;
+	return VO_OK;
+}
+
+int vo_last_profile(vo_ctx *ctx, double *k_pass1_ms, double *k_pass2_ms)
+{
+	if (!ctx) return VO_ERR_ARG;
+	DeviceGuard g(ctx->device);
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	float t = 0;
+	if (k_pass1_ms) { *k_pass1_ms = 0; if (ctx->kev_valid[0]) { VO_CUDA(cudaEventElapsedTime(&t, ctx->kev[0], ctx->kev[1])); *k_pass1_ms = t; } }
+	if (k_pass2_ms) { *k_pass2_ms = 0; if (ctx->kev_valid[1]) { VO_CUDA(cudaEventElapsedTime(&t, ctx->kev[2], ctx->kev[3])); *k_pass2_ms = t; } }
+	return VO_OK;
+}
+
+int vo_dvol_from_device(vo_ctx *ctx, int nx, int ny, const void *d_off, const void *d_spans, uint64_t nspans, vo_dvol **out)
+{
+	if (!ctx || !out || !d_off) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	VO_TRY(check_dims(ctx, nx, ny));
+	if (nspans >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "more than 2^32-1 intervals");
+	const unsigned long long n = (unsigned long long)nx * ny;
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &v));
+	int rc = dalloc(ctx, &v->spans, nspans);
+	if (rc) { free_dvol(ctx, v); return rc; }
+	v->nspans = nspans;
+	cudaError_t e = cudaMemcpyAsync(v->off, d_off, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
+	if (e == cudaSuccess && nspans) e = cudaMemcpyAsync(v->spans, d_spans, nspans * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e != cudaSuccess) { free_dvol(ctx, v); cudaGetLastError(); return fail(ctx, VO_ERR_CUDA, std::string("from_device: ") + cudaGetErrorString(e)); }
+	*out = v;
+	return VO_OK;
+}
 
 void vo_free(void *p)
 {
@@ -792,10 +862,10 @@ int vo_dvol_download(vo_ctx *ctx, const vo_dvol *v, uint32_t *off, double *spans
 	ctx->err.clear();
 	DeviceGuard g(ctx->device);
 	const unsigned long long n = (unsigned long long)v->nx * v->ny;
-	VO_CUDA(cudaMemcpyAsync(off, v->off, (n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaMemcpyAsync(off, v->off, (n + 1) * sizeof(uint32_t), cudaMemcpyDefault, ctx->stream));
 	if (v->nspans) {
 		if (!spans) return fail(ctx, VO_ERR_ARG, "spans is NULL");
-		VO_CUDA(cudaMemcpyAsync(spans, v->spans, v->nspans * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(spans, v->spans, v->nspans * sizeof(double2), cudaMemcpyDefault, ctx->stream));
 	}
 	VO_CUDA(cudaStreamSynchronize(ctx->stream));
 	return VO_OK;

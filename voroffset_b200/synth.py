@@ -116,17 +116,22 @@ def lattice(n: int, padding: int = 10, seed: int = 3) -> CompressedVolume:
     grid_ok_x = (cx > 0) & (cx < n)
     grid_ok_y = (cy > 0) & (cy < n)
     z0, z1 = 1.0 + _JZ, n - 1.0 - _JZ * 0.7
+
+    def jit(i, j, k):                                    # per-column pseudo-random jitter in [0, 0.02)
+        t = math.sin(i * 12.9898 + j * 78.233 + k * 37.719) * 43758.5453
+        return 0.02 * (t - math.floor(t))
+
     lists = []
     for j in range(vol.ny):
         for i in range(vol.nx):
             if not (grid_ok_x[i] and grid_ok_y[j]):
                 lists.append(())
             elif in_x[i] and in_y[j]:
-                lists.append((z0 + 0.011 * ((i * 7 + j * 3) % 13), z1 - 0.013 * ((i * 5 + j * 11) % 17)))  # z-bar
+                lists.append((z0 + jit(i, j, 0), z1 - jit(i, j, 1)))                      # z-bar
             elif in_x[i] or in_y[j]:
                 ev = []
                 for k, (a, b) in enumerate(bz):          # x- or y-bar seen end-on: one interval per z level
-                    ev += [a + 0.0021 * ((i + 2 * j + k) % 7), b + 0.0017 * ((2 * i + j + k) % 5)]
+                    ev += [a + jit(i, j, 2 * k + 2), b + jit(i, j, 2 * k + 3)]
                 lists.append(ev)
             else:
                 lists.append(())
