@@ -68,6 +68,9 @@ void       *vo_stream(const vo_ctx *ctx);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches).                 */
 uint64_t    vo_launch_count(const vo_ctx *ctx);
 
+/* Tuning knobs. "pass1" = "auto" (default: tile kernel when it fits) | "tile" | "simple" (one thread per
+ * (x, y, class); kept as the general fallback and as an independent implementation for the tests).     */
+int         vo_set_option(vo_ctx *ctx, const char *key, const char *value);
 /* Timing on the context's own stream (torch.cuda.Event only sees torch's streams): vo_mark records event
  * `slot` (0..7); vo_elapsed_ms waits for slot_b and returns the device time between the two marks.     */
 int         vo_mark(vo_ctx *ctx, int slot);

@@ -29,7 +29,7 @@ EXPORTS = [
     "vo_launch_count", "vo_morph3d", "vo_morph2d", "vo_xor3d", "vo_dvol_upload", "vo_dvol_download",
     "vo_dvol_info", "vo_dvol_free", "vo_dvol_rows", "vo_dvol_concat_rows", "vo_morph3d_dev", "vo_xor3d_dev",
     "vo_pass1_dev", "vo_pass2_dev", "vo_dmid_free", "vo_dmid_info", "vo_morph2d_dev",
-    "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device",
+    "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device", "vo_set_option",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
     L.vo_dmid_free.restype = None
     L.vo_dmid_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     L.vo_morph2d_dev.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double, C.POINTER(_vp), _f64p]
+    L.vo_set_option.argtypes = [_vp, C.c_char_p, C.c_char_p]
     L.vo_mark.argtypes = [_vp, C.c_int]
     L.vo_elapsed_ms.argtypes = [_vp, C.c_int, C.c_int, _f64p]
     L.vo_last_profile.argtypes = [_vp, _f64p, _f64p]
@@ -127,6 +128,9 @@ class Context:
     @property
     def stream(self) -> int:
         return int(self.lib.vo_stream(self.handle) or 0)
+
+    def set_option(self, key: str, value: str):
+        self.check(self.lib.vo_set_option(self.handle, key.encode(), value.encode()))
 
     def mark(self, slot: int):
         self.check(self.lib.vo_mark(self.handle, slot))

@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(128) k_pass1(Pass1Args a)
 	const int j = (int)(rest % (unsigned)(a.J + 1));
 	const int y = (int)(rest / (unsigned)(a.J + 1));
 
-	RunUnion<CAP> u;
-	u.init();
+	double2 ulist[CAP];
+	RunUnion<CAP> u(ulist);
 	const int X = a.reach[j];
 	const int lo = max(-X, -x), hi = min(X, a.nx - 1 - x);
 	const double *Hrow = a.H + (size_t)j * (a.J + 1);
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 	const int x = (int)(c % (unsigned)a.nx);
 	const int y = a.y0 + (int)(c / (unsigned)a.nx);
 
-	RunUnion<CAP> u;
-	u.init();
+	double2 ulist[CAP];
+	RunUnion<CAP> u(ulist);
 	const int lo = max(-a.J, -y), hi = min(a.J, a.ny - 1 - y);
 	for (int dy = lo; dy <= hi; ++dy) {
 		const double2 s = __ldg(a.mid + ((size_t)(y + dy) * (a.J + 1) + abs(dy)) * a.nx + x);
@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(128) k_brute(BruteArgs a)
 	const int x = (int)(c % (unsigned)a.nx);
 	const int y = (int)(c / (unsigned)a.nx);
 
-	RunUnion<CAP> u;
-	u.init();
+	double2 ulist[CAP];
+	RunUnion<CAP> u(ulist);
 	const int ylo = max(-a.J, -y), yhi = min(a.J, a.ny - 1 - y);
 	const int xlo = max(-a.J, -x), xhi = min(a.J, a.nx - 1 - x);
 	for (int dy = ylo; dy <= yhi; ++dy) {
@@ -244,8 +244,8 @@ __global__ void __launch_bounds__(64) k_dilate2d(Dil2dArgs a)
 	if (tid >= a.nwork) return;
 	const unsigned long long c = a.work ? a.work[tid] : tid;
 	const int i = (int)c;
-	RunUnion<CAP> u;
-	u.init();
+	double2 ulist[CAP];
+	RunUnion<CAP> u(ulist);
 	for (int di = -a.J; di <= a.J; ++di) {
 		const int r = i + di;
 		const double h = __ldg(a.h2 + abs(di));

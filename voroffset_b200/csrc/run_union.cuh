@@ -37,16 +37,50 @@ __device__ __forceinline__ unsigned int slot_pool_count(double2 s)
 	return (unsigned int)__double_as_longlong(s.y);
 }
 
+// Slow path of the running union: insert [s, e] into the sorted disjoint list L[0..n) (n >= 2).
+// Returns the new length, or -1 when the list would outgrow CAP. Kept out of line (and free of any
+// reference to the caller's scalar state) so that the fast-path state stays in registers.
+template <int CAP>
+__device__ __noinline__ int run_union_insert_list(double2 *L, int n, double s, double e)
+{
+	int i = 0;
+	while (i < n && L[i].y < s) ++i;              // intervals entirely below the candidate
+	if (i == n) {                                  // append
+		if (n == CAP) return -1;
+		L[n] = make_double2(s, e);
+		return n + 1;
+	}
+	if (L[i].x > e) {                              // falls into a gap: open a new interval at i
+		if (n == CAP) return -1;
+		for (int k = n; k > i; --k) L[k] = L[k - 1];
+		L[i] = make_double2(s, e);
+		return n + 1;
+	}
+	double ns = fmin(s, L[i].x), ne = fmax(e, L[i].y);
+	int j = i + 1;
+	while (j < n && L[j].x <= e) { ne = fmax(ne, L[j].y); ++j; }
+	L[i] = make_double2(ns, ne);
+	const int drop = j - i - 1;
+	if (drop > 0) {
+		for (int k = j; k < n; ++k) L[k - drop] = L[k];
+		n -= drop;
+	}
+	return n;
+}
+
 // Sorted disjoint closed intervals. One interval lives in registers (the overwhelmingly common case for
-// smooth solids); from two on the list lives in L[] (local memory).
+// smooth solids); from two on the list lives in the caller-provided array L (local memory). The struct
+// only holds scalars and a pointer, so it is scalar-replaced into registers.
 template <int CAP>
 struct RunUnion {
 	double s0, e0;
 	int n;
 	bool overflow;
-	double2 L[CAP];
+	double2 *L;
 
-	__device__ __forceinline__ void init() { n = 0; overflow = false; s0 = 0; e0 = 0; }
+	__device__ __forceinline__ explicit RunUnion(double2 *list) : s0(0), e0(0), n(0), overflow(false), L(list) {}
+
+	__device__ __forceinline__ void init() { n = 0; overflow = false; }
 
 	__device__ __forceinline__ double2 get(int k) const { return n == 1 ? make_double2(s0, e0) : L[k]; }
 
@@ -58,48 +92,18 @@ struct RunUnion {
 				e0 = fmax(e0, e);
 				return;
 			}
-			insert_second(s, e);
+			if (CAP < 2) { overflow = true; return; }
+			if (e < s0) { L[0] = make_double2(s, e); L[1] = make_double2(s0, e0); }
+			else        { L[0] = make_double2(s0, e0); L[1] = make_double2(s, e); }
+			n = 2;
 			return;
 		}
 		if (n == 0) { s0 = s; e0 = e; n = 1; return; }
-		insert_list(s, e);
-	}
-
-	__device__ __noinline__ void insert_second(double s, double e)
-	{
-		if (CAP < 2) { overflow = true; return; }
-		if (e < s0) { L[0] = make_double2(s, e); L[1] = make_double2(s0, e0); }
-		else        { L[0] = make_double2(s0, e0); L[1] = make_double2(s, e); }
-		n = 2;
-	}
-
-	__device__ __noinline__ void insert_list(double s, double e)
-	{
 		if (overflow) return;
-		int i = 0;
-		while (i < n && L[i].y < s) ++i;          // intervals entirely below the candidate
-		if (i == n) {                              // append
-			if (n == CAP) { overflow = true; return; }
-			L[n++] = make_double2(s, e);
-			return;
-		}
-		if (L[i].x > e) {                          // falls into a gap: open a new interval at i
-			if (n == CAP) { overflow = true; return; }
-			for (int k = n; k > i; --k) L[k] = L[k - 1];
-			L[i] = make_double2(s, e);
-			++n;
-			return;
-		}
-		double ns = fmin(s, L[i].x), ne = fmax(e, L[i].y);
-		int j = i + 1;
-		while (j < n && L[j].x <= e) { ne = fmax(ne, L[j].y); ++j; }
-		L[i] = make_double2(ns, ne);
-		const int drop = j - i - 1;
-		if (drop > 0) {
-			for (int k = j; k < n; ++k) L[k - drop] = L[k];
-			n -= drop;
-			if (n == 1) { s0 = L[0].x; e0 = L[0].y; }
-		}
+		const int r = run_union_insert_list<CAP>(L, n, s, e);
+		if (r < 0) { overflow = true; return; }
+		n = r;
+		if (n == 1) { s0 = L[0].x; e0 = L[0].y; }
 	}
 };
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <new>
 #include <string>
@@ -16,6 +17,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "pass1_tile.cuh"
 #include "scan.cuh"
 
 using namespace vo;
@@ -35,6 +37,7 @@ struct vo_ctx {
 	cudaEvent_t mark[8] = {};
 	cudaEvent_t kev[4] = {};          // [0,1] around k_pass1<CAP_FAST>, [2,3] around k_pass2<CAP_FAST>
 	bool kev_valid[2] = {false, false};
+	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
 };
 
 struct vo_dvol {
@@ -363,6 +366,36 @@ int check_radius(vo_ctx *ctx, double R)
 	return VO_OK;
 }
 
+// Tables of the tile kernel: the cap table transposed ([d][j], conflict-free for lanes = classes) and
+// the dominance bound Dmono[d] = min over d' >= d and live classes j of H[j][d'-1] - H[j][d'].
+struct TileTables {
+	vo_ctx *ctx;
+	double *Ht = nullptr, *Dmono = nullptr;
+	explicit TileTables(vo_ctx *c) : ctx(c) {}
+	~TileTables() { dfree(ctx, Ht); dfree(ctx, Dmono); }
+	int upload(const Tables &t)
+	{
+		const int J = t.J, n = J + 1;
+		std::vector<double> ht((size_t)n * n), dm((size_t)J + 2, 0.0);
+		for (int j = 0; j < n; ++j)
+			for (int d = 0; d < n; ++d) ht[(size_t)d * n + j] = t.H[(size_t)j * n + d];
+		const double inf = std::numeric_limits<double>::infinity();
+		dm[J + 1] = inf;
+		for (int d = J; d >= 1; --d) {
+			double m = inf;
+			for (int j = 0; j < n; ++j)
+				if (t.reach[j] >= d) m = std::min(m, t.H[(size_t)j * n + d - 1] - t.H[(size_t)j * n + d]);
+			dm[d] = std::min(m, dm[d + 1]);
+		}
+		VO_TRY(dalloc(ctx, &Ht, (unsigned long long)n * n));
+		VO_TRY(dalloc(ctx, &Dmono, (unsigned long long)J + 2));
+		VO_CUDA(cudaMemcpyAsync(Ht, ht.data(), ht.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(Dmono, dm.data(), dm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaStreamSynchronize(ctx->stream));
+		return VO_OK;
+	}
+};
+
 // ---- 'ours' pass 1 ------------------------------------------------------------------------------------
 int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 {
@@ -370,10 +403,20 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	Tables t = make_tables(R);
 	DevTables dt(ctx);
 	VO_TRY(dt.upload(t));
+	const unsigned long long ncols = (unsigned long long)in->nx * in->ny;
+	// tile kernel (pass1_tile.cuh) whenever its tables and tile fit in shared memory and a row segment's
+	// candidates are expected to fit; otherwise the one-thread-per-(x,y,j) kernel does everything
+	const int TX = t.J <= 32 ? 128 : 64;
+	const int cmax = 1536;
+	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
+	const bool use_tile = t.J <= 63 && ncols > 0 && k_in * (TX + 2 * t.J) <= 0.6 * cmax && !ctx->force_simple_pass1;
+	TileTables tt(ctx);
+	if (use_tile) VO_TRY(tt.upload(t));
+
 	vo_dmid *m = new (std::nothrow) vo_dmid();
 	if (!m) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
 	m->nx = in->nx; m->ny = in->ny; m->J = t.J; m->R = R;
-	const unsigned long long nslots = (unsigned long long)in->nx * in->ny * (t.J + 1);
+	const unsigned long long nslots = ncols * (t.J + 1);
 	int rc = dalloc(ctx, &m->slots, nslots);
 	unsigned long long pool_cap = 65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
@@ -383,7 +426,8 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	if (rc != VO_OK) { vo_dmid_free(ctx, m); return rc; }
 	m->pool_cap = pool_cap;
 	auto bail = [&](int code) { vo_dmid_free(ctx, m); return code; };
-	for (int attempt = 0; attempt < 3; ++attempt) {
+	bool tile_now = use_tile;
+	for (int attempt = 0; attempt < 4; ++attempt) {
 		cudaError_t e = cudaMemsetAsync(ctx->d_ctr, 0, 3 * sizeof(unsigned long long), ctx->stream);
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, cudaGetErrorString(e)));
 		Pass1Args a;
@@ -391,7 +435,22 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		a.off = in->off; a.spans = in->spans; a.H = dt.H; a.reach = dt.reach;
 		a.mid = m->slots; a.pool = m->pool; a.cursor = ctx->d_ctr; a.pool_cap = m->pool_cap;
 		a.redo = rb.rd; a.work = nullptr; a.nwork = nslots;
-		if (nslots) {
+		if (nslots && tile_now) {
+			Pass1TileArgs g;
+			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.TX = TX; g.cmax = cmax;
+			g.tiles_x = (in->nx + TX - 1) / TX;
+			g.off = in->off; g.spans = in->spans; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
+			g.mid = m->slots; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
+			const size_t smem = pass1_tile_smem(t.J, TX, cmax);
+			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e)));
+			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
+			cudaEventRecord(ctx->kev[0], ctx->stream);
+			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, 512, smem, ctx->stream>>>(g);
+			cudaEventRecord(ctx->kev[1], ctx->stream);
+			ctx->kev_valid[0] = true;
+			ctx->launches++;
+		} else if (nslots) {
 			cudaEventRecord(ctx->kev[0], ctx->stream);
 			k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
@@ -404,7 +463,10 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		rc = read_counters(ctx, h);
 		if (rc) return bail(rc);
 		const unsigned int nredo = (unsigned int)h[2];
-		if (nredo > redo_cap) return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
+		if (nredo > redo_cap) {
+			if (tile_now) { tile_now = false; continue; }       // too many oversized tiles: simple kernel for everything
+			return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
+		}
 		if (nredo) {
 			a.work = rb.rd.list; a.nwork = nredo;
 			cudaMemsetAsync(ctx->d_ctr + 2, 0, sizeof(unsigned long long), ctx->stream);
@@ -782,6 +844,16 @@ void vo_destroy(vo_ctx *ctx)
 const char *vo_last_error(const vo_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 void *vo_stream(const vo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t vo_launch_count(const vo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
+{
+	if (!ctx || !key || !value) return VO_ERR_ARG;
+	if (std::strcmp(key, "pass1") == 0) {
+		if (std::strcmp(value, "simple") == 0) { ctx->force_simple_pass1 = true; return VO_OK; }
+		if (std::strcmp(value, "tile") == 0 || std::strcmp(value, "auto") == 0) { ctx->force_simple_pass1 = false; return VO_OK; }
+	}
+	return fail(ctx, VO_ERR_ARG, "unknown option");
+}
 
 int vo_mark(vo_ctx *ctx, int slot)
 {
