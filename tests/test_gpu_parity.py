@@ -273,3 +273,19 @@ def _rows(vol, y0, y1):
     c0, c1 = y0 * vol.nx, y1 * vol.nx
     off = vol.off[c0:c1 + 1].astype(np.int64)
     return (off - off[0]).astype(np.uint32), vol.spans[off[0]:off[-1]]
+
+
+# ---- the reference-side binding (integration/) behind the reference's own base-class pointer ------------
+def test_dropin_subclasses_match_reference_operators():
+    """oracle/_ref/dropin_check drives vor3d::VoronoiMorphoVorPower / BruteForce and the B200-backed
+    subclasses of vor3d::VoronoiMorpho through the same std::unique_ptr<VoronoiMorpho>, on the reference's
+    own CompressedVolume, with the call structure of offset3d.cpp:116-136 (built where /root/reference exists)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "dropin_check")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/dropin_check not built (needs /root/reference at build time)")
+    res = subprocess.run([exe, "56", "5.5"], capture_output=True, text=True, timeout=600)
+    print(res.stdout)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("OK") == 9

@@ -88,8 +88,8 @@ struct RunUnion {
 	{
 		if (n == 1) {
 			if (s <= e0 && e >= s0) {         // touches or overlaps: coalesce in registers
-				s0 = fmin(s0, s);
-				e0 = fmax(e0, e);
+				s0 = (s < s0) ? s : s0;           // plain compare-select: no NaN handling needed here
+				e0 = (e > e0) ? e : e0;
 				return;
 			}
 			if (CAP < 2) { overflow = true; return; }
