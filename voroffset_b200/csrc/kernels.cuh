@@ -126,6 +126,9 @@ struct Pass2Args {
 	int nx, ny, J;          // grid of the mid volume
 	int y0, y1;             // rows produced
 	const double2 *mid;
+	const uint16_t *flags;  // [ny*nx] per mid column: classes j < (flags & 0xff) are needed by the consumer rows
+	                        // above (y - j), classes j < (flags >> 8) by the rows below (y + j); every other
+	                        // slot was never written by pass 1 and must not be read (pass1_tile.cuh)
 	const double2 *pool;
 	Stage st;
 	Redo redo;
@@ -146,7 +149,12 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 	RunUnion<CAP> u(ulist);
 	const int lo = max(-a.J, -y), hi = min(a.J, a.ny - 1 - y);
 	for (int dy = lo; dy <= hi; ++dy) {
-		const double2 s = __ldg(a.mid + ((size_t)(y + dy) * (a.J + 1) + abs(dy)) * a.nx + x);
+		const int j = abs(dy);
+		const unsigned int f = __ldg(a.flags + (size_t)(y + dy) * a.nx + x);
+		// this output is a consumer "above" row y+dy when dy > 0, "below" when dy < 0
+		const int need = dy > 0 ? (int)(f & 0xffu) : dy < 0 ? (int)(f >> 8) : (int)max(f & 0xffu, f >> 8);
+		if (j >= need) continue;
+		const double2 s = __ldg(a.mid + ((size_t)(y + dy) * (a.J + 1) + j) * a.nx + x);
 		if (s.x <= s.y) u.insert(s.x, s.y);
 		else if (slot_is_pool(s)) {
 			const unsigned long long base = slot_pool_base(s);

@@ -1,79 +1,132 @@
-// 'ours', pass 1, tile kernel: one CTA per (row y, tile of TX output columns).
+// 'ours', pass 1, tile kernel with exact 2D dominance pruning.
 //
-// What it computes is exactly what k_pass1 (kernels.cuh) computes - for every output column x of the row
-// and every radius class j the union over |dx| <= reach[j] of the neighbours' intervals grown by
-// H[j][|dx|] - but organised for the machine:
+// What it computes is what k_pass1 (kernels.cuh) computes - for an output column x of row y and a radius
+// class j the union over |dx| <= reach[j] of the neighbours' intervals grown by H[j][|dx|] - but only
+// for the (candidate, class) pairs that can still matter, and only for the classes some consumer of
+// pass 2 will read:
 //
-//  * the row segment [x0-J, x0+TX+J) is staged ONCE in shared memory as a flat candidate array
-//    (interval, segment column), instead of every (x, j) thread walking the CSR on its own;
-//  * a warp owns one output column at a time and its LANES ARE THE RADIUS CLASSES: a candidate is
-//    broadcast from shared memory and lane j adds its own cap Ht[|dx|][j] (conflict-free row of the
-//    transposed table), so the 33 classes of R = 32 cost one instruction stream;
-//  * candidates that cannot matter are skipped with an EXACT dominance test (below), found 32 at a
-//    time with a ballot;
-//  * results are collected in a shared-memory tile [j][x] and written to the mid volume as full
-//    128-byte lines.
+//  * the row segment [x0-J, x0+TX+J) is staged once in shared memory as a flat candidate array
+//    (interval, segment column, thresholds) straight from the CSR;
+//  * x-dominance (per candidate, per side): if the neighbouring column one step closer to the output has
+//    an interval q with  max(a_q - a_p, b_p - b_q) <= Dmono[d],  Dmono[d] = min over d' >= d and live
+//    classes j of H[j][d'-1] - H[j][d'],  then for EVERY class q's capped interval contains p's for all
+//    outputs at distance >= d on that side, and p is skipped there;
+//  * y-dominance (k_ythresh, per interval, per side): the same test against the column one row closer to
+//    the consumer row, with  Emono[j] = min over j' >= j and d <= reach[j'] of H[j'-1][d] - H[j'][d]:
+//    the consumer at row distance >= Ty on that side is served by the neighbouring row's class j-1 slot,
+//    so p takes part only in the classes j < max(Ty_up, Ty_dn);
+//  * a thread owns one output column: it collects its surviving candidates (a short list in shared
+//    memory), then evaluates the classes 0 .. Tmax-1 only, where Tmax is the largest class any survivor
+//    still needs; the two per-side maxima are published as flags so that pass 2 skips every other slot
+//    without reading it (the mid volume stays unwritten there);
+//  * lanes run along x: slot writes are full 128-byte lines.
 //
-// Exact pruning. Let p be an interval of column c and q an interval of the neighbouring column c' that
-// is one step closer to the output column x (|c'-x| = d-1, |c-x| = d). For class j the two candidates
-// are [a_p - H_j(d), b_p + H_j(d)] and [a_q - H_j(d-1), b_q + H_j(d-1)], and q is alive whenever p is.
-// With D_j(d) = H_j(d-1) - H_j(d) > 0, q's candidate contains p's for EVERY class as soon as
-//     max(a_q - a_p, b_p - b_q) <= min_j D_j(d),
-// and then p can be dropped without changing the union (containment is decided on the same table
-// values the candidates are built from; fp64 subtraction is monotone, so containment of the real
-// numbers carries over to the rounded endpoints). The host passes Dmono[d] = min over d' >= d and all
-// live classes of D_j(d') (non-decreasing in d), so "dominated at distance d" implies "dominated at
-// every larger distance" and one threshold byte per candidate and side suffices. Dominance is
-// transitive and distances strictly decrease along a chain, so every dropped candidate is contained in
-// a kept one. This plays the role of the reference's Voronoi pruning (Voronoi2D.cpp:329-586: a seed is
-// retired once its cell no longer reaches the sweep line) but is conservative, branch-light and
-// identical for all classes. On the torus workloads it keeps ~7 of ~38 candidates per column (R = 32).
+// Why this is exact: containment is decided on the same table values the candidates are built from and
+// fp64 subtraction is monotone, so "q's capped interval contains p's" carries over to the rounded
+// endpoints; every dropped pair is contained in a pair one lattice step (in x or in y) closer to the
+// consumer, |dx| + |dy| strictly decreases along such a chain, and the pair at (0,0) is never dropped -
+// so the union every consumer sees is unchanged, bit for bit. This is the role the reference's
+// Voronoi-vertex / power-diagram events play (Voronoi2D.cpp:329-586, SeparatePower2D.cpp:118-293:
+// seeds are retired once their cell no longer reaches the sweep line) in a conservative, data-parallel
+// form. On the C5 torus it keeps ~7 of ~38 candidates per column and ~13 of 33 classes.
 #pragma once
 #include "kernels.cuh"
 
 namespace vo {
 
-struct Pass1TileArgs {
-	int nx, ny, J, TX, cmax, tiles_x;
+constexpr int P1_TX = 128;      // output columns (= threads) per CTA
+constexpr int P1_LCAP = 32;     // survivors kept per output column before falling back
+
+// ---- y-direction dominance thresholds, one thread per column ----------------------------------------
+struct YThreshArgs {
+	int nx, ny, J;
 	const uint32_t *off;
 	const double2 *spans;
-	const double *Ht;       // (J+1)*(J+1), transposed cap table: Ht[d*(J+1) + j] = H[j][d] (-1 = out of reach)
+	const double *Emono;    // J+2: Emono[j], j = 1..J; Emono[J+1] = +inf
+	uint16_t *ty;           // per interval: Ty_up | Ty_dn << 8, each in [1, J+1]
+};
+
+__device__ __forceinline__ int first_ge(const double *tab, int J, double need)
+{
+	int lo = 1, hi = J + 1;                       // tab is non-decreasing, tab[J+1] = +inf
+	while (lo < hi) { const int mid = (lo + hi) >> 1; if (tab[mid] >= need) hi = mid; else lo = mid + 1; }
+	return lo;
+}
+
+__global__ void __launch_bounds__(256) k_ythresh(YThreshArgs a)
+{
+	extern __shared__ double s_E[];
+	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) s_E[i] = a.Emono[i];
+	__syncthreads();
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= (unsigned long long)a.nx * a.ny) return;
+	const uint32_t o0 = a.off[c], o1 = a.off[c + 1];
+	if (o0 == o1) return;
+	const int y = (int)(c / (unsigned)a.nx);
+	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	uint32_t u0 = 0, u1 = 0, d0 = 0, d1 = 0;
+	if (y > 0) { u0 = a.off[c - a.nx]; u1 = a.off[c - a.nx + 1]; }
+	if (y < a.ny - 1) { d0 = a.off[c + a.nx]; d1 = a.off[c + a.nx + 1]; }
+	for (uint32_t k = o0; k < o1; ++k) {
+		const double2 p = a.spans[k];
+		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
+		double need_up = inf, need_dn = inf;
+		for (uint32_t q = u0; q < u1; ++q) { const double2 v = a.spans[q]; need_up = fmin(need_up, fmax(v.x - p.x, p.y - v.y)); }
+		for (uint32_t q = d0; q < d1; ++q) { const double2 v = a.spans[q]; need_dn = fmin(need_dn, fmax(v.x - p.x, p.y - v.y)); }
+		const int tu = first_ge(s_E, a.J, need_up + m), td = first_ge(s_E, a.J, need_dn + m);
+		a.ty[k] = (uint16_t)(tu | (td << 8));
+	}
+}
+
+// ---- pass 1 ------------------------------------------------------------------------------------------
+struct Pass1TileArgs {
+	int nx, ny, J, cmax, tiles_x;
+	const uint32_t *off;
+	const double2 *spans;
+	const uint16_t *ty;     // k_ythresh output
+	const double *H;        // (J+1)*(J+1), [j][d] (-1 = out of reach)
 	const int *reach;       // J+1
-	const double *Dmono;    // J+2: Dmono[d], d = 1..J; Dmono[J+1] = +inf
+	const double *Dmono;    // J+2
 	double2 *mid;
+	uint16_t *flags;        // [ny*nx]: classes needed by the consumers above (low byte) / below (high byte)
 	double2 *pool;
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
 };
 
-__host__ __device__ inline size_t pass1_tile_smem(int J, int TX, int cmax)
+__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax)
 {
-	const size_t JP = (size_t)J + 1, SEG = (size_t)TX + 2 * J;
+	const size_t JP = (size_t)J + 1, SEG = (size_t)P1_TX + 2 * J;
 	size_t b = 0;
-	b += JP * TX * sizeof(double2);          // out tile
-	b += (size_t)cmax * sizeof(double2);     // candidates
-	b += JP * JP * sizeof(double);           // Ht
-	b += (JP + 1) * sizeof(double);          // Dmono
-	b += ((SEG + 1 + 1) & ~(size_t)1) * sizeof(uint32_t); // segment offsets (even count keeps alignment)
-	b += (size_t)cmax * sizeof(uint32_t);    // per candidate: first surviving output | width << 8 | column << 16
-	return b + 16;
+	b += (size_t)cmax * sizeof(double2);                    // candidates
+	b += JP * JP * sizeof(double);                          // H
+	b += (JP + 1) * sizeof(double);                         // Dmono
+	b += (size_t)P1_LCAP * P1_TX * sizeof(uint32_t);        // survivor lists [s][thread]
+	b += ((SEG + 2) & ~(size_t)1) * sizeof(uint32_t);       // segment offsets
+	b += (size_t)cmax * sizeof(uint32_t);                   // first surviving output | width << 8 | column << 16
+	b += ((JP + 1) & ~(size_t)1) * sizeof(int);             // reach
+	b += (size_t)cmax * sizeof(uint16_t);                   // y thresholds
+	b += JP;                                                // largest class within reach of a distance
+	return b + 32;
 }
 
 template <int CAP>
-__global__ void __launch_bounds__(512) k_pass1_tile(Pass1TileArgs a)
+__global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int J = a.J, JP = J + 1, TX = a.TX, SEG = TX + 2 * J;
-	double2 *s_out = reinterpret_cast<double2 *>(smem_raw);
-	double2 *s_cand = s_out + (size_t)JP * TX;
-	double *s_Ht = reinterpret_cast<double *>(s_cand + a.cmax);
-	double *s_D = s_Ht + (size_t)JP * JP;
-	uint32_t *s_off = reinterpret_cast<uint32_t *>(s_D + JP + 1);
-	uint32_t *s_sv = s_off + ((SEG + 2) & ~1);   // per candidate: first surviving output | width << 8 | column << 16
+	const int J = a.J, JP = J + 1, TX = P1_TX, SEG = TX + 2 * J;
+	double2 *s_cand = reinterpret_cast<double2 *>(smem_raw);
+	double *s_H = reinterpret_cast<double *>(s_cand + a.cmax);
+	double *s_D = s_H + (size_t)JP * JP;
+	uint32_t *s_list = reinterpret_cast<uint32_t *>(s_D + JP + 1);
+	uint32_t *s_off = s_list + (size_t)P1_LCAP * TX;
+	uint32_t *s_sv = s_off + ((SEG + 2) & ~1);
+	int *s_reach = reinterpret_cast<int *>(s_sv + a.cmax);
+	uint16_t *s_ty = reinterpret_cast<uint16_t *>(s_reach + ((JP + 1) & ~1));
+	uint8_t *s_jmax = reinterpret_cast<uint8_t *>(s_ty + a.cmax);
 
 	const int tid = threadIdx.x, nthr = blockDim.x;
-	const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
 	const int y = blockIdx.x / a.tiles_x;
 	const int x0 = (blockIdx.x % a.tiles_x) * TX;
 	const int txe = min(TX, a.nx - x0);
@@ -88,28 +141,32 @@ __global__ void __launch_bounds__(512) k_pass1_tile(Pass1TileArgs a)
 	const uint32_t base = s_off[0];
 	const int ncand = (int)(s_off[SEG] - base);
 	if (ncand > a.cmax) {                                   // oversized segment: leave the tile to k_pass1
+		if (tid < txe) a.flags[rowbase + x0 + tid] = (uint16_t)(JP | (JP << 8));
 		for (int idx = tid; idx < JP * txe; idx += nthr) {
 			const int j = idx / txe, xi = idx % txe;
 			redo_push(a.redo, ((unsigned long long)y * JP + j) * a.nx + x0 + xi);
 		}
 		return;
 	}
-	if (ncand == 0) {                                       // nothing in reach: the whole tile is empty
-		const double2 e = slot_empty();
-		for (int idx = tid; idx < JP * txe; idx += nthr) {
-			const int j = idx / txe, xi = idx % txe;
-			a.mid[((size_t)y * JP + j) * a.nx + x0 + xi] = e;
-		}
+	if (ncand == 0) {                                       // nothing in reach: no slot of the tile is needed
+		if (tid < txe) a.flags[rowbase + x0 + tid] = 0;
 		return;
 	}
-	for (int i = tid; i < JP * JP; i += nthr) s_Ht[i] = __ldg(a.Ht + i);
+	for (int i = tid; i < JP * JP; i += nthr) s_H[i] = __ldg(a.H + i);
 	for (int i = tid; i < JP + 1; i += nthr) s_D[i] = __ldg(a.Dmono + i);
-	for (int k = tid; k < ncand; k += nthr) s_cand[k] = __ldg(a.spans + base + k);
+	for (int i = tid; i < JP; i += nthr) s_reach[i] = __ldg(a.reach + i);
+	for (int k = tid; k < ncand; k += nthr) { s_cand[k] = __ldg(a.spans + base + k); s_ty[k] = __ldg(a.ty + base + k); }
 	for (int i = tid; i < SEG; i += nthr)
 		for (uint32_t k = s_off[i] - base; k < s_off[i + 1] - base; ++k) s_sv[k] = (uint32_t)i << 16;
 	__syncthreads();
+	// largest class whose reach covers distance d (reach is non-increasing in j)
+	for (int d = tid; d < JP; d += nthr) {
+		int jm = 0;
+		for (int j = 0; j < JP; ++j) if (s_reach[j] >= d) jm = j;
+		s_jmax[d] = (uint8_t)jm;
+	}
 
-	// ---- phase 1: dominance thresholds ----------------------------------------------------------
+	// ---- phase 1: x-dominance thresholds ----------------------------------------------------------
 	for (int k = tid; k < ncand; k += nthr) {
 		const int i = (int)(s_sv[k] >> 16);
 		const double2 p = s_cand[k];
@@ -121,78 +178,73 @@ __global__ void __launch_bounds__(512) k_pass1_tile(Pass1TileArgs a)
 		if (i < SEG - 1)
 			for (uint32_t q = s_off[i + 1] - base; q < s_off[i + 2] - base; ++q)
 				need_lo = fmin(need_lo, fmax(s_cand[q].x - p.x, p.y - s_cand[q].y));
-		need_hi += m;
-		need_lo += m;
-		// first d in [1, J] with Dmono[d] >= need (Dmono is non-decreasing, Dmono[J+1] = +inf)
-		int lo = 1, hi = JP;
-		while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_D[mid] >= need_hi) hi = mid; else lo = mid + 1; }
-		const int t_hi = lo;           // dominated for outputs at distance >= t_hi on the left of the candidate
-		lo = 1; hi = JP;
-		while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_D[mid] >= need_lo) hi = mid; else lo = mid + 1; }
-		const int t_lo = lo;           // ... on the right
-		// the candidate survives for the outputs ix in [i - (t_hi-1), i + (t_lo-1)] (segment coordinates);
-		// packed as first | width << 8 | column << 16
+		const int t_hi = first_ge(s_D, J, need_hi + m);   // dominated for outputs at distance >= t_hi on the left
+		const int t_lo = first_ge(s_D, J, need_lo + m);   // ... on the right
+		// survives for the outputs ix in [i - (t_hi-1), i + (t_lo-1)] (segment coordinates)
 		const int first = max(i - (t_hi - 1), 0);
 		const int last = min(i + (t_lo - 1), SEG - 1);
 		s_sv[k] = (uint32_t)first | ((uint32_t)(last - first) << 8) | ((uint32_t)i << 16);
 	}
 	__syncthreads();
+	if (tid >= txe) return;
 
-	// ---- phase 2: one warp per output column, lanes = radius classes ----------------------------
-	double2 ulist[CAP];
-	for (int jbase = 0; jbase <= J; jbase += 32) {
-		const int j = jbase + lane;
-		const bool active = j <= J;
-		const int Xj = active ? __ldg(a.reach + j) : -1;
-		const int Xmax = __shfl_sync(0xffffffffu, Xj, 0);       // classes are ordered by decreasing reach
-		const double *Htj = s_Ht + (active ? j : 0);
-		for (int xi = warp; xi < txe; xi += nwarp) {
-			const int ix = xi + J;
-			// candidates within the largest reach of this round of classes
-			const int kb = (int)(s_off[ix - Xmax] - base), ke = (int)(s_off[ix + Xmax + 1] - base);
-			RunUnion<CAP> u(ulist);
-			for (int kk = kb; kk < ke; kk += 32) {
-				const int k = kk + lane;
-				bool sv = false;
-				if (k < ke) {
-					const uint32_t w = s_sv[k];
-					sv = (uint32_t)(ix - (int)(w & 0xffu)) <= ((w >> 8) & 0xffu);
-				}
-				unsigned m = __ballot_sync(0xffffffffu, sv);
-				while (m) {
-					const int k2 = kk + __ffs(m) - 1;
-					m &= m - 1;
-					const int d = abs((int)(s_sv[k2] >> 16) - ix);
-					if (d <= Xj) {
-						const double2 ab = s_cand[k2];
-						const double h = Htj[d * JP];
-						u.insert(ab.x - h, ab.y + h);
-					}
-				}
-			}
-			if (active) {
-				double2 out;
-				if (u.overflow) {
-					redo_push(a.redo, ((unsigned long long)y * JP + j) * a.nx + x0 + xi);
-					out = slot_empty();
-				} else if (u.n == 0) out = slot_empty();
-				else if (u.n == 1) out = make_double2(u.s0, u.e0);
-				else {
-					const unsigned long long pb = atomicAdd(a.cursor, (unsigned long long)u.n);
-					if (pb + u.n <= a.pool_cap)
-						for (int q = 0; q < u.n; ++q) a.pool[pb + q] = u.L[q];
-					out = slot_pool(pb, (unsigned int)u.n);
-				}
-				s_out[(size_t)j * TX + xi] = out;
-			}
+	// ---- phase 2: one thread per output column ------------------------------------------------------
+	const int xi = tid, ix = xi + J;
+	const int kb = (int)(s_off[ix - J] - base), ke = (int)(s_off[ix + J + 1] - base);
+	int S = 0, Fup = 0, Fdn = 0;
+	for (int k = kb; k < ke; ++k) {
+		const uint32_t w = s_sv[k];
+		if ((uint32_t)(ix - (int)(w & 0xffu)) <= ((w >> 8) & 0xffu)) {
+			const int d = abs((int)(w >> 16) - ix);
+			const int jm = (int)s_jmax[d] + 1;            // classes that can reach this distance
+			const uint32_t ty = s_ty[k];
+			const int tu = min((int)(ty & 0xffu), jm), td = min((int)(ty >> 8), jm);
+			Fup = max(Fup, tu);
+			Fdn = max(Fdn, td);
+			if (S < P1_LCAP) s_list[S * TX + xi] = (uint32_t)k | ((uint32_t)d << 12) | ((uint32_t)max(tu, td) << 20);
+			++S;
 		}
 	}
-	__syncthreads();
-
-	// ---- phase 3: coalesced store of the tile ---------------------------------------------------
-	for (int idx = tid; idx < JP * TX; idx += nthr) {
-		const int j = idx / TX, xi = idx % TX;
-		if (xi < txe) a.mid[((size_t)y * JP + j) * a.nx + x0 + xi] = s_out[idx];
+	a.flags[rowbase + x0 + xi] = (uint16_t)(Fup | (Fdn << 8));
+	const int Tmax = max(Fup, Fdn);
+	// more survivors than the list holds (steep walls, many layers): re-scan the candidate range per class
+	const bool direct = S > P1_LCAP;
+	const int niter = direct ? ke - kb : S;
+	double2 ulist[CAP];
+	for (int j = 0; j < Tmax; ++j) {
+		const int Xj = s_reach[j];
+		const double *Hrow = s_H + (size_t)j * JP;
+		RunUnion<CAP> u(ulist);
+		for (int s = 0; s < niter; ++s) {
+			uint32_t e;
+			if (!direct) e = s_list[s * TX + xi];
+			else {
+				const int k = kb + s;
+				const uint32_t w = s_sv[k];
+				if ((uint32_t)(ix - (int)(w & 0xffu)) > ((w >> 8) & 0xffu)) continue;
+				const int dd = abs((int)(w >> 16) - ix);
+				const uint32_t ty = s_ty[k];
+				e = (uint32_t)k | ((uint32_t)dd << 12) | ((uint32_t)max(ty & 0xffu, ty >> 8) << 20);   // d <= Xj below caps the class
+			}
+			const int d = (int)((e >> 12) & 0xffu);
+			if ((int)(e >> 20) > j && d <= Xj) {
+				const double2 ab = s_cand[e & 0xfffu];
+				const double h = Hrow[d];
+				u.insert(ab.x - h, ab.y + h);
+			}
+		}
+		const unsigned long long slot = ((unsigned long long)y * JP + j) * a.nx + x0 + xi;
+		double2 out;
+		if (u.overflow) { redo_push(a.redo, slot); out = slot_empty(); }
+		else if (u.n == 0) out = slot_empty();
+		else if (u.n == 1) out = make_double2(u.s0, u.e0);
+		else {
+			const unsigned long long pb = atomicAdd(a.cursor, (unsigned long long)u.n);
+			if (pb + u.n <= a.pool_cap)
+				for (int q = 0; q < u.n; ++q) a.pool[pb + q] = u.L[q];
+			out = slot_pool(pb, (unsigned int)u.n);
+		}
+		a.mid[slot] = out;
 	}
 }
 

@@ -37,6 +37,7 @@ struct vo_ctx {
 	cudaEvent_t mark[8] = {};
 	cudaEvent_t kev[4] = {};          // [0,1] around k_pass1<CAP_FAST>, [2,3] around k_pass2<CAP_FAST>
 	bool kev_valid[2] = {false, false};
+	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
 };
 
@@ -52,6 +53,7 @@ struct vo_dmid {
 	double R = 0;
 	double2 *slots = nullptr;
 	double2 *pool = nullptr;
+	uint16_t *flags = nullptr;      // per mid column: classes needed by the consumer rows above / below
 	uint64_t pool_cap = 0, pool_used = 0;
 };
 
@@ -366,31 +368,36 @@ int check_radius(vo_ctx *ctx, double R)
 	return VO_OK;
 }
 
-// Tables of the tile kernel: the cap table transposed ([d][j], conflict-free for lanes = classes) and
-// the dominance bound Dmono[d] = min over d' >= d and live classes j of H[j][d'-1] - H[j][d'].
+// Dominance bounds of the tile kernel (pass1_tile.cuh), from the same cap table the candidates use:
+//   Dmono[d] = min over d' >= d and classes j with reach[j] >= d' of H[j][d'-1] - H[j][d']   (x direction)
+//   Emono[j] = min over j' >= j and d <= reach[j'] of H[j'-1][d] - H[j'][d]                    (y direction)
+// both non-decreasing in their index, entry J+1 = +inf.
 struct TileTables {
 	vo_ctx *ctx;
-	double *Ht = nullptr, *Dmono = nullptr;
+	double *Dmono = nullptr, *Emono = nullptr;
 	explicit TileTables(vo_ctx *c) : ctx(c) {}
-	~TileTables() { dfree(ctx, Ht); dfree(ctx, Dmono); }
+	~TileTables() { dfree(ctx, Dmono); dfree(ctx, Emono); }
 	int upload(const Tables &t)
 	{
 		const int J = t.J, n = J + 1;
-		std::vector<double> ht((size_t)n * n), dm((size_t)J + 2, 0.0);
-		for (int j = 0; j < n; ++j)
-			for (int d = 0; d < n; ++d) ht[(size_t)d * n + j] = t.H[(size_t)j * n + d];
+		std::vector<double> dm((size_t)J + 2, 0.0), em((size_t)J + 2, 0.0);
 		const double inf = std::numeric_limits<double>::infinity();
-		dm[J + 1] = inf;
+		dm[J + 1] = em[J + 1] = inf;
 		for (int d = J; d >= 1; --d) {
 			double m = inf;
 			for (int j = 0; j < n; ++j)
 				if (t.reach[j] >= d) m = std::min(m, t.H[(size_t)j * n + d - 1] - t.H[(size_t)j * n + d]);
 			dm[d] = std::min(m, dm[d + 1]);
 		}
-		VO_TRY(dalloc(ctx, &Ht, (unsigned long long)n * n));
+		for (int j = J; j >= 1; --j) {
+			double m = inf;
+			for (int d = 0; d <= t.reach[j]; ++d) m = std::min(m, t.H[(size_t)(j - 1) * n + d] - t.H[(size_t)j * n + d]);
+			em[j] = std::min(m, em[j + 1]);
+		}
 		VO_TRY(dalloc(ctx, &Dmono, (unsigned long long)J + 2));
-		VO_CUDA(cudaMemcpyAsync(Ht, ht.data(), ht.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		VO_TRY(dalloc(ctx, &Emono, (unsigned long long)J + 2));
 		VO_CUDA(cudaMemcpyAsync(Dmono, dm.data(), dm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(Emono, em.data(), em.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 		VO_CUDA(cudaStreamSynchronize(ctx->stream));
 		return VO_OK;
 	}
@@ -406,10 +413,12 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	const unsigned long long ncols = (unsigned long long)in->nx * in->ny;
 	// tile kernel (pass1_tile.cuh) whenever its tables and tile fit in shared memory and a row segment's
 	// candidates are expected to fit; otherwise the one-thread-per-(x,y,j) kernel does everything
-	const int TX = t.J <= 32 ? 128 : 64;
-	const int cmax = 1536;
+	const int TX = P1_TX;
+	const int cmax = 1024;
 	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
-	const bool use_tile = t.J <= 63 && ncols > 0 && k_in * (TX + 2 * t.J) <= 0.6 * cmax && !ctx->force_simple_pass1;
+	// (small problems do not fill the machine with one thread per column: the simple kernel has J+1 times more threads)
+	const bool big = ncols * (unsigned long long)(t.J + 1) >= (2ull << 20) || ctx->force_tile_pass1;
+	const bool use_tile = t.J <= 63 && ncols > 0 && k_in * (TX + 2 * t.J) <= 0.6 * cmax && big && !ctx->force_simple_pass1;
 	TileTables tt(ctx);
 	if (use_tile) VO_TRY(tt.upload(t));
 
@@ -420,6 +429,9 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	int rc = dalloc(ctx, &m->slots, nslots);
 	unsigned long long pool_cap = 65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
+	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, ncols);
+	Tmp<uint16_t> ty(ctx);
+	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &ty.p, in->nspans);
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nslots, 1ull), 1ull << 22);
 	if (rc == VO_OK) rc = rb.alloc(redo_cap);
@@ -436,21 +448,27 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		a.mid = m->slots; a.pool = m->pool; a.cursor = ctx->d_ctr; a.pool_cap = m->pool_cap;
 		a.redo = rb.rd; a.work = nullptr; a.nwork = nslots;
 		if (nslots && tile_now) {
+			YThreshArgs yt;
+			yt.nx = in->nx; yt.ny = in->ny; yt.J = t.J; yt.off = in->off; yt.spans = in->spans; yt.Emono = tt.Emono; yt.ty = ty.p;
+			k_ythresh<<<blocks_for(ncols, 256), 256, (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(yt);
+			ctx->launches++;
 			Pass1TileArgs g;
-			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.TX = TX; g.cmax = cmax;
+			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.cmax = cmax;
 			g.tiles_x = (in->nx + TX - 1) / TX;
-			g.off = in->off; g.spans = in->spans; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
-			g.mid = m->slots; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
-			const size_t smem = pass1_tile_smem(t.J, TX, cmax);
+			g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.H = dt.H; g.reach = dt.reach; g.Dmono = tt.Dmono;
+			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
+			const size_t smem = pass1_tile_smem(t.J, cmax);
 			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e)));
 			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
 			cudaEventRecord(ctx->kev[0], ctx->stream);
-			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, 512, smem, ctx->stream>>>(g);
+			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, P1_TX, smem, ctx->stream>>>(g);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
 			ctx->launches++;
 		} else if (nslots) {
+			// every class of every column is computed: all flag bytes = J + 1
+			cudaMemsetAsync(m->flags, t.J + 1, ncols * sizeof(uint16_t), ctx->stream);
 			cudaEventRecord(ctx->kev[0], ctx->stream);
 			k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
@@ -493,7 +511,7 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
 	if (y0 < 0 || y1 > m->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "pass 2 row range outside the mid volume");
 	Pass2Args a;
 	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = y0; a.y1 = y1;
-	a.mid = m->slots; a.pool = m->pool;
+	a.mid = m->slots; a.flags = m->flags; a.pool = m->pool;
 	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
@@ -849,8 +867,9 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 {
 	if (!ctx || !key || !value) return VO_ERR_ARG;
 	if (std::strcmp(key, "pass1") == 0) {
-		if (std::strcmp(value, "simple") == 0) { ctx->force_simple_pass1 = true; return VO_OK; }
-		if (std::strcmp(value, "tile") == 0 || std::strcmp(value, "auto") == 0) { ctx->force_simple_pass1 = false; return VO_OK; }
+		if (std::strcmp(value, "simple") == 0) { ctx->force_simple_pass1 = true; ctx->force_tile_pass1 = false; return VO_OK; }
+		if (std::strcmp(value, "tile") == 0) { ctx->force_simple_pass1 = false; ctx->force_tile_pass1 = true; return VO_OK; }
+		if (std::strcmp(value, "auto") == 0) { ctx->force_simple_pass1 = false; ctx->force_tile_pass1 = false; return VO_OK; }
 	}
 	return fail(ctx, VO_ERR_ARG, "unknown option");
 }
@@ -1087,6 +1106,7 @@ void vo_dmid_free(vo_ctx *ctx, vo_dmid *m)
 	DeviceGuard g(ctx->device);
 	dfree(ctx, m->slots);
 	dfree(ctx, m->pool);
+	dfree(ctx, m->flags);
 	delete m;
 }
 
