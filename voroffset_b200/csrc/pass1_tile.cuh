@@ -19,6 +19,10 @@
 //    memory), then evaluates the classes 0 .. Tmax-1 only, where Tmax is the largest class any survivor
 //    still needs; the two per-side maxima are published as flags so that pass 2 skips every other slot
 //    without reading it (the mid volume stays unwritten there);
+//  * classes are evaluated EIGHT AT A TIME in registers: a survivor is loaded once, its eight caps come
+//    from one row of the transposed table with 128-bit shared loads, and the eight (lo, hi) running
+//    unions are independent instruction streams (no dependent load chain per candidate). A class whose
+//    union is not a single interval is flagged and redone by the general list-based path;
 //  * lanes run along x: slot writes are full 128-byte lines.
 //
 // Why this is exact: containment is decided on the same table values the candidates are built from and
@@ -35,7 +39,8 @@
 namespace vo {
 
 constexpr int P1_TX = 128;      // output columns (= threads) per CTA
-constexpr int P1_LCAP = 32;     // survivors kept per output column before falling back
+constexpr int P1_LCAP = 32;     // survivors listed per output column (more: the candidate range is re-scanned)
+constexpr int P1_CB = 8;        // classes evaluated together in registers
 
 // ---- y-direction dominance thresholds, one thread per column ----------------------------------------
 struct YThreshArgs {
@@ -84,7 +89,7 @@ struct Pass1TileArgs {
 	const uint32_t *off;
 	const double2 *spans;
 	const uint16_t *ty;     // k_ythresh output
-	const double *H;        // (J+1)*(J+1), [j][d] (-1 = out of reach)
+	const double *Ht;       // (J+1) rows of JPP = roundup(J+1, 8) doubles: Ht[d*JPP + j] = H[j][d]
 	const int *reach;       // J+1
 	const double *Dmono;    // J+2
 	double2 *mid;
@@ -93,19 +98,24 @@ struct Pass1TileArgs {
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
+	const unsigned int *tiles; // NULL: all tiles; else the tile ids to run (second launch with a larger cmax)
+	unsigned int *big_tiles;   // tiles whose segment holds more than cmax candidates (NULL: send them to redo)
+	unsigned int *big_count;
 };
+
+__host__ __device__ inline int pass1_jpp(int J) { return (J + 1 + P1_CB - 1) / P1_CB * P1_CB; }
 
 __host__ __device__ inline size_t pass1_tile_smem(int J, int cmax)
 {
 	const size_t JP = (size_t)J + 1, SEG = (size_t)P1_TX + 2 * J;
 	size_t b = 0;
 	b += (size_t)cmax * sizeof(double2);                    // candidates
-	b += JP * JP * sizeof(double);                          // H
+	b += JP * pass1_jpp(J) * sizeof(double);                // Ht
 	b += (JP + 1) * sizeof(double);                         // Dmono
-	b += (size_t)P1_LCAP * P1_TX * sizeof(uint32_t);        // survivor lists [s][thread]
 	b += ((SEG + 2) & ~(size_t)1) * sizeof(uint32_t);       // segment offsets
-	b += (size_t)cmax * sizeof(uint32_t);                   // first surviving output | width << 8 | column << 16
+	b += (size_t)cmax * sizeof(uint32_t);                   // first surviving output | width << 8 | column << 16 | T << 24
 	b += ((JP + 1) & ~(size_t)1) * sizeof(int);             // reach
+	b += (size_t)P1_LCAP * P1_TX * sizeof(uint16_t);        // survivor lists [s][thread]
 	b += (size_t)cmax * sizeof(uint16_t);                   // y thresholds
 	b += JP;                                                // largest class within reach of a distance
 	return b + 32;
@@ -115,20 +125,21 @@ template <int CAP>
 __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int J = a.J, JP = J + 1, TX = P1_TX, SEG = TX + 2 * J;
+	const int J = a.J, JP = J + 1, JPP = pass1_jpp(J), TX = P1_TX, SEG = TX + 2 * J;
 	double2 *s_cand = reinterpret_cast<double2 *>(smem_raw);
-	double *s_H = reinterpret_cast<double *>(s_cand + a.cmax);
-	double *s_D = s_H + (size_t)JP * JP;
-	uint32_t *s_list = reinterpret_cast<uint32_t *>(s_D + JP + 1);
-	uint32_t *s_off = s_list + (size_t)P1_LCAP * TX;
+	double *s_Ht = reinterpret_cast<double *>(s_cand + a.cmax);
+	double *s_D = s_Ht + (size_t)JP * JPP;
+	uint32_t *s_off = reinterpret_cast<uint32_t *>(s_D + JP + 1);
 	uint32_t *s_sv = s_off + ((SEG + 2) & ~1);
 	int *s_reach = reinterpret_cast<int *>(s_sv + a.cmax);
-	uint16_t *s_ty = reinterpret_cast<uint16_t *>(s_reach + ((JP + 1) & ~1));
+	uint16_t *s_list = reinterpret_cast<uint16_t *>(s_reach + ((JP + 1) & ~1));
+	uint16_t *s_ty = s_list + (size_t)P1_LCAP * TX;
 	uint8_t *s_jmax = reinterpret_cast<uint8_t *>(s_ty + a.cmax);
 
 	const int tid = threadIdx.x, nthr = blockDim.x;
-	const int y = blockIdx.x / a.tiles_x;
-	const int x0 = (blockIdx.x % a.tiles_x) * TX;
+	const unsigned int tile = a.tiles ? a.tiles[blockIdx.x] : blockIdx.x;
+	const int y = (int)(tile / (unsigned)a.tiles_x);
+	const int x0 = (int)(tile % (unsigned)a.tiles_x) * TX;
 	const int txe = min(TX, a.nx - x0);
 	const size_t rowbase = (size_t)y * a.nx;
 
@@ -140,7 +151,12 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 	__syncthreads();
 	const uint32_t base = s_off[0];
 	const int ncand = (int)(s_off[SEG] - base);
-	if (ncand > a.cmax) {                                   // oversized segment: leave the tile to k_pass1
+	if (ncand > a.cmax) {
+		if (a.big_tiles) {                                  // run again with a larger candidate buffer
+			if (tid == 0) a.big_tiles[atomicAdd(a.big_count, 1u)] = tile;
+			return;
+		}
+		// no larger buffer: leave every slot of the tile to k_pass1
 		if (tid < txe) a.flags[rowbase + x0 + tid] = (uint16_t)(JP | (JP << 8));
 		for (int idx = tid; idx < JP * txe; idx += nthr) {
 			const int j = idx / txe, xi = idx % txe;
@@ -152,7 +168,7 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 		if (tid < txe) a.flags[rowbase + x0 + tid] = 0;
 		return;
 	}
-	for (int i = tid; i < JP * JP; i += nthr) s_H[i] = __ldg(a.H + i);
+	for (int i = tid; i < JP * JPP; i += nthr) s_Ht[i] = __ldg(a.Ht + i);
 	for (int i = tid; i < JP + 1; i += nthr) s_D[i] = __ldg(a.Dmono + i);
 	for (int i = tid; i < JP; i += nthr) s_reach[i] = __ldg(a.reach + i);
 	for (int k = tid; k < ncand; k += nthr) { s_cand[k] = __ldg(a.spans + base + k); s_ty[k] = __ldg(a.ty + base + k); }
@@ -183,7 +199,8 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 		// survives for the outputs ix in [i - (t_hi-1), i + (t_lo-1)] (segment coordinates)
 		const int first = max(i - (t_hi - 1), 0);
 		const int last = min(i + (t_lo - 1), SEG - 1);
-		s_sv[k] = (uint32_t)first | ((uint32_t)(last - first) << 8) | ((uint32_t)i << 16);
+		const uint32_t ty = s_ty[k];
+		s_sv[k] = (uint32_t)first | ((uint32_t)(last - first) << 8) | ((uint32_t)i << 16) | (max(ty & 0xffu, ty >> 8) << 24);
 	}
 	__syncthreads();
 	if (tid >= txe) return;
@@ -195,56 +212,86 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 	for (int k = kb; k < ke; ++k) {
 		const uint32_t w = s_sv[k];
 		if ((uint32_t)(ix - (int)(w & 0xffu)) <= ((w >> 8) & 0xffu)) {
-			const int d = abs((int)(w >> 16) - ix);
+			const int d = abs((int)((w >> 16) & 0xffu) - ix);
 			const int jm = (int)s_jmax[d] + 1;            // classes that can reach this distance
 			const uint32_t ty = s_ty[k];
-			const int tu = min((int)(ty & 0xffu), jm), td = min((int)(ty >> 8), jm);
-			Fup = max(Fup, tu);
-			Fdn = max(Fdn, td);
-			if (S < P1_LCAP) s_list[S * TX + xi] = (uint32_t)k | ((uint32_t)d << 12) | ((uint32_t)max(tu, td) << 20);
+			Fup = max(Fup, min((int)(ty & 0xffu), jm));
+			Fdn = max(Fdn, min((int)(ty >> 8), jm));
+			if (S < P1_LCAP) s_list[S * TX + xi] = (uint16_t)k;
 			++S;
 		}
 	}
 	a.flags[rowbase + x0 + xi] = (uint16_t)(Fup | (Fdn << 8));
 	const int Tmax = max(Fup, Fdn);
-	// more survivors than the list holds (steep walls, many layers): re-scan the candidate range per class
+	// more survivors than the list holds (steep walls, many layers): re-scan the candidate range instead
 	const bool direct = S > P1_LCAP;
 	const int niter = direct ? ke - kb : S;
-	double2 ulist[CAP];
-	for (int j = 0; j < Tmax; ++j) {
-		const int Xj = s_reach[j];
-		const double *Hrow = s_H + (size_t)j * JP;
-		RunUnion<CAP> u(ulist);
+	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+
+	for (int cb = 0; cb < Tmax; cb += P1_CB) {
+		double lo[P1_CB], hi[P1_CB];
+#pragma unroll
+		for (int q = 0; q < P1_CB; ++q) { lo[q] = inf; hi[q] = -inf; }
+		unsigned int complex_mask = 0;                  // classes whose union is not a single interval
 		for (int s = 0; s < niter; ++s) {
-			uint32_t e;
-			if (!direct) e = s_list[s * TX + xi];
+			int k;
+			if (!direct) k = s_list[s * TX + xi];
+			else k = kb + s;
+			const uint32_t w = s_sv[k];
+			if (direct && (uint32_t)(ix - (int)(w & 0xffu)) > ((w >> 8) & 0xffu)) continue;
+			const int d = abs((int)((w >> 16) & 0xffu) - ix);
+			const int te = min((int)(w >> 24), (int)s_jmax[d] + 1) - cb;   // classes [cb, cb + te) take this survivor
+			if (te <= 0) continue;
+			const double2 ab = s_cand[k];
+			const double2 *hp = reinterpret_cast<const double2 *>(s_Ht + (size_t)d * JPP + cb);
+			double h[P1_CB];
+#pragma unroll
+			for (int q = 0; q < P1_CB / 2; ++q) { const double2 v = hp[q]; h[2 * q] = v.x; h[2 * q + 1] = v.y; }
+#pragma unroll
+			for (int q = 0; q < P1_CB; ++q) {
+				if (q < te) {
+					const double cs = ab.x - h[q], ce = ab.y + h[q];
+					if ((cs <= hi[q] && ce >= lo[q]) || lo[q] > hi[q]) {
+						lo[q] = cs < lo[q] ? cs : lo[q];
+						hi[q] = ce > hi[q] ? ce : hi[q];
+					} else complex_mask |= 1u << q;
+				}
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < P1_CB; ++q) {
+			const int j = cb + q;
+			if (j >= Tmax) break;
+			const unsigned long long slot = ((unsigned long long)y * JP + j) * a.nx + x0 + xi;
+			double2 out;
+			if (!((complex_mask >> q) & 1u)) out = make_double2(lo[q], hi[q]);   // (+inf, -inf) is the empty slot
 			else {
-				const int k = kb + s;
-				const uint32_t w = s_sv[k];
-				if ((uint32_t)(ix - (int)(w & 0xffu)) > ((w >> 8) & 0xffu)) continue;
-				const int dd = abs((int)(w >> 16) - ix);
-				const uint32_t ty = s_ty[k];
-				e = (uint32_t)k | ((uint32_t)dd << 12) | ((uint32_t)max(ty & 0xffu, ty >> 8) << 20);   // d <= Xj below caps the class
+				// general path: sorted list of disjoint intervals for this class
+				double2 ulist[CAP];
+				RunUnion<CAP> u(ulist);
+				for (int s = 0; s < niter; ++s) {
+					const int k = direct ? kb + s : (int)s_list[s * TX + xi];
+					const uint32_t w = s_sv[k];
+					if (direct && (uint32_t)(ix - (int)(w & 0xffu)) > ((w >> 8) & 0xffu)) continue;
+					const int d = abs((int)((w >> 16) & 0xffu) - ix);
+					if (j < min((int)(w >> 24), (int)s_jmax[d] + 1)) {
+						const double2 ab = s_cand[k];
+						const double hh = s_Ht[(size_t)d * JPP + j];
+						u.insert(ab.x - hh, ab.y + hh);
+					}
+				}
+				if (u.overflow) { redo_push(a.redo, slot); out = slot_empty(); }
+				else if (u.n == 0) out = slot_empty();
+				else if (u.n == 1) out = make_double2(u.s0, u.e0);
+				else {
+					const unsigned long long pb = atomicAdd(a.cursor, (unsigned long long)u.n);
+					if (pb + u.n <= a.pool_cap)
+						for (int t = 0; t < u.n; ++t) a.pool[pb + t] = u.L[t];
+					out = slot_pool(pb, (unsigned int)u.n);
+				}
 			}
-			const int d = (int)((e >> 12) & 0xffu);
-			if ((int)(e >> 20) > j && d <= Xj) {
-				const double2 ab = s_cand[e & 0xfffu];
-				const double h = Hrow[d];
-				u.insert(ab.x - h, ab.y + h);
-			}
+			a.mid[slot] = out;
 		}
-		const unsigned long long slot = ((unsigned long long)y * JP + j) * a.nx + x0 + xi;
-		double2 out;
-		if (u.overflow) { redo_push(a.redo, slot); out = slot_empty(); }
-		else if (u.n == 0) out = slot_empty();
-		else if (u.n == 1) out = make_double2(u.s0, u.e0);
-		else {
-			const unsigned long long pb = atomicAdd(a.cursor, (unsigned long long)u.n);
-			if (pb + u.n <= a.pool_cap)
-				for (int q = 0; q < u.n; ++q) a.pool[pb + q] = u.L[q];
-			out = slot_pool(pb, (unsigned int)u.n);
-		}
-		a.mid[slot] = out;
 	}
 }
 

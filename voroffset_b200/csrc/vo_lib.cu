@@ -31,7 +31,7 @@ struct vo_ctx {
 	cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 	std::string err;
 	uint64_t launches = 0;
-	// small persistent device scratch: [0] mid-pool cursor, [1] stage-pool cursor, [2] redo count
+	// small persistent device scratch: [0] mid-pool cursor, [1] stage-pool cursor, [2] redo count, [3] big-tile count
 	unsigned long long *d_ctr = nullptr;
 	// caller-visible timing marks (vo_mark / vo_elapsed_ms) and per-kernel profile of the last dilation
 	cudaEvent_t mark[8] = {};
@@ -273,9 +273,9 @@ struct RedoBuf {
 	}
 };
 
-int read_counters(vo_ctx *ctx, unsigned long long h[3])
+int read_counters(vo_ctx *ctx, unsigned long long h[4])
 {
-	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	VO_CUDA(cudaStreamSynchronize(ctx->stream));
 	return VO_OK;
 }
@@ -313,14 +313,14 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nlists, 1ull), 1ull << 22);
 	VO_TRY(rb.alloc(redo_cap));
 	for (int attempt = 0; attempt < 3; ++attempt) {
-		VO_CUDA(cudaMemsetAsync(ctx->d_ctr, 0, 3 * sizeof(unsigned long long), ctx->stream));
+		VO_CUDA(cudaMemsetAsync(ctx->d_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
 		args.st = sb.st;
 		args.redo = rb.rd;
 		args.work = nullptr;
 		args.nwork = nlists;
 		if (nlists) { launch_fast(args); ctx->launches++; }
 		VO_CUDA(cudaGetLastError());
-		unsigned long long h[3];
+		unsigned long long h[4];
 		VO_TRY(read_counters(ctx, h));
 		const unsigned int nredo = (unsigned int)h[2];
 		if (nredo > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
@@ -374,9 +374,9 @@ int check_radius(vo_ctx *ctx, double R)
 // both non-decreasing in their index, entry J+1 = +inf.
 struct TileTables {
 	vo_ctx *ctx;
-	double *Dmono = nullptr, *Emono = nullptr;
+	double *Dmono = nullptr, *Emono = nullptr, *Ht = nullptr;   // Ht[d*JPP + j] = H[j][d], rows padded to 8 classes
 	explicit TileTables(vo_ctx *c) : ctx(c) {}
-	~TileTables() { dfree(ctx, Dmono); dfree(ctx, Emono); }
+	~TileTables() { dfree(ctx, Dmono); dfree(ctx, Emono); dfree(ctx, Ht); }
 	int upload(const Tables &t)
 	{
 		const int J = t.J, n = J + 1;
@@ -394,6 +394,12 @@ struct TileTables {
 			for (int d = 0; d <= t.reach[j]; ++d) m = std::min(m, t.H[(size_t)(j - 1) * n + d] - t.H[(size_t)j * n + d]);
 			em[j] = std::min(m, em[j + 1]);
 		}
+		const int jpp = pass1_jpp(J);
+		std::vector<double> ht((size_t)n * jpp, -1.0);
+		for (int j = 0; j < n; ++j)
+			for (int d = 0; d < n; ++d) ht[(size_t)d * jpp + j] = t.H[(size_t)j * n + d];
+		VO_TRY(dalloc(ctx, &Ht, (unsigned long long)ht.size()));
+		VO_CUDA(cudaMemcpyAsync(Ht, ht.data(), ht.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 		VO_TRY(dalloc(ctx, &Dmono, (unsigned long long)J + 2));
 		VO_TRY(dalloc(ctx, &Emono, (unsigned long long)J + 2));
 		VO_CUDA(cudaMemcpyAsync(Dmono, dm.data(), dm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -432,6 +438,8 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, ncols);
 	Tmp<uint16_t> ty(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &ty.p, in->nspans);
+	Tmp<unsigned int> big_tiles(ctx);
+	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nslots, 1ull), 1ull << 22);
 	if (rc == VO_OK) rc = rb.alloc(redo_cap);
@@ -440,7 +448,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	auto bail = [&](int code) { vo_dmid_free(ctx, m); return code; };
 	bool tile_now = use_tile;
 	for (int attempt = 0; attempt < 4; ++attempt) {
-		cudaError_t e = cudaMemsetAsync(ctx->d_ctr, 0, 3 * sizeof(unsigned long long), ctx->stream);
+		cudaError_t e = cudaMemsetAsync(ctx->d_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream);
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, cudaGetErrorString(e)));
 		Pass1Args a;
 		a.nx = in->nx; a.ny = in->ny; a.J = t.J;
@@ -453,19 +461,32 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			k_ythresh<<<blocks_for(ncols, 256), 256, (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(yt);
 			ctx->launches++;
 			Pass1TileArgs g;
-			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.cmax = cmax;
+			g.nx = in->nx; g.ny = in->ny; g.J = t.J;
 			g.tiles_x = (in->nx + TX - 1) / TX;
-			g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.H = dt.H; g.reach = dt.reach; g.Dmono = tt.Dmono;
+			g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
 			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
-			const size_t smem = pass1_tile_smem(t.J, cmax);
-			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e)));
 			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
+			// first launch with a small candidate buffer (more CTAs per SM); tiles with denser segments are
+			// collected and run again with the large buffer
+			const int cmax_small = 256;
+			g.cmax = cmax_small; g.tiles = nullptr; g.big_tiles = big_tiles.p;
+			g.big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
+			const size_t smem_small = pass1_tile_smem(t.J, cmax_small), smem_big = pass1_tile_smem(t.J, cmax);
+			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e)));
 			cudaEventRecord(ctx->kev[0], ctx->stream);
-			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, P1_TX, smem, ctx->stream>>>(g);
+			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, P1_TX, smem_small, ctx->stream>>>(g);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
 			ctx->launches++;
+			unsigned long long hb[4];
+			rc = read_counters(ctx, hb);
+			if (rc) return bail(rc);
+			if (hb[3]) {
+				g.cmax = cmax; g.tiles = big_tiles.p; g.big_tiles = nullptr; g.big_count = nullptr;
+				k_pass1_tile<CAP_FAST><<<(unsigned int)hb[3], P1_TX, smem_big, ctx->stream>>>(g);
+				ctx->launches++;
+			}
 		} else if (nslots) {
 			// every class of every column is computed: all flag bytes = J + 1
 			cudaMemsetAsync(m->flags, t.J + 1, ncols * sizeof(uint16_t), ctx->stream);
@@ -477,7 +498,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		}
 		e = cudaGetLastError();
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1: ") + cudaGetErrorString(e)));
-		unsigned long long h[3];
+		unsigned long long h[4];
 		rc = read_counters(ctx, h);
 		if (rc) return bail(rc);
 		const unsigned int nredo = (unsigned int)h[2];
