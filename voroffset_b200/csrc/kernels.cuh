@@ -126,8 +126,8 @@ struct Pass2Args {
 	int nx, ny, J;          // grid of the mid volume
 	int y0, y1;             // rows produced
 	const double2 *mid;
-	const uint16_t *flags;  // [ny*nx] per mid column: classes j < (flags & 0xff) are needed by the consumer rows
-	                        // above (y - j), classes j < (flags >> 8) by the rows below (y + j); every other
+	const uint8_t *flags;   // [2][ny*nx] per mid column: classes j < flags[0][c] are needed by the consumer rows
+	                        // above (y - j), classes j < flags[1][c] by the rows below (y + j); every other
 	                        // slot was never written by pass 1 and must not be read (pass1_tile.cuh)
 	const double2 *pool;
 	Stage st;
@@ -135,6 +135,21 @@ struct Pass2Args {
 	const unsigned long long *work;
 	unsigned long long nwork;
 };
+
+template <int CAP>
+__device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot, const double2 *pool)
+{
+	const double2 s = __ldg(slot);
+	if (s.x <= s.y) u.insert(s.x, s.y);
+	else if (slot_is_pool(s)) {
+		const unsigned long long base = slot_pool_base(s);
+		const unsigned int n = slot_pool_count(s);
+		for (unsigned int k = 0; k < n; ++k) {
+			const double2 v = __ldg(pool + base + k);
+			u.insert(v.x, v.y);
+		}
+	}
+}
 
 template <int CAP>
 __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
@@ -147,23 +162,63 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 
 	double2 ulist[CAP];
 	RunUnion<CAP> u(ulist);
-	const int lo = max(-a.J, -y), hi = min(a.J, a.ny - 1 - y);
-	for (int dy = lo; dy <= hi; ++dy) {
-		const int j = abs(dy);
-		const unsigned int f = __ldg(a.flags + (size_t)(y + dy) * a.nx + x);
-		// this output is a consumer "above" row y+dy when dy > 0, "below" when dy < 0
-		const int need = dy > 0 ? (int)(f & 0xffu) : dy < 0 ? (int)(f >> 8) : (int)max(f & 0xffu, f >> 8);
-		if (j >= need) continue;
-		const double2 s = __ldg(a.mid + ((size_t)(y + dy) * (a.J + 1) + j) * a.nx + x);
-		if (s.x <= s.y) u.insert(s.x, s.y);
-		else if (slot_is_pool(s)) {
-			const unsigned long long base = slot_pool_base(s);
-			const unsigned int n = slot_pool_count(s);
-			for (unsigned int k = 0; k < n; ++k) {
-				const double2 v = __ldg(a.pool + base + k);
-				u.insert(v.x, v.y);
+	const int up = min(a.J, y), dn = min(a.J, a.ny - 1 - y);    // rows available above / below
+	const size_t nx = (size_t)a.nx, midrow = (size_t)(a.J + 1) * nx;
+	const uint8_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
+	const size_t cc = (size_t)y * nx + x;
+	const double2 *self = a.mid + (size_t)y * midrow + x;
+	if (a.J <= 63) {
+		// step 1: which rows are needed? All flag bytes are loaded back to back (independent loads) into two
+		// bit masks: bit j-1 of m_up = row y-j is needed (this output lies BELOW that row: its "dn" byte
+		// decides), bit j-1 of m_dn = row y+j is needed (its "up" byte decides).
+		unsigned long long m_up = 0, m_dn = 0;
+		{
+			const uint8_t *f = f_dn + cc - nx;
+#pragma unroll 8
+			for (int j = 1; j <= up; ++j, f -= nx) m_up |= (unsigned long long)(j < (int)__ldg(f)) << (j - 1);
+			f = f_up + cc + nx;
+#pragma unroll 8
+			for (int j = 1; j <= dn; ++j, f += nx) m_dn |= (unsigned long long)(j < (int)__ldg(f)) << (j - 1);
+		}
+		// the output's own row: class 0 is needed as soon as anything is in reach
+		if (max(__ldg(f_up + cc), __ldg(f_dn + cc)) > 0) pass2_take(u, self, a.pool);
+		// step 2: fetch the needed slots four at a time (independent loads), then fold them in
+		const size_t step_up = midrow - nx, step_dn = midrow + nx;     // slot (y-j, class j) = self - j*step_up, ...
+		while (m_up | m_dn) {
+			const double2 *p[4];
+			int n = 0;
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				p[i] = self;
+				if (m_up) { const int j = __ffsll((long long)m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
+				else if (m_dn) { const int j = __ffsll((long long)m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
+			}
+			double2 v[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) v[i] = __ldg(p[i]);
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				if (i < n) {
+					if (v[i].x <= v[i].y) u.insert(v[i].x, v[i].y);
+					else if (slot_is_pool(v[i])) {
+						const unsigned long long base = slot_pool_base(v[i]);
+						const unsigned int cnt = slot_pool_count(v[i]);
+						for (unsigned int k = 0; k < cnt; ++k) { const double2 w = __ldg(a.pool + base + k); u.insert(w.x, w.y); }
+					}
+				}
 			}
 		}
+	} else {
+		// general form (more than 64 classes: every class of every column was computed by k_pass1)
+		const uint8_t *f = f_dn + (size_t)(y - up) * nx + x;
+		const double2 *row = a.mid + (size_t)(y - up) * midrow + x;
+		for (int j = up; j >= 1; --j, f += nx, row += midrow)
+			if (j < (int)__ldg(f)) pass2_take(u, row + (size_t)j * nx, a.pool);
+		if (max(__ldg(f_up + cc), __ldg(f_dn + cc)) > 0) pass2_take(u, self, a.pool);
+		f = f_up + (size_t)(y + 1) * nx + x;
+		row = a.mid + (size_t)(y + 1) * midrow + x;
+		for (int j = 1; j <= dn; ++j, f += nx, row += midrow)
+			if (j < (int)__ldg(f)) pass2_take(u, row + (size_t)j * nx, a.pool);
 	}
 	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);

@@ -93,7 +93,7 @@ struct Pass1TileArgs {
 	const int *reach;       // J+1
 	const double *Dmono;    // J+2
 	double2 *mid;
-	uint16_t *flags;        // [ny*nx]: classes needed by the consumers above (low byte) / below (high byte)
+	uint8_t *flags;         // [2][ny*nx]: classes needed by the consumer rows above ([0]) / below ([1])
 	double2 *pool;
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
@@ -122,7 +122,7 @@ __host__ __device__ inline size_t pass1_tile_smem(int J, int cmax)
 }
 
 template <int CAP>
-__global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
+__global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int J = a.J, JP = J + 1, JPP = pass1_jpp(J), TX = P1_TX, SEG = TX + 2 * J;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 	const int y = (int)(tile / (unsigned)a.tiles_x);
 	const int x0 = (int)(tile % (unsigned)a.tiles_x) * TX;
 	const int txe = min(TX, a.nx - x0);
-	const size_t rowbase = (size_t)y * a.nx;
+	const size_t rowbase = (size_t)y * a.nx, ncols_all = (size_t)a.nx * a.ny;
 
 	// ---- phase 0: stage the row segment -------------------------------------------------------
 	for (int i = tid; i <= SEG; i += nthr) {
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 			return;
 		}
 		// no larger buffer: leave every slot of the tile to k_pass1
-		if (tid < txe) a.flags[rowbase + x0 + tid] = (uint16_t)(JP | (JP << 8));
+		if (tid < txe) { a.flags[rowbase + x0 + tid] = (uint8_t)JP; a.flags[ncols_all + rowbase + x0 + tid] = (uint8_t)JP; }
 		for (int idx = tid; idx < JP * txe; idx += nthr) {
 			const int j = idx / txe, xi = idx % txe;
 			redo_push(a.redo, ((unsigned long long)y * JP + j) * a.nx + x0 + xi);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 		return;
 	}
 	if (ncand == 0) {                                       // nothing in reach: no slot of the tile is needed
-		if (tid < txe) a.flags[rowbase + x0 + tid] = 0;
+		if (tid < txe) { a.flags[rowbase + x0 + tid] = 0; a.flags[ncols_all + rowbase + x0 + tid] = 0; }
 		return;
 	}
 	for (int i = tid; i < JP * JPP; i += nthr) s_Ht[i] = __ldg(a.Ht + i);
@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 			++S;
 		}
 	}
-	a.flags[rowbase + x0 + xi] = (uint16_t)(Fup | (Fdn << 8));
+	a.flags[rowbase + x0 + xi] = (uint8_t)Fup;
+	a.flags[ncols_all + rowbase + x0 + xi] = (uint8_t)Fdn;
 	const int Tmax = max(Fup, Fdn);
 	// more survivors than the list holds (steep walls, many layers): re-scan the candidate range instead
 	const bool direct = S > P1_LCAP;
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 #pragma unroll
 		for (int q = 0; q < P1_CB; ++q) { lo[q] = inf; hi[q] = -inf; }
 		unsigned int complex_mask = 0;                  // classes whose union is not a single interval
+		unsigned int seen_mask = 0;                     // classes that already hold an interval
 		for (int s = 0; s < niter; ++s) {
 			int k;
 			if (!direct) k = s_list[s * TX + xi];
@@ -251,12 +253,14 @@ __global__ void __launch_bounds__(P1_TX) k_pass1_tile(Pass1TileArgs a)
 			for (int q = 0; q < P1_CB; ++q) {
 				if (q < te) {
 					const double cs = ab.x - h[q], ce = ab.y + h[q];
-					if ((cs <= hi[q] && ce >= lo[q]) || lo[q] > hi[q]) {
-						lo[q] = cs < lo[q] ? cs : lo[q];
-						hi[q] = ce > hi[q] ? ce : hi[q];
-					} else complex_mask |= 1u << q;
+					// a candidate that misses the running hull of a non-empty class makes the class "complex"
+					// (redone below with the general list); the hull itself is updated unconditionally
+					if (!(cs <= hi[q] && ce >= lo[q])) complex_mask |= seen_mask & (1u << q);
+					lo[q] = cs < lo[q] ? cs : lo[q];
+					hi[q] = ce > hi[q] ? ce : hi[q];
 				}
 			}
+			seen_mask |= (te >= P1_CB) ? 0xffu : ((1u << te) - 1u);
 		}
 #pragma unroll
 		for (int q = 0; q < P1_CB; ++q) {

@@ -53,7 +53,7 @@ struct vo_dmid {
 	double R = 0;
 	double2 *slots = nullptr;
 	double2 *pool = nullptr;
-	uint16_t *flags = nullptr;      // per mid column: classes needed by the consumer rows above / below
+	uint8_t *flags = nullptr;       // [2][ny*nx]: classes needed by the consumer rows above / below each mid column
 	uint64_t pool_cap = 0, pool_used = 0;
 };
 
@@ -435,7 +435,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	int rc = dalloc(ctx, &m->slots, nslots);
 	unsigned long long pool_cap = 65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
-	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, ncols);
+	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, 2 * ncols);
 	Tmp<uint16_t> ty(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &ty.p, in->nspans);
 	Tmp<unsigned int> big_tiles(ctx);
@@ -489,7 +489,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			}
 		} else if (nslots) {
 			// every class of every column is computed: all flag bytes = J + 1
-			cudaMemsetAsync(m->flags, t.J + 1, ncols * sizeof(uint16_t), ctx->stream);
+			cudaMemsetAsync(m->flags, t.J + 1, 2 * ncols, ctx->stream);
 			cudaEventRecord(ctx->kev[0], ctx->stream);
 			k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
