@@ -31,6 +31,24 @@ struct Redo {
 	unsigned int cap;
 };
 
+// Which lists a gather launch processes. First launch: ids 0..n-1 (list == NULL). Redo launch: the ids the
+// first launch pushed to the redo list; their number is only known on the device, so the launch uses a
+// fixed grid, reads *count itself and strides over the list - the host never has to synchronise in between.
+struct Work {
+	const unsigned long long *list;
+	unsigned long long n;
+	const unsigned int *count;     // device-side length of `list` (redo launch), capped by cap
+	unsigned int cap;
+	unsigned int *fail;            // redo launch: incremented when an item outgrows CAP_BIG as well
+};
+
+// CAP == CAP_FAST is the first launch (one id per thread, no loop); CAP == CAP_BIG is the redo launch.
+#define VO_FOR_WORK(CAPV, wk, c)                                                                                 \
+	const unsigned long long vo_n_ = (CAPV) != CAP_FAST ? (unsigned long long)min(*(wk).count, (wk).cap) : (wk).n; \
+	for (unsigned long long vo_t_ = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, c = 0;           \
+	     vo_t_ < vo_n_ && ((c = (CAPV) != CAP_FAST ? (wk).list[vo_t_] : vo_t_), true);                          \
+	     vo_t_ = (CAPV) != CAP_FAST ? vo_t_ + (unsigned long long)gridDim.x * blockDim.x : vo_n_)
+
 template <int CAP>
 __device__ __forceinline__ void stage_emit(const Stage &st, size_t c, const RunUnion<CAP> &u)
 {
@@ -49,6 +67,13 @@ __device__ __forceinline__ void redo_push(const Redo &rd, unsigned long long id)
 {
 	unsigned int k = atomicAdd(rd.count, 1u);
 	if (k < rd.cap) rd.list[k] = id;
+}
+
+// a list outgrew its running-union capacity: first launch -> redo list, redo launch -> failure counter
+__device__ __forceinline__ void overflow_item(const Work &wk, const Redo &rd, unsigned long long id)
+{
+	if (wk.count) atomicAdd(wk.fail, 1u);   // redo launch
+	else redo_push(rd, id);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -70,16 +95,12 @@ struct Pass1Args {
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
 	Redo redo;
-	const unsigned long long *work; // NULL: all slots; else the redo list
-	unsigned long long nwork;
+	Work wk;
 };
 
 template <int CAP>
-__global__ void __launch_bounds__(128) k_pass1(Pass1Args a)
+__device__ __forceinline__ void pass1_item(const Pass1Args &a, unsigned long long slot)
 {
-	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid >= a.nwork) return;
-	const unsigned long long slot = a.work ? a.work[tid] : tid;
 	const int x = (int)(slot % (unsigned)a.nx);
 	const unsigned long long rest = slot / (unsigned)a.nx;
 	const int j = (int)(rest % (unsigned)(a.J + 1));
@@ -104,7 +125,7 @@ __global__ void __launch_bounds__(128) k_pass1(Pass1Args a)
 		o0 = o1;
 	}
 	double2 out;
-	if (u.overflow) { redo_push(a.redo, slot); out = slot_empty(); }
+	if (u.overflow) { overflow_item(a.wk, a.redo, slot); out = slot_empty(); }
 	else if (u.n == 0) out = slot_empty();
 	else if (u.n == 1) out = make_double2(u.s0, u.e0);
 	else {
@@ -114,6 +135,12 @@ __global__ void __launch_bounds__(128) k_pass1(Pass1Args a)
 		out = slot_pool(base, (unsigned int)u.n);
 	}
 	a.mid[slot] = out;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(128) k_pass1(Pass1Args a)
+{
+	VO_FOR_WORK(CAP, a.wk, slot) pass1_item<CAP>(a, slot);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -132,8 +159,7 @@ struct Pass2Args {
 	const double2 *pool;
 	Stage st;
 	Redo redo;
-	const unsigned long long *work;
-	unsigned long long nwork;
+	Work wk;
 };
 
 template <int CAP>
@@ -152,11 +178,8 @@ __device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot
 }
 
 template <int CAP>
-__global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
+__device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long long c)   // c: output list, rows relative to y0
 {
-	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid >= a.nwork) return;
-	const unsigned long long c = a.work ? a.work[tid] : tid;     // output list index, rows relative to y0
 	const int x = (int)(c % (unsigned)a.nx);
 	const int y = a.y0 + (int)(c / (unsigned)a.nx);
 
@@ -220,8 +243,14 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 		for (int j = 1; j <= dn; ++j, f += nx, row += midrow)
 			if (j < (int)__ldg(f)) pass2_take(u, row + (size_t)j * nx, a.pool);
 	}
-	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
+	if (u.overflow) { overflow_item(a.wk, a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
+{
+	VO_FOR_WORK(CAP, a.wk, c) pass2_item<CAP>(a, c);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -235,16 +264,12 @@ struct BruteArgs {
 	const double *HB;       // (J+1)*(J+1), [|dy|][|dx|]
 	Stage st;
 	Redo redo;
-	const unsigned long long *work;
-	unsigned long long nwork;
+	Work wk;
 };
 
 template <int CAP>
-__global__ void __launch_bounds__(128) k_brute(BruteArgs a)
+__device__ __forceinline__ void brute_item(const BruteArgs &a, unsigned long long c)
 {
-	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid >= a.nwork) return;
-	const unsigned long long c = a.work ? a.work[tid] : tid;
 	const int x = (int)(c % (unsigned)a.nx);
 	const int y = (int)(c / (unsigned)a.nx);
 
@@ -269,8 +294,14 @@ __global__ void __launch_bounds__(128) k_brute(BruteArgs a)
 			o0 = o1;
 		}
 	}
-	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
+	if (u.overflow) { overflow_item(a.wk, a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(128) k_brute(BruteArgs a)
+{
+	VO_FOR_WORK(CAP, a.wk, c) brute_item<CAP>(a, c);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -287,8 +318,7 @@ struct Dil2dArgs {
 	const double *h2;       // J+1
 	Stage st;
 	Redo redo;
-	const unsigned long long *work;
-	unsigned long long nwork;
+	Work wk;
 };
 
 template <int CAP>
@@ -301,11 +331,8 @@ __device__ __forceinline__ void clamp_insert(RunUnion<CAP> &u, double y1, double
 }
 
 template <int CAP>
-__global__ void __launch_bounds__(64) k_dilate2d(Dil2dArgs a)
+__device__ __forceinline__ void dilate2d_item(const Dil2dArgs &a, unsigned long long c)
 {
-	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid >= a.nwork) return;
-	const unsigned long long c = a.work ? a.work[tid] : tid;
 	const int i = (int)c;
 	double2 ulist[CAP];
 	RunUnion<CAP> u(ulist);
@@ -330,8 +357,14 @@ __global__ void __launch_bounds__(64) k_dilate2d(Dil2dArgs a)
 			clamp_insert(u, -1.0, j2, h, a.W);
 		}
 	}
-	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
+	if (u.overflow) { overflow_item(a.wk, a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(64) k_dilate2d(Dil2dArgs a)
+{
+	VO_FOR_WORK(CAP, a.wk, c) dilate2d_item<CAP>(a, c);
 }
 
 // Staged lists -> canonical CSR (after the exclusive scan of cnt).

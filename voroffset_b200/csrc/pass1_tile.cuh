@@ -100,7 +100,7 @@ struct Pass1TileArgs {
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
 	const unsigned int *tiles; // NULL: all tiles; else the tile ids to run (second launch with a larger cmax)
 	unsigned int *big_tiles;   // tiles whose segment holds more than cmax candidates (NULL: send them to redo)
-	unsigned int *big_count;
+	unsigned int *big_count;   // first launch: incremented; second launch: number of entries of `tiles`
 };
 
 __host__ __device__ inline int pass1_jpp(int J) { return (J + 1 + P1_CB - 1) / P1_CB * P1_CB; }
@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
 	uint8_t *s_jmax = reinterpret_cast<uint8_t *>(s_ty + a.cmax);
 
 	const int tid = threadIdx.x, nthr = blockDim.x;
+	if (a.tiles && blockIdx.x >= *a.big_count) return;      // second launch: only the collected tiles
 	const unsigned int tile = a.tiles ? a.tiles[blockIdx.x] : blockIdx.x;
 	const int y = (int)(tile / (unsigned)a.tiles_x);
 	const int x0 = (int)(tile % (unsigned)a.tiles_x) * TX;
@@ -249,18 +250,21 @@ __global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
 			double h[P1_CB];
 #pragma unroll
 			for (int q = 0; q < P1_CB / 2; ++q) { const double2 v = hp[q]; h[2 * q] = v.x; h[2 * q + 1] = v.y; }
+			// branch-free: a class that does not take this survivor gets the cap -inf, i.e. the candidate
+			// (+inf, -inf), which leaves its hull untouched. A candidate that misses the running hull of a
+			// non-empty class makes the class "complex" (redone below with the general list).
+			const unsigned int valid = (te >= P1_CB) ? 0xffu : ((1u << te) - 1u);
+			unsigned int miss = 0;
 #pragma unroll
 			for (int q = 0; q < P1_CB; ++q) {
-				if (q < te) {
-					const double cs = ab.x - h[q], ce = ab.y + h[q];
-					// a candidate that misses the running hull of a non-empty class makes the class "complex"
-					// (redone below with the general list); the hull itself is updated unconditionally
-					if (!(cs <= hi[q] && ce >= lo[q])) complex_mask |= seen_mask & (1u << q);
-					lo[q] = cs < lo[q] ? cs : lo[q];
-					hi[q] = ce > hi[q] ? ce : hi[q];
-				}
+				const double hq = (q < te) ? h[q] : -inf;
+				const double cs = ab.x - hq, ce = ab.y + hq;
+				miss |= (cs <= hi[q] && ce >= lo[q]) ? 0u : (1u << q);
+				lo[q] = cs < lo[q] ? cs : lo[q];
+				hi[q] = ce > hi[q] ? ce : hi[q];
 			}
-			seen_mask |= (te >= P1_CB) ? 0xffu : ((1u << te) - 1u);
+			complex_mask |= miss & valid & seen_mask;
+			seen_mask |= valid;
 		}
 #pragma unroll
 		for (int q = 0; q < P1_CB; ++q) {

@@ -37,6 +37,7 @@ struct vo_ctx {
 	cudaEvent_t mark[8] = {};
 	cudaEvent_t kev[4] = {};          // [0,1] around k_pass1<CAP_FAST>, [2,3] around k_pass2<CAP_FAST>
 	bool kev_valid[2] = {false, false};
+	void *table_cache = nullptr;      // TableCache*: cap tables of the last radius, kept on the device
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
 };
@@ -273,36 +274,22 @@ struct RedoBuf {
 	}
 };
 
-int read_counters(vo_ctx *ctx, unsigned long long h[4])
-{
-	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-	VO_CUDA(cudaStreamSynchronize(ctx->stream));
-	return VO_OK;
-}
+constexpr int NCTR = 8;   // [0] mid-pool cursor [1] stage-pool cursor [2] redo count [3] big-tile count [4] redo failures
 
-int finish_stage(vo_ctx *ctx, const Stage &st, int nx, int ny, vo_dvol **out)
+int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 {
-	const unsigned long long nlists = (unsigned long long)nx * ny;
-	vo_dvol *v = nullptr;
-	VO_TRY(new_dvol(ctx, nx, ny, &v));
-	unsigned long long total = 0;
-	int rc = scan_counts(ctx, st.cnt, nlists, v->off, &total);
-	if (rc == VO_OK) rc = dalloc(ctx, &v->spans, total);
-	if (rc != VO_OK) { free_dvol(ctx, v); return rc; }
-	v->nspans = total;
-	if (nlists) {
-		k_compact<<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(st, nlists, v->off, v->spans);
-		ctx->launches++;
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess) { free_dvol(ctx, v); return fail(ctx, VO_ERR_CUDA, std::string("k_compact: ") + cudaGetErrorString(e)); }
-	}
-	*out = v;
+	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, NCTR * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
 	return VO_OK;
 }
 
 // Generic driver for the staged gather kernels: first launch with CAP_FAST over all lists, then the
 // redo launch with CAP_BIG over the lists whose running union outgrew CAP_FAST; the staging pool is
 // regrown and the launch repeated if it was too small (the cursor keeps counting past the capacity).
+// The whole chain - gather, redo, prefix sum - is enqueued without a host round trip; the single
+// synchronisation at the end returns the counters and the grand total together.
+constexpr unsigned int REDO_GRID = 148 * 4;
+
 template <typename Args, typename LaunchFast, typename LaunchBig>
 int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long long pool_guess,
                LaunchFast launch_fast, LaunchBig launch_big, int nx, int ny, vo_dvol **out)
@@ -312,30 +299,46 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	VO_TRY(sb.alloc(nlists, pool_guess));
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nlists, 1ull), 1ull << 22);
 	VO_TRY(rb.alloc(redo_cap));
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &v));
+	struct Guard { vo_ctx *c; vo_dvol *&p; ~Guard() { if (p) free_dvol(c, p); } } guard{ctx, v};
+	const unsigned int ntiles = blocks_for(nlists, SCAN_TILE);
+	Tmp<unsigned long long> sums(ctx);
+	VO_TRY(dalloc(ctx, &sums.p, (unsigned long long)ntiles + 1));
 	for (int attempt = 0; attempt < 3; ++attempt) {
-		VO_CUDA(cudaMemsetAsync(ctx->d_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream));
-		args.st = sb.st;
-		args.redo = rb.rd;
-		args.work = nullptr;
-		args.nwork = nlists;
-		if (nlists) { launch_fast(args); ctx->launches++; }
-		VO_CUDA(cudaGetLastError());
-		unsigned long long h[4];
+		VO_CUDA(cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), ctx->stream));
+		unsigned long long h[NCTR] = {0}, total = 0;
+		if (nlists) {
+			args.st = sb.st;
+			args.redo = rb.rd;
+			args.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
+			launch_fast(args);
+			args.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
+			launch_big(args, REDO_GRID);
+			k_scan_reduce<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p);
+			k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(sums.p, ntiles);
+			k_scan_apply<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p, v->off);
+			ctx->launches += 5;
+			VO_CUDA(cudaGetLastError());
+			VO_CUDA(cudaMemcpyAsync(&total, sums.p + ntiles, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+		} else {
+			VO_CUDA(cudaMemsetAsync(v->off, 0, sizeof(uint32_t), ctx->stream));
+		}
 		VO_TRY(read_counters(ctx, h));
-		const unsigned int nredo = (unsigned int)h[2];
-		if (nredo > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
-		if (nredo) {
-			args.work = rb.rd.list;
-			args.nwork = nredo;
-			VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 2, 0, sizeof(unsigned long long), ctx->stream));
-			launch_big(args);
+		if (h[2] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
+		if (h[4]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
+		if (h[1] > sb.st.pool_cap) { VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024)); continue; }
+		if (total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
+		VO_TRY(dalloc(ctx, &v->spans, total));
+		v->nspans = total;
+		if (nlists) {
+			k_compact<<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans);
 			ctx->launches++;
 			VO_CUDA(cudaGetLastError());
-			VO_TRY(read_counters(ctx, h));
-			if (h[2]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
 		}
-		if (h[1] <= sb.st.pool_cap) return finish_stage(ctx, sb.st, nx, ny, out);
-		VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024));
+		*out = v;
+		v = nullptr;          // released from the guard
+		return VO_OK;
 	}
 	return fail(ctx, VO_ERR_OVERFLOW, "staging pool did not converge");
 }
@@ -409,13 +412,48 @@ struct TileTables {
 	}
 };
 
+// The tables only depend on the radius: keep the last set on the device so that repeated calls with the
+// same radius (opening / closing, benchmark steps, slabs) do not upload or synchronise again.
+struct TableCache {
+	double R;
+	Tables t;
+	DevTables dt;
+	TileTables tt;
+	bool has_tile = false;
+	TableCache(vo_ctx *ctx, double r) : R(r), t(make_tables(r)), dt(ctx), tt(ctx) {}
+};
+
+void free_table_cache(vo_ctx *ctx)
+{
+	delete static_cast<TableCache *>(ctx->table_cache);
+	ctx->table_cache = nullptr;
+}
+
+int get_tables(vo_ctx *ctx, double R, bool need_tile, TableCache **out)
+{
+	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
+	if (!tc || std::memcmp(&tc->R, &R, sizeof(double)) != 0) {
+		free_table_cache(ctx);
+		tc = new (std::nothrow) TableCache(ctx, R);
+		if (!tc) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
+		ctx->table_cache = tc;
+		int rc = tc->dt.upload(tc->t);
+		if (rc) { free_table_cache(ctx); return rc; }
+	}
+	if (need_tile && !tc->has_tile) {
+		int rc = tc->tt.upload(tc->t);
+		if (rc) { free_table_cache(ctx); return rc; }
+		tc->has_tile = true;
+	}
+	*out = tc;
+	return VO_OK;
+}
+
 // ---- 'ours' pass 1 ------------------------------------------------------------------------------------
 int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 {
 	VO_TRY(check_radius(ctx, R));
-	Tables t = make_tables(R);
-	DevTables dt(ctx);
-	VO_TRY(dt.upload(t));
+	const int J0 = (int)std::floor(R);
 	const unsigned long long ncols = (unsigned long long)in->nx * in->ny;
 	// tile kernel (pass1_tile.cuh) whenever its tables and tile fit in shared memory and a row segment's
 	// candidates are expected to fit; otherwise the one-thread-per-(x,y,j) kernel does everything
@@ -423,10 +461,13 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	const int cmax = 1024;
 	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
 	// (small problems do not fill the machine with one thread per column: the simple kernel has J+1 times more threads)
-	const bool big = ncols * (unsigned long long)(t.J + 1) >= (2ull << 20) || ctx->force_tile_pass1;
-	const bool use_tile = t.J <= 63 && ncols > 0 && k_in * (TX + 2 * t.J) <= 0.6 * cmax && big && !ctx->force_simple_pass1;
-	TileTables tt(ctx);
-	if (use_tile) VO_TRY(tt.upload(t));
+	const bool big = ncols * (unsigned long long)(J0 + 1) >= (2ull << 20) || ctx->force_tile_pass1;
+	const bool use_tile = J0 <= 63 && ncols > 0 && k_in * (TX + 2 * J0) <= 0.6 * cmax && big && !ctx->force_simple_pass1;
+	TableCache *tc = nullptr;
+	VO_TRY(get_tables(ctx, R, use_tile, &tc));
+	const Tables &t = tc->t;
+	DevTables &dt = tc->dt;
+	TileTables &tt = tc->tt;
 
 	vo_dmid *m = new (std::nothrow) vo_dmid();
 	if (!m) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
@@ -448,13 +489,14 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	auto bail = [&](int code) { vo_dmid_free(ctx, m); return code; };
 	bool tile_now = use_tile;
 	for (int attempt = 0; attempt < 4; ++attempt) {
-		cudaError_t e = cudaMemsetAsync(ctx->d_ctr, 0, 4 * sizeof(unsigned long long), ctx->stream);
+		cudaError_t e = cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), ctx->stream);
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, cudaGetErrorString(e)));
 		Pass1Args a;
 		a.nx = in->nx; a.ny = in->ny; a.J = t.J;
 		a.off = in->off; a.spans = in->spans; a.H = dt.H; a.reach = dt.reach;
 		a.mid = m->slots; a.pool = m->pool; a.cursor = ctx->d_ctr; a.pool_cap = m->pool_cap;
-		a.redo = rb.rd; a.work = nullptr; a.nwork = nslots;
+		a.redo = rb.rd;
+		a.wk = Work{nullptr, nslots, nullptr, 0u, nullptr};
 		if (nslots && tile_now) {
 			YThreshArgs yt;
 			yt.nx = in->nx; yt.ny = in->ny; yt.J = t.J; yt.off = in->off; yt.spans = in->spans; yt.Emono = tt.Emono; yt.ty = ty.p;
@@ -467,7 +509,8 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
 			// first launch with a small candidate buffer (more CTAs per SM); tiles with denser segments are
-			// collected and run again with the large buffer
+			// collected on the device and run by a second launch with the large buffer (its CTAs beyond the
+			// collected count exit at once, so no host round trip is needed in between)
 			const int cmax_small = 256;
 			g.cmax = cmax_small; g.tiles = nullptr; g.big_tiles = big_tiles.p;
 			g.big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
@@ -478,15 +521,9 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, P1_TX, smem_small, ctx->stream>>>(g);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
-			ctx->launches++;
-			unsigned long long hb[4];
-			rc = read_counters(ctx, hb);
-			if (rc) return bail(rc);
-			if (hb[3]) {
-				g.cmax = cmax; g.tiles = big_tiles.p; g.big_tiles = nullptr; g.big_count = nullptr;
-				k_pass1_tile<CAP_FAST><<<(unsigned int)hb[3], P1_TX, smem_big, ctx->stream>>>(g);
-				ctx->launches++;
-			}
+			g.cmax = cmax; g.tiles = big_tiles.p; g.big_tiles = nullptr;
+			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, P1_TX, smem_big, ctx->stream>>>(g);
+			ctx->launches += 2;
 		} else if (nslots) {
 			// every class of every column is computed: all flag bytes = J + 1
 			cudaMemsetAsync(m->flags, t.J + 1, 2 * ncols, ctx->stream);
@@ -496,27 +533,22 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			ctx->kev_valid[0] = true;
 			ctx->launches++;
 		}
+		if (nslots) {
+			// redo launch over the device-side list (fixed grid, reads the count itself)
+			a.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
+			k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, ctx->stream>>>(a);
+			ctx->launches++;
+		}
 		e = cudaGetLastError();
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1: ") + cudaGetErrorString(e)));
-		unsigned long long h[4];
+		unsigned long long h[NCTR];
 		rc = read_counters(ctx, h);
 		if (rc) return bail(rc);
-		const unsigned int nredo = (unsigned int)h[2];
-		if (nredo > redo_cap) {
+		if (h[2] > redo_cap) {
 			if (tile_now) { tile_now = false; continue; }       // too many oversized tiles: simple kernel for everything
 			return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
 		}
-		if (nredo) {
-			a.work = rb.rd.list; a.nwork = nredo;
-			cudaMemsetAsync(ctx->d_ctr + 2, 0, sizeof(unsigned long long), ctx->stream);
-			k_pass1<CAP_BIG><<<blocks_for(nredo, 128), 128, 0, ctx->stream>>>(a);
-			ctx->launches++;
-			e = cudaGetLastError();
-			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1 redo: ") + cudaGetErrorString(e)));
-			rc = read_counters(ctx, h);
-			if (rc) return bail(rc);
-			if (h[2]) return bail(fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union"));
-		}
+		if (h[4]) return bail(fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union"));
 		if (h[0] <= m->pool_cap) { m->pool_used = h[0]; *out = m; return VO_OK; }
 		dfree(ctx, m->pool);
 		m->pool = nullptr;
@@ -538,28 +570,29 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
 		[&](Pass2Args &g) {
 			cudaEventRecord(ctx->kev[2], s);
-			k_pass2<CAP_FAST><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g);
+			k_pass2<CAP_FAST><<<blocks_for(g.wk.n, 128), 128, 0, s>>>(g);
 			cudaEventRecord(ctx->kev[3], s);
 			ctx->kev_valid[1] = true;
 		},
-		[&](Pass2Args &g) { k_pass2<CAP_BIG><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
+		[&](Pass2Args &g, unsigned int grid) { k_pass2<CAP_BIG><<<grid, 128, 0, s>>>(g); },
 		m->nx, y1 - y0, out);
 }
 
 int brute(vo_ctx *ctx, const vo_dvol *in, double R, vo_dvol **out)
 {
 	VO_TRY(check_radius(ctx, R));
-	Tables t = make_tables(R);
-	DevTables dt(ctx);
-	VO_TRY(dt.upload(t));
+	TableCache *tc = nullptr;
+	VO_TRY(get_tables(ctx, R, false, &tc));
+	const Tables &t = tc->t;
+	DevTables &dt = tc->dt;
 	BruteArgs a;
 	a.nx = in->nx; a.ny = in->ny; a.J = t.J;
 	a.off = in->off; a.spans = in->spans; a.HB = dt.HB;
 	const unsigned long long nlists = (unsigned long long)in->nx * in->ny;
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
-		[&](BruteArgs &g) { k_brute<CAP_FAST><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
-		[&](BruteArgs &g) { k_brute<CAP_BIG><<<blocks_for(g.nwork, 128), 128, 0, s>>>(g); },
+		[&](BruteArgs &g) { k_brute<CAP_FAST><<<blocks_for(g.wk.n, 128), 128, 0, s>>>(g); },
+		[&](BruteArgs &g, unsigned int grid) { k_brute<CAP_BIG><<<grid, 128, 0, s>>>(g); },
 		in->nx, in->ny, out);
 }
 
@@ -710,8 +743,8 @@ int dilate2d(vo_ctx *ctx, const vo_dvol *in, int width, double R, int complement
 	const unsigned long long nlists = (unsigned long long)in->nx;
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + 4 * in->nspans,
-		[&](Dil2dArgs &g) { k_dilate2d<CAP_FAST><<<blocks_for(g.nwork, 64), 64, 0, s>>>(g); },
-		[&](Dil2dArgs &g) { k_dilate2d<CAP_BIG><<<blocks_for(g.nwork, 64), 64, 0, s>>>(g); },
+		[&](Dil2dArgs &g) { k_dilate2d<CAP_FAST><<<blocks_for(g.wk.n, 64), 64, 0, s>>>(g); },
+		[&](Dil2dArgs &g, unsigned int grid) { k_dilate2d<CAP_BIG><<<grid, 64, 0, s>>>(g); },
 		in->nx, 1, out);
 }
 
@@ -853,7 +886,7 @@ int vo_create(int device, vo_ctx **out)
 	for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->mark[i]) == cudaSuccess;
 	for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&ctx->kev[i]) == cudaSuccess;
-	ok = ok && cudaMalloc((void **)&ctx->d_ctr, 4 * sizeof(unsigned long long)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&ctx->d_ctr, 8 * sizeof(unsigned long long)) == cudaSuccess;
 	if (ok) {
 		// keep freed blocks in the stream-ordered pool: steady-state calls then allocate without the driver
 		cudaMemPool_t pool;
@@ -872,6 +905,7 @@ void vo_destroy(vo_ctx *ctx)
 	if (!ctx) return;
 	DeviceGuard g(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	free_table_cache(ctx);
 	if (ctx->d_ctr) cudaFree(ctx->d_ctr);
 	for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
