@@ -320,18 +320,21 @@ def main():
             "config": {"workload": workload_name(a), "grid_per_gpu": [vol.nx, vol.ny], "radius": R, "method": "ours",
                        "operation": "dilation", "k_in": round(k_in, 4), "k_out": round(k_out, 4),
                        "parallelism": f"y-slabs x{world}, floor(R)-row input halo over NCCL" if world > 1 else "single GPU",
-                       "l2": "flushed between timed steps (256 MiB memset, untimed); the mid volume (2.2 GB) also exceeds L2",
+                       "l2": "flushed between timed steps (256 MiB memset, untimed); the touched part of the mid volume (~0.5 GB) also exceeds L2",
                        "timing": "CUDA events on the library stream around each step, summed, max over ranks"},
             "e2e": e2e, "gpu_launches": int(launches),
             "pass_ms": {"pass1": statistics.mean(p1_ms), "pass2": statistics.mean(p2_ms),
                         "k_pass1": k1, "k_pass2": statistics.mean(k2_ms)},
-            "roofline": {"bound": "hbm", "kernel": "k_pass1<16>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_pass1_tile<16>", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": ncu_traffic(a.n, R), "peak_source": peak_src,
                          "algorithmic_bytes_per_column": b1, "k_mid": k_mid, "k_mid_source": k_mid_src,
+                         "definition": "SURVEY.md 8(d): B1 = (4 + 16 k_in) + (4 + 24 k_mid) bytes per column, k_mid = pieces per "
+                                       "column of the REFERENCE's mid volume; our kernel never materialises those pieces "
+                                       "(`traffic` = what it really moves, from ncu), so this fraction measures speed against the "
+                                       "reference's data flow, not DRAM utilisation",
                          "whole_dilation": {"bytes_per_column": b1 + b2,
                                             "achieved": (b1 + b2) * ncols / ((total_ms / a.steps) * 1e-3) / 1e9,
-                                            "frac": (b1 + b2) * ncols / ((total_ms / a.steps) * 1e-3) / 1e9 / peak},
-                         "bytes_actually_written_by_kernel_per_column": 16 * (math.floor(R) + 1)},
+                                            "frac": (b1 + b2) * ncols / ((total_ms / a.steps) * 1e-3) / 1e9 / peak}},
             "clocks": clk,
         }
         if world == 1 and not a.no_cpu_baseline:
