@@ -34,6 +34,9 @@
 // seeds are retired once their cell no longer reaches the sweep line) in a conservative, data-parallel
 // form. On the C5 torus it keeps ~7 of ~38 candidates per column and ~13 of 33 classes.
 #pragma once
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+
 #include "kernels.cuh"
 
 namespace vo {
@@ -98,9 +101,19 @@ struct Pass1TileArgs {
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
-	const unsigned int *tiles; // NULL: all tiles; else the tile ids to run (second launch with a larger cmax)
-	unsigned int *big_tiles;   // tiles whose segment holds more than cmax candidates (NULL: send them to redo)
-	unsigned int *big_count;   // first launch: incremented; second launch: number of entries of `tiles`
+	// Device-side dispatch (no host round trip between the launches):
+	//   launch 1  <MULTI=false>, small candidate buffer, all tiles. Tiles with a multi-interval column go to
+	//             multi_tiles, tiles with more than cmax candidates to big_tiles.
+	//   launch 2  <MULTI=false>, large buffer, tiles = big_tiles.
+	//   launch 3  <MULTI=true> (two hulls per class), tiles = multi_tiles.
+	// A launch over a list uses the full grid; CTAs beyond *tiles_count exit at once.
+	const unsigned int *tiles;        // NULL: all tiles
+	const unsigned int *tiles_count;
+	unsigned int *tiles_next;         // list launches: next list position to hand out
+	unsigned int *big_tiles;          // NULL: oversized tiles go to the redo list (k_pass1)
+	unsigned int *big_count;
+	unsigned int *multi_tiles;
+	unsigned int *multi_count;
 };
 
 __host__ __device__ inline int pass1_jpp(int J) { return (J + 1 + P1_CB - 1) / P1_CB * P1_CB; }
@@ -121,8 +134,156 @@ __host__ __device__ inline size_t pass1_tile_smem(int J, int cmax)
 	return b + 32;
 }
 
+// Pool space for `n` entries, one atomic per converged group of threads instead of one per thread.
+__device__ __forceinline__ unsigned long long pool_alloc(unsigned long long *cursor, unsigned int n)
+{
+	namespace cg = cooperative_groups;
+	auto g = cg::coalesced_threads();
+	const unsigned int pre = cg::exclusive_scan(g, n);
+	const unsigned int total = g.shfl(pre + n, g.size() - 1);
+	unsigned long long base = 0;
+	if (g.thread_rank() == 0) base = atomicAdd(cursor, (unsigned long long)total);
+	return g.shfl(base, 0) + pre;
+}
+
+// Per-thread view of the staged tile (phase 2).
+struct TileThread {
+	const double2 *cand;
+	const double *Ht;
+	const uint32_t *sv;        // first | width << 8 | column << 16 | (T-1) << 24 | layer << 30
+	const uint16_t *list;
+	const uint8_t *jmax;
+	int JP, JPP, xi, ix, kb, niter, Tmax, y, x0;
+	bool direct;
+
+	__device__ __forceinline__ bool survivor(int s, int &k, uint32_t &w) const
+	{
+		k = direct ? kb + s : (int)list[s * P1_TX + xi];
+		w = sv[k];
+		return !direct || (uint32_t)(ix - (int)(w & 0xffu)) <= ((w >> 8) & 0xffu);
+	}
+	__device__ __forceinline__ int dist(uint32_t w) const { return abs((int)((w >> 16) & 0xffu) - ix); }
+	// classes [0, classes(w, d)) take this survivor
+	__device__ __forceinline__ int classes(uint32_t w, int d) const { return min((int)((w >> 24) & 0x3fu) + 1, (int)jmax[d] + 1); }
+};
+
+// General path for one class: sorted list of disjoint intervals (any number of components).
 template <int CAP>
-__global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
+__device__ __noinline__ double2 class_general(const Pass1TileArgs &a, const TileThread &t, int j, unsigned long long slot)
+{
+	double2 ulist[CAP];
+	RunUnion<CAP> u(ulist);
+	for (int s = 0; s < t.niter; ++s) {
+		int k;
+		uint32_t w;
+		if (!t.survivor(s, k, w)) continue;
+		const int d = t.dist(w);
+		if (j < t.classes(w, d)) {
+			const double2 ab = t.cand[k];
+			const double hh = t.Ht[(size_t)d * t.JPP + j];
+			u.insert(ab.x - hh, ab.y + hh);
+		}
+	}
+	if (u.overflow) { redo_push(a.redo, slot); return slot_empty(); }
+	if (u.n == 0) return slot_empty();
+	if (u.n == 1) return make_double2(u.s0, u.e0);
+	const unsigned long long pb = atomicAdd(a.cursor, (unsigned long long)u.n);
+	if (pb + u.n <= a.pool_cap)
+		for (int q = 0; q < u.n; ++q) a.pool[pb + q] = u.L[q];
+	return slot_pool(pb, (unsigned int)u.n);
+}
+
+// Classes CB at a time in registers, NL hulls per class. Hull l collects the survivors that are the l-th
+// interval of their column (the last hull also takes any further ones): for shells, slabs and complements
+// (erosion) each such layer unions to ONE interval, so a class costs NL (lo, hi) pairs and no list. A
+// survivor that misses the running hull of its layer makes the class "complex" (general path).
+template <int CB, int NL, int CAP>
+__device__ __forceinline__ void eval_classes(const Pass1TileArgs &a, const TileThread &t)
+{
+	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	const unsigned int full = (1u << CB) - 1u;
+	for (int cb = 0; cb < t.Tmax; cb += CB) {
+		double lo[NL][CB], hi[NL][CB];
+		unsigned int seen[NL];
+#pragma unroll
+		for (int l = 0; l < NL; ++l) {
+			seen[l] = 0;
+#pragma unroll
+			for (int q = 0; q < CB; ++q) { lo[l][q] = inf; hi[l][q] = -inf; }
+		}
+		unsigned int complex_mask = 0;
+		for (int s = 0; s < t.niter; ++s) {
+			int k;
+			uint32_t w;
+			if (!t.survivor(s, k, w)) continue;
+			const int d = t.dist(w);
+			const int te = t.classes(w, d) - cb;           // classes [cb, cb + te) take this survivor
+			if (te <= 0) continue;
+			const double2 ab = t.cand[k];
+			const double2 *hp = reinterpret_cast<const double2 *>(t.Ht + (size_t)d * t.JPP + cb);
+			double h[CB];
+#pragma unroll
+			for (int q = 0; q < CB / 2; ++q) { const double2 v = hp[q]; h[2 * q] = v.x; h[2 * q + 1] = v.y; }
+			// branch-free: a class that does not take this survivor gets the cap -inf, i.e. the candidate
+			// (+inf, -inf), which leaves its hull untouched
+			const unsigned int valid = te >= CB ? full : ((1u << te) - 1u);
+			const int lay = NL == 1 ? 0 : min((int)(w >> 30), NL - 1);
+#pragma unroll
+			for (int l = 0; l < NL; ++l) {
+				if (NL == 1 || lay == l) {
+					unsigned int miss = 0;
+#pragma unroll
+					for (int q = 0; q < CB; ++q) {
+						const double hq = (q < te) ? h[q] : -inf;
+						const double cs = ab.x - hq, ce = ab.y + hq;
+						miss |= (cs <= hi[l][q] && ce >= lo[l][q]) ? 0u : (1u << q);
+						lo[l][q] = cs < lo[l][q] ? cs : lo[l][q];
+						hi[l][q] = ce > hi[l][q] ? ce : hi[l][q];
+					}
+					complex_mask |= miss & valid & seen[l];
+					seen[l] |= valid;
+				}
+			}
+		}
+		// classes whose two hulls stay apart need two pool entries: one allocation for the whole block
+		unsigned int two_mask = 0;
+		if (NL == 2) {
+#pragma unroll
+			for (int q = 0; q < CB; ++q) {
+				const bool both = lo[0][q] <= hi[0][q] && lo[NL - 1][q] <= hi[NL - 1][q];
+				const bool apart = !(lo[NL - 1][q] <= hi[0][q] && hi[NL - 1][q] >= lo[0][q]);
+				if (cb + q < t.Tmax && both && apart && !((complex_mask >> q) & 1u)) two_mask |= 1u << q;
+			}
+		}
+		unsigned long long pb = 0;
+		if (two_mask) pb = pool_alloc(a.cursor, 2u * __popc(two_mask));
+#pragma unroll
+		for (int q = 0; q < CB; ++q) {
+			const int j = cb + q;
+			if (j >= t.Tmax) break;
+			const unsigned long long slot = ((unsigned long long)t.y * t.JP + j) * a.nx + t.x0 + t.xi;
+			double2 out;
+			if ((complex_mask >> q) & 1u) out = class_general<CAP>(a, t, j, slot);
+			else if (NL == 1) out = make_double2(lo[0][q], hi[0][q]);          // (+inf, -inf) is the empty slot
+			else if ((two_mask >> q) & 1u) {
+				const bool first0 = lo[0][q] < lo[NL - 1][q];
+				const double2 h0 = make_double2(lo[0][q], hi[0][q]), h1 = make_double2(lo[NL - 1][q], hi[NL - 1][q]);
+				if (pb + 2 <= a.pool_cap) { a.pool[pb] = first0 ? h0 : h1; a.pool[pb + 1] = first0 ? h1 : h0; }
+				out = slot_pool(pb, 2u);
+				pb += 2;
+			} else {
+				// at most one interval: the hulls overlap, or one (or both) is empty ((+inf, -inf) drops out of min / max)
+				const double l0 = lo[0][q] < lo[NL - 1][q] ? lo[0][q] : lo[NL - 1][q];
+				const double h0 = hi[0][q] > hi[NL - 1][q] ? hi[0][q] : hi[NL - 1][q];
+				out = make_double2(l0, h0);
+			}
+			a.mid[slot] = out;
+		}
+	}
+}
+
+template <int CAP, bool MULTI>
+__device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const unsigned int tile)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int J = a.J, JP = J + 1, JPP = pass1_jpp(J), TX = P1_TX, SEG = TX + 2 * J;
@@ -137,19 +298,23 @@ __global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
 	uint8_t *s_jmax = reinterpret_cast<uint8_t *>(s_ty + a.cmax);
 
 	const int tid = threadIdx.x, nthr = blockDim.x;
-	if (a.tiles && blockIdx.x >= *a.big_count) return;      // second launch: only the collected tiles
-	const unsigned int tile = a.tiles ? a.tiles[blockIdx.x] : blockIdx.x;
 	const int y = (int)(tile / (unsigned)a.tiles_x);
 	const int x0 = (int)(tile % (unsigned)a.tiles_x) * TX;
 	const int txe = min(TX, a.nx - x0);
 	const size_t rowbase = (size_t)y * a.nx, ncols_all = (size_t)a.nx * a.ny;
 
 	// ---- phase 0: stage the row segment -------------------------------------------------------
+	bool multi = false;                                     // does a column of the segment hold several intervals?
 	for (int i = tid; i <= SEG; i += nthr) {
 		const int gx = min(max(x0 - J + i, 0), a.nx);      // columns outside the grid collapse to empty ranges
-		s_off[i] = __ldg(a.off + rowbase + gx);
+		const uint32_t o = __ldg(a.off + rowbase + gx);
+		s_off[i] = o;
+		if (!MULTI && i < SEG) multi |= __ldg(a.off + rowbase + min(max(x0 - J + i + 1, 0), a.nx)) - o > 1u;
 	}
-	__syncthreads();
+	if (__syncthreads_or(multi)) {                          // (never taken by the MULTI variant)
+		if (tid == 0) a.multi_tiles[atomicAdd(a.multi_count, 1u)] = tile;   // -> two-hull variant, launch 3
+		return;
+	}
 	const uint32_t base = s_off[0];
 	const int ncand = (int)(s_off[SEG] - base);
 	if (ncand > a.cmax) {
@@ -201,7 +366,8 @@ __global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
 		const int first = max(i - (t_hi - 1), 0);
 		const int last = min(i + (t_lo - 1), SEG - 1);
 		const uint32_t ty = s_ty[k];
-		s_sv[k] = (uint32_t)first | ((uint32_t)(last - first) << 8) | ((uint32_t)i << 16) | (max(ty & 0xffu, ty >> 8) << 24);
+		const uint32_t layer = min((uint32_t)k - (s_off[i] - base), 3u);      // position of the interval inside its column
+		s_sv[k] = (uint32_t)first | ((uint32_t)(last - first) << 8) | ((uint32_t)i << 16) | ((max(ty & 0xffu, ty >> 8) - 1u) << 24) | (layer << 30);
 	}
 	__syncthreads();
 	if (tid >= txe) return;
@@ -210,9 +376,11 @@ __global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
 	const int xi = tid, ix = xi + J;
 	const int kb = (int)(s_off[ix - J] - base), ke = (int)(s_off[ix + J + 1] - base);
 	int S = 0, Fup = 0, Fdn = 0;
+	uint32_t maxlayer = 0;
 	for (int k = kb; k < ke; ++k) {
 		const uint32_t w = s_sv[k];
 		if ((uint32_t)(ix - (int)(w & 0xffu)) <= ((w >> 8) & 0xffu)) {
+			maxlayer = max(maxlayer, w >> 30);
 			const int d = abs((int)((w >> 16) & 0xffu) - ix);
 			const int jm = (int)s_jmax[d] + 1;            // classes that can reach this distance
 			const uint32_t ty = s_ty[k];
@@ -226,79 +394,32 @@ __global__ void __launch_bounds__(P1_TX, 6) k_pass1_tile(Pass1TileArgs a)
 	a.flags[ncols_all + rowbase + x0 + xi] = (uint8_t)Fdn;
 	const int Tmax = max(Fup, Fdn);
 	// more survivors than the list holds (steep walls, many layers): re-scan the candidate range instead
-	const bool direct = S > P1_LCAP;
-	const int niter = direct ? ke - kb : S;
-	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	TileThread t;
+	t.cand = s_cand; t.Ht = s_Ht; t.sv = s_sv; t.list = s_list; t.jmax = s_jmax;
+	t.JP = JP; t.JPP = JPP; t.xi = xi; t.ix = ix; t.kb = kb; t.Tmax = Tmax; t.y = y; t.x0 = x0;
+	t.direct = S > P1_LCAP;
+	t.niter = t.direct ? ke - kb : S;
+	if (!MULTI || maxlayer == 0) eval_classes<P1_CB, 1, CAP>(a, t);   // every survivor is the first interval of its column
+	else eval_classes<P1_CB / 2, 2, CAP>(a, t);                       // two hulls per class, four classes at a time
+}
 
-	for (int cb = 0; cb < Tmax; cb += P1_CB) {
-		double lo[P1_CB], hi[P1_CB];
-#pragma unroll
-		for (int q = 0; q < P1_CB; ++q) { lo[q] = inf; hi[q] = -inf; }
-		unsigned int complex_mask = 0;                  // classes whose union is not a single interval
-		unsigned int seen_mask = 0;                     // classes that already hold an interval
-		for (int s = 0; s < niter; ++s) {
-			int k;
-			if (!direct) k = s_list[s * TX + xi];
-			else k = kb + s;
-			const uint32_t w = s_sv[k];
-			if (direct && (uint32_t)(ix - (int)(w & 0xffu)) > ((w >> 8) & 0xffu)) continue;
-			const int d = abs((int)((w >> 16) & 0xffu) - ix);
-			const int te = min((int)(w >> 24), (int)s_jmax[d] + 1) - cb;   // classes [cb, cb + te) take this survivor
-			if (te <= 0) continue;
-			const double2 ab = s_cand[k];
-			const double2 *hp = reinterpret_cast<const double2 *>(s_Ht + (size_t)d * JPP + cb);
-			double h[P1_CB];
-#pragma unroll
-			for (int q = 0; q < P1_CB / 2; ++q) { const double2 v = hp[q]; h[2 * q] = v.x; h[2 * q + 1] = v.y; }
-			// branch-free: a class that does not take this survivor gets the cap -inf, i.e. the candidate
-			// (+inf, -inf), which leaves its hull untouched. A candidate that misses the running hull of a
-			// non-empty class makes the class "complex" (redone below with the general list).
-			const unsigned int valid = (te >= P1_CB) ? 0xffu : ((1u << te) - 1u);
-			unsigned int miss = 0;
-#pragma unroll
-			for (int q = 0; q < P1_CB; ++q) {
-				const double hq = (q < te) ? h[q] : -inf;
-				const double cs = ab.x - hq, ce = ab.y + hq;
-				miss |= (cs <= hi[q] && ce >= lo[q]) ? 0u : (1u << q);
-				lo[q] = cs < lo[q] ? cs : lo[q];
-				hi[q] = ce > hi[q] ? ce : hi[q];
-			}
-			complex_mask |= miss & valid & seen_mask;
-			seen_mask |= valid;
-		}
-#pragma unroll
-		for (int q = 0; q < P1_CB; ++q) {
-			const int j = cb + q;
-			if (j >= Tmax) break;
-			const unsigned long long slot = ((unsigned long long)y * JP + j) * a.nx + x0 + xi;
-			double2 out;
-			if (!((complex_mask >> q) & 1u)) out = make_double2(lo[q], hi[q]);   // (+inf, -inf) is the empty slot
-			else {
-				// general path: sorted list of disjoint intervals for this class
-				double2 ulist[CAP];
-				RunUnion<CAP> u(ulist);
-				for (int s = 0; s < niter; ++s) {
-					const int k = direct ? kb + s : (int)s_list[s * TX + xi];
-					const uint32_t w = s_sv[k];
-					if (direct && (uint32_t)(ix - (int)(w & 0xffu)) > ((w >> 8) & 0xffu)) continue;
-					const int d = abs((int)((w >> 16) & 0xffu) - ix);
-					if (j < min((int)(w >> 24), (int)s_jmax[d] + 1)) {
-						const double2 ab = s_cand[k];
-						const double hh = s_Ht[(size_t)d * JPP + j];
-						u.insert(ab.x - hh, ab.y + hh);
-					}
-				}
-				if (u.overflow) { redo_push(a.redo, slot); out = slot_empty(); }
-				else if (u.n == 0) out = slot_empty();
-				else if (u.n == 1) out = make_double2(u.s0, u.e0);
-				else {
-					const unsigned long long pb = atomicAdd(a.cursor, (unsigned long long)u.n);
-					if (pb + u.n <= a.pool_cap)
-						for (int t = 0; t < u.n; ++t) a.pool[pb + t] = u.L[t];
-					out = slot_pool(pb, (unsigned int)u.n);
-				}
-			}
-			a.mid[slot] = out;
+// LIST = false: launch over all tiles, one tile per CTA. LIST = true: launch over a collected list; a fixed
+// grid strides over it (the list length is only known on the device).
+template <int CAP, bool MULTI, bool LIST>
+__global__ void __launch_bounds__(P1_TX, MULTI ? 5 : 6) k_pass1_tile(Pass1TileArgs a)
+{
+	if (!LIST) pass1_tile_body<CAP, MULTI>(a, blockIdx.x);
+	else {
+		// one resident wave of CTAs pulls tiles from the list (tile costs vary a lot: dynamic beats strided)
+		__shared__ unsigned int s_next;
+		const unsigned int n = *a.tiles_count;
+		for (;;) {
+			if (threadIdx.x == 0) s_next = atomicAdd(a.tiles_next, 1u);
+			__syncthreads();
+			const unsigned int i = s_next;
+			if (i >= n) break;
+			pass1_tile_body<CAP, MULTI>(a, a.tiles[i]);
+			__syncthreads();                                // the next tile reuses the shared buffers (and s_next)
 		}
 	}
 }

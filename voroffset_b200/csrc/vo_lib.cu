@@ -38,6 +38,7 @@ struct vo_ctx {
 	cudaEvent_t kev[4] = {};          // [0,1] around k_pass1<CAP_FAST>, [2,3] around k_pass2<CAP_FAST>
 	bool kev_valid[2] = {false, false};
 	void *table_cache = nullptr;      // TableCache*: cap tables of the last radius, kept on the device
+	unsigned long long pool_hint = 0; // mid-pool entries the last pass 1 needed (+25 %)
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
 };
@@ -274,7 +275,7 @@ struct RedoBuf {
 	}
 };
 
-constexpr int NCTR = 8;   // [0] mid-pool cursor [1] stage-pool cursor [2] redo count [3] big-tile count [4] redo failures
+constexpr int NCTR = 8;   // [0] mid-pool cursor [1] stage-pool cursor [2] redo count [3] big-tile count [4] redo failures [5] multi-tile count
 
 int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 {
@@ -474,13 +475,14 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	m->nx = in->nx; m->ny = in->ny; m->J = t.J; m->R = R;
 	const unsigned long long nslots = ncols * (t.J + 1);
 	int rc = dalloc(ctx, &m->slots, nslots);
-	unsigned long long pool_cap = 65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4);
+	unsigned long long pool_cap = std::max(65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4), ctx->pool_hint);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, 2 * ncols);
 	Tmp<uint16_t> ty(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &ty.p, in->nspans);
-	Tmp<unsigned int> big_tiles(ctx);
+	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
+	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &multi_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nslots, 1ull), 1ull << 22);
 	if (rc == VO_OK) rc = rb.alloc(redo_cap);
@@ -508,22 +510,42 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
 			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
-			// first launch with a small candidate buffer (more CTAs per SM); tiles with denser segments are
-			// collected on the device and run by a second launch with the large buffer (its CTAs beyond the
-			// collected count exit at once, so no host round trip is needed in between)
-			const int cmax_small = 256;
-			g.cmax = cmax_small; g.tiles = nullptr; g.big_tiles = big_tiles.p;
-			g.big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
+			const double seg_est = k_in * (TX + 2 * t.J) * 1.3;
+			const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : cmax;
 			const size_t smem_small = pass1_tile_smem(t.J, cmax_small), smem_big = pass1_tile_smem(t.J, cmax);
-			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e)));
+			unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
+			unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
+			g.big_count = big_count; g.multi_tiles = multi_tiles.p; g.multi_count = multi_count;
+			// list launches: exactly one resident wave of CTAs striding over the collected tiles
+			auto wave = [&](const void *kernel, size_t smem) {
+				int occ = 1, sms = 148;
+				cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, P1_TX, smem);
+				cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+				return (unsigned int)std::min<unsigned long long>(ntiles, (unsigned long long)std::max(occ, 1) * sms);
+			};
 			cudaEventRecord(ctx->kev[0], ctx->stream);
-			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, P1_TX, smem_small, ctx->stream>>>(g);
+			// launch 1: single-interval tiles, small candidate buffer
+			g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.tiles_next = nullptr; g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
+			k_pass1_tile<CAP_FAST, false, false><<<(unsigned int)ntiles, P1_TX, smem_small, ctx->stream>>>(g);
+			ctx->launches++;
+			if (cmax_small < cmax) {        // launch 2: the single-interval tiles that need the large buffer
+				g.cmax = cmax; g.tiles = big_tiles.p; g.tiles_count = big_count; g.big_tiles = nullptr;
+				g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
+				k_pass1_tile<CAP_FAST, false, true><<<wave((const void *)k_pass1_tile<CAP_FAST, false, true>, smem_big), P1_TX, smem_big, ctx->stream>>>(g);
+				ctx->launches++;
+			}
+			// launch 3: tiles with multi-interval columns (two hulls per class); oversized ones go to the redo list
+			g.cmax = cmax_small < 512 ? 512 : cmax_small; g.tiles = multi_tiles.p; g.tiles_count = multi_count; g.big_tiles = nullptr;
+			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 7);
+			const size_t smem_multi = pass1_tile_smem(t.J, g.cmax);
+			k_pass1_tile<CAP_FAST, true, true><<<wave((const void *)k_pass1_tile<CAP_FAST, true, true>, smem_multi), P1_TX, smem_multi, ctx->stream>>>(g);
+			ctx->launches++;
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
-			g.cmax = cmax; g.tiles = big_tiles.p; g.big_tiles = nullptr;
-			k_pass1_tile<CAP_FAST><<<(unsigned int)ntiles, P1_TX, smem_big, ctx->stream>>>(g);
-			ctx->launches += 2;
 		} else if (nslots) {
 			// every class of every column is computed: all flag bytes = J + 1
 			cudaMemsetAsync(m->flags, t.J + 1, 2 * ncols, ctx->stream);
@@ -549,7 +571,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
 		}
 		if (h[4]) return bail(fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union"));
-		if (h[0] <= m->pool_cap) { m->pool_used = h[0]; *out = m; return VO_OK; }
+		if (h[0] <= m->pool_cap) { m->pool_used = h[0]; ctx->pool_hint = h[0] + h[0] / 4; *out = m; return VO_OK; }
 		dfree(ctx, m->pool);
 		m->pool = nullptr;
 		m->pool_cap = h[0] + h[0] / 8 + 1024;
