@@ -13,7 +13,7 @@
 
 namespace vo {
 
-constexpr int CAP_FAST = 16;    // running-union capacity of the first launch
+constexpr int CAP_FAST = 32;    // running-union capacity of the first launch
 constexpr int CAP_BIG = 512;    // capacity of the redo launch for lists that outgrew CAP_FAST
 constexpr int STAGE_INLINE = 2; // inline slots per staged list
 

@@ -459,11 +459,11 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	// tile kernel (pass1_tile.cuh) whenever its tables and tile fit in shared memory and a row segment's
 	// candidates are expected to fit; otherwise the one-thread-per-(x,y,j) kernel does everything
 	const int TX = P1_TX;
-	const int cmax = 1024;
+	const int cmax = 2048;      // largest candidate buffer of the tile kernel (12-bit candidate ids allow 4096)
 	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
 	// (small problems do not fill the machine with one thread per column: the simple kernel has J+1 times more threads)
 	const bool big = ncols * (unsigned long long)(J0 + 1) >= (2ull << 20) || ctx->force_tile_pass1;
-	const bool use_tile = J0 <= 63 && ncols > 0 && k_in * (TX + 2 * J0) <= 0.6 * cmax && big && !ctx->force_simple_pass1;
+	const bool use_tile = J0 <= 63 && ncols > 0 && k_in * (TX + 2 * J0) <= 0.75 * cmax && big && !ctx->force_simple_pass1;
 	TableCache *tc = nullptr;
 	VO_TRY(get_tables(ctx, R, use_tile, &tc));
 	const Tables &t = tc->t;
@@ -511,7 +511,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
 			const double seg_est = k_in * (TX + 2 * t.J) * 1.3;
-			const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : cmax;
+			const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : seg_est <= 1024 ? 1024 : cmax;
 			const size_t smem_small = pass1_tile_smem(t.J, cmax_small), smem_big = pass1_tile_smem(t.J, cmax);
 			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
