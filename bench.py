@@ -269,6 +269,8 @@ def main():
         sp_pin = torch.from_numpy(vol.spans).pin_memory()
         h2d = off_pin.numel() * 4 + sp_pin.numel() * 8
         d2h = 0
+        # pinned result buffers of the N > 1 path (the single-GPU call returns library-owned pinned blocks)
+        out_pin = [torch.empty(ncols + 1, dtype=torch.int32).pin_memory(), torch.empty(4 * sp_pin.numel(), dtype=torch.float64).pin_memory()]
 
         def step_e2e():
             nonlocal d2h
@@ -283,8 +285,11 @@ def main():
                 ctx.check(ctx.lib.vo_dvol_upload(ctx.handle, vol.nx, vol.ny, off_pin.data_ptr(), sp_pin.data_ptr(), C.byref(h)))
                 d = morpho.DeviceVolume(ctx, h, vol)
                 out = sd.dilate(d, R)
-                res = out.download()
-                d2h = (ncols + 1) * 4 + res.numSegments() * 16
+                nseg_out = out.info()[2]
+                if out_pin[1].numel() < 2 * nseg_out:
+                    out_pin[1] = torch.empty(int(2.2 * nseg_out), dtype=torch.float64).pin_memory()
+                ctx.check(ctx.lib.vo_dvol_download(ctx.handle, out.handle, out_pin[0].data_ptr(), out_pin[1].data_ptr()))
+                d2h = (ncols + 1) * 4 + nseg_out * 16
                 out.free(); d.free()
 
         for _ in range(max(1, min(a.warmup, 2))):

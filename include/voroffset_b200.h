@@ -121,6 +121,11 @@ int  vo_dvol_info(const vo_dvol *vol, int *nx, int *ny, uint64_t *nspans, const 
 void vo_dvol_free(vo_ctx *ctx, vo_dvol *vol);
 /* Copy of rows [y0, y1) of a resident volume (a y-slab; rows are contiguous in the x-fastest layout). */
 int  vo_dvol_rows(vo_ctx *ctx, const vo_dvol *vol, int y0, int y1, vo_dvol **out);
+/* Rows [y0, y1) copied straight into caller-owned DEVICE buffers (d_off: (y1-y0)*nx+1 uint32, rebased to
+ * start at 0; d_spans: room for cap_spans intervals). *nspans is always set; the spans are only copied
+ * when they fit. This is what a halo exchange sends (voroffset_b200/slab.py).                          */
+int  vo_dvol_rows_to(vo_ctx *ctx, const vo_dvol *vol, int y0, int y1, void *d_off, void *d_spans,
+                     uint64_t cap_spans, uint64_t *nspans);
 /* Concatenate up to three y-slabs of equal nx (NULL entries are skipped).                             */
 int  vo_dvol_concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const vo_dvol *c, vo_dvol **out);
 

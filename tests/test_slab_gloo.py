@@ -30,15 +30,19 @@ class OracleSlabBackend:
         off = vol.off[c0:c1 + 1].astype(np.int64)
         return (off - off[0]), vol.spans[off[0]:off[-1]]
 
-    def rows_as_tensors(self, vol, y0, y1):
-        off, sp = self._rows(vol, y0, y1)
-        return torch.from_numpy(off.astype(np.int32)), torch.from_numpy(np.ascontiguousarray(sp).reshape(-1).copy())
-
-    def empty_tensors(self, n_off, n_spans):
+    def new_tensors(self, n_off, n_spans):
         return torch.empty(n_off, dtype=torch.int32), torch.empty(max(2 * n_spans, 2), dtype=torch.float64)
 
+    def rows_into(self, vol, y0, y1, off_t, spans_t):
+        off, sp = self._rows(vol, y0, y1)
+        off_t[: off.size] = torch.from_numpy(off.astype(np.int32))
+        n = sp.shape[0]
+        if n and 2 * n <= spans_t.numel():
+            spans_t[: 2 * n] = torch.from_numpy(np.ascontiguousarray(sp).reshape(-1).copy())
+        return n
+
     def from_tensors(self, nx, ny, off, spans, n_spans, like):
-        return like.like(nx, ny, off.numpy().astype(np.uint32), spans.numpy()[:2 * n_spans].reshape(-1, 2))
+        return like.like(nx, ny, off.numpy()[: nx * ny + 1].astype(np.uint32), spans.numpy()[:2 * n_spans].reshape(-1, 2).copy())
 
     def concat(self, parts):
         parts = [p for p in parts if p is not None]
@@ -77,7 +81,19 @@ def _worker(rank, world, port, radius, out_dir):
     mine = slab.shard_rows(vol, rank, world)
     sd = slab.SlabDilation(OracleSlabBackend(), rank, world)
     out = sd.dilate(mine, radius)
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), off=out.off, spans=out.spans, ny=out.ny, halo=sd.last_halo_bytes)
+    msgs = [sd.last_messages]
+    # steady state: same link objects, one message batch per step; then a much denser volume (the halo
+    # outgrows the agreed capacity -> overflow follow-up), then back
+    out2 = sd.dilate(mine, radius)
+    msgs.append(sd.last_messages)
+    dense = slab.shard_rows(synth.random_volume(vol.nx, vol.ny, kmax=40, seed=5, zrange=400.0), rank, world)
+    out3 = sd.dilate(dense, radius)
+    msgs.append(sd.last_messages)
+    out4 = sd.dilate(mine, radius)
+    msgs.append(sd.last_messages)
+    assert out2.bit_equal(out) and out4.bit_equal(out)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), off=out.off, spans=out.spans, ny=out.ny, halo=sd.last_halo_bytes,
+             msgs=np.array(msgs), d_off=out3.off, d_spans=out3.spans)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -99,6 +115,12 @@ def test_slabs_reproduce_the_single_process_result(tmp_path, world, radius):
         assert np.array_equal(z["spans"].view(np.uint64), piece.spans.view(np.uint64)), f"rank {r}: endpoints differ"
         if radius >= 1 and world > 1:
             assert int(z["halo"]) > 0
+            msgs = z["msgs"].tolist()
+            assert msgs[0] == 2 and msgs[1] == 1 and msgs[3] == 1      # count swap + payload, then one batch per step
+            assert msgs[2] in (1, 2)                                    # overflow follow-up when the dense halo did not fit
+        dense = synth.random_volume(vol.nx, vol.ny, kmax=40, seed=5, zrange=400.0)
+        dpiece = slab.shard_rows(Oracle(threads=2).morph3d(dense, "dilation", radius, "ours"), r, world)
+        assert np.array_equal(z["d_off"], dpiece.off) and np.array_equal(z["d_spans"].view(np.uint64), dpiece.spans.view(np.uint64))
 
 
 def test_slab_bounds_cover_everything():

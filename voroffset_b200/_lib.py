@@ -29,7 +29,7 @@ EXPORTS = [
     "vo_launch_count", "vo_morph3d", "vo_morph2d", "vo_xor3d", "vo_dvol_upload", "vo_dvol_download",
     "vo_dvol_info", "vo_dvol_free", "vo_dvol_rows", "vo_dvol_concat_rows", "vo_morph3d_dev", "vo_xor3d_dev",
     "vo_pass1_dev", "vo_pass2_dev", "vo_dmid_free", "vo_dmid_info", "vo_morph2d_dev",
-    "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device", "vo_set_option",
+    "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device", "vo_set_option", "vo_dvol_rows_to",
 ]
 
 _lib = None
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     L.vo_dvol_free.restype = None
     L.vo_dvol_rows.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]
     L.vo_dvol_concat_rows.argtypes = [_vp, _vp, _vp, _vp, C.POINTER(_vp)]
+    L.vo_dvol_rows_to.argtypes = [_vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.vo_morph3d_dev.argtypes = [_vp, C.c_int, C.c_int, _vp, C.c_double, C.c_double, C.c_double,
                                  C.POINTER(_vp), _f64p, _f64p]
     L.vo_xor3d_dev.argtypes = [_vp, _vp, _vp, C.c_double, C.c_double, C.c_double, C.POINTER(_vp), _f64p]

@@ -1083,6 +1083,30 @@ int vo_dvol_rows(vo_ctx *ctx, const vo_dvol *v, int y0, int y1, vo_dvol **out)
 	return VO_OK;
 }
 
+int vo_dvol_rows_to(vo_ctx *ctx, const vo_dvol *v, int y0, int y1, void *d_off, void *d_spans, uint64_t cap_spans, uint64_t *nspans)
+{
+	if (!ctx || !v || !d_off || !nspans) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	if (y0 < 0 || y1 > v->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "row range outside the volume");
+	const unsigned long long c0 = (unsigned long long)y0 * v->nx, c1 = (unsigned long long)y1 * v->nx;
+	uint32_t ends[2] = {0, 0};
+	VO_CUDA(cudaMemcpyAsync(&ends[0], v->off + c0, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaMemcpyAsync(&ends[1], v->off + c1, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	const uint64_t n = ends[1] - ends[0];
+	*nspans = n;
+	VO_CUDA(cudaMemcpyAsync(d_off, v->off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+	k_rebase<<<blocks_for(c1 - c0 + 1, 256), 256, 0, ctx->stream>>>(static_cast<uint32_t *>(d_off), c1 - c0 + 1, ends[0], 0u);
+	ctx->launches++;
+	if (n && n <= cap_spans) {
+		if (!d_spans) return fail(ctx, VO_ERR_ARG, "d_spans is NULL");
+		VO_CUDA(cudaMemcpyAsync(d_spans, v->spans + ends[0], n * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	return VO_OK;
+}
+
 int vo_dvol_concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const vo_dvol *c, vo_dvol **out)
 {
 	if (!ctx || !out) return VO_ERR_ARG;

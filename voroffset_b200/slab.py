@@ -4,15 +4,22 @@ Why y-slabs: on the device the first pass gathers along x inside each row (slab-
 pass unions radius classes along y, reaching at most J = floor(R) rows (the reference's locality:
 Voronoi2D.cpp:651,658 / SeparatePower2D.cpp:241,266 - a seed influences at most floor(R) lines). With the
 x-fastest layout (CompressedVolume.h:28-29) the J boundary rows of a slab are one contiguous CSR range,
-so the halo is a plain (offsets, spans) pair: no packing kernel, just two point-to-point messages per
-neighbour (sizes first, payload second) over torch.distributed - NCCL/NVLink on GPUs, gloo in the CPU
-tests. This is the reference's dormant TBB decomposition (VoronoiVorPower.cpp:41-63,70-92: tasks own
-disjoint slices) stretched across devices; SURVEY.md 8(e) describes the same scheme for x-slabs, the
-axis differs only because our pass order is x then y.
+so the halo is a plain (offsets, spans) pair: no packing kernel, point-to-point messages to the two
+neighbours over torch.distributed - NCCL/NVLink on GPUs, gloo in the CPU tests. This is the reference's
+dormant TBB decomposition (VoronoiVorPower.cpp:41-63,70-92: tasks own disjoint slices) stretched across
+devices; SURVEY.md 8(e) describes the same scheme for x-slabs, the axis differs only because our pass
+order is x then y.
 
 The halo carries INPUT rows (exchanged before pass 1; each rank then runs pass 1 on its J halo rows too).
 That costs 2J/ny_local extra pass-1 work and moves ~J*nx*(4 + 16 k_in) bytes per neighbour instead of
-the (J+1)x larger mid rows.
+the much larger mid rows.
+
+Message protocol (per neighbour and direction). The number of intervals in a halo is data dependent, the
+receive buffer must be posted with a size. First call: the two sides swap their interval counts, then the
+payload. Afterwards both sides remember a capacity for each direction (1.5x the last count, a pure
+function of what was sent, so sender and receiver always agree) and a step is ONE batch of messages:
+offsets + [count, overflow flag] in a fixed-size int32 tensor, spans padded to the agreed capacity. If a
+halo ever outgrows its capacity the flag is set and the exact-size payload follows in a second message.
 
 The driver is written against a small backend interface so that the exchange / cropping logic runs in
 the world_size-2 gloo tests on CPU (tests inject a checker-backed backend); the product backend below
@@ -44,6 +51,11 @@ def slab_bounds(ny: int, world: int):
     return out
 
 
+def _grow(n: int) -> int:
+    """Capacity both sides derive from a transmitted count."""
+    return max(1024, int(n * 1.5) + 16)
+
+
 class CudaSlabBackend:
     """Product backend: volumes are `DeviceVolume`s, halos travel as CUDA tensors."""
 
@@ -55,23 +67,19 @@ class CudaSlabBackend:
         nx, ny, n, _, _ = vol.info()
         return nx, ny
 
-    def rows_as_tensors(self, vol: DeviceVolume, y0: int, y1: int):
-        part = vol.rows(y0, y1)
-        nx, ny, n, _, _ = part.info()
-        off = torch.empty(nx * ny + 1, dtype=torch.int32, device=self.device)
-        spans = torch.empty(max(n, 1) * 2, dtype=torch.float64, device=self.device)
-        torch.cuda.synchronize(self.device)
-        # vo_dvol_download accepts device destinations (cudaMemcpyDefault) and synchronises its stream
-        self.ctx.check(self.ctx.lib.vo_dvol_download(self.ctx.handle, part.handle, off.data_ptr(), spans.data_ptr()))
-        part.free()
-        return off, spans[: 2 * n]
-
-    def empty_tensors(self, n_off: int, n_spans: int):
+    def new_tensors(self, n_off: int, n_spans: int):
         return (torch.empty(n_off, dtype=torch.int32, device=self.device),
                 torch.empty(max(2 * n_spans, 2), dtype=torch.float64, device=self.device))
 
+    def rows_into(self, vol: DeviceVolume, y0: int, y1: int, off: torch.Tensor, spans: torch.Tensor) -> int:
+        """Rows [y0, y1) into (off[: (y1-y0)*nx+1], spans); returns the interval count (spans untouched if too small)."""
+        n = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.vo_dvol_rows_to(self.ctx.handle, vol.handle, y0, y1, off.data_ptr(), spans.data_ptr(),
+                                                    spans.numel() // 2, C.byref(n)))
+        return int(n.value)
+
     def from_tensors(self, nx: int, ny: int, off: torch.Tensor, spans: torch.Tensor, n_spans: int, like: DeviceVolume):
-        torch.cuda.synchronize(self.device)
+        torch.cuda.current_stream(self.device).synchronize()
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.vo_dvol_from_device(self.ctx.handle, nx, ny, off.data_ptr(), spans.data_ptr(),
                                                         n_spans, C.byref(h)))
@@ -96,6 +104,15 @@ class CudaSlabBackend:
             vol.free()
 
 
+class _Link:
+    """Per-neighbour message buffers and the capacities agreed so far."""
+
+    def __init__(self):
+        self.cap_out = None      # capacity (intervals) the neighbour expects from me
+        self.cap_in = None       # capacity I expect from the neighbour
+        self.off_out = self.sp_out = self.off_in = self.sp_in = None
+
+
 class SlabDilation:
     """Dilation of a y-slab-sharded volume. Every rank calls `dilate` with its own rows; the result is
     the rank's rows of the global dilation (bit-identical to the single-GPU result)."""
@@ -107,51 +124,107 @@ class SlabDilation:
         self.world = dist.get_world_size(group) if world is None else world
         self.last_ms = (0.0, 0.0)
         self.last_halo_bytes = 0
+        self.last_messages = 0
+        self._links = {}
+        self._shape = None
+
+    # -- messaging --------------------------------------------------------------------------------
+    def _batch(self, ops):
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            self.last_messages += 1
 
     def _exchange(self, vol, nx: int, ny: int, J: int):
         """Send my first J rows to rank-1 and my last J rows to rank+1; receive theirs."""
         be = self.backend
-        prev_r = self.rank - 1 if self.rank > 0 else None
-        next_r = self.rank + 1 if self.rank < self.world - 1 else None
-        send = {}
-        if prev_r is not None:
-            send[prev_r] = be.rows_as_tensors(vol, 0, J)
-        if next_r is not None:
-            send[next_r] = be.rows_as_tensors(vol, ny - J, ny)
-        # 1st message: span counts
-        dev = next(iter(send.values()))[0].device if send else None
-        counts_out = {r: torch.tensor([t[1].numel() // 2], dtype=torch.int64, device=dev) for r, t in send.items()}
-        counts_in = {r: torch.zeros(1, dtype=torch.int64, device=dev) for r in send}
+        if self._shape != (nx, J):               # geometry changed: forget the agreed capacities
+            self._links, self._shape = {}, (nx, J)
+        L = J * nx + 1                           # offsets of a halo
+        nbrs = [(r, rows) for r, rows in ((self.rank - 1, (0, J)), (self.rank + 1, (ny - J, ny))) if 0 <= r < self.world]
+        links = {r: self._links.setdefault(r, _Link()) for r, _ in nbrs}
+        self.last_messages, nbytes = 0, 0
+
+        # fill the send buffers (offsets + header [count, overflow]; spans if they fit the agreed capacity)
+        n_out = {}
+        for r, (y0, y1) in nbrs:
+            lk = links[r]
+            if lk.off_out is None or lk.sp_out.numel() // 2 < (lk.cap_out or 1024):
+                lk.off_out, lk.sp_out = be.new_tensors(L + 2, lk.cap_out or 1024)
+            n = be.rows_into(vol, y0, y1, lk.off_out, lk.sp_out)
+            if lk.cap_out is not None and n > lk.cap_out or lk.cap_out is None and n > lk.sp_out.numel() // 2:
+                # does not fit: exact-size payload (second message / first call)
+                _, exact = be.new_tensors(1, n)
+                n = be.rows_into(vol, y0, y1, lk.off_out, exact)
+                lk.exact_out = exact
+            else:
+                lk.exact_out = None
+            n_out[r] = n
+
+        first = [r for r, _ in nbrs if links[r].cap_out is None]
+        if first:
+            # first call on this link: swap the counts, then exact-size payloads
+            dev = links[first[0]].off_out.device
+            c_out = {r: torch.tensor([n_out[r]], dtype=torch.int64, device=dev) for r in first}
+            c_in = {r: torch.zeros(1, dtype=torch.int64, device=dev) for r in first}
+            ops = []
+            for r in first:
+                ops += [dist.P2POp(dist.isend, c_out[r], r, self.group), dist.P2POp(dist.irecv, c_in[r], r, self.group)]
+            self._batch(ops)
+            for r in first:
+                lk = links[r]
+                lk.cap_in, lk.cap_out = _grow(int(c_in[r].item())), _grow(n_out[r])
+                lk.n_in_first = int(c_in[r].item())
+
+        # main message: fixed-size offsets (+ header) and capacity-padded spans
         ops = []
-        for r in send:
-            ops.append(dist.P2POp(dist.isend, counts_out[r], r, self.group))
-            ops.append(dist.P2POp(dist.irecv, counts_in[r], r, self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        # 2nd message: offsets + spans
-        recv = {}
-        ops = []
-        nbytes = 0
-        for r in send:
-            n_in = int(counts_in[r].item())
-            off_in, sp_in = be.empty_tensors(J * nx + 1, n_in)
-            recv[r] = (off_in, sp_in, n_in)
-            off_out, sp_out = send[r]
-            ops.append(dist.P2POp(dist.isend, off_out, r, self.group))
-            ops.append(dist.P2POp(dist.irecv, off_in, r, self.group))
-            if sp_out.numel():
-                ops.append(dist.P2POp(dist.isend, sp_out, r, self.group))
-            if n_in:
-                ops.append(dist.P2POp(dist.irecv, sp_in[: 2 * n_in], r, self.group))
-            nbytes += off_out.numel() * 4 + sp_out.numel() * 8
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        for r, _ in nbrs:
+            lk = links[r]
+            overflow = 1 if (lk.exact_out is not None and r not in first) else 0
+            hdr = torch.tensor([n_out[r] & 0x7fffffff, overflow], dtype=torch.int32, device=lk.off_out.device)
+            lk.off_out[L:L + 2] = hdr
+            if lk.off_in is None or lk.sp_in.numel() // 2 < lk.cap_in:
+                lk.off_in, lk.sp_in = be.new_tensors(L + 2, lk.cap_in)
+            ops += [dist.P2POp(dist.isend, lk.off_out, r, self.group), dist.P2POp(dist.irecv, lk.off_in, r, self.group)]
+            if r in first:
+                # exact sizes known from the count swap
+                src = lk.exact_out if lk.exact_out is not None else lk.sp_out
+                if n_out[r]:
+                    ops.append(dist.P2POp(dist.isend, src[: 2 * n_out[r]], r, self.group))
+                if lk.n_in_first:
+                    ops.append(dist.P2POp(dist.irecv, lk.sp_in[: 2 * lk.n_in_first], r, self.group))
+                nbytes += 2 * n_out[r] * 8
+            else:
+                ops += [dist.P2POp(dist.isend, lk.sp_out[: 2 * lk.cap_out], r, self.group),
+                        dist.P2POp(dist.irecv, lk.sp_in[: 2 * lk.cap_in], r, self.group)]
+                nbytes += 2 * lk.cap_out * 8
+            nbytes += (L + 2) * 4
+        self._batch(ops)
+
+        # headers, overflow follow-ups, new capacities
+        n_in, ops, exact_in = {}, [], {}
+        for r, _ in nbrs:
+            lk = links[r]
+            hdr = lk.off_in[L:L + 2].tolist()
+            n_in[r] = int(hdr[0])
+            if r not in first:
+                if hdr[1]:                                      # neighbour's halo outgrew the capacity
+                    _, exact_in[r] = be.new_tensors(1, n_in[r])
+                    ops.append(dist.P2POp(dist.irecv, exact_in[r][: 2 * n_in[r]], r, self.group))
+                if lk.exact_out is not None:
+                    ops.append(dist.P2POp(dist.isend, lk.exact_out[: 2 * n_out[r]], r, self.group))
+                    nbytes += 2 * n_out[r] * 8
+        self._batch(ops)
+        halos = {}
+        for r, _ in nbrs:
+            lk = links[r]
+            spans_in = exact_in.get(r, lk.sp_in)
+            halos[r] = be.from_tensors(nx, J, lk.off_in, spans_in, n_in[r], like=vol)
+            lk.cap_in = max(lk.cap_in, _grow(n_in[r]))
+            lk.cap_out = max(lk.cap_out, _grow(n_out[r]))
+            lk.exact_out = None
         self.last_halo_bytes = nbytes
-        halo_prev = be.from_tensors(nx, J, *recv[prev_r], like=vol) if prev_r is not None else None
-        halo_next = be.from_tensors(nx, J, *recv[next_r], like=vol) if next_r is not None else None
-        return halo_prev, halo_next
+        return halos.get(self.rank - 1), halos.get(self.rank + 1)
 
     def dilate(self, vol, radius: float):
         be = self.backend
