@@ -289,3 +289,17 @@ def test_dropin_subclasses_match_reference_operators():
     print(res.stdout)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("OK") == 9
+
+
+def test_pipelined_host_path_equals_plain_path(ctx):
+    """Large host-buffer dilations overlap upload / passes / download band by band (vo_lib.cu:
+    dilate_ours_pipelined); the result must be the plain path's, bit for bit."""
+    vol = synth.torus_z(1792, padding=0)
+    op = morpho.make_operator("ours", ctx)
+    ctx.set_option("pipeline", "off")
+    plain, _, _ = op.dilation(vol, 31.5)
+    ctx.set_option("pipeline", "on")
+    piped, t1, _ = op.dilation(vol, 31.5)
+    assert piped.bit_equal(plain) and t1 > 0
+    again, _, _ = op.dilation(vol, 31.5)          # second call reuses the size hints
+    assert again.bit_equal(plain)

@@ -52,6 +52,7 @@ struct YThreshArgs {
 	const double2 *spans;
 	const double *Emono;    // J+2: Emono[j], j = 1..J; Emono[J+1] = +inf
 	uint16_t *ty;           // per interval: Ty_up | Ty_dn << 8, each in [1, J+1]
+	unsigned long long c_begin, c_end;   // columns processed by this launch (a band of rows, or everything)
 };
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
@@ -66,8 +67,8 @@ __global__ void __launch_bounds__(256) k_ythresh(YThreshArgs a)
 	extern __shared__ double s_E[];
 	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) s_E[i] = a.Emono[i];
 	__syncthreads();
-	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= (unsigned long long)a.nx * a.ny) return;
+	const unsigned long long c = a.c_begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= a.c_end) return;
 	const uint32_t o0 = a.off[c], o1 = a.off[c + 1];
 	if (o0 == o1) return;
 	const int y = (int)(c / (unsigned)a.nx);
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(256) k_ythresh(YThreshArgs a)
 // ---- pass 1 ------------------------------------------------------------------------------------------
 struct Pass1TileArgs {
 	int nx, ny, J, cmax, tiles_x;
+	unsigned int tile0;     // first tile of a launch over all tiles of a band of rows
 	const uint32_t *off;
 	const double2 *spans;
 	const uint16_t *ty;     // k_ythresh output
@@ -408,7 +410,7 @@ __device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const un
 template <int CAP, bool MULTI, bool LIST>
 __global__ void __launch_bounds__(P1_TX, MULTI ? 5 : 6) k_pass1_tile(Pass1TileArgs a)
 {
-	if (!LIST) pass1_tile_body<CAP, MULTI>(a, blockIdx.x);
+	if (!LIST) pass1_tile_body<CAP, MULTI>(a, a.tile0 + blockIdx.x);
 	else {
 		// one resident wave of CTAs pulls tiles from the list (tile costs vary a lot: dynamic beats strided)
 		__shared__ unsigned int s_next;

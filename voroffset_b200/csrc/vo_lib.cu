@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -39,6 +40,10 @@ struct vo_ctx {
 	bool kev_valid[2] = {false, false};
 	void *table_cache = nullptr;      // TableCache*: cap tables of the last radius, kept on the device
 	unsigned long long pool_hint = 0; // mid-pool entries the last pass 1 needed (+25 %)
+	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
+	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
+	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
+	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
 };
@@ -266,16 +271,17 @@ struct RedoBuf {
 	Redo rd{};
 	explicit RedoBuf(vo_ctx *c) : ctx(c) {}
 	~RedoBuf() { dfree(ctx, rd.list); }
-	int alloc(unsigned int cap)
+	int alloc(unsigned int cap, int counter = 2)
 	{
 		VO_TRY(dalloc(ctx, &rd.list, cap));
 		rd.cap = cap;
-		rd.count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 2);
+		rd.count = reinterpret_cast<unsigned int *>(ctx->d_ctr + counter);
 		return VO_OK;
 	}
 };
 
-constexpr int NCTR = 8;   // [0] mid-pool cursor [1] stage-pool cursor [2] redo count [3] big-tile count [4] redo failures [5] multi-tile count
+constexpr int NCTR = 16;  // pass 1: [0] mid-pool cursor [2] redo count [3] big-tile count [4] redo failures [5] multi-tile count
+                          //         [6] [7] list cursors; staged gathers (pass 2, ...): [1] stage-pool cursor [8] redo count [9] failures
 
 int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 {
@@ -299,7 +305,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	RedoBuf rb(ctx);
 	VO_TRY(sb.alloc(nlists, pool_guess));
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nlists, 1ull), 1ull << 22);
-	VO_TRY(rb.alloc(redo_cap));
+	VO_TRY(rb.alloc(redo_cap, 8));
 	vo_dvol *v = nullptr;
 	VO_TRY(new_dvol(ctx, nx, ny, &v));
 	struct Guard { vo_ctx *c; vo_dvol *&p; ~Guard() { if (p) free_dvol(c, p); } } guard{ctx, v};
@@ -307,14 +313,16 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	Tmp<unsigned long long> sums(ctx);
 	VO_TRY(dalloc(ctx, &sums.p, (unsigned long long)ntiles + 1));
 	for (int attempt = 0; attempt < 3; ++attempt) {
-		VO_CUDA(cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), ctx->stream));
+		// only the counters of the staged gather: a pass 1 may be in flight on the same stream (pipelined path)
+		VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
+		VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
 		unsigned long long h[NCTR] = {0}, total = 0;
 		if (nlists) {
 			args.st = sb.st;
 			args.redo = rb.rd;
 			args.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
 			launch_fast(args);
-			args.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
+			args.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
 			launch_big(args, REDO_GRID);
 			k_scan_reduce<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p);
 			k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(sums.p, ntiles);
@@ -326,8 +334,8 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 			VO_CUDA(cudaMemsetAsync(v->off, 0, sizeof(uint32_t), ctx->stream));
 		}
 		VO_TRY(read_counters(ctx, h));
-		if (h[2] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
-		if (h[4]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
+		if (h[8] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
+		if (h[9]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
 		if (h[1] > sb.st.pool_cap) { VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024)); continue; }
 		if (total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
 		VO_TRY(dalloc(ctx, &v->spans, total));
@@ -502,10 +510,11 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		if (nslots && tile_now) {
 			YThreshArgs yt;
 			yt.nx = in->nx; yt.ny = in->ny; yt.J = t.J; yt.off = in->off; yt.spans = in->spans; yt.Emono = tt.Emono; yt.ty = ty.p;
+			yt.c_begin = 0; yt.c_end = ncols;
 			k_ythresh<<<blocks_for(ncols, 256), 256, (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(yt);
 			ctx->launches++;
 			Pass1TileArgs g;
-			g.nx = in->nx; g.ny = in->ny; g.J = t.J;
+			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.tile0 = 0;
 			g.tiles_x = (in->nx + TX - 1) / TX;
 			g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
 			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
@@ -877,6 +886,292 @@ int download_new(vo_ctx *ctx, const vo_dvol *v, uint32_t **out_off, double **out
 	return VO_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Pipelined host-buffer dilation ('ours'): the grid is cut into bands of rows and the three stages
+//   H2D of band b+1  |  pass 1 of band b, pass 2 + compaction of band b-1  |  D2H of band b-2
+// run concurrently on three streams, so the PCIe transfers hide behind the kernels (and vice versa).
+// Pass 1 of a row needs only that row (its y-thresholds also the two neighbouring rows), pass 2 of a row
+// needs the mid rows within floor(R): band b-1 can be finished as soon as pass 1 of band b is enqueued.
+// Results are identical to the plain path (same kernels, same tables). Returns PIPE_NA when the case is
+// not worth / not able to be pipelined (small grids, simple-kernel cases, any pool overflow): the caller
+// then takes the plain path.
+// ---------------------------------------------------------------------------------------------------
+constexpr int PIPE_NA = -1;
+
+// copy streams and events live in the context (created on first use, destroyed with it)
+struct PipeRes {
+	vo_ctx *ctx;
+	cudaStream_t s_in = nullptr, s_out = nullptr;
+	size_t used = 0;
+	explicit PipeRes(vo_ctx *c) : ctx(c) {}
+	~PipeRes()
+	{
+		if (s_in) cudaStreamSynchronize(s_in);
+		if (s_out) cudaStreamSynchronize(s_out);
+	}
+	bool init()
+	{
+		if (!ctx->s_in && cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess) return false;
+		if (!ctx->s_out && cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess) return false;
+		s_in = ctx->s_in; s_out = ctx->s_out;
+		return true;
+	}
+	cudaEvent_t event()
+	{
+		if (used == ctx->pipe_ev.size()) {
+			cudaEvent_t e = nullptr;
+			cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+			ctx->pipe_ev.push_back(e);
+		}
+		return ctx->pipe_ev[used++];
+	}
+};
+
+int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans, double R,
+                          uint32_t **out_off, double **out_spans, uint64_t *out_nspans, PassTimes *pt)
+{
+	if (ctx->force_simple_pass1 || ctx->no_pipeline) return PIPE_NA;
+	if (check_radius(ctx, R) != VO_OK) return PIPE_NA;             // let the plain path report it
+	const int J = (int)std::floor(R);
+	const unsigned long long ncols = (unsigned long long)nx * ny;
+	if (nx <= 0 || ny <= 0 || !off || off[0] != 0 || ncols >= (1ull << 32) - 8) return PIPE_NA;
+	const uint64_t nspans = off[ncols];
+	const int TX = P1_TX, cmax = 2048;
+	const double k_in = (double)nspans / (double)ncols;
+	// about six bands: enough to overlap, few enough that the per-band launch / readback overhead stays small
+	const int BH = std::max(2 * (J + 1), ((ny + 5) / 6 + 7) & ~7);   // band height >= reach of pass 2
+	const int nb = (ny + BH - 1) / BH;
+	if (J > 63 || nb < 3 || ncols * (unsigned long long)(J + 1) < (48ull << 20) || k_in * (TX + 2 * J) > 0.75 * cmax) return PIPE_NA;
+	if (nspans && !spans) return PIPE_NA;
+
+	TableCache *tc = nullptr;
+	VO_TRY(get_tables(ctx, R, true, &tc));
+	const Tables &t = tc->t;
+	DevTables &dt = tc->dt;
+	TileTables &tt = tc->tt;
+
+	PipeRes pr(ctx);
+	if (!pr.init()) { cudaGetLastError(); return PIPE_NA; }
+
+	// device input, mid volume, scratch
+	vo_dvol *in = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &in));
+	struct InGuard { vo_ctx *c; vo_dvol *p; ~InGuard() { free_dvol(c, p); } } in_guard{ctx, in};
+	VO_TRY(dalloc(ctx, &in->spans, nspans));
+	in->nspans = nspans;
+	vo_dmid *m = new (std::nothrow) vo_dmid();
+	if (!m) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
+	struct MidGuard { vo_ctx *c; vo_dmid *p; ~MidGuard() { vo_dmid_free(c, p); } } mid_guard{ctx, m};
+	m->nx = nx; m->ny = ny; m->J = J; m->R = R;
+	const unsigned long long nslots = ncols * (J + 1);
+	VO_TRY(dalloc(ctx, &m->slots, nslots));
+	m->pool_cap = std::max(65536ull + (unsigned long long)(J + 1) * (nspans / 4), ctx->pool_hint);
+	VO_TRY(dalloc(ctx, &m->pool, m->pool_cap));
+	VO_TRY(dalloc(ctx, &m->flags, 2 * ncols));
+	Tmp<uint16_t> ty(ctx);
+	VO_TRY(dalloc(ctx, &ty.p, nspans));
+	const int tiles_x = (nx + TX - 1) / TX;
+	const unsigned long long ntiles = (unsigned long long)tiles_x * ny;
+	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
+	VO_TRY(dalloc(ctx, &big_tiles.p, ntiles));
+	VO_TRY(dalloc(ctx, &multi_tiles.p, ntiles));
+	RedoBuf rb(ctx);
+	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(nslots, 1ull << 22);
+	VO_TRY(rb.alloc(redo_cap));
+
+	// result buffers (pinned): offsets are exact, the span buffer is sized from the last result (grown if needed)
+	uint32_t *ho = (uint32_t *)host_block((ncols + 1) * sizeof(uint32_t));
+	uint64_t hs_cap = std::max<uint64_t>(ctx->out_hint, 2 * nspans + (1u << 16));
+	double *hs = (double *)host_block(hs_cap * sizeof(double2));
+	auto drop_host = [&]() { vo_free(ho); vo_free(hs); };
+	if (!ho || !hs) { drop_host(); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
+
+	// stage 0: all uploads are enqueued up front, one event per band
+	std::vector<cudaEvent_t> ev_in(nb), ev_done(nb);
+	for (int b = 0; b < nb; ++b) {
+		const int y0 = b * BH, y1 = std::min(ny, y0 + BH);
+		const unsigned long long c0 = (unsigned long long)y0 * nx, c1 = (unsigned long long)y1 * nx;
+		cudaMemcpyAsync(in->off + c0, off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, pr.s_in);
+		if (off[c1] > off[c0])
+			cudaMemcpyAsync(in->spans + off[c0], spans + 2 * (size_t)off[c0], (size_t)(off[c1] - off[c0]) * sizeof(double2), cudaMemcpyHostToDevice, pr.s_in);
+		ev_in[b] = pr.event();
+		ev_done[b] = pr.event();
+		cudaEventRecord(ev_in[b], pr.s_in);
+	}
+	if (cudaGetLastError() != cudaSuccess) { drop_host(); return PIPE_NA; }
+
+	cudaStream_t sm = ctx->stream;
+	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
+	cudaEventRecord(ctx->ev[0], sm);
+
+	// launch parameters shared by all bands
+	YThreshArgs yt;
+	yt.nx = nx; yt.ny = ny; yt.J = J; yt.off = in->off; yt.spans = in->spans; yt.Emono = tt.Emono; yt.ty = ty.p;
+	Pass1TileArgs g;
+	g.nx = nx; g.ny = ny; g.J = J; g.tiles_x = tiles_x;
+	g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
+	g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
+	unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
+	unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
+	g.big_count = big_count; g.multi_tiles = multi_tiles.p; g.multi_count = multi_count;
+	const double seg_est = k_in * (TX + 2 * J) * 1.3;
+	const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : seg_est <= 1024 ? 1024 : cmax;
+	const size_t smem_small = pass1_tile_smem(J, cmax_small), smem_big = pass1_tile_smem(J, cmax);
+	const int cmax_multi = cmax_small < 512 ? 512 : cmax_small;
+	const size_t smem_multi = pass1_tile_smem(J, cmax_multi);
+	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+	int sms = 148, occ_big = 1, occ_multi = 1;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_big, k_pass1_tile<CAP_FAST, false, true>, P1_TX, smem_big);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_multi, k_pass1_tile<CAP_FAST, true, true>, P1_TX, smem_multi);
+	Pass1Args a1;
+	a1.nx = nx; a1.ny = ny; a1.J = J; a1.off = in->off; a1.spans = in->spans; a1.H = dt.H; a1.reach = dt.reach;
+	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rb.rd;
+	a1.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
+
+	auto pass1_band = [&](int b) {
+		const int y0 = b * BH, y1 = std::min(ny, y0 + BH);
+		yt.c_begin = (unsigned long long)y0 * nx; yt.c_end = (unsigned long long)y1 * nx;
+		k_ythresh<<<blocks_for(yt.c_end - yt.c_begin, 256), 256, (size_t)(J + 2) * sizeof(double), sm>>>(yt);
+		const unsigned int band_tiles = (unsigned int)tiles_x * (unsigned int)(y1 - y0);
+		g.tile0 = (unsigned int)tiles_x * (unsigned int)y0;
+		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.tiles_next = nullptr;
+		g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
+		k_pass1_tile<CAP_FAST, false, false><<<band_tiles, P1_TX, smem_small, sm>>>(g);
+		ctx->launches += 2;
+		if (cmax_small < cmax) {
+			g.cmax = cmax; g.tiles = big_tiles.p; g.tiles_count = big_count; g.big_tiles = nullptr;
+			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
+			k_pass1_tile<CAP_FAST, false, true><<<std::min<unsigned int>(band_tiles, (unsigned int)(occ_big * sms)), P1_TX, smem_big, sm>>>(g);
+			ctx->launches++;
+		}
+		g.cmax = cmax_multi; g.tiles = multi_tiles.p; g.tiles_count = multi_count; g.big_tiles = nullptr;
+		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 7);
+		k_pass1_tile<CAP_FAST, true, true><<<std::min<unsigned int>(band_tiles, (unsigned int)(occ_multi * sms)), P1_TX, smem_multi, sm>>>(g);
+		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier bands' overflow lists as well: idempotent)
+		ctx->launches += 2;
+	};
+
+	// Per-band state of the second half (pass 2 -> prefix sum -> compaction -> download). A band is ENQUEUED
+	// (gather, redo, scan, asynchronous readback of its counters and total) one iteration before it is FINISHED
+	// (wait for the readback, allocate, compact, download), so the compute stream always has the next band's
+	// pass 1 queued while the host waits.
+	struct Band {
+		int y0 = 0, y1 = 0;
+		StageBuf sb;
+		RedoBuf rb;
+		Tmp<unsigned long long> sums;
+		vo_dvol *v = nullptr;
+		unsigned long long *h = nullptr;      // pinned: NCTR counters + total
+		cudaEvent_t ready = nullptr;
+		explicit Band(vo_ctx *c) : sb(c), rb(c), sums(c) {}
+	};
+	std::vector<std::unique_ptr<Band>> bstate;
+	unsigned long long *h_pin = (unsigned long long *)host_block((size_t)nb * (NCTR + 1) * sizeof(unsigned long long));
+	if (!h_pin) { drop_host(); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
+	uint64_t base = 0;          // intervals of the bands finished so far
+	std::vector<vo_dvol *> bands;
+	int rc = VO_OK;
+
+	auto enqueue_band = [&](int b) -> int {
+		std::unique_ptr<Band> B(new Band(ctx));
+		B->y0 = b * BH; B->y1 = std::min(ny, B->y0 + BH);
+		const unsigned long long nlists = (unsigned long long)nx * (B->y1 - B->y0);
+		VO_TRY(B->sb.alloc(nlists, 65536ull + nlists / 8));
+		VO_TRY(B->rb.alloc((unsigned int)std::min<unsigned long long>(nlists, 1ull << 22), 8));
+		VO_TRY(new_dvol(ctx, nx, B->y1 - B->y0, &B->v));
+		const unsigned int nt = blocks_for(nlists, SCAN_TILE);
+		VO_TRY(dalloc(ctx, &B->sums.p, (unsigned long long)nt + 1));
+		B->h = h_pin + (size_t)b * (NCTR + 1);
+		B->ready = pr.event();
+		cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), sm);
+		cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), sm);
+		Pass2Args a2;
+		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = B->y0; a2.y1 = B->y1;
+		a2.mid = m->slots; a2.flags = m->flags; a2.pool = m->pool; a2.st = B->sb.st; a2.redo = B->rb.rd;
+		a2.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
+		k_pass2<CAP_FAST><<<blocks_for(nlists, 128), 128, 0, sm>>>(a2);
+		a2.wk = Work{B->rb.rd.list, 0ull, B->rb.rd.count, B->rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
+		k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
+		k_scan_reduce<<<nt, SCAN_THREADS, 0, sm>>>(B->sb.st.cnt, nlists, B->sums.p);
+		k_scan_tiles<<<1, 1024, 0, sm>>>(B->sums.p, nt);
+		k_scan_apply<<<nt, SCAN_THREADS, 0, sm>>>(B->sb.st.cnt, nlists, B->sums.p, B->v->off);
+		ctx->launches += 5;
+		cudaMemcpyAsync(B->h, ctx->d_ctr, NCTR * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm);
+		cudaMemcpyAsync(B->h + NCTR, B->sums.p + nt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm);
+		cudaEventRecord(B->ready, sm);
+		bstate.push_back(std::move(B));
+		return VO_OK;
+	};
+
+	auto finish_band = [&](Band &B) -> int {
+		const unsigned long long c0 = (unsigned long long)B.y0 * nx, c1 = (unsigned long long)B.y1 * nx;
+		const unsigned long long nlists = c1 - c0;
+		VO_CUDA(cudaEventSynchronize(B.ready));
+		const unsigned long long total = B.h[NCTR];
+		if (B.h[8] > B.rb.rd.cap || B.h[9] || B.h[1] > B.sb.st.pool_cap) return PIPE_NA;      // rare: plain path handles it
+		if (base + total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
+		VO_TRY(dalloc(ctx, &B.v->spans, total));
+		B.v->nspans = total;
+		if (base + total > hs_cap) {                        // grow the pinned span buffer (keeps what is already there)
+			cudaStreamSynchronize(pr.s_out);
+			const uint64_t ncap = 2 * (base + total) + (1u << 16);
+			double *nh = (double *)host_block(ncap * sizeof(double2));
+			if (!nh) return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed");
+			std::memcpy(nh, hs, base * sizeof(double2));
+			vo_free(hs);
+			hs = nh; hs_cap = ncap;
+		}
+		k_compact<<<blocks_for(nlists, 256), 256, 0, sm>>>(B.sb.st, nlists, B.v->off, B.v->spans);
+		if (base) k_rebase<<<blocks_for(nlists + 1, 256), 256, 0, sm>>>(B.v->off, nlists + 1, 0u, (uint32_t)base);
+		ctx->launches += 2;
+		cudaEvent_t done = pr.event();
+		cudaEventRecord(done, sm);
+		cudaStreamWaitEvent(pr.s_out, done, 0);
+		cudaMemcpyAsync(ho + c0, B.v->off, (nlists + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+		if (total) cudaMemcpyAsync(hs + 2 * base, B.v->spans, total * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
+		base += total;
+		bands.push_back(B.v);       // released after the output stream has drained (no stall of the compute stream)
+		B.v = nullptr;
+		return VO_OK;
+	};
+
+	for (int b = 0; b <= nb + 1 && rc == VO_OK; ++b) {
+		if (b < nb) {
+			// the y-thresholds of a band's last row read the first row of the next band
+			cudaStreamWaitEvent(sm, ev_in[std::min(b + 1, nb - 1)], 0);
+			pass1_band(b);
+		}
+		if (b >= 1 && b - 1 < nb) rc = enqueue_band(b - 1);                  // pass 2 of band b-1 needs pass 1 of band b
+		if (rc == VO_OK && b >= 2) rc = finish_band(*bstate[b - 2]);
+	}
+	for (auto &B : bstate) if (B->v) { free_dvol(ctx, B->v); B->v = nullptr; }
+	cudaEventRecord(ctx->ev[2], sm);
+	unsigned long long h[NCTR];
+	if (rc == VO_OK) rc = read_counters(ctx, h);
+	cudaStreamSynchronize(pr.s_out);
+	cudaStreamSynchronize(pr.s_in);
+	for (auto bd : bands) free_dvol(ctx, bd);
+	bstate.clear();
+	vo_free(h_pin);
+	if (rc == VO_OK && cudaGetLastError() != cudaSuccess) rc = PIPE_NA;
+	if (rc == VO_OK && (h[0] > m->pool_cap || h[2] > redo_cap || h[4])) {
+		ctx->pool_hint = std::max<unsigned long long>(ctx->pool_hint, h[0] + h[0] / 4);
+		rc = PIPE_NA;                                           // let the plain path deal with it (it regrows / reports)
+	}
+	if (rc != VO_OK) { drop_host(); return rc; }
+	ctx->pool_hint = h[0] + h[0] / 4;
+	ctx->out_hint = base + base / 8 + (1u << 16);
+	float tms = 0;
+	cudaEventElapsedTime(&tms, ctx->ev[0], ctx->ev[2]);
+	if (pt) { pt->ms1 = tms; pt->ms2 = 0; }                     // the passes interleave: one figure for both
+	*out_off = ho; *out_spans = hs;
+	if (out_nspans) *out_nspans = base;
+	return VO_OK;
+}
+
 struct DeviceGuard {
 	int prev = -1;
 	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -908,7 +1203,7 @@ int vo_create(int device, vo_ctx **out)
 	for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->mark[i]) == cudaSuccess;
 	for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&ctx->kev[i]) == cudaSuccess;
-	ok = ok && cudaMalloc((void **)&ctx->d_ctr, 8 * sizeof(unsigned long long)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&ctx->d_ctr, 16 * sizeof(unsigned long long)) == cudaSuccess;
 	if (ok) {
 		// keep freed blocks in the stream-ordered pool: steady-state calls then allocate without the driver
 		cudaMemPool_t pool;
@@ -932,6 +1227,9 @@ void vo_destroy(vo_ctx *ctx)
 	for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
+	for (auto &e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
+	if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+	if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -943,6 +1241,10 @@ uint64_t vo_launch_count(const vo_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 {
 	if (!ctx || !key || !value) return VO_ERR_ARG;
+	if (std::strcmp(key, "pipeline") == 0) {
+		if (std::strcmp(value, "off") == 0) { ctx->no_pipeline = true; return VO_OK; }
+		if (std::strcmp(value, "on") == 0 || std::strcmp(value, "auto") == 0) { ctx->no_pipeline = false; return VO_OK; }
+	}
 	if (std::strcmp(key, "pass1") == 0) {
 		if (std::strcmp(value, "simple") == 0) { ctx->force_simple_pass1 = true; ctx->force_tile_pass1 = false; return VO_OK; }
 		if (std::strcmp(value, "tile") == 0) { ctx->force_simple_pass1 = false; ctx->force_tile_pass1 = true; return VO_OK; }
@@ -1243,9 +1545,20 @@ int vo_morph3d(vo_ctx *ctx, int op, int method, int nx, int ny, double zmin, dou
 	if (!ctx || !out_off || !out_spans) return VO_ERR_ARG;
 	ctx->err.clear();
 	DeviceGuard g(ctx->device);
+	PassTimes pt;
+	if (op == VO_OP_DILATION && method == VO_METHOD_OURS) {
+		// large grids: upload, the two passes and the download overlap band by band
+		const int prc = dilate_ours_pipelined(ctx, nx, ny, off, spans, radius, out_off, out_spans, out_nspans, &pt);
+		if (prc == VO_OK) {
+			if (ms_pass1) *ms_pass1 = pt.ms1;
+			if (ms_pass2) *ms_pass2 = pt.ms2;
+			return VO_OK;
+		}
+		if (prc != PIPE_NA) return prc;
+		ctx->err.clear();
+	}
 	vo_dvol *in = nullptr, *res = nullptr;
 	VO_TRY(upload(ctx, nx, ny, off, spans, &in));
-	PassTimes pt;
 	int rc = morph3d_dev(ctx, op, method, in, zmin, zmax, radius, &res, &pt);
 	free_dvol(ctx, in);
 	VO_TRY(rc);
