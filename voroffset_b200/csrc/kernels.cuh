@@ -367,6 +367,160 @@ __global__ void __launch_bounds__(64) k_dilate2d(Dil2dArgs a)
 	VO_FOR_WORK(CAP, a.wk, c) dilate2d_item<CAP>(a, c);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// vor2d, block-per-row variant: rows of a 2D image hold tens of intervals and gather from 2J+1 rows, so a
+// row's union has up to a few thousand candidates - too long for one thread's running list, too little
+// for the tile kernel. One CTA per row: candidates (clamped like DoubleVoronoi.cpp:713-725) go to shared
+// memory, are sorted by start (bitonic), a prefix maximum of the ends marks where a new component starts
+// (start > every earlier end; touching intervals merge like appendSegment), and the components are written
+// straight to the staged output. Rows with more than D2B_MAX candidates go to the redo list and are
+// handled by the one-thread-per-row kernel.
+// ---------------------------------------------------------------------------------------------------
+constexpr int D2B_MAX = 2048;       // candidates per row held in shared memory
+constexpr int D2B_THREADS = 256;
+
+__device__ __forceinline__ double2 clamp_candidate(double y1, double y2, double h, double W)
+{
+	const double a = (y1 - h > 0) ? y1 - h : 0;
+	const double b = (y2 + h < W) ? y2 + h : W;
+	if (a > W || b < 0) return slot_empty();
+	return make_double2(a, b);
+}
+
+__global__ void __launch_bounds__(D2B_THREADS) k_dilate2d_block(Dil2dArgs a)
+{
+	__shared__ double s_key[D2B_MAX];      // starts
+	__shared__ double s_val[D2B_MAX];      // ends, later their running maximum
+	__shared__ int s_rowbase[130];         // first candidate slot of each source row (2J+1 <= 129)
+	__shared__ int s_scan[D2B_THREADS];
+	__shared__ int s_total, s_ncomp;
+	__shared__ unsigned long long s_pool;
+	const int i = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+	if (i >= a.rows) return;
+	const int nsrc = 2 * a.J + 1;
+	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	// candidates per source row (complement rows have one more seed than intervals; sentinels have one)
+	if (tid == 0) {
+		int tot = 0;
+		for (int q = 0; q < nsrc; ++q) {
+			const int r = i - a.J + q;
+			int c = 0;
+			if (!a.complement) { if (r >= 0 && r < a.rows) c = (int)(a.off[r + 1] - a.off[r]); }
+			else if (r == -1 || r == a.rows) c = 1;
+			else if (r >= 0 && r < a.rows) c = (int)(a.off[r + 1] - a.off[r]) + 1;
+			s_rowbase[q] = tot;
+			tot += c;
+		}
+		s_rowbase[nsrc] = tot;
+		s_total = tot;
+	}
+	__syncthreads();
+	const int total = s_total;
+	if (total > D2B_MAX || nsrc > 129) {                   // too long for shared memory: one-thread-per-row kernel
+		if (tid == 0) { redo_push(a.redo, (unsigned long long)i); a.st.cnt[i] = 0; }
+		return;
+	}
+	int npow = 1;
+	while (npow < total) npow <<= 1;
+	for (int k = total + tid; k < npow; k += nthr) { s_key[k] = inf; s_val[k] = -inf; }
+	// fill: a warp per source row, lanes over its seeds
+	const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+	for (int q = warp; q < nsrc; q += nwarp) {
+		const int r = i - a.J + q;
+		const int b0 = s_rowbase[q], n = s_rowbase[q + 1] - b0;
+		if (n == 0) continue;
+		const double h = __ldg(a.h2 + abs(r - i));
+		if (!a.complement) {
+			const uint32_t o = a.off[r];
+			for (int k = lane; k < n; k += 32) {
+				const double2 v = __ldg(a.spans + o + k);
+				const double2 c = clamp_candidate(v.x, v.y, h, a.W);
+				s_key[b0 + k] = c.x; s_val[b0 + k] = c.y;
+			}
+		} else if (r == -1 || r == a.rows) {
+			if (lane == 0) { const double2 c = clamp_candidate(-1.0, a.W, h, a.W); s_key[b0] = c.x; s_val[b0] = c.y; }
+		} else {
+			// seeds of the complement: [-1, a_0], [b_0, a_1], ..., [b_last, W]   (DoubleVoronoi.h:132-144)
+			const uint32_t o = a.off[r];
+			for (int k = lane; k < n; k += 32) {
+				const double lo = (k == 0) ? -1.0 : __ldg(a.spans + o + k - 1).y;
+				const double hi = (k == n - 1) ? a.W : __ldg(a.spans + o + k).x;
+				const double2 c = clamp_candidate(lo, hi, h, a.W);
+				s_key[b0 + k] = c.x; s_val[b0 + k] = c.y;
+			}
+		}
+	}
+	__syncthreads();
+	// bitonic sort by start (dropped candidates carry start = +inf and end = -inf: they sink to the end)
+	for (int k = 2; k <= npow; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int t = tid; t < npow; t += nthr) {
+				const int p = t ^ j;
+				if (p > t) {
+					const bool up = (t & k) == 0;
+					const double kt = s_key[t], kp = s_key[p];
+					if ((kt > kp) == up) {
+						s_key[t] = kp; s_key[p] = kt;
+						const double vt = s_val[t]; s_val[t] = s_val[p]; s_val[p] = vt;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	// running maximum of the ends (each thread owns a contiguous chunk), component starts, their ranks
+	const int chunk = (npow + nthr - 1) / nthr;
+	const int c0 = tid * chunk, c1 = min(c0 + chunk, npow);
+	double m = -inf;
+	for (int k = c0; k < c1; ++k) { m = s_val[k] > m ? s_val[k] : m; }
+	__shared__ double s_cmax[D2B_THREADS];
+	s_cmax[tid] = m;
+	__syncthreads();
+	double before = -inf;                                   // maximum end of everything before this chunk
+	for (int q = 0; q < tid; ++q) before = s_cmax[q] > before ? s_cmax[q] : before;
+	int nstart = 0;
+	double run = before;
+	for (int k = c0; k < c1; ++k) {
+		if (s_key[k] != inf && s_key[k] > run) ++nstart;   // opens a new component (the very first has run = -inf)
+		run = s_val[k] > run ? s_val[k] : run;
+	}
+	s_scan[tid] = nstart;
+	__syncthreads();
+	if (tid == 0) {
+		int acc = 0;
+		for (int q = 0; q < nthr; ++q) { const int v = s_scan[q]; s_scan[q] = acc; acc += v; }
+		s_ncomp = acc;
+		a.st.cnt[i] = (uint32_t)acc;
+		if (acc > STAGE_INLINE) {
+			s_pool = atomicAdd(a.st.cursor, (unsigned long long)acc);
+			a.st.inl[(size_t)i * STAGE_INLINE] = slot_pool(s_pool, (unsigned int)acc);
+		}
+	}
+	__syncthreads();
+	const int ncomp = s_ncomp;
+	if (ncomp == 0) return;
+	const bool pooled = ncomp > STAGE_INLINE;
+	if (pooled && s_pool + ncomp > a.st.pool_cap) return;   // the host regrows the pool and repeats
+	double2 *dst = pooled ? a.st.pool + s_pool : a.st.inl + (size_t)i * STAGE_INLINE;
+	// component c = [start of its first element, running maximum just before the next component starts]:
+	// the thread that meets the NEXT start closes a component; the last one ends at the overall maximum.
+	int comp = s_scan[tid] - 1;                             // component the chunk begins inside (-1: none yet)
+	run = before;
+	for (int k = c0; k < c1; ++k) {
+		if (s_key[k] == inf) break;
+		if (s_key[k] > run) {
+			if (comp >= 0) dst[comp].y = run;
+			++comp;
+			dst[comp].x = s_key[k];
+		}
+		run = s_val[k] > run ? s_val[k] : run;
+	}
+	if (tid == 0) {
+		double all = -inf;
+		for (int q = 0; q < nthr; ++q) all = s_cmax[q] > all ? s_cmax[q] : all;
+		dst[ncomp - 1].y = all;
+	}
+}
+
 // Staged lists -> canonical CSR (after the exclusive scan of cnt).
 __global__ void __launch_bounds__(256) k_compact(Stage st, unsigned long long nlists,
                                                  const uint32_t *__restrict__ off, double2 *__restrict__ spans)

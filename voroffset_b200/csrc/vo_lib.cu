@@ -774,7 +774,7 @@ int dilate2d(vo_ctx *ctx, const vo_dvol *in, int width, double R, int complement
 	const unsigned long long nlists = (unsigned long long)in->nx;
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + 4 * in->nspans,
-		[&](Dil2dArgs &g) { k_dilate2d<CAP_FAST><<<blocks_for(g.wk.n, 64), 64, 0, s>>>(g); },
+		[&](Dil2dArgs &g) { k_dilate2d_block<<<(unsigned int)g.wk.n, D2B_THREADS, 0, s>>>(g); },   // CTA per row; overflow -> redo
 		[&](Dil2dArgs &g, unsigned int grid) { k_dilate2d<CAP_BIG><<<grid, 64, 0, s>>>(g); },
 		in->nx, 1, out);
 }
