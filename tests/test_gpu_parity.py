@@ -65,6 +65,28 @@ def test_seeded_3d(ctx, oracle, name, gen, radius, method):
         util.assert_same(got, oracle.morph3d(vol, opn, radius, method), opn, method, f"cuda vs oracle [{name}]")
 
 
+TILE_CASES = [c for c in SEEDED if c[0] not in ("all_empty",)] + [
+    ("lattice_n128_R9", lambda: synth.lattice(128, padding=10), 9.0),
+    ("blobs_n128_R20", lambda: synth.blobs(128, padding=22, seed=11), 20.5),
+    ("random_k8_wide", lambda: synth.random_volume(150, 24, kmax=8, padding=3, seed=12), 6.4),
+]
+
+
+@pytest.mark.parametrize("name,gen,radius", TILE_CASES, ids=[c[0] for c in TILE_CASES])
+def test_tile_kernel_forced_3d(ctx, oracle, name, gen, radius):
+    """Small grids normally take the one-thread-per-slot pass 1; force the pruned tile kernel (pass1_tile.cuh)
+    so that its dominance logic is checked bit for bit against the oracle on every seeded input."""
+    vol = gen()
+    op = morpho.make_operator("ours", ctx)
+    ctx.set_option("pass1", "tile")
+    try:
+        for opn in OPS:
+            got, _, _ = morpho.apply_operation(op, opn, vol, radius)
+            util.assert_same(got, oracle.morph3d(vol, opn, radius, "ours"), opn, "ours", f"tile kernel vs oracle [{name}]")
+    finally:
+        ctx.set_option("pass1", "auto")
+
+
 def test_many_layers_use_the_redo_path(ctx, oracle):
     # 40 thin layers per column: the running union outgrows the fast capacity (16) and is redone
     rng = np.random.RandomState(0)

@@ -153,14 +153,18 @@ struct Pass2Args {
 	int nx, ny, J;          // grid of the mid volume
 	int y0, y1;             // rows produced
 	const double2 *mid;
-	const uint8_t *flags;   // [2][ny*nx] per mid column: classes j < flags[0][c] are needed by the consumer rows
-	                        // above (y - j), classes j < flags[1][c] by the rows below (y + j); every other
-	                        // slot was never written by pass 1 and must not be read (pass1_tile.cuh)
+	const uint16_t *flags;  // [2][ny*nx] per mid column: lo | hi << 8; the classes lo <= j < hi of flags[0][c] are
+	                        // needed by the consumer rows above (y - j), those of flags[1][c] by the rows below
+	                        // (y + j); every other slot was never written by pass 1 and must not be read
+	                        // (pass1_tile.cuh)
 	const double2 *pool;
 	Stage st;
 	Redo redo;
 	Work wk;
 };
+
+// class window flag (lo | hi << 8): is class j needed?
+__device__ __forceinline__ bool flag_has(uint16_t w, int j) { return (int)(w & 0xffu) <= j && j < (int)(w >> 8); }
 
 template <int CAP>
 __device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot, const double2 *pool)
@@ -187,7 +191,7 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 	RunUnion<CAP> u(ulist);
 	const int up = min(a.J, y), dn = min(a.J, a.ny - 1 - y);    // rows available above / below
 	const size_t nx = (size_t)a.nx, midrow = (size_t)(a.J + 1) * nx;
-	const uint8_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
+	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
 	const size_t cc = (size_t)y * nx + x;
 	const double2 *self = a.mid + (size_t)y * midrow + x;
 	if (a.J <= 63) {
@@ -196,15 +200,15 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 		// decides), bit j-1 of m_dn = row y+j is needed (its "up" byte decides).
 		unsigned long long m_up = 0, m_dn = 0;
 		{
-			const uint8_t *f = f_dn + cc - nx;
+			const uint16_t *f = f_dn + cc - nx;
 #pragma unroll 8
-			for (int j = 1; j <= up; ++j, f -= nx) m_up |= (unsigned long long)(j < (int)__ldg(f)) << (j - 1);
+			for (int j = 1; j <= up; ++j, f -= nx) m_up |= (unsigned long long)flag_has(__ldg(f), j) << (j - 1);
 			f = f_up + cc + nx;
 #pragma unroll 8
-			for (int j = 1; j <= dn; ++j, f += nx) m_dn |= (unsigned long long)(j < (int)__ldg(f)) << (j - 1);
+			for (int j = 1; j <= dn; ++j, f += nx) m_dn |= (unsigned long long)flag_has(__ldg(f), j) << (j - 1);
 		}
-		// the output's own row: class 0 is needed as soon as anything is in reach
-		if (max(__ldg(f_up + cc), __ldg(f_dn + cc)) > 0) pass2_take(u, self, a.pool);
+		// the output's own row: class 0
+		if (flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0)) pass2_take(u, self, a.pool);
 		// step 2: fetch the needed slots four at a time (independent loads), then fold them in
 		const size_t step_up = midrow - nx, step_dn = midrow + nx;     // slot (y-j, class j) = self - j*step_up, ...
 		while (m_up | m_dn) {
@@ -233,15 +237,15 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 		}
 	} else {
 		// general form (more than 64 classes: every class of every column was computed by k_pass1)
-		const uint8_t *f = f_dn + (size_t)(y - up) * nx + x;
+		const uint16_t *f = f_dn + (size_t)(y - up) * nx + x;
 		const double2 *row = a.mid + (size_t)(y - up) * midrow + x;
 		for (int j = up; j >= 1; --j, f += nx, row += midrow)
-			if (j < (int)__ldg(f)) pass2_take(u, row + (size_t)j * nx, a.pool);
-		if (max(__ldg(f_up + cc), __ldg(f_dn + cc)) > 0) pass2_take(u, self, a.pool);
+			if (flag_has(__ldg(f), j)) pass2_take(u, row + (size_t)j * nx, a.pool);
+		if (flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0)) pass2_take(u, self, a.pool);
 		f = f_up + (size_t)(y + 1) * nx + x;
 		row = a.mid + (size_t)(y + 1) * midrow + x;
 		for (int j = 1; j <= dn; ++j, f += nx, row += midrow)
-			if (j < (int)__ldg(f)) pass2_take(u, row + (size_t)j * nx, a.pool);
+			if (flag_has(__ldg(f), j)) pass2_take(u, row + (size_t)j * nx, a.pool);
 	}
 	if (u.overflow) { overflow_item(a.wk, a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);

@@ -60,7 +60,7 @@ struct vo_dmid {
 	double R = 0;
 	double2 *slots = nullptr;
 	double2 *pool = nullptr;
-	uint8_t *flags = nullptr;       // [2][ny*nx]: classes needed by the consumer rows above / below each mid column
+	uint16_t *flags = nullptr;      // [2][ny*nx]: class window (lo | hi << 8) needed by the consumer rows above / below each mid column
 	uint64_t pool_cap = 0, pool_used = 0;
 };
 
@@ -381,19 +381,32 @@ int check_radius(vo_ctx *ctx, double R)
 }
 
 // Dominance bounds of the tile kernel (pass1_tile.cuh), from the same cap table the candidates use:
-//   Dmono[d] = min over d' >= d and classes j with reach[j] >= d' of H[j][d'-1] - H[j][d']   (x direction)
-//   Emono[j] = min over j' >= j and d <= reach[j'] of H[j'-1][d] - H[j'][d]                    (y direction)
-// both non-decreasing in their index, entry J+1 = +inf.
+//   Dmono[d]  = min over d' >= d and classes j with reach[j] >= d' of H[j][d'-1] - H[j][d']   (near, x)
+//   Emono[j]  = min over j' >= j and d <= reach[j'] of H[j'-1][d] - H[j'][d]                    (near, y)
+//   G[jt][d]  = max over 1 <= d' <= d and j <= min(jt, jmax[d'+1]) of H[j][d'] - H[j][d'+1]    (far, x)
+//   Ef[d][c]  = max over 1 <= c' <= c of H[c'-1][d] - H[c'][d], +inf for c > jmax[d]           (far, y)
+// the near bounds non-decreasing with entry J+1 = +inf; the far bounds non-decreasing along d / c, rounded
+// UP to float (a larger bound only prunes less), +inf where no farther neighbour is in reach.
 struct TileTables {
 	vo_ctx *ctx;
-	double *Dmono = nullptr, *Emono = nullptr, *Ht = nullptr;   // Ht[d*JPP + j] = H[j][d], rows padded to 8 classes
+	double *Dmono = nullptr, *Emono = nullptr, *Ht = nullptr;   // Ht[d*JPP + j] = H[j][d], rows padded
+	float *G = nullptr, *Ef = nullptr;
+	uint8_t *jmax = nullptr;
 	explicit TileTables(vo_ctx *c) : ctx(c) {}
-	~TileTables() { dfree(ctx, Dmono); dfree(ctx, Emono); dfree(ctx, Ht); }
+	~TileTables() { dfree(ctx, Dmono); dfree(ctx, Emono); dfree(ctx, Ht); dfree(ctx, G); dfree(ctx, Ef); dfree(ctx, jmax); }
+	static float round_up(double x)
+	{
+		float f = (float)x;
+		if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+		return f;
+	}
 	int upload(const Tables &t)
 	{
 		const int J = t.J, n = J + 1;
+		if (J > 255) return VO_OK;                       // (the tile kernel is only used up to J = 63)
 		std::vector<double> dm((size_t)J + 2, 0.0), em((size_t)J + 2, 0.0);
 		const double inf = std::numeric_limits<double>::infinity();
+		const float finf = std::numeric_limits<float>::infinity();
 		dm[J + 1] = em[J + 1] = inf;
 		for (int d = J; d >= 1; --d) {
 			double m = inf;
@@ -406,6 +419,28 @@ struct TileTables {
 			for (int d = 0; d <= t.reach[j]; ++d) m = std::min(m, t.H[(size_t)(j - 1) * n + d] - t.H[(size_t)j * n + d]);
 			em[j] = std::min(m, em[j + 1]);
 		}
+		std::vector<uint8_t> jm((size_t)J + 2, 0);
+		for (int d = 0; d <= J; ++d)
+			for (int j = 0; j < n; ++j) if (t.reach[j] >= d) jm[d] = (uint8_t)j;
+		std::vector<float> g((size_t)n * n, 0.0f), ef((size_t)n * (n + 1), 0.0f);
+		for (int jt = 0; jt < n; ++jt) {
+			double run = 0.0;
+			for (int d = 1; d < J; ++d) {
+				for (int j = 0; j <= std::min(jt, (int)jm[d + 1]); ++j)
+					run = std::max(run, t.H[(size_t)j * n + d] - t.H[(size_t)j * n + d + 1]);
+				g[(size_t)jt * n + d] = round_up(run);
+			}
+			g[(size_t)jt * n + J] = finf;
+		}
+		for (int d = 0; d <= J; ++d) {
+			double run = 0.0;
+			for (int c = 1; c <= J + 1; ++c) {
+				if (c <= (int)jm[d]) {
+					run = std::max(run, t.H[(size_t)(c - 1) * n + d] - t.H[(size_t)c * n + d]);
+					ef[(size_t)d * (n + 1) + c] = round_up(run);
+				} else ef[(size_t)d * (n + 1) + c] = finf;
+			}
+		}
 		const int jpp = pass1_jpp(J);
 		std::vector<double> ht((size_t)n * jpp, -1.0);
 		for (int j = 0; j < n; ++j)
@@ -414,8 +449,14 @@ struct TileTables {
 		VO_CUDA(cudaMemcpyAsync(Ht, ht.data(), ht.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 		VO_TRY(dalloc(ctx, &Dmono, (unsigned long long)J + 2));
 		VO_TRY(dalloc(ctx, &Emono, (unsigned long long)J + 2));
+		VO_TRY(dalloc(ctx, &G, (unsigned long long)g.size()));
+		VO_TRY(dalloc(ctx, &Ef, (unsigned long long)ef.size()));
+		VO_TRY(dalloc(ctx, &jmax, (unsigned long long)jm.size()));
 		VO_CUDA(cudaMemcpyAsync(Dmono, dm.data(), dm.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 		VO_CUDA(cudaMemcpyAsync(Emono, em.data(), em.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(G, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(Ef, ef.data(), ef.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+		VO_CUDA(cudaMemcpyAsync(jmax, jm.data(), jm.size(), cudaMemcpyHostToDevice, ctx->stream));
 		VO_CUDA(cudaStreamSynchronize(ctx->stream));
 		return VO_OK;
 	}
@@ -486,8 +527,6 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	unsigned long long pool_cap = std::max(65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4), ctx->pool_hint);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, 2 * ncols);
-	Tmp<uint16_t> ty(ctx);
-	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &ty.p, in->nspans);
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &multi_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
@@ -508,20 +547,16 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		a.redo = rb.rd;
 		a.wk = Work{nullptr, nslots, nullptr, 0u, nullptr};
 		if (nslots && tile_now) {
-			YThreshArgs yt;
-			yt.nx = in->nx; yt.ny = in->ny; yt.J = t.J; yt.off = in->off; yt.spans = in->spans; yt.Emono = tt.Emono; yt.ty = ty.p;
-			yt.c_begin = 0; yt.c_end = ncols;
-			k_ythresh<<<blocks_for(ncols, 256), 256, (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(yt);
-			ctx->launches++;
 			Pass1TileArgs g;
 			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.tile0 = 0;
 			g.tiles_x = (in->nx + TX - 1) / TX;
-			g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
+			g.off = in->off; g.spans = in->spans; g.Ht = tt.Ht; g.Dmono = tt.Dmono; g.Emono = tt.Emono;
+			g.G = tt.G; g.Ef = tt.Ef; g.jmax = tt.jmax;
 			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
 			const double seg_est = k_in * (TX + 2 * t.J) * 1.3;
 			const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : seg_est <= 1024 ? 1024 : cmax;
-			const size_t smem_small = pass1_tile_smem(t.J, cmax_small), smem_big = pass1_tile_smem(t.J, cmax);
+			const size_t smem_small = pass1_tile_smem(t.J, cmax_small, P1_LCAP_S), smem_big = pass1_tile_smem(t.J, cmax, P1_LCAP_M);
 			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
@@ -550,14 +585,15 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			// launch 3: tiles with multi-interval columns (two hulls per class); oversized ones go to the redo list
 			g.cmax = cmax_small < 512 ? 512 : cmax_small; g.tiles = multi_tiles.p; g.tiles_count = multi_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 7);
-			const size_t smem_multi = pass1_tile_smem(t.J, g.cmax);
+			const size_t smem_multi = pass1_tile_smem(t.J, g.cmax, P1_LCAP_M);
 			k_pass1_tile<CAP_FAST, true, true><<<wave((const void *)k_pass1_tile<CAP_FAST, true, true>, smem_multi), P1_TX, smem_multi, ctx->stream>>>(g);
 			ctx->launches++;
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
 		} else if (nslots) {
-			// every class of every column is computed: all flag bytes = J + 1
-			cudaMemsetAsync(m->flags, t.J + 1, 2 * ncols, ctx->stream);
+			// every class of every column is computed: all class windows = [0, J + 1)
+			k_fill16<<<blocks_for(2 * ncols, 256), 256, 0, ctx->stream>>>(m->flags, 2 * ncols, (uint16_t)((t.J + 1) << 8));
+			ctx->launches++;
 			cudaEventRecord(ctx->kev[0], ctx->stream);
 			k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
@@ -946,7 +982,6 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 
 	TableCache *tc = nullptr;
 	VO_TRY(get_tables(ctx, R, true, &tc));
-	const Tables &t = tc->t;
 	DevTables &dt = tc->dt;
 	TileTables &tt = tc->tt;
 
@@ -968,8 +1003,6 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	m->pool_cap = std::max(65536ull + (unsigned long long)(J + 1) * (nspans / 4), ctx->pool_hint);
 	VO_TRY(dalloc(ctx, &m->pool, m->pool_cap));
 	VO_TRY(dalloc(ctx, &m->flags, 2 * ncols));
-	Tmp<uint16_t> ty(ctx);
-	VO_TRY(dalloc(ctx, &ty.p, nspans));
 	const int tiles_x = (nx + TX - 1) / TX;
 	const unsigned long long ntiles = (unsigned long long)tiles_x * ny;
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
@@ -1005,20 +1038,19 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	cudaEventRecord(ctx->ev[0], sm);
 
 	// launch parameters shared by all bands
-	YThreshArgs yt;
-	yt.nx = nx; yt.ny = ny; yt.J = J; yt.off = in->off; yt.spans = in->spans; yt.Emono = tt.Emono; yt.ty = ty.p;
 	Pass1TileArgs g;
 	g.nx = nx; g.ny = ny; g.J = J; g.tiles_x = tiles_x;
-	g.off = in->off; g.spans = in->spans; g.ty = ty.p; g.Ht = tt.Ht; g.reach = dt.reach; g.Dmono = tt.Dmono;
+	g.off = in->off; g.spans = in->spans; g.Ht = tt.Ht; g.Dmono = tt.Dmono; g.Emono = tt.Emono;
+	g.G = tt.G; g.Ef = tt.Ef; g.jmax = tt.jmax;
 	g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 	unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
 	unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
 	g.big_count = big_count; g.multi_tiles = multi_tiles.p; g.multi_count = multi_count;
 	const double seg_est = k_in * (TX + 2 * J) * 1.3;
 	const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : seg_est <= 1024 ? 1024 : cmax;
-	const size_t smem_small = pass1_tile_smem(J, cmax_small), smem_big = pass1_tile_smem(J, cmax);
+	const size_t smem_small = pass1_tile_smem(J, cmax_small, P1_LCAP_S), smem_big = pass1_tile_smem(J, cmax, P1_LCAP_M);
 	const int cmax_multi = cmax_small < 512 ? 512 : cmax_small;
-	const size_t smem_multi = pass1_tile_smem(J, cmax_multi);
+	const size_t smem_multi = pass1_tile_smem(J, cmax_multi, P1_LCAP_M);
 	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
@@ -1033,14 +1065,12 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 
 	auto pass1_band = [&](int b) {
 		const int y0 = b * BH, y1 = std::min(ny, y0 + BH);
-		yt.c_begin = (unsigned long long)y0 * nx; yt.c_end = (unsigned long long)y1 * nx;
-		k_ythresh<<<blocks_for(yt.c_end - yt.c_begin, 256), 256, (size_t)(J + 2) * sizeof(double), sm>>>(yt);
 		const unsigned int band_tiles = (unsigned int)tiles_x * (unsigned int)(y1 - y0);
 		g.tile0 = (unsigned int)tiles_x * (unsigned int)y0;
 		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.tiles_next = nullptr;
 		g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
 		k_pass1_tile<CAP_FAST, false, false><<<band_tiles, P1_TX, smem_small, sm>>>(g);
-		ctx->launches += 2;
+		ctx->launches++;
 		if (cmax_small < cmax) {
 			g.cmax = cmax; g.tiles = big_tiles.p; g.tiles_count = big_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
