@@ -27,6 +27,13 @@ for l in dis.splitlines():
         lines.append((cur, l.split("*/", 1)[1].strip()))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+# one section per profiled launch ("Kernel Name" row, header row, instructions); NCU_KERNEL = substring of the
+# demangled name picks the launch (default: the first section)
+want = os.environ.get("NCU_KERNEL", "")
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = next((i for i in starts if want in rows[i][1]), starts[0])
+nxt = next((i for i in starts if i > pick), len(rows))
+rows = rows[pick:nxt]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
 ci = {n: hdr.index(n) for n in ("Source", "# Samples", "Instructions Executed", "Thread Instructions Executed")}

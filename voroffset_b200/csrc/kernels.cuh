@@ -157,6 +157,8 @@ struct Pass2Args {
 	                        // needed by the consumer rows above (y - j), those of flags[1][c] by the rows below
 	                        // (y + j); every other slot was never written by pass 1 and must not be read
 	                        // (pass1_tile.cuh)
+	const unsigned long long *tilemask;   // [2][ny * ceil(nx / 128)]: OR of the class windows (bit j = class j) of the
+	                        // columns of a pass-1 tile, consumers above ([0]) / below ([1]); NULL-free only for J <= 63
 	const double2 *pool;
 	Stage st;
 	Redo redo;
@@ -181,6 +183,42 @@ __device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot
 	}
 }
 
+// The slots of output column (x, y) named by two bit masks (bit j-1 of m_up: class j of row y-j, of m_dn: class j
+// of row y+j; self: class 0 of the own row), fetched four at a time (independent loads) and folded into the union.
+template <int CAP>
+__device__ __forceinline__ void pass2_gather(const Pass2Args &a, RunUnion<CAP> &u, int x, int y,
+                                             unsigned long long m_up, unsigned long long m_dn, bool self_needed)
+{
+	const size_t nx = (size_t)a.nx, midrow = (size_t)(a.J + 1) * nx;
+	const double2 *self = a.mid + (size_t)y * midrow + x;
+	if (self_needed) pass2_take(u, self, a.pool);
+	const size_t step_up = midrow - nx, step_dn = midrow + nx;     // slot (y-j, class j) = self - j*step_up, ...
+	while (m_up | m_dn) {
+		const double2 *p[4];
+		int n = 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			p[i] = self;
+			if (m_up) { const int j = __ffsll((long long)m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
+			else if (m_dn) { const int j = __ffsll((long long)m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
+		}
+		double2 v[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) v[i] = __ldg(p[i]);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			if (i < n) {
+				if (v[i].x <= v[i].y) u.insert(v[i].x, v[i].y);
+				else if (slot_is_pool(v[i])) {
+					const unsigned long long base = slot_pool_base(v[i]);
+					const unsigned int cnt = slot_pool_count(v[i]);
+					for (unsigned int k = 0; k < cnt; ++k) { const double2 w = __ldg(a.pool + base + k); u.insert(w.x, w.y); }
+				}
+			}
+		}
+	}
+}
+
 template <int CAP>
 __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long long c)   // c: output list, rows relative to y0
 {
@@ -195,9 +233,9 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 	const size_t cc = (size_t)y * nx + x;
 	const double2 *self = a.mid + (size_t)y * midrow + x;
 	if (a.J <= 63) {
-		// step 1: which rows are needed? All flag bytes are loaded back to back (independent loads) into two
-		// bit masks: bit j-1 of m_up = row y-j is needed (this output lies BELOW that row: its "dn" byte
-		// decides), bit j-1 of m_dn = row y+j is needed (its "up" byte decides).
+		// which rows are needed? All flags are loaded back to back (independent loads) into two bit masks:
+		// bit j-1 of m_up = row y-j is needed (this output lies BELOW that row: its "dn" window decides),
+		// bit j-1 of m_dn = row y+j is needed (its "up" window decides).
 		unsigned long long m_up = 0, m_dn = 0;
 		{
 			const uint16_t *f = f_dn + cc - nx;
@@ -207,34 +245,7 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 #pragma unroll 8
 			for (int j = 1; j <= dn; ++j, f += nx) m_dn |= (unsigned long long)flag_has(__ldg(f), j) << (j - 1);
 		}
-		// the output's own row: class 0
-		if (flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0)) pass2_take(u, self, a.pool);
-		// step 2: fetch the needed slots four at a time (independent loads), then fold them in
-		const size_t step_up = midrow - nx, step_dn = midrow + nx;     // slot (y-j, class j) = self - j*step_up, ...
-		while (m_up | m_dn) {
-			const double2 *p[4];
-			int n = 0;
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				p[i] = self;
-				if (m_up) { const int j = __ffsll((long long)m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
-				else if (m_dn) { const int j = __ffsll((long long)m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
-			}
-			double2 v[4];
-#pragma unroll
-			for (int i = 0; i < 4; ++i) v[i] = __ldg(p[i]);
-#pragma unroll
-			for (int i = 0; i < 4; ++i) {
-				if (i < n) {
-					if (v[i].x <= v[i].y) u.insert(v[i].x, v[i].y);
-					else if (slot_is_pool(v[i])) {
-						const unsigned long long base = slot_pool_base(v[i]);
-						const unsigned int cnt = slot_pool_count(v[i]);
-						for (unsigned int k = 0; k < cnt; ++k) { const double2 w = __ldg(a.pool + base + k); u.insert(w.x, w.y); }
-					}
-				}
-			}
-		}
+		pass2_gather(a, u, x, y, m_up, m_dn, flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0));
 	} else {
 		// general form (more than 64 classes: every class of every column was computed by k_pass1)
 		const uint16_t *f = f_dn + (size_t)(y - up) * nx + x;
@@ -255,6 +266,58 @@ template <int CAP>
 __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 {
 	VO_FOR_WORK(CAP, a.wk, c) pass2_item<CAP>(a, c);
+}
+
+// Row-segment form of pass 2 (J <= 63): a CTA owns the P2_TX = P1_TX output columns of one tile of pass 1 in one
+// row. Pass 1 leaves, per tile and side, the OR of the class windows of its columns (`tilemask`); a producer row
+// whose tile mask lacks class j cannot concern any consumer of the segment at row distance j. The lanes of a warp
+// test the 2J tile masks in parallel (two rows per lane), the ballots name the ~10 candidate rows, and only for
+// those are the per-column windows read - instead of 2J+1 flags per consumer.
+constexpr int P2_TX = 128;
+
+template <int CAP>
+__global__ void __launch_bounds__(P2_TX) k_pass2_rows(Pass2Args a)
+{
+	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
+	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);
+	const int y = a.y0 + (int)(blockIdx.x / (unsigned)tiles_x);
+	const int x = tile * P2_TX + (int)threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const size_t nx = (size_t)a.nx;
+	const unsigned long long *t_up = a.tilemask, *t_dn = a.tilemask + (size_t)a.ny * tiles_x;
+	// coarse: bit j-1 of c_up = the tile of row y-j holds a column whose "dn" window has class j, ...
+	unsigned long long c_up = 0, c_dn = 0;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const int j = lane + 1 + 32 * h;
+		bool pu = false, pd = false;
+		if (j <= a.J) {
+			if (y - j >= 0) pu = (__ldg(t_dn + (size_t)(y - j) * tiles_x + tile) >> j) & 1ull;
+			if (y + j < a.ny) pd = (__ldg(t_up + (size_t)(y + j) * tiles_x + tile) >> j) & 1ull;
+		}
+		c_up |= (unsigned long long)__ballot_sync(0xffffffffu, pu) << (32 * h);
+		c_dn |= (unsigned long long)__ballot_sync(0xffffffffu, pd) << (32 * h);
+	}
+	if (x >= a.nx) return;
+	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
+	const size_t cc = (size_t)y * nx + x;
+	unsigned long long m_up = 0, m_dn = 0;
+	while (c_up) {
+		const int j = __ffsll((long long)c_up);
+		c_up &= c_up - 1;
+		m_up |= (unsigned long long)flag_has(__ldg(f_dn + cc - (size_t)j * nx), j) << (j - 1);
+	}
+	while (c_dn) {
+		const int j = __ffsll((long long)c_dn);
+		c_dn &= c_dn - 1;
+		m_dn |= (unsigned long long)flag_has(__ldg(f_up + cc + (size_t)j * nx), j) << (j - 1);
+	}
+	double2 ulist[CAP];
+	RunUnion<CAP> u(ulist);
+	pass2_gather(a, u, x, y, m_up, m_dn, flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0));
+	const unsigned long long c = (unsigned long long)(y - a.y0) * nx + x;
+	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
+	stage_emit(a.st, (size_t)c, u);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -33,14 +33,19 @@
 // the sweep line) in a data-parallel form. On the C5 torus ~2.6 of ~38 candidates per column survive, in
 // ~3.4 classes each (near tests alone: 7.6 candidates x 15 classes).
 //
-// Kernel structure (CTA = one row segment of P1_TX output columns):
-//   phase 0  the segment [x0-J, x0+TX+J) of row y is staged in shared memory as a flat candidate array;
-//   phase 1  thread per candidate: the four nn values (columns cx-1 / cx+1 from shared memory, rows y-1 / y+1
-//            from global memory) -> near / far thresholds, packed per candidate;
-//   phase 2  thread per output column: scan of its candidate range -> short survivor list with the class
-//            windows -> per-column window hulls (published as flags: pass 2 reads only those slots, pass 1
-//            writes only those) -> classes evaluated CB at a time in registers ((lo, hi) hulls per layer;
-//            a class whose union is not one interval per layer is redone by the general list path).
+// Kernel structure:
+//   k_thresh      thread per input column: the four nn values of each of its intervals -> near / far thresholds,
+//                 16 bytes per interval (tile independent, so halo candidates are not recomputed per tile);
+//   k_pass1_tile  persistent CTAs (one resident wave) pull row segments of P1_TX output columns; the cap tables
+//                 are staged in shared memory once per CTA. Per tile:
+//     phase 0  the segment [x0-J, x0+TX+J) of row y is staged as a flat candidate array (interval + thresholds);
+//     phase 1  thread per candidate: walks the output columns it survives for, computes the class windows of
+//              each surviving pair (the far test in y depends on the distance) and appends the pair to that
+//              output's list in shared memory;
+//     phase 2  thread per output column: window hulls of its list (published as flags: pass 2 reads only
+//              those slots, pass 1 writes only those) -> classes evaluated CB at a time in registers ((lo, hi)
+//              hulls per layer; a class whose union is not one interval per layer is redone by the general
+//              list path). Lists that overflow are replaced by a re-scan of the candidate range.
 // Lanes run along x: slot writes are full lines.
 #pragma once
 #include <cooperative_groups.h>
@@ -52,71 +57,8 @@ namespace vo {
 
 constexpr int P1_TX = 128;      // output columns (= threads) per CTA
 constexpr int P1_CB = 4;        // classes evaluated together in registers
-constexpr int P1_LCAP_S = 12;   // survivors listed per output column, single-interval launch
+constexpr int P1_LCAP_S = 32;   // survivors listed per output column, single-interval launch
 constexpr int P1_LCAP_M = 32;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
-
-struct Pass1TileArgs {
-	int nx, ny, J, cmax, tiles_x;
-	unsigned int tile0;     // first tile of a launch over all tiles of a band of rows
-	const uint32_t *off;
-	const double2 *spans;
-	const double *Ht;       // (J+1) rows of JPP doubles: Ht[d*JPP + j] = H[j][d] (-1 beyond the reach / the table)
-	const double *Dmono;    // J+2
-	const double *Emono;    // J+2
-	const float *G;         // (J+1)*(J+1): G[jt*(J+1) + d], rounded up, G[.][J] = +inf
-	const float *Ef;        // (J+1)*(J+2): Ef[d*(J+2) + c], rounded up, +inf for c > jmax[d]
-	const uint8_t *jmax;    // J+2: largest class whose reach covers distance d (jmax[J+1] = 0, never used for a live pair)
-	double2 *mid;
-	uint16_t *flags;        // [2][ny*nx]: lo | hi << 8 of the class window needed by the consumers above ([0]) / below ([1])
-	double2 *pool;
-	unsigned long long *cursor;
-	unsigned long long pool_cap;
-	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
-	// Device-side dispatch (no host round trip between the launches):
-	//   launch 1  <MULTI=false>, small candidate buffer, all tiles. Tiles with a multi-interval column go to
-	//             multi_tiles, tiles with more than cmax candidates to big_tiles.
-	//   launch 2  <MULTI=false>, large buffer, tiles = big_tiles.
-	//   launch 3  <MULTI=true> (two hulls per class), tiles = multi_tiles.
-	// A launch over a list uses one resident wave of CTAs pulling tiles with an atomic counter.
-	const unsigned int *tiles;        // NULL: all tiles
-	const unsigned int *tiles_count;
-	unsigned int *tiles_next;         // list launches: next list position to hand out
-	unsigned int *big_tiles;          // NULL: oversized tiles go to the redo list (k_pass1)
-	unsigned int *big_count;
-	unsigned int *multi_tiles;
-	unsigned int *multi_count;
-};
-
-__host__ __device__ inline int pass1_jpp(int J) { return (J + 1 + P1_CB + 1) & ~1; }
-
-__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap)
-{
-	const size_t JP = (size_t)J + 1, SEG = (size_t)P1_TX + 2 * J;
-	size_t b = 0;
-	b += (size_t)cmax * sizeof(double2);                    // candidates
-	b += JP * pass1_jpp(J) * sizeof(double);                // Ht
-	b += 2 * (JP + 1) * sizeof(double);                     // Dmono, Emono
-	b += ((JP * JP + 1) & ~(size_t)1) * sizeof(float);      // G
-	b += ((JP * (JP + 1) + 1) & ~(size_t)1) * sizeof(float);// Ef
-	b += 2 * (size_t)cmax * sizeof(float);                  // far values (up / down consumers)
-	b += 2 * (size_t)cmax * sizeof(uint32_t);               // packed thresholds
-	b += ((SEG + 2) & ~(size_t)1) * sizeof(uint32_t);       // segment offsets
-	b += 2 * (size_t)lcap * P1_TX * sizeof(uint32_t);       // survivor lists [s][thread]: candidate word, window word
-	b += (JP + 1 + 3) & ~(size_t)3;                         // jmax
-	return b + 32;
-}
-
-// Pool space for `n` entries, one atomic per converged group of threads instead of one per thread.
-__device__ __forceinline__ unsigned long long pool_alloc(unsigned long long *cursor, unsigned int n)
-{
-	namespace cg = cooperative_groups;
-	auto g = cg::coalesced_threads();
-	const unsigned int pre = cg::exclusive_scan(g, n);
-	const unsigned int total = g.shfl(pre + n, g.size() - 1);
-	unsigned long long base = 0;
-	if (g.thread_rank() == 0) base = atomicAdd(cursor, (unsigned long long)total);
-	return g.shfl(base, 0) + pre;
-}
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
 {
@@ -138,62 +80,257 @@ __device__ __forceinline__ int first_gt(const float *tab, int last, float v)
 __device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint32_t q0, uint32_t q1)
 {
 	double r = __longlong_as_double(0x7FF0000000000000LL);
-	for (uint32_t k = q0; k < q1; ++k) { const double2 v = q[k]; r = fmin(r, fmax(v.x - p.x, p.y - v.y)); }
+	for (uint32_t k = q0; k < q1; ++k) { const double2 v = __ldg(q + k); r = fmin(r, fmax(v.x - p.x, p.y - v.y)); }
 	return r;
 }
+
+// ---- dominance thresholds, one thread per input column ------------------------------------------------
+// thr[k] = { tnL | tnR << 8 | tfL << 16 | tfR << 24,
+//            (Ty_up - 1) | (Ty_dn - 1) << 8 | layer << 16 | reach[T-1] << 24,  float bits of v_up,  of v_dn }
+//   tnL / tnR : near, x: dropped for the outputs on the left / right at distances >= tn       (1 .. J+1)
+//   tfL / tfR : far, x: dropped for the outputs on the left / right at distances in [1, tf)   (1 .. J), except
+//               for the classes beyond the farther neighbour's reach (only at distances >= reach[T-1])
+//   Ty_up/dn  : near, y: takes part in the classes j < Ty for the consumers above / below, T = max of both
+//   v_up/dn   : far, y: -nn - m of the row FARTHER from the consumers above / below (rounded down)
+//   layer     : position of the interval inside its column (3 = third or later)
+struct ThreshArgs {
+	int nx, ny, J;
+	const uint32_t *off;
+	const double2 *spans;
+	const double *Dmono;    // J+2
+	const double *Emono;    // J+2
+	const float *G;         // (J+1)*(J+1)
+	const int *reach;       // J+1
+	uint4 *thr;             // per interval
+	unsigned long long c_begin, c_end;   // columns processed by this launch (a band of rows, or everything)
+};
+
+__global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
+{
+	extern __shared__ double s_DE[];
+	double *s_D = s_DE, *s_E = s_DE + a.J + 2;
+	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) { s_D[i] = a.Dmono[i]; s_E[i] = a.Emono[i]; }
+	__syncthreads();
+	const unsigned long long c = a.c_begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= a.c_end) return;
+	const uint32_t o0 = __ldg(a.off + c), o1 = __ldg(a.off + c + 1);
+	if (o0 == o1) return;
+	const int J = a.J, JP = J + 1;
+	const int x = (int)(c % (unsigned)a.nx), y = (int)(c / (unsigned)a.nx);
+	uint32_t l0 = 0, l1 = 0, r0 = 0, r1 = 0, u0 = 0, u1 = 0, d0 = 0, d1 = 0;
+	if (x > 0) { l0 = __ldg(a.off + c - 1); l1 = o0; }
+	if (x < a.nx - 1) { r0 = o1; r1 = __ldg(a.off + c + 2); }
+	if (y > 0) { u0 = __ldg(a.off + c - a.nx); u1 = __ldg(a.off + c - a.nx + 1); }
+	if (y < a.ny - 1) { d0 = __ldg(a.off + c + a.nx); d1 = __ldg(a.off + c + a.nx + 1); }
+	for (uint32_t k = o0; k < o1; ++k) {
+		const double2 p = __ldg(a.spans + k);
+		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
+		const double nnL = nn_of(p, a.spans, l0, l1), nnR = nn_of(p, a.spans, r0, r1);
+		const double nnU = nn_of(p, a.spans, u0, u1), nnD = nn_of(p, a.spans, d0, d1);
+		const int tnL = first_ge(s_D, J, nnL + m), tnR = first_ge(s_D, J, nnR + m);
+		const int tyu = first_ge(s_E, J, nnU + m), tyd = first_ge(s_E, J, nnD + m);
+		const int T = max(tyu, tyd);
+		int tfL = 1, tfR = 1;
+		if (J >= 1) {
+			const float *g = a.G + (size_t)(T - 1) * JP;
+			tfL = first_gt(g, J, __double2float_rd(-nnR - m));     // outputs on the left: the right neighbour is farther
+			tfR = first_gt(g, J, __double2float_rd(-nnL - m));
+		}
+		const uint32_t layer = min(k - o0, 3u);
+		uint4 t;
+		t.x = (uint32_t)tnL | ((uint32_t)tnR << 8) | ((uint32_t)tfL << 16) | ((uint32_t)tfR << 24);
+		t.y = (uint32_t)(tyu - 1) | ((uint32_t)(tyd - 1) << 8) | (layer << 16) | ((uint32_t)__ldg(a.reach + T - 1) << 24);
+		t.z = __float_as_uint(__double2float_rd(-nnD - m));        // consumers above: row y+1 is farther
+		t.w = __float_as_uint(__double2float_rd(-nnU - m));
+		a.thr[k] = t;
+	}
+}
+
+// ---- pass 1 ------------------------------------------------------------------------------------------
+struct Pass1TileArgs {
+	int nx, ny, J, cmax, tiles_x;
+	unsigned int tile0, ntiles;         // tiles [tile0, tile0 + ntiles) when `tiles` is NULL
+	const uint32_t *off;
+	const double2 *spans;
+	const uint4 *thr;       // k_thresh output
+	const double *Ht;       // (J+1) rows of JPP doubles: Ht[d*JPP + j] = H[j][d] (-1 beyond the reach / the table)
+	const float *Ef;        // (J+1)*(J+2): Ef[d*(J+2) + c], rounded up, +inf for c > jmax[d]
+	const uint8_t *jmax;    // J+2: largest class whose reach covers distance d
+	double2 *mid;
+	uint16_t *flags;        // [2][ny*nx]: lo | hi << 8 of the class window needed by the consumers above ([0]) / below ([1])
+	unsigned long long *tilemask;   // [2][ny*tiles_x]: OR of those windows over the columns of a tile (bit j = class j), zeroed by the host
+	double2 *pool;
+	unsigned long long *cursor;
+	unsigned long long pool_cap;
+	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
+	// Device-side dispatch (no host round trip between the launches). Every launch is one resident wave of CTAs
+	// pulling tiles with an atomic counter (tile costs vary a lot):
+	//   launch 1  <MULTI=false>, small candidate buffer, all tiles. Tiles with a multi-interval column go to
+	//             multi_tiles, tiles with more than cmax candidates to big_tiles.
+	//   launch 2  <MULTI=false>, large buffer, tiles = big_tiles.
+	//   launch 3  <MULTI=true> (two hulls per class), tiles = multi_tiles.
+	const unsigned int *tiles;        // NULL: all tiles of [tile0, tile0 + ntiles)
+	const unsigned int *tiles_count;  // length of `tiles` (device side)
+	unsigned int *tiles_next;         // next position to hand out
+	unsigned int *big_tiles;          // NULL: oversized tiles go to the redo list (k_pass1)
+	unsigned int *big_count;
+	unsigned int *multi_tiles;
+	unsigned int *multi_count;
+};
+
+__host__ __device__ inline int pass1_jpp(int J) { return (J + 1 + P1_CB + 1) & ~1; }
+
+__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap)
+{
+	const size_t JP = (size_t)J + 1, SEG = (size_t)P1_TX + 2 * J;
+	size_t b = 0;
+	b += (size_t)cmax * sizeof(double2);                    // candidates
+	b += (size_t)cmax * sizeof(uint4);                      // their thresholds
+	b += JP * pass1_jpp(J) * sizeof(double);                // Ht
+	b += ((JP * (JP + 1) + 3) & ~(size_t)3) * sizeof(float);// Ef
+	b += ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);       // segment offsets
+	b += (size_t)P1_TX * sizeof(uint32_t);                  // list lengths
+	b += 2 * (size_t)lcap * P1_TX * sizeof(uint32_t);       // survivor lists [s][thread]: candidate word, window word
+	b += ((size_t)cmax + 3) & ~(size_t)3;                   // segment column of each candidate
+	b += (JP + 1 + 3) & ~(size_t)3;                         // jmax
+	return b + 32;
+}
+
+// Pool space for `n` entries, one atomic per converged group of threads instead of one per thread.
+__device__ __forceinline__ unsigned long long pool_alloc(unsigned long long *cursor, unsigned int n)
+{
+	namespace cg = cooperative_groups;
+	auto g = cg::coalesced_threads();
+	const unsigned int pre = cg::exclusive_scan(g, n);
+	const unsigned int total = g.shfl(pre + n, g.size() - 1);
+	unsigned long long base = 0;
+	if (g.thread_rank() == 0) base = atomicAdd(cursor, (unsigned long long)total);
+	return g.shfl(base, 0) + pre;
+}
+
+// Class windows of a pair from its thresholds: lo_u | hi_u << 8 | lo_d << 16 | hi_d << 24 (0 = both empty).
+// base: first class the far test in x leaves to the pair; fu / fd: classes the far test in y drops (leading).
+__device__ __forceinline__ uint32_t pair_windows(int tyu, int tyd, int jm1, int base, int fu, int fd)
+{
+	int hu = min(tyu, jm1), hd = min(tyd, jm1);
+	int lu = max(base, fu), ld = max(base, fd);
+	if (lu > 0 || ld > 0) { lu = max(lu, 1); ld = max(ld, 1); }          // class 0 needs both windows
+	if (lu >= hu) lu = hu = 0;
+	if (ld >= hd) ld = hd = 0;
+	return (uint32_t)lu | ((uint32_t)hu << 8) | ((uint32_t)ld << 16) | ((uint32_t)hd << 24);
+}
+
+// Shared-memory layout of the tile kernel (dynamic shared memory, see pass1_tile_smem).
+struct TileSmem {
+	double2 *cand;
+	uint4 *thr;
+	double *Ht;
+	float *Ef;
+	uint32_t *off, *cnt, *listA, *listW;
+	uint8_t *ci, *jmax;
+	__device__ __forceinline__ TileSmem(unsigned char *raw, int J, int cmax, int lcap)
+	{
+		const int JP = J + 1, SEG = P1_TX + 2 * J;
+		cand = reinterpret_cast<double2 *>(raw);
+		thr = reinterpret_cast<uint4 *>(cand + cmax);
+		Ht = reinterpret_cast<double *>(thr + cmax);
+		Ef = reinterpret_cast<float *>(Ht + (size_t)JP * pass1_jpp(J));
+		off = reinterpret_cast<uint32_t *>(Ef + ((JP * (JP + 1) + 3) & ~3));
+		cnt = off + ((SEG + 4) & ~3);
+		listA = cnt + P1_TX;
+		listW = listA + (size_t)lcap * P1_TX;
+		ci = reinterpret_cast<uint8_t *>(listW + (size_t)lcap * P1_TX);
+		jmax = ci + ((cmax + 3) & ~3);
+	}
+};
+
+// The staged tile.
+template <int LCAP>
+struct Tile {
+	const double2 *cand;
+	const uint4 *thr;
+	const uint8_t *ci;         // segment column of each candidate
+	const double *Ht;
+	const float *Ef;
+	const uint8_t *jmax;
+	uint32_t *cnt;             // [P1_TX] list lengths
+	uint32_t *listA, *listW;   // [s * P1_TX + xi]: k | d << 16, window word
+	int J, JPP;
+
+	// Phase 1: candidate k appends itself to the lists of the output columns it survives for.
+	__device__ __forceinline__ void scatter(int k, int txe) const
+	{
+		const uint4 th = thr[k];
+		const int i = (int)ci[k];
+		const int tyu = (int)(th.y & 0xffu) + 1, tyd = (int)((th.y >> 8) & 0xffu) + 1, T = max(tyu, tyd), rx = (int)(th.y >> 24);
+		const float vu = __uint_as_float(th.z), vd = __uint_as_float(th.w);
+#pragma unroll 1
+		for (int side = 0; side < 2; ++side) {             // 0: outputs on the left (ix = i - d, incl. d = 0), 1: on the right
+			const int tn = side ? (int)((th.x >> 8) & 0xffu) : (int)(th.x & 0xffu);
+			const int tf = side ? (int)(th.x >> 24) : (int)((th.x >> 16) & 0xffu);
+			// distances that hit an output column [J, J + txe) and survive the near test
+			int d = side ? max(J - i, 1) : max(i - (J + txe - 1), 0);
+			const int dhi = min(side ? J + txe - 1 - i : i - J, min(tn - 1, J));
+			int fu = -1, fd = -1;                           // far, y: dropped leading classes (non-increasing in d)
+#pragma unroll 1
+			for (; d <= dhi; ++d) {
+				int base = 0;
+				if (d >= 1 && d < tf) {
+					// far-dominated in x: only the classes beyond the farther neighbour's reach remain (d >= reach[T-1])
+					if (d < rx) { d = min(tf, rx) - 1; continue; }
+					base = (int)jmax[d + 1] + 1;
+				}
+				const int jm1 = (int)jmax[d] + 1;
+				if (base >= min(T, jm1)) continue;
+				const float *row = Ef + (size_t)d * (J + 2);
+				if (fu < 0) { fu = first_gt(row, J + 1, vu) - 1; fd = first_gt(row, J + 1, vd) - 1; }
+				else {
+					while (fu > 0 && row[fu] > vu) --fu;
+					while (fd > 0 && row[fd] > vd) --fd;
+				}
+				const uint32_t w = pair_windows(tyu, tyd, jm1, base, fu, fd);
+				if (w == 0) continue;
+				const int xo = (side ? i + d : i - d) - J;
+				const uint32_t pos = atomicAdd(cnt + xo, 1u);
+				if (pos < (uint32_t)LCAP) { listA[pos * P1_TX + xo] = (uint32_t)k | ((uint32_t)d << 16); listW[pos * P1_TX + xo] = w; }
+			}
+		}
+	}
+};
 
 // Per-thread view of the staged tile (phase 2).
 template <int LCAP>
 struct TileThread {
-	const double2 *cand;
-	const double *Ht;
-	const float *Ef;
-	const float *vu, *vd;      // far values per candidate (consumers above / below)
-	const uint32_t *wa;        // first | width << 8 | column << 16 | layer << 24
-	const uint32_t *wb;        // tfL | tfR << 8 | (Ty_up - 1) << 16 | (Ty_dn - 1) << 24
-	uint32_t *listA, *listB;   // [s * P1_TX + xi]
-	const uint8_t *jmax;
-	int J, JPP, xi, ix, kb, niter, y, x0;
+	Tile<LCAP> t;
+	int xi, ix, kb, niter, y, x0;
 	bool direct;
 
-	// Is candidate k a surviving pair for this output, before the (d-dependent) far test in y? On success
-	// `e` = k | d << 16 | base << 24 (base: first class the x-far test leaves to this pair).
-	__device__ __forceinline__ bool near_alive(int k, uint32_t &e) const
+	// direct mode (the list overflowed): candidate k of the range re-tested for this output
+	__device__ __forceinline__ bool pair_direct(int k, uint32_t &e, uint32_t &w) const
 	{
-		const uint32_t w = wa[k];
-		if ((uint32_t)(ix - (int)(w & 0xffu)) > ((w >> 8) & 0xffu)) return false;
-		const int i = (int)((w >> 16) & 0xffu), d = abs(i - ix);
-		const uint32_t b = wb[k];
-		const int tf = ix < i ? (int)(b & 0xffu) : (int)((b >> 8) & 0xffu);
-		const int T = (int)max((b >> 16) & 0xffu, b >> 24) + 1;
-		const int base = (d >= 1 && d < tf) ? (int)jmax[d + 1] + 1 : 0;
-		if (base >= min(T, (int)jmax[d] + 1)) return false;
-		e = (uint32_t)k | ((uint32_t)d << 16) | ((uint32_t)base << 24);
-		return true;
-	}
-	// Class windows of a near-alive pair: lo_u | hi_u << 8 | lo_d << 16 | hi_d << 24 (0 = both empty).
-	__device__ __forceinline__ uint32_t windows(uint32_t e) const
-	{
-		const int k = (int)(e & 0xffffu), d = (int)((e >> 16) & 0xffu), base = (int)(e >> 24);
-		const uint32_t b = wb[k];
-		const int jm1 = (int)jmax[d] + 1;
-		int hu = min((int)((b >> 16) & 0xffu) + 1, jm1), hd = min((int)(b >> 24) + 1, jm1);
-		const float *row = Ef + (size_t)d * (J + 2);
-		int lu = max(base, first_gt(row, J + 1, vu[k]) - 1);
-		int ld = max(base, first_gt(row, J + 1, vd[k]) - 1);
-		if (lu > 0 || ld > 0) { lu = max(lu, 1); ld = max(ld, 1); }      // class 0 needs both windows
-		if (lu >= hu) lu = hu = 0;
-		if (ld >= hd) ld = hd = 0;
-		return (uint32_t)lu | ((uint32_t)hu << 8) | ((uint32_t)ld << 16) | ((uint32_t)hd << 24);
-	}
-	// s-th entry of the survivor loop: candidate word and window word (0: not a survivor).
-	__device__ __forceinline__ bool survivor(int s, uint32_t &e, uint32_t &w) const
-	{
-		if (!direct) { e = listA[s * P1_TX + xi]; w = listB[s * P1_TX + xi]; return w != 0; }
-		if (!near_alive(kb + s, e)) return false;
-		w = windows(e);
+		const uint4 th = t.thr[k];
+		const int i = (int)t.ci[k], d = abs(i - ix);
+		const bool left = ix < i;
+		const int tn = left ? (int)(th.x & 0xffu) : (int)((th.x >> 8) & 0xffu);
+		if (d >= 1 && d >= tn) return false;
+		const int tf = left ? (int)((th.x >> 16) & 0xffu) : (int)(th.x >> 24);
+		const int tyu = (int)(th.y & 0xffu) + 1, tyd = (int)((th.y >> 8) & 0xffu) + 1;
+		const int base = (d >= 1 && d < tf) ? (int)t.jmax[d + 1] + 1 : 0;
+		const int jm1 = (int)t.jmax[d] + 1;
+		if (base >= min(max(tyu, tyd), jm1)) return false;
+		const float *row = t.Ef + (size_t)d * (t.J + 2);
+		const int fu = first_gt(row, t.J + 1, __uint_as_float(th.z)) - 1, fd = first_gt(row, t.J + 1, __uint_as_float(th.w)) - 1;
+		w = pair_windows(tyu, tyd, jm1, base, fu, fd);
+		e = (uint32_t)k | ((uint32_t)d << 16);
 		return w != 0;
 	}
+	// s-th entry of the survivor loop: candidate word (k | d << 16) and window word
+	__device__ __forceinline__ bool survivor(int s, uint32_t &e, uint32_t &w) const
+	{
+		if (!direct) { e = t.listA[s * P1_TX + xi]; w = t.listW[s * P1_TX + xi]; return true; }
+		return pair_direct(kb + s, e, w);
+	}
+	__device__ __forceinline__ int layer(uint32_t e) const { return (int)((t.thr[e & 0xffffu].y >> 16) & 3u); }
 };
 
 // bits q in [0, CB) with l <= cb + q < h
@@ -203,6 +340,14 @@ __device__ __forceinline__ unsigned int range_mask(int l, int h, int cb)
 	const int a = min(max(l - cb, 0), CB), b = min(max(h - cb, 0), CB);
 	return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
+// bits [lo, hi) of a 64-bit class mask (hi <= 64)
+__device__ __forceinline__ unsigned long long class_mask(int lo, int hi)
+{
+	if (hi <= lo) return 0ull;
+	const unsigned long long upto = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
+	return upto & ~((1ull << lo) - 1ull);
+}
+
 template <int CB>
 __device__ __forceinline__ unsigned int window_mask(uint32_t w, int cb)
 {
@@ -219,8 +364,8 @@ __device__ __noinline__ double2 class_general(const Pass1TileArgs &a, const Tile
 		uint32_t e, w;
 		if (!t.survivor(s, e, w)) continue;
 		if (window_mask<1>(w, j)) {
-			const double2 ab = t.cand[e & 0xffffu];
-			const double hh = t.Ht[(size_t)((e >> 16) & 0xffu) * t.JPP + j];
+			const double2 ab = t.t.cand[e & 0xffffu];
+			const double hh = t.t.Ht[(size_t)((e >> 16) & 0xffu) * t.t.JPP + j];
 			u.insert(ab.x - hh, ab.y + hh);
 		}
 	}
@@ -257,14 +402,14 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 		const unsigned int valid = window_mask<CB>(w, cb);
 		if (!valid) continue;
 		const int k = (int)(e & 0xffffu), d = (int)((e >> 16) & 0xffu);
-		const double2 ab = t.cand[k];
-		const double *hp = t.Ht + (size_t)d * t.JPP + cb;
+		const double2 ab = t.t.cand[k];
+		const double *hp = t.t.Ht + (size_t)d * t.t.JPP + cb;
 		double h[CB];
 #pragma unroll
 		for (int q = 0; q < CB; ++q) h[q] = hp[q];
 		// branch-free: a class that does not take this survivor gets the cap -inf, i.e. the candidate
 		// (+inf, -inf), which leaves its hull untouched
-		const int lay = NL == 1 ? 0 : min((int)((t.wa[k] >> 24) & 3u), NL - 1);
+		const int lay = NL == 1 ? 0 : min(t.layer(e), NL - 1);
 #pragma unroll
 		for (int l = 0; l < NL; ++l) {
 			if (NL == 1 || lay == l) {
@@ -298,7 +443,7 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 	for (int q = 0; q < CB; ++q) {
 		if (!((need >> q) & 1u)) continue;
 		const int j = cb + q;
-		const unsigned long long slot = ((unsigned long long)t.y * (t.J + 1) + j) * a.nx + t.x0 + t.xi;
+		const unsigned long long slot = ((unsigned long long)t.y * (t.t.J + 1) + j) * a.nx + t.x0 + t.xi;
 		double2 out;
 		if ((complex_mask >> q) & 1u) out = class_general<CAP, LCAP>(a, t, j, slot);
 		else if (NL == 1) out = make_double2(lo[0][q], hi[0][q]);          // (+inf, -inf) is the empty slot
@@ -340,24 +485,14 @@ __device__ __forceinline__ void eval_classes(const Pass1TileArgs &a, const TileT
 }
 
 template <int CAP, bool MULTI, int LCAP>
-__device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const unsigned int tile)
+__device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const unsigned int tile, unsigned char *smem_raw)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int J = a.J, JP = J + 1, JPP = pass1_jpp(J), TX = P1_TX, SEG = TX + 2 * J;
-	double2 *s_cand = reinterpret_cast<double2 *>(smem_raw);
-	double *s_Ht = reinterpret_cast<double *>(s_cand + a.cmax);
-	double *s_D = s_Ht + (size_t)JP * JPP;
-	double *s_E = s_D + JP + 1;
-	float *s_G = reinterpret_cast<float *>(s_E + JP + 1);
-	float *s_Ef = s_G + ((JP * JP + 1) & ~1);
-	float *s_vu = s_Ef + ((JP * (JP + 1) + 1) & ~1);
-	float *s_vd = s_vu + a.cmax;
-	uint32_t *s_wa = reinterpret_cast<uint32_t *>(s_vd + a.cmax);
-	uint32_t *s_wb = s_wa + a.cmax;
-	uint32_t *s_off = s_wb + a.cmax;
-	uint32_t *s_listA = s_off + ((SEG + 2) & ~1);
-	uint32_t *s_listB = s_listA + (size_t)LCAP * TX;
-	uint8_t *s_jmax = reinterpret_cast<uint8_t *>(s_listB + (size_t)LCAP * TX);
+	const TileSmem sm(smem_raw, J, a.cmax, LCAP);
+	double2 *s_cand = sm.cand;
+	uint4 *s_thr = sm.thr;
+	uint32_t *s_off = sm.off, *s_cnt = sm.cnt;
+	uint8_t *s_ci = sm.ci;
 
 	const int tid = threadIdx.x, nthr = blockDim.x;
 	const int y = (int)(tile / (unsigned)a.tiles_x);
@@ -387,6 +522,7 @@ __device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const un
 		}
 		// no larger buffer: leave every slot of the tile to k_pass1
 		if (tid < txe) { a.flags[rowbase + x0 + tid] = full; a.flags[ncols_all + rowbase + x0 + tid] = full; }
+		if (tid == 0) { a.tilemask[tile] = ~0ull; a.tilemask[(size_t)a.tiles_x * a.ny + tile] = ~0ull; }
 		for (int idx = tid; idx < JP * txe; idx += nthr) {
 			const int j = idx / txe, xi = idx % txe;
 			redo_push(a.redo, ((unsigned long long)y * JP + j) * a.nx + x0 + xi);
@@ -397,109 +533,87 @@ __device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const un
 		if (tid < txe) { a.flags[rowbase + x0 + tid] = 0; a.flags[ncols_all + rowbase + x0 + tid] = 0; }
 		return;
 	}
-	for (int i = tid; i < JP * JPP; i += nthr) s_Ht[i] = __ldg(a.Ht + i);
-	for (int i = tid; i < JP + 1; i += nthr) { s_D[i] = __ldg(a.Dmono + i); s_E[i] = __ldg(a.Emono + i); }
-	for (int i = tid; i < JP * JP; i += nthr) s_G[i] = __ldg(a.G + i);
-	for (int i = tid; i < JP * (JP + 1); i += nthr) s_Ef[i] = __ldg(a.Ef + i);
-	for (int i = tid; i < JP + 1; i += nthr) s_jmax[i] = __ldg(a.jmax + i);
-	for (int k = tid; k < ncand; k += nthr) s_cand[k] = __ldg(a.spans + base + k);
+	for (int k = tid; k < ncand; k += nthr) { s_cand[k] = __ldg(a.spans + base + k); s_thr[k] = __ldg(a.thr + base + k); }
 	for (int i = tid; i < SEG; i += nthr)
-		for (uint32_t k = s_off[i] - base; k < s_off[i + 1] - base; ++k) s_wa[k] = (uint32_t)i << 16;
+		for (uint32_t k = s_off[i] - base; k < s_off[i + 1] - base; ++k) s_ci[k] = (uint8_t)i;
+	if (tid < TX) s_cnt[tid] = 0;
 	__syncthreads();
 
-	// ---- phase 1: dominance thresholds, thread per candidate -------------------------------------------
-	for (int k = tid; k < ncand; k += nthr) {
-		const int i = (int)(s_wa[k] >> 16);
-		const double2 p = s_cand[k];
-		const double inf = __longlong_as_double(0x7FF0000000000000LL);
-		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
-		double nnL = inf, nnR = inf, nnU = inf, nnD = inf;
-		if (i > 0) nnL = nn_of(p, s_cand, s_off[i - 1] - base, s_off[i] - base);
-		if (i < SEG - 1) nnR = nn_of(p, s_cand, s_off[i + 1] - base, s_off[i + 2] - base);
-		const size_t c = rowbase + (size_t)(x0 - J + i);                // the candidate's own column (inside the grid)
-		if (y > 0) nnU = nn_of(p, a.spans, __ldg(a.off + c - a.nx), __ldg(a.off + c - a.nx + 1));
-		if (y < a.ny - 1) nnD = nn_of(p, a.spans, __ldg(a.off + c + a.nx), __ldg(a.off + c + a.nx + 1));
-		// near: dominated for outputs at distance >= t (x) / consumers at row distance >= Ty (y)
-		const int tnL = first_ge(s_D, J, nnL + m), tnR = first_ge(s_D, J, nnR + m);
-		const int tyu = first_ge(s_E, J, nnU + m), tyd = first_ge(s_E, J, nnD + m);
-		// far, x: dominated for the outputs on the left at distances [1, tfL) by the right neighbour, ...
-		const float *g = s_G + (size_t)(max(tyu, tyd) - 1) * JP;
-		const int tfL = first_gt(g, J, __double2float_rd(-nnR - m));
-		const int tfR = first_gt(g, J, __double2float_rd(-nnL - m));
-		// survives the near tests for the outputs ix in [i - (tnL-1), i + (tnR-1)] (segment coordinates)
-		const int first = max(i - (tnL - 1), 0);
-		const int last = min(i + (tnR - 1), SEG - 1);
-		const uint32_t layer = min((uint32_t)k - (s_off[i] - base), 3u);     // position of the interval inside its column
-		s_wa[k] = (uint32_t)first | ((uint32_t)(last - first) << 8) | ((uint32_t)i << 16) | (layer << 24);
-		s_wb[k] = (uint32_t)tfL | ((uint32_t)tfR << 8) | ((uint32_t)(tyu - 1) << 16) | ((uint32_t)(tyd - 1) << 24);
-		// far, y: the consumers above are served by row y+1 instead, those below by row y-1
-		s_vu[k] = __double2float_rd(-nnD - m);
-		s_vd[k] = __double2float_rd(-nnU - m);
-	}
+	Tile<LCAP> tl;
+	tl.cand = s_cand; tl.thr = s_thr; tl.ci = s_ci; tl.Ht = sm.Ht; tl.Ef = sm.Ef; tl.jmax = sm.jmax;
+	tl.cnt = s_cnt; tl.listA = sm.listA; tl.listW = sm.listW; tl.J = J; tl.JPP = JPP;
+
+	// ---- phase 1: thread per candidate, surviving pairs appended to the output lists --------------------
+	for (int k = tid; k < ncand; k += nthr) tl.scatter(k, txe);
 	__syncthreads();
-	if (tid >= txe) return;
 
 	// ---- phase 2: one thread per output column ------------------------------------------------------
+	const bool active = tid < txe;
 	const int xi = tid, ix = xi + J;
 	TileThread<LCAP> t;
-	t.cand = s_cand; t.Ht = s_Ht; t.Ef = s_Ef; t.vu = s_vu; t.vd = s_vd; t.wa = s_wa; t.wb = s_wb;
-	t.listA = s_listA; t.listB = s_listB; t.jmax = s_jmax;
-	t.J = J; t.JPP = JPP; t.xi = xi; t.ix = ix; t.y = y; t.x0 = x0;
-	const int kb = (int)(s_off[ix - J] - base), ke = (int)(s_off[ix + J + 1] - base);
-	t.kb = kb;
-	int S = 0;
-	for (int k = kb; k < ke; ++k) {
-		uint32_t e;
-		if (t.near_alive(k, e)) {
-			if (S < LCAP) s_listA[S * TX + xi] = e;
-			++S;
+	t.t = tl; t.xi = xi; t.ix = ix; t.y = y; t.x0 = x0;
+	int UL = 255, UH = 0, DL = 255, DH = 0;
+	int maxlayer = 0;
+	if (active) {
+		t.kb = (int)(s_off[ix - J] - base);
+		const int S = (int)s_cnt[xi];
+		// more survivors than the list holds (steep walls, many layers): re-scan the candidate range instead
+		t.direct = S > LCAP;
+		t.niter = t.direct ? (int)(s_off[ix + J + 1] - base) - t.kb : S;
+		for (int s = 0; s < t.niter; ++s) {
+			uint32_t e, w;
+			if (!t.survivor(s, e, w)) continue;
+			if (MULTI) maxlayer = max(maxlayer, t.layer(e));
+			const int lu = (int)(w & 0xffu), hu = (int)((w >> 8) & 0xffu), ld = (int)((w >> 16) & 0xffu), hd = (int)(w >> 24);
+			if (hu > lu) { UL = min(UL, lu); UH = max(UH, hu); }
+			if (hd > ld) { DL = min(DL, ld); DH = max(DH, hd); }
+		}
+		if (UH == 0) UL = 0;
+		if (DH == 0) DL = 0;
+		a.flags[rowbase + x0 + xi] = (uint16_t)(UL | (UH << 8));
+		a.flags[ncols_all + rowbase + x0 + xi] = (uint16_t)(DL | (DH << 8));
+	} else { UL = UH = DL = DH = 0; }
+	// OR of the windows over the tile: pass 2 skips a producer row whose tile lacks the class
+	{
+		const unsigned long long mu = class_mask(UL, UH), md = class_mask(DL, DH);
+		const unsigned int mu0 = __reduce_or_sync(0xffffffffu, (unsigned int)mu), mu1 = __reduce_or_sync(0xffffffffu, (unsigned int)(mu >> 32));
+		const unsigned int md0 = __reduce_or_sync(0xffffffffu, (unsigned int)md), md1 = __reduce_or_sync(0xffffffffu, (unsigned int)(md >> 32));
+		if ((tid & 31) == 0) {
+			const size_t ntl = (size_t)a.tiles_x * a.ny;
+			if (mu0 | mu1) atomicOr(a.tilemask + tile, (unsigned long long)mu0 | ((unsigned long long)mu1 << 32));
+			if (md0 | md1) atomicOr(a.tilemask + ntl + tile, (unsigned long long)md0 | ((unsigned long long)md1 << 32));
 		}
 	}
-	// more survivors than the list holds (steep walls, many layers): re-scan the candidate range instead
-	t.direct = S > LCAP;
-	t.niter = t.direct ? ke - kb : S;
-	int UL = 255, UH = 0, DL = 255, DH = 0;
-	uint32_t maxlayer = 0;
-	for (int s = 0; s < t.niter; ++s) {
-		uint32_t e, w;
-		if (t.direct) { if (!t.near_alive(kb + s, e)) continue; }
-		else e = s_listA[s * TX + xi];
-		w = t.windows(e);
-		if (!t.direct) s_listB[s * TX + xi] = w;
-		if (w == 0) continue;
-		if (MULTI) maxlayer = max(maxlayer, (s_wa[e & 0xffffu] >> 24) & 3u);
-		const int lu = (int)(w & 0xffu), hu = (int)((w >> 8) & 0xffu), ld = (int)((w >> 16) & 0xffu), hd = (int)(w >> 24);
-		if (hu > lu) { UL = min(UL, lu); UH = max(UH, hu); }
-		if (hd > ld) { DL = min(DL, ld); DH = max(DH, hd); }
-	}
-	if (UH == 0) UL = 0;
-	if (DH == 0) DL = 0;
-	a.flags[rowbase + x0 + xi] = (uint16_t)(UL | (UH << 8));
-	a.flags[ncols_all + rowbase + x0 + xi] = (uint16_t)(DL | (DH << 8));
-	if (UH == 0 && DH == 0) return;
+	if (!active || (UH == 0 && DH == 0)) return;
 	if (!MULTI || maxlayer == 0) eval_classes<P1_CB, 1, CAP, LCAP>(a, t, UL, UH, DL, DH);   // every survivor is the first interval of its column
 	else eval_classes<P1_CB, 2, CAP, LCAP>(a, t, UL, UH, DL, DH);                           // two hulls per class
 }
 
-// LIST = false: launch over all tiles, one tile per CTA. LIST = true: launch over a collected list; a fixed
-// grid strides over it (the list length is only known on the device).
+// One resident wave of CTAs; every CTA stages the tables once and then pulls tiles with an atomic counter.
+// LIST = false: the tiles [tile0, tile0 + ntiles). LIST = true: the tiles of a list collected by an earlier
+// launch (its length is only known on the device).
 template <int CAP, bool MULTI, bool LIST>
 __global__ void __launch_bounds__(P1_TX, MULTI ? 4 : 5) k_pass1_tile(Pass1TileArgs a)
 {
 	constexpr int LCAP = (MULTI || LIST) ? P1_LCAP_M : P1_LCAP_S;
-	if (!LIST) pass1_tile_body<CAP, MULTI, LCAP>(a, a.tile0 + blockIdx.x);
-	else {
-		// one resident wave of CTAs pulls tiles from the list (tile costs vary a lot: dynamic beats strided)
-		__shared__ unsigned int s_next;
-		const unsigned int n = *a.tiles_count;
-		for (;;) {
-			if (threadIdx.x == 0) s_next = atomicAdd(a.tiles_next, 1u);
-			__syncthreads();
-			const unsigned int i = s_next;
-			if (i >= n) break;
-			pass1_tile_body<CAP, MULTI, LCAP>(a, a.tiles[i]);
-			__syncthreads();                                // the next tile reuses the shared buffers (and s_next)
-		}
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	__shared__ unsigned int s_next;
+	const unsigned int n = LIST ? *a.tiles_count : a.ntiles;
+	if (n == 0) return;
+	{
+		const int JP = a.J + 1;
+		const TileSmem sm(smem_raw, a.J, a.cmax, LCAP);
+		for (int i = threadIdx.x; i < JP * pass1_jpp(a.J); i += blockDim.x) sm.Ht[i] = __ldg(a.Ht + i);
+		for (int i = threadIdx.x; i < JP * (JP + 1); i += blockDim.x) sm.Ef[i] = __ldg(a.Ef + i);
+		for (int i = threadIdx.x; i < JP + 1; i += blockDim.x) sm.jmax[i] = __ldg(a.jmax + i);
+	}
+	for (;;) {
+		if (threadIdx.x == 0) s_next = atomicAdd(a.tiles_next, 1u);
+		__syncthreads();                                    // (also publishes the tables before the first tile)
+		const unsigned int i = s_next;
+		if (i >= n) break;
+		pass1_tile_body<CAP, MULTI, LCAP>(a, LIST ? a.tiles[i] : a.tile0 + i, smem_raw);
+		__syncthreads();                                    // the next tile reuses the shared buffers (and s_next)
 	}
 }
 

@@ -61,8 +61,10 @@ struct vo_dmid {
 	double2 *slots = nullptr;
 	double2 *pool = nullptr;
 	uint16_t *flags = nullptr;      // [2][ny*nx]: class window (lo | hi << 8) needed by the consumer rows above / below each mid column
+	unsigned long long *tilemask = nullptr;   // [2][ny * ceil(nx / P1_TX)]: OR of the windows per pass-1 tile
 	uint64_t pool_cap = 0, pool_used = 0;
 };
+static_assert(P1_TX == P2_TX, "pass 2 reads the tile masks of pass 1: same tile width");
 
 namespace {
 
@@ -281,7 +283,7 @@ struct RedoBuf {
 };
 
 constexpr int NCTR = 16;  // pass 1: [0] mid-pool cursor [2] redo count [3] big-tile count [4] redo failures [5] multi-tile count
-                          //         [6] [7] list cursors; staged gathers (pass 2, ...): [1] stage-pool cursor [8] redo count [9] failures
+                          //         [6] [7] list cursors [10] tile cursor of the first launch; staged gathers (pass 2, ...): [1] stage-pool cursor [8] redo count [9] failures
 
 int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 {
@@ -527,6 +529,10 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	unsigned long long pool_cap = std::max(65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4), ctx->pool_hint);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, 2 * ncols);
+	const unsigned long long nmask = 2ull * in->ny * ((in->nx + TX - 1) / TX);
+	if (rc == VO_OK) rc = dalloc(ctx, &m->tilemask, nmask);
+	Tmp<uint4> thr(ctx);
+	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &thr.p, in->nspans);
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &multi_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
@@ -547,12 +553,18 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		a.redo = rb.rd;
 		a.wk = Work{nullptr, nslots, nullptr, 0u, nullptr};
 		if (nslots && tile_now) {
+			cudaMemsetAsync(m->tilemask, 0, nmask * sizeof(unsigned long long), ctx->stream);
+			ThreshArgs ta;
+			ta.nx = in->nx; ta.ny = in->ny; ta.J = t.J; ta.off = in->off; ta.spans = in->spans;
+			ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
+			ta.c_begin = 0; ta.c_end = ncols;
+			k_thresh<<<blocks_for(ncols, 256), 256, 2 * (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(ta);
+			ctx->launches++;
 			Pass1TileArgs g;
 			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.tile0 = 0;
 			g.tiles_x = (in->nx + TX - 1) / TX;
-			g.off = in->off; g.spans = in->spans; g.Ht = tt.Ht; g.Dmono = tt.Dmono; g.Emono = tt.Emono;
-			g.G = tt.G; g.Ef = tt.Ef; g.jmax = tt.jmax;
-			g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
+			g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
+			g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
 			const double seg_est = k_in * (TX + 2 * t.J) * 1.3;
 			const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : seg_est <= 1024 ? 1024 : cmax;
@@ -573,8 +585,10 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			};
 			cudaEventRecord(ctx->kev[0], ctx->stream);
 			// launch 1: single-interval tiles, small candidate buffer
-			g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.tiles_next = nullptr; g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
-			k_pass1_tile<CAP_FAST, false, false><<<(unsigned int)ntiles, P1_TX, smem_small, ctx->stream>>>(g);
+			g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.ntiles = (unsigned int)ntiles;
+			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 10);
+			g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
+			k_pass1_tile<CAP_FAST, false, false><<<wave((const void *)k_pass1_tile<CAP_FAST, false, false>, smem_small), P1_TX, smem_small, ctx->stream>>>(g);
 			ctx->launches++;
 			if (cmax_small < cmax) {        // launch 2: the single-interval tiles that need the large buffer
 				g.cmax = cmax; g.tiles = big_tiles.p; g.tiles_count = big_count; g.big_tiles = nullptr;
@@ -593,6 +607,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 		} else if (nslots) {
 			// every class of every column is computed: all class windows = [0, J + 1)
 			k_fill16<<<blocks_for(2 * ncols, 256), 256, 0, ctx->stream>>>(m->flags, 2 * ncols, (uint16_t)((t.J + 1) << 8));
+			cudaMemsetAsync(m->tilemask, 0xFF, nmask * sizeof(unsigned long long), ctx->stream);
 			ctx->launches++;
 			cudaEventRecord(ctx->kev[0], ctx->stream);
 			k_pass1<CAP_FAST><<<blocks_for(nslots, 128), 128, 0, ctx->stream>>>(a);
@@ -631,13 +646,16 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
 	if (y0 < 0 || y1 > m->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "pass 2 row range outside the mid volume");
 	Pass2Args a;
 	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = y0; a.y1 = y1;
-	a.mid = m->slots; a.flags = m->flags; a.pool = m->pool;
+	a.mid = m->slots; a.flags = m->flags; a.tilemask = m->tilemask; a.pool = m->pool;
 	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
 		[&](Pass2Args &g) {
 			cudaEventRecord(ctx->kev[2], s);
-			k_pass2<CAP_FAST><<<blocks_for(g.wk.n, 128), 128, 0, s>>>(g);
+			if (g.J <= 63)
+				k_pass2_rows<CAP_FAST><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+			else
+				k_pass2<CAP_FAST><<<blocks_for(g.wk.n, 128), 128, 0, s>>>(g);
 			cudaEventRecord(ctx->kev[3], s);
 			ctx->kev_valid[1] = true;
 		},
@@ -1003,7 +1021,10 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	m->pool_cap = std::max(65536ull + (unsigned long long)(J + 1) * (nspans / 4), ctx->pool_hint);
 	VO_TRY(dalloc(ctx, &m->pool, m->pool_cap));
 	VO_TRY(dalloc(ctx, &m->flags, 2 * ncols));
+	Tmp<uint4> thr(ctx);
+	VO_TRY(dalloc(ctx, &thr.p, nspans));
 	const int tiles_x = (nx + TX - 1) / TX;
+	VO_TRY(dalloc(ctx, &m->tilemask, 2ull * ny * tiles_x));
 	const unsigned long long ntiles = (unsigned long long)tiles_x * ny;
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
 	VO_TRY(dalloc(ctx, &big_tiles.p, ntiles));
@@ -1035,14 +1056,17 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 
 	cudaStream_t sm = ctx->stream;
 	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
+	cudaMemsetAsync(m->tilemask, 0, 2ull * ny * tiles_x * sizeof(unsigned long long), sm);
 	cudaEventRecord(ctx->ev[0], sm);
 
 	// launch parameters shared by all bands
+	ThreshArgs ta;
+	ta.nx = nx; ta.ny = ny; ta.J = J; ta.off = in->off; ta.spans = in->spans;
+	ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
 	Pass1TileArgs g;
 	g.nx = nx; g.ny = ny; g.J = J; g.tiles_x = tiles_x;
-	g.off = in->off; g.spans = in->spans; g.Ht = tt.Ht; g.Dmono = tt.Dmono; g.Emono = tt.Emono;
-	g.G = tt.G; g.Ef = tt.Ef; g.jmax = tt.jmax;
-	g.mid = m->slots; g.flags = m->flags; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
+	g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
+	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 	unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
 	unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
 	g.big_count = big_count; g.multi_tiles = multi_tiles.p; g.multi_count = multi_count;
@@ -1054,8 +1078,9 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-	int sms = 148, occ_big = 1, occ_multi = 1;
+	int sms = 148, occ_big = 1, occ_multi = 1, occ_small = 1;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_small, k_pass1_tile<CAP_FAST, false, false>, P1_TX, smem_small);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_big, k_pass1_tile<CAP_FAST, false, true>, P1_TX, smem_big);
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_multi, k_pass1_tile<CAP_FAST, true, true>, P1_TX, smem_multi);
 	Pass1Args a1;
@@ -1065,12 +1090,19 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 
 	auto pass1_band = [&](int b) {
 		const int y0 = b * BH, y1 = std::min(ny, y0 + BH);
+		// the tile lists and cursors are per band ([3] big count, [5] multi count, [6] [7] [10] cursors)
+		cudaMemsetAsync(ctx->d_ctr + 3, 0, sizeof(unsigned long long), sm);
+		cudaMemsetAsync(ctx->d_ctr + 5, 0, 3 * sizeof(unsigned long long), sm);
+		cudaMemsetAsync(ctx->d_ctr + 10, 0, sizeof(unsigned long long), sm);
+		ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
+		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
 		const unsigned int band_tiles = (unsigned int)tiles_x * (unsigned int)(y1 - y0);
 		g.tile0 = (unsigned int)tiles_x * (unsigned int)y0;
-		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.tiles_next = nullptr;
+		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.ntiles = band_tiles;
+		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 10);
 		g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
-		k_pass1_tile<CAP_FAST, false, false><<<band_tiles, P1_TX, smem_small, sm>>>(g);
-		ctx->launches++;
+		k_pass1_tile<CAP_FAST, false, false><<<std::min<unsigned int>(band_tiles, (unsigned int)(occ_small * sms)), P1_TX, smem_small, sm>>>(g);
+		ctx->launches += 2;
 		if (cmax_small < cmax) {
 			g.cmax = cmax; g.tiles = big_tiles.p; g.tiles_count = big_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
@@ -1120,9 +1152,9 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), sm);
 		Pass2Args a2;
 		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = B->y0; a2.y1 = B->y1;
-		a2.mid = m->slots; a2.flags = m->flags; a2.pool = m->pool; a2.st = B->sb.st; a2.redo = B->rb.rd;
+		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.st = B->sb.st; a2.redo = B->rb.rd;
 		a2.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
-		k_pass2<CAP_FAST><<<blocks_for(nlists, 128), 128, 0, sm>>>(a2);
+		k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(B->y1 - B->y0), P2_TX, 0, sm>>>(a2);
 		a2.wk = Work{B->rb.rd.list, 0ull, B->rb.rd.count, B->rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
 		k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
 		k_scan_reduce<<<nt, SCAN_THREADS, 0, sm>>>(B->sb.st.cnt, nlists, B->sums.p);
@@ -1540,6 +1572,7 @@ void vo_dmid_free(vo_ctx *ctx, vo_dmid *m)
 	dfree(ctx, m->slots);
 	dfree(ctx, m->pool);
 	dfree(ctx, m->flags);
+	dfree(ctx, m->tilemask);
 	delete m;
 }
 
