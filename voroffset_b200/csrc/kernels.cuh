@@ -301,20 +301,30 @@ __global__ void __launch_bounds__(P2_TX) k_pass2_rows(Pass2Args a)
 	if (x >= a.nx) return;
 	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
 	const size_t cc = (size_t)y * nx + x;
+	// windows of the candidate rows, four independent loads at a time (the masks are warp-uniform)
 	unsigned long long m_up = 0, m_dn = 0;
-	while (c_up) {
-		const int j = __ffsll((long long)c_up);
-		c_up &= c_up - 1;
-		m_up |= (unsigned long long)flag_has(__ldg(f_dn + cc - (size_t)j * nx), j) << (j - 1);
-	}
-	while (c_dn) {
-		const int j = __ffsll((long long)c_dn);
-		c_dn &= c_dn - 1;
-		m_dn |= (unsigned long long)flag_has(__ldg(f_up + cc + (size_t)j * nx), j) << (j - 1);
+	const uint16_t w_up = __ldg(f_up + cc), w_dn = __ldg(f_dn + cc);
+	while (c_up | c_dn) {
+		int jj[4];
+		const uint16_t *p[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			jj[i] = 0; p[i] = f_up + cc;
+			if (c_up) { const int j = __ffsll((long long)c_up); c_up &= c_up - 1; jj[i] = -j; p[i] = f_dn + cc - (size_t)j * nx; }
+			else if (c_dn) { const int j = __ffsll((long long)c_dn); c_dn &= c_dn - 1; jj[i] = j; p[i] = f_up + cc + (size_t)j * nx; }
+		}
+		uint16_t w[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) w[i] = __ldg(p[i]);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			if (jj[i] < 0) m_up |= (unsigned long long)flag_has(w[i], -jj[i]) << (-jj[i] - 1);
+			else if (jj[i] > 0) m_dn |= (unsigned long long)flag_has(w[i], jj[i]) << (jj[i] - 1);
+		}
 	}
 	double2 ulist[CAP];
 	RunUnion<CAP> u(ulist);
-	pass2_gather(a, u, x, y, m_up, m_dn, flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0));
+	pass2_gather(a, u, x, y, m_up, m_dn, flag_has(w_up, 0) || flag_has(w_dn, 0));
 	const unsigned long long c = (unsigned long long)(y - a.y0) * nx + x;
 	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);

@@ -184,15 +184,16 @@ __host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap)
 {
 	const size_t JP = (size_t)J + 1, SEG = (size_t)P1_TX + 2 * J;
 	size_t b = 0;
-	b += (size_t)cmax * sizeof(double2);                    // candidates
-	b += (size_t)cmax * sizeof(uint4);                      // their thresholds
+	b += 2 * (size_t)cmax * sizeof(double2);                // candidates (double-buffered: the next tile is staged
+	b += 2 * (size_t)cmax * sizeof(uint4);                  // their thresholds    while the current one is processed)
 	b += JP * pass1_jpp(J) * sizeof(double);                // Ht
 	b += ((JP * (JP + 1) + 3) & ~(size_t)3) * sizeof(float);// Ef
-	b += ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);       // segment offsets
+	b += 2 * ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);   // segment offsets (double-buffered)
 	b += (size_t)P1_TX * sizeof(uint32_t);                  // list lengths
-	b += 2 * (size_t)lcap * P1_TX * sizeof(uint32_t);       // survivor lists [s][thread]: candidate word, window word
-	b += ((size_t)cmax + 3) & ~(size_t)3;                   // segment column of each candidate
-	b += (JP + 1 + 3) & ~(size_t)3;                         // jmax
+	b += (size_t)lcap * P1_TX * sizeof(uint32_t);           // survivor lists [s][thread]
+	b += 2 * (((size_t)cmax + 15) & ~(size_t)15);           // segment column of each candidate (double-buffered)
+	b += (JP + 1 + 15) & ~(size_t)15;                       // jmax
+	b += 2 * sizeof(unsigned long long);                    // mbarriers of the two staging buffers
 	return b + 32;
 }
 
@@ -222,27 +223,69 @@ __device__ __forceinline__ uint32_t pair_windows(int tyu, int tyd, int jm1, int 
 
 // Shared-memory layout of the tile kernel (dynamic shared memory, see pass1_tile_smem).
 struct TileSmem {
-	double2 *cand;
-	uint4 *thr;
+	double2 *cand[2];
+	uint4 *thr[2];
 	double *Ht;
 	float *Ef;
-	uint32_t *off, *cnt, *listA, *listW;
-	uint8_t *ci, *jmax;
+	uint32_t *off[2], *cnt, *list;
+	uint8_t *ci[2], *jmax;
+	unsigned long long *mbar;      // [2]
 	__device__ __forceinline__ TileSmem(unsigned char *raw, int J, int cmax, int lcap)
 	{
 		const int JP = J + 1, SEG = P1_TX + 2 * J;
-		cand = reinterpret_cast<double2 *>(raw);
-		thr = reinterpret_cast<uint4 *>(cand + cmax);
-		Ht = reinterpret_cast<double *>(thr + cmax);
+		cand[0] = reinterpret_cast<double2 *>(raw);
+		cand[1] = cand[0] + cmax;
+		thr[0] = reinterpret_cast<uint4 *>(cand[1] + cmax);
+		thr[1] = thr[0] + cmax;
+		Ht = reinterpret_cast<double *>(thr[1] + cmax);
 		Ef = reinterpret_cast<float *>(Ht + (size_t)JP * pass1_jpp(J));
-		off = reinterpret_cast<uint32_t *>(Ef + ((JP * (JP + 1) + 3) & ~3));
-		cnt = off + ((SEG + 4) & ~3);
-		listA = cnt + P1_TX;
-		listW = listA + (size_t)lcap * P1_TX;
-		ci = reinterpret_cast<uint8_t *>(listW + (size_t)lcap * P1_TX);
-		jmax = ci + ((cmax + 3) & ~3);
+		off[0] = reinterpret_cast<uint32_t *>(Ef + ((JP * (JP + 1) + 3) & ~3));
+		off[1] = off[0] + ((SEG + 4) & ~3);
+		cnt = off[1] + ((SEG + 4) & ~3);
+		list = cnt + P1_TX;
+		ci[0] = reinterpret_cast<uint8_t *>(list + (size_t)lcap * P1_TX);
+		ci[1] = ci[0] + ((cmax + 15) & ~15);
+		jmax = ci[1] + ((cmax + 15) & ~15);
+		mbar = reinterpret_cast<unsigned long long *>(jmax + ((JP + 1 + 15) & ~15));
 	}
 };
+
+// ---- bulk asynchronous copies (TMA, 1D) global -> shared, completion on an mbarrier -----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned int count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra DONE_%=;\n"
+		"bra WAIT_%=;\n"
+		"DONE_%=:\n"
+		"}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// bytes: multiple of 16; src / dst 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Survivor list entry: k | lo_u << 11 | n_u << 17 | lo_d << 21 | n_d << 27 (candidate index, the two class windows
+// as start + length; lengths up to 15, longer windows are split over several entries).
+__device__ __forceinline__ uint32_t entry_windows(uint32_t e)        // -> lo_u | hi_u << 8 | lo_d << 16 | hi_d << 24
+{
+	const uint32_t lu = (e >> 11) & 63u, nu = (e >> 17) & 15u, ld = (e >> 21) & 63u, nd = (e >> 27) & 15u;
+	return lu | ((lu + nu) << 8) | (ld << 16) | ((ld + nd) << 24);
+}
 
 // The staged tile.
 template <int LCAP>
@@ -254,8 +297,20 @@ struct Tile {
 	const float *Ef;
 	const uint8_t *jmax;
 	uint32_t *cnt;             // [P1_TX] list lengths
-	uint32_t *listA, *listW;   // [s * P1_TX + xi]: k | d << 16, window word
+	uint32_t *list;            // [s * P1_TX + xi]
 	int J, JPP;
+
+	__device__ __forceinline__ void push(int xo, int k, uint32_t w) const
+	{
+		int lu = (int)(w & 0xffu), nu = (int)((w >> 8) & 0xffu) - lu, ld = (int)((w >> 16) & 0xffu), nd = (int)(w >> 24) - ld;
+		do {
+			const int cu = min(nu, 15), cd = min(nd, 15);
+			const uint32_t pos = atomicAdd(cnt + xo, 1u);
+			if (pos < (uint32_t)LCAP)
+				list[pos * P1_TX + xo] = (uint32_t)k | ((uint32_t)lu << 11) | ((uint32_t)cu << 17) | ((uint32_t)ld << 21) | ((uint32_t)cd << 27);
+			lu += cu; nu -= cu; ld += cd; nd -= cd;
+		} while (nu > 0 || nd > 0);
+	}
 
 	// Phase 1: candidate k appends itself to the lists of the output columns it survives for.
 	__device__ __forceinline__ void scatter(int k, int txe) const
@@ -290,9 +345,7 @@ struct Tile {
 				}
 				const uint32_t w = pair_windows(tyu, tyd, jm1, base, fu, fd);
 				if (w == 0) continue;
-				const int xo = (side ? i + d : i - d) - J;
-				const uint32_t pos = atomicAdd(cnt + xo, 1u);
-				if (pos < (uint32_t)LCAP) { listA[pos * P1_TX + xo] = (uint32_t)k | ((uint32_t)d << 16); listW[pos * P1_TX + xo] = w; }
+				push((side ? i + d : i - d) - J, k, w);
 			}
 		}
 	}
@@ -306,10 +359,11 @@ struct TileThread {
 	bool direct;
 
 	// direct mode (the list overflowed): candidate k of the range re-tested for this output
-	__device__ __forceinline__ bool pair_direct(int k, uint32_t &e, uint32_t &w) const
+	__device__ __forceinline__ bool pair_direct(int k, int &d, uint32_t &w) const
 	{
 		const uint4 th = t.thr[k];
-		const int i = (int)t.ci[k], d = abs(i - ix);
+		const int i = (int)t.ci[k];
+		d = abs(i - ix);
 		const bool left = ix < i;
 		const int tn = left ? (int)(th.x & 0xffu) : (int)((th.x >> 8) & 0xffu);
 		if (d >= 1 && d >= tn) return false;
@@ -321,16 +375,22 @@ struct TileThread {
 		const float *row = t.Ef + (size_t)d * (t.J + 2);
 		const int fu = first_gt(row, t.J + 1, __uint_as_float(th.z)) - 1, fd = first_gt(row, t.J + 1, __uint_as_float(th.w)) - 1;
 		w = pair_windows(tyu, tyd, jm1, base, fu, fd);
-		e = (uint32_t)k | ((uint32_t)d << 16);
 		return w != 0;
 	}
-	// s-th entry of the survivor loop: candidate word (k | d << 16) and window word
-	__device__ __forceinline__ bool survivor(int s, uint32_t &e, uint32_t &w) const
+	// s-th entry of the survivor loop: candidate k, its distance d and its window word
+	__device__ __forceinline__ bool survivor(int s, int &k, int &d, uint32_t &w) const
 	{
-		if (!direct) { e = t.listA[s * P1_TX + xi]; w = t.listW[s * P1_TX + xi]; return true; }
-		return pair_direct(kb + s, e, w);
+		if (!direct) {
+			const uint32_t e = t.list[s * P1_TX + xi];
+			k = (int)(e & 2047u);
+			d = abs((int)t.ci[k] - ix);
+			w = entry_windows(e);
+			return true;
+		}
+		k = kb + s;
+		return pair_direct(k, d, w);
 	}
-	__device__ __forceinline__ int layer(uint32_t e) const { return (int)((t.thr[e & 0xffffu].y >> 16) & 3u); }
+	__device__ __forceinline__ int layer(int k) const { return (int)((t.thr[k].y >> 16) & 3u); }
 };
 
 // bits q in [0, CB) with l <= cb + q < h
@@ -361,11 +421,12 @@ __device__ __noinline__ double2 class_general(const Pass1TileArgs &a, const Tile
 	double2 ulist[CAP];
 	RunUnion<CAP> u(ulist);
 	for (int s = 0; s < t.niter; ++s) {
-		uint32_t e, w;
-		if (!t.survivor(s, e, w)) continue;
+		int k, d;
+		uint32_t w;
+		if (!t.survivor(s, k, d, w)) continue;
 		if (window_mask<1>(w, j)) {
-			const double2 ab = t.t.cand[e & 0xffffu];
-			const double hh = t.t.Ht[(size_t)((e >> 16) & 0xffu) * t.t.JPP + j];
+			const double2 ab = t.t.cand[k];
+			const double hh = t.t.Ht[(size_t)d * t.t.JPP + j];
 			u.insert(ab.x - hh, ab.y + hh);
 		}
 	}
@@ -397,11 +458,11 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 	}
 	unsigned int complex_mask = 0;
 	for (int s = 0; s < t.niter; ++s) {
-		uint32_t e, w;
-		if (!t.survivor(s, e, w)) continue;
+		int k, d;
+		uint32_t w;
+		if (!t.survivor(s, k, d, w)) continue;
 		const unsigned int valid = window_mask<CB>(w, cb);
 		if (!valid) continue;
-		const int k = (int)(e & 0xffffu), d = (int)((e >> 16) & 0xffu);
 		const double2 ab = t.t.cand[k];
 		const double *hp = t.t.Ht + (size_t)d * t.t.JPP + cb;
 		double h[CB];
@@ -409,7 +470,7 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 		for (int q = 0; q < CB; ++q) h[q] = hp[q];
 		// branch-free: a class that does not take this survivor gets the cap -inf, i.e. the candidate
 		// (+inf, -inf), which leaves its hull untouched
-		const int lay = NL == 1 ? 0 : min(t.layer(e), NL - 1);
+		const int lay = NL == 1 ? 0 : min(t.layer(k), NL - 1);
 #pragma unroll
 		for (int l = 0; l < NL; ++l) {
 			if (NL == 1 || lay == l) {
@@ -484,94 +545,47 @@ __device__ __forceinline__ void eval_classes(const Pass1TileArgs &a, const TileT
 	}
 }
 
+// What a tile turns out to be once its segment offsets are known (uniform over the CTA).
+enum TileKind { TK_NORMAL = 0, TK_EMPTY, TK_MULTI, TK_BIG, TK_REDO };
+
+struct TileHead {
+	unsigned int tile;
+	int y, x0, txe, ncand, kind;
+	uint32_t base;
+};
+
+// Phase 2 of a staged tile: thread per output column (all threads of the CTA enter; `active` = owns a column).
 template <int CAP, bool MULTI, int LCAP>
-__device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const unsigned int tile, unsigned char *smem_raw)
+__device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHead &h, const Tile<LCAP> &tl, const uint32_t *s_off)
 {
-	const int J = a.J, JP = J + 1, JPP = pass1_jpp(J), TX = P1_TX, SEG = TX + 2 * J;
-	const TileSmem sm(smem_raw, J, a.cmax, LCAP);
-	double2 *s_cand = sm.cand;
-	uint4 *s_thr = sm.thr;
-	uint32_t *s_off = sm.off, *s_cnt = sm.cnt;
-	uint8_t *s_ci = sm.ci;
-
-	const int tid = threadIdx.x, nthr = blockDim.x;
-	const int y = (int)(tile / (unsigned)a.tiles_x);
-	const int x0 = (int)(tile % (unsigned)a.tiles_x) * TX;
-	const int txe = min(TX, a.nx - x0);
-	const size_t rowbase = (size_t)y * a.nx, ncols_all = (size_t)a.nx * a.ny;
-	const uint16_t full = (uint16_t)(JP << 8);             // window [0, J+1)
-
-	// ---- phase 0: stage the row segment -------------------------------------------------------
-	bool multi = false;                                     // does a column of the segment hold several intervals?
-	for (int i = tid; i <= SEG; i += nthr) {
-		const int gx = min(max(x0 - J + i, 0), a.nx);      // columns outside the grid collapse to empty ranges
-		const uint32_t o = __ldg(a.off + rowbase + gx);
-		s_off[i] = o;
-		if (!MULTI && i < SEG) multi |= __ldg(a.off + rowbase + min(max(x0 - J + i + 1, 0), a.nx)) - o > 1u;
-	}
-	if (__syncthreads_or(multi)) {                          // (never taken by the MULTI variant)
-		if (tid == 0) a.multi_tiles[atomicAdd(a.multi_count, 1u)] = tile;   // -> two-hull variant, launch 3
-		return;
-	}
-	const uint32_t base = s_off[0];
-	const int ncand = (int)(s_off[SEG] - base);
-	if (ncand > a.cmax) {
-		if (a.big_tiles) {                                  // run again with a larger candidate buffer
-			if (tid == 0) a.big_tiles[atomicAdd(a.big_count, 1u)] = tile;
-			return;
-		}
-		// no larger buffer: leave every slot of the tile to k_pass1
-		if (tid < txe) { a.flags[rowbase + x0 + tid] = full; a.flags[ncols_all + rowbase + x0 + tid] = full; }
-		if (tid == 0) { a.tilemask[tile] = ~0ull; a.tilemask[(size_t)a.tiles_x * a.ny + tile] = ~0ull; }
-		for (int idx = tid; idx < JP * txe; idx += nthr) {
-			const int j = idx / txe, xi = idx % txe;
-			redo_push(a.redo, ((unsigned long long)y * JP + j) * a.nx + x0 + xi);
-		}
-		return;
-	}
-	if (ncand == 0) {                                       // nothing in reach: no slot of the tile is needed
-		if (tid < txe) { a.flags[rowbase + x0 + tid] = 0; a.flags[ncols_all + rowbase + x0 + tid] = 0; }
-		return;
-	}
-	for (int k = tid; k < ncand; k += nthr) { s_cand[k] = __ldg(a.spans + base + k); s_thr[k] = __ldg(a.thr + base + k); }
-	for (int i = tid; i < SEG; i += nthr)
-		for (uint32_t k = s_off[i] - base; k < s_off[i + 1] - base; ++k) s_ci[k] = (uint8_t)i;
-	if (tid < TX) s_cnt[tid] = 0;
-	__syncthreads();
-
-	Tile<LCAP> tl;
-	tl.cand = s_cand; tl.thr = s_thr; tl.ci = s_ci; tl.Ht = sm.Ht; tl.Ef = sm.Ef; tl.jmax = sm.jmax;
-	tl.cnt = s_cnt; tl.listA = sm.listA; tl.listW = sm.listW; tl.J = J; tl.JPP = JPP;
-
-	// ---- phase 1: thread per candidate, surviving pairs appended to the output lists --------------------
-	for (int k = tid; k < ncand; k += nthr) tl.scatter(k, txe);
-	__syncthreads();
-
-	// ---- phase 2: one thread per output column ------------------------------------------------------
-	const bool active = tid < txe;
+	const int J = a.J, tid = threadIdx.x;
+	const size_t rowbase = (size_t)h.y * a.nx, ncols_all = (size_t)a.nx * a.ny;
+	const bool active = tid < h.txe;
 	const int xi = tid, ix = xi + J;
 	TileThread<LCAP> t;
-	t.t = tl; t.xi = xi; t.ix = ix; t.y = y; t.x0 = x0;
+	t.t = tl; t.xi = xi; t.ix = ix; t.y = h.y; t.x0 = h.x0;
 	int UL = 255, UH = 0, DL = 255, DH = 0;
 	int maxlayer = 0;
 	if (active) {
-		t.kb = (int)(s_off[ix - J] - base);
-		const int S = (int)s_cnt[xi];
+		t.kb = (int)(s_off[ix - J] - h.base);
+		const int S = (int)tl.cnt[xi];
 		// more survivors than the list holds (steep walls, many layers): re-scan the candidate range instead
 		t.direct = S > LCAP;
-		t.niter = t.direct ? (int)(s_off[ix + J + 1] - base) - t.kb : S;
+		t.niter = t.direct ? (int)(s_off[ix + J + 1] - h.base) - t.kb : S;
 		for (int s = 0; s < t.niter; ++s) {
-			uint32_t e, w;
-			if (!t.survivor(s, e, w)) continue;
-			if (MULTI) maxlayer = max(maxlayer, t.layer(e));
+			int k, d;
+			uint32_t w;
+			if (!t.survivor(s, k, d, w)) continue;
+			if (MULTI) maxlayer = max(maxlayer, t.layer(k));
 			const int lu = (int)(w & 0xffu), hu = (int)((w >> 8) & 0xffu), ld = (int)((w >> 16) & 0xffu), hd = (int)(w >> 24);
 			if (hu > lu) { UL = min(UL, lu); UH = max(UH, hu); }
 			if (hd > ld) { DL = min(DL, ld); DH = max(DH, hd); }
 		}
 		if (UH == 0) UL = 0;
 		if (DH == 0) DL = 0;
-		a.flags[rowbase + x0 + xi] = (uint16_t)(UL | (UH << 8));
-		a.flags[ncols_all + rowbase + x0 + xi] = (uint16_t)(DL | (DH << 8));
+		a.flags[rowbase + h.x0 + xi] = (uint16_t)(UL | (UH << 8));
+		a.flags[ncols_all + rowbase + h.x0 + xi] = (uint16_t)(DL | (DH << 8));
+		tl.cnt[xi] = 0;                                    // ready for the next tile
 	} else { UL = UH = DL = DH = 0; }
 	// OR of the windows over the tile: pass 2 skips a producer row whose tile lacks the class
 	{
@@ -580,8 +594,8 @@ __device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const un
 		const unsigned int md0 = __reduce_or_sync(0xffffffffu, (unsigned int)md), md1 = __reduce_or_sync(0xffffffffu, (unsigned int)(md >> 32));
 		if ((tid & 31) == 0) {
 			const size_t ntl = (size_t)a.tiles_x * a.ny;
-			if (mu0 | mu1) atomicOr(a.tilemask + tile, (unsigned long long)mu0 | ((unsigned long long)mu1 << 32));
-			if (md0 | md1) atomicOr(a.tilemask + ntl + tile, (unsigned long long)md0 | ((unsigned long long)md1 << 32));
+			if (mu0 | mu1) atomicOr(a.tilemask + h.tile, (unsigned long long)mu0 | ((unsigned long long)mu1 << 32));
+			if (md0 | md1) atomicOr(a.tilemask + ntl + h.tile, (unsigned long long)md0 | ((unsigned long long)md1 << 32));
 		}
 	}
 	if (!active || (UH == 0 && DH == 0)) return;
@@ -589,31 +603,155 @@ __device__ __forceinline__ void pass1_tile_body(const Pass1TileArgs &a, const un
 	else eval_classes<P1_CB, 2, CAP, LCAP>(a, t, UL, UH, DL, DH);                           // two hulls per class
 }
 
+// Tiles that are not processed here: empty ones, ones for another launch, ones left to k_pass1.
+template <bool MULTI>
+__device__ __forceinline__ void tile_other(const Pass1TileArgs &a, const TileHead &h)
+{
+	const int tid = threadIdx.x, nthr = blockDim.x, JP = a.J + 1;
+	const size_t rowbase = (size_t)h.y * a.nx, ncols_all = (size_t)a.nx * a.ny;
+	if (h.kind == TK_EMPTY) {                               // nothing in reach: no slot of the tile is needed
+		if (tid < h.txe) { a.flags[rowbase + h.x0 + tid] = 0; a.flags[ncols_all + rowbase + h.x0 + tid] = 0; }
+	} else if (h.kind == TK_MULTI) {                        // -> two-hull variant, launch 3
+		if (tid == 0) a.multi_tiles[atomicAdd(a.multi_count, 1u)] = h.tile;
+	} else if (h.kind == TK_BIG) {                          // -> launch 2, larger candidate buffer
+		if (tid == 0) a.big_tiles[atomicAdd(a.big_count, 1u)] = h.tile;
+	} else {                                                // TK_REDO: leave every slot of the tile to k_pass1
+		const uint16_t full = (uint16_t)(JP << 8);         // window [0, J+1)
+		if (tid < h.txe) { a.flags[rowbase + h.x0 + tid] = full; a.flags[ncols_all + rowbase + h.x0 + tid] = full; }
+		if (tid == 0) { a.tilemask[h.tile] = ~0ull; a.tilemask[(size_t)a.tiles_x * a.ny + h.tile] = ~0ull; }
+		for (int idx = tid; idx < JP * h.txe; idx += nthr) {
+			const int j = idx / h.txe, xi = idx % h.txe;
+			redo_push(a.redo, ((unsigned long long)h.y * JP + j) * a.nx + h.x0 + xi);
+		}
+	}
+}
+
 // One resident wave of CTAs; every CTA stages the tables once and then pulls tiles with an atomic counter.
 // LIST = false: the tiles [tile0, tile0 + ntiles). LIST = true: the tiles of a list collected by an earlier
 // launch (its length is only known on the device).
+// Software pipeline over the tiles of a CTA (global latency is what bounds a tile otherwise):
+//   - the position of the tile after next is fetched (atomicAdd) while the current tile is processed;
+//   - the segment offsets of the NEXT tile are loaded into registers before phase 1 of the current tile and
+//     published to shared memory at the barrier that ends phase 1;
+//   - right after that barrier one thread starts the bulk copies (TMA, cp.async.bulk) of the next tile's
+//     candidates and thresholds into the other staging buffer; they land during phase 2 of the current tile
+//     and are awaited (mbarrier) at the top of the next iteration.
 template <int CAP, bool MULTI, bool LIST>
 __global__ void __launch_bounds__(P1_TX, MULTI ? 4 : 5) k_pass1_tile(Pass1TileArgs a)
 {
 	constexpr int LCAP = (MULTI || LIST) ? P1_LCAP_M : P1_LCAP_S;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	__shared__ unsigned int s_next;
+	__shared__ unsigned int s_pos[2];
 	const unsigned int n = LIST ? *a.tiles_count : a.ntiles;
 	if (n == 0) return;
-	{
-		const int JP = a.J + 1;
-		const TileSmem sm(smem_raw, a.J, a.cmax, LCAP);
-		for (int i = threadIdx.x; i < JP * pass1_jpp(a.J); i += blockDim.x) sm.Ht[i] = __ldg(a.Ht + i);
-		for (int i = threadIdx.x; i < JP * (JP + 1); i += blockDim.x) sm.Ef[i] = __ldg(a.Ef + i);
-		for (int i = threadIdx.x; i < JP + 1; i += blockDim.x) sm.jmax[i] = __ldg(a.jmax + i);
+	const int J = a.J, JP = J + 1, SEG = P1_TX + 2 * J, tid = threadIdx.x, nthr = blockDim.x;
+	const TileSmem sm(smem_raw, J, a.cmax, LCAP);
+	for (int i = tid; i < JP * pass1_jpp(J); i += nthr) sm.Ht[i] = __ldg(a.Ht + i);
+	for (int i = tid; i < JP * (JP + 1); i += nthr) sm.Ef[i] = __ldg(a.Ef + i);
+	for (int i = tid; i < JP + 1; i += nthr) sm.jmax[i] = __ldg(a.jmax + i);
+	if (tid < P1_TX) sm.cnt[tid] = 0;
+	if (tid == 0) {
+		mbar_init(sm.mbar + 0, 1); mbar_init(sm.mbar + 1, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		s_pos[0] = atomicAdd(a.tiles_next, 1u);
+		s_pos[1] = atomicAdd(a.tiles_next, 1u);
 	}
-	for (;;) {
-		if (threadIdx.x == 0) s_next = atomicAdd(a.tiles_next, 1u);
-		__syncthreads();                                    // (also publishes the tables before the first tile)
-		const unsigned int i = s_next;
-		if (i >= n) break;
-		pass1_tile_body<CAP, MULTI, LCAP>(a, LIST ? a.tiles[i] : a.tile0 + i, smem_raw);
-		__syncthreads();                                    // the next tile reuses the shared buffers (and s_next)
+	__syncthreads();
+
+	Tile<LCAP> tl;
+	tl.Ht = sm.Ht; tl.Ef = sm.Ef; tl.jmax = sm.jmax; tl.cnt = sm.cnt; tl.list = sm.list; tl.J = J; tl.JPP = pass1_jpp(J);
+
+	// segment offsets of the tile at list position `pos` -> registers (two entries per thread; o[r][1] = the next
+	// column's offset, for the multi-interval test)
+	auto load_offsets = [&](unsigned int pos, uint32_t (&o)[2][2], TileHead &h) {
+		h.tile = LIST ? a.tiles[pos] : a.tile0 + pos;
+		h.y = (int)(h.tile / (unsigned)a.tiles_x);
+		h.x0 = (int)(h.tile % (unsigned)a.tiles_x) * P1_TX;
+		h.txe = min(P1_TX, a.nx - h.x0);
+		const size_t rowbase = (size_t)h.y * a.nx;
+#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const int i = tid + r * P1_TX;
+			o[r][0] = o[r][1] = 0;
+			if (i <= SEG) {
+				o[r][0] = __ldg(a.off + rowbase + min(max(h.x0 - J + i, 0), a.nx));   // columns outside the grid collapse to empty ranges
+				if (!MULTI && i < SEG) o[r][1] = __ldg(a.off + rowbase + min(max(h.x0 - J + i + 1, 0), a.nx));
+			}
+		}
+	};
+	// registers -> shared memory; returns this thread's "a column of the segment holds several intervals"
+	auto store_offsets = [&](const uint32_t (&o)[2][2], uint32_t *s_off) -> bool {
+		bool multi = false;
+#pragma unroll
+		for (int r = 0; r < 2; ++r) {
+			const int i = tid + r * P1_TX;
+			if (i <= SEG) { s_off[i] = o[r][0]; if (!MULTI && i < SEG) multi |= o[r][1] - o[r][0] > 1u; }
+		}
+		return multi;
+	};
+	auto classify = [&](TileHead &h, const uint32_t *s_off, bool multi) {
+		h.base = s_off[0];
+		h.ncand = (int)(s_off[SEG] - h.base);
+		h.kind = multi ? TK_MULTI : h.ncand > a.cmax ? (a.big_tiles ? TK_BIG : TK_REDO) : h.ncand == 0 ? TK_EMPTY : TK_NORMAL;
+	};
+	// start the staging of a NORMAL tile into buffer b: bulk copies by one thread, the column map by all
+	auto stage = [&](const TileHead &h, int b) {
+		if (tid == 0) {
+			const unsigned int bytes = (unsigned int)h.ncand * 16u;
+			mbar_expect_tx(sm.mbar + b, 2u * bytes);
+			bulk_g2s(sm.cand[b], a.spans + h.base, bytes, sm.mbar + b);
+			bulk_g2s(sm.thr[b], a.thr + h.base, bytes, sm.mbar + b);
+		}
+		const uint32_t *s_off = sm.off[b];
+		for (int i = tid; i < SEG; i += nthr)
+			for (uint32_t k = s_off[i] - h.base; k < s_off[i + 1] - h.base; ++k) sm.ci[b][k] = (uint8_t)i;
+	};
+
+	// prologue: the first tile is loaded synchronously
+	unsigned int pos = s_pos[0];
+	if (pos >= n) return;
+	TileHead cur, nxt;
+	uint32_t o[2][2];
+	int buf = 0;
+	unsigned int phase[2] = {0u, 0u};
+	load_offsets(pos, o, cur);
+	{
+		const bool m = store_offsets(o, sm.off[0]);
+		const bool multi = __syncthreads_or(m);
+		classify(cur, sm.off[0], multi);
+		if (cur.kind == TK_NORMAL) stage(cur, 0);
+	}
+	__syncthreads();
+
+	for (unsigned int it = 0;; ++it) {
+		const unsigned int npos = s_pos[(it + 1) & 1];      // position of the next tile
+		const bool have_next = npos < n;
+		if (tid == 0) s_pos[it & 1] = atomicAdd(a.tiles_next, 1u);    // the one after it (read two barriers from now)
+		if (have_next) load_offsets(npos, o, nxt);
+
+		// ---- current tile, phase 1 ----
+		if (cur.kind == TK_NORMAL) {
+			mbar_wait(sm.mbar + buf, phase[buf]);            // candidates and thresholds have landed
+			phase[buf] ^= 1u;
+			tl.cand = sm.cand[buf]; tl.thr = sm.thr[buf]; tl.ci = sm.ci[buf];
+			for (int k = tid; k < cur.ncand; k += nthr) tl.scatter(k, cur.txe);
+		} else tile_other<MULTI>(a, cur);
+
+		// ---- publish the next tile's offsets, start its staging ----
+		bool m = false;
+		if (have_next) m = store_offsets(o, sm.off[buf ^ 1]);
+		const bool nmulti = __syncthreads_or(m);             // (also: phase 1 of the current tile is complete)
+		if (have_next) {
+			classify(nxt, sm.off[buf ^ 1], nmulti);
+			if (nxt.kind == TK_NORMAL) stage(nxt, buf ^ 1);
+		}
+
+		// ---- current tile, phase 2 ----
+		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP>(a, cur, tl, sm.off[buf]);
+		__syncthreads();                                    // lists, counters and the staging buffer are free again
+		if (!have_next) break;
+		cur = nxt;
+		buf ^= 1;
 	}
 }
 
