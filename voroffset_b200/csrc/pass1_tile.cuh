@@ -36,8 +36,8 @@
 // Kernel structure:
 //   k_thresh      thread per input column: the four nn values of each of its intervals -> near / far thresholds,
 //                 16 bytes per interval (tile independent, so halo candidates are not recomputed per tile);
-//   k_pass1_tile  persistent CTAs (one resident wave) pull row segments of P1_TX output columns; the cap tables
-//                 are staged in shared memory once per CTA. Per tile:
+//   k_pass1_tile  one CTA per SM, cap tables staged in shared memory once; every warp pulls tiles (row segments of
+//                 P1_W = 32 output columns) on its own, without CTA barriers. Per tile:
 //     phase 0  the segment [x0-J, x0+TX+J) of row y is staged as a flat candidate array (interval + thresholds);
 //     phase 1  thread per candidate: walks the output columns it survives for, computes the class windows of
 //              each surviving pair (the far test in y depends on the distance) and appends the pair to that
@@ -55,10 +55,12 @@
 
 namespace vo {
 
-constexpr int P1_TX = 128;      // output columns (= threads) per CTA
+constexpr int P1_W = 32;        // output columns of a tile = lanes of the warp that owns it
+constexpr int P1_TX = 128;      // columns per tile mask (the unit pass 2 skips producer rows by)
 constexpr int P1_CB = 4;        // classes evaluated together in registers
-constexpr int P1_LCAP_S = 32;   // survivors listed per output column, single-interval launch
-constexpr int P1_LCAP_M = 32;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
+constexpr int P1_LCAP_S = 24;   // survivors listed per output column, single-interval launch
+constexpr int P1_LCAP_M = 64;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
+constexpr int P1_MAXWARPS = 16; // warps per CTA (one CTA per SM; fewer when the per-warp buffers are large)
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
 {
@@ -76,12 +78,32 @@ __device__ __forceinline__ int first_gt(const float *tab, int last, float v)
 	return lo;
 }
 
-// nn(p, column): min over the intervals q of the column of max(a_q - a_p, b_p - b_q)
-__device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint32_t q0, uint32_t q1)
+// nn(p, column): min over the intervals q of the column of max(a_q - a_p, b_p - b_q).
+// Clipped form (erosion: the dilated complement is only read inside (clo, chi), Voronoi.cpp:57-89 drops the rest):
+// an endpoint at or beyond the clip bound is SATURATED - whatever cap it gets, it stays outside the range - so
+// on that side a saturated q contains everything and nothing unsaturated contains a saturated p. Without this
+// the complement's intervals, which all share the endpoint zmin-1 or zmax+1, could never dominate each other
+// from farther away (the closer one always reaches lower), and every candidate up to the tangent point survived.
+__device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint32_t q0, uint32_t q1, double clo, double chi)
 {
-	double r = __longlong_as_double(0x7FF0000000000000LL);
-	for (uint32_t k = q0; k < q1; ++k) { const double2 v = __ldg(q + k); r = fmin(r, fmax(v.x - p.x, p.y - v.y)); }
+	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	const bool plo = p.x <= clo, phi = p.y >= chi;
+	double r = inf;
+	for (uint32_t k = q0; k < q1; ++k) {
+		const double2 v = __ldg(q + k);
+		const double ta = v.x <= clo ? -inf : (plo ? inf : v.x - p.x);
+		const double tb = v.y >= chi ? -inf : (phi ? inf : p.y - v.y);
+		r = fmin(r, fmax(ta, tb));
+	}
 	return r;
+}
+
+// margin by which the farther neighbour contains p (rounded down; finite, so that the +inf sentinels of the far
+// tables always stop a search; -inf: never dominated from farther away)
+__device__ __forceinline__ float far_value(double nn, double m, bool never)
+{
+	if (never) return __int_as_float(0xff800000);
+	return fminf(__double2float_rd(-nn - m), 3.0e38f);
 }
 
 // ---- dominance thresholds, one thread per input column ------------------------------------------------
@@ -103,6 +125,7 @@ struct ThreshArgs {
 	const int *reach;       // J+1
 	uint4 *thr;             // per interval
 	unsigned long long c_begin, c_end;   // columns processed by this launch (a band of rows, or everything)
+	double clip_lo, clip_hi;             // the result is only read inside (clip_lo, clip_hi); -inf / +inf: everywhere
 };
 
 __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
@@ -125,30 +148,35 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	for (uint32_t k = o0; k < o1; ++k) {
 		const double2 p = __ldg(a.spans + k);
 		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
-		const double nnL = nn_of(p, a.spans, l0, l1), nnR = nn_of(p, a.spans, r0, r1);
-		const double nnU = nn_of(p, a.spans, u0, u1), nnD = nn_of(p, a.spans, d0, d1);
+		const double nnL = nn_of(p, a.spans, l0, l1, a.clip_lo, a.clip_hi), nnR = nn_of(p, a.spans, r0, r1, a.clip_lo, a.clip_hi);
+		const double nnU = nn_of(p, a.spans, u0, u1, a.clip_lo, a.clip_hi), nnD = nn_of(p, a.spans, d0, d1, a.clip_lo, a.clip_hi);
+		// an interval saturated on both sides covers the whole range: it yields to a CLOSER one of its kind (near
+		// tests) but never to a farther one - otherwise two of them could drop each other
+		const bool whole = p.x <= a.clip_lo && p.y >= a.clip_hi;
 		const int tnL = first_ge(s_D, J, nnL + m), tnR = first_ge(s_D, J, nnR + m);
 		const int tyu = first_ge(s_E, J, nnU + m), tyd = first_ge(s_E, J, nnD + m);
 		const int T = max(tyu, tyd);
 		int tfL = 1, tfR = 1;
 		if (J >= 1) {
 			const float *g = a.G + (size_t)(T - 1) * JP;
-			tfL = first_gt(g, J, __double2float_rd(-nnR - m));     // outputs on the left: the right neighbour is farther
-			tfR = first_gt(g, J, __double2float_rd(-nnL - m));
+			tfL = first_gt(g, J, far_value(nnR, m, whole));         // outputs on the left: the right neighbour is farther
+			tfR = first_gt(g, J, far_value(nnL, m, whole));
 		}
 		const uint32_t layer = min(k - o0, 3u);
 		uint4 t;
 		t.x = (uint32_t)tnL | ((uint32_t)tnR << 8) | ((uint32_t)tfL << 16) | ((uint32_t)tfR << 24);
 		t.y = (uint32_t)(tyu - 1) | ((uint32_t)(tyd - 1) << 8) | (layer << 16) | ((uint32_t)__ldg(a.reach + T - 1) << 24);
-		t.z = __float_as_uint(__double2float_rd(-nnD - m));        // consumers above: row y+1 is farther
-		t.w = __float_as_uint(__double2float_rd(-nnU - m));
+		t.z = __float_as_uint(far_value(nnD, m, whole));            // consumers above: row y+1 is farther
+		t.w = __float_as_uint(far_value(nnU, m, whole));
 		a.thr[k] = t;
 	}
 }
 
 // ---- pass 1 ------------------------------------------------------------------------------------------
 struct Pass1TileArgs {
-	int nx, ny, J, cmax, tiles_x;
+	int nx, ny, J, cmax;
+	int tiles_xw;           // tiles (P1_W columns) per row
+	int tiles_x;            // tile masks (P1_TX columns) per row
 	unsigned int tile0, ntiles;         // tiles [tile0, tile0 + ntiles) when `tiles` is NULL
 	const uint32_t *off;
 	const double2 *spans;
@@ -180,21 +208,31 @@ struct Pass1TileArgs {
 
 __host__ __device__ inline int pass1_jpp(int J) { return (J + 1 + P1_CB + 1) & ~1; }
 
-__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap)
+// dynamic shared memory: the cap tables once per CTA, then one staging area per warp
+__host__ __device__ inline size_t pass1_table_smem(int J)
 {
-	const size_t JP = (size_t)J + 1, SEG = (size_t)P1_TX + 2 * J;
+	const size_t JP = (size_t)J + 1;
+	size_t b = JP * pass1_jpp(J) * sizeof(double);          // Ht
+	b += ((JP * (JP + 1) + 3) & ~(size_t)3) * sizeof(float);// Ef
+	b += (JP + 1 + 15) & ~(size_t)15;                       // jmax
+	return b;
+}
+__host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap)
+{
+	const size_t SEG = (size_t)P1_W + 2 * J;
 	size_t b = 0;
 	b += 2 * (size_t)cmax * sizeof(double2);                // candidates (double-buffered: the next tile is staged
 	b += 2 * (size_t)cmax * sizeof(uint4);                  // their thresholds    while the current one is processed)
-	b += JP * pass1_jpp(J) * sizeof(double);                // Ht
-	b += ((JP * (JP + 1) + 3) & ~(size_t)3) * sizeof(float);// Ef
 	b += 2 * ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);   // segment offsets (double-buffered)
-	b += (size_t)P1_TX * sizeof(uint32_t);                  // list lengths
-	b += (size_t)lcap * P1_TX * sizeof(uint32_t);           // survivor lists [s][thread]
+	b += (size_t)P1_W * sizeof(uint32_t);                   // list lengths
+	b += (size_t)lcap * P1_W * sizeof(uint32_t);            // survivor lists [s][lane]
 	b += 2 * (((size_t)cmax + 15) & ~(size_t)15);           // segment column of each candidate (double-buffered)
-	b += (JP + 1 + 15) & ~(size_t)15;                       // jmax
 	b += 2 * sizeof(unsigned long long);                    // mbarriers of the two staging buffers
-	return b + 32;
+	return b;
+}
+__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap, int nwarps)
+{
+	return pass1_table_smem(J) + (size_t)nwarps * pass1_warp_smem(J, cmax, lcap) + 32;
 }
 
 // Pool space for `n` entries, one atomic per converged group of threads instead of one per thread.
@@ -221,32 +259,39 @@ __device__ __forceinline__ uint32_t pair_windows(int tyu, int tyd, int jm1, int 
 	return (uint32_t)lu | ((uint32_t)hu << 8) | ((uint32_t)ld << 16) | ((uint32_t)hd << 24);
 }
 
-// Shared-memory layout of the tile kernel (dynamic shared memory, see pass1_tile_smem).
-struct TileSmem {
-	double2 *cand[2];
-	uint4 *thr[2];
+// Shared-memory layout of the tile kernel (see pass1_tile_smem).
+struct TableSmem {
 	double *Ht;
 	float *Ef;
-	uint32_t *off[2], *cnt, *list;
-	uint8_t *ci[2], *jmax;
-	unsigned long long *mbar;      // [2]
-	__device__ __forceinline__ TileSmem(unsigned char *raw, int J, int cmax, int lcap)
+	uint8_t *jmax;
+	__device__ __forceinline__ TableSmem(unsigned char *raw, int J)
 	{
-		const int JP = J + 1, SEG = P1_TX + 2 * J;
+		const int JP = J + 1;
+		Ht = reinterpret_cast<double *>(raw);
+		Ef = reinterpret_cast<float *>(Ht + (size_t)JP * pass1_jpp(J));
+		jmax = reinterpret_cast<uint8_t *>(Ef + ((JP * (JP + 1) + 3) & ~3));
+	}
+};
+struct WarpSmem {
+	double2 *cand[2];
+	uint4 *thr[2];
+	uint32_t *off[2], *cnt, *list;
+	uint8_t *ci[2];
+	unsigned long long *mbar;      // [2]
+	__device__ __forceinline__ WarpSmem(unsigned char *raw, int J, int cmax, int lcap)
+	{
+		const int SEG = P1_W + 2 * J;
 		cand[0] = reinterpret_cast<double2 *>(raw);
 		cand[1] = cand[0] + cmax;
 		thr[0] = reinterpret_cast<uint4 *>(cand[1] + cmax);
 		thr[1] = thr[0] + cmax;
-		Ht = reinterpret_cast<double *>(thr[1] + cmax);
-		Ef = reinterpret_cast<float *>(Ht + (size_t)JP * pass1_jpp(J));
-		off[0] = reinterpret_cast<uint32_t *>(Ef + ((JP * (JP + 1) + 3) & ~3));
+		off[0] = reinterpret_cast<uint32_t *>(thr[1] + cmax);
 		off[1] = off[0] + ((SEG + 4) & ~3);
 		cnt = off[1] + ((SEG + 4) & ~3);
-		list = cnt + P1_TX;
-		ci[0] = reinterpret_cast<uint8_t *>(list + (size_t)lcap * P1_TX);
+		list = cnt + P1_W;
+		ci[0] = reinterpret_cast<uint8_t *>(list + (size_t)lcap * P1_W);
 		ci[1] = ci[0] + ((cmax + 15) & ~15);
-		jmax = ci[1] + ((cmax + 15) & ~15);
-		mbar = reinterpret_cast<unsigned long long *>(jmax + ((JP + 1 + 15) & ~15));
+		mbar = reinterpret_cast<unsigned long long *>(ci[1] + ((cmax + 15) & ~15));
 	}
 };
 
@@ -296,8 +341,8 @@ struct Tile {
 	const double *Ht;
 	const float *Ef;
 	const uint8_t *jmax;
-	uint32_t *cnt;             // [P1_TX] list lengths
-	uint32_t *list;            // [s * P1_TX + xi]
+	uint32_t *cnt;             // [P1_W] list lengths
+	uint32_t *list;            // [s * P1_W + xi]
 	int J, JPP;
 
 	__device__ __forceinline__ void push(int xo, int k, uint32_t w) const
@@ -307,7 +352,7 @@ struct Tile {
 			const int cu = min(nu, 15), cd = min(nd, 15);
 			const uint32_t pos = atomicAdd(cnt + xo, 1u);
 			if (pos < (uint32_t)LCAP)
-				list[pos * P1_TX + xo] = (uint32_t)k | ((uint32_t)lu << 11) | ((uint32_t)cu << 17) | ((uint32_t)ld << 21) | ((uint32_t)cd << 27);
+				list[pos * P1_W + xo] = (uint32_t)k | ((uint32_t)lu << 11) | ((uint32_t)cu << 17) | ((uint32_t)ld << 21) | ((uint32_t)cd << 27);
 			lu += cu; nu -= cu; ld += cd; nd -= cd;
 		} while (nu > 0 || nd > 0);
 	}
@@ -381,7 +426,7 @@ struct TileThread {
 	__device__ __forceinline__ bool survivor(int s, int &k, int &d, uint32_t &w) const
 	{
 		if (!direct) {
-			const uint32_t e = t.list[s * P1_TX + xi];
+			const uint32_t e = t.list[s * P1_W + xi];
 			k = (int)(e & 2047u);
 			d = abs((int)t.ci[k] - ix);
 			w = entry_windows(e);
@@ -554,14 +599,14 @@ struct TileHead {
 	uint32_t base;
 };
 
-// Phase 2 of a staged tile: thread per output column (all threads of the CTA enter; `active` = owns a column).
+// Phase 2 of a staged tile: lane per output column (the whole warp enters; `active` = owns a column).
 template <int CAP, bool MULTI, int LCAP>
 __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHead &h, const Tile<LCAP> &tl, const uint32_t *s_off)
 {
-	const int J = a.J, tid = threadIdx.x;
+	const int J = a.J, lane = threadIdx.x & 31;
 	const size_t rowbase = (size_t)h.y * a.nx, ncols_all = (size_t)a.nx * a.ny;
-	const bool active = tid < h.txe;
-	const int xi = tid, ix = xi + J;
+	const bool active = lane < h.txe;
+	const int xi = lane, ix = xi + J;
 	TileThread<LCAP> t;
 	t.t = tl; t.xi = xi; t.ix = ix; t.y = h.y; t.x0 = h.x0;
 	int UL = 255, UH = 0, DL = 255, DH = 0;
@@ -587,15 +632,15 @@ __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHe
 		a.flags[ncols_all + rowbase + h.x0 + xi] = (uint16_t)(DL | (DH << 8));
 		tl.cnt[xi] = 0;                                    // ready for the next tile
 	} else { UL = UH = DL = DH = 0; }
-	// OR of the windows over the tile: pass 2 skips a producer row whose tile lacks the class
+	// OR of the windows over the tile: pass 2 skips a producer row whose tile mask lacks the class
 	{
 		const unsigned long long mu = class_mask(UL, UH), md = class_mask(DL, DH);
 		const unsigned int mu0 = __reduce_or_sync(0xffffffffu, (unsigned int)mu), mu1 = __reduce_or_sync(0xffffffffu, (unsigned int)(mu >> 32));
 		const unsigned int md0 = __reduce_or_sync(0xffffffffu, (unsigned int)md), md1 = __reduce_or_sync(0xffffffffu, (unsigned int)(md >> 32));
-		if ((tid & 31) == 0) {
-			const size_t ntl = (size_t)a.tiles_x * a.ny;
-			if (mu0 | mu1) atomicOr(a.tilemask + h.tile, (unsigned long long)mu0 | ((unsigned long long)mu1 << 32));
-			if (md0 | md1) atomicOr(a.tilemask + ntl + h.tile, (unsigned long long)md0 | ((unsigned long long)md1 << 32));
+		if (lane == 0) {
+			const size_t ntl = (size_t)a.tiles_x * a.ny, mt = (size_t)h.y * a.tiles_x + h.x0 / P1_TX;
+			if (mu0 | mu1) atomicOr(a.tilemask + mt, (unsigned long long)mu0 | ((unsigned long long)mu1 << 32));
+			if (md0 | md1) atomicOr(a.tilemask + ntl + mt, (unsigned long long)md0 | ((unsigned long long)md1 << 32));
 		}
 	}
 	if (!active || (UH == 0 && DH == 0)) return;
@@ -607,71 +652,77 @@ __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHe
 template <bool MULTI>
 __device__ __forceinline__ void tile_other(const Pass1TileArgs &a, const TileHead &h)
 {
-	const int tid = threadIdx.x, nthr = blockDim.x, JP = a.J + 1;
+	const int lane = threadIdx.x & 31, JP = a.J + 1;
 	const size_t rowbase = (size_t)h.y * a.nx, ncols_all = (size_t)a.nx * a.ny;
 	if (h.kind == TK_EMPTY) {                               // nothing in reach: no slot of the tile is needed
-		if (tid < h.txe) { a.flags[rowbase + h.x0 + tid] = 0; a.flags[ncols_all + rowbase + h.x0 + tid] = 0; }
+		if (lane < h.txe) { a.flags[rowbase + h.x0 + lane] = 0; a.flags[ncols_all + rowbase + h.x0 + lane] = 0; }
 	} else if (h.kind == TK_MULTI) {                        // -> two-hull variant, launch 3
-		if (tid == 0) a.multi_tiles[atomicAdd(a.multi_count, 1u)] = h.tile;
+		if (lane == 0) a.multi_tiles[atomicAdd(a.multi_count, 1u)] = h.tile;
 	} else if (h.kind == TK_BIG) {                          // -> launch 2, larger candidate buffer
-		if (tid == 0) a.big_tiles[atomicAdd(a.big_count, 1u)] = h.tile;
+		if (lane == 0) a.big_tiles[atomicAdd(a.big_count, 1u)] = h.tile;
 	} else {                                                // TK_REDO: leave every slot of the tile to k_pass1
 		const uint16_t full = (uint16_t)(JP << 8);         // window [0, J+1)
-		if (tid < h.txe) { a.flags[rowbase + h.x0 + tid] = full; a.flags[ncols_all + rowbase + h.x0 + tid] = full; }
-		if (tid == 0) { a.tilemask[h.tile] = ~0ull; a.tilemask[(size_t)a.tiles_x * a.ny + h.tile] = ~0ull; }
-		for (int idx = tid; idx < JP * h.txe; idx += nthr) {
+		if (lane < h.txe) { a.flags[rowbase + h.x0 + lane] = full; a.flags[ncols_all + rowbase + h.x0 + lane] = full; }
+		if (lane == 0) {
+			const size_t ntl = (size_t)a.tiles_x * a.ny, mt = (size_t)h.y * a.tiles_x + h.x0 / P1_TX;
+			atomicOr(a.tilemask + mt, ~0ull);
+			atomicOr(a.tilemask + ntl + mt, ~0ull);
+		}
+		for (int idx = lane; idx < JP * h.txe; idx += 32) {
 			const int j = idx / h.txe, xi = idx % h.txe;
 			redo_push(a.redo, ((unsigned long long)h.y * JP + j) * a.nx + h.x0 + xi);
 		}
 	}
 }
 
-// One resident wave of CTAs; every CTA stages the tables once and then pulls tiles with an atomic counter.
+// One CTA per SM; the cap tables are staged once per CTA, then every WARP works on its own: it pulls tiles
+// (P1_W output columns of one row) with an atomic counter and never meets a CTA barrier again - tile costs vary
+// a lot (steep walls), and a warp that lags only delays itself.
 // LIST = false: the tiles [tile0, tile0 + ntiles). LIST = true: the tiles of a list collected by an earlier
 // launch (its length is only known on the device).
-// Software pipeline over the tiles of a CTA (global latency is what bounds a tile otherwise):
+// Software pipeline over the tiles of a warp (global latency is what bounds a tile otherwise):
 //   - the position of the tile after next is fetched (atomicAdd) while the current tile is processed;
 //   - the segment offsets of the NEXT tile are loaded into registers before phase 1 of the current tile and
-//     published to shared memory at the barrier that ends phase 1;
-//   - right after that barrier one thread starts the bulk copies (TMA, cp.async.bulk) of the next tile's
-//     candidates and thresholds into the other staging buffer; they land during phase 2 of the current tile
-//     and are awaited (mbarrier) at the top of the next iteration.
+//     published to shared memory when phase 1 ends;
+//   - right after that one lane starts the bulk copies (TMA, cp.async.bulk) of the next tile's candidates and
+//     thresholds into the other staging buffer; they land during phase 2 of the current tile and are awaited
+//     (mbarrier) at the top of the next iteration.
 template <int CAP, bool MULTI, bool LIST>
-__global__ void __launch_bounds__(P1_TX, MULTI ? 4 : 5) k_pass1_tile(Pass1TileArgs a)
+__global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArgs a)
 {
 	constexpr int LCAP = (MULTI || LIST) ? P1_LCAP_M : P1_LCAP_S;
+	constexpr int NR = 5;                                   // segment offsets per lane: P1_W + 2 * 63 + 1 <= 32 * NR
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	__shared__ unsigned int s_pos[2];
 	const unsigned int n = LIST ? *a.tiles_count : a.ntiles;
 	if (n == 0) return;
-	const int J = a.J, JP = J + 1, SEG = P1_TX + 2 * J, tid = threadIdx.x, nthr = blockDim.x;
-	const TileSmem sm(smem_raw, J, a.cmax, LCAP);
-	for (int i = tid; i < JP * pass1_jpp(J); i += nthr) sm.Ht[i] = __ldg(a.Ht + i);
-	for (int i = tid; i < JP * (JP + 1); i += nthr) sm.Ef[i] = __ldg(a.Ef + i);
-	for (int i = tid; i < JP + 1; i += nthr) sm.jmax[i] = __ldg(a.jmax + i);
-	if (tid < P1_TX) sm.cnt[tid] = 0;
-	if (tid == 0) {
+	const int J = a.J, JP = J + 1, SEG = P1_W + 2 * J, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned int FULL = 0xffffffffu;
+	const TableSmem tb(smem_raw, J);
+	for (int i = threadIdx.x; i < JP * pass1_jpp(J); i += blockDim.x) tb.Ht[i] = __ldg(a.Ht + i);
+	for (int i = threadIdx.x; i < JP * (JP + 1); i += blockDim.x) tb.Ef[i] = __ldg(a.Ef + i);
+	for (int i = threadIdx.x; i < JP + 1; i += blockDim.x) tb.jmax[i] = __ldg(a.jmax + i);
+	const WarpSmem sm(smem_raw + pass1_table_smem(J) + (size_t)warp * pass1_warp_smem(J, a.cmax, LCAP), J, a.cmax, LCAP);
+	sm.cnt[lane] = 0;
+	if (lane == 0) {
 		mbar_init(sm.mbar + 0, 1); mbar_init(sm.mbar + 1, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		s_pos[0] = atomicAdd(a.tiles_next, 1u);
-		s_pos[1] = atomicAdd(a.tiles_next, 1u);
 	}
-	__syncthreads();
+	__syncthreads();                                        // the only CTA barrier: tables (and mbarriers) are in place
 
 	Tile<LCAP> tl;
-	tl.Ht = sm.Ht; tl.Ef = sm.Ef; tl.jmax = sm.jmax; tl.cnt = sm.cnt; tl.list = sm.list; tl.J = J; tl.JPP = pass1_jpp(J);
+	tl.Ht = tb.Ht; tl.Ef = tb.Ef; tl.jmax = tb.jmax; tl.cnt = sm.cnt; tl.list = sm.list; tl.J = J; tl.JPP = pass1_jpp(J);
 
-	// segment offsets of the tile at list position `pos` -> registers (two entries per thread; o[r][1] = the next
-	// column's offset, for the multi-interval test)
-	auto load_offsets = [&](unsigned int pos, uint32_t (&o)[2][2], TileHead &h) {
+	// segment offsets of the tile at list position `pos` -> registers (o[r][1] = the next column's offset, for the
+	// multi-interval test)
+	auto load_offsets = [&](unsigned int pos, uint32_t (&o)[NR][2], TileHead &h) {
 		h.tile = LIST ? a.tiles[pos] : a.tile0 + pos;
-		h.y = (int)(h.tile / (unsigned)a.tiles_x);
-		h.x0 = (int)(h.tile % (unsigned)a.tiles_x) * P1_TX;
-		h.txe = min(P1_TX, a.nx - h.x0);
+		h.y = (int)(h.tile / (unsigned)a.tiles_xw);
+		h.x0 = (int)(h.tile % (unsigned)a.tiles_xw) * P1_W;
+		h.txe = min(P1_W, a.nx - h.x0);
 		const size_t rowbase = (size_t)h.y * a.nx;
 #pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			const int i = tid + r * P1_TX;
+		for (int r = 0; r < NR; ++r) {
+			const int i = lane + r * 32;
 			o[r][0] = o[r][1] = 0;
 			if (i <= SEG) {
 				o[r][0] = __ldg(a.off + rowbase + min(max(h.x0 - J + i, 0), a.nx));   // columns outside the grid collapse to empty ranges
@@ -679,54 +730,56 @@ __global__ void __launch_bounds__(P1_TX, MULTI ? 4 : 5) k_pass1_tile(Pass1TileAr
 			}
 		}
 	};
-	// registers -> shared memory; returns this thread's "a column of the segment holds several intervals"
-	auto store_offsets = [&](const uint32_t (&o)[2][2], uint32_t *s_off) -> bool {
+	// registers -> shared memory; returns "a column of the segment holds several intervals" (warp-uniform)
+	auto store_offsets = [&](const uint32_t (&o)[NR][2], uint32_t *s_off) -> bool {
 		bool multi = false;
 #pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			const int i = tid + r * P1_TX;
+		for (int r = 0; r < NR; ++r) {
+			const int i = lane + r * 32;
 			if (i <= SEG) { s_off[i] = o[r][0]; if (!MULTI && i < SEG) multi |= o[r][1] - o[r][0] > 1u; }
 		}
-		return multi;
+		__syncwarp();                                       // the stores are visible to the whole warp
+		return __any_sync(FULL, multi);
 	};
 	auto classify = [&](TileHead &h, const uint32_t *s_off, bool multi) {
 		h.base = s_off[0];
 		h.ncand = (int)(s_off[SEG] - h.base);
 		h.kind = multi ? TK_MULTI : h.ncand > a.cmax ? (a.big_tiles ? TK_BIG : TK_REDO) : h.ncand == 0 ? TK_EMPTY : TK_NORMAL;
 	};
-	// start the staging of a NORMAL tile into buffer b: bulk copies by one thread, the column map by all
+	// start the staging of a NORMAL tile into buffer b: bulk copies by one lane, the column map by all
 	auto stage = [&](const TileHead &h, int b) {
-		if (tid == 0) {
+		if (lane == 0) {
 			const unsigned int bytes = (unsigned int)h.ncand * 16u;
 			mbar_expect_tx(sm.mbar + b, 2u * bytes);
 			bulk_g2s(sm.cand[b], a.spans + h.base, bytes, sm.mbar + b);
 			bulk_g2s(sm.thr[b], a.thr + h.base, bytes, sm.mbar + b);
 		}
 		const uint32_t *s_off = sm.off[b];
-		for (int i = tid; i < SEG; i += nthr)
+		for (int i = lane; i < SEG; i += 32)
 			for (uint32_t k = s_off[i] - h.base; k < s_off[i + 1] - h.base; ++k) sm.ci[b][k] = (uint8_t)i;
 	};
+	auto fetch_pos = [&]() -> unsigned int { return lane == 0 ? atomicAdd(a.tiles_next, 1u) : 0u; };
 
-	// prologue: the first tile is loaded synchronously
-	unsigned int pos = s_pos[0];
+	// prologue: the first tile is loaded synchronously, the positions of the next two are in flight
+	unsigned int pos = __shfl_sync(FULL, fetch_pos(), 0);
 	if (pos >= n) return;
+	unsigned int npos_raw = fetch_pos();                    // position of the next tile (lane 0 holds it)
 	TileHead cur, nxt;
-	uint32_t o[2][2];
+	uint32_t o[NR][2];
 	int buf = 0;
 	unsigned int phase[2] = {0u, 0u};
 	load_offsets(pos, o, cur);
 	{
-		const bool m = store_offsets(o, sm.off[0]);
-		const bool multi = __syncthreads_or(m);
+		const bool multi = store_offsets(o, sm.off[0]);
 		classify(cur, sm.off[0], multi);
 		if (cur.kind == TK_NORMAL) stage(cur, 0);
+		__syncwarp();
 	}
-	__syncthreads();
 
-	for (unsigned int it = 0;; ++it) {
-		const unsigned int npos = s_pos[(it + 1) & 1];      // position of the next tile
+	for (;;) {
+		const unsigned int npos = __shfl_sync(FULL, npos_raw, 0);
 		const bool have_next = npos < n;
-		if (tid == 0) s_pos[it & 1] = atomicAdd(a.tiles_next, 1u);    // the one after it (read two barriers from now)
+		npos_raw = fetch_pos();                              // the one after it (used at the top of the next iteration)
 		if (have_next) load_offsets(npos, o, nxt);
 
 		// ---- current tile, phase 1 ----
@@ -734,21 +787,20 @@ __global__ void __launch_bounds__(P1_TX, MULTI ? 4 : 5) k_pass1_tile(Pass1TileAr
 			mbar_wait(sm.mbar + buf, phase[buf]);            // candidates and thresholds have landed
 			phase[buf] ^= 1u;
 			tl.cand = sm.cand[buf]; tl.thr = sm.thr[buf]; tl.ci = sm.ci[buf];
-			for (int k = tid; k < cur.ncand; k += nthr) tl.scatter(k, cur.txe);
+			for (int k = lane; k < cur.ncand; k += 32) tl.scatter(k, cur.txe);
 		} else tile_other<MULTI>(a, cur);
 
 		// ---- publish the next tile's offsets, start its staging ----
-		bool m = false;
-		if (have_next) m = store_offsets(o, sm.off[buf ^ 1]);
-		const bool nmulti = __syncthreads_or(m);             // (also: phase 1 of the current tile is complete)
 		if (have_next) {
+			const bool nmulti = store_offsets(o, sm.off[buf ^ 1]);
 			classify(nxt, sm.off[buf ^ 1], nmulti);
 			if (nxt.kind == TK_NORMAL) stage(nxt, buf ^ 1);
 		}
+		__syncwarp();                                       // phase 1 of the current tile is complete (lists visible)
 
 		// ---- current tile, phase 2 ----
 		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP>(a, cur, tl, sm.off[buf]);
-		__syncthreads();                                    // lists, counters and the staging buffer are free again
+		__syncwarp();                                       // lists, counters and the staging buffer are free again
 		if (!have_next) break;
 		cur = nxt;
 		buf ^= 1;

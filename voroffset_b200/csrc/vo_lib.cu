@@ -501,8 +501,77 @@ int get_tables(vo_ctx *ctx, double R, bool need_tile, TableCache **out)
 	return VO_OK;
 }
 
+// Launch plan of the tile kernel (pass1_tile.cuh): candidate-buffer sizes, warps per CTA and shared memory of the
+// three launches, from the grid and the mean fill. One CTA per SM; warps work on their own.
+struct TilePlan {
+	int J = 0, tiles_xw = 0, tiles_x = 0, sms = 148;
+	int cmax_small = 0, cmax_big = 0, cmax_multi = 0;
+	int nw_small = 1, nw_big = 1, nw_multi = 1;
+	size_t smem_small = 0, smem_big = 0, smem_multi = 0;
+	static constexpr int CMAX = 2048;       // largest candidate buffer (11-bit candidate ids in the survivor lists)
+	static bool fits(int J, double k_in) { return J <= 63 && k_in * (P1_W + 2 * J) <= 0.75 * CMAX; }
+	int init(vo_ctx *ctx, int nx, int J_, double k_in)
+	{
+		J = J_;
+		tiles_xw = (nx + P1_W - 1) / P1_W;
+		tiles_x = (nx + P1_TX - 1) / P1_TX;
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+		const int SEG = P1_W + 2 * J;
+		auto pick = [](double est) { int c = 64; while (c < CMAX && c < est) c <<= 1; return c; };
+		// launch 1 only sees single-interval columns: at most SEG candidates
+		cmax_small = std::min(pick(k_in * SEG * 1.5), (SEG + 15) & ~15);
+		cmax_big = CMAX;
+		cmax_multi = std::max(pick(k_in * SEG * 1.5), 128);
+		const size_t budget = 220 * 1024;
+		auto warps = [&](int cmax, int lcap) {
+			const size_t per = pass1_warp_smem(J, cmax, lcap), tab = pass1_table_smem(J) + 32;
+			return (int)std::max<size_t>(1, std::min<size_t>(P1_MAXWARPS, (budget - tab) / per));
+		};
+		nw_small = warps(cmax_small, P1_LCAP_S); nw_big = warps(cmax_big, P1_LCAP_M); nw_multi = warps(cmax_multi, P1_LCAP_M);
+		smem_small = pass1_tile_smem(J, cmax_small, P1_LCAP_S, nw_small);
+		smem_big = pass1_tile_smem(J, cmax_big, P1_LCAP_M, nw_big);
+		smem_multi = pass1_tile_smem(J, cmax_multi, P1_LCAP_M, nw_multi);
+		cudaError_t e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+		if (e != cudaSuccess) return fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e));
+		return VO_OK;
+	}
+	// The three launches over the tiles [tile0, tile0 + ntiles). `g` holds the data pointers; the lists and cursors
+	// ([3] big count, [5] multi count, [6] [7] [10] cursors of d_ctr) must be zero.
+	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles, unsigned int *big_tiles, unsigned int *multi_tiles,
+	            cudaStream_t s) const
+	{
+		g.J = J; g.tiles_xw = tiles_xw; g.tiles_x = tiles_x; g.tile0 = tile0; g.ntiles = ntiles;
+		unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
+		unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
+		g.big_count = big_count; g.multi_tiles = multi_tiles; g.multi_count = multi_count;
+		auto grid = [&](int nw) { return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)sms, (ntiles + nw - 1) / nw)); };
+		// launch 1: single-interval tiles, small candidate buffer
+		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr;
+		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 10);
+		g.big_tiles = cmax_small < cmax_big ? big_tiles : nullptr;
+		k_pass1_tile<CAP_FAST, false, false><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
+		ctx->launches++;
+		if (cmax_small < cmax_big) {    // launch 2: the single-interval tiles that need the large buffer
+			g.cmax = cmax_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
+			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
+			k_pass1_tile<CAP_FAST, false, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
+			ctx->launches++;
+		}
+		// launch 3: tiles with multi-interval columns (two hulls per class); oversized ones go to the redo list
+		g.cmax = cmax_multi; g.tiles = multi_tiles; g.tiles_count = multi_count; g.big_tiles = nullptr;
+		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 7);
+		k_pass1_tile<CAP_FAST, true, true><<<grid(nw_multi), 32 * nw_multi, smem_multi, s>>>(g);
+		ctx->launches++;
+	}
+};
+
 // ---- 'ours' pass 1 ------------------------------------------------------------------------------------
-int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
+// clip_lo / clip_hi: the caller only reads the dilation inside (clip_lo, clip_hi) (erosion); the pruning of the tile
+// kernel may then ignore what happens outside. -inf / +inf: the exact dilation everywhere.
+int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
+          double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity())
 {
 	VO_TRY(check_radius(ctx, R));
 	const int J0 = (int)std::floor(R);
@@ -510,11 +579,10 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	// tile kernel (pass1_tile.cuh) whenever its tables and tile fit in shared memory and a row segment's
 	// candidates are expected to fit; otherwise the one-thread-per-(x,y,j) kernel does everything
 	const int TX = P1_TX;
-	const int cmax = 2048;      // largest candidate buffer of the tile kernel (12-bit candidate ids allow 4096)
 	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
 	// (small problems do not fill the machine with one thread per column: the simple kernel has J+1 times more threads)
 	const bool big = ncols * (unsigned long long)(J0 + 1) >= (2ull << 20) || ctx->force_tile_pass1;
-	const bool use_tile = J0 <= 63 && ncols > 0 && k_in * (TX + 2 * J0) <= 0.75 * cmax && big && !ctx->force_simple_pass1;
+	const bool use_tile = ncols > 0 && TilePlan::fits(J0, k_in) && big && !ctx->force_simple_pass1;
 	TableCache *tc = nullptr;
 	VO_TRY(get_tables(ctx, R, use_tile, &tc));
 	const Tables &t = tc->t;
@@ -533,9 +601,12 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 	if (rc == VO_OK) rc = dalloc(ctx, &m->tilemask, nmask);
 	Tmp<uint4> thr(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &thr.p, in->nspans);
+	TilePlan plan;
+	if (rc == VO_OK && use_tile) rc = plan.init(ctx, in->nx, t.J, k_in);
+	const unsigned long long ntiles = (unsigned long long)plan.tiles_xw * in->ny;
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
-	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
-	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &multi_tiles.p, (unsigned long long)((in->nx + TX - 1) / TX) * in->ny);
+	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, ntiles);
+	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &multi_tiles.p, ntiles);
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nslots, 1ull), 1ull << 22);
 	if (rc == VO_OK) rc = rb.alloc(redo_cap);
@@ -557,51 +628,15 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out)
 			ThreshArgs ta;
 			ta.nx = in->nx; ta.ny = in->ny; ta.J = t.J; ta.off = in->off; ta.spans = in->spans;
 			ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
-			ta.c_begin = 0; ta.c_end = ncols;
+			ta.c_begin = 0; ta.c_end = ncols; ta.clip_lo = clip_lo; ta.clip_hi = clip_hi;
 			k_thresh<<<blocks_for(ncols, 256), 256, 2 * (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(ta);
 			ctx->launches++;
 			Pass1TileArgs g;
-			g.nx = in->nx; g.ny = in->ny; g.J = t.J; g.tile0 = 0;
-			g.tiles_x = (in->nx + TX - 1) / TX;
+			g.nx = in->nx; g.ny = in->ny;
 			g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
 			g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
-			const unsigned long long ntiles = (unsigned long long)g.tiles_x * in->ny;
-			const double seg_est = k_in * (TX + 2 * t.J) * 1.3;
-			const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : seg_est <= 1024 ? 1024 : cmax;
-			const size_t smem_small = pass1_tile_smem(t.J, cmax_small, P1_LCAP_S), smem_big = pass1_tile_smem(t.J, cmax, P1_LCAP_M);
-			e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-			if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e)));
-			unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
-			unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
-			g.big_count = big_count; g.multi_tiles = multi_tiles.p; g.multi_count = multi_count;
-			// list launches: exactly one resident wave of CTAs striding over the collected tiles
-			auto wave = [&](const void *kernel, size_t smem) {
-				int occ = 1, sms = 148;
-				cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, P1_TX, smem);
-				cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-				return (unsigned int)std::min<unsigned long long>(ntiles, (unsigned long long)std::max(occ, 1) * sms);
-			};
 			cudaEventRecord(ctx->kev[0], ctx->stream);
-			// launch 1: single-interval tiles, small candidate buffer
-			g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.ntiles = (unsigned int)ntiles;
-			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 10);
-			g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
-			k_pass1_tile<CAP_FAST, false, false><<<wave((const void *)k_pass1_tile<CAP_FAST, false, false>, smem_small), P1_TX, smem_small, ctx->stream>>>(g);
-			ctx->launches++;
-			if (cmax_small < cmax) {        // launch 2: the single-interval tiles that need the large buffer
-				g.cmax = cmax; g.tiles = big_tiles.p; g.tiles_count = big_count; g.big_tiles = nullptr;
-				g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
-				k_pass1_tile<CAP_FAST, false, true><<<wave((const void *)k_pass1_tile<CAP_FAST, false, true>, smem_big), P1_TX, smem_big, ctx->stream>>>(g);
-				ctx->launches++;
-			}
-			// launch 3: tiles with multi-interval columns (two hulls per class); oversized ones go to the redo list
-			g.cmax = cmax_small < 512 ? 512 : cmax_small; g.tiles = multi_tiles.p; g.tiles_count = multi_count; g.big_tiles = nullptr;
-			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 7);
-			const size_t smem_multi = pass1_tile_smem(t.J, g.cmax, P1_LCAP_M);
-			k_pass1_tile<CAP_FAST, true, true><<<wave((const void *)k_pass1_tile<CAP_FAST, true, true>, smem_multi), P1_TX, smem_multi, ctx->stream>>>(g);
-			ctx->launches++;
+			plan.launch(ctx, g, 0u, (unsigned int)ntiles, big_tiles.p, multi_tiles.p, ctx->stream);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
 		} else if (nslots) {
@@ -684,13 +719,14 @@ int brute(vo_ctx *ctx, const vo_dvol *in, double R, vo_dvol **out)
 struct PassTimes { double ms1 = 0, ms2 = 0; };
 
 // dilation of a resident volume; fills the per-pass device times
-int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, PassTimes *pt)
+int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, PassTimes *pt,
+           double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity())
 {
 	float t1 = 0, t2 = 0;
 	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 	if (method == VO_METHOD_OURS) {
 		vo_dmid *mid = nullptr;
-		VO_TRY(pass1(ctx, in, R, &mid));
+		VO_TRY(pass1(ctx, in, R, &mid, clip_lo, clip_hi));
 		cudaEventRecord(ctx->ev[1], ctx->stream);
 		int rc = pass2(ctx, mid, 0, mid->ny, out);
 		vo_dmid_free(ctx, mid);
@@ -772,7 +808,9 @@ int erode(vo_ctx *ctx, int method, const vo_dvol *in, double zmin, double zmax, 
 	const double z_min = zmin - 1, z_max = zmax + 1;
 	vo_dvol *neg = nullptr, *dil = nullptr;
 	VO_TRY(negate(ctx, in, 1, z_min, z_max, &neg));
-	int rc = dilate(ctx, method, neg, R, &dil, pt);
+	// negateInv only reads the dilated complement inside (z_min + 1, z_max - 1): everything at or beyond those bounds
+	// is dropped (MorphologyOperators.cpp:292-312), so 'ours' may prune with that clip range (pass1_tile.cuh: nn_of)
+	int rc = dilate(ctx, method, neg, R, &dil, pt, z_min + 1, z_max - 1);
 	free_dvol(ctx, neg);
 	VO_TRY(rc);
 	rc = negate_inv(ctx, dil, 1, z_min + 1, z_max - 1, out);
@@ -990,12 +1028,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const unsigned long long ncols = (unsigned long long)nx * ny;
 	if (nx <= 0 || ny <= 0 || !off || off[0] != 0 || ncols >= (1ull << 32) - 8) return PIPE_NA;
 	const uint64_t nspans = off[ncols];
-	const int TX = P1_TX, cmax = 2048;
 	const double k_in = (double)nspans / (double)ncols;
 	// about six bands: enough to overlap, few enough that the per-band launch / readback overhead stays small
 	const int BH = std::max(2 * (J + 1), ((ny + 5) / 6 + 7) & ~7);   // band height >= reach of pass 2
 	const int nb = (ny + BH - 1) / BH;
-	if (J > 63 || nb < 3 || ncols * (unsigned long long)(J + 1) < (48ull << 20) || k_in * (TX + 2 * J) > 0.75 * cmax) return PIPE_NA;
+	if (nb < 3 || ncols * (unsigned long long)(J + 1) < (48ull << 20) || !TilePlan::fits(J, k_in)) return PIPE_NA;
 	if (nspans && !spans) return PIPE_NA;
 
 	TableCache *tc = nullptr;
@@ -1023,9 +1060,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	VO_TRY(dalloc(ctx, &m->flags, 2 * ncols));
 	Tmp<uint4> thr(ctx);
 	VO_TRY(dalloc(ctx, &thr.p, nspans));
-	const int tiles_x = (nx + TX - 1) / TX;
+	TilePlan plan;
+	VO_TRY(plan.init(ctx, nx, J, k_in));
+	const int tiles_x = plan.tiles_x;
 	VO_TRY(dalloc(ctx, &m->tilemask, 2ull * ny * tiles_x));
-	const unsigned long long ntiles = (unsigned long long)tiles_x * ny;
+	const unsigned long long ntiles = (unsigned long long)plan.tiles_xw * ny;
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
 	VO_TRY(dalloc(ctx, &big_tiles.p, ntiles));
 	VO_TRY(dalloc(ctx, &multi_tiles.p, ntiles));
@@ -1063,26 +1102,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	ThreshArgs ta;
 	ta.nx = nx; ta.ny = ny; ta.J = J; ta.off = in->off; ta.spans = in->spans;
 	ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
+	ta.clip_lo = -std::numeric_limits<double>::infinity(); ta.clip_hi = std::numeric_limits<double>::infinity();
 	Pass1TileArgs g;
-	g.nx = nx; g.ny = ny; g.J = J; g.tiles_x = tiles_x;
+	g.nx = nx; g.ny = ny;
 	g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
 	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
-	unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
-	unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
-	g.big_count = big_count; g.multi_tiles = multi_tiles.p; g.multi_count = multi_count;
-	const double seg_est = k_in * (TX + 2 * J) * 1.3;
-	const int cmax_small = seg_est <= 256 ? 256 : seg_est <= 512 ? 512 : seg_est <= 1024 ? 1024 : cmax;
-	const size_t smem_small = pass1_tile_smem(J, cmax_small, P1_LCAP_S), smem_big = pass1_tile_smem(J, cmax, P1_LCAP_M);
-	const int cmax_multi = cmax_small < 512 ? 512 : cmax_small;
-	const size_t smem_multi = pass1_tile_smem(J, cmax_multi, P1_LCAP_M);
-	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-	cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-	int sms = 148, occ_big = 1, occ_multi = 1, occ_small = 1;
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_small, k_pass1_tile<CAP_FAST, false, false>, P1_TX, smem_small);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_big, k_pass1_tile<CAP_FAST, false, true>, P1_TX, smem_big);
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_multi, k_pass1_tile<CAP_FAST, true, true>, P1_TX, smem_multi);
 	Pass1Args a1;
 	a1.nx = nx; a1.ny = ny; a1.J = J; a1.off = in->off; a1.spans = in->spans; a1.H = dt.H; a1.reach = dt.reach;
 	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rb.rd;
@@ -1096,24 +1120,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaMemsetAsync(ctx->d_ctr + 10, 0, sizeof(unsigned long long), sm);
 		ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
 		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
-		const unsigned int band_tiles = (unsigned int)tiles_x * (unsigned int)(y1 - y0);
-		g.tile0 = (unsigned int)tiles_x * (unsigned int)y0;
-		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.ntiles = band_tiles;
-		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 10);
-		g.big_tiles = cmax_small < cmax ? big_tiles.p : nullptr;
-		k_pass1_tile<CAP_FAST, false, false><<<std::min<unsigned int>(band_tiles, (unsigned int)(occ_small * sms)), P1_TX, smem_small, sm>>>(g);
-		ctx->launches += 2;
-		if (cmax_small < cmax) {
-			g.cmax = cmax; g.tiles = big_tiles.p; g.tiles_count = big_count; g.big_tiles = nullptr;
-			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
-			k_pass1_tile<CAP_FAST, false, true><<<std::min<unsigned int>(band_tiles, (unsigned int)(occ_big * sms)), P1_TX, smem_big, sm>>>(g);
-			ctx->launches++;
-		}
-		g.cmax = cmax_multi; g.tiles = multi_tiles.p; g.tiles_count = multi_count; g.big_tiles = nullptr;
-		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 7);
-		k_pass1_tile<CAP_FAST, true, true><<<std::min<unsigned int>(band_tiles, (unsigned int)(occ_multi * sms)), P1_TX, smem_multi, sm>>>(g);
+		ctx->launches++;
+		plan.launch(ctx, g, (unsigned int)plan.tiles_xw * (unsigned int)y0, (unsigned int)plan.tiles_xw * (unsigned int)(y1 - y0),
+		            big_tiles.p, multi_tiles.p, sm);
 		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier bands' overflow lists as well: idempotent)
-		ctx->launches += 2;
+		ctx->launches++;
 	};
 
 	// Per-band state of the second half (pass 2 -> prefix sum -> compaction -> download). A band is ENQUEUED
