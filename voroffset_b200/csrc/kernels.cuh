@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 constexpr int P2_TX = 128;
 
 template <int CAP>
-__global__ void __launch_bounds__(P2_TX) k_pass2_rows(Pass2Args a)
+__global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 {
 	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
 	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);

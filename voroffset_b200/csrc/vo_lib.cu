@@ -40,6 +40,7 @@ struct vo_ctx {
 	bool kev_valid[2] = {false, false};
 	void *table_cache = nullptr;      // TableCache*: cap tables of the last radius, kept on the device
 	unsigned long long pool_hint = 0; // mid-pool entries the last pass 1 needed (+25 %)
+	unsigned long long stage_hint = 0; // staging-pool entries the last staged gather needed (+25 %)
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
@@ -305,7 +306,8 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 {
 	StageBuf sb(ctx);
 	RedoBuf rb(ctx);
-	VO_TRY(sb.alloc(nlists, pool_guess));
+	// (the last call's need is the best guess for repeated calls on similar data: no second gather)
+	VO_TRY(sb.alloc(nlists, std::max(pool_guess, std::min(ctx->stage_hint, 4 * nlists + 65536ull))));
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nlists, 1ull), 1ull << 22);
 	VO_TRY(rb.alloc(redo_cap, 8));
 	vo_dvol *v = nullptr;
@@ -338,6 +340,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 		VO_TRY(read_counters(ctx, h));
 		if (h[8] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
 		if (h[9]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
+		ctx->stage_hint = h[1] + h[1] / 4;
 		if (h[1] > sb.st.pool_cap) { VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024)); continue; }
 		if (total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
 		VO_TRY(dalloc(ctx, &v->spans, total));
@@ -580,8 +583,9 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	// candidates are expected to fit; otherwise the one-thread-per-(x,y,j) kernel does everything
 	const int TX = P1_TX;
 	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
-	// (small problems do not fill the machine with one thread per column: the simple kernel has J+1 times more threads)
-	const bool big = ncols * (unsigned long long)(J0 + 1) >= (2ull << 20) || ctx->force_tile_pass1;
+	// (small problems do not fill the machine with one lane per column: the simple kernel has J+1 times more threads;
+	// dense columns tip the balance earlier - the tile kernel's class windows also spare pass 2 most of its reads)
+	const bool big = (double)ncols * (J0 + 1) * std::max(1.0, k_in) >= (double)(2ull << 20) || ctx->force_tile_pass1;
 	const bool use_tile = ncols > 0 && TilePlan::fits(J0, k_in) && big && !ctx->force_simple_pass1;
 	TableCache *tc = nullptr;
 	VO_TRY(get_tables(ctx, R, use_tile, &tc));
