@@ -147,6 +147,22 @@ int  vo_pass2_dev(vo_ctx *ctx, const vo_dmid *mid, int y0, int y1, vo_dvol **out
 void vo_dmid_free(vo_ctx *ctx, vo_dmid *mid);
 int  vo_dmid_info(const vo_dmid *mid, int *nx, int *ny, int *classes, uint64_t *bytes);
 
+/* Overlapped form of the two calls above for a y-slab of a grid sharded over several GPUs (voroffset_b200/slab.py;
+ * the reference's dormant TBB decomposition, VoronoiVorPower.cpp:41-63,70-92, stretched across devices).
+ * vo_slab_begin starts pass 1 on the rows of `own` that do not depend on a neighbour and returns at once; the caller
+ * exchanges the floor(R) boundary rows with its neighbours meanwhile (NCCL); vo_slab_finish takes the received halos
+ * (device pointers: (floor(R)*nx + 1) uint32 offsets starting at 0 and n intervals each; NULL / 0 where there is no
+ * neighbour), finishes pass 1, runs pass 2 on the own rows and releases the slab. cap_prev / cap_next: upper bounds
+ * of the halos' interval counts, agreed with the neighbours beforehand. VO_ERR_ARG from vo_slab_begin = not a case
+ * for the overlapped path (small grid, radius < 1, ...): use vo_pass1_dev / vo_pass2_dev on the concatenated rows.   */
+typedef struct vo_slab vo_slab;
+int  vo_slab_begin(vo_ctx *ctx, const vo_dvol *own, double radius, int has_prev, int has_next,
+                   uint64_t cap_prev, uint64_t cap_next, vo_slab **out);
+int  vo_slab_finish(vo_ctx *ctx, vo_slab *slab, const void *d_off_prev, const void *d_spans_prev, uint64_t n_prev,
+                    const void *d_off_next, const void *d_spans_next, uint64_t n_next,
+                    vo_dvol **out, double *ms_pass1, double *ms_pass2);
+void vo_slab_abort(vo_ctx *ctx, vo_slab *slab);
+
 /* 2D on resident data (one list per row).                                                             */
 int  vo_morph2d_dev(vo_ctx *ctx, int op, const vo_dvol *rows_as_vol /* nx = rows, ny = 1 */, int width,
                     double r, vo_dvol **out, double *ms);

@@ -192,6 +192,50 @@ def test_resident_operator_matches_host_call(ctx):
         assert r.download().bit_equal(h)
 
 
+def test_overlapped_slab_api_matches_single_call(ctx):
+    """vo_slab_begin / vo_slab_finish (the multi-GPU step, voroffset_b200/slab.py) on ONE device: the volume is cut
+    into three y-slabs, every slab is dilated with the halos its neighbours would send, the rows must be the
+    single-call result bit for bit."""
+    import ctypes as C
+    import torch
+    vol = synth.torus_z(640, padding=0)
+    R, J = 20.5, 20
+    op = morpho.make_operator("ours", ctx)
+    whole, _, _ = op.dilation(vol, R)
+    d = morpho.DeviceVolume.upload(ctx, vol)
+    dev = torch.device("cuda", ctx.device)
+    bounds = [(0, 200), (200, 430), (430, vol.ny)]
+    pieces = []
+    for y0, y1 in bounds:
+        own = d.rows(y0, y1)
+        halos = []
+        for (h0, h1), present in (((y0 - J, y0), y0 > 0), ((y1, y1 + J), y1 < vol.ny)):
+            if not present:
+                halos.append(None)
+                continue
+            off = torch.empty(J * vol.nx + 1, dtype=torch.int32, device=dev)
+            sp = torch.empty(2 * 200000, dtype=torch.float64, device=dev)
+            n = C.c_uint64(0)
+            ctx.check(ctx.lib.vo_dvol_rows_to(ctx.handle, d.handle, h0, h1, off.data_ptr(), sp.data_ptr(), 200000, C.byref(n)))
+            halos.append((off, sp, int(n.value)))
+        slab = C.c_void_p()
+        rc = ctx.lib.vo_slab_begin(ctx.handle, own.handle, R, int(halos[0] is not None), int(halos[1] is not None),
+                                   halos[0][2] + 100 if halos[0] else 0, halos[1][2] + 7 if halos[1] else 0, C.byref(slab))
+        assert rc == 0, ctx.lib.vo_last_error(ctx.handle)
+        args = []
+        for h in halos:
+            args += [None, None, 0] if h is None else [h[0].data_ptr(), h[1].data_ptr(), h[2]]
+        out = C.c_void_p()
+        ctx.check(ctx.lib.vo_slab_finish(ctx.handle, slab, *args, C.byref(out), None, None))
+        pieces.append(morpho.DeviceVolume(ctx, out, vol))
+        own.free()
+    assert morpho.concat_rows(ctx, pieces).download().bit_equal(whole)
+    # a small grid is declined (the caller then takes the plain path)
+    small = morpho.DeviceVolume.upload(ctx, synth.blobs(24, padding=2, seed=3))
+    slab = C.c_void_p()
+    assert ctx.lib.vo_slab_begin(ctx.handle, small.handle, 3.0, 0, 1, 0, 1000, C.byref(slab)) == 1
+
+
 # ---- xor --------------------------------------------------------------------------------------------------
 def test_xor(ctx, oracle):
     a, b = synth.blobs(64, padding=4, seed=1), synth.blobs(64, padding=4, seed=2)

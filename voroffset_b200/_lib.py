@@ -30,6 +30,7 @@ EXPORTS = [
     "vo_dvol_info", "vo_dvol_free", "vo_dvol_rows", "vo_dvol_concat_rows", "vo_morph3d_dev", "vo_xor3d_dev",
     "vo_pass1_dev", "vo_pass2_dev", "vo_dmid_free", "vo_dmid_info", "vo_morph2d_dev",
     "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device", "vo_set_option", "vo_dvol_rows_to",
+    "vo_slab_begin", "vo_slab_finish", "vo_slab_abort",
 ]
 
 _lib = None
@@ -91,6 +92,10 @@ def load() -> C.CDLL:
     L.vo_elapsed_ms.argtypes = [_vp, C.c_int, C.c_int, _f64p]
     L.vo_last_profile.argtypes = [_vp, _f64p, _f64p]
     L.vo_dvol_from_device.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp)]
+    L.vo_slab_begin.argtypes = [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(_vp)]
+    L.vo_slab_finish.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, C.POINTER(_vp), _f64p, _f64p]
+    L.vo_slab_abort.argtypes = [_vp, _vp]
+    L.vo_slab_abort.restype = None
     _lib = L
     return L
 

@@ -67,6 +67,8 @@ struct vo_dmid {
 };
 static_assert(P1_TX == P2_TX, "pass 2 reads the tile masks of pass 1: same tile width");
 
+struct vo_slab;   // a y-slab dilation in flight (defined with its helpers below)
+
 namespace {
 
 int fail(vo_ctx *ctx, int code, const std::string &msg)
@@ -1249,6 +1251,185 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	return VO_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Overlapped y-slab dilation (multi-GPU, voroffset_b200/slab.py). A rank owns ny rows and needs floor(R) input
+// rows of each neighbour. vo_slab_begin lays out the EXTENDED volume [prev halo | own rows | next halo] before the
+// halos exist - their spans get reserved regions of agreed capacity, the previous halo right-aligned in its region
+// so that the CSR stays contiguous - and enqueues pass 1 of the own rows that do not depend on a halo. The caller
+// runs the NCCL exchange meanwhile; vo_slab_finish drops the halos in, runs pass 1 on the 2 + 2 floor(R) remaining
+// rows and pass 2 on the own rows. Same kernels and tables as the plain path: the rows are bit-identical.
+// ---------------------------------------------------------------------------------------------------
+} // namespace (reopened below)
+
+struct vo_slab {
+	vo_ctx *ctx = nullptr;
+	vo_dvol *ext = nullptr;
+	vo_dmid *mid = nullptr;
+	int nx = 0, ny = 0, J = 0, jp = 0, jn = 0;      // own rows; halo rows before / after (0 or J)
+	uint64_t cap_prev = 0, cap_next = 0, n_own = 0;
+	double R = 0;
+	TilePlan plan;
+	uint4 *thr = nullptr;
+	unsigned int *big_tiles = nullptr, *multi_tiles = nullptr;
+	unsigned long long *redo_list = nullptr;
+	unsigned int redo_cap = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+};
+
+namespace {
+
+void free_slab(vo_slab *S)
+{
+	if (!S) return;
+	vo_ctx *ctx = S->ctx;
+	free_dvol(ctx, S->ext);
+	if (S->mid) vo_dmid_free(ctx, S->mid);
+	dfree(ctx, S->thr); dfree(ctx, S->big_tiles); dfree(ctx, S->multi_tiles); dfree(ctx, S->redo_list);
+	for (cudaEvent_t e : {S->ev0, S->ev1, S->ev2}) if (e) cudaEventDestroy(e);
+	delete S;
+}
+
+// pass 1 (thresholds + the three tile launches + redo) of rows [y0, y1) of the extended volume; no host sync
+void slab_pass1_rows(vo_slab *S, int y0, int y1)
+{
+	if (y1 <= y0) return;
+	vo_ctx *ctx = S->ctx;
+	cudaStream_t sm = ctx->stream;
+	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
+	const int nx = S->nx, J = S->J;
+	cudaMemsetAsync(ctx->d_ctr + 3, 0, sizeof(unsigned long long), sm);
+	cudaMemsetAsync(ctx->d_ctr + 5, 0, 3 * sizeof(unsigned long long), sm);
+	cudaMemsetAsync(ctx->d_ctr + 10, 0, sizeof(unsigned long long), sm);
+	ThreshArgs ta;
+	ta.nx = nx; ta.ny = S->ext->ny; ta.J = J; ta.off = S->ext->off; ta.spans = S->ext->spans;
+	ta.Dmono = tc->tt.Dmono; ta.Emono = tc->tt.Emono; ta.G = tc->tt.G; ta.reach = tc->dt.reach; ta.thr = S->thr;
+	ta.clip_lo = -std::numeric_limits<double>::infinity(); ta.clip_hi = std::numeric_limits<double>::infinity();
+	ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
+	k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
+	ctx->launches++;
+	vo_dmid *m = S->mid;
+	Redo rd{S->redo_list, reinterpret_cast<unsigned int *>(ctx->d_ctr + 2), S->redo_cap};
+	Pass1TileArgs g;
+	g.nx = nx; g.ny = S->ext->ny;
+	g.off = S->ext->off; g.spans = S->ext->spans; g.thr = S->thr; g.Ht = tc->tt.Ht; g.Ef = tc->tt.Ef; g.jmax = tc->tt.jmax;
+	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rd;
+	S->plan.launch(ctx, g, (unsigned int)S->plan.tiles_xw * (unsigned int)y0, (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0),
+	               S->big_tiles, S->multi_tiles, sm);
+	Pass1Args a1;
+	a1.nx = nx; a1.ny = S->ext->ny; a1.J = J; a1.off = S->ext->off; a1.spans = S->ext->spans; a1.H = tc->dt.H; a1.reach = tc->dt.reach;
+	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rd;
+	a1.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
+	k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier row ranges' overflow lists as well: idempotent)
+	ctx->launches++;
+}
+
+int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_next, uint64_t cap_prev, uint64_t cap_next, vo_slab **out)
+{
+	VO_TRY(check_radius(ctx, R));
+	const int J = (int)std::floor(R), nx = own->nx, ny = own->ny;
+	const int jp = has_prev ? J : 0, jn = has_next ? J : 0;
+	if (!has_prev) cap_prev = 0;
+	if (!has_next) cap_next = 0;
+	const int ey = jp + ny + jn;
+	VO_TRY(check_dims(ctx, nx, ey));
+	const unsigned long long ncols = (unsigned long long)nx * ey, nown = (unsigned long long)nx * ny;
+	const uint64_t total = cap_prev + own->nspans + cap_next;
+	const double k_in = nown ? (double)own->nspans / (double)nown : 0.0;
+	if (J < 1 || ny < 2 || total >= (1ull << 32) || !TilePlan::fits(J, k_in) || ctx->force_simple_pass1 ||
+	    (double)ncols * (J + 1) * std::max(1.0, k_in) < (double)(2ull << 20))
+		return VO_ERR_ARG;                                   // not a case for the overlapped path (the caller takes the plain one)
+	TableCache *tc = nullptr;
+	VO_TRY(get_tables(ctx, R, true, &tc));
+	vo_slab *S = new (std::nothrow) vo_slab();
+	if (!S) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
+	S->ctx = ctx; S->nx = nx; S->ny = ny; S->J = J; S->jp = jp; S->jn = jn; S->R = R;
+	S->cap_prev = cap_prev; S->cap_next = cap_next; S->n_own = own->nspans;
+	auto bail = [&](int rc) { free_slab(S); return rc; };
+	int rc = new_dvol(ctx, nx, ey, &S->ext);
+	if (rc == VO_OK) rc = dalloc(ctx, &S->ext->spans, total);
+	if (rc) return bail(rc);
+	S->ext->nspans = total;
+	vo_dmid *m = new (std::nothrow) vo_dmid();
+	if (!m) return bail(fail(ctx, VO_ERR_NOMEM, "out of host memory"));
+	S->mid = m;
+	m->nx = nx; m->ny = ey; m->J = J; m->R = R;
+	const unsigned long long nslots = ncols * (J + 1);
+	m->pool_cap = std::max(65536ull + (unsigned long long)(J + 1) * (total / 4), ctx->pool_hint);
+	rc = dalloc(ctx, &m->slots, nslots);
+	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, m->pool_cap);
+	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, 2 * ncols);
+	if (rc == VO_OK) rc = S->plan.init(ctx, nx, J, k_in);
+	const unsigned long long nmask = 2ull * ey * S->plan.tiles_x, ntiles = (unsigned long long)S->plan.tiles_xw * ey;
+	if (rc == VO_OK) rc = dalloc(ctx, &m->tilemask, nmask);
+	if (rc == VO_OK) rc = dalloc(ctx, &S->thr, total);
+	if (rc == VO_OK) rc = dalloc(ctx, &S->big_tiles, ntiles);
+	if (rc == VO_OK) rc = dalloc(ctx, &S->multi_tiles, ntiles);
+	S->redo_cap = (unsigned int)std::min<unsigned long long>(nslots, 1ull << 22);
+	if (rc == VO_OK) rc = dalloc(ctx, &S->redo_list, S->redo_cap);
+	if (rc) return bail(rc);
+	bool ok = cudaEventCreate(&S->ev0) == cudaSuccess && cudaEventCreate(&S->ev1) == cudaSuccess && cudaEventCreate(&S->ev2) == cudaSuccess;
+	if (!ok) { cudaGetLastError(); return bail(fail(ctx, VO_ERR_CUDA, "cudaEventCreate")); }
+	cudaStream_t sm = ctx->stream;
+	cudaEventRecord(S->ev0, sm);
+	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
+	cudaMemsetAsync(m->tilemask, 0, nmask * sizeof(unsigned long long), sm);
+	// own rows into the extended volume: offsets shifted by the reserved region of the previous halo
+	cudaMemcpyAsync(S->ext->off + (size_t)jp * nx, own->off, (nown + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
+	if (cap_prev) { k_rebase<<<blocks_for(nown + 1, 256), 256, 0, sm>>>(S->ext->off + (size_t)jp * nx, nown + 1, 0u, (uint32_t)cap_prev); ctx->launches++; }
+	if (own->nspans) cudaMemcpyAsync(S->ext->spans + cap_prev, own->spans, own->nspans * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
+	// rows whose thresholds only read own rows
+	slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0));
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)));
+	*out = S;
+	return VO_OK;
+}
+
+int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, uint64_t n_prev,
+                const void *d_off_next, const void *d_spans_next, uint64_t n_next, vo_dvol **out, double *ms1, double *ms2)
+{
+	vo_ctx *ctx = S->ctx;
+	cudaStream_t sm = ctx->stream;
+	const int nx = S->nx, ny = S->ny, jp = S->jp, jn = S->jn;
+	if ((jp && (n_prev > S->cap_prev || !d_off_prev)) || (jn && (n_next > S->cap_next || !d_off_next)))
+		return fail(ctx, VO_ERR_OVERFLOW, "halo larger than its reserved region");
+	if (jp) {
+		const unsigned long long n = (unsigned long long)jp * nx;          // (the entry after the last halo column is the first own offset)
+		cudaMemcpyAsync(S->ext->off, d_off_prev, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
+		k_rebase<<<blocks_for(n, 256), 256, 0, sm>>>(S->ext->off, n, 0u, (uint32_t)(S->cap_prev - n_prev));
+		ctx->launches++;
+		if (n_prev) cudaMemcpyAsync(S->ext->spans + (S->cap_prev - n_prev), d_spans_prev, n_prev * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
+	}
+	if (jn) {
+		const unsigned long long n = (unsigned long long)jn * nx + 1;
+		uint32_t *dst = S->ext->off + (size_t)(jp + ny) * nx;
+		cudaMemcpyAsync(dst, d_off_next, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
+		k_rebase<<<blocks_for(n, 256), 256, 0, sm>>>(dst, n, 0u, (uint32_t)(S->cap_prev + S->n_own));
+		ctx->launches++;
+		if (n_next) cudaMemcpyAsync(S->ext->spans + S->cap_prev + S->n_own, d_spans_next, n_next * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
+	}
+	if (jp) slab_pass1_rows(S, 0, jp + 1);
+	if (jn) slab_pass1_rows(S, jp + ny - 1, jp + ny + jn);
+	cudaEventRecord(S->ev1, sm);
+	unsigned long long h[NCTR];
+	VO_TRY(read_counters(ctx, h));
+	VO_CUDA(cudaGetLastError());
+	if (h[0] > S->mid->pool_cap) { ctx->pool_hint = h[0] + h[0] / 4; return fail(ctx, VO_ERR_OVERFLOW, "mid pool too small"); }
+	if (h[2] > S->redo_cap || h[4]) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
+	S->mid->pool_used = h[0];
+	ctx->pool_hint = h[0] + h[0] / 4;
+	VO_TRY(pass2(ctx, S->mid, jp, jp + ny, out));
+	VO_CUDA(cudaEventRecord(S->ev2, sm));
+	VO_CUDA(cudaEventSynchronize(S->ev2));
+	float t1 = 0, t2 = 0;
+	cudaEventElapsedTime(&t1, S->ev0, S->ev1);
+	cudaEventElapsedTime(&t2, S->ev1, S->ev2);
+	if (ms1) *ms1 = t1;
+	if (ms2) *ms2 = t2;
+	return VO_OK;
+}
+
 struct DeviceGuard {
 	int prev = -1;
 	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -1599,6 +1780,35 @@ int vo_dmid_info(const vo_dmid *m, int *nx, int *ny, int *classes, uint64_t *byt
 	if (classes) *classes = m->J + 1;
 	if (bytes) *bytes = ((uint64_t)m->nx * m->ny * (m->J + 1) + m->pool_used) * sizeof(double2);
 	return VO_OK;
+}
+
+int vo_slab_begin(vo_ctx *ctx, const vo_dvol *own, double radius, int has_prev, int has_next, uint64_t cap_prev, uint64_t cap_next,
+                  vo_slab **out)
+{
+	if (!ctx || !own || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	*out = nullptr;
+	return slab_begin(ctx, own, radius, has_prev, has_next, cap_prev, cap_next, out);
+}
+
+int vo_slab_finish(vo_ctx *ctx, vo_slab *slab, const void *d_off_prev, const void *d_spans_prev, uint64_t n_prev,
+                   const void *d_off_next, const void *d_spans_next, uint64_t n_next, vo_dvol **out, double *ms_pass1, double *ms_pass2)
+{
+	if (!ctx || !slab || !out || slab->ctx != ctx) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	const int rc = slab_finish(slab, d_off_prev, d_spans_prev, n_prev, d_off_next, d_spans_next, n_next, out, ms_pass1, ms_pass2);
+	free_slab(slab);
+	return rc;
+}
+
+void vo_slab_abort(vo_ctx *ctx, vo_slab *slab)
+{
+	if (!ctx || !slab) return;
+	DeviceGuard g(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	free_slab(slab);
 }
 
 int vo_morph2d_dev(vo_ctx *ctx, int op, const vo_dvol *rows, int width, double r, vo_dvol **out, double *ms)

@@ -103,6 +103,31 @@ class CudaSlabBackend:
         if vol is not None:
             vol.free()
 
+    # -- overlapped form: pass 1 of the halo-independent rows runs while the halos travel ----------------
+    def slab_begin(self, vol: DeviceVolume, radius: float, has_prev: bool, has_next: bool, cap_prev: int, cap_next: int):
+        """Returns an opaque handle, or None when the library declines (small grids, radius < 1, ...)."""
+        h = C.c_void_p()
+        rc = self.ctx.lib.vo_slab_begin(self.ctx.handle, vol.handle, float(radius), int(has_prev), int(has_next),
+                                        int(cap_prev), int(cap_next), C.byref(h))
+        if rc == 1:                                   # VO_ERR_ARG: not a case for the overlapped path
+            return None
+        self.ctx.check(rc)
+        return h
+
+    def slab_finish(self, slab, prev, nxt, like: DeviceVolume):
+        """prev / nxt: (offsets tensor, spans tensor, interval count) or None. Returns (result, ms1, ms2)."""
+        torch.cuda.current_stream(self.device).synchronize()
+        args = []
+        for part in (prev, nxt):
+            args += [None, None, 0] if part is None else [part[0].data_ptr(), part[1].data_ptr(), int(part[2])]
+        out = C.c_void_p()
+        ms1, ms2 = C.c_double(0), C.c_double(0)
+        self.ctx.check(self.ctx.lib.vo_slab_finish(self.ctx.handle, slab, *args, C.byref(out), C.byref(ms1), C.byref(ms2)))
+        return DeviceVolume(self.ctx, out, like.meta), ms1.value, ms2.value
+
+    def slab_abort(self, slab):
+        self.ctx.lib.vo_slab_abort(self.ctx.handle, slab)
+
 
 class _Link:
     """Per-neighbour message buffers and the capacities agreed so far."""
@@ -226,12 +251,87 @@ class SlabDilation:
         self.last_halo_bytes = nbytes
         return halos.get(self.rank - 1), halos.get(self.rank + 1)
 
+    def _dilate_overlapped(self, vol, radius: float, nx: int, ny: int, J: int):
+        """Steady-state step on a backend with slab_begin / slab_finish: the single message batch is posted first,
+        pass 1 of the rows that do not depend on a halo runs while it travels. Returns None when this step has to
+        take the plain path (first call on a link, a halo that outgrew its capacity, library declines)."""
+        be = self.backend
+        if self._shape != (nx, J):
+            return None
+        L = J * nx + 1
+        nbrs = [(r, rows) for r, rows in ((self.rank - 1, (0, J)), (self.rank + 1, (ny - J, ny))) if 0 <= r < self.world]
+        links = {r: self._links.get(r) for r, _ in nbrs}
+        if any(lk is None or lk.cap_out is None or lk.cap_in is None or lk.off_in is None for lk in links.values()):
+            return None
+        n_out = {}
+        for r, (y0, y1) in nbrs:
+            lk = links[r]
+            n = be.rows_into(vol, y0, y1, lk.off_out, lk.sp_out)
+            if n > lk.cap_out or lk.sp_out.numel() // 2 < lk.cap_out or lk.sp_in.numel() // 2 < lk.cap_in:
+                return None                           # (rows_into left the buffers reusable: the plain path repeats it)
+            n_out[r] = n
+        ops, nbytes = [], 0
+        for r, _ in nbrs:
+            lk = links[r]
+            lk.off_out[L:L + 2] = torch.tensor([n_out[r] & 0x7fffffff, 0], dtype=torch.int32, device=lk.off_out.device)
+            ops += [dist.P2POp(dist.isend, lk.off_out, r, self.group), dist.P2POp(dist.irecv, lk.off_in, r, self.group),
+                    dist.P2POp(dist.isend, lk.sp_out[: 2 * lk.cap_out], r, self.group),
+                    dist.P2POp(dist.irecv, lk.sp_in[: 2 * lk.cap_in], r, self.group)]
+            nbytes += 2 * lk.cap_out * 8 + (L + 2) * 4
+        works = dist.batch_isend_irecv(ops)
+        prev_lk, next_lk = links.get(self.rank - 1), links.get(self.rank + 1)
+        slab = be.slab_begin(vol, radius, prev_lk is not None, next_lk is not None,
+                             prev_lk.cap_in if prev_lk else 0, next_lk.cap_in if next_lk else 0)
+        for w in works:
+            w.wait()
+        self.last_messages, self.last_halo_bytes = 1, nbytes
+        hdr = {r: links[r].off_in[L:L + 2].tolist() for r, _ in nbrs}
+        overflow = any(h[1] for h in hdr.values())
+        if overflow:
+            # a neighbour's halo outgrew the agreed capacity: its exact payload follows; this step finishes on the plain path
+            ops, exact_in = [], {}
+            for r, _ in nbrs:
+                if hdr[r][1]:
+                    _, exact_in[r] = be.new_tensors(1, int(hdr[r][0]))
+                    ops.append(dist.P2POp(dist.irecv, exact_in[r][: 2 * int(hdr[r][0])], r, self.group))
+            self._batch(ops)
+        parts = {}
+        for r, _ in nbrs:
+            lk = links[r]
+            n_in = int(hdr[r][0])
+            parts[r] = (lk.off_in, exact_in[r] if overflow and hdr[r][1] else lk.sp_in, n_in)
+            lk.cap_in = max(lk.cap_in, _grow(n_in))
+            lk.cap_out = max(lk.cap_out, _grow(n_out[r]))
+        if slab is not None and not overflow:
+            out, ms1, ms2 = be.slab_finish(slab, parts.get(self.rank - 1), parts.get(self.rank + 1), like=vol)
+            self.last_ms = (ms1, ms2)
+            return out
+        if slab is not None:
+            be.slab_abort(slab)
+        halos = {r: be.from_tensors(nx, J, p[0], p[1], p[2], like=vol) for r, p in parts.items()}
+        return self._finish_plain(vol, radius, ny, J, halos.get(self.rank - 1), halos.get(self.rank + 1))
+
+    def _finish_plain(self, vol, radius, ny, J, halo_prev, halo_next):
+        be = self.backend
+        ext = be.concat([halo_prev, vol, halo_next])
+        y0 = J if halo_prev is not None else 0
+        out, ms1, ms2 = be.dilate_rows(ext, radius, y0, y0 + ny)
+        be.release(ext)
+        be.release(halo_prev)
+        be.release(halo_next)
+        self.last_ms = (ms1, ms2)
+        return out
+
     def dilate(self, vol, radius: float):
         be = self.backend
         nx, ny = be.shape(vol)
         J = int(math.floor(radius))
         if self.world > 1 and ny < J:
             raise ValueError(f"slab of {ny} rows is thinner than the halo ({J} rows): use fewer ranks")
+        if self.world > 1 and J > 0 and hasattr(be, "slab_begin"):
+            out = self._dilate_overlapped(vol, radius, nx, ny, J)
+            if out is not None:
+                return out
         halo_prev = halo_next = None
         if self.world > 1 and J > 0:
             halo_prev, halo_next = self._exchange(vol, nx, ny, J)
