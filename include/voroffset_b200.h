@@ -156,8 +156,13 @@ int  vo_dmid_info(const vo_dmid *mid, int *nx, int *ny, int *classes, uint64_t *
  * of the halos' interval counts, agreed with the neighbours beforehand. VO_ERR_ARG from vo_slab_begin = not a case
  * for the overlapped path (small grid, radius < 1, ...): use vo_pass1_dev / vo_pass2_dev on the concatenated rows.   */
 typedef struct vo_slab vo_slab;
+/* d_off_to_* / d_spans_to_* (optional): send buffers of the two neighbours. The boundary rows are packed into them on
+ * the device before pass 1 starts - floor(R)*nx + 1 offsets, then [interval count, overflow flag]; the spans only
+ * when they fit cap_to_* (flag 1 otherwise) - and comm_stream (a cudaStream_t) is made to wait for that packing.      */
 int  vo_slab_begin(vo_ctx *ctx, const vo_dvol *own, double radius, int has_prev, int has_next,
-                   uint64_t cap_prev, uint64_t cap_next, vo_slab **out);
+                   uint64_t cap_prev, uint64_t cap_next,
+                   void *d_off_to_prev, void *d_spans_to_prev, uint64_t cap_to_prev,
+                   void *d_off_to_next, void *d_spans_to_next, uint64_t cap_to_next, void *comm_stream, vo_slab **out);
 int  vo_slab_finish(vo_ctx *ctx, vo_slab *slab, const void *d_off_prev, const void *d_spans_prev, uint64_t n_prev,
                     const void *d_off_next, const void *d_spans_next, uint64_t n_next,
                     vo_dvol **out, double *ms_pass1, double *ms_pass2);

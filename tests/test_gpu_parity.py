@@ -220,7 +220,8 @@ def test_overlapped_slab_api_matches_single_call(ctx):
             halos.append((off, sp, int(n.value)))
         slab = C.c_void_p()
         rc = ctx.lib.vo_slab_begin(ctx.handle, own.handle, R, int(halos[0] is not None), int(halos[1] is not None),
-                                   halos[0][2] + 100 if halos[0] else 0, halos[1][2] + 7 if halos[1] else 0, C.byref(slab))
+                                   halos[0][2] + 100 if halos[0] else 0, halos[1][2] + 7 if halos[1] else 0,
+                                   None, None, 0, None, None, 0, None, C.byref(slab))
         assert rc == 0, ctx.lib.vo_last_error(ctx.handle)
         args = []
         for h in halos:
@@ -233,7 +234,19 @@ def test_overlapped_slab_api_matches_single_call(ctx):
     # a small grid is declined (the caller then takes the plain path)
     small = morpho.DeviceVolume.upload(ctx, synth.blobs(24, padding=2, seed=3))
     slab = C.c_void_p()
-    assert ctx.lib.vo_slab_begin(ctx.handle, small.handle, 3.0, 0, 1, 0, 1000, C.byref(slab)) == 1
+    assert ctx.lib.vo_slab_begin(ctx.handle, small.handle, 3.0, 0, 1, 0, 1000, None, None, 0, None, None, 0, None, C.byref(slab)) == 1
+    # the device-side halo packing (what a rank sends): offsets from 0, [count, overflow], spans when they fit
+    J2, nx2 = 20, vol.nx
+    off = torch.zeros(J2 * nx2 + 3, dtype=torch.int32, device=dev)
+    sp = torch.zeros(2 * 50000, dtype=torch.float64, device=dev)
+    rc = ctx.lib.vo_slab_begin(ctx.handle, d.handle, R, 0, 1, 0, 1000, None, None, 0, off.data_ptr(), sp.data_ptr(), 50000,
+                               torch.cuda.current_stream(dev).cuda_stream, C.byref(slab))
+    assert rc == 0
+    ctx.lib.vo_slab_abort(ctx.handle, slab)
+    want = vol.off[(vol.ny - J2) * nx2:].astype(np.int64)
+    got = off.cpu().numpy()
+    assert np.array_equal(got[:J2 * nx2 + 1], want - want[0]) and got[J2 * nx2 + 1] == want[-1] - want[0] and got[J2 * nx2 + 2] == 0
+    assert np.array_equal(sp.cpu().numpy()[:2 * (want[-1] - want[0])].reshape(-1, 2), vol.spans[want[0]:want[-1]])
 
 
 # ---- xor --------------------------------------------------------------------------------------------------

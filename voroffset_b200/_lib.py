@@ -92,7 +92,8 @@ def load() -> C.CDLL:
     L.vo_elapsed_ms.argtypes = [_vp, C.c_int, C.c_int, _f64p]
     L.vo_last_profile.argtypes = [_vp, _f64p, _f64p]
     L.vo_dvol_from_device.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp)]
-    L.vo_slab_begin.argtypes = [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(_vp)]
+    L.vo_slab_begin.argtypes = [_vp, _vp, C.c_double, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, _vp, C.POINTER(_vp)]
     L.vo_slab_finish.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, C.POINTER(_vp), _f64p, _f64p]
     L.vo_slab_abort.argtypes = [_vp, _vp]
     L.vo_slab_abort.restype = None

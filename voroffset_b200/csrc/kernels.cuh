@@ -793,6 +793,21 @@ __global__ void __launch_bounds__(256) k_rebase(uint32_t *off, unsigned long lon
 	if (i < n) off[i] = off[i] - base + add;
 }
 
+// Rows [c0, c1) (columns) of a volume packed for a halo message: offsets rebased to 0, then the header
+// [interval count, overflow flag], spans copied when they fit `cap` intervals (voroffset_b200/slab.py protocol).
+__global__ void __launch_bounds__(256) k_halo_pack(const uint32_t *__restrict__ off, const double2 *__restrict__ spans,
+                                                   unsigned long long c0, unsigned long long c1, uint32_t *__restrict__ out_off,
+                                                   double2 *__restrict__ out_spans, unsigned long long cap)
+{
+	const uint32_t b = off[c0], e = off[c1];
+	const unsigned long long n = c1 - c0, cnt = e - b;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	for (unsigned long long i = t0; i <= n; i += stride) out_off[i] = off[c0 + i] - b;
+	if (t0 == 0) { out_off[n + 1] = (uint32_t)(cnt & 0x7fffffffu); out_off[n + 2] = cnt > cap ? 1u : 0u; }
+	if (cnt <= cap)
+		for (unsigned long long k = t0; k < cnt; k += stride) out_spans[k] = spans[b + k];
+}
+
 // Sum of (z2 - z1) per block, accumulated in double with a fixed tree order; host adds the partials.
 __global__ void __launch_bounds__(256) k_sum(const double *__restrict__ v, unsigned long long n, double *__restrict__ partial)
 {

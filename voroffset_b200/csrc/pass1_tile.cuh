@@ -61,6 +61,7 @@ constexpr int P1_CB = 4;        // classes evaluated together in registers
 constexpr int P1_LCAP_S = 24;   // survivors listed per output column, single-interval launch
 constexpr int P1_LCAP_M = 64;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
 constexpr int P1_MAXWARPS = 16; // warps per CTA (one CTA per SM; fewer when the per-warp buffers are large)
+constexpr int P1_OVF = 224;     // further survivors per output column kept in a global-memory spill area of the warp
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
 {
@@ -177,7 +178,8 @@ struct Pass1TileArgs {
 	int nx, ny, J, cmax;
 	int tiles_xw;           // tiles (P1_W columns) per row
 	int tiles_x;            // tile masks (P1_TX columns) per row
-	unsigned int tile0, ntiles;         // tiles [tile0, tile0 + ntiles) when `tiles` is NULL
+	unsigned int tile0, ntiles;         // tiles [tile0, tile0 + ntiles0) and [tile0b, tile0b + ntiles - ntiles0) when `tiles` is NULL
+	unsigned int tile0b, ntiles0;
 	const uint32_t *off;
 	const double2 *spans;
 	const uint4 *thr;       // k_thresh output
@@ -190,6 +192,7 @@ struct Pass1TileArgs {
 	double2 *pool;
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
+	uint32_t *ovf;          // [CTAs * warps][P1_OVF][P1_W]: survivor entries beyond the shared-memory lists
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
 	// Device-side dispatch (no host round trip between the launches). Every launch is one resident wave of CTAs
 	// pulling tiles with an atomic counter (tile costs vary a lot):
@@ -343,6 +346,7 @@ struct Tile {
 	const uint8_t *jmax;
 	uint32_t *cnt;             // [P1_W] list lengths
 	uint32_t *list;            // [s * P1_W + xi]
+	uint32_t *ovf;             // [(s - LCAP) * P1_W + xi], global memory
 	int J, JPP;
 
 	__device__ __forceinline__ void push(int xo, int k, uint32_t w) const
@@ -351,8 +355,9 @@ struct Tile {
 		do {
 			const int cu = min(nu, 15), cd = min(nd, 15);
 			const uint32_t pos = atomicAdd(cnt + xo, 1u);
-			if (pos < (uint32_t)LCAP)
-				list[pos * P1_W + xo] = (uint32_t)k | ((uint32_t)lu << 11) | ((uint32_t)cu << 17) | ((uint32_t)ld << 21) | ((uint32_t)cd << 27);
+			const uint32_t e = (uint32_t)k | ((uint32_t)lu << 11) | ((uint32_t)cu << 17) | ((uint32_t)ld << 21) | ((uint32_t)cd << 27);
+			if (pos < (uint32_t)LCAP) list[pos * P1_W + xo] = e;
+			else if (pos < (uint32_t)(LCAP + P1_OVF)) ovf[(pos - LCAP) * P1_W + xo] = e;
 			lu += cu; nu -= cu; ld += cd; nd -= cd;
 		} while (nu > 0 || nd > 0);
 	}
@@ -426,7 +431,7 @@ struct TileThread {
 	__device__ __forceinline__ bool survivor(int s, int &k, int &d, uint32_t &w) const
 	{
 		if (!direct) {
-			const uint32_t e = t.list[s * P1_W + xi];
+			const uint32_t e = s < LCAP ? t.list[s * P1_W + xi] : t.ovf[(s - LCAP) * P1_W + xi];
 			k = (int)(e & 2047u);
 			d = abs((int)t.ci[k] - ix);
 			w = entry_windows(e);
@@ -614,8 +619,8 @@ __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHe
 	if (active) {
 		t.kb = (int)(s_off[ix - J] - h.base);
 		const int S = (int)tl.cnt[xi];
-		// more survivors than the list holds (steep walls, many layers): re-scan the candidate range instead
-		t.direct = S > LCAP;
+		// more survivors than the lists hold (very many layers): re-scan the candidate range instead
+		t.direct = S > LCAP + P1_OVF;
 		t.niter = t.direct ? (int)(s_off[ix + J + 1] - h.base) - t.kb : S;
 		for (int s = 0; s < t.niter; ++s) {
 			int k, d;
@@ -710,12 +715,13 @@ __global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArg
 	__syncthreads();                                        // the only CTA barrier: tables (and mbarriers) are in place
 
 	Tile<LCAP> tl;
-	tl.Ht = tb.Ht; tl.Ef = tb.Ef; tl.jmax = tb.jmax; tl.cnt = sm.cnt; tl.list = sm.list; tl.J = J; tl.JPP = pass1_jpp(J);
+	tl.Ht = tb.Ht; tl.Ef = tb.Ef; tl.jmax = tb.jmax; tl.cnt = sm.cnt; tl.list = sm.list; tl.J = J;
+	tl.ovf = a.ovf + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * (size_t)P1_OVF * P1_W; tl.JPP = pass1_jpp(J);
 
 	// segment offsets of the tile at list position `pos` -> registers (o[r][1] = the next column's offset, for the
 	// multi-interval test)
 	auto load_offsets = [&](unsigned int pos, uint32_t (&o)[NR][2], TileHead &h) {
-		h.tile = LIST ? a.tiles[pos] : a.tile0 + pos;
+		h.tile = LIST ? a.tiles[pos] : (pos < a.ntiles0 ? a.tile0 + pos : a.tile0b + (pos - a.ntiles0));
 		h.y = (int)(h.tile / (unsigned)a.tiles_xw);
 		h.x0 = (int)(h.tile % (unsigned)a.tiles_xw) * P1_W;
 		h.txe = min(P1_W, a.nx - h.x0);

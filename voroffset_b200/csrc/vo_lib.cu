@@ -41,6 +41,7 @@ struct vo_ctx {
 	void *table_cache = nullptr;      // TableCache*: cap tables of the last radius, kept on the device
 	unsigned long long pool_hint = 0; // mid-pool entries the last pass 1 needed (+25 %)
 	unsigned long long stage_hint = 0; // staging-pool entries the last staged gather needed (+25 %)
+	uint32_t *ovf = nullptr;          // spill area of the tile kernel's survivor lists (pass1_tile.cuh), allocated on first use
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
@@ -521,6 +522,10 @@ struct TilePlan {
 		tiles_xw = (nx + P1_W - 1) / P1_W;
 		tiles_x = (nx + P1_TX - 1) / P1_TX;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+		if (!ctx->ovf) {
+			cudaError_t ea = cudaMalloc((void **)&ctx->ovf, (size_t)sms * P1_MAXWARPS * P1_OVF * P1_W * sizeof(uint32_t));
+			if (ea != cudaSuccess) { cudaGetLastError(); ctx->ovf = nullptr; return fail(ctx, VO_ERR_NOMEM, "spill area of the tile kernel"); }
+		}
 		const int SEG = P1_W + 2 * J;
 		auto pick = [](double est) { int c = 64; while (c < CMAX && c < est) c <<= 1; return c; };
 		// launch 1 only sees single-interval columns: at most SEG candidates
@@ -544,10 +549,15 @@ struct TilePlan {
 	}
 	// The three launches over the tiles [tile0, tile0 + ntiles). `g` holds the data pointers; the lists and cursors
 	// ([3] big count, [5] multi count, [6] [7] [10] cursors of d_ctr) must be zero.
-	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles, unsigned int *big_tiles, unsigned int *multi_tiles,
-	            cudaStream_t s) const
+	// A second range [tile0b, tile0b + ntilesb) may follow the first; reserve_sms CTAs fewer are launched (room for the
+	// NCCL kernels of a halo exchange in flight).
+	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles0, unsigned int *big_tiles, unsigned int *multi_tiles,
+	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0) const
 	{
-		g.J = J; g.tiles_xw = tiles_xw; g.tiles_x = tiles_x; g.tile0 = tile0; g.ntiles = ntiles;
+		const unsigned int ntiles = ntiles0 + ntilesb;
+		const int sms = std::max(1, this->sms - reserve_sms);
+		g.J = J; g.tiles_xw = tiles_xw; g.tiles_x = tiles_x; g.tile0 = tile0; g.ntiles = ntiles; g.tile0b = tile0b; g.ntiles0 = ntiles0;
+		g.ovf = ctx->ovf;
 		unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
 		unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
 		g.big_count = big_count; g.multi_tiles = multi_tiles; g.multi_count = multi_count;
@@ -1290,9 +1300,11 @@ void free_slab(vo_slab *S)
 	delete S;
 }
 
-// pass 1 (thresholds + the three tile launches + redo) of rows [y0, y1) of the extended volume; no host sync
-void slab_pass1_rows(vo_slab *S, int y0, int y1)
+// pass 1 (thresholds + the three tile launches + redo) of rows [y0, y1) and [y0b, y1b) of the extended volume; no
+// host sync
+void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int reserve_sms = 0)
 {
+	if (y1 <= y0) { y0 = y0b; y1 = y1b; y0b = y1b = 0; }
 	if (y1 <= y0) return;
 	vo_ctx *ctx = S->ctx;
 	cudaStream_t sm = ctx->stream;
@@ -1308,6 +1320,11 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1)
 	ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
 	k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
 	ctx->launches++;
+	if (y1b > y0b) {
+		ta.c_begin = (unsigned long long)y0b * nx; ta.c_end = (unsigned long long)y1b * nx;
+		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
+		ctx->launches++;
+	}
 	vo_dmid *m = S->mid;
 	Redo rd{S->redo_list, reinterpret_cast<unsigned int *>(ctx->d_ctr + 2), S->redo_cap};
 	Pass1TileArgs g;
@@ -1315,7 +1332,8 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1)
 	g.off = S->ext->off; g.spans = S->ext->spans; g.thr = S->thr; g.Ht = tc->tt.Ht; g.Ef = tc->tt.Ef; g.jmax = tc->tt.jmax;
 	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rd;
 	S->plan.launch(ctx, g, (unsigned int)S->plan.tiles_xw * (unsigned int)y0, (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0),
-	               S->big_tiles, S->multi_tiles, sm);
+	               S->big_tiles, S->multi_tiles, sm, (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
+	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms);
 	Pass1Args a1;
 	a1.nx = nx; a1.ny = S->ext->ny; a1.J = J; a1.off = S->ext->off; a1.spans = S->ext->spans; a1.H = tc->dt.H; a1.reach = tc->dt.reach;
 	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rd;
@@ -1324,7 +1342,10 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1)
 	ctx->launches++;
 }
 
-int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_next, uint64_t cap_prev, uint64_t cap_next, vo_slab **out)
+struct HaloOut { void *d_off; void *d_spans; uint64_t cap; };   // send buffer of one neighbour (d_off == NULL: none)
+
+int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_next, uint64_t cap_prev, uint64_t cap_next,
+               HaloOut to_prev, HaloOut to_next, void *wait_stream, vo_slab **out)
 {
 	VO_TRY(check_radius(ctx, R));
 	const int J = (int)std::floor(R), nx = own->nx, ny = own->ny;
@@ -1372,14 +1393,30 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	if (!ok) { cudaGetLastError(); return bail(fail(ctx, VO_ERR_CUDA, "cudaEventCreate")); }
 	cudaStream_t sm = ctx->stream;
 	cudaEventRecord(S->ev0, sm);
+	// the halos this rank SENDS are packed first (device side, no host round trip), so that the exchange can start
+	// while pass 1 runs; `wait_stream` (the caller's communication stream) is made to wait for them
+	if (has_prev && to_prev.d_off) {
+		k_halo_pack<<<64, 256, 0, sm>>>(own->off, own->spans, 0ull, (unsigned long long)J * nx, static_cast<uint32_t *>(to_prev.d_off),
+		                                static_cast<double2 *>(to_prev.d_spans), to_prev.cap);
+		ctx->launches++;
+	}
+	if (has_next && to_next.d_off) {
+		k_halo_pack<<<64, 256, 0, sm>>>(own->off, own->spans, (unsigned long long)(ny - J) * nx, (unsigned long long)ny * nx,
+		                                static_cast<uint32_t *>(to_next.d_off), static_cast<double2 *>(to_next.d_spans), to_next.cap);
+		ctx->launches++;
+	}
+	if ((to_prev.d_off || to_next.d_off)) {
+		cudaEventRecord(S->ev1, sm);
+		cudaStreamWaitEvent(static_cast<cudaStream_t>(wait_stream), S->ev1, 0);
+	}
 	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
 	cudaMemsetAsync(m->tilemask, 0, nmask * sizeof(unsigned long long), sm);
 	// own rows into the extended volume: offsets shifted by the reserved region of the previous halo
 	cudaMemcpyAsync(S->ext->off + (size_t)jp * nx, own->off, (nown + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
 	if (cap_prev) { k_rebase<<<blocks_for(nown + 1, 256), 256, 0, sm>>>(S->ext->off + (size_t)jp * nx, nown + 1, 0u, (uint32_t)cap_prev); ctx->launches++; }
 	if (own->nspans) cudaMemcpyAsync(S->ext->spans + cap_prev, own->spans, own->nspans * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
-	// rows whose thresholds only read own rows
-	slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0));
+	// rows whose thresholds only read own rows (a few SMs stay free for the exchange's kernels)
+	slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0), 0, 0, 8);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)));
 	*out = S;
@@ -1409,8 +1446,7 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 		ctx->launches++;
 		if (n_next) cudaMemcpyAsync(S->ext->spans + S->cap_prev + S->n_own, d_spans_next, n_next * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
 	}
-	if (jp) slab_pass1_rows(S, 0, jp + 1);
-	if (jn) slab_pass1_rows(S, jp + ny - 1, jp + ny + jn);
+	slab_pass1_rows(S, 0, jp ? jp + 1 : 0, jp + ny - 1, jn ? jp + ny + jn : 0);
 	cudaEventRecord(S->ev1, sm);
 	unsigned long long h[NCTR];
 	VO_TRY(read_counters(ctx, h));
@@ -1482,6 +1518,7 @@ void vo_destroy(vo_ctx *ctx)
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	free_table_cache(ctx);
 	if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+	if (ctx->ovf) cudaFree(ctx->ovf);
 	for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
@@ -1783,13 +1820,15 @@ int vo_dmid_info(const vo_dmid *m, int *nx, int *ny, int *classes, uint64_t *byt
 }
 
 int vo_slab_begin(vo_ctx *ctx, const vo_dvol *own, double radius, int has_prev, int has_next, uint64_t cap_prev, uint64_t cap_next,
-                  vo_slab **out)
+                  void *d_off_to_prev, void *d_spans_to_prev, uint64_t cap_to_prev,
+                  void *d_off_to_next, void *d_spans_to_next, uint64_t cap_to_next, void *comm_stream, vo_slab **out)
 {
 	if (!ctx || !own || !out) return VO_ERR_ARG;
 	ctx->err.clear();
 	DeviceGuard g(ctx->device);
 	*out = nullptr;
-	return slab_begin(ctx, own, radius, has_prev, has_next, cap_prev, cap_next, out);
+	return slab_begin(ctx, own, radius, has_prev, has_next, cap_prev, cap_next, HaloOut{d_off_to_prev, d_spans_to_prev, cap_to_prev},
+	                  HaloOut{d_off_to_next, d_spans_to_next, cap_to_next}, comm_stream, out);
 }
 
 int vo_slab_finish(vo_ctx *ctx, vo_slab *slab, const void *d_off_prev, const void *d_spans_prev, uint64_t n_prev,

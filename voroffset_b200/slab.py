@@ -104,11 +104,16 @@ class CudaSlabBackend:
             vol.free()
 
     # -- overlapped form: pass 1 of the halo-independent rows runs while the halos travel ----------------
-    def slab_begin(self, vol: DeviceVolume, radius: float, has_prev: bool, has_next: bool, cap_prev: int, cap_next: int):
-        """Returns an opaque handle, or None when the library declines (small grids, radius < 1, ...)."""
+    def slab_begin(self, vol: DeviceVolume, radius: float, prev_link, next_link):
+        """Packs the two outgoing halos into the links' send buffers (on the device) and starts pass 1 of the rows
+        that need no halo. Returns an opaque handle, or None when the library declines (small grids, radius < 1, ...)."""
         h = C.c_void_p()
-        rc = self.ctx.lib.vo_slab_begin(self.ctx.handle, vol.handle, float(radius), int(has_prev), int(has_next),
-                                        int(cap_prev), int(cap_next), C.byref(h))
+        send = []
+        for lk in (prev_link, next_link):
+            send += [None, None, 0] if lk is None else [lk.off_out.data_ptr(), lk.sp_out.data_ptr(), int(lk.cap_out)]
+        rc = self.ctx.lib.vo_slab_begin(self.ctx.handle, vol.handle, float(radius), int(prev_link is not None), int(next_link is not None),
+                                        int(prev_link.cap_in) if prev_link else 0, int(next_link.cap_in) if next_link else 0,
+                                        *send, torch.cuda.current_stream(self.device).cuda_stream, C.byref(h))
         if rc == 1:                                   # VO_ERR_ARG: not a case for the overlapped path
             return None
         self.ctx.check(rc)
@@ -252,62 +257,66 @@ class SlabDilation:
         return halos.get(self.rank - 1), halos.get(self.rank + 1)
 
     def _dilate_overlapped(self, vol, radius: float, nx: int, ny: int, J: int):
-        """Steady-state step on a backend with slab_begin / slab_finish: the single message batch is posted first,
-        pass 1 of the rows that do not depend on a halo runs while it travels. Returns None when this step has to
-        take the plain path (first call on a link, a halo that outgrew its capacity, library declines)."""
+        """Steady-state step on a backend with slab_begin / slab_finish: the outgoing halos are packed on the device,
+        the single message batch travels while pass 1 of the rows that do not depend on a halo runs. Returns None
+        when this step has to take the plain path from the start (first call on a link, library declines)."""
         be = self.backend
         if self._shape != (nx, J):
             return None
         L = J * nx + 1
         nbrs = [(r, rows) for r, rows in ((self.rank - 1, (0, J)), (self.rank + 1, (ny - J, ny))) if 0 <= r < self.world]
         links = {r: self._links.get(r) for r, _ in nbrs}
-        if any(lk is None or lk.cap_out is None or lk.cap_in is None or lk.off_in is None for lk in links.values()):
+        for lk in links.values():
+            if lk is None or lk.cap_out is None or lk.cap_in is None or lk.off_in is None or lk.off_out is None:
+                return None
+            if lk.sp_out.numel() // 2 < lk.cap_out:
+                lk.off_out, lk.sp_out = be.new_tensors(L + 2, lk.cap_out)
+            if lk.sp_in.numel() // 2 < lk.cap_in:
+                lk.off_in, lk.sp_in = be.new_tensors(L + 2, lk.cap_in)
+        slab = be.slab_begin(vol, radius, links.get(self.rank - 1), links.get(self.rank + 1))
+        if slab is None:
             return None
-        n_out = {}
-        for r, (y0, y1) in nbrs:
-            lk = links[r]
-            n = be.rows_into(vol, y0, y1, lk.off_out, lk.sp_out)
-            if n > lk.cap_out or lk.sp_out.numel() // 2 < lk.cap_out or lk.sp_in.numel() // 2 < lk.cap_in:
-                return None                           # (rows_into left the buffers reusable: the plain path repeats it)
-            n_out[r] = n
         ops, nbytes = [], 0
         for r, _ in nbrs:
             lk = links[r]
-            lk.off_out[L:L + 2] = torch.tensor([n_out[r] & 0x7fffffff, 0], dtype=torch.int32, device=lk.off_out.device)
             ops += [dist.P2POp(dist.isend, lk.off_out, r, self.group), dist.P2POp(dist.irecv, lk.off_in, r, self.group),
                     dist.P2POp(dist.isend, lk.sp_out[: 2 * lk.cap_out], r, self.group),
                     dist.P2POp(dist.irecv, lk.sp_in[: 2 * lk.cap_in], r, self.group)]
             nbytes += 2 * lk.cap_out * 8 + (L + 2) * 4
-        works = dist.batch_isend_irecv(ops)
-        prev_lk, next_lk = links.get(self.rank - 1), links.get(self.rank + 1)
-        slab = be.slab_begin(vol, radius, prev_lk is not None, next_lk is not None,
-                             prev_lk.cap_in if prev_lk else 0, next_lk.cap_in if next_lk else 0)
-        for w in works:
+        for w in dist.batch_isend_irecv(ops):
             w.wait()
         self.last_messages, self.last_halo_bytes = 1, nbytes
-        hdr = {r: links[r].off_in[L:L + 2].tolist() for r, _ in nbrs}
-        overflow = any(h[1] for h in hdr.values())
+        order = [r for r, _ in nbrs]
+        hdrs = torch.stack([links[r].off_in[L:L + 2] for r in order] + [links[r].off_out[L:L + 2] for r in order]).tolist()
+        hdr_in = {r: hdrs[i] for i, r in enumerate(order)}
+        hdr_out = {r: hdrs[len(order) + i] for i, r in enumerate(order)}
+        overflow = any(h[1] for h in hdr_in.values()) or any(h[1] for h in hdr_out.values())
+        exact_in = {}
         if overflow:
-            # a neighbour's halo outgrew the agreed capacity: its exact payload follows; this step finishes on the plain path
-            ops, exact_in = [], {}
-            for r, _ in nbrs:
-                if hdr[r][1]:
-                    _, exact_in[r] = be.new_tensors(1, int(hdr[r][0]))
-                    ops.append(dist.P2POp(dist.irecv, exact_in[r][: 2 * int(hdr[r][0])], r, self.group))
+            # a halo outgrew its agreed capacity: the exact payload follows, this step finishes on the plain path
+            ops, keep = [], []
+            for r, (y0, y1) in nbrs:
+                if hdr_in[r][1]:
+                    _, exact_in[r] = be.new_tensors(1, int(hdr_in[r][0]))
+                    ops.append(dist.P2POp(dist.irecv, exact_in[r][: 2 * int(hdr_in[r][0])], r, self.group))
+                if hdr_out[r][1]:
+                    off_tmp, exact = be.new_tensors(L + 2, int(hdr_out[r][0]))
+                    be.rows_into(vol, y0, y1, off_tmp, exact)
+                    keep.append(exact)
+                    ops.append(dist.P2POp(dist.isend, exact[: 2 * int(hdr_out[r][0])], r, self.group))
             self._batch(ops)
         parts = {}
         for r, _ in nbrs:
             lk = links[r]
-            n_in = int(hdr[r][0])
-            parts[r] = (lk.off_in, exact_in[r] if overflow and hdr[r][1] else lk.sp_in, n_in)
+            n_in = int(hdr_in[r][0])
+            parts[r] = (lk.off_in, exact_in.get(r, lk.sp_in), n_in)
             lk.cap_in = max(lk.cap_in, _grow(n_in))
-            lk.cap_out = max(lk.cap_out, _grow(n_out[r]))
-        if slab is not None and not overflow:
+            lk.cap_out = max(lk.cap_out, _grow(int(hdr_out[r][0])))
+        if not overflow:
             out, ms1, ms2 = be.slab_finish(slab, parts.get(self.rank - 1), parts.get(self.rank + 1), like=vol)
             self.last_ms = (ms1, ms2)
             return out
-        if slab is not None:
-            be.slab_abort(slab)
+        be.slab_abort(slab)
         halos = {r: be.from_tensors(nx, J, p[0], p[1], p[2], like=vol) for r, p in parts.items()}
         return self._finish_plain(vol, radius, ny, J, halos.get(self.rank - 1), halos.get(self.rank + 1))
 
