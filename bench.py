@@ -12,7 +12,7 @@ One JSON line on stdout (rank 0):
   value        whole-job columns/s with inputs resident in HBM (CUDA events on the library's stream)
   e2e          the same through the host-buffer C-ABI call (vo_morph3d): H2D of the CSR input from pinned
                memory, both passes, D2H of the CSR result, all inside the timed region
-  roofline     dominant kernel (k_pass1): algorithmic bytes / its event-timed duration
+  roofline     dominant kernel (k_pass1_tile): algorithmic bytes / its event-timed duration
   cpu_baseline the reference's own code (oracle/_ref) on a bounded sample with all host threads
 """
 from __future__ import annotations
@@ -330,7 +330,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches),
             "pass_ms": {"pass1": statistics.mean(p1_ms), "pass2": statistics.mean(p2_ms),
                         "k_pass1": k1, "k_pass2": statistics.mean(k2_ms)},
-            "roofline": {"bound": "hbm", "kernel": "k_pass1_tile<16>", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_pass1_tile (the three tile launches of pass 1)", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": ncu_traffic(a.n, R), "peak_source": peak_src,
                          "algorithmic_bytes_per_column": b1, "k_mid": k_mid, "k_mid_source": k_mid_src,
                          "definition": "SURVEY.md 8(d): B1 = (4 + 16 k_in) + (4 + 24 k_mid) bytes per column, k_mid = pieces per "

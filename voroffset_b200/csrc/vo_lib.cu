@@ -1331,9 +1331,12 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	g.nx = nx; g.ny = S->ext->ny;
 	g.off = S->ext->off; g.spans = S->ext->spans; g.thr = S->thr; g.Ht = tc->tt.Ht; g.Ef = tc->tt.Ef; g.jmax = tc->tt.jmax;
 	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rd;
+	const bool interior = reserve_sms > 0;               // the large launch: the one vo_last_profile reports
+	if (interior) cudaEventRecord(ctx->kev[0], sm);
 	S->plan.launch(ctx, g, (unsigned int)S->plan.tiles_xw * (unsigned int)y0, (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0),
 	               S->big_tiles, S->multi_tiles, sm, (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
 	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms);
+	if (interior) { cudaEventRecord(ctx->kev[1], sm); ctx->kev_valid[0] = true; }
 	Pass1Args a1;
 	a1.nx = nx; a1.ny = S->ext->ny; a1.J = J; a1.off = S->ext->off; a1.spans = S->ext->spans; a1.H = tc->dt.H; a1.reach = tc->dt.reach;
 	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rd;
