@@ -209,6 +209,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     ctx = _lib.Context(local)
+    if os.environ.get("VO_SLAB"):                   # development switch: "overlap" / "serial" halo exchange
+        ctx.set_option("slab", os.environ["VO_SLAB"])
     vol = synth.torus_z(a.n)                       # this rank's slab: rows [rank*n, (rank+1)*n) of the global grid
     R = a.radius
     ncols = vol.nx * vol.ny

@@ -193,6 +193,7 @@ struct Pass1TileArgs {
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
 	uint32_t *ovf;          // [CTAs * warps][P1_OVF][P1_W]: survivor entries beyond the shared-memory lists
+	unsigned long long *dbg;   // development aid (NULL normally): per tile {cycles, candidates, survivor entries, cycles of phase 1}
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
 	// Device-side dispatch (no host round trip between the launches). Every launch is one resident wave of CTAs
 	// pulling tiles with an atomic counter (tile costs vary a lot):
@@ -789,6 +790,7 @@ __global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArg
 		if (have_next) load_offsets(npos, o, nxt);
 
 		// ---- current tile, phase 1 ----
+		const long long dbg_t0 = a.dbg ? clock64() : 0;
 		if (cur.kind == TK_NORMAL) {
 			mbar_wait(sm.mbar + buf, phase[buf]);            // candidates and thresholds have landed
 			phase[buf] ^= 1u;
@@ -805,8 +807,16 @@ __global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArg
 		__syncwarp();                                       // phase 1 of the current tile is complete (lists visible)
 
 		// ---- current tile, phase 2 ----
+		unsigned int dbg_entries = 0;
+		const long long dbg_t1 = a.dbg ? clock64() : 0;
+		if (a.dbg && cur.kind == TK_NORMAL) { __syncwarp(); dbg_entries = __reduce_add_sync(FULL, sm.cnt[lane]); }
 		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP>(a, cur, tl, sm.off[buf]);
 		__syncwarp();                                       // lists, counters and the staging buffer are free again
+		if (a.dbg && lane == 0 && cur.kind == TK_NORMAL) {     // (scripts/tile_costs.py)
+			unsigned long long *d = a.dbg + 4ull * cur.tile;
+			d[0] = (unsigned long long)(clock64() - dbg_t0); d[1] = (unsigned long long)cur.ncand; d[2] = dbg_entries;
+			d[3] = (unsigned long long)(dbg_t1 - dbg_t0);
+		}
 		if (!have_next) break;
 		cur = nxt;
 		buf ^= 1;

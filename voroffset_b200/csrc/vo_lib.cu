@@ -41,9 +41,12 @@ struct vo_ctx {
 	void *table_cache = nullptr;      // TableCache*: cap tables of the last radius, kept on the device
 	unsigned long long pool_hint = 0; // mid-pool entries the last pass 1 needed (+25 %)
 	unsigned long long stage_hint = 0; // staging-pool entries the last staged gather needed (+25 %)
+	unsigned long long *dbg_tiles = nullptr;   // vo_set_option("tile_debug", "<device pointer>"): per-tile statistics
 	uint32_t *ovf = nullptr;          // spill area of the tile kernel's survivor lists (pass1_tile.cuh), allocated on first use
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
+	int pipe_bands = 4;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
+	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
 	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
 	bool force_tile_pass1 = false;
@@ -558,6 +561,7 @@ struct TilePlan {
 		const int sms = std::max(1, this->sms - reserve_sms);
 		g.J = J; g.tiles_xw = tiles_xw; g.tiles_x = tiles_x; g.tile0 = tile0; g.ntiles = ntiles; g.tile0b = tile0b; g.ntiles0 = ntiles0;
 		g.ovf = ctx->ovf;
+		g.dbg = ctx->dbg_tiles;
 		unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
 		unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
 		g.big_count = big_count; g.multi_tiles = multi_tiles; g.multi_count = multi_count;
@@ -1046,7 +1050,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const uint64_t nspans = off[ncols];
 	const double k_in = (double)nspans / (double)ncols;
 	// about six bands: enough to overlap, few enough that the per-band launch / readback overhead stays small
-	const int BH = std::max(2 * (J + 1), ((ny + 5) / 6 + 7) & ~7);   // band height >= reach of pass 2
+	const int nbw = std::max(3, ctx->pipe_bands);
+	const int BH = std::max(2 * (J + 1), ((ny + nbw - 1) / nbw + 7) & ~7);   // band height >= reach of pass 2
 	const int nb = (ny + BH - 1) / BH;
 	if (nb < 3 || ncols * (unsigned long long)(J + 1) < (48ull << 20) || !TilePlan::fits(J, k_in)) return PIPE_NA;
 	if (nspans && !spans) return PIPE_NA;
@@ -1285,6 +1290,7 @@ struct vo_slab {
 	unsigned long long *redo_list = nullptr;
 	unsigned int redo_cap = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+	bool overlapped = false;
 };
 
 namespace {
@@ -1331,7 +1337,8 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	g.nx = nx; g.ny = S->ext->ny;
 	g.off = S->ext->off; g.spans = S->ext->spans; g.thr = S->thr; g.Ht = tc->tt.Ht; g.Ef = tc->tt.Ef; g.jmax = tc->tt.jmax;
 	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rd;
-	const bool interior = reserve_sms > 0;               // the large launch: the one vo_last_profile reports
+	const bool interior = reserve_sms != 0;              // the large launch: the one vo_last_profile reports
+	reserve_sms = std::max(reserve_sms, 0);
 	if (interior) cudaEventRecord(ctx->kev[0], sm);
 	S->plan.launch(ctx, g, (unsigned int)S->plan.tiles_xw * (unsigned int)y0, (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0),
 	               S->big_tiles, S->multi_tiles, sm, (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
@@ -1418,8 +1425,13 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	cudaMemcpyAsync(S->ext->off + (size_t)jp * nx, own->off, (nown + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
 	if (cap_prev) { k_rebase<<<blocks_for(nown + 1, 256), 256, 0, sm>>>(S->ext->off + (size_t)jp * nx, nown + 1, 0u, (uint32_t)cap_prev); ctx->launches++; }
 	if (own->nspans) cudaMemcpyAsync(S->ext->spans + cap_prev, own->spans, own->nspans * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
-	// rows whose thresholds only read own rows (a few SMs stay free for the exchange's kernels)
-	slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0), 0, 0, 8);
+	// "overlap" (default): the rows whose thresholds only read own rows start now (a few SMs stay free for the
+	// exchange's kernels) and the rest follows in vo_slab_finish. "serial": everything in vo_slab_finish, as ONE launch
+	// set. On the C5 slabs the two are within 1 % of each other (1.68 ms per step on 2 GPUs): every launch of the tile
+	// kernel ends with a tail of a few heavy tiles (steep walls), and the second tail costs what the exchange of
+	// ~100 KB takes; with larger halos the overlap wins.
+	S->overlapped = ctx->slab_overlap;
+	if (S->overlapped) slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0), 0, 0, 8);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)));
 	*out = S;
@@ -1449,7 +1461,8 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 		ctx->launches++;
 		if (n_next) cudaMemcpyAsync(S->ext->spans + S->cap_prev + S->n_own, d_spans_next, n_next * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
 	}
-	slab_pass1_rows(S, 0, jp ? jp + 1 : 0, jp + ny - 1, jn ? jp + ny + jn : 0);
+	if (S->overlapped) slab_pass1_rows(S, 0, jp ? jp + 1 : 0, jp + ny - 1, jn ? jp + ny + jn : 0);
+	else slab_pass1_rows(S, 0, jp + ny + jn, 0, 0, -1);
 	cudaEventRecord(S->ev1, sm);
 	unsigned long long h[NCTR];
 	VO_TRY(read_counters(ctx, h));
@@ -1542,6 +1555,18 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "pipeline") == 0) {
 		if (std::strcmp(value, "off") == 0) { ctx->no_pipeline = true; return VO_OK; }
 		if (std::strcmp(value, "on") == 0 || std::strcmp(value, "auto") == 0) { ctx->no_pipeline = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "slab") == 0) {
+		if (std::strcmp(value, "overlap") == 0) { ctx->slab_overlap = true; return VO_OK; }
+		if (std::strcmp(value, "serial") == 0) { ctx->slab_overlap = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "bands") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 3 && n <= 64) { ctx->pipe_bands = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "tile_debug") == 0) {           // development aid: scripts/tile_costs.py
+		ctx->dbg_tiles = reinterpret_cast<unsigned long long *>(std::strtoull(value, nullptr, 0));
+		return VO_OK;
 	}
 	if (std::strcmp(key, "pass1") == 0) {
 		if (std::strcmp(value, "simple") == 0) { ctx->force_simple_pass1 = true; ctx->force_tile_pass1 = false; return VO_OK; }
