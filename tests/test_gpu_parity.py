@@ -87,6 +87,59 @@ def test_tile_kernel_forced_3d(ctx, oracle, name, gen, radius):
         ctx.set_option("pass1", "auto")
 
 
+def test_erosion_with_data_touching_the_z_bounds(ctx, oracle):
+    """Erosion of 'ours' prunes with the clip range of negateInv (pass1_tile.cuh: saturated endpoints). A tight
+    bounding box makes the lowest interval start EXACTLY at zmin and the highest end exactly at zmax
+    (negate_ray's == tests, MorphologyOperators.cpp:241,250): the complement then has columns without a lower /
+    upper part next to columns with one. Forced tile kernel, all four operations, against the oracle."""
+    for seed, kmax, R in ((21, 3, 4.5), (22, 6, 7.2), (23, 1, 9.0)):
+        v = synth.random_volume(70, 40, kmax=kmax, padding=0, seed=seed, fill=0.8)
+        lo, hi = float(v.spans[:, 0].min()), float(v.spans[:, 1].max())
+        # snap a fifth of the columns to the bounds so that many of them touch
+        sp = v.spans.copy()
+        first = v.off[:-1][np.diff(v.off.astype(np.int64)) > 0].astype(np.int64)
+        last = v.off[1:][np.diff(v.off.astype(np.int64)) > 0].astype(np.int64) - 1
+        meta = dict(origin=(0.0, 0.0, lo), extent=(float(v.nx), float(v.ny), hi - lo), spacing=1.0, padding=0)
+        zmax = CompressedVolume(v.nx, v.ny, v.off, sp, **meta).zmax      # lo + (hi - lo), as the reference computes it
+        sp[:, 1] = np.minimum(sp[:, 1], zmax)
+        sp[first[::5], 0] = lo
+        sp[last[::7], 1] = zmax
+        vol = CompressedVolume(v.nx, v.ny, v.off, sp, **meta)
+        assert vol.zmin == lo and vol.zmax == zmax and sp[:, 0].min() == lo and sp[:, 1].max() == zmax
+        op = morpho.make_operator("ours", ctx)
+        for mode in ("auto", "tile"):
+            ctx.set_option("pass1", mode)
+            try:
+                for opn in OPS:
+                    got, _, _ = morpho.apply_operation(op, opn, vol, R)
+                    util.assert_same(got, oracle.morph3d(vol, opn, R, "ours"), opn, "ours", f"z-bounds seed {seed} [{mode}]")
+            finally:
+                ctx.set_option("pass1", "auto")
+
+
+def test_config5_all_operations_ours_vs_brute_force_2048(ctx):
+    """The north-star size (n = 2048, R = 32) for all four operations: the pruned two-pass method against the
+    brute-force sphere union (an independent kernel without any pruning), both on the GPU. Identical topology;
+    endpoints within 1e-11 dexel (the two methods round their caps differently)."""
+    vol = synth.torus_z(2048, padding=34)
+    ours, brute = morpho.make_operator("ours", ctx), morpho.make_operator("brute_force", ctx)
+    d = morpho.DeviceVolume.upload(ctx, vol)
+    for opn in OPS:
+        a, _, _ = ours.morph_dev(opn, d, 32.0)
+        b, _, _ = brute.morph_dev(opn, d, 32.0)
+        ha, hb = a.download(), b.download()
+        a.free(); b.free()
+        assert ha.same_topology(hb), opn
+        assert np.abs(ha.spans - hb.spans).max() <= 1e-11, opn
+    # opening is anti-extensive, closing extensive (single-interval columns)
+    ci = vol.counts()
+    o, _, _ = ours.morph_dev("opening", d, 32.0)
+    c, _, _ = ours.morph_dev("closing", d, 32.0)
+    co, cc = o.download().counts(), c.download().counts()
+    o.free(); c.free()
+    assert np.all(ci[co > 0] >= 1) and np.all(cc[ci > 0] >= 1)
+
+
 def test_many_layers_use_the_redo_path(ctx, oracle):
     # 40 thin layers per column: the running union outgrows the fast capacity (16) and is redone
     rng = np.random.RandomState(0)

@@ -629,6 +629,8 @@ struct NegArgs {
 	uint32_t *cnt;          // count kernel output
 	const uint32_t *out_off;
 	double2 *out_spans;
+	unsigned int *outside;  // (count pass, optional) set when a column has data outside [lo, hi]: the complement is then
+	                        // not a set of proper intervals and erosion must not prune with the clip range
 };
 
 __device__ __forceinline__ bool neg_src(const NegArgs &a, unsigned long long c, uint32_t &o0, uint32_t &o1)
@@ -658,6 +660,7 @@ __global__ void __launch_bounds__(256) k_negate(NegArgs a, unsigned long long nl
 	}
 	const bool f = (a.spans[o0].x == a.lo);          // first event == lo: erased
 	const bool l = (a.spans[o1 - 1].y == a.hi);      // last event == hi: popped
+	if (!FILL && a.outside && (a.spans[o0].x < a.lo || a.spans[o1 - 1].y > a.hi)) *a.outside = 1u;
 	const uint32_t n = k + 1 - (f ? 1u : 0u) - (l ? 1u : 0u);
 	if (!FILL) { a.cnt[c] = n; return; }
 	double2 *dst = a.out_spans + a.out_off[c];

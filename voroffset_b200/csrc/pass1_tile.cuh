@@ -92,6 +92,7 @@ __device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint3
 	double r = inf;
 	for (uint32_t k = q0; k < q1; ++k) {
 		const double2 v = __ldg(q + k);
+		if (!(v.x <= v.y)) continue;                       // (not an interval, see k_thresh)
 		const double ta = v.x <= clo ? -inf : (plo ? inf : v.x - p.x);
 		const double tb = v.y >= chi ? -inf : (phi ? inf : p.y - v.y);
 		r = fmin(r, fmax(ta, tb));
@@ -149,8 +150,13 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	for (uint32_t k = o0; k < o1; ++k) {
 		const double2 p = __ldg(a.spans + k);
 		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
-		const double nnL = nn_of(p, a.spans, l0, l1, a.clip_lo, a.clip_hi), nnR = nn_of(p, a.spans, r0, r1, a.clip_lo, a.clip_hi);
-		const double nnU = nn_of(p, a.spans, u0, u1, a.clip_lo, a.clip_hi), nnD = nn_of(p, a.spans, d0, d1, a.clip_lo, a.clip_hi);
+		// An entry with z1 > z2 is not an interval; it is never pruned and never prunes. (The one known source - the
+		// erosion of data outside [zmin, zmax], where negate_ray prepends the bound without looking,
+		// MorphologyOperators.cpp:241-248 - is sent to the unpruned kernel by erode() anyway.)
+		const bool proper = p.x <= p.y;
+		const double pinf = __longlong_as_double(0x7FF0000000000000LL);
+		const double nnL = proper ? nn_of(p, a.spans, l0, l1, a.clip_lo, a.clip_hi) : pinf, nnR = proper ? nn_of(p, a.spans, r0, r1, a.clip_lo, a.clip_hi) : pinf;
+		const double nnU = proper ? nn_of(p, a.spans, u0, u1, a.clip_lo, a.clip_hi) : pinf, nnD = proper ? nn_of(p, a.spans, d0, d1, a.clip_lo, a.clip_hi) : pinf;
 		// an interval saturated on both sides covers the whole range: it yields to a CLOSER one of its kind (near
 		// tests) but never to a farther one - otherwise two of them could drop each other
 		const bool whole = p.x <= a.clip_lo && p.y >= a.clip_hi;

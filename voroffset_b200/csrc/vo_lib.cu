@@ -768,7 +768,7 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 }
 
 // negate (Voronoi.cpp:18-55) / negateInv (Voronoi.cpp:57-89) / vor2d negate, all count -> scan -> fill
-int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out)
+int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out, unsigned int *outside = nullptr)
 {
 	const int mx = in->nx + 2 * border, my = in->ny + 2 * border;
 	VO_TRY(check_dims(ctx, mx, my));
@@ -780,7 +780,8 @@ int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_
 	if (rc) { free_dvol(ctx, v); return rc; }
 	NegArgs a;
 	a.nx = in->nx; a.ny = in->ny; a.border = border; a.lo = lo; a.hi = hi;
-	a.off = in->off; a.spans = in->spans; a.cnt = cnt.p; a.out_off = nullptr; a.out_spans = nullptr;
+	a.off = in->off; a.spans = in->spans; a.cnt = cnt.p; a.out_off = nullptr; a.out_spans = nullptr; a.outside = outside;
+	if (outside) cudaMemsetAsync(outside, 0, sizeof(unsigned int), ctx->stream);
 	if (nlists) { k_negate<false><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
 	unsigned long long total = 0;
 	rc = scan_counts(ctx, cnt.p, nlists, v->off, &total);
@@ -827,10 +828,22 @@ int erode(vo_ctx *ctx, int method, const vo_dvol *in, double zmin, double zmax, 
 {
 	const double z_min = zmin - 1, z_max = zmax + 1;
 	vo_dvol *neg = nullptr, *dil = nullptr;
-	VO_TRY(negate(ctx, in, 1, z_min, z_max, &neg));
+	unsigned int *outside = reinterpret_cast<unsigned int *>(ctx->d_ctr + NCTR);
+	VO_TRY(negate(ctx, in, 1, z_min, z_max, &neg, outside));
 	// negateInv only reads the dilated complement inside (z_min + 1, z_max - 1): everything at or beyond those bounds
 	// is dropped (MorphologyOperators.cpp:292-312), so 'ours' may prune with that clip range (pass1_tile.cuh: nn_of)
+	// Data outside [z_min, z_max] (no head-room: offset3d's -p) turns the complement into something that is not a
+	// set of intervals (negate_ray prepends / appends the bounds without looking); the reference still computes with
+	// it. k_negate raises a flag then, and that dilation takes the unpruned one-thread-per-slot kernel, which folds
+	// whatever it is given exactly like the reference's unions do.
+	unsigned int h_outside = 0;
+	cudaError_t ec = cudaMemcpyAsync(&h_outside, outside, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream);
+	if (ec == cudaSuccess) ec = cudaStreamSynchronize(ctx->stream);
+	if (ec != cudaSuccess) { free_dvol(ctx, neg); return fail(ctx, VO_ERR_CUDA, std::string("erode: ") + cudaGetErrorString(ec)); }
+	const bool saved_simple = ctx->force_simple_pass1;
+	if (h_outside) ctx->force_simple_pass1 = true;
 	int rc = dilate(ctx, method, neg, R, &dil, pt, z_min + 1, z_max - 1);
+	ctx->force_simple_pass1 = saved_simple;
 	free_dvol(ctx, neg);
 	VO_TRY(rc);
 	rc = negate_inv(ctx, dil, 1, z_min + 1, z_max - 1, out);
@@ -1513,7 +1526,7 @@ int vo_create(int device, vo_ctx **out)
 	for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->mark[i]) == cudaSuccess;
 	for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&ctx->kev[i]) == cudaSuccess;
-	ok = ok && cudaMalloc((void **)&ctx->d_ctr, 16 * sizeof(unsigned long long)) == cudaSuccess;
+	ok = ok && cudaMalloc((void **)&ctx->d_ctr, (NCTR + 8) * sizeof(unsigned long long)) == cudaSuccess;   // [NCTR]: erosion's "data outside the z range" flag
 	if (ok) {
 		// keep freed blocks in the stream-ordered pool: steady-state calls then allocate without the driver
 		cudaMemPool_t pool;
