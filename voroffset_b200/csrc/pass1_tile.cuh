@@ -65,7 +65,9 @@ constexpr int P1_OVF = 224;     // further survivors per output column kept in a
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
 {
-	int lo = 1, hi = J + 1;                       // tab is non-decreasing, tab[J+1] = +inf
+	if (tab[1] >= need) return 1;                 // the two common cases first: contained in the neighbour outright,
+	if (!(tab[J] >= need)) return J + 1;          // ... or no neighbour / nowhere near it
+	int lo = 2, hi = J;                           // tab is non-decreasing, tab[J+1] = +inf
 	while (lo < hi) { const int mid = (lo + hi) >> 1; if (tab[mid] >= need) hi = mid; else lo = mid + 1; }
 	return lo;
 }

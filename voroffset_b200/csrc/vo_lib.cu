@@ -39,8 +39,11 @@ struct vo_ctx {
 	cudaEvent_t kev[4] = {};          // [0,1] around k_pass1<CAP_FAST>, [2,3] around k_pass2<CAP_FAST>
 	bool kev_valid[2] = {false, false};
 	void *table_cache = nullptr;      // TableCache*: cap tables of the last radius, kept on the device
-	unsigned long long pool_hint = 0; // mid-pool entries the last pass 1 needed (+25 %)
-	unsigned long long stage_hint = 0; // staging-pool entries the last staged gather needed (+25 %)
+	// pool sizes the recent calls needed (+25 %), forgotten slowly: opening / closing alternate between a dilation
+	// that needs next to nothing and an erosion that needs millions of entries - a hint that followed the last call
+	// only would make every second pass run twice
+	unsigned long long pool_hint = 0;  // mid-pool entries (pass 1)
+	unsigned long long stage_hint = 0; // staging-pool entries (staged gathers)
 	unsigned long long *dbg_tiles = nullptr;   // vo_set_option("tile_debug", "<device pointer>"): per-tile statistics
 	uint32_t *ovf = nullptr;          // spill area of the tile kernel's survivor lists (pass1_tile.cuh), allocated on first use
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
@@ -97,6 +100,11 @@ int fail(vo_ctx *ctx, int code, const std::string &msg)
 		if (rc_ != VO_OK) return rc_;                                                                   \
 	} while (0)
 
+inline unsigned long long next_hint(unsigned long long hint, unsigned long long used)
+{
+	return std::max(used + used / 4, hint - hint / 8);
+}
+
 inline unsigned int blocks_for(unsigned long long n, int threads)
 {
 	unsigned long long b = (n + threads - 1) / threads;
@@ -107,6 +115,14 @@ template <typename T> int dalloc(vo_ctx *ctx, T **p, unsigned long long count)
 {
 	*p = nullptr;
 	size_t bytes = (size_t)std::max<unsigned long long>(count, 1ull) * sizeof(T);
+	// Large requests are rounded up to eight size classes per octave: the stream-ordered pool then hands the block
+	// of the previous call back even when the grid differs by a border column (erosion) or the result by a few
+	// intervals, instead of mapping fresh memory (milliseconds) every other call.
+	if (bytes >= (1u << 20)) {
+		size_t q = (size_t)1 << 17;
+		while ((q << 4) <= bytes) q <<= 1;
+		bytes = (bytes + q - 1) / q * q;
+	}
 	VO_CUDA(cudaMallocAsync((void **)p, bytes, ctx->stream));
 	return VO_OK;
 }
@@ -346,7 +362,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 		VO_TRY(read_counters(ctx, h));
 		if (h[8] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
 		if (h[9]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
-		ctx->stage_hint = h[1] + h[1] / 4;
+		ctx->stage_hint = next_hint(ctx->stage_hint, h[1]);
 		if (h[1] > sb.st.pool_cap) { VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024)); continue; }
 		if (total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
 		VO_TRY(dalloc(ctx, &v->spans, total));
@@ -686,7 +702,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
 		}
 		if (h[4]) return bail(fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union"));
-		if (h[0] <= m->pool_cap) { m->pool_used = h[0]; ctx->pool_hint = h[0] + h[0] / 4; *out = m; return VO_OK; }
+		if (h[0] <= m->pool_cap) { m->pool_used = h[0]; ctx->pool_hint = next_hint(ctx->pool_hint, h[0]); *out = m; return VO_OK; }
 		dfree(ctx, m->pool);
 		m->pool = nullptr;
 		m->pool_cap = h[0] + h[0] / 8 + 1024;
@@ -1269,7 +1285,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		rc = PIPE_NA;                                           // let the plain path deal with it (it regrows / reports)
 	}
 	if (rc != VO_OK) { drop_host(); return rc; }
-	ctx->pool_hint = h[0] + h[0] / 4;
+	ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
 	ctx->out_hint = base + base / 8 + (1u << 16);
 	float tms = 0;
 	cudaEventElapsedTime(&tms, ctx->ev[0], ctx->ev[2]);
@@ -1483,7 +1499,7 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 	if (h[0] > S->mid->pool_cap) { ctx->pool_hint = h[0] + h[0] / 4; return fail(ctx, VO_ERR_OVERFLOW, "mid pool too small"); }
 	if (h[2] > S->redo_cap || h[4]) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
 	S->mid->pool_used = h[0];
-	ctx->pool_hint = h[0] + h[0] / 4;
+	ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
 	VO_TRY(pass2(ctx, S->mid, jp, jp + ny, out));
 	VO_CUDA(cudaEventRecord(S->ev2, sm));
 	VO_CUDA(cudaEventSynchronize(S->ev2));
