@@ -571,32 +571,34 @@ struct TilePlan {
 	// A second range [tile0b, tile0b + ntilesb) may follow the first; reserve_sms CTAs fewer are launched (room for the
 	// NCCL kernels of a halo exchange in flight).
 	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles0, unsigned int *big_tiles, unsigned int *multi_tiles,
-	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0) const
+	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0,
+	            unsigned long long *bank = nullptr) const
 	{
+		if (!bank) bank = ctx->d_ctr;                       // ([3] [5] [6] [7] [10] of `bank`: the lists and cursors of this launch set)
 		const unsigned int ntiles = ntiles0 + ntilesb;
 		const int sms = std::max(1, this->sms - reserve_sms);
 		g.J = J; g.tiles_xw = tiles_xw; g.tiles_x = tiles_x; g.tile0 = tile0; g.ntiles = ntiles; g.tile0b = tile0b; g.ntiles0 = ntiles0;
 		g.ovf = ctx->ovf;
 		g.dbg = ctx->dbg_tiles;
-		unsigned int *big_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 3);
-		unsigned int *multi_count = reinterpret_cast<unsigned int *>(ctx->d_ctr + 5);
+		unsigned int *big_count = reinterpret_cast<unsigned int *>(bank + 3);
+		unsigned int *multi_count = reinterpret_cast<unsigned int *>(bank + 5);
 		g.big_count = big_count; g.multi_tiles = multi_tiles; g.multi_count = multi_count;
 		auto grid = [&](int nw) { return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)sms, (ntiles + nw - 1) / nw)); };
 		// launch 1: single-interval tiles, small candidate buffer
 		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr;
-		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 10);
+		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 10);
 		g.big_tiles = cmax_small < cmax_big ? big_tiles : nullptr;
 		k_pass1_tile<CAP_FAST, false, false><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
 		ctx->launches++;
 		if (cmax_small < cmax_big) {    // launch 2: the single-interval tiles that need the large buffer
 			g.cmax = cmax_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
-			g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 6);
+			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 6);
 			k_pass1_tile<CAP_FAST, false, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
 			ctx->launches++;
 		}
 		// launch 3: tiles with multi-interval columns (two hulls per class); oversized ones go to the redo list
 		g.cmax = cmax_multi; g.tiles = multi_tiles; g.tiles_count = multi_count; g.big_tiles = nullptr;
-		g.tiles_next = reinterpret_cast<unsigned int *>(ctx->d_ctr + 7);
+		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 7);
 		k_pass1_tile<CAP_FAST, true, true><<<grid(nw_multi), 32 * nw_multi, smem_multi, s>>>(g);
 		ctx->launches++;
 	}
@@ -1316,6 +1318,8 @@ struct vo_slab {
 	TilePlan plan;
 	uint4 *thr = nullptr;
 	unsigned int *big_tiles = nullptr, *multi_tiles = nullptr;
+	unsigned int *big_tiles_b = nullptr, *multi_tiles_b = nullptr;   // ... of the boundary rows' launch set
+	cudaEvent_t ev_setup = nullptr, ev_side = nullptr;
 	unsigned long long *redo_list = nullptr;
 	unsigned int redo_cap = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -1331,23 +1335,29 @@ void free_slab(vo_slab *S)
 	free_dvol(ctx, S->ext);
 	if (S->mid) vo_dmid_free(ctx, S->mid);
 	dfree(ctx, S->thr); dfree(ctx, S->big_tiles); dfree(ctx, S->multi_tiles); dfree(ctx, S->redo_list);
-	for (cudaEvent_t e : {S->ev0, S->ev1, S->ev2}) if (e) cudaEventDestroy(e);
+	dfree(ctx, S->big_tiles_b); dfree(ctx, S->multi_tiles_b);
+	for (cudaEvent_t e : {S->ev0, S->ev1, S->ev2, S->ev_setup, S->ev_side}) if (e) cudaEventDestroy(e);
 	delete S;
 }
 
 // pass 1 (thresholds + the three tile launches + redo) of rows [y0, y1) and [y0b, y1b) of the extended volume; no
 // host sync
-void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int reserve_sms = 0)
+void slab_redo(vo_slab *S);
+
+// `side` = true: the launch set of the boundary rows, on the side stream with its own tile lists and cursors, so
+// that it can run next to the set of the interior rows (their redo launch follows once, after both).
+void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int reserve_sms = 0, bool side = false)
 {
 	if (y1 <= y0) { y0 = y0b; y1 = y1b; y0b = y1b = 0; }
 	if (y1 <= y0) return;
 	vo_ctx *ctx = S->ctx;
-	cudaStream_t sm = ctx->stream;
+	cudaStream_t sm = side ? ctx->s_in : ctx->stream;
+	unsigned long long *bank = side ? ctx->d_ctr + NCTR + 8 : ctx->d_ctr;
 	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
 	const int nx = S->nx, J = S->J;
-	cudaMemsetAsync(ctx->d_ctr + 3, 0, sizeof(unsigned long long), sm);
-	cudaMemsetAsync(ctx->d_ctr + 5, 0, 3 * sizeof(unsigned long long), sm);
-	cudaMemsetAsync(ctx->d_ctr + 10, 0, sizeof(unsigned long long), sm);
+	cudaMemsetAsync(bank + 3, 0, sizeof(unsigned long long), sm);
+	cudaMemsetAsync(bank + 5, 0, 3 * sizeof(unsigned long long), sm);
+	cudaMemsetAsync(bank + 10, 0, sizeof(unsigned long long), sm);
 	ThreshArgs ta;
 	ta.nx = nx; ta.ny = S->ext->ny; ta.J = J; ta.off = S->ext->off; ta.spans = S->ext->spans;
 	ta.Dmono = tc->tt.Dmono; ta.Emono = tc->tt.Emono; ta.G = tc->tt.G; ta.reach = tc->dt.reach; ta.thr = S->thr;
@@ -1370,14 +1380,28 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	reserve_sms = std::max(reserve_sms, 0);
 	if (interior) cudaEventRecord(ctx->kev[0], sm);
 	S->plan.launch(ctx, g, (unsigned int)S->plan.tiles_xw * (unsigned int)y0, (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0),
-	               S->big_tiles, S->multi_tiles, sm, (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
-	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms);
+	               side ? S->big_tiles_b : S->big_tiles, side ? S->multi_tiles_b : S->multi_tiles, sm,
+	               (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
+	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms, bank);
 	if (interior) { cudaEventRecord(ctx->kev[1], sm); ctx->kev_valid[0] = true; }
+	if (side) return;
+	slab_redo(S);
+}
+
+// lists that outgrew the fast capacity, and oversized tiles: one strided launch over the redo list (idempotent)
+void slab_redo(vo_slab *S)
+{
+	vo_ctx *ctx = S->ctx;
+	cudaStream_t sm = ctx->stream;
+	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
+	const int nx = S->nx, J = S->J;
+	vo_dmid *m = S->mid;
+	Redo rd{S->redo_list, reinterpret_cast<unsigned int *>(ctx->d_ctr + 2), S->redo_cap};
 	Pass1Args a1;
 	a1.nx = nx; a1.ny = S->ext->ny; a1.J = J; a1.off = S->ext->off; a1.spans = S->ext->spans; a1.H = tc->dt.H; a1.reach = tc->dt.reach;
 	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rd;
 	a1.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
-	k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier row ranges' overflow lists as well: idempotent)
+	k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);
 	ctx->launches++;
 }
 
@@ -1425,10 +1449,16 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	if (rc == VO_OK) rc = dalloc(ctx, &S->thr, total);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->big_tiles, ntiles);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->multi_tiles, ntiles);
+	const unsigned long long ntiles_b = (unsigned long long)S->plan.tiles_xw * (jp + jn + 2);
+	if (rc == VO_OK) rc = dalloc(ctx, &S->big_tiles_b, ntiles_b);
+	if (rc == VO_OK) rc = dalloc(ctx, &S->multi_tiles_b, ntiles_b);
+	if (rc == VO_OK && !ctx->s_in && cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); rc = fail(ctx, VO_ERR_CUDA, "cudaStreamCreate"); }
 	S->redo_cap = (unsigned int)std::min<unsigned long long>(nslots, 1ull << 22);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->redo_list, S->redo_cap);
 	if (rc) return bail(rc);
-	bool ok = cudaEventCreate(&S->ev0) == cudaSuccess && cudaEventCreate(&S->ev1) == cudaSuccess && cudaEventCreate(&S->ev2) == cudaSuccess;
+	bool ok = cudaEventCreate(&S->ev0) == cudaSuccess && cudaEventCreate(&S->ev1) == cudaSuccess && cudaEventCreate(&S->ev2) == cudaSuccess &&
+	          cudaEventCreateWithFlags(&S->ev_setup, cudaEventDisableTiming) == cudaSuccess &&
+	          cudaEventCreateWithFlags(&S->ev_side, cudaEventDisableTiming) == cudaSuccess;
 	if (!ok) { cudaGetLastError(); return bail(fail(ctx, VO_ERR_CUDA, "cudaEventCreate")); }
 	cudaStream_t sm = ctx->stream;
 	cudaEventRecord(S->ev0, sm);
@@ -1455,11 +1485,11 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	if (cap_prev) { k_rebase<<<blocks_for(nown + 1, 256), 256, 0, sm>>>(S->ext->off + (size_t)jp * nx, nown + 1, 0u, (uint32_t)cap_prev); ctx->launches++; }
 	if (own->nspans) cudaMemcpyAsync(S->ext->spans + cap_prev, own->spans, own->nspans * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
 	// "overlap" (default): the rows whose thresholds only read own rows start now (a few SMs stay free for the
-	// exchange's kernels) and the rest follows in vo_slab_finish. "serial": everything in vo_slab_finish, as ONE launch
-	// set. On the C5 slabs the two are within 1 % of each other (1.68 ms per step on 2 GPUs): every launch of the tile
-	// kernel ends with a tail of a few heavy tiles (steep walls), and the second tail costs what the exchange of
-	// ~100 KB takes; with larger halos the overlap wins.
+	// exchange's kernels and for what follows) and the boundary rows join them from the side stream in vo_slab_finish.
+	// "serial": everything in vo_slab_finish, as one launch set after the exchange (C5 slabs on 2 GPUs: 1.72 ms per
+	// step against 1.39 ms overlapped; a single GPU takes 1.26 ms for the same rows).
 	S->overlapped = ctx->slab_overlap;
+	cudaEventRecord(S->ev_setup, sm);                       // (the side stream of vo_slab_finish starts from here)
 	if (S->overlapped) slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0), 0, 0, 8);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)));
@@ -1475,23 +1505,32 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 	const int nx = S->nx, ny = S->ny, jp = S->jp, jn = S->jn;
 	if ((jp && (n_prev > S->cap_prev || !d_off_prev)) || (jn && (n_next > S->cap_next || !d_off_next)))
 		return fail(ctx, VO_ERR_OVERFLOW, "halo larger than its reserved region");
+	// Overlapped: the halos and pass 1 of the boundary rows go to the side stream, so that they run NEXT TO the launch
+	// set of the interior rows (which left a few SMs free; its CTAs retire one by one and the boundary CTAs take their
+	// place) instead of adding their own tail after it. Serial: everything on the main stream.
+	cudaStream_t sh = S->overlapped ? ctx->s_in : sm;
+	if (S->overlapped) cudaStreamWaitEvent(sh, S->ev_setup, 0);
 	if (jp) {
 		const unsigned long long n = (unsigned long long)jp * nx;          // (the entry after the last halo column is the first own offset)
-		cudaMemcpyAsync(S->ext->off, d_off_prev, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
-		k_rebase<<<blocks_for(n, 256), 256, 0, sm>>>(S->ext->off, n, 0u, (uint32_t)(S->cap_prev - n_prev));
+		cudaMemcpyAsync(S->ext->off, d_off_prev, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh);
+		k_rebase<<<blocks_for(n, 256), 256, 0, sh>>>(S->ext->off, n, 0u, (uint32_t)(S->cap_prev - n_prev));
 		ctx->launches++;
-		if (n_prev) cudaMemcpyAsync(S->ext->spans + (S->cap_prev - n_prev), d_spans_prev, n_prev * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
+		if (n_prev) cudaMemcpyAsync(S->ext->spans + (S->cap_prev - n_prev), d_spans_prev, n_prev * sizeof(double2), cudaMemcpyDeviceToDevice, sh);
 	}
 	if (jn) {
 		const unsigned long long n = (unsigned long long)jn * nx + 1;
 		uint32_t *dst = S->ext->off + (size_t)(jp + ny) * nx;
-		cudaMemcpyAsync(dst, d_off_next, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
-		k_rebase<<<blocks_for(n, 256), 256, 0, sm>>>(dst, n, 0u, (uint32_t)(S->cap_prev + S->n_own));
+		cudaMemcpyAsync(dst, d_off_next, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sh);
+		k_rebase<<<blocks_for(n, 256), 256, 0, sh>>>(dst, n, 0u, (uint32_t)(S->cap_prev + S->n_own));
 		ctx->launches++;
-		if (n_next) cudaMemcpyAsync(S->ext->spans + S->cap_prev + S->n_own, d_spans_next, n_next * sizeof(double2), cudaMemcpyDeviceToDevice, sm);
+		if (n_next) cudaMemcpyAsync(S->ext->spans + S->cap_prev + S->n_own, d_spans_next, n_next * sizeof(double2), cudaMemcpyDeviceToDevice, sh);
 	}
-	if (S->overlapped) slab_pass1_rows(S, 0, jp ? jp + 1 : 0, jp + ny - 1, jn ? jp + ny + jn : 0);
-	else slab_pass1_rows(S, 0, jp + ny + jn, 0, 0, -1);
+	if (S->overlapped) {
+		slab_pass1_rows(S, 0, jp ? jp + 1 : 0, jp + ny - 1, jn ? jp + ny + jn : 0, 0, true);
+		cudaEventRecord(S->ev_side, sh);
+		cudaStreamWaitEvent(sm, S->ev_side, 0);
+		slab_redo(S);                                       // (whatever either launch set left on the redo list)
+	} else slab_pass1_rows(S, 0, jp + ny + jn, 0, 0, -1);
 	cudaEventRecord(S->ev1, sm);
 	unsigned long long h[NCTR];
 	VO_TRY(read_counters(ctx, h));
@@ -1542,7 +1581,7 @@ int vo_create(int device, vo_ctx **out)
 	for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; i < 8 && ok; ++i) ok = cudaEventCreate(&ctx->mark[i]) == cudaSuccess;
 	for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&ctx->kev[i]) == cudaSuccess;
-	ok = ok && cudaMalloc((void **)&ctx->d_ctr, (NCTR + 8) * sizeof(unsigned long long)) == cudaSuccess;   // [NCTR]: erosion's "data outside the z range" flag
+	ok = ok && cudaMalloc((void **)&ctx->d_ctr, (NCTR + 8 + NCTR) * sizeof(unsigned long long)) == cudaSuccess;   // [NCTR]: erosion's "data outside the z range" flag; [NCTR + 8 ...]: tile cursors of a second, concurrent launch set (slab boundary rows)
 	if (ok) {
 		// keep freed blocks in the stream-ordered pool: steady-state calls then allocate without the driver
 		cudaMemPool_t pool;
