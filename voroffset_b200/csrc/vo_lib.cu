@@ -48,9 +48,10 @@ struct vo_ctx {
 	uint32_t *ovf = nullptr;          // spill area of the tile kernel's survivor lists (pass1_tile.cuh), allocated on first use
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
-	int pipe_bands = 4;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
+	int pipe_bands = 6;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
 	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
+	cudaStream_t s_p[2] = {nullptr, nullptr};       // its two pass-1 streams (consecutive bands overlap)
 	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
@@ -1117,9 +1118,13 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const int tiles_x = plan.tiles_x;
 	VO_TRY(dalloc(ctx, &m->tilemask, 2ull * ny * tiles_x));
 	const unsigned long long ntiles = (unsigned long long)plan.tiles_xw * ny;
-	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
+	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx), big_tiles1(ctx), multi_tiles1(ctx);
 	VO_TRY(dalloc(ctx, &big_tiles.p, ntiles));
 	VO_TRY(dalloc(ctx, &multi_tiles.p, ntiles));
+	VO_TRY(dalloc(ctx, &big_tiles1.p, ntiles));
+	VO_TRY(dalloc(ctx, &multi_tiles1.p, ntiles));
+	for (auto &st : ctx->s_p)
+		if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(nslots, 1ull << 22);
 	VO_TRY(rb.alloc(redo_cap));
@@ -1149,6 +1154,12 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
 	cudaMemsetAsync(m->tilemask, 0, 2ull * ny * tiles_x * sizeof(unsigned long long), sm);
 	cudaEventRecord(ctx->ev[0], sm);
+	{
+		cudaEvent_t ev_init = pr.event();
+		cudaEventRecord(ev_init, sm);
+		for (auto st : ctx->s_p) cudaStreamWaitEvent(st, ev_init, 0);
+	}
+	std::vector<cudaEvent_t> ev_p1(nb);
 
 	// launch parameters shared by all bands
 	ThreshArgs ta;
@@ -1164,17 +1175,26 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rb.rd;
 	a1.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
 
+	// Pass 1 of band b runs on one of two streams, with that stream's own tile lists and cursors: the launch set of
+	// band b+1 starts while the last heavy tiles of band b are still being worked on (every launch of the tile kernel
+	// ends with such a tail), its CTAs taking over the SMs as those of band b retire.
 	auto pass1_band = [&](int b) {
-		const int y0 = b * BH, y1 = std::min(ny, y0 + BH);
-		// the tile lists and cursors are per band ([3] big count, [5] multi count, [6] [7] [10] cursors)
-		cudaMemsetAsync(ctx->d_ctr + 3, 0, sizeof(unsigned long long), sm);
-		cudaMemsetAsync(ctx->d_ctr + 5, 0, 3 * sizeof(unsigned long long), sm);
-		cudaMemsetAsync(ctx->d_ctr + 10, 0, sizeof(unsigned long long), sm);
+		const int y0 = b * BH, y1 = std::min(ny, y0 + BH), w = b & 1;
+		cudaStream_t sp = ctx->s_p[w];
+		unsigned long long *bank = w ? ctx->d_ctr + NCTR + 8 : ctx->d_ctr;
+		cudaStreamWaitEvent(sp, ev_in[std::min(b + 1, nb - 1)], 0);     // thresholds of a band's last row read the next band's first row
+		cudaMemsetAsync(bank + 3, 0, sizeof(unsigned long long), sp);
+		cudaMemsetAsync(bank + 5, 0, 3 * sizeof(unsigned long long), sp);
+		cudaMemsetAsync(bank + 10, 0, sizeof(unsigned long long), sp);
 		ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
-		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
+		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sp>>>(ta);
 		ctx->launches++;
 		plan.launch(ctx, g, (unsigned int)plan.tiles_xw * (unsigned int)y0, (unsigned int)plan.tiles_xw * (unsigned int)(y1 - y0),
-		            big_tiles.p, multi_tiles.p, sm);
+		            w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, 0, bank);
+		ev_p1[b] = pr.event();
+		cudaEventRecord(ev_p1[b], sp);
+		// the main stream continues once the band is done: whatever outgrew the fast paths so far is redone there
+		cudaStreamWaitEvent(sm, ev_p1[b], 0);
 		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier bands' overflow lists as well: idempotent)
 		ctx->launches++;
 	};
@@ -1265,8 +1285,6 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 
 	for (int b = 0; b <= nb + 1 && rc == VO_OK; ++b) {
 		if (b < nb) {
-			// the y-thresholds of a band's last row read the first row of the next band
-			cudaStreamWaitEvent(sm, ev_in[std::min(b + 1, nb - 1)], 0);
 			pass1_band(b);
 		}
 		if (b >= 1 && b - 1 < nb) rc = enqueue_band(b - 1);                  // pass 2 of band b-1 needs pass 1 of band b
@@ -1607,6 +1625,7 @@ void vo_destroy(vo_ctx *ctx)
 	for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
+	for (auto &st : ctx->s_p) if (st) cudaStreamDestroy(st);
 	if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
 	if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
