@@ -1137,6 +1137,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	if (!ho || !hs) { drop_host(); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
 
 	// stage 0: all uploads are enqueued up front, one event per band
+	cudaEvent_t ev_t0 = nullptr;
+	if (std::getenv("VO_TRACE")) { cudaEventCreate(&ev_t0); cudaEventRecord(ev_t0, pr.s_in); }
 	std::vector<cudaEvent_t> ev_in(nb), ev_done(nb);
 	for (int b = 0; b < nb; ++b) {
 		const int y0 = b * BH, y1 = std::min(ny, y0 + BH);
@@ -1149,8 +1151,21 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaEventRecord(ev_in[b], pr.s_in);
 	}
 	if (cudaGetLastError() != cudaSuccess) { drop_host(); return PIPE_NA; }
+	cudaEvent_t ev_up_done = nullptr;
+	if (std::getenv("VO_TRACE")) { cudaEventCreate(&ev_up_done); cudaEventRecord(ev_up_done, pr.s_in); }
 
 	cudaStream_t sm = ctx->stream;
+	// VO_TRACE=1: device-side timeline of the call on stderr (development aid, scripts/e2e_bands.py)
+	static const bool trace = std::getenv("VO_TRACE") != nullptr;
+	std::vector<std::pair<std::string, cudaEvent_t>> marks;
+	auto mark = [&](const char *name, int b, cudaStream_t st) {
+		if (!trace) return;
+		cudaEvent_t ev;
+		cudaEventCreate(&ev);
+		cudaEventRecord(ev, st);
+		marks.emplace_back(std::string(name) + " " + std::to_string(b), ev);
+	};
+	if (trace && ev_t0) marks.emplace_back("start 0", ev_t0);
 	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
 	cudaMemsetAsync(m->tilemask, 0, 2ull * ny * tiles_x * sizeof(unsigned long long), sm);
 	cudaEventRecord(ctx->ev[0], sm);
@@ -1183,6 +1198,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaStream_t sp = ctx->s_p[w];
 		unsigned long long *bank = w ? ctx->d_ctr + NCTR + 8 : ctx->d_ctr;
 		cudaStreamWaitEvent(sp, ev_in[std::min(b + 1, nb - 1)], 0);     // thresholds of a band's last row read the next band's first row
+		mark("pass1 begin", b, sp);
 		cudaMemsetAsync(bank + 3, 0, sizeof(unsigned long long), sp);
 		cudaMemsetAsync(bank + 5, 0, 3 * sizeof(unsigned long long), sp);
 		cudaMemsetAsync(bank + 10, 0, sizeof(unsigned long long), sp);
@@ -1193,6 +1209,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		            w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, 0, bank);
 		ev_p1[b] = pr.event();
 		cudaEventRecord(ev_p1[b], sp);
+		mark("pass1 end", b, sp);
 		// the main stream continues once the band is done: whatever outgrew the fast paths so far is redone there
 		cudaStreamWaitEvent(sm, ev_p1[b], 0);
 		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier bands' overflow lists as well: idempotent)
@@ -1233,6 +1250,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		B->ready = pr.event();
 		cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), sm);
 		cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), sm);
+		mark("pass2 begin", b, sm);
 		Pass2Args a2;
 		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = B->y0; a2.y1 = B->y1;
 		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.st = B->sb.st; a2.redo = B->rb.rd;
@@ -1247,6 +1265,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaMemcpyAsync(B->h, ctx->d_ctr, NCTR * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm);
 		cudaMemcpyAsync(B->h + NCTR, B->sums.p + nt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm);
 		cudaEventRecord(B->ready, sm);
+		mark("pass2 end", b, sm);
 		bstate.push_back(std::move(B));
 		return VO_OK;
 	};
@@ -1275,8 +1294,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaEvent_t done = pr.event();
 		cudaEventRecord(done, sm);
 		cudaStreamWaitEvent(pr.s_out, done, 0);
+		mark("compact end", B.y0 / BH, sm);
+		mark("download begin", B.y0 / BH, pr.s_out);
 		cudaMemcpyAsync(ho + c0, B.v->off, (nlists + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
 		if (total) cudaMemcpyAsync(hs + 2 * base, B.v->spans, total * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
+		mark("download end", B.y0 / BH, pr.s_out);
 		base += total;
 		bands.push_back(B.v);       // released after the output stream has drained (no stall of the compute stream)
 		B.v = nullptr;
@@ -1299,6 +1321,15 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	for (auto bd : bands) free_dvol(ctx, bd);
 	bstate.clear();
 	vo_free(h_pin);
+	if (trace && !marks.empty()) {
+		float t = 0;
+		if (ev_up_done) { cudaEventElapsedTime(&t, marks[0].second, ev_up_done); std::fprintf(stderr, "[vo trace] %-18s %8.3f ms\n", "uploads end", t); cudaEventDestroy(ev_up_done); }
+		for (auto &mk : marks) {
+			if (cudaEventElapsedTime(&t, marks[0].second, mk.second) == cudaSuccess) std::fprintf(stderr, "[vo trace] %-18s %8.3f ms\n", mk.first.c_str(), t);
+		}
+		for (auto &mk : marks) cudaEventDestroy(mk.second);
+		cudaGetLastError();
+	}
 	if (rc == VO_OK && cudaGetLastError() != cudaSuccess) rc = PIPE_NA;
 	if (rc == VO_OK && (h[0] > m->pool_cap || h[2] > redo_cap || h[4])) {
 		ctx->pool_hint = std::max<unsigned long long>(ctx->pool_hint, h[0] + h[0] / 4);
