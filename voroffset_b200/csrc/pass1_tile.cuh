@@ -130,6 +130,8 @@ struct ThreshArgs {
 	uint4 *thr;             // per interval
 	unsigned long long c_begin, c_end;   // columns processed by this launch (a band of rows, or everything)
 	double clip_lo, clip_hi;             // the result is only read inside (clip_lo, clip_hi); -inf / +inf: everywhere
+	unsigned int *est = nullptr;         // optional, [ny * tiles_xw], zeroed by the host: estimated cost of every pass-1 tile
+	int tiles_xw = 0;                    //   (surviving pairs weighted by their classes; only the ORDER of the tiles uses it)
 };
 
 __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
@@ -139,16 +141,22 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) { s_D[i] = a.Dmono[i]; s_E[i] = a.Emono[i]; }
 	__syncthreads();
 	const unsigned long long c = a.c_begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= a.c_end) return;
-	const uint32_t o0 = __ldg(a.off + c), o1 = __ldg(a.off + c + 1);
-	if (o0 == o1) return;
+	const bool in_range = c < a.c_end;
+	if (!a.est && !in_range) return;
+	uint32_t o0 = 0, o1 = 0;
+	if (in_range) { o0 = __ldg(a.off + c); o1 = __ldg(a.off + c + 1); }
+	if (!a.est && o0 == o1) return;
 	const int J = a.J, JP = J + 1;
-	const int x = (int)(c % (unsigned)a.nx), y = (int)(c / (unsigned)a.nx);
+	const int x = in_range ? (int)(c % (unsigned)a.nx) : 0, y = in_range ? (int)(c / (unsigned)a.nx) : 0;
 	uint32_t l0 = 0, l1 = 0, r0 = 0, r1 = 0, u0 = 0, u1 = 0, d0 = 0, d1 = 0;
-	if (x > 0) { l0 = __ldg(a.off + c - 1); l1 = o0; }
-	if (x < a.nx - 1) { r0 = o1; r1 = __ldg(a.off + c + 2); }
-	if (y > 0) { u0 = __ldg(a.off + c - a.nx); u1 = __ldg(a.off + c - a.nx + 1); }
-	if (y < a.ny - 1) { d0 = __ldg(a.off + c + a.nx); d1 = __ldg(a.off + c + a.nx + 1); }
+	if (o0 != o1) {
+		if (x > 0) { l0 = __ldg(a.off + c - 1); l1 = o0; }
+		if (x < a.nx - 1) { r0 = o1; r1 = __ldg(a.off + c + 2); }
+		if (y > 0) { u0 = __ldg(a.off + c - a.nx); u1 = __ldg(a.off + c - a.nx + 1); }
+		if (y < a.ny - 1) { d0 = __ldg(a.off + c + a.nx); d1 = __ldg(a.off + c + a.nx + 1); }
+	}
+	unsigned int cost_l = 0, cost_s = 0, cost_r = 0;     // pairs of this column with outputs in the tile on the left / its own / on the right
+	const int xi = x & (P1_W - 1);
 	for (uint32_t k = o0; k < o1; ++k) {
 		const double2 p = __ldg(a.spans + k);
 		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
@@ -178,7 +186,79 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 		t.z = __float_as_uint(far_value(nnD, m, whole));            // consumers above: row y+1 is farther
 		t.w = __float_as_uint(far_value(nnU, m, whole));
 		a.thr[k] = t;
+		if (a.est) {
+			// the distances Tile::scatter will list this interval at: {0} and [s, hi] on the left, [s, hi] on the right
+			const int rx = __ldg(a.reach + T - 1);
+			const unsigned int w = 4u + (unsigned int)T;
+			const int hiL = min(tnL - 1, J), sL = max(1, min(tfL, rx)), hiR = min(tnR - 1, J), sR = max(1, min(tfR, rx));
+			const int nL = max(0, hiL - sL + 1), nLs = max(0, min(hiL, xi) - sL + 1);
+			const int nR = max(0, hiR - sR + 1), nRs = max(0, min(hiR, P1_W - 1 - xi) - sR + 1);
+			cost_s += w * (unsigned int)(1 + nLs + nRs);
+			cost_l += w * (unsigned int)(nL - nLs);
+			cost_r += w * (unsigned int)(nR - nRs);
+		}
 	}
+	if (a.est) {
+		// one atomic per warp and tile (lanes are consecutive columns: usually a single tile)
+		const unsigned int tile = in_range ? (unsigned int)y * (unsigned int)a.tiles_xw + (unsigned int)(x / P1_W) : 0xffffffffu;
+		const unsigned int grp = __match_any_sync(0xffffffffu, tile);
+		const unsigned int sl = __reduce_add_sync(grp, cost_l), ss = __reduce_add_sync(grp, cost_s), sr = __reduce_add_sync(grp, cost_r);
+		if (in_range && (threadIdx.x & 31) == __ffs(grp) - 1) {
+			const int tx = x / P1_W;
+			if (ss) atomicAdd(a.est + tile, ss);
+			if (sl && tx > 0) atomicAdd(a.est + tile - 1, sl);
+			if (sr && tx + 1 < a.tiles_xw) atomicAdd(a.est + tile + 1, sr);
+		}
+	}
+}
+
+// ---- tile order: expensive tiles first (costs differ by two orders of magnitude; a launch that ends with the
+// expensive ones ends with a long tail of a few busy warps). Buckets of log2(cost), descending; the order inside a
+// bucket is whatever the atomics give.
+constexpr int P1_NBUCKET = 32;
+struct OrderArgs {
+	const unsigned int *est;
+	unsigned int tile0, ntiles0, tile0b, ntiles;       // positions [0, ntiles) <-> tiles, as in Pass1TileArgs
+	unsigned int *hist;                                // [2 * P1_NBUCKET], zeroed by the host: counts, then fill cursors
+	unsigned int *order;                               // [ntiles]
+};
+__device__ __forceinline__ int order_bucket(unsigned int est) { return P1_NBUCKET - 1 - (est ? 32 - __clz(est) : 0) * (P1_NBUCKET - 1) / 32; }
+
+__global__ void __launch_bounds__(256) k_order_count(OrderArgs a)
+{
+	__shared__ unsigned int h[P1_NBUCKET];
+	if (threadIdx.x < P1_NBUCKET) h[threadIdx.x] = 0;
+	__syncthreads();
+	const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pos < a.ntiles) {
+		const unsigned int tile = pos < a.ntiles0 ? a.tile0 + pos : a.tile0b + (pos - a.ntiles0);
+		atomicAdd(&h[order_bucket(__ldg(a.est + tile))], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < P1_NBUCKET && h[threadIdx.x]) atomicAdd(a.hist + threadIdx.x, h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_order_place(OrderArgs a)
+{
+	__shared__ unsigned int base[P1_NBUCKET], h[P1_NBUCKET], start[P1_NBUCKET];
+	if (threadIdx.x < P1_NBUCKET) h[threadIdx.x] = 0;
+	if (threadIdx.x == 0) {
+		unsigned int acc = 0;
+		for (int b = 0; b < P1_NBUCKET; ++b) { base[b] = acc; acc += a.hist[b]; }
+	}
+	__syncthreads();
+	const unsigned int pos = blockIdx.x * blockDim.x + threadIdx.x;
+	unsigned int tile = 0, rank = 0;
+	int b = -1;
+	if (pos < a.ntiles) {
+		tile = pos < a.ntiles0 ? a.tile0 + pos : a.tile0b + (pos - a.ntiles0);
+		b = order_bucket(__ldg(a.est + tile));
+		rank = atomicAdd(&h[b], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < P1_NBUCKET && h[threadIdx.x]) start[threadIdx.x] = atomicAdd(a.hist + P1_NBUCKET + threadIdx.x, h[threadIdx.x]);
+	__syncthreads();
+	if (b >= 0) a.order[base[b] + start[b] + rank] = tile;
 }
 
 // ---- pass 1 ------------------------------------------------------------------------------------------
@@ -210,6 +290,7 @@ struct Pass1TileArgs {
 	//   launch 2  <MULTI=false>, large buffer, tiles = big_tiles.
 	//   launch 3  <MULTI=true> (two hulls per class), tiles = multi_tiles.
 	const unsigned int *tiles;        // NULL: all tiles of [tile0, tile0 + ntiles)
+	const unsigned int *order;        // with tiles == NULL, optional: the same tiles as a permutation (k_order_place), expensive ones first
 	const unsigned int *tiles_count;  // length of `tiles` (device side)
 	unsigned int *tiles_next;         // next position to hand out
 	unsigned int *big_tiles;          // NULL: oversized tiles go to the redo list (k_pass1)
@@ -730,7 +811,7 @@ __global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArg
 	// segment offsets of the tile at list position `pos` -> registers (o[r][1] = the next column's offset, for the
 	// multi-interval test)
 	auto load_offsets = [&](unsigned int pos, uint32_t (&o)[NR][2], TileHead &h) {
-		h.tile = LIST ? a.tiles[pos] : (pos < a.ntiles0 ? a.tile0 + pos : a.tile0b + (pos - a.ntiles0));
+		h.tile = LIST ? a.tiles[pos] : a.order ? __ldg(a.order + pos) : (pos < a.ntiles0 ? a.tile0 + pos : a.tile0b + (pos - a.ntiles0));
 		h.y = (int)(h.tile / (unsigned)a.tiles_xw);
 		h.x0 = (int)(h.tile % (unsigned)a.tiles_xw) * P1_W;
 		h.txe = min(P1_W, a.nx - h.x0);

@@ -48,10 +48,12 @@ struct vo_ctx {
 	uint32_t *ovf = nullptr;          // spill area of the tile kernel's survivor lists (pass1_tile.cuh), allocated on first use
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
+	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
 	int pipe_bands = 6;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
 	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
 	cudaStream_t s_p[2] = {nullptr, nullptr};       // its two pass-1 streams (consecutive bands overlap)
+	cudaStream_t s_hi = nullptr;                    // its second-half stream (highest priority)
 	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
@@ -573,7 +575,7 @@ struct TilePlan {
 	// NCCL kernels of a halo exchange in flight).
 	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles0, unsigned int *big_tiles, unsigned int *multi_tiles,
 	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0,
-	            unsigned long long *bank = nullptr) const
+	            unsigned long long *bank = nullptr, const unsigned int *order = nullptr) const
 	{
 		if (!bank) bank = ctx->d_ctr;                       // ([3] [5] [6] [7] [10] of `bank`: the lists and cursors of this launch set)
 		const unsigned int ntiles = ntiles0 + ntilesb;
@@ -586,7 +588,7 @@ struct TilePlan {
 		g.big_count = big_count; g.multi_tiles = multi_tiles; g.multi_count = multi_count;
 		auto grid = [&](int nw) { return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)sms, (ntiles + nw - 1) / nw)); };
 		// launch 1: single-interval tiles, small candidate buffer
-		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr;
+		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.order = order;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 10);
 		g.big_tiles = cmax_small < cmax_big ? big_tiles : nullptr;
 		k_pass1_tile<CAP_FAST, false, false><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
@@ -602,6 +604,19 @@ struct TilePlan {
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 7);
 		k_pass1_tile<CAP_FAST, true, true><<<grid(nw_multi), 32 * nw_multi, smem_multi, s>>>(g);
 		ctx->launches++;
+	}
+	// Expensive tiles first: `est` (k_thresh, per tile) -> `order`, a permutation of the positions of the same two
+	// ranges launch() takes; scratch = [2 * P1_NBUCKET] zeroed counters.
+	static void order_tiles(vo_ctx *ctx, const unsigned int *est, unsigned int *scratch, unsigned int *order, unsigned int tile0,
+	                        unsigned int ntiles0, unsigned int tile0b, unsigned int ntilesb, cudaStream_t s)
+	{
+		OrderArgs oa;
+		oa.est = est; oa.tile0 = tile0; oa.ntiles0 = ntiles0; oa.tile0b = tile0b; oa.ntiles = ntiles0 + ntilesb;
+		oa.hist = scratch; oa.order = order;
+		if (!oa.ntiles) return;
+		k_order_count<<<blocks_for(oa.ntiles, 256), 256, 0, s>>>(oa);
+		k_order_place<<<blocks_for(oa.ntiles, 256), 256, 0, s>>>(oa);
+		ctx->launches += 2;
 	}
 };
 
@@ -646,6 +661,11 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, ntiles);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &multi_tiles.p, ntiles);
+	// tile order (expensive first): [2 * P1_NBUCKET counters | cost estimate per tile], and the permutation
+	Tmp<unsigned int> est(ctx), order(ctx);
+	const bool ordered = use_tile && ctx->tile_order && ntiles >= 4096;
+	if (rc == VO_OK && ordered) rc = dalloc(ctx, &est.p, ntiles + 2 * P1_NBUCKET);
+	if (rc == VO_OK && ordered) rc = dalloc(ctx, &order.p, ntiles);
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nslots, 1ull), 1ull << 22);
 	if (rc == VO_OK) rc = rb.alloc(redo_cap);
@@ -668,14 +688,19 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			ta.nx = in->nx; ta.ny = in->ny; ta.J = t.J; ta.off = in->off; ta.spans = in->spans;
 			ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
 			ta.c_begin = 0; ta.c_end = ncols; ta.clip_lo = clip_lo; ta.clip_hi = clip_hi;
+			if (ordered) {
+				cudaMemsetAsync(est.p, 0, (ntiles + 2 * P1_NBUCKET) * sizeof(unsigned int), ctx->stream);
+				ta.est = est.p + 2 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw;
+			}
 			k_thresh<<<blocks_for(ncols, 256), 256, 2 * (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(ta);
 			ctx->launches++;
+			if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p, order.p, 0u, (unsigned int)ntiles, 0u, 0u, ctx->stream);
 			Pass1TileArgs g;
 			g.nx = in->nx; g.ny = in->ny;
 			g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
 			g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			cudaEventRecord(ctx->kev[0], ctx->stream);
-			plan.launch(ctx, g, 0u, (unsigned int)ntiles, big_tiles.p, multi_tiles.p, ctx->stream);
+			plan.launch(ctx, g, 0u, (unsigned int)ntiles, big_tiles.p, multi_tiles.p, ctx->stream, 0u, 0u, 0, nullptr, ordered ? order.p : nullptr);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
 		} else if (nslots) {
@@ -1123,8 +1148,21 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	VO_TRY(dalloc(ctx, &multi_tiles.p, ntiles));
 	VO_TRY(dalloc(ctx, &big_tiles1.p, ntiles));
 	VO_TRY(dalloc(ctx, &multi_tiles1.p, ntiles));
+	// tile order per band (expensive first): [per stream 2 * P1_NBUCKET counters | cost estimate per tile], permutations per stream
+	Tmp<unsigned int> est(ctx), order0(ctx), order1(ctx);
+	const bool ordered = ctx->tile_order;
+	if (ordered) {
+		VO_TRY(dalloc(ctx, &est.p, ntiles + 4 * P1_NBUCKET));
+		VO_TRY(dalloc(ctx, &order0.p, ntiles));
+		VO_TRY(dalloc(ctx, &order1.p, ntiles));
+	}
 	for (auto &st : ctx->s_p)
 		if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
+	if (!ctx->s_hi) {       // the second half (pass 2, scan, compaction) of a band outranks pass 1 of the bands behind it
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		if (cudaStreamCreateWithPriority(&ctx->s_hi, cudaStreamNonBlocking, greatest) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
+	}
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(nslots, 1ull << 22);
 	VO_TRY(rb.alloc(redo_cap));
@@ -1154,7 +1192,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	cudaEvent_t ev_up_done = nullptr;
 	if (std::getenv("VO_TRACE")) { cudaEventCreate(&ev_up_done); cudaEventRecord(ev_up_done, pr.s_in); }
 
-	cudaStream_t sm = ctx->stream;
+	cudaStream_t sm = ctx->s_hi;
 	// VO_TRACE=1: device-side timeline of the call on stderr (development aid, scripts/e2e_bands.py)
 	static const bool trace = std::getenv("VO_TRACE") != nullptr;
 	std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -1166,13 +1204,15 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		marks.emplace_back(std::string(name) + " " + std::to_string(b), ev);
 	};
 	if (trace && ev_t0) marks.emplace_back("start 0", ev_t0);
-	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
-	cudaMemsetAsync(m->tilemask, 0, 2ull * ny * tiles_x * sizeof(unsigned long long), sm);
-	cudaEventRecord(ctx->ev[0], sm);
+	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), ctx->stream);
+	cudaMemsetAsync(m->tilemask, 0, 2ull * ny * tiles_x * sizeof(unsigned long long), ctx->stream);
+	if (ordered) cudaMemsetAsync(est.p, 0, (ntiles + 4 * P1_NBUCKET) * sizeof(unsigned int), ctx->stream);
+	cudaEventRecord(ctx->ev[0], ctx->stream);
 	{
 		cudaEvent_t ev_init = pr.event();
-		cudaEventRecord(ev_init, sm);
+		cudaEventRecord(ev_init, ctx->stream);
 		for (auto st : ctx->s_p) cudaStreamWaitEvent(st, ev_init, 0);
+		cudaStreamWaitEvent(sm, ev_init, 0);
 	}
 	std::vector<cudaEvent_t> ev_p1(nb);
 
@@ -1203,14 +1243,24 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaMemsetAsync(bank + 5, 0, 3 * sizeof(unsigned long long), sp);
 		cudaMemsetAsync(bank + 10, 0, sizeof(unsigned long long), sp);
 		ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
+		const unsigned int t0 = (unsigned int)plan.tiles_xw * (unsigned int)y0, nt = (unsigned int)plan.tiles_xw * (unsigned int)(y1 - y0);
+		unsigned int *ord = nullptr;
+		if (ordered) {
+			unsigned int *scratch = est.p + 2 * P1_NBUCKET * w;
+			if (b >= 2) cudaMemsetAsync(scratch, 0, 2 * P1_NBUCKET * sizeof(unsigned int), sp);
+			ta.est = est.p + 4 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw;
+			ord = (w ? order1.p : order0.p) + t0;
+		}
 		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sp>>>(ta);
 		ctx->launches++;
-		plan.launch(ctx, g, (unsigned int)plan.tiles_xw * (unsigned int)y0, (unsigned int)plan.tiles_xw * (unsigned int)(y1 - y0),
-		            w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, 0, bank);
+		if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p + 2 * P1_NBUCKET * w, ord, t0, nt, 0u, 0u, sp);
+		plan.launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, 0, bank, ord);
 		ev_p1[b] = pr.event();
 		cudaEventRecord(ev_p1[b], sp);
 		mark("pass1 end", b, sp);
-		// the main stream continues once the band is done: whatever outgrew the fast paths so far is redone there
+	};
+	// the second-half stream continues once the band is done: whatever outgrew the fast paths so far is redone there
+	auto pass1_redo = [&](int b) {
 		cudaStreamWaitEvent(sm, ev_p1[b], 0);
 		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier bands' overflow lists as well: idempotent)
 		ctx->launches++;
@@ -1236,6 +1286,9 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	uint64_t base = 0;          // intervals of the bands finished so far
 	std::vector<vo_dvol *> bands;
 	int rc = VO_OK;
+	// declared last, hence destroyed first: on every way out the side streams are drained BEFORE the temporaries above
+	// go back to the pool of the context stream (stream-ordered frees only order against that stream)
+	struct Join { vo_ctx *c; ~Join() { cudaStreamSynchronize(c->s_hi); for (auto st : c->s_p) cudaStreamSynchronize(st); } } join{ctx};
 
 	auto enqueue_band = [&](int b) -> int {
 		std::unique_ptr<Band> B(new Band(ctx));
@@ -1305,15 +1358,22 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		return VO_OK;
 	};
 
+	// Pass 1 of EVERY band is enqueued up front (it only waits for its upload), so the host's waits for the band
+	// totals below never leave the device without work.
+	for (int b = 0; b < nb; ++b) pass1_band(b);
 	for (int b = 0; b <= nb + 1 && rc == VO_OK; ++b) {
-		if (b < nb) {
-			pass1_band(b);
-		}
+		if (b < nb) pass1_redo(b);
 		if (b >= 1 && b - 1 < nb) rc = enqueue_band(b - 1);                  // pass 2 of band b-1 needs pass 1 of band b
 		if (rc == VO_OK && b >= 2) rc = finish_band(*bstate[b - 2]);
 	}
 	for (auto &B : bstate) if (B->v) { free_dvol(ctx, B->v); B->v = nullptr; }
-	cudaEventRecord(ctx->ev[2], sm);
+	{
+		cudaEvent_t ev_fin = pr.event();
+		cudaEventRecord(ev_fin, sm);
+		for (auto st : ctx->s_p) { cudaEvent_t e = pr.event(); cudaEventRecord(e, st); cudaStreamWaitEvent(ctx->stream, e, 0); }
+		cudaStreamWaitEvent(ctx->stream, ev_fin, 0);
+	}
+	cudaEventRecord(ctx->ev[2], ctx->stream);
 	unsigned long long h[NCTR];
 	if (rc == VO_OK) rc = read_counters(ctx, h);
 	cudaStreamSynchronize(pr.s_out);
@@ -1657,6 +1717,7 @@ void vo_destroy(vo_ctx *ctx)
 	for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
 	for (auto &st : ctx->s_p) if (st) cudaStreamDestroy(st);
+	if (ctx->s_hi) cudaStreamDestroy(ctx->s_hi);
 	if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
 	if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1681,6 +1742,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "bands") == 0) {
 		const int n = std::atoi(value);
 		if (n >= 3 && n <= 64) { ctx->pipe_bands = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "tile_order") == 0) {
+		if (std::strcmp(value, "off") == 0) { ctx->tile_order = false; return VO_OK; }
+		if (std::strcmp(value, "on") == 0) { ctx->tile_order = true; return VO_OK; }
 	}
 	if (std::strcmp(key, "tile_debug") == 0) {           // development aid: scripts/tile_costs.py
 		ctx->dbg_tiles = reinterpret_cast<unsigned long long *>(std::strtoull(value, nullptr, 0));
