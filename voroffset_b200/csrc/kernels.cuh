@@ -598,14 +598,17 @@ __global__ void __launch_bounds__(D2B_THREADS) k_dilate2d_block(Dil2dArgs a)
 	}
 }
 
-// Staged lists -> canonical CSR (after the exclusive scan of cnt).
+// Staged lists -> canonical CSR (after the exclusive scan of cnt). Lists that would end beyond `cap` intervals
+// are skipped (the caller notices from the total and repeats with a larger buffer).
 __global__ void __launch_bounds__(256) k_compact(Stage st, unsigned long long nlists,
-                                                 const uint32_t *__restrict__ off, double2 *__restrict__ spans)
+                                                 const uint32_t *__restrict__ off, double2 *__restrict__ spans,
+                                                 unsigned long long cap = ~0ull)
 {
 	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= nlists) return;
 	const uint32_t n = st.cnt[c];
 	if (n == 0) return;
+	if ((unsigned long long)off[c] + n > cap) return;
 	double2 *dst = spans + off[c];
 	if (n <= STAGE_INLINE) {
 		for (uint32_t k = 0; k < n; ++k) dst[k] = st.inl[c * STAGE_INLINE + k];

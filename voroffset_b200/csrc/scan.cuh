@@ -59,9 +59,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__
 }
 
 // One block: in-place exclusive scan of the tile sums; tile_sum[ntiles] receives the grand total.
-__global__ void __launch_bounds__(1024) k_scan_tiles(unsigned long long *__restrict__ tile_sum, uint32_t ntiles)
+// base_in (optional): the scan starts from *base_in instead of 0 (offsets of a band of a larger volume);
+// base_out (optional) receives the grand total as well.
+__global__ void __launch_bounds__(1024) k_scan_tiles(unsigned long long *__restrict__ tile_sum, uint32_t ntiles,
+                                                     const unsigned long long *base_in = nullptr, unsigned long long *base_out = nullptr)
 {
-	unsigned long long carry = 0;
+	unsigned long long carry = base_in ? *base_in : 0ull;
 	for (uint32_t b = 0; b < ntiles; b += blockDim.x) {
 		uint32_t k = b + threadIdx.x;
 		unsigned long long v = (k < ntiles) ? tile_sum[k] : 0ull;
@@ -70,7 +73,7 @@ __global__ void __launch_bounds__(1024) k_scan_tiles(unsigned long long *__restr
 		if (k < ntiles) tile_sum[k] = carry + ex;
 		carry += tot;
 	}
-	if (threadIdx.x == 0) tile_sum[ntiles] = carry;
+	if (threadIdx.x == 0) { tile_sum[ntiles] = carry; if (base_out) *base_out = carry; }
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t *__restrict__ cnt, uint64_t n,

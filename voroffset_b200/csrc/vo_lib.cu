@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -49,11 +50,13 @@ struct vo_ctx {
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
-	int pipe_bands = 6;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
+	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
+	int pipe_bands = 8;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
 	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
 	cudaStream_t s_p[2] = {nullptr, nullptr};       // its two pass-1 streams (consecutive bands overlap)
-	cudaStream_t s_hi = nullptr;                    // its second-half stream (highest priority)
+	cudaStream_t s_hi[3] = {nullptr, nullptr, nullptr};   // its second-half streams (highest priority): two for alternating bands, one for the pass-1 redo launches
+	cudaStream_t s_ctl = nullptr;                   // its control stream (band totals -> host)
 	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
@@ -532,7 +535,7 @@ int get_tables(vo_ctx *ctx, double R, bool need_tile, TableCache **out)
 // Launch plan of the tile kernel (pass1_tile.cuh): candidate-buffer sizes, warps per CTA and shared memory of the
 // three launches, from the grid and the mean fill. One CTA per SM; warps work on their own.
 struct TilePlan {
-	int J = 0, tiles_xw = 0, tiles_x = 0, sms = 148;
+	int J = 0, tiles_xw = 0, tiles_x = 0, sms = 148, cps = 1;
 	int cmax_small = 0, cmax_big = 0, cmax_multi = 0;
 	int nw_small = 1, nw_big = 1, nw_multi = 1;
 	size_t smem_small = 0, smem_big = 0, smem_multi = 0;
@@ -545,7 +548,8 @@ struct TilePlan {
 		tiles_x = (nx + P1_TX - 1) / P1_TX;
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
 		if (!ctx->ovf) {
-			cudaError_t ea = cudaMalloc((void **)&ctx->ovf, (size_t)sms * P1_MAXWARPS * P1_OVF * P1_W * sizeof(uint32_t));
+			// (two banks: a second launch set may run beside the first - slab boundary rows, alternating pipeline bands)
+			cudaError_t ea = cudaMalloc((void **)&ctx->ovf, 2 * (size_t)sms * P1_MAXWARPS * P1_OVF * P1_W * sizeof(uint32_t));
 			if (ea != cudaSuccess) { cudaGetLastError(); ctx->ovf = nullptr; return fail(ctx, VO_ERR_NOMEM, "spill area of the tile kernel"); }
 		}
 		const int SEG = P1_W + 2 * J;
@@ -554,10 +558,15 @@ struct TilePlan {
 		cmax_small = std::min(pick(k_in * SEG * 1.5), (SEG + 15) & ~15);
 		cmax_big = CMAX;
 		cmax_multi = std::max(pick(k_in * SEG * 1.5), 128);
-		const size_t budget = 220 * 1024;
+		// `cps` CTAs per SM share its shared memory (228 KB, 1 KB of it reserved per CTA) and its 16 warps' worth of
+		// registers: several small CTAs give an SM back piecewise when a launch runs out of tiles, one large CTA only
+		// when its last warp is done
+		cps = std::max(1, std::min(ctx->tile_ctas, 8));
+		const size_t budget = std::min<size_t>(220 * 1024, 228 * 1024 / cps - 1024 - 256);
 		auto warps = [&](int cmax, int lcap) {
 			const size_t per = pass1_warp_smem(J, cmax, lcap), tab = pass1_table_smem(J) + 32;
-			return (int)std::max<size_t>(1, std::min<size_t>(P1_MAXWARPS, (budget - tab) / per));
+			if (budget < tab + per) return 1;
+			return (int)std::max<size_t>(1, std::min<size_t>(P1_MAXWARPS / cps, (budget - tab) / per));
 		};
 		nw_small = warps(cmax_small, P1_LCAP_S); nw_big = warps(cmax_big, P1_LCAP_M); nw_multi = warps(cmax_multi, P1_LCAP_M);
 		smem_small = pass1_tile_smem(J, cmax_small, P1_LCAP_S, nw_small);
@@ -581,12 +590,14 @@ struct TilePlan {
 		const unsigned int ntiles = ntiles0 + ntilesb;
 		const int sms = std::max(1, this->sms - reserve_sms);
 		g.J = J; g.tiles_xw = tiles_xw; g.tiles_x = tiles_x; g.tile0 = tile0; g.ntiles = ntiles; g.tile0b = tile0b; g.ntiles0 = ntiles0;
-		g.ovf = ctx->ovf;
+		g.ovf = ctx->ovf + (bank == ctx->d_ctr ? (size_t)0 : (size_t)this->sms * P1_MAXWARPS * P1_OVF * P1_W);
 		g.dbg = ctx->dbg_tiles;
 		unsigned int *big_count = reinterpret_cast<unsigned int *>(bank + 3);
 		unsigned int *multi_count = reinterpret_cast<unsigned int *>(bank + 5);
 		g.big_count = big_count; g.multi_tiles = multi_tiles; g.multi_count = multi_count;
-		auto grid = [&](int nw) { return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)sms, (ntiles + nw - 1) / nw)); };
+		// (a large buffer may leave room for fewer CTAs per SM than planned: the grid is then more than one wave, which
+		// the tile counter does not mind)
+		auto grid = [&](int nw) { return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)(sms * cps), (ntiles + nw - 1) / nw)); };
 		// launch 1: single-interval tiles, small candidate buffer
 		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.order = order;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 10);
@@ -1106,10 +1117,33 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	if (nx <= 0 || ny <= 0 || !off || off[0] != 0 || ncols >= (1ull << 32) - 8) return PIPE_NA;
 	const uint64_t nspans = off[ncols];
 	const double k_in = (double)nspans / (double)ncols;
-	// about six bands: enough to overlap, few enough that the per-band launch / readback overhead stays small
-	const int nbw = std::max(3, ctx->pipe_bands);
-	const int BH = std::max(2 * (J + 1), ((ny + nbw - 1) / nbw + 7) & ~7);   // band height >= reach of pass 2
-	const int nb = (ny + BH - 1) / BH;
+	// Bands of rows: eight by default (vo_set_option("bands", N)) - enough to overlap the copies with the passes, few
+	// enough that a launch set of pass 1 still has many tiles per warp. (Small bands at both ends and large ones in
+	// between - early first download, short last stage - were tried and lose: the passes, not the copies, bound the call.)
+	// Every band is at least 2 (floor(R) + 1) rows high (pass 2 of a band then only reaches into its two neighbours).
+	std::vector<int> ys;
+	{
+		const int hmin = 2 * (J + 1);
+		std::vector<int> wts;
+		wts.assign(std::max(3, ctx->pipe_bands), 1);
+		int wsum = 0;
+		for (int w : wts) wsum += w;
+		if (ny / wsum < hmin) {                              // too few rows for that shape: equal bands of the minimum height or more
+			const int n = std::max(1, std::min((int)wts.size(), ny / hmin));
+			wts.assign(n, 1); wsum = n;
+		}
+		ys.push_back(0);
+		int acc = 0;
+		for (size_t i = 0; i + 1 < wts.size(); ++i) {
+			acc += wts[i];
+			const int y = std::min(ny, (int)(((long long)ny * acc / wsum + 7) & ~7ll));
+			if (y - ys.back() >= hmin && ny - y >= hmin) ys.push_back(y);
+		}
+		ys.push_back(ny);
+	}
+	const int nb = (int)ys.size() - 1;
+	int BH = 0;                                              // the tallest band
+	for (int b = 0; b < nb; ++b) BH = std::max(BH, ys[b + 1] - ys[b]);
 	if (nb < 3 || ncols * (unsigned long long)(J + 1) < (48ull << 20) || !TilePlan::fits(J, k_in)) return PIPE_NA;
 	if (nspans && !spans) return PIPE_NA;
 
@@ -1158,28 +1192,48 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	}
 	for (auto &st : ctx->s_p)
 		if (!st && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
-	if (!ctx->s_hi) {       // the second half (pass 2, scan, compaction) of a band outranks pass 1 of the bands behind it
+	for (auto &st : ctx->s_hi) {       // the second half (pass 2, scan, compaction) of a band outranks pass 1 of the bands behind it
+		if (st) continue;
 		int least = 0, greatest = 0;
 		cudaDeviceGetStreamPriorityRange(&least, &greatest);
-		if (cudaStreamCreateWithPriority(&ctx->s_hi, cudaStreamNonBlocking, greatest) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
+		if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
 	}
-	RedoBuf rb(ctx);
-	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(nslots, 1ull << 22);
-	VO_TRY(rb.alloc(redo_cap));
+	// redo lists of pass 1, one per band (slot ids that outgrew the fast paths; their counts sit behind the band totals in `gb`)
+	const unsigned int rcap1 = (unsigned int)std::min<unsigned long long>((unsigned long long)nx * BH * (J + 1), 1ull << 20);
+	Tmp<unsigned long long> redo1(ctx);
+	VO_TRY(dalloc(ctx, &redo1.p, (unsigned long long)rcap1 * nb));
 
-	// result buffers (pinned): offsets are exact, the span buffer is sized from the last result (grown if needed)
+	// second half: whole-grid staging, per-band redo lists and scan scratch, the result volume on the device
+	const uint64_t hs_cap = std::min<uint64_t>(std::max<uint64_t>(ctx->out_hint, 2 * nspans + (1u << 16)), (1ull << 32) - 1);
+	const unsigned long long dcap = hs_cap;
+	StageBuf sb(ctx);
+	VO_TRY(sb.alloc(ncols, 65536ull + ncols / 8));
+	const unsigned int rcap2 = (unsigned int)std::min<unsigned long long>((unsigned long long)nx * BH, 1ull << 22);
+	Tmp<unsigned long long> redo2(ctx), sums(ctx), gb(ctx);
+	VO_TRY(dalloc(ctx, &redo2.p, (unsigned long long)rcap2 * nb));
+	const unsigned int nt_max = blocks_for((unsigned long long)nx * BH, SCAN_TILE);
+	VO_TRY(dalloc(ctx, &sums.p, ((unsigned long long)nt_max + 1) * nb));
+	VO_TRY(dalloc(ctx, &gb.p, 3ull * nb + 1));                // [nb + 1] running totals, [nb] redo counts of pass 2, [nb] of pass 1
+	vo_dvol *dout = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &dout));
+	struct OutGuard { vo_ctx *c; vo_dvol *p; ~OutGuard() { free_dvol(c, p); } } out_guard{ctx, dout};
+	VO_TRY(dalloc(ctx, &dout->spans, dcap));
+	if (!ctx->s_ctl && cudaStreamCreateWithFlags(&ctx->s_ctl, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
+
+	// result buffers (pinned): offsets are exact, the span buffer is sized from the last result
 	uint32_t *ho = (uint32_t *)host_block((ncols + 1) * sizeof(uint32_t));
-	uint64_t hs_cap = std::max<uint64_t>(ctx->out_hint, 2 * nspans + (1u << 16));
 	double *hs = (double *)host_block(hs_cap * sizeof(double2));
+	unsigned long long *h_tot = (unsigned long long *)host_block((size_t)nb * sizeof(unsigned long long));
 	auto drop_host = [&]() { vo_free(ho); vo_free(hs); };
-	if (!ho || !hs) { drop_host(); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
+	if (!ho || !hs || !h_tot) { drop_host(); vo_free(h_tot); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
 
 	// stage 0: all uploads are enqueued up front, one event per band
+	const auto host_t0 = std::chrono::steady_clock::now();
 	cudaEvent_t ev_t0 = nullptr;
 	if (std::getenv("VO_TRACE")) { cudaEventCreate(&ev_t0); cudaEventRecord(ev_t0, pr.s_in); }
 	std::vector<cudaEvent_t> ev_in(nb), ev_done(nb);
 	for (int b = 0; b < nb; ++b) {
-		const int y0 = b * BH, y1 = std::min(ny, y0 + BH);
+		const int y0 = ys[b], y1 = ys[b + 1];
 		const unsigned long long c0 = (unsigned long long)y0 * nx, c1 = (unsigned long long)y1 * nx;
 		cudaMemcpyAsync(in->off + c0, off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, pr.s_in);
 		if (off[c1] > off[c0])
@@ -1192,7 +1246,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	cudaEvent_t ev_up_done = nullptr;
 	if (std::getenv("VO_TRACE")) { cudaEventCreate(&ev_up_done); cudaEventRecord(ev_up_done, pr.s_in); }
 
-	cudaStream_t sm = ctx->s_hi;
+	cudaStream_t sh[2] = {ctx->s_hi[0], ctx->s_hi[1]}, s_redo = ctx->s_hi[2];
 	// VO_TRACE=1: device-side timeline of the call on stderr (development aid, scripts/e2e_bands.py)
 	static const bool trace = std::getenv("VO_TRACE") != nullptr;
 	std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -1201,20 +1255,24 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaEvent_t ev;
 		cudaEventCreate(&ev);
 		cudaEventRecord(ev, st);
-		marks.emplace_back(std::string(name) + " " + std::to_string(b), ev);
+		const double host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+		char buf[96];
+		std::snprintf(buf, sizeof buf, "%s %d (enqueued at host %.3f ms)", name, b, host_ms);
+		marks.emplace_back(buf, ev);
 	};
 	if (trace && ev_t0) marks.emplace_back("start 0", ev_t0);
 	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), ctx->stream);
 	cudaMemsetAsync(m->tilemask, 0, 2ull * ny * tiles_x * sizeof(unsigned long long), ctx->stream);
 	if (ordered) cudaMemsetAsync(est.p, 0, (ntiles + 4 * P1_NBUCKET) * sizeof(unsigned int), ctx->stream);
+	cudaMemsetAsync(gb.p, 0, (3ull * nb + 1) * sizeof(unsigned long long), ctx->stream);
 	cudaEventRecord(ctx->ev[0], ctx->stream);
 	{
 		cudaEvent_t ev_init = pr.event();
 		cudaEventRecord(ev_init, ctx->stream);
 		for (auto st : ctx->s_p) cudaStreamWaitEvent(st, ev_init, 0);
-		cudaStreamWaitEvent(sm, ev_init, 0);
+		for (auto st : ctx->s_hi) cudaStreamWaitEvent(st, ev_init, 0);
 	}
-	std::vector<cudaEvent_t> ev_p1(nb);
+	std::vector<cudaEvent_t> ev_p1(nb), ev_r1(nb), ev_scan(nb);
 
 	// launch parameters shared by all bands
 	ThreshArgs ta;
@@ -1224,17 +1282,17 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	Pass1TileArgs g;
 	g.nx = nx; g.ny = ny;
 	g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
-	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
+	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap;
 	Pass1Args a1;
 	a1.nx = nx; a1.ny = ny; a1.J = J; a1.off = in->off; a1.spans = in->spans; a1.H = dt.H; a1.reach = dt.reach;
-	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap; a1.redo = rb.rd;
-	a1.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
+	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap;
+	auto redo_of = [&](int b) { return Redo{redo1.p + (size_t)b * rcap1, reinterpret_cast<unsigned int *>(gb.p + 2 * nb + 1 + b), rcap1}; };
 
 	// Pass 1 of band b runs on one of two streams, with that stream's own tile lists and cursors: the launch set of
 	// band b+1 starts while the last heavy tiles of band b are still being worked on (every launch of the tile kernel
 	// ends with such a tail), its CTAs taking over the SMs as those of band b retire.
 	auto pass1_band = [&](int b) {
-		const int y0 = b * BH, y1 = std::min(ny, y0 + BH), w = b & 1;
+		const int y0 = ys[b], y1 = ys[b + 1], w = b & 1;
 		cudaStream_t sp = ctx->s_p[w];
 		unsigned long long *bank = w ? ctx->d_ctr + NCTR + 8 : ctx->d_ctr;
 		cudaStreamWaitEvent(sp, ev_in[std::min(b + 1, nb - 1)], 0);     // thresholds of a band's last row read the next band's first row
@@ -1253,145 +1311,121 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		}
 		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sp>>>(ta);
 		ctx->launches++;
+		mark("  thresh end", b, sp);
 		if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p + 2 * P1_NBUCKET * w, ord, t0, nt, 0u, 0u, sp);
+		mark("  order end", b, sp);
+		g.redo = redo_of(b);
 		plan.launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, 0, bank, ord);
 		ev_p1[b] = pr.event();
 		cudaEventRecord(ev_p1[b], sp);
 		mark("pass1 end", b, sp);
 	};
-	// the second-half stream continues once the band is done: whatever outgrew the fast paths so far is redone there
+	// whatever outgrew the fast paths of band b is redone on a stream of its own, in band order: ev_r1[b] = pass 1 of
+	// the bands 0 .. b is complete
 	auto pass1_redo = [&](int b) {
-		cudaStreamWaitEvent(sm, ev_p1[b], 0);
-		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a1);     // (re-runs earlier bands' overflow lists as well: idempotent)
+		cudaStreamWaitEvent(s_redo, ev_p1[b], 0);
+		a1.redo = redo_of(b);
+		a1.wk = Work{a1.redo.list, 0ull, a1.redo.count, a1.redo.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
+		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, s_redo>>>(a1);
 		ctx->launches++;
+		ev_r1[b] = pr.event();
+		cudaEventRecord(ev_r1[b], s_redo);
 	};
 
-	// Per-band state of the second half (pass 2 -> prefix sum -> compaction -> download). A band is ENQUEUED
-	// (gather, redo, scan, asynchronous readback of its counters and total) one iteration before it is FINISHED
-	// (wait for the readback, allocate, compact, download), so the compute stream always has the next band's
-	// pass 1 queued while the host waits.
-	struct Band {
-		int y0 = 0, y1 = 0;
-		StageBuf sb;
-		RedoBuf rb;
-		Tmp<unsigned long long> sums;
-		vo_dvol *v = nullptr;
-		unsigned long long *h = nullptr;      // pinned: NCTR counters + total
-		cudaEvent_t ready = nullptr;
-		explicit Band(vo_ctx *c) : sb(c), rb(c), sums(c) {}
-	};
-	std::vector<std::unique_ptr<Band>> bstate;
-	unsigned long long *h_pin = (unsigned long long *)host_block((size_t)nb * (NCTR + 1) * sizeof(unsigned long long));
-	if (!h_pin) { drop_host(); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
-	uint64_t base = 0;          // intervals of the bands finished so far
-	std::vector<vo_dvol *> bands;
+	// Second half of a band: pass 2 -> prefix sum -> compaction, enqueued WITHOUT a host round trip. The bands share
+	// whole-grid staging buffers (each uses its slice) and write one result volume on the device; the running interval
+	// total lives on the device (gb[b] = intervals of the bands before b), so the offsets come out global. The host only
+	// learns the totals to size the downloads, on a control stream of its own: the compute streams never wait for it.
 	int rc = VO_OK;
 	// declared last, hence destroyed first: on every way out the side streams are drained BEFORE the temporaries above
 	// go back to the pool of the context stream (stream-ordered frees only order against that stream)
-	struct Join { vo_ctx *c; ~Join() { cudaStreamSynchronize(c->s_hi); for (auto st : c->s_p) cudaStreamSynchronize(st); } } join{ctx};
+	struct Join { vo_ctx *c; ~Join() { for (auto st : c->s_hi) cudaStreamSynchronize(st); cudaStreamSynchronize(c->s_ctl); for (auto st : c->s_p) cudaStreamSynchronize(st); } } join{ctx};
 
-	auto enqueue_band = [&](int b) -> int {
-		std::unique_ptr<Band> B(new Band(ctx));
-		B->y0 = b * BH; B->y1 = std::min(ny, B->y0 + BH);
-		const unsigned long long nlists = (unsigned long long)nx * (B->y1 - B->y0);
-		VO_TRY(B->sb.alloc(nlists, 65536ull + nlists / 8));
-		VO_TRY(B->rb.alloc((unsigned int)std::min<unsigned long long>(nlists, 1ull << 22), 8));
-		VO_TRY(new_dvol(ctx, nx, B->y1 - B->y0, &B->v));
+	std::vector<cudaEvent_t> ev_tot(nb);
+	auto second_half = [&](int b) {
+		const int y0 = ys[b], y1 = ys[b + 1];
+		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
 		const unsigned int nt = blocks_for(nlists, SCAN_TILE);
-		VO_TRY(dalloc(ctx, &B->sums.p, (unsigned long long)nt + 1));
-		B->h = h_pin + (size_t)b * (NCTR + 1);
-		B->ready = pr.event();
-		cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), sm);
-		cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), sm);
+		unsigned long long *sums_b = sums.p + (size_t)b * (nt_max + 1);
+		Stage st = sb.st;
+		st.cnt += c0; st.inl += c0 * STAGE_INLINE;
+		const Redo rd{redo2.p + (size_t)b * rcap2, reinterpret_cast<unsigned int *>(gb.p + nb + 1 + b), rcap2};
+		cudaStream_t sm = sh[b & 1];                        // consecutive bands overlap; only the running total is a chain
+		cudaStreamWaitEvent(sm, ev_r1[std::min(b + 1, nb - 1)], 0);     // pass 2 of band b reads the mid rows of band b+1
 		mark("pass2 begin", b, sm);
 		Pass2Args a2;
-		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = B->y0; a2.y1 = B->y1;
-		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.st = B->sb.st; a2.redo = B->rb.rd;
+		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = y0; a2.y1 = y1;
+		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.st = st; a2.redo = rd;
 		a2.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
-		k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(B->y1 - B->y0), P2_TX, 0, sm>>>(a2);
-		a2.wk = Work{B->rb.rd.list, 0ull, B->rb.rd.count, B->rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
+		k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		a2.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
 		k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
-		k_scan_reduce<<<nt, SCAN_THREADS, 0, sm>>>(B->sb.st.cnt, nlists, B->sums.p);
-		k_scan_tiles<<<1, 1024, 0, sm>>>(B->sums.p, nt);
-		k_scan_apply<<<nt, SCAN_THREADS, 0, sm>>>(B->sb.st.cnt, nlists, B->sums.p, B->v->off);
-		ctx->launches += 5;
-		cudaMemcpyAsync(B->h, ctx->d_ctr, NCTR * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm);
-		cudaMemcpyAsync(B->h + NCTR, B->sums.p + nt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sm);
-		cudaEventRecord(B->ready, sm);
+		k_scan_reduce<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b);
+		if (b > 0) cudaStreamWaitEvent(sm, ev_scan[b - 1], 0);
+		k_scan_tiles<<<1, 1024, 0, sm>>>(sums_b, nt, gb.p + b, gb.p + b + 1);
+		ev_scan[b] = pr.event();
+		cudaEventRecord(ev_scan[b], sm);
+		k_scan_apply<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b, dout->off + c0);
+		k_compact<<<blocks_for(nlists, 256), 256, 0, sm>>>(st, nlists, dout->off + c0, dout->spans, dcap);
+		ctx->launches += 6;
+		cudaEventRecord(ev_done[b], sm);
 		mark("pass2 end", b, sm);
-		bstate.push_back(std::move(B));
-		return VO_OK;
+		cudaStreamWaitEvent(ctx->s_ctl, ev_done[b], 0);
+		cudaMemcpyAsync(h_tot + b, gb.p + b + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_ctl);
+		ev_tot[b] = pr.event();
+		cudaEventRecord(ev_tot[b], ctx->s_ctl);
 	};
 
-	auto finish_band = [&](Band &B) -> int {
-		const unsigned long long c0 = (unsigned long long)B.y0 * nx, c1 = (unsigned long long)B.y1 * nx;
-		const unsigned long long nlists = c1 - c0;
-		VO_CUDA(cudaEventSynchronize(B.ready));
-		const unsigned long long total = B.h[NCTR];
-		if (B.h[8] > B.rb.rd.cap || B.h[9] || B.h[1] > B.sb.st.pool_cap) return PIPE_NA;      // rare: plain path handles it
-		if (base + total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
-		VO_TRY(dalloc(ctx, &B.v->spans, total));
-		B.v->nspans = total;
-		if (base + total > hs_cap) {                        // grow the pinned span buffer (keeps what is already there)
-			cudaStreamSynchronize(pr.s_out);
-			const uint64_t ncap = 2 * (base + total) + (1u << 16);
-			double *nh = (double *)host_block(ncap * sizeof(double2));
-			if (!nh) return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed");
-			std::memcpy(nh, hs, base * sizeof(double2));
-			vo_free(hs);
-			hs = nh; hs_cap = ncap;
-		}
-		k_compact<<<blocks_for(nlists, 256), 256, 0, sm>>>(B.sb.st, nlists, B.v->off, B.v->spans);
-		if (base) k_rebase<<<blocks_for(nlists + 1, 256), 256, 0, sm>>>(B.v->off, nlists + 1, 0u, (uint32_t)base);
-		ctx->launches += 2;
-		cudaEvent_t done = pr.event();
-		cudaEventRecord(done, sm);
-		cudaStreamWaitEvent(pr.s_out, done, 0);
-		mark("compact end", B.y0 / BH, sm);
-		mark("download begin", B.y0 / BH, pr.s_out);
-		cudaMemcpyAsync(ho + c0, B.v->off, (nlists + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
-		if (total) cudaMemcpyAsync(hs + 2 * base, B.v->spans, total * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
-		mark("download end", B.y0 / BH, pr.s_out);
-		base += total;
-		bands.push_back(B.v);       // released after the output stream has drained (no stall of the compute stream)
-		B.v = nullptr;
-		return VO_OK;
-	};
-
-	// Pass 1 of EVERY band is enqueued up front (it only waits for its upload), so the host's waits for the band
-	// totals below never leave the device without work.
+	// Everything is enqueued up front: pass 1 of every band (it only waits for its upload), then the second halves
+	// (pass 2 of band b-1 needs pass 1 of band b). After that the host follows the bands and starts their downloads.
 	for (int b = 0; b < nb; ++b) pass1_band(b);
-	for (int b = 0; b <= nb + 1 && rc == VO_OK; ++b) {
-		if (b < nb) pass1_redo(b);
-		if (b >= 1 && b - 1 < nb) rc = enqueue_band(b - 1);                  // pass 2 of band b-1 needs pass 1 of band b
-		if (rc == VO_OK && b >= 2) rc = finish_band(*bstate[b - 2]);
+	for (int b = 0; b < nb; ++b) pass1_redo(b);
+	for (int b = 0; b < nb; ++b) second_half(b);
+	uint64_t base = 0;          // intervals of the bands downloaded so far
+	for (int b = 0; b < nb && rc == VO_OK; ++b) {
+		const int y0 = ys[b], y1 = ys[b + 1];
+		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
+		if (cudaEventSynchronize(ev_tot[b]) != cudaSuccess) { rc = PIPE_NA; break; }
+		const uint64_t tot = h_tot[b];
+		if (tot > dcap) {                                   // result buffers too small (first call, or a much larger result): plain path
+			ctx->out_hint = std::max<uint64_t>(ctx->out_hint, 2 * tot);
+			rc = PIPE_NA;
+			break;
+		}
+		mark("download begin", b, pr.s_out);
+		cudaMemcpyAsync(ho + c0, dout->off + c0, (nlists + (b == nb - 1 ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+		if (tot > base) cudaMemcpyAsync(hs + 2 * base, dout->spans + base, (tot - base) * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
+		mark("download end", b, pr.s_out);
+		base = tot;
 	}
-	for (auto &B : bstate) if (B->v) { free_dvol(ctx, B->v); B->v = nullptr; }
 	{
-		cudaEvent_t ev_fin = pr.event();
-		cudaEventRecord(ev_fin, sm);
 		for (auto st : ctx->s_p) { cudaEvent_t e = pr.event(); cudaEventRecord(e, st); cudaStreamWaitEvent(ctx->stream, e, 0); }
-		cudaStreamWaitEvent(ctx->stream, ev_fin, 0);
+		for (auto st : ctx->s_hi) { cudaEvent_t e = pr.event(); cudaEventRecord(e, st); cudaStreamWaitEvent(ctx->stream, e, 0); }
 	}
 	cudaEventRecord(ctx->ev[2], ctx->stream);
 	unsigned long long h[NCTR];
+	std::vector<unsigned long long> hgb(3 * (size_t)nb + 1, 0ull);
+	if (rc == VO_OK && cudaMemcpyAsync(hgb.data(), gb.p, hgb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = PIPE_NA;
 	if (rc == VO_OK) rc = read_counters(ctx, h);
 	cudaStreamSynchronize(pr.s_out);
 	cudaStreamSynchronize(pr.s_in);
-	for (auto bd : bands) free_dvol(ctx, bd);
-	bstate.clear();
-	vo_free(h_pin);
+	vo_free(h_tot);
+	if (rc == VO_OK) {
+		bool redo = h[9] != 0 || h[1] > sb.st.pool_cap;         // rare: the plain path regrows / reports
+		for (int b = 0; b < nb; ++b) redo = redo || (unsigned int)hgb[nb + 1 + b] > rcap2 || (unsigned int)hgb[2 * nb + 1 + b] > rcap1;
+		if (redo) rc = PIPE_NA;
+	}
 	if (trace && !marks.empty()) {
 		float t = 0;
 		if (ev_up_done) { cudaEventElapsedTime(&t, marks[0].second, ev_up_done); std::fprintf(stderr, "[vo trace] %-18s %8.3f ms\n", "uploads end", t); cudaEventDestroy(ev_up_done); }
 		for (auto &mk : marks) {
-			if (cudaEventElapsedTime(&t, marks[0].second, mk.second) == cudaSuccess) std::fprintf(stderr, "[vo trace] %-18s %8.3f ms\n", mk.first.c_str(), t);
+			if (cudaEventElapsedTime(&t, marks[0].second, mk.second) == cudaSuccess) std::fprintf(stderr, "[vo trace] %8.3f ms  %s\n", t, mk.first.c_str());
 		}
 		for (auto &mk : marks) cudaEventDestroy(mk.second);
 		cudaGetLastError();
 	}
 	if (rc == VO_OK && cudaGetLastError() != cudaSuccess) rc = PIPE_NA;
-	if (rc == VO_OK && (h[0] > m->pool_cap || h[2] > redo_cap || h[4])) {
+	if (rc == VO_OK && (h[0] > m->pool_cap || h[4])) {
 		ctx->pool_hint = std::max<unsigned long long>(ctx->pool_hint, h[0] + h[0] / 4);
 		rc = PIPE_NA;                                           // let the plain path deal with it (it regrows / reports)
 	}
@@ -1717,7 +1751,8 @@ void vo_destroy(vo_ctx *ctx)
 	for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
 	for (auto &st : ctx->s_p) if (st) cudaStreamDestroy(st);
-	if (ctx->s_hi) cudaStreamDestroy(ctx->s_hi);
+	for (auto &st : ctx->s_hi) if (st) cudaStreamDestroy(st);
+	if (ctx->s_ctl) cudaStreamDestroy(ctx->s_ctl);
 	if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
 	if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1742,6 +1777,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "bands") == 0) {
 		const int n = std::atoi(value);
 		if (n >= 3 && n <= 64) { ctx->pipe_bands = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "tile_ctas") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 1 && n <= 8) { ctx->tile_ctas = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "tile_order") == 0) {
 		if (std::strcmp(value, "off") == 0) { ctx->tile_order = false; return VO_OK; }
