@@ -1462,6 +1462,8 @@ struct vo_slab {
 	uint4 *thr = nullptr;
 	unsigned int *big_tiles = nullptr, *multi_tiles = nullptr;
 	unsigned int *big_tiles_b = nullptr, *multi_tiles_b = nullptr;   // ... of the boundary rows' launch set
+	unsigned int *est = nullptr, *order = nullptr;  // tile order (expensive first): [2 sets x 2 P1_NBUCKET counters | cost per tile]; permutations of the two sets
+	unsigned long long ntiles = 0;
 	cudaEvent_t ev_setup = nullptr, ev_side = nullptr;
 	unsigned long long *redo_list = nullptr;
 	unsigned int redo_cap = 0;
@@ -1478,7 +1480,7 @@ void free_slab(vo_slab *S)
 	free_dvol(ctx, S->ext);
 	if (S->mid) vo_dmid_free(ctx, S->mid);
 	dfree(ctx, S->thr); dfree(ctx, S->big_tiles); dfree(ctx, S->multi_tiles); dfree(ctx, S->redo_list);
-	dfree(ctx, S->big_tiles_b); dfree(ctx, S->multi_tiles_b);
+	dfree(ctx, S->big_tiles_b); dfree(ctx, S->multi_tiles_b); dfree(ctx, S->est); dfree(ctx, S->order);
 	for (cudaEvent_t e : {S->ev0, S->ev1, S->ev2, S->ev_setup, S->ev_side}) if (e) cudaEventDestroy(e);
 	delete S;
 }
@@ -1506,12 +1508,21 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	ta.Dmono = tc->tt.Dmono; ta.Emono = tc->tt.Emono; ta.G = tc->tt.G; ta.reach = tc->dt.reach; ta.thr = S->thr;
 	ta.clip_lo = -std::numeric_limits<double>::infinity(); ta.clip_hi = std::numeric_limits<double>::infinity();
 	ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
+	if (S->est) { ta.est = S->est + 4 * P1_NBUCKET; ta.tiles_xw = S->plan.tiles_xw; }
 	k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
 	ctx->launches++;
 	if (y1b > y0b) {
 		ta.c_begin = (unsigned long long)y0b * nx; ta.c_end = (unsigned long long)y1b * nx;
 		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
 		ctx->launches++;
+	}
+	const unsigned int *order = nullptr;
+	if (S->est) {      // (each of the two launch sets of a step orders its tiles once: the counters were zeroed by vo_slab_begin)
+		unsigned int *ord = S->order + (side ? S->ntiles : 0ull);
+		TilePlan::order_tiles(ctx, ta.est, S->est + (side ? 2 * P1_NBUCKET : 0), ord, (unsigned int)S->plan.tiles_xw * (unsigned int)y0,
+		                      (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0), (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
+		                      (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), sm);
+		order = ord;
 	}
 	vo_dmid *m = S->mid;
 	Redo rd{S->redo_list, reinterpret_cast<unsigned int *>(ctx->d_ctr + 2), S->redo_cap};
@@ -1525,7 +1536,7 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	S->plan.launch(ctx, g, (unsigned int)S->plan.tiles_xw * (unsigned int)y0, (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0),
 	               side ? S->big_tiles_b : S->big_tiles, side ? S->multi_tiles_b : S->multi_tiles, sm,
 	               (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
-	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms, bank);
+	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms, bank, order);
 	if (interior) { cudaEventRecord(ctx->kev[1], sm); ctx->kev_valid[0] = true; }
 	if (side) return;
 	slab_redo(S);
@@ -1595,6 +1606,9 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	const unsigned long long ntiles_b = (unsigned long long)S->plan.tiles_xw * (jp + jn + 2);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->big_tiles_b, ntiles_b);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->multi_tiles_b, ntiles_b);
+	S->ntiles = ntiles;
+	if (rc == VO_OK && ctx->tile_order) rc = dalloc(ctx, &S->est, ntiles + 4 * P1_NBUCKET);
+	if (rc == VO_OK && ctx->tile_order) rc = dalloc(ctx, &S->order, 2 * ntiles);
 	if (rc == VO_OK && !ctx->s_in && cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); rc = fail(ctx, VO_ERR_CUDA, "cudaStreamCreate"); }
 	S->redo_cap = (unsigned int)std::min<unsigned long long>(nslots, 1ull << 22);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->redo_list, S->redo_cap);
@@ -1623,6 +1637,7 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	}
 	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), sm);
 	cudaMemsetAsync(m->tilemask, 0, nmask * sizeof(unsigned long long), sm);
+	if (S->est) cudaMemsetAsync(S->est, 0, (ntiles + 4 * P1_NBUCKET) * sizeof(unsigned int), sm);
 	// own rows into the extended volume: offsets shifted by the reserved region of the previous halo
 	cudaMemcpyAsync(S->ext->off + (size_t)jp * nx, own->off, (nown + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, sm);
 	if (cap_prev) { k_rebase<<<blocks_for(nown + 1, 256), 256, 0, sm>>>(S->ext->off + (size_t)jp * nx, nown + 1, 0u, (uint32_t)cap_prev); ctx->launches++; }
