@@ -212,6 +212,96 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	}
 }
 
+// Four lanes per column, one per lattice neighbour (0: left, 1: right, 2: row above, 3: row below): each computes
+// the nn values of the column's intervals against ITS neighbour and the near threshold that follows from them, the
+// quad exchanges them by shuffles, the x lanes then search the far thresholds (they need T = max of the y lanes'
+// results) and lane 0 writes the 16 bytes. Columns with many intervals (lattices: 10 x 10 pairs per neighbour)
+// get four times the parallelism. Used for volumes with several intervals per column (launch_thresh in vo_lib.cu);
+// for sparse height-field-like volumes the four-fold thread count costs more than it gives (C5: 0.27 vs 0.12 ms).
+constexpr int TH_Q = 4;
+__global__ void __launch_bounds__(256) k_thresh_quad(ThreshArgs a)
+{
+	extern __shared__ double s_DE[];
+	double *s_D = s_DE, *s_E = s_DE + a.J + 2;
+	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) { s_D[i] = a.Dmono[i]; s_E[i] = a.Emono[i]; }
+	__syncthreads();
+	const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const unsigned long long c = a.c_begin + t / TH_Q;
+	const int dir = (int)(threadIdx.x & (TH_Q - 1)), lane = (int)(threadIdx.x & 31);
+	const unsigned int qmask = 0xFu << (lane & ~(TH_Q - 1));
+	const bool in_range = c < a.c_end;
+	if (!a.est && !in_range) return;
+	uint32_t o0 = 0, o1 = 0;
+	if (in_range) { o0 = __ldg(a.off + c); o1 = __ldg(a.off + c + 1); }
+	if (!a.est && o0 == o1) return;
+	const int J = a.J, JP = J + 1;
+	const int x = in_range ? (int)(c % (unsigned)a.nx) : 0, y = in_range ? (int)(c / (unsigned)a.nx) : 0;
+	uint32_t q0 = 0, q1 = 0;                             // this lane's neighbour column (empty range: none)
+	if (o0 != o1) {
+		if (dir == 0) { if (x > 0) { q0 = __ldg(a.off + c - 1); q1 = o0; } }
+		else if (dir == 1) { if (x < a.nx - 1) { q0 = o1; q1 = __ldg(a.off + c + 2); } }
+		else if (dir == 2) { if (y > 0) { q0 = __ldg(a.off + c - a.nx); q1 = __ldg(a.off + c - a.nx + 1); } }
+		else { if (y < a.ny - 1) { q0 = __ldg(a.off + c + a.nx); q1 = __ldg(a.off + c + a.nx + 1); } }
+	}
+	unsigned int cost_l = 0, cost_s = 0, cost_r = 0;     // pairs of this column with outputs in the tile on the left / its own / on the right
+	const int xi = x & (P1_W - 1);
+	for (uint32_t k = o0; k < o1; ++k) {                 // (the same trip count in all four lanes of a quad)
+		const double2 p = __ldg(a.spans + k);
+		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
+		// An entry with z1 > z2 is not an interval; it is never pruned and never prunes. (The one known source - the
+		// erosion of data outside [zmin, zmax], where negate_ray prepends the bound without looking,
+		// MorphologyOperators.cpp:241-248 - is sent to the unpruned kernel by erode() anyway.)
+		const bool proper = p.x <= p.y;
+		const double pinf = __longlong_as_double(0x7FF0000000000000LL);
+		const double nn = proper ? nn_of(p, a.spans, q0, q1, a.clip_lo, a.clip_hi) : pinf;
+		// an interval saturated on both sides covers the whole range: it yields to a CLOSER one of its kind (near
+		// tests) but never to a farther one - otherwise two of them could drop each other
+		const bool whole = p.x <= a.clip_lo && p.y >= a.clip_hi;
+		const int tnear = first_ge(dir < 2 ? s_D : s_E, J, nn + m);      // tnL, tnR, Ty_up, Ty_dn by lane
+		const float fv = far_value(nn, m, whole);
+		const int tnL = __shfl_sync(qmask, tnear, 0, TH_Q), tnR = __shfl_sync(qmask, tnear, 1, TH_Q);
+		const int tyu = __shfl_sync(qmask, tnear, 2, TH_Q), tyd = __shfl_sync(qmask, tnear, 3, TH_Q);
+		const int T = max(tyu, tyd);
+		// far, x: the outputs on the LEFT have the right neighbour as the farther one, so lane 1 finds tfL and lane 0 tfR
+		int tfar = 1;
+		if (J >= 1 && dir < 2) tfar = first_gt(a.G + (size_t)(T - 1) * JP, J, fv);
+		const int tfL = __shfl_sync(qmask, tfar, 1, TH_Q), tfR = __shfl_sync(qmask, tfar, 0, TH_Q);
+		const float vD = __shfl_sync(qmask, fv, 3, TH_Q), vU = __shfl_sync(qmask, fv, 2, TH_Q);
+		if (dir == 0) {
+			const int rx = __ldg(a.reach + T - 1);
+			const uint32_t layer = min(k - o0, 3u);
+			uint4 th;
+			th.x = (uint32_t)tnL | ((uint32_t)tnR << 8) | ((uint32_t)tfL << 16) | ((uint32_t)tfR << 24);
+			th.y = (uint32_t)(tyu - 1) | ((uint32_t)(tyd - 1) << 8) | (layer << 16) | ((uint32_t)rx << 24);
+			th.z = __float_as_uint(vD);                                 // consumers above: row y+1 is farther
+			th.w = __float_as_uint(vU);
+			a.thr[k] = th;
+			if (a.est) {
+				// the distances Tile::scatter will list this interval at: {0} and [s, hi] on the left, [s, hi] on the right
+				const unsigned int w = 4u + (unsigned int)T;
+				const int hiL = min(tnL - 1, J), sL = max(1, min(tfL, rx)), hiR = min(tnR - 1, J), sR = max(1, min(tfR, rx));
+				const int nL = max(0, hiL - sL + 1), nLs = max(0, min(hiL, xi) - sL + 1);
+				const int nR = max(0, hiR - sR + 1), nRs = max(0, min(hiR, P1_W - 1 - xi) - sR + 1);
+				cost_s += w * (unsigned int)(1 + nLs + nRs);
+				cost_l += w * (unsigned int)(nL - nLs);
+				cost_r += w * (unsigned int)(nR - nRs);
+			}
+		}
+	}
+	if (a.est) {
+		// one atomic per warp and tile (a warp holds eight consecutive columns: usually a single tile)
+		const unsigned int tile = in_range ? (unsigned int)y * (unsigned int)a.tiles_xw + (unsigned int)(x / P1_W) : 0xffffffffu;
+		const unsigned int grp = __match_any_sync(0xffffffffu, tile);
+		const unsigned int sl = __reduce_add_sync(grp, cost_l), ss = __reduce_add_sync(grp, cost_s), sr = __reduce_add_sync(grp, cost_r);
+		if (in_range && lane == __ffs(grp) - 1) {
+			const int tx = x / P1_W;
+			if (ss) atomicAdd(a.est + tile, ss);
+			if (sl && tx > 0) atomicAdd(a.est + tile - 1, sl);
+			if (sr && tx + 1 < a.tiles_xw) atomicAdd(a.est + tile + 1, sr);
+		}
+	}
+}
+
 // ---- tile order: expensive tiles first (costs differ by two orders of magnitude; a launch that ends with the
 // expensive ones ends with a long tail of a few busy warps). Buckets of log2(cost), descending; the order inside a
 // bucket is whatever the atomics give.

@@ -51,6 +51,7 @@ struct vo_ctx {
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
+	int band_split = 2;               // vo_set_option("band_split", "N"): a band's pass-1 launch set takes 1/N of the SMs (host-buffer pipeline)
 	int pipe_bands = 8;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
 	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
@@ -534,6 +535,16 @@ int get_tables(vo_ctx *ctx, double R, bool need_tile, TableCache **out)
 
 // Launch plan of the tile kernel (pass1_tile.cuh): candidate-buffer sizes, warps per CTA and shared memory of the
 // three launches, from the grid and the mean fill. One CTA per SM; warps work on their own.
+// thresholds of the columns [ta.c_begin, ta.c_end): one thread per column, or four (one per neighbour) when the
+// columns hold several intervals each
+inline void launch_thresh(const ThreshArgs &ta, double k_in, cudaStream_t s)
+{
+	const unsigned long long n = ta.c_end - ta.c_begin;
+	const size_t smem = 2 * (size_t)(ta.J + 2) * sizeof(double);
+	if (k_in >= 4.0) k_thresh_quad<<<blocks_for(TH_Q * n, 256), 256, smem, s>>>(ta);
+	else k_thresh<<<blocks_for(n, 256), 256, smem, s>>>(ta);
+}
+
 struct TilePlan {
 	int J = 0, tiles_xw = 0, tiles_x = 0, sms = 148, cps = 1;
 	int cmax_small = 0, cmax_big = 0, cmax_multi = 0;
@@ -703,7 +714,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 				cudaMemsetAsync(est.p, 0, (ntiles + 2 * P1_NBUCKET) * sizeof(unsigned int), ctx->stream);
 				ta.est = est.p + 2 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw;
 			}
-			k_thresh<<<blocks_for(ncols, 256), 256, 2 * (size_t)(t.J + 2) * sizeof(double), ctx->stream>>>(ta);
+			launch_thresh(ta, k_in, ctx->stream);
 			ctx->launches++;
 			if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p, order.p, 0u, (unsigned int)ntiles, 0u, 0u, ctx->stream);
 			Pass1TileArgs g;
@@ -1309,13 +1320,16 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			ta.est = est.p + 4 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw;
 			ord = (w ? order1.p : order0.p) + t0;
 		}
-		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sp>>>(ta);
+		launch_thresh(ta, k_in, sp);
 		ctx->launches++;
 		mark("  thresh end", b, sp);
 		if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p + 2 * P1_NBUCKET * w, ord, t0, nt, 0u, 0u, sp);
 		mark("  order end", b, sp);
 		g.redo = redo_of(b);
-		plan.launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, 0, bank, ord);
+		// (the two streams' launch sets may each take a share of the SMs, so that they run side by side instead of the
+		// second waiting for CTAs of the first to retire)
+		const int reserve = ctx->band_split > 1 ? plan.sms - plan.sms / ctx->band_split : 0;
+		plan.launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, reserve, bank, ord);
 		ev_p1[b] = pr.event();
 		cudaEventRecord(ev_p1[b], sp);
 		mark("pass1 end", b, sp);
@@ -1464,6 +1478,7 @@ struct vo_slab {
 	unsigned int *big_tiles_b = nullptr, *multi_tiles_b = nullptr;   // ... of the boundary rows' launch set
 	unsigned int *est = nullptr, *order = nullptr;  // tile order (expensive first): [2 sets x 2 P1_NBUCKET counters | cost per tile]; permutations of the two sets
 	unsigned long long ntiles = 0;
+	double k_in = 0;
 	cudaEvent_t ev_setup = nullptr, ev_side = nullptr;
 	unsigned long long *redo_list = nullptr;
 	unsigned int redo_cap = 0;
@@ -1509,11 +1524,11 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	ta.clip_lo = -std::numeric_limits<double>::infinity(); ta.clip_hi = std::numeric_limits<double>::infinity();
 	ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
 	if (S->est) { ta.est = S->est + 4 * P1_NBUCKET; ta.tiles_xw = S->plan.tiles_xw; }
-	k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
+	launch_thresh(ta, S->k_in, sm);
 	ctx->launches++;
 	if (y1b > y0b) {
 		ta.c_begin = (unsigned long long)y0b * nx; ta.c_end = (unsigned long long)y1b * nx;
-		k_thresh<<<blocks_for(ta.c_end - ta.c_begin, 256), 256, 2 * (size_t)(J + 2) * sizeof(double), sm>>>(ta);
+		launch_thresh(ta, S->k_in, sm);
 		ctx->launches++;
 	}
 	const unsigned int *order = nullptr;
@@ -1597,6 +1612,7 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	rc = dalloc(ctx, &m->slots, nslots);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, m->pool_cap);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, 2 * ncols);
+	S->k_in = k_in;
 	if (rc == VO_OK) rc = S->plan.init(ctx, nx, J, k_in);
 	const unsigned long long nmask = 2ull * ey * S->plan.tiles_x, ntiles = (unsigned long long)S->plan.tiles_xw * ey;
 	if (rc == VO_OK) rc = dalloc(ctx, &m->tilemask, nmask);
@@ -1792,6 +1808,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "bands") == 0) {
 		const int n = std::atoi(value);
 		if (n >= 3 && n <= 64) { ctx->pipe_bands = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "band_split") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 1 && n <= 4) { ctx->band_split = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "tile_ctas") == 0) {
 		const int n = std::atoi(value);
