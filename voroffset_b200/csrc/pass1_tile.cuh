@@ -59,8 +59,10 @@ constexpr int P1_W = 32;        // output columns of a tile = lanes of the warp 
 constexpr int P1_TX = 128;      // columns per tile mask (the unit pass 2 skips producer rows by)
 constexpr int P1_CB = 4;        // classes evaluated together in registers
 constexpr int P1_LCAP_S = 24;   // survivors listed per output column, single-interval launch
-constexpr int P1_LCAP_M = 64;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
-constexpr int P1_MAXWARPS = 16; // warps per CTA (one CTA per SM; fewer when the per-warp buffers are large)
+constexpr int P1_LCAP_M = 32;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
+constexpr int P1_MAXWARPS = 16; // warps per CTA (one CTA per SM; fewer when the per-warp buffers are large). (20 warps at 96
+                                // registers were tried: the spills cost more than the extra warps give, 0.71 vs 0.65 ms on C5.)
+constexpr int P1_MAXWARPS_M = 16; // ... of the two-hull variant
 constexpr int P1_OVF = 224;     // further survivors per output column kept in a global-memory spill area of the warp
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
@@ -405,11 +407,12 @@ __host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap)
 	const size_t SEG = (size_t)P1_W + 2 * J;
 	size_t b = 0;
 	b += 2 * (size_t)cmax * sizeof(double2);                // candidates (double-buffered: the next tile is staged
-	b += 2 * (size_t)cmax * sizeof(uint4);                  // their thresholds    while the current one is processed)
+	b += (size_t)cmax * sizeof(uint4);                      // their thresholds    while the current one is processed); the
+	                                                        // thresholds are only read by phase 1: ONE buffer, refilled after it
 	b += 2 * ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);   // segment offsets (double-buffered)
 	b += (size_t)P1_W * sizeof(uint32_t);                   // list lengths
 	b += (size_t)lcap * P1_W * sizeof(uint32_t);            // survivor lists [s][lane]
-	b += 2 * (((size_t)cmax + 15) & ~(size_t)15);           // segment column of each candidate (double-buffered)
+	b += 4 * (((size_t)cmax + 15) & ~(size_t)15);           // segment column and layer of each candidate (double-buffered)
 	b += 2 * sizeof(unsigned long long);                    // mbarriers of the two staging buffers
 	return b;
 }
@@ -457,24 +460,25 @@ struct TableSmem {
 };
 struct WarpSmem {
 	double2 *cand[2];
-	uint4 *thr[2];
+	uint4 *thr;
 	uint32_t *off[2], *cnt, *list;
-	uint8_t *ci[2];
+	uint8_t *ci[2], *ly[2];
 	unsigned long long *mbar;      // [2]
 	__device__ __forceinline__ WarpSmem(unsigned char *raw, int J, int cmax, int lcap)
 	{
 		const int SEG = P1_W + 2 * J;
 		cand[0] = reinterpret_cast<double2 *>(raw);
 		cand[1] = cand[0] + cmax;
-		thr[0] = reinterpret_cast<uint4 *>(cand[1] + cmax);
-		thr[1] = thr[0] + cmax;
-		off[0] = reinterpret_cast<uint32_t *>(thr[1] + cmax);
+		thr = reinterpret_cast<uint4 *>(cand[1] + cmax);
+		off[0] = reinterpret_cast<uint32_t *>(thr + cmax);
 		off[1] = off[0] + ((SEG + 4) & ~3);
 		cnt = off[1] + ((SEG + 4) & ~3);
 		list = cnt + P1_W;
 		ci[0] = reinterpret_cast<uint8_t *>(list + (size_t)lcap * P1_W);
 		ci[1] = ci[0] + ((cmax + 15) & ~15);
-		mbar = reinterpret_cast<unsigned long long *>(ci[1] + ((cmax + 15) & ~15));
+		ly[0] = ci[1] + ((cmax + 15) & ~15);
+		ly[1] = ly[0] + ((cmax + 15) & ~15);
+		mbar = reinterpret_cast<unsigned long long *>(ly[1] + ((cmax + 15) & ~15));
 	}
 };
 
@@ -519,8 +523,10 @@ __device__ __forceinline__ uint32_t entry_windows(uint32_t e)        // -> lo_u 
 template <int LCAP>
 struct Tile {
 	const double2 *cand;
-	const uint4 *thr;
+	const uint4 *thr;          // thresholds of the candidates: valid during phase 1 only (the buffer is refilled for the next tile)
+	const uint4 *gthr;         // ... the same in global memory (phase 2, direct mode)
 	const uint8_t *ci;         // segment column of each candidate
+	const uint8_t *ly;         // its layer (position inside its column, 3 = third or later)
 	const double *Ht;
 	const float *Ef;
 	const uint8_t *jmax;
@@ -591,7 +597,7 @@ struct TileThread {
 	// direct mode (the list overflowed): candidate k of the range re-tested for this output
 	__device__ __forceinline__ bool pair_direct(int k, int &d, uint32_t &w) const
 	{
-		const uint4 th = t.thr[k];
+		const uint4 th = __ldg(t.gthr + k);
 		const int i = (int)t.ci[k];
 		d = abs(i - ix);
 		const bool left = ix < i;
@@ -620,7 +626,7 @@ struct TileThread {
 		k = kb + s;
 		return pair_direct(k, d, w);
 	}
-	__device__ __forceinline__ int layer(int k) const { return (int)((t.thr[k].y >> 16) & 3u); }
+	__device__ __forceinline__ int layer(int k) const { return (int)t.ly[k]; }
 };
 
 // bits q in [0, CB) with l <= cb + q < h
@@ -873,7 +879,7 @@ __device__ __forceinline__ void tile_other(const Pass1TileArgs &a, const TileHea
 //     thresholds into the other staging buffer; they land during phase 2 of the current tile and are awaited
 //     (mbarrier) at the top of the next iteration.
 template <int CAP, bool MULTI, bool LIST>
-__global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArgs a)
+__global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1) k_pass1_tile(Pass1TileArgs a)
 {
 	constexpr int LCAP = (MULTI || LIST) ? P1_LCAP_M : P1_LCAP_S;
 	constexpr int NR = 5;                                   // segment offsets per lane: P1_W + 2 * 63 + 1 <= 32 * NR
@@ -938,11 +944,11 @@ __global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArg
 			const unsigned int bytes = (unsigned int)h.ncand * 16u;
 			mbar_expect_tx(sm.mbar + b, 2u * bytes);
 			bulk_g2s(sm.cand[b], a.spans + h.base, bytes, sm.mbar + b);
-			bulk_g2s(sm.thr[b], a.thr + h.base, bytes, sm.mbar + b);
+			bulk_g2s(sm.thr, a.thr + h.base, bytes, sm.mbar + b);
 		}
 		const uint32_t *s_off = sm.off[b];
 		for (int i = lane; i < SEG; i += 32)
-			for (uint32_t k = s_off[i] - h.base; k < s_off[i + 1] - h.base; ++k) sm.ci[b][k] = (uint8_t)i;
+			for (uint32_t k0 = s_off[i] - h.base, k = k0; k < s_off[i + 1] - h.base; ++k) { sm.ci[b][k] = (uint8_t)i; sm.ly[b][k] = (uint8_t)min(k - k0, 3u); }
 	};
 	auto fetch_pos = [&]() -> unsigned int { return lane == 0 ? atomicAdd(a.tiles_next, 1u) : 0u; };
 
@@ -973,7 +979,7 @@ __global__ void __launch_bounds__(32 * P1_MAXWARPS, 1) k_pass1_tile(Pass1TileArg
 		if (cur.kind == TK_NORMAL) {
 			mbar_wait(sm.mbar + buf, phase[buf]);            // candidates and thresholds have landed
 			phase[buf] ^= 1u;
-			tl.cand = sm.cand[buf]; tl.thr = sm.thr[buf]; tl.ci = sm.ci[buf];
+			tl.cand = sm.cand[buf]; tl.thr = sm.thr; tl.gthr = a.thr + cur.base; tl.ci = sm.ci[buf]; tl.ly = sm.ly[buf];
 			for (int k = lane; k < cur.ncand; k += 32) tl.scatter(k, cur.txe);
 		} else tile_other<MULTI>(a, cur);
 

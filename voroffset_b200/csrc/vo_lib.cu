@@ -574,12 +574,13 @@ struct TilePlan {
 		// when its last warp is done
 		cps = std::max(1, std::min(ctx->tile_ctas, 8));
 		const size_t budget = std::min<size_t>(220 * 1024, 228 * 1024 / cps - 1024 - 256);
-		auto warps = [&](int cmax, int lcap) {
+		auto warps = [&](int cmax, int lcap, int maxw) {
 			const size_t per = pass1_warp_smem(J, cmax, lcap), tab = pass1_table_smem(J) + 32;
 			if (budget < tab + per) return 1;
-			return (int)std::max<size_t>(1, std::min<size_t>(P1_MAXWARPS / cps, (budget - tab) / per));
+			return (int)std::max<size_t>(1, std::min<size_t>(maxw / cps, (budget - tab) / per));
 		};
-		nw_small = warps(cmax_small, P1_LCAP_S); nw_big = warps(cmax_big, P1_LCAP_M); nw_multi = warps(cmax_multi, P1_LCAP_M);
+		nw_small = warps(cmax_small, P1_LCAP_S, P1_MAXWARPS); nw_big = warps(cmax_big, P1_LCAP_M, P1_MAXWARPS);
+		nw_multi = warps(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M);
 		smem_small = pass1_tile_smem(J, cmax_small, P1_LCAP_S, nw_small);
 		smem_big = pass1_tile_smem(J, cmax_big, P1_LCAP_M, nw_big);
 		smem_multi = pass1_tile_smem(J, cmax_multi, P1_LCAP_M, nw_multi);
