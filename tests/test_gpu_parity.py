@@ -435,3 +435,33 @@ def test_pipelined_host_path_equals_plain_path(ctx):
     assert piped.bit_equal(plain) and t1 > 0
     again, _, _ = op.dilation(vol, 31.5)          # second call reuses the size hints
     assert again.bit_equal(plain)
+
+
+def _points_volume(nx, ny, points):
+    """Volume with one short interval in each of the given (x, y) columns."""
+    cnt = np.zeros(nx * ny, dtype=np.int64)
+    pts = sorted(set((y * nx + x) for x, y in points))
+    cnt[pts] = 1
+    off = np.concatenate(([0], np.cumsum(cnt))).astype(np.uint32)
+    spans = np.array([[100.0 + 0.37 * (c % 17), 101.5 + 0.37 * (c % 17)] for c in pts]).reshape(-1, 2)
+    return CompressedVolume(nx, ny, off, spans)
+
+
+def test_pipelined_host_path_edge_cases(ctx):
+    """The banded host-buffer path on inputs that stress its bookkeeping: an empty volume, isolated points (the result
+    has ~3000 times the intervals of the input, so it outgrows the result buffers sized from the input and the call
+    must fall back, then succeed banded with the learnt size), and the same context going back to a small result."""
+    nx, ny, R = 1536, 1056, 32.0                     # large enough for the banded path (vo_lib.cu: dilate_ours_pipelined)
+    op = morpho.make_operator("ours", ctx)
+    rng = np.random.RandomState(5)
+    pts = [(int(rng.randint(40, nx - 40)), int(rng.randint(40, ny - 40))) for _ in range(120)]
+    pts += [(0, 0), (nx - 1, ny - 1), (nx - 1, 0), (0, ny - 1), (700, 131), (700, 132), (701, 527), (701, 528)]   # corners, band seams
+    for name, vol in (("empty", _points_volume(nx, ny, [])), ("points", _points_volume(nx, ny, pts)),
+                      ("one point", _points_volume(nx, ny, [(5, 5)]))):
+        ctx.set_option("pipeline", "off")
+        plain, _, _ = op.dilation(vol, R)
+        ctx.set_option("pipeline", "on")
+        for attempt in range(3):
+            piped, _, _ = op.dilation(vol, R)
+            assert piped.bit_equal(plain), f"{name}, call {attempt}"
+    assert plain.numSegments() > 0
