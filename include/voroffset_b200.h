@@ -168,6 +168,18 @@ int  vo_slab_finish(vo_ctx *ctx, vo_slab *slab, const void *d_off_prev, const vo
                     vo_dvol **out, double *ms_pass1, double *ms_pass2);
 void vo_slab_abort(vo_ctx *ctx, vo_slab *slab);
 
+/* ---- the step before the path: mesh -> dexel volume --------------------------------------------- */
+/* Replaces the ray-marching loop of vor3d::create_dexels, compute_sign (src/vor3d/Dexelize.cpp:166-225, with
+ * point_in_triangle_2d :74-92 and intersect_ray_z :136-162): for every column (x,y) of an nx*ny grid the z values
+ * (in dexel units, z / spacing, :204) at which the vertical line through the column centre
+ * ((x+0.5)*spacing + origin_x, (y+0.5)*spacing + origin_y) crosses a facet, ascending (:210), as (z1,z2) pairs.
+ *   verts : double[3*nv] xyz; tris : int32[3*nf] vertex indices (host or device memory).
+ *   origin_x/y, spacing, nx, ny : the CompressedVolume's own (origin already lowered by padding*spacing,
+ *                CompressedVolume.cpp:17-21); a column with an odd number of crossings (open surface) loses the last.
+ * The result stays resident in HBM, ready for vo_morph3d_dev; *ms = device time.                          */
+int  vo_dexelize_dev(vo_ctx *ctx, uint64_t nv, const double *verts, uint64_t nf, const int32_t *tris,
+                     double origin_x, double origin_y, double spacing, int nx, int ny, vo_dvol **out, double *ms);
+
 /* 2D on resident data (one list per row).                                                             */
 int  vo_morph2d_dev(vo_ctx *ctx, int op, const vo_dvol *rows_as_vol /* nx = rows, ny = 1 */, int width,
                     double r, vo_dvol **out, double *ms);

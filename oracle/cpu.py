@@ -64,6 +64,8 @@ class Oracle:
                                      C.POINTER(_u64p), C.POINTER(_f64p)]
         L.oracle_cap_table_ours.argtypes = [C.c_double, C.POINTER(C.c_int), C.POINTER(_f64p)]
         L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_dexelize.argtypes = [C.c_uint64, _f64p, C.c_uint64, C.POINTER(C.c_int32), C.c_double, C.c_double,
+                                      C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_u64p), C.POINTER(_f64p)]
         self.set_threads(threads)
 
     def set_threads(self, n: int):
@@ -72,6 +74,20 @@ class Oracle:
 
     def _free(self, p):
         self.lib.oracle_free(C.cast(p, C.c_void_p))
+
+    def dexelize(self, V, F, grid: CompressedVolume, window=None) -> CompressedVolume:
+        """compute_sign (Dexelize.cpp:166-225) for the columns x0 <= x < x1, y0 <= y < y1 of `grid` (default: all)."""
+        V = np.ascontiguousarray(V, dtype=np.float64).reshape(-1, 3)
+        F = np.ascontiguousarray(F, dtype=np.int32).reshape(-1, 3)
+        x0, x1, y0, y1 = window or (0, grid.nx, 0, grid.ny)
+        poff, pev = _u64p(), _f64p()
+        rc = self.lib.oracle_dexelize(V.shape[0], V.ctypes.data_as(_f64p), F.shape[0], F.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      grid.origin[0], grid.origin[1], grid.spacing, x0, x1, y0, y1,
+                                      C.byref(poff), C.byref(pev))
+        if rc:
+            raise RuntimeError("oracle_dexelize failed")
+        off, spans = _take(self._free, (x1 - x0) * (y1 - y0), poff, pev)
+        return grid.like(x1 - x0, y1 - y0, off, spans)
 
     def morph3d(self, vol: CompressedVolume, op: str, radius: float, method: str = "ours") -> CompressedVolume:
         off, ev = _in_arrays(vol.off, vol.spans)

@@ -572,3 +572,131 @@ int oracle_morph2d(int op, int rows, int width, const uint64_t *off, const doubl
 	if (rc) return rc;
 	return pack_lists(lists, (uint64_t)rows, out_off, out_ev);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Dexeliser, the step before the path: compute_sign (src/vor3d/Dexelize.cpp:166-225).
+ * PARITY UNPINNED: the reference's Dexelize.cpp needs geogram (mesh container, AABB tree), which is
+ * absent here, so this restatement cannot be checked against a compiled reference; the reference has
+ * no test or golden vector for it either. What is restated, literally:
+ *   orientation / point_in_triangle_2d  Dexelize.cpp:58-92 (after SDFGen)
+ *   orient_2d_inexact                    Dexelize.cpp:107-121  (a11*a22 - a12*a21, geogram det2x2)
+ *   intersect_ray_z                      Dexelize.cpp:136-162  (z = u*p1z + v*p2z + w*p3z; facets
+ *                                        whose projection has zero signed area yield nothing)
+ *   compute_sign                         Dexelize.cpp:186-212: centre = (x+0.5)*spacing + origin
+ *                                        (CompressedVolumeBase.cpp:5-11); the AABB query with a box of
+ *                                        zero xy extent hands over exactly the facets whose bounding
+ *                                        box contains the centre (geogram bboxes_overlap, inclusive);
+ *                                        push z / spacing; std::sort.
+ * The reference keeps a list with an odd number of crossings as it is; the CSR containers hold
+ * intervals, so the last crossing of such a column is dropped (voroffset_b200/cpp/vo_host.cpp does
+ * the same). Columns x0 <= x < x1, y0 <= y < y1 are produced, numbered x-fastest inside that window,
+ * every facet is looked at for every column (no spatial index: that is the point of a checker).
+ * ---------------------------------------------------------------------------------------------- */
+static int dex_orientation(double x1, double y1, double x2, double y2, double *twice_signed_area)
+{
+	*twice_signed_area = y1 * x2 - x1 * y2;
+	if (*twice_signed_area > 0) return 1;
+	else if (*twice_signed_area < 0) return -1;
+	else if (y2 > y1) return 1;
+	else if (y2 < y1) return -1;
+	else if (x1 > x2) return 1;
+	else if (x1 < x2) return -1;
+	else return 0;
+}
+
+static int dex_point_in_triangle_2d(double x0, double y0, double x1, double y1, double x2, double y2,
+	double x3, double y3, double *a, double *b, double *c)
+{
+	x1 -= x0; x2 -= x0; x3 -= x0;
+	y1 -= y0; y2 -= y0; y3 -= y0;
+	int signa = dex_orientation(x2, y2, x3, y3, a);
+	if (signa == 0) return 0;
+	int signb = dex_orientation(x3, y3, x1, y1, b);
+	if (signb != signa) return 0;
+	int signc = dex_orientation(x1, y1, x2, y2, c);
+	if (signc != signa) return 0;
+	double sum = *a + *b + *c;
+	*a /= sum; *b /= sum; *c /= sum;
+	return 1;
+}
+
+static int cmp_double(const void *a, const void *b)
+{
+	const double p = *(const double *)a, q = *(const double *)b;
+	return (p > q) - (p < q);
+}
+
+typedef struct {
+	uint64_t nv, nf; const double *V; const int32_t *F; const double *fbox; /* [4*nf] bx0,bx1,by0,by1 */
+	double ox, oy, spacing; int x0, x1, y0; list_t *lists; atomic_int fail;
+} dex_ctx_t;
+
+static void dex_chunk(int64_t c0, int64_t c1, void *p)
+{
+	dex_ctx_t *k = (dex_ctx_t *)p;
+	const int w = k->x1 - k->x0;
+	double *z = NULL; size_t zn = 0, zcap = 0;
+	int fail = 0;
+	for (int64_t c = c0; c < c1 && !fail; ++c) {
+		const int x = k->x0 + (int)(c % w), y = k->y0 + (int)(c / w);
+		const double cx = (x + 0.5) * k->spacing + k->ox, cy = (y + 0.5) * k->spacing + k->oy;
+		zn = 0;
+		for (uint64_t f = 0; f < k->nf; ++f) {
+			const double *b = k->fbox + 4 * f;
+			if (cx < b[0] || cx > b[1] || cy < b[2] || cy > b[3]) continue;   /* the AABB query */
+			const double *p1 = k->V + 3 * (uint64_t)k->F[3 * f], *p2 = k->V + 3 * (uint64_t)k->F[3 * f + 1],
+			             *p3 = k->V + 3 * (uint64_t)k->F[3 * f + 2];
+			double u, v, t;
+			if (!dex_point_in_triangle_2d(cx, cy, p1[0], p1[1], p2[0], p2[1], p3[0], p3[1], &u, &v, &t)) continue;
+			const double zz = u * p1[2] + v * p2[2] + t * p3[2];
+			const double a11 = p2[0] - p1[0], a12 = p2[1] - p1[1], a21 = p3[0] - p1[0], a22 = p3[1] - p1[1];
+			const double delta = a11 * a22 - a12 * a21;
+			if (delta > 0 || delta < 0) {
+				if (zn == zcap) {
+					size_t nc = zcap ? 2 * zcap : 32;
+					double *nz = (double *)realloc(z, nc * sizeof(double));
+					if (!nz) { fail = 1; break; }
+					z = nz; zcap = nc;
+				}
+				z[zn++] = zz / k->spacing;
+			}
+		}
+		qsort(z, zn, sizeof(double), cmp_double);
+		list_t *dst = &k->lists[c];
+		dst->n = zn / 2; dst->v = NULL;
+		if (dst->n) {
+			dst->v = (iv_t *)malloc(dst->n * sizeof(iv_t));
+			if (!dst->v) { fail = 1; break; }
+			for (size_t i = 0; i < dst->n; ++i) { dst->v[i].s = z[2 * i]; dst->v[i].e = z[2 * i + 1]; }
+		}
+	}
+	free(z);
+	if (fail) atomic_store(&k->fail, 1);
+}
+
+int oracle_dexelize(uint64_t nv, const double *V, uint64_t nf, const int32_t *F, double ox, double oy,
+	double spacing, int x0, int x1, int y0, int y1, uint64_t **out_off, double **out_ev)
+{
+	if (x1 < x0 || y1 < y0 || !(spacing > 0)) return 1;
+	for (uint64_t i = 0; i < 3 * nf; ++i) if (F[i] < 0 || (uint64_t)F[i] >= nv) return 1;
+	const uint64_t N = (uint64_t)(x1 - x0) * (uint64_t)(y1 - y0);
+	list_t *lists = (list_t *)calloc(N ? N : 1, sizeof(list_t));
+	double *fbox = (double *)malloc((nf ? nf : 1) * 4 * sizeof(double));
+	if (!lists || !fbox) { free(lists); free(fbox); return 1; }
+	for (uint64_t f = 0; f < nf; ++f) {
+		double *b = fbox + 4 * f;
+		b[0] = b[2] = INFINITY; b[1] = b[3] = -INFINITY;
+		for (int k = 0; k < 3; ++k) {
+			const double *p = V + 3 * (uint64_t)F[3 * f + k];
+			if (p[0] < b[0]) b[0] = p[0];
+			if (p[0] > b[1]) b[1] = p[0];
+			if (p[1] < b[2]) b[2] = p[1];
+			if (p[1] > b[3]) b[3] = p[1];
+		}
+	}
+	dex_ctx_t k = { nv, nf, V, F, fbox, ox, oy, spacing, x0, x1, y0, lists, 0 };
+	if (N) parallel_for((int64_t)N, 64, dex_chunk, &k);
+	free(fbox);
+	if (atomic_load(&k.fail)) return 1;
+	return pack_lists(lists, N, out_off, out_ev);
+}

@@ -30,7 +30,7 @@ EXPORTS = [
     "vo_dvol_info", "vo_dvol_free", "vo_dvol_rows", "vo_dvol_concat_rows", "vo_morph3d_dev", "vo_xor3d_dev",
     "vo_pass1_dev", "vo_pass2_dev", "vo_dmid_free", "vo_dmid_info", "vo_morph2d_dev",
     "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device", "vo_set_option", "vo_dvol_rows_to",
-    "vo_slab_begin", "vo_slab_finish", "vo_slab_abort",
+    "vo_slab_begin", "vo_slab_finish", "vo_slab_abort", "vo_dexelize_dev",
 ]
 
 _lib = None
@@ -87,6 +87,8 @@ def load() -> C.CDLL:
     L.vo_dmid_free.restype = None
     L.vo_dmid_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     L.vo_morph2d_dev.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_double, C.POINTER(_vp), _f64p]
+    L.vo_dexelize_dev.argtypes = [_vp, C.c_uint64, _vp, C.c_uint64, _vp, C.c_double, C.c_double, C.c_double,
+                                  C.c_int, C.c_int, C.POINTER(_vp), _f64p]
     L.vo_set_option.argtypes = [_vp, C.c_char_p, C.c_char_p]
     L.vo_mark.argtypes = [_vp, C.c_int]
     L.vo_elapsed_ms.argtypes = [_vp, C.c_int, C.c_int, _f64p]

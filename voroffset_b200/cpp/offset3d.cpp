@@ -81,7 +81,8 @@ int main(int argc, char *argv[])
 
 		// Load input model and dexelize (offset3d.cpp:66-70)
 		if (ends(args.input, ".vol")) { std::ifstream in(args.input); input.load(in); }
-		else input = vor3d::create_dexels(args.input, args.dexels_size, args.padding, args.num_dexels);
+		else input = vor3d::create_dexels(args.input, args.dexels_size, args.padding, args.num_dexels,
+		                                  args.operation == "noop" ? -1 : 0);   // on the GPU whenever one is needed anyway
 
 		if (args.radius_in_mm) args.radius /= input.spacing();                                    // offset3d.cpp:73-75
 		std::cout << "[Stats] Grid size: " << input.gridSize()[0] << " " << input.gridSize()[1] << "\n"

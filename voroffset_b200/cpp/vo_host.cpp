@@ -275,7 +275,7 @@ namespace voroffset3d
 		}
 	}
 
-	CompressedVolume create_dexels(const std::string &filename, double &voxel_size, int padding, int num_voxels)
+	CompressedVolume create_dexels(const std::string &filename, double &voxel_size, int padding, int num_voxels, int device)
 	{
 		const Mesh M = mesh_load(filename);
 		std::array<double, 3> lo = M.V[0], hi = M.V[0];
@@ -285,9 +285,33 @@ namespace voroffset3d
 		CompressedVolume dexels(lo, extent, voxel_size, padding);
 		const int nx = dexels.gridSize()[0], ny = dexels.gridSize()[1];
 		const double spacing = dexels.spacing();
-		// Bucket the facets by the columns their xy bounding box covers (the reference's AABB tree is only a
-		// superset filter for the same per-facet test, Dexelize.cpp:182-207).
+		if (device >= 0) {
+			// the ray-marching loop (compute_sign, Dexelize.cpp:166-225) on the GPU: facets are the work items there
+			vo_ctx *ctx = nullptr;
+			if (vo_create(device, &ctx) != VO_OK) throw std::runtime_error("vo_create failed: no usable CUDA device (there is no CPU fallback)");
+			std::vector<int32_t> tris;
+			tris.reserve(3 * M.F.size());
+			for (const auto &t : M.F) for (int k = 0; k < 3; ++k) tris.push_back(t[k]);
+			vo_dvol *dv = nullptr;
+			int rc = vo_dexelize_dev(ctx, M.V.size(), M.V[0].data(), M.F.size(), tris.data(), dexels.origin()[0], dexels.origin()[1],
+			                         spacing, nx, ny, &dv, nullptr);
+			uint64_t n = 0;
+			std::vector<uint32_t> off((size_t)nx * ny + 1);
+			std::vector<double> spans;
+			if (rc == VO_OK) rc = vo_dvol_info(dv, nullptr, nullptr, &n, nullptr, nullptr);
+			if (rc == VO_OK) { spans.resize(2 * n + 2); rc = vo_dvol_download(ctx, dv, off.data(), spans.data()); }
+			const std::string err = rc == VO_OK ? "" : vo_last_error(ctx);
+			if (dv) vo_dvol_free(ctx, dv);
+			vo_destroy(ctx);
+			if (rc != VO_OK) throw std::runtime_error("Assertion failed: " + err);
+			dexels.from_csr(off.data(), spans.data());
+			return dexels;
+		}
+		// Host loop (offset3d -x noop, which needs no GPU). Bucket the facets by the columns their xy bounding box can
+		// cover; the exact test below is the reference's AABB query: a facet is handed to intersect_ray_z when its
+		// bounding box contains the column centre (Dexelize.cpp:190-207, a query box of zero extent in x and y).
 		std::vector<std::vector<int>> bucket((size_t)nx * ny);
+		std::vector<std::array<double, 4>> fbox(M.F.size());
 		for (int f = 0; f < (int)M.F.size(); ++f) {
 			const auto &t = M.F[f];
 			double bx0 = 1e300, bx1 = -1e300, by0 = 1e300, by1 = -1e300;
@@ -295,6 +319,7 @@ namespace voroffset3d
 				bx0 = std::min(bx0, M.V[t[k]][0]); bx1 = std::max(bx1, M.V[t[k]][0]);
 				by0 = std::min(by0, M.V[t[k]][1]); by1 = std::max(by1, M.V[t[k]][1]);
 			}
+			fbox[f] = {{bx0, bx1, by0, by1}};
 			const int x0 = std::max(0, (int)std::floor((bx0 - dexels.origin()[0]) / spacing - 0.5) - 1);
 			const int x1 = std::min(nx - 1, (int)std::ceil((bx1 - dexels.origin()[0]) / spacing - 0.5) + 1);
 			const int y0 = std::max(0, (int)std::floor((by0 - dexels.origin()[1]) / spacing - 0.5) - 1);
@@ -306,6 +331,8 @@ namespace voroffset3d
 				const auto c = dexels.dexelCenter(x, y);
 				std::vector<double> inter;
 				for (int f : bucket[x + (size_t)nx * y]) {
+					const auto &b = fbox[f];
+					if (c[0] < b[0] || c[0] > b[1] || c[1] < b[2] || c[1] > b[3]) continue;
 					const auto &p1 = M.V[M.F[f][0]], &p2 = M.V[M.F[f][1]], &p3 = M.V[M.F[f][2]];
 					double u, v, w;
 					if (point_in_triangle_2d(c[0], c[1], p1[0], p1[1], p2[0], p2[1], p3[0], p3[1], u, v, w)) {

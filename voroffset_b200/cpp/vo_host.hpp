@@ -120,7 +120,9 @@ namespace voroffset3d
 	class VoronoiMorphoBruteForce : public VoronoiMorpho { public: explicit VoronoiMorphoBruteForce(int device = 0) : VoronoiMorpho(VO_METHOD_BRUTE_FORCE, device) {} };
 
 	// Geogram-free restatement of src/vor3d/Dexelize.cpp (mesh -> dexels, dexels -> hex mesh / points).
-	CompressedVolume create_dexels(const std::string &filename, double &voxel_size, int padding = 0, int num_voxels = -1);
+	// device >= 0: the ray-marching loop runs on that GPU (vo_dexelize_dev); device < 0: host loop (offset3d -x noop,
+	// the one mode that needs no GPU). Both give the same bits.
+	CompressedVolume create_dexels(const std::string &filename, double &voxel_size, int padding = 0, int num_voxels = -1, int device = -1);
 	void dexel_dump(const std::string &filename, const CompressedVolume &voxels);
 }
 

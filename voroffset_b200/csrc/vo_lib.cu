@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <chrono>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -21,6 +22,7 @@
 #include "kernels.cuh"
 #include "pass1_tile.cuh"
 #include "scan.cuh"
+#include "dexelize.cuh"
 
 using namespace vo;
 
@@ -1725,6 +1727,86 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 	return VO_OK;
 }
 
+// ---- dexeliser (the step before the path): compute_sign of src/vor3d/Dexelize.cpp:166-225, facets as work items ----
+int dexelize_dev(vo_ctx *ctx, uint64_t nv, const double *verts, uint64_t nf, const int32_t *tris,
+                 double ox, double oy, double spacing, int nx, int ny, vo_dvol **out)
+{
+	VO_TRY(check_dims(ctx, nx, ny));
+	if (!(spacing > 0)) return fail(ctx, VO_ERR_ARG, "dexelize: spacing must be positive");
+	if (nv >= (1ull << 31) || nf >= (1ull << 31) / 3) return fail(ctx, VO_ERR_OVERFLOW, "dexelize: mesh too large for 32-bit indices");
+	if ((nv && !verts) || (nf && !tris)) return fail(ctx, VO_ERR_ARG, "dexelize: null mesh arrays");
+	const unsigned long long ncols = (unsigned long long)nx * ny;
+	vo_dvol *v = nullptr;
+	VO_TRY(new_dvol(ctx, nx, ny, &v));
+	std::unique_ptr<vo_dvol, std::function<void(vo_dvol *)>> guard(v, [ctx](vo_dvol *p) { free_dvol(ctx, p); });
+	if (ncols == 0 || nf == 0 || nv == 0) {
+		VO_CUDA(cudaMemsetAsync(v->off, 0, (ncols + 1) * sizeof(uint32_t), ctx->stream));
+		VO_TRY(dalloc(ctx, &v->spans, 0));
+		*out = guard.release();
+		return VO_OK;
+	}
+	Tmp<double> dV(ctx), raw(ctx);
+	Tmp<int> dF(ctx);
+	Tmp<int4> box(ctx);
+	Tmp<uint32_t> nchunk(ctx), chunk_off(ctx), cnt(ctx), raw_off(ctx), pairs(ctx);
+	Tmp<unsigned int> bad(ctx);
+	VO_TRY(dalloc(ctx, &dV.p, 3 * nv));
+	VO_TRY(dalloc(ctx, &dF.p, 3 * nf));
+	VO_TRY(dalloc(ctx, &box.p, nf));
+	VO_TRY(dalloc(ctx, &nchunk.p, nf));
+	VO_TRY(dalloc(ctx, &chunk_off.p, nf + 1));
+	VO_TRY(dalloc(ctx, &cnt.p, ncols));
+	VO_TRY(dalloc(ctx, &raw_off.p, ncols + 1));
+	VO_TRY(dalloc(ctx, &pairs.p, ncols));
+	VO_TRY(dalloc(ctx, &bad.p, 1));
+	VO_CUDA(cudaMemcpyAsync(dV.p, verts, 3 * nv * sizeof(double), cudaMemcpyDefault, ctx->stream));
+	VO_CUDA(cudaMemcpyAsync(dF.p, tris, 3 * nf * sizeof(int), cudaMemcpyDefault, ctx->stream));
+	VO_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(unsigned int), ctx->stream));
+	VO_CUDA(cudaMemsetAsync(cnt.p, 0, ncols * sizeof(uint32_t), ctx->stream));
+	DexArgs a{};
+	a.V = dV.p; a.F = dF.p; a.nv = (unsigned int)nv; a.nf = (unsigned int)nf;
+	a.ox = ox; a.oy = oy; a.spacing = spacing; a.nx = nx; a.ny = ny;
+	a.box = box.p; a.nchunk = nchunk.p; a.chunk_off = chunk_off.p; a.cnt = cnt.p; a.bad = bad.p;
+	k_dex_plan<<<blocks_for(nf, 256), 256, 0, ctx->stream>>>(a);
+	ctx->launches++;
+	unsigned long long nchunks = 0;
+	{
+		// scan_counts checks its total against the uint32 range of the CSR offsets, which also bounds the chunk ids
+		int rc = scan_counts(ctx, nchunk.p, nf, chunk_off.p, &nchunks);
+		if (rc == VO_ERR_OVERFLOW) return fail(ctx, rc, "dexelize: too many (facet, column-chunk) pairs");
+		VO_TRY(rc);
+	}
+	unsigned int h_bad = 0;
+	VO_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(h_bad), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (h_bad) return fail(ctx, VO_ERR_ARG, "dexelize: a facet names a vertex outside [0, nv)");
+	a.nchunks = nchunks;
+	const unsigned int hit_blocks = blocks_for(nchunks * 32ull, 256);
+	if (nchunks) { k_dex_hits<false><<<hit_blocks, 256, 0, ctx->stream>>>(a); ctx->launches++; }
+	unsigned long long total_raw = 0, total = 0;
+	{
+		int rc = scan_counts(ctx, cnt.p, ncols, raw_off.p, &total_raw);
+		if (rc == VO_ERR_OVERFLOW) return fail(ctx, rc, "dexelize: more than 2^32-1 crossings");
+		VO_TRY(rc);
+	}
+	k_dex_pairs<<<blocks_for(ncols, 256), 256, 0, ctx->stream>>>(cnt.p, ncols, pairs.p);
+	ctx->launches++;
+	VO_TRY(scan_counts(ctx, pairs.p, ncols, v->off, &total));
+	VO_TRY(dalloc(ctx, &raw.p, total_raw));
+	VO_TRY(dalloc(ctx, &v->spans, total));
+	v->nspans = total;
+	a.raw_off = raw_off.p; a.raw = raw.p; a.out_off = v->off; a.out = v->spans;
+	if (total_raw) {
+		VO_CUDA(cudaMemsetAsync(cnt.p, 0, ncols * sizeof(uint32_t), ctx->stream));
+		k_dex_hits<true><<<hit_blocks, 256, 0, ctx->stream>>>(a);
+		k_dex_sort<<<blocks_for(ncols, 256), 256, 0, ctx->stream>>>(a, ncols);
+		ctx->launches += 2;
+	}
+	VO_CUDA(cudaGetLastError());
+	*out = guard.release();
+	return VO_OK;
+}
+
 struct DeviceGuard {
 	int prev = -1;
 	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -2076,6 +2158,22 @@ int vo_pass2_dev(vo_ctx *ctx, const vo_dmid *mid, int y0, int y1, vo_dvol **out,
 	DeviceGuard g(ctx->device);
 	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 	VO_TRY(pass2(ctx, mid, y0, y1, out));
+	VO_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	VO_CUDA(cudaEventSynchronize(ctx->ev[1]));
+	float t = 0;
+	cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]);
+	if (ms) *ms = t;
+	return VO_OK;
+}
+
+int vo_dexelize_dev(vo_ctx *ctx, uint64_t nv, const double *verts, uint64_t nf, const int32_t *tris,
+                    double origin_x, double origin_y, double spacing, int nx, int ny, vo_dvol **out, double *ms)
+{
+	if (!ctx || !out) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	VO_TRY(dexelize_dev(ctx, nv, verts, nf, tris, origin_x, origin_y, spacing, nx, ny, out));
 	VO_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 	VO_CUDA(cudaEventSynchronize(ctx->ev[1]));
 	float t = 0;

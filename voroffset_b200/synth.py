@@ -256,3 +256,62 @@ def random_image(rows: int, width: int, kmax: int = 6, seed: int = 11) -> DexelI
         pts = np.sort(rng.uniform(0.01, width - 0.01, size=2 * k))
         lists.append(pts.tolist())
     return DexelImage.from_lists(width, lists)
+
+
+# ---- triangle meshes (input of the dexeliser, Dexelize.cpp:231-274) -----------------------------------------------
+def torus_mesh(nu: int = 256, nv: int = 128, major: float = 1.0, minor: float = 0.35, axis: str = "z"):
+    """Closed triangulated torus, `nu` x `nv` quads cut in two; vertices slightly rotated / shifted so that no edge is
+    parallel to the grid and no vertex sits on a column centre (generic position)."""
+    u = (np.arange(nu) + 0.137) * (2 * math.pi / nu)
+    v = (np.arange(nv) + 0.291) * (2 * math.pi / nv)
+    U, W = np.meshgrid(u, v, indexing="ij")
+    rho = major + minor * np.cos(W)
+    P = np.stack([rho * np.cos(U), rho * np.sin(U), minor * np.sin(W)], axis=-1).reshape(-1, 3)
+    if axis == "x":
+        P = P[:, [2, 0, 1]]
+    P = P + np.array([1.3e-4, -2.1e-4, 0.7e-4])
+    i, j = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+    a = (i * nv + j).reshape(-1)
+    b = (((i + 1) % nu) * nv + j).reshape(-1)
+    c = (((i + 1) % nu) * nv + (j + 1) % nv).reshape(-1)
+    d = (i * nv + (j + 1) % nv).reshape(-1)
+    F = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.int32)
+    return np.ascontiguousarray(P), np.ascontiguousarray(F)
+
+
+def box_mesh(lo=(-1.0, -0.8, -0.6), hi=(1.0, 0.8, 0.6), tilt: float = 0.0113):
+    """Twelve large triangles (every facet covers a big part of the grid); `tilt` shears the box so that the side walls
+    are not vertical (a vertical facet has a flat projection and never yields a crossing, Dexelize.cpp:150-157)."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    P = np.array([[x, y, z] for z in (lo[2], hi[2]) for y in (lo[1], hi[1]) for x in (lo[0], hi[0])], dtype=np.float64)
+    P[:, 0] += tilt * P[:, 2] + 0.37 * tilt * P[:, 1]
+    P[:, 1] += 0.71 * tilt * P[:, 2]
+    quads = [(0, 2, 3, 1), (4, 5, 7, 6), (0, 1, 5, 4), (2, 6, 7, 3), (0, 4, 6, 2), (1, 3, 7, 5)]
+    F = np.array([t for q in quads for t in ((q[0], q[1], q[2]), (q[0], q[2], q[3]))], dtype=np.int32)
+    return P, F
+
+
+def boxes_mesh(count: int = 200, seed: int = 5, span: float = 1.0):
+    """`count` small sheared boxes at random places (overlapping: several crossings per column, like the lattice)."""
+    rng = np.random.default_rng(seed)
+    Vs, Fs = [], []
+    for k in range(count):
+        c = rng.uniform(-span, span, 3)
+        h = rng.uniform(0.03, 0.12, 3) * span
+        P, F = box_mesh(c - h, c + h, tilt=0.0113 + 0.001 * (k % 7))
+        Fs.append(F + 8 * k)
+        Vs.append(P)
+    return np.concatenate(Vs), np.concatenate(Fs).astype(np.int32)
+
+
+def open_patch_mesh(n: int = 24):
+    """An open height-field patch above a closed box: columns under the patch only see an odd number of crossings."""
+    P, F = box_mesh((-1.0, -1.0, -0.5), (1.0, 1.0, 0.1))
+    g = np.linspace(-0.613, 0.577, n)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    Z = 0.6 + 0.1 * np.sin(3 * X) * np.cos(2 * Y)
+    Q = np.stack([X, Y, Z], -1).reshape(-1, 3)
+    i, j = np.meshgrid(np.arange(n - 1), np.arange(n - 1), indexing="ij")
+    a = (i * n + j).reshape(-1) + 8
+    G = np.concatenate([np.stack([a, a + n, a + n + 1], 1), np.stack([a, a + n + 1, a + 1], 1)]).astype(np.int32)
+    return np.concatenate([P, Q]), np.concatenate([F, G]).astype(np.int32)
