@@ -38,7 +38,9 @@ for opn in ("dilation", "erosion", "opening", "closing"):
 timed3d("C4 torus_z -n 1024 -p 18 -r 16", v4, 16.0, "dilation", "brute_force", reps=2)
 v5 = synth.torus_z(2048)
 timed3d("C5 torus_z -n 2048 -r 32", v5, 32.0, "dilation", "ours")
-timed3d("C5 torus_z -n 2048 -p 34 -r 32", synth.torus_z(2048, padding=34), 32.0, "erosion", "ours", reps=3)
+v5p = synth.torus_z(2048, padding=34)
+for opn in ("erosion", "opening", "closing"):
+    timed3d("C5 torus_z -n 2048 -p 34 -r 32", v5p, 32.0, opn, "ours", reps=3)
 timed3d("C5 torus_z -n 2048 -r 32", v5, 32.0, "dilation", "brute_force", reps=1)
 
 # C2: 2D, 2048 rows

@@ -4,9 +4,10 @@
 // point_in_triangle_2d (Dexelize.cpp:56-92, after SDFGen), orient_2d_inexact (Dexelize.cpp:94-113) and
 // intersect_ray_z (Dexelize.cpp:136-162). The reference walks the columns one after the other and asks an
 // AABB tree for the facets whose bounding box contains the column centre; per (column, facet) pair the test is
-// independent, so here the loop is turned inside out: the FACETS are the work items. A facet's column box is cut
-// into chunks of 32 x DEX_ROWS columns, a warp takes a chunk (lane = column along x: neighbouring lanes write
-// neighbouring counters), hits are counted per column, prefix-summed, written on a second identical sweep, and
+// independent, so here the loop is turned inside out: the FACETS are the work items. The columns of a facet's box
+// are numbered row by row and cut into chunks of DEX_CELLS; a warp takes a chunk, 32 consecutive cells at a time
+// (a facet of a fine mesh covers a handful of columns: one warp, one step; a facet as large as the grid becomes
+// thousands of chunks), hits are counted per column, prefix-summed, written on a second identical sweep, and
 // every column then sorts its handful of z values (std::sort in the reference, Dexelize.cpp:210). fp64
 // throughout, compiled with --fmad=false: every hit carries the reference's operation order.
 #pragma once
@@ -14,7 +15,7 @@
 
 namespace vo {
 
-constexpr int DEX_ROWS = 8;      // rows per chunk (a chunk is 32 x DEX_ROWS columns)
+constexpr int DEX_CELLS = 256;   // columns of a facet's box per chunk (one warp: DEX_CELLS / 32 steps)
 constexpr int DEX_SORT_REG = 8;  // z values a column sorts in registers; longer lists are sorted in place
 
 struct DexArgs {
@@ -82,14 +83,16 @@ __global__ void k_dex_plan(DexArgs a)
 		const double det = (p2x - p1x) * (p3y - p1y) - (p2y - p1y) * (p3x - p1x);   // orient_2d_inexact, Dexelize.cpp:103-112
 		const double bx0 = fmin(p1x, fmin(p2x, p3x)), bx1 = fmax(p1x, fmax(p2x, p3x));
 		const double by0 = fmin(p1y, fmin(p2y, p3y)), by1 = fmax(p1y, fmax(p2y, p3y));
-		// one column of slack on either side: the exact containment test is made per column against the centre itself
-		const double fx0 = floor((bx0 - a.ox) / a.spacing - 0.5) - 1.0, fx1 = ceil((bx1 - a.ox) / a.spacing - 0.5) + 1.0;
-		const double fy0 = floor((by0 - a.oy) / a.spacing - 0.5) - 1.0, fy1 = ceil((by1 - a.oy) / a.spacing - 0.5) + 1.0;
+		// centres inside the box: ceil(t0) <= x <= floor(t1) with t = (b - origin) / spacing - 0.5; rounding the other way
+		// leaves up to one column of slack on either side, far more than the rounding error of t, and the exact
+		// containment test is made per column against the centre itself (k_dex_hits)
+		const double fx0 = floor((bx0 - a.ox) / a.spacing - 0.5), fx1 = ceil((bx1 - a.ox) / a.spacing - 0.5);
+		const double fy0 = floor((by0 - a.oy) / a.spacing - 0.5), fy1 = ceil((by1 - a.oy) / a.spacing - 0.5);
 		if (det != 0 && fx1 >= 0 && fy1 >= 0 && fx0 <= a.nx - 1 && fy0 <= a.ny - 1) {   // (NaN coordinates fail these)
 			box.x = (int)fmax(fx0, 0.0); box.y = (int)fmin(fx1, (double)(a.nx - 1));
 			box.z = (int)fmax(fy0, 0.0); box.w = (int)fmin(fy1, (double)(a.ny - 1));
 			if (box.y >= box.x && box.w >= box.z)
-				n = (uint32_t)((box.y - box.x) / 32 + 1) * (uint32_t)((box.w - box.z) / DEX_ROWS + 1);
+				n = (uint32_t)(((unsigned long long)(box.y - box.x + 1) * (unsigned long long)(box.w - box.z + 1) + DEX_CELLS - 1) / DEX_CELLS);
 			else
 				box = make_int4(0, -1, 0, -1);
 		}
@@ -106,33 +109,39 @@ __global__ void __launch_bounds__(256) k_dex_hits(DexArgs a)
 	const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (w >= a.nchunks) return;
 	const int lane = threadIdx.x & 31;
-	// facet of chunk w: last f with chunk_off[f] <= w
-	unsigned int lo = 0, hi = a.nf;
+	// facet of chunk w: the last f with chunk_off[f] <= w. 32-ary search, one probe per lane: four dependent rounds
+	// for half a million facets instead of twenty.
+	unsigned int lo = 0, hi = a.nf;       // chunk_off[lo] <= w < chunk_off[hi]
 	while (hi - lo > 1) {
-		const unsigned int mid = (lo + hi) >> 1;
-		if (a.chunk_off[mid] <= w) lo = mid; else hi = mid;
+		const unsigned int step = (hi - lo + 31) / 32;
+		const unsigned int probe = lo + (lane + 1) * step;
+		const bool le = probe < hi && a.chunk_off[probe] <= w;
+		const unsigned int k = __popc(__ballot_sync(0xffffffffu, le));   // chunk_off ascends: the votes are a prefix
+		hi = min(hi, lo + (k + 1) * step);
+		lo += k * step;
 	}
 	const unsigned int f = lo;
 	const int4 box = a.box[f];
-	const unsigned int local = (unsigned int)(w - a.chunk_off[f]);
-	const unsigned int chunks_x = (unsigned int)(box.y - box.x) / 32 + 1;
-	const int x = box.x + (int)(local % chunks_x) * 32 + lane;
-	const int ya = box.z + (int)(local / chunks_x) * DEX_ROWS;
-	const int yb = min(ya + DEX_ROWS - 1, box.w);
+	const unsigned int wd = (unsigned int)(box.y - box.x + 1);
+	const unsigned int ncell = wd * (unsigned int)(box.w - box.z + 1);          // <= nx * ny < 2^32 - 2 DEX_CELLS (dexelize_dev)
+	const unsigned int base = (unsigned int)(w - a.chunk_off[f]) * DEX_CELLS;
 	const int i1 = a.F[3 * f], i2 = a.F[3 * f + 1], i3 = a.F[3 * f + 2];
 	const double p1x = a.V[3 * i1], p1y = a.V[3 * i1 + 1], p1z = a.V[3 * i1 + 2];
 	const double p2x = a.V[3 * i2], p2y = a.V[3 * i2 + 1], p2z = a.V[3 * i2 + 2];
 	const double p3x = a.V[3 * i3], p3y = a.V[3 * i3 + 1], p3z = a.V[3 * i3 + 2];
-	if (x > box.y) return;
-	const double cx = (x + 0.5) * a.spacing + a.ox;
 	// the AABB query of the reference hands compute_sign exactly the facets whose box contains the centre
-	// (Dexelize.cpp:190-207: a box of zero extent in x and y)
+	// (Dexelize.cpp:190-207: a query box of zero extent in x and y)
 	const double bx0 = fmin(p1x, fmin(p2x, p3x)), bx1 = fmax(p1x, fmax(p2x, p3x));
-	if (!(cx >= bx0 && cx <= bx1)) return;
 	const double by0 = fmin(p1y, fmin(p2y, p3y)), by1 = fmax(p1y, fmax(p2y, p3y));
-	for (int y = ya; y <= yb; ++y) {
+	for (int it = 0; it < DEX_CELLS / 32; ++it) {
+		if (base + (unsigned int)(it * 32) >= ncell) break;       // (base < ncell < 2^32 - 2 DEX_CELLS: no wrap-around, dexelize_dev checks)
+		const unsigned int id = base + (unsigned int)(it * 32 + lane);
+		if (id >= ncell) continue;
+		const unsigned int row = id / wd;
+		const int x = box.x + (int)(id - row * wd), y = box.z + (int)row;
+		const double cx = (x + 0.5) * a.spacing + a.ox;
 		const double cy = (y + 0.5) * a.spacing + a.oy;
-		if (!(cy >= by0 && cy <= by1)) continue;
+		if (!(cx >= bx0 && cx <= bx1 && cy >= by0 && cy <= by1)) continue;
 		double u, v, t;
 		if (!dex_point_in_triangle(cx, cy, p1x, p1y, p2x, p2y, p3x, p3y, u, v, t)) continue;
 		const unsigned long long c = (unsigned long long)x + (unsigned long long)a.nx * y;

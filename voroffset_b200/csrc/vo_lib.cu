@@ -63,6 +63,14 @@ struct vo_ctx {
 	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
+	// Large scratch blocks (>= 1 MiB) released by dfree are kept WHOLE and handed to the next request they fit
+	// (dalloc). The driver's stream-ordered pool splits a released block for smaller requests; an erosion / closing
+	// alternates between requests of very different sizes (a 2.4 GB mid volume, pools sized by decaying hints) and
+	// every few calls the pool had to map fresh memory: 5 ms operations took 15-35 ms now and then.
+	std::unordered_map<void *, size_t> big_live;            // blocks handed out -> capacity
+	std::vector<std::pair<void *, size_t>> big_free;        // released blocks, oldest first
+	size_t big_free_bytes = 0, big_free_limit = (size_t)48 << 30;   // vo_create sets the limit to a third of the device memory
+	bool block_cache = true;          // vo_set_option("block_cache", "off")
 };
 
 struct vo_dvol {
@@ -120,25 +128,67 @@ inline unsigned int blocks_for(unsigned long long n, int threads)
 	return (unsigned int)(b ? b : 1);
 }
 
+void release_big_free(vo_ctx *ctx, size_t keep_bytes)
+{
+	size_t i = 0;
+	while (ctx->big_free_bytes > keep_bytes && i < ctx->big_free.size()) {
+		cudaFreeAsync(ctx->big_free[i].first, ctx->stream);
+		ctx->big_free_bytes -= ctx->big_free[i].second;
+		++i;
+	}
+	ctx->big_free.erase(ctx->big_free.begin(), ctx->big_free.begin() + i);
+}
+
 template <typename T> int dalloc(vo_ctx *ctx, T **p, unsigned long long count)
 {
 	*p = nullptr;
 	size_t bytes = (size_t)std::max<unsigned long long>(count, 1ull) * sizeof(T);
-	// Large requests are rounded up to eight size classes per octave: the stream-ordered pool then hands the block
-	// of the previous call back even when the grid differs by a border column (erosion) or the result by a few
-	// intervals, instead of mapping fresh memory (milliseconds) every other call.
+	const bool big = bytes >= (1u << 20) && ctx->block_cache;
+	// Large requests are rounded up to eight size classes per octave: a block released by the previous call then fits
+	// even when the grid differs by a border column (erosion) or the result by a few intervals.
 	if (bytes >= (1u << 20)) {
 		size_t q = (size_t)1 << 17;
 		while ((q << 4) <= bytes) q <<= 1;
 		bytes = (bytes + q - 1) / q * q;
 	}
-	VO_CUDA(cudaMallocAsync((void **)p, bytes, ctx->stream));
+	if (big) {
+		// smallest released block that holds the request without wasting more than half of itself. Reuse is in stream
+		// order like cudaMallocAsync after cudaFreeAsync: every block is allocated, first used and released on
+		// ctx->stream (other streams join it through events before a release).
+		int best = -1;
+		for (int i = 0; i < (int)ctx->big_free.size(); ++i) {
+			const size_t cap = ctx->big_free[i].second;
+			if (cap >= bytes && cap / 2 <= bytes && (best < 0 || cap < ctx->big_free[best].second)) best = i;
+		}
+		if (best >= 0) {
+			*p = (T *)ctx->big_free[best].first;
+			ctx->big_live[*p] = ctx->big_free[best].second;
+			ctx->big_free_bytes -= ctx->big_free[best].second;
+			ctx->big_free.erase(ctx->big_free.begin() + best);
+			return VO_OK;
+		}
+	}
+	cudaError_t e = cudaMallocAsync((void **)p, bytes, ctx->stream);
+	if (e == cudaErrorMemoryAllocation && !ctx->big_free.empty()) {
+		cudaGetLastError();
+		release_big_free(ctx, 0);
+		cudaStreamSynchronize(ctx->stream);
+		e = cudaMallocAsync((void **)p, bytes, ctx->stream);
+	}
+	VO_CUDA(e);
+	if (big) ctx->big_live[*p] = bytes;
 	return VO_OK;
 }
 
 template <typename T> void dfree(vo_ctx *ctx, T *p)
 {
-	if (p) cudaFreeAsync((void *)p, ctx->stream);
+	if (!p) return;
+	auto it = ctx->big_live.find((void *)p);
+	if (it == ctx->big_live.end()) { cudaFreeAsync((void *)p, ctx->stream); return; }
+	ctx->big_free.emplace_back(it->first, it->second);
+	ctx->big_free_bytes += it->second;
+	ctx->big_live.erase(it);
+	if (ctx->big_free_bytes > ctx->big_free_limit) release_big_free(ctx, ctx->big_free_limit);
 }
 
 // RAII for temporaries allocated on the context stream
@@ -1733,6 +1783,7 @@ int dexelize_dev(vo_ctx *ctx, uint64_t nv, const double *verts, uint64_t nf, con
 {
 	VO_TRY(check_dims(ctx, nx, ny));
 	if (!(spacing > 0)) return fail(ctx, VO_ERR_ARG, "dexelize: spacing must be positive");
+	if ((unsigned long long)nx * (unsigned long long)ny >= (1ull << 32) - 2 * DEX_CELLS) return fail(ctx, VO_ERR_OVERFLOW, "dexelize: grid too large for 32-bit cell numbers");
 	if (nv >= (1ull << 31) || nf >= (1ull << 31) / 3) return fail(ctx, VO_ERR_OVERFLOW, "dexelize: mesh too large for 32-bit indices");
 	if ((nv && !verts) || (nf && !tris)) return fail(ctx, VO_ERR_ARG, "dexelize: null mesh arrays");
 	const unsigned long long ncols = (unsigned long long)nx * ny;
@@ -1847,6 +1898,11 @@ int vo_create(int device, vo_ctx **out)
 			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
 		}
 	}
+	if (ok) {
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->big_free_limit = total_b / 3;
+		else cudaGetLastError();
+	}
 	if (!ok) { cudaGetLastError(); vo_destroy(ctx); return VO_ERR_CUDA; }
 	*out = ctx;
 	return VO_OK;
@@ -1858,6 +1914,7 @@ void vo_destroy(vo_ctx *ctx)
 	DeviceGuard g(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	free_table_cache(ctx);
+	if (ctx->stream) { release_big_free(ctx, 0); cudaStreamSynchronize(ctx->stream); }
 	if (ctx->d_ctr) cudaFree(ctx->d_ctr);
 	if (ctx->ovf) cudaFree(ctx->ovf);
 	for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -1883,6 +1940,22 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "pipeline") == 0) {
 		if (std::strcmp(value, "off") == 0) { ctx->no_pipeline = true; return VO_OK; }
 		if (std::strcmp(value, "on") == 0 || std::strcmp(value, "auto") == 0) { ctx->no_pipeline = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "block_cache") == 0) {
+		if (std::strcmp(value, "on") == 0) {
+			DeviceGuard g(ctx->device);
+			size_t free_b = 0, total_b = 0;
+			ctx->block_cache = true;
+			ctx->big_free_limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b ? total_b / 3 : (size_t)48 << 30;
+			return VO_OK;
+		}
+		if (std::strcmp(value, "off") == 0) {
+			DeviceGuard g(ctx->device);
+			ctx->block_cache = false;
+			ctx->big_free_limit = 0;       // blocks still out are released to the driver's pool when they come back
+			release_big_free(ctx, 0);
+			return VO_OK;
+		}
 	}
 	if (std::strcmp(key, "slab") == 0) {
 		if (std::strcmp(value, "overlap") == 0) { ctx->slab_overlap = true; return VO_OK; }
