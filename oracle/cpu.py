@@ -44,6 +44,14 @@ def _take(lib_free, n_lists, poff, pev):
     return off, spans
 
 
+def _curves(curves):
+    coff = np.zeros(len(curves) + 1, dtype=np.uint64)
+    coff[1:] = np.cumsum([len(c) for c in curves])
+    pts = np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float64).reshape(-1, 2) for c in curves])
+                               if len(curves) else np.zeros((1, 2))).reshape(-1)
+    return coff, pts
+
+
 class Oracle:
     """Plain-C restatement (oracle.c)."""
 
@@ -64,6 +72,7 @@ class Oracle:
                                      C.POINTER(_u64p), C.POINTER(_f64p)]
         L.oracle_cap_table_ours.argtypes = [C.c_double, C.POINTER(C.c_int), C.POINTER(_f64p)]
         L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_from_image2d.argtypes = [C.c_int, C.c_int, _u64p, _f64p, C.POINTER(_u64p), C.POINTER(_f64p)]
         L.oracle_dexelize.argtypes = [C.c_uint64, _f64p, C.c_uint64, C.POINTER(C.c_int32), C.c_double, C.c_double,
                                       C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_u64p), C.POINTER(_f64p)]
         self.set_threads(threads)
@@ -74,6 +83,17 @@ class Oracle:
 
     def _free(self, p):
         self.lib.oracle_free(C.cast(p, C.c_void_p))
+
+    def from_image(self, width: int, rows: int, curves) -> DexelImage:
+        """DoubleCompressedImage(width, rows).fromImage(curves) (DoubleCompressedImage.cpp:25-111); a curve is an
+        (n, 2) array of (x, y) = (real, imag) points."""
+        coff, pts = _curves(curves)
+        poff, pev = _u64p(), _f64p()
+        if self.lib.oracle_from_image2d(rows, len(curves), coff.ctypes.data_as(_u64p), pts.ctypes.data_as(_f64p),
+                                        C.byref(poff), C.byref(pev)):
+            raise RuntimeError("oracle_from_image2d failed")
+        o, s = _take(self._free, rows, poff, pev)
+        return DexelImage(rows, width, o, s)
 
     def dexelize(self, V, F, grid: CompressedVolume, window=None) -> CompressedVolume:
         """compute_sign (Dexelize.cpp:166-225) for the columns x0 <= x < x1, y0 <= y < y1 of `grid` (default: all)."""
@@ -172,6 +192,8 @@ class Reference:
                                   C.POINTER(_u64p), C.POINTER(_f64p), _f64p, _f64p, C.c_char_p, C.c_int]
         L.ref3d_xor.argtypes = [C.c_int, C.c_int, _f64p, _f64p, C.c_double, C.c_int, _u64p, _f64p, _u64p, _f64p,
                                 _f64p, C.POINTER(_u64p), C.POINTER(_f64p), C.c_char_p, C.c_int]
+        L.ref2d_from_image.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _f64p, C.POINTER(_u64p), C.POINTER(_f64p),
+                                       C.c_char_p, C.c_int]
         L.ref2d_morph.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _f64p, C.c_double,
                                   C.POINTER(_u64p), C.POINTER(_f64p), C.c_char_p, C.c_int]
 
@@ -230,6 +252,18 @@ class Reference:
             raise RuntimeError(err.value.decode(errors="replace"))
         o, s = _take(self._free, a.nx * a.ny, poff, pev)
         return vol.value, a.like(a.nx, a.ny, o, s)
+
+    def from_image(self, width: int, rows: int, curves) -> DexelImage:
+        """The reference's own DoubleCompressedImage::fromImage (DoubleCompressedImage.cpp:25-40)."""
+        coff, pts = _curves(curves)
+        poff, pev = _u64p(), _f64p()
+        err = C.create_string_buffer(1024)
+        rc = self.lib.ref2d_from_image(width, rows, len(curves), coff.ctypes.data_as(_u64p), pts.ctypes.data_as(_f64p),
+                                       C.byref(poff), C.byref(pev), err, 1024)
+        if rc:
+            raise RuntimeError(err.value.decode(errors="replace"))
+        o, s = _take(self._free, rows, poff, pev)
+        return DexelImage(rows, width, o, s)
 
     def morph2d(self, img: DexelImage, op: str, r: float) -> DexelImage:
         off, ev = _in_arrays(img.off, img.spans)

@@ -700,3 +700,90 @@ int oracle_dexelize(uint64_t nv, const double *V, uint64_t nf, const int32_t *F,
 	if (atomic_load(&k.fail)) return 1;
 	return pack_lists(lists, N, out_off, out_ev);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * 2D ingestion: DoubleCompressedImage::fromImage / scanLine / unionIntersections
+ * (src/vor2d/DoubleCompressedImage.cpp:25-111), restated literally. Curve k = points
+ * pts[2*coff[k]] .. pts[2*coff[k+1]) as (x, y) = (real, imag). Ray j (0 <= j < h) is the scan line
+ * x = j (an INTEGER abscissa, not a pixel centre); it collects the y values where the closed polygon
+ * crosses it, sorted per curve; curves are assumed not to overlap: the crossings of a curve are appended
+ * when they start at or after the ray's last value and are put in FRONT of the ray otherwise (:88-111).
+ * PINNED against the compiled reference (oracle/_ref: ref2d_from_image) by tests/test_from_image.py.
+ * ---------------------------------------------------------------------------------------------- */
+int oracle_from_image2d(int h, int ncurves, const uint64_t *coff, const double *pts,
+	uint64_t **out_off, double **out_ev)
+{
+	if (h < 0 || ncurves < 0) return 1;
+	list_t *lists = (list_t *)calloc(h ? (size_t)h : 1, sizeof(list_t));
+	if (!lists) return 1;
+	double *ray = NULL, *cross = NULL; size_t rcap = 0, ccap = 0;
+	int fail = 0;
+	for (int line = 0; line < h && !fail; ++line) {
+		size_t rn = 0;
+		const double lx = (double)line;
+		for (int k = 0; k < ncurves && !fail; ++k) {
+			const double *c = pts + 2 * coff[k];
+			const int64_t n = (int64_t)(coff[k + 1] - coff[k]);
+			size_t cn = 0;
+			#define RE(i) c[2 * ((i) % n)]
+			#define IM(i) c[2 * ((i) % n) + 1]
+			for (int64_t i = 0; i < n && !fail; ++i) {
+				double y; int have = 0;
+				if (RE(i) < lx) {
+					if (RE(i + 1) > lx) {
+						const double s = (RE(i + 1) - lx) / (RE(i + 1) - RE(i));
+						y = s * IM(i) + (1 - s) * IM(i + 1); have = 1;
+					} else {
+						int64_t j = 1;
+						while (RE(i + j) == lx) j++;
+						if (RE(i + j) > lx) { y = IM(i + j - 1); have = 1; }
+					}
+				} else if (RE(i) > lx) {
+					if (RE(i + 1) < lx) {
+						const double s = (RE(i + 1) - lx) / (RE(i + 1) - RE(i));
+						y = s * IM(i) + (1 - s) * IM(i + 1); have = 1;
+					} else {
+						int64_t j = 1;
+						while (RE(i + j) == lx) j++;
+						if (RE(i + j) < lx) { y = IM(i + j - 1); have = 1; }
+					}
+				}
+				if (have) {
+					if (cn == ccap) {
+						size_t nc = ccap ? 2 * ccap : 32;
+						double *nz = (double *)realloc(cross, nc * sizeof(double));
+						if (!nz) { fail = 1; break; }
+						cross = nz; ccap = nc;
+					}
+					cross[cn++] = y;
+				}
+			}
+			#undef RE
+			#undef IM
+			if (fail || cn == 0) continue;
+			qsort(cross, cn, sizeof(double), cmp_double);
+			if (rn + cn > rcap) {
+				size_t nc = 2 * (rn + cn);
+				double *nz = (double *)realloc(ray, nc * sizeof(double));
+				if (!nz) { fail = 1; break; }
+				ray = nz; rcap = nc;
+			}
+			if (rn == 0 || ray[rn - 1] <= cross[0]) {
+				memcpy(ray + rn, cross, cn * sizeof(double));
+			} else {
+				memmove(ray + cn, ray, rn * sizeof(double));
+				memcpy(ray, cross, cn * sizeof(double));
+			}
+			rn += cn;
+		}
+		lists[line].n = rn / 2; lists[line].v = NULL;
+		if (lists[line].n) {
+			lists[line].v = (iv_t *)malloc(lists[line].n * sizeof(iv_t));
+			if (!lists[line].v) { fail = 1; break; }
+			for (size_t i = 0; i < lists[line].n; ++i) { lists[line].v[i].s = ray[2 * i]; lists[line].v[i].e = ray[2 * i + 1]; }
+		}
+	}
+	free(ray); free(cross);
+	if (fail) return 1;
+	return pack_lists(lists, (uint64_t)h, out_off, out_ev);
+}

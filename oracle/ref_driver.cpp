@@ -190,4 +190,33 @@ int ref2d_morph(int op, int rows, int width, const uint64_t *off, const double *
 	}
 }
 
+// DoubleCompressedImage::fromImage (src/vor2d/DoubleCompressedImage.cpp:25-111) on `ncurves` closed polygons:
+// curve k = points pts[2*coff[k]] .. pts[2*coff[k+1]) as (x, y) pairs = (real, imag) of the reference's PointF.
+// The image is constructed as src/vor2d/Dexelize.cpp:42 does: DoubleCompressedImage(w, h) with h rays.
+int ref2d_from_image(int w, int h, int ncurves, const uint64_t *coff, const double *pts,
+	uint64_t **out_off, double **out_ev, char *err, int errlen)
+{
+	try {
+		std::vector<voroffset::Curve> curves((size_t)ncurves);
+		for (int k = 0; k < ncurves; ++k)
+			for (uint64_t i = coff[k]; i < coff[k + 1]; ++i) curves[k].push_back(voroffset::PointF(pts[2 * i], pts[2 * i + 1]));
+		voroffset::DoubleCompressedImage img(w, h);
+		img.fromImage(curves);
+		const int rows = img.height();
+		uint64_t *o = (uint64_t *)std::malloc(((size_t)rows + 1) * sizeof(uint64_t));
+		if (!o) { set_err(err, errlen, "out of memory"); return 3; }
+		o[0] = 0;
+		for (int i = 0; i < rows; ++i) o[i + 1] = o[i] + img.m_Rays[i].size() / 2;
+		double *e = (double *)std::malloc((2 * o[rows] + 2) * sizeof(double));
+		if (!e) { std::free(o); set_err(err, errlen, "out of memory"); return 3; }
+		for (int i = 0; i < rows; ++i)
+			std::memcpy(e + 2 * o[i], img.m_Rays[i].data(), (img.m_Rays[i].size() / 2) * 2 * sizeof(double));
+		*out_off = o; *out_ev = e;
+		return 0;
+	} catch (const std::exception &e) {
+		set_err(err, errlen, e.what());
+		return 1;
+	}
+}
+
 } // extern "C"

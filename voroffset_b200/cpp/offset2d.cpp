@@ -1,5 +1,6 @@
 // offset2d re-hosted on voroffset_b200: the flags of app/cli2d/offset2d.cpp:30-39 (-i -o -r -e -f -t -n).
-// nanosvg is not available, so the input is either the reference's own dexel text format
+// Input: an SVG file like the reference (".svg": vo_svg.cpp reads it with nanosvg's conventions and rasterises with
+// the restated DoubleCompressedImage::fromImage), the reference's own dexel text format
 // (DoubleCompressedImage::save/load, ".dex") or a plain polygon file (".poly": first line "width height",
 // then one closed polygon per line as "x0 y0 x1 y1 ..." in pixels), scan-converted at row centres.
 // The morphology runs on the GPU through the C ABI.
@@ -91,7 +92,8 @@ int main(int argc, char *argv[])
 	if (args.input.empty() || !std::ifstream(args.input)) { std::cerr << "input: File does not exist\n"; return 1; }
 	try {
 		vor::DoubleCompressedImage dexels;
-		if (ends(args.input, ".poly")) dexels = load_poly(args.input);
+		if (ends(args.input, ".svg")) dexels = vor::create_dexels(args.input);           // offset2d.cpp:47
+		else if (ends(args.input, ".poly")) dexels = load_poly(args.input);
 		else { std::ifstream in(args.input); dexels.load(in); }
 		if (args.transpose) transpose(dexels);                      // offset2d.cpp:50-52
 		if (args.negate) dexels.negate();                           // offset2d.cpp:53-55

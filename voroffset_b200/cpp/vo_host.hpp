@@ -9,6 +9,7 @@
 // Same member names and argument meaning as the reference; Eigen vectors become std::array.
 #pragma once
 #include <array>
+#include <complex>
 #include <cmath>
 #include <cstdint>
 #include <functional>
@@ -129,6 +130,8 @@ namespace voroffset3d
 namespace voroffset
 {
 	typedef double Scalar;
+	typedef std::complex<double> PointF;    // src/vor2d/Common.h:15-16
+	typedef std::vector<PointF> Curve;
 
 	class DoubleCompressedImage
 	{
@@ -142,6 +145,7 @@ namespace voroffset
 		int width() const { return m_XSize; }
 		int height() const { return (int)m_Rays.size(); }
 		void resize(int w, int h) { m_XSize = w; m_Rays.assign(h, {}); }
+		void fromImage(const std::vector<Curve> &input_curves);   // DoubleCompressedImage.cpp:25-40 (vo_svg.cpp)
 		bool isValid() const;                  // DoubleCompressedImage.cpp:197-223
 		void save(std::ostream &out) const;    // DoubleCompressedImage.cpp:145-160
 		void load(std::istream &in);           // DoubleCompressedImage.cpp:162-183
@@ -154,5 +158,11 @@ namespace voroffset
 
 	private:
 		void apply(int op, double r);
+		void scanLine(std::vector<Scalar> &intersections, int line_x, const Curve &curve);          // DoubleCompressedImage.cpp:43-86
+		void unionIntersections(std::vector<Scalar> &intersections_1, const std::vector<Scalar> &intersections_2);   // :88-111
 	};
+
+	// src/vor2d/Dexelize.cpp:22-47 without nanosvg (vo_svg.cpp): SVG -> contours (mm at 90 DPI) -> fromImage
+	std::vector<Curve> svg_contours(const std::string &file, double &width_mm, double &height_mm);
+	DoubleCompressedImage create_dexels(const std::string &file);
 }
