@@ -194,6 +194,7 @@ class Reference:
                                 _f64p, C.POINTER(_u64p), C.POINTER(_f64p), C.c_char_p, C.c_int]
         L.ref2d_from_image.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _f64p, C.POINTER(_u64p), C.POINTER(_f64p),
                                        C.c_char_p, C.c_int]
+        L.ref2d_transpose.argtypes = [C.c_int, C.c_int, _u64p, _f64p, C.POINTER(_u64p), C.POINTER(_f64p), C.c_char_p, C.c_int]
         L.ref2d_morph.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _f64p, C.c_double,
                                   C.POINTER(_u64p), C.POINTER(_f64p), C.c_char_p, C.c_int]
 
@@ -264,6 +265,18 @@ class Reference:
             raise RuntimeError(err.value.decode(errors="replace"))
         o, s = _take(self._free, rows, poff, pev)
         return DexelImage(rows, width, o, s)
+
+    def transposed(self, img: DexelImage) -> DexelImage:
+        """The reference's own DoubleCompressedImage::transposeInPlace (DoubleCompressedImage.cpp:478-584)."""
+        off, ev = _in_arrays(img.off, img.spans)
+        poff, pev = _u64p(), _f64p()
+        err = C.create_string_buffer(1024)
+        rc = self.lib.ref2d_transpose(img.rows, img.width, off.ctypes.data_as(_u64p), ev.ctypes.data_as(_f64p),
+                                      C.byref(poff), C.byref(pev), err, 1024)
+        if rc:
+            raise RuntimeError(err.value.decode(errors="replace"))
+        o, s = _take(self._free, img.width, poff, pev)
+        return DexelImage(img.width, img.rows, o, s)
 
     def morph2d(self, img: DexelImage, op: str, r: float) -> DexelImage:
         off, ev = _in_arrays(img.off, img.spans)

@@ -219,4 +219,30 @@ int ref2d_from_image(int w, int h, int ncurves, const uint64_t *coff, const doub
 	}
 }
 
+// DoubleCompressedImage::transposeInPlace (src/vor2d/DoubleCompressedImage.cpp:478-584); the result has `width`
+// rays of length `rows`.
+int ref2d_transpose(int rows, int width, const uint64_t *off, const double *ev,
+	uint64_t **out_off, double **out_ev, char *err, int errlen)
+{
+	try {
+		voroffset::DoubleCompressedImage img(width, rows);
+		for (int i = 0; i < rows; ++i) img.m_Rays[i].assign(ev + 2 * off[i], ev + 2 * off[i + 1]);
+		img.transposeInPlace();
+		const int n = img.height();
+		uint64_t *o = (uint64_t *)std::malloc(((size_t)n + 1) * sizeof(uint64_t));
+		if (!o) { set_err(err, errlen, "out of memory"); return 3; }
+		o[0] = 0;
+		for (int i = 0; i < n; ++i) o[i + 1] = o[i] + img.m_Rays[i].size() / 2;
+		double *e = (double *)std::malloc((2 * o[n] + 2) * sizeof(double));
+		if (!e) { std::free(o); set_err(err, errlen, "out of memory"); return 3; }
+		for (int i = 0; i < n; ++i)
+			std::memcpy(e + 2 * o[i], img.m_Rays[i].data(), (img.m_Rays[i].size() / 2) * 2 * sizeof(double));
+		*out_off = o; *out_ev = e;
+		return 0;
+	} catch (const std::exception &e) {
+		set_err(err, errlen, e.what());
+		return 1;
+	}
+}
+
 } // extern "C"

@@ -144,3 +144,23 @@ def test_svg_reader_units_viewbox_transforms_and_errors(tmp_path):
     for bad in ('<path d="M 0 0 A 5 5 0 0 1 10 10 Z"/>', '<rect x="1" y="1" width="5" height="5" rx="1"/>', '<use href="#a"/>'):
         rb, _ = run(bad)
         assert rb.returncode == 1 and "not supported" in rb.stderr
+
+
+@pytest.mark.parametrize("seed", [4, 5])
+def test_offset2d_transpose_matches_the_reference(reference, tmp_path, seed):
+    """offset2d -t: DoubleCompressedImage::transposeInPlace (DoubleCompressedImage.cpp:478-584, events truncated to
+    int) restated in voroffset_b200/cpp/vo_svg.cpp, against the reference's own routine."""
+    from voroffset_b200 import synth
+    img = synth.random_image(37, 53, kmax=4, seed=seed)
+    src, out = tmp_path / "in.dex", tmp_path / "out.dex"
+    with open(src, "w") as f:
+        f.write(f"{img.width} {img.rows}\n")
+        for i in range(img.rows):
+            row = img.spans[int(img.off[i]):int(img.off[i + 1])].reshape(-1)
+            f.write(str(row.size) + "".join(f" {v!r}" for v in row.tolist()) + "\n")
+    r = _offset2d(src, "-o", out, "-t")
+    assert r.returncode == 0, r.stderr
+    got = _load_dex(out)
+    want = reference.transposed(img)
+    assert (got.rows, got.width) == (want.rows, want.width) == (img.width, img.rows)
+    assert got.numSegments() > 20 and got.bit_equal(want)

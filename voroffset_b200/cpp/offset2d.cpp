@@ -53,24 +53,6 @@ static vor::DoubleCompressedImage load_poly(const std::string &file)
 	return img;
 }
 
-// transposeInPlace (DoubleCompressedImage.cpp:478-584) is upstream of the hot path: a plain host restatement
-// that rasterises the row intervals onto unit columns (rows become the sweep axis of the transposed image).
-static void transpose(vor::DoubleCompressedImage &img)
-{
-	const int w = img.width(), h = img.height();
-	vor::DoubleCompressedImage t(h, w);
-	for (int x = 0; x < w; ++x) {
-		const double xc = x + 0.5;
-		bool inside = false;
-		for (int y = 0; y <= h; ++y) {
-			bool in = false;
-			if (y < h) for (size_t k = 0; k + 1 < img.m_Rays[y].size(); k += 2) in |= img.m_Rays[y][k] <= xc && xc < img.m_Rays[y][k + 1];
-			if (in != inside) { t.m_Rays[x].push_back((double)y); inside = in; }
-		}
-	}
-	img = t;
-}
-
 int main(int argc, char *argv[])
 {
 	struct { std::string input, output = "out.dex"; double radius = 0; bool erode = false, force = false, transpose = false, negate = false; } args;
@@ -95,7 +77,7 @@ int main(int argc, char *argv[])
 		if (ends(args.input, ".svg")) dexels = vor::create_dexels(args.input);           // offset2d.cpp:47
 		else if (ends(args.input, ".poly")) dexels = load_poly(args.input);
 		else { std::ifstream in(args.input); dexels.load(in); }
-		if (args.transpose) transpose(dexels);                      // offset2d.cpp:50-52
+		if (args.transpose) dexels.transposeInPlace();                      // offset2d.cpp:50-52
 		if (args.negate) dexels.negate();                           // offset2d.cpp:53-55
 		if (args.radius > 0) {                                      // offset2d.cpp:58-66
 			std::cout << "-- Performing offset by radius r = " << args.radius << std::endl;

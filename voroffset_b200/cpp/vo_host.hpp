@@ -146,6 +146,7 @@ namespace voroffset
 		int height() const { return (int)m_Rays.size(); }
 		void resize(int w, int h) { m_XSize = w; m_Rays.assign(h, {}); }
 		void fromImage(const std::vector<Curve> &input_curves);   // DoubleCompressedImage.cpp:25-40 (vo_svg.cpp)
+		void transposeInPlace();               // DoubleCompressedImage.cpp:478-584 (vo_svg.cpp)
 		bool isValid() const;                  // DoubleCompressedImage.cpp:197-223
 		void save(std::ostream &out) const;    // DoubleCompressedImage.cpp:145-160
 		void load(std::istream &in);           // DoubleCompressedImage.cpp:162-183

@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <set>
 #include <sstream>
 #include <stdexcept>
 
@@ -77,6 +78,47 @@ namespace voroffset
 		if (b.empty()) return;
 		if (a.empty() || a.back() <= b.front()) a.insert(a.end(), b.begin(), b.end());
 		else a.insert(a.begin(), b.begin(), b.end());
+	}
+
+	// DoubleCompressedImage.cpp:478-584 (the #else branch that is compiled), restated literally: events are
+	// truncated to int (the routine comes from the integer-pixel CompressedImage), pixel (i, j) is covered when an
+	// odd number of events of ray j lie at or before i, and runs of covered pixels along j become the new rays.
+	// An image without events only swaps its dimensions (the reference indexes m_Rays[-1] there).
+	void DoubleCompressedImage::transposeInPlace()
+	{
+		std::set<std::pair<int, int>> allEvents;
+		for (int j = 0; j < (int)m_Rays.size(); ++j)
+			for (const auto &val : m_Rays[j]) allEvents.emplace((int)val, j);
+		{
+			const int tmp = m_XSize;
+			m_XSize = (int)m_Rays.size();
+			m_Rays.assign(tmp, {});
+		}
+		if (allEvents.empty()) return;
+		auto toggle = [](std::set<int> &s, int x) { if (s.count(x)) s.erase(x); else s.insert(x); };
+		int startCol = -1, endCol = -1, prevLine = -1;
+		std::set<int> currentLine;
+		for (const auto &ev : allEvents) {
+			const int i = ev.first, j = ev.second;
+			if (prevLine != i) {
+				toggle(currentLine, startCol);
+				toggle(currentLine, endCol);
+				startCol = endCol = j;
+				if (prevLine != -1)
+					for (int ii = prevLine; ii < i; ++ii)
+						for (int v : currentLine) m_Rays.at(ii).push_back(v);
+			}
+			if (j != endCol) {
+				toggle(currentLine, startCol);
+				toggle(currentLine, endCol);
+				startCol = j;
+			}
+			endCol = j + 1;
+			prevLine = i;
+		}
+		toggle(currentLine, startCol);
+		toggle(currentLine, endCol);
+		m_Rays.at(prevLine).insert(m_Rays.at(prevLine).end(), currentLine.begin(), currentLine.end());
 	}
 
 	// ---- a small SVG reader with nanosvg's conventions ----------------------------------------------
