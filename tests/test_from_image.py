@@ -134,6 +134,12 @@ def test_svg_reader_units_viewbox_transforms_and_errors(tmp_path):
     cnt = np.diff(img.off.astype(np.int64))
     assert list(np.nonzero(cnt)[0]) == list(range(11, 40))           # 10 mm < x < 40 mm (a vertex ON a line does not count twice)
     assert np.allclose(img.spans[0], [20.0, 70.0], atol=1e-4)
+    # quad-mesh export (src/vor2d/Dexelize.cpp:48-89): four vertices and one quad per interval
+    obj = tmp_path / "t.obj"
+    assert _offset2d(tmp_path / "t.svg", "-o", obj, "-f").returncode == 0
+    lines = obj.read_text().split("\n")
+    assert sum(l.startswith("v ") for l in lines) == 4 * img.numSegments() and sum(l.startswith("f ") for l in lines) == img.numSegments()
+    assert lines[0].split()[:2] == ["v", "11"] and float(lines[0].split()[2]) == float(img.spans[0, 0])
     # the same rectangle through a group transform and a relative path
     r2, img2 = run('<g transform="translate(20 40) scale(2)"><path d="m 0 0 h 30 v 50 h -30 z"/></g>')
     assert r2.returncode == 0, r2.stderr

@@ -88,8 +88,8 @@ int main(int argc, char *argv[])
 			std::cerr << "-- Output file already exists. Please use -f to force overwriting." << std::endl;
 		} else {
 			std::cout << "-- Saving" << std::endl;
-			std::ofstream out(args.output);
-			dexels.save(out);
+			if (ends(args.output, ".obj")) vor::dexel_dump(args.output, dexels);   // offset2d.cpp:69-81
+			else { std::ofstream out(args.output); dexels.save(out); }
 		}
 	} catch (const std::exception &e) {
 		std::cerr << "error: " << e.what() << std::endl;

@@ -166,4 +166,5 @@ namespace voroffset
 	// src/vor2d/Dexelize.cpp:22-47 without nanosvg (vo_svg.cpp): SVG -> contours (mm at 90 DPI) -> fromImage
 	std::vector<Curve> svg_contours(const std::string &file, double &width_mm, double &height_mm);
 	DoubleCompressedImage create_dexels(const std::string &file);
+	void dexel_dump(const std::string &filename, const DoubleCompressedImage &dexels);   // src/vor2d/Dexelize.cpp:48-89, OBJ
 }

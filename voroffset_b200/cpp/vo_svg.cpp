@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <iomanip>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -502,5 +503,25 @@ namespace voroffset
 		DoubleCompressedImage dexels((int)std::ceil(h * 25.4 / 90), (int)std::ceil(w * 25.4 / 90));
 		dexels.fromImage(contours);
 		return dexels;
+	}
+
+	// src/vor2d/Dexelize.cpp:48-89 without geogram: one quad per interval, ray x spans [x, x+1], z = 1; vertices
+	// in the reference's order (min,min) (max,min) (min,max) (max,max) and the quad (v, v+1, v+2, v+3) as it is
+	// created there. compute_borders / connect / remove_isolated do not change what mesh_save writes for an OBJ.
+	void dexel_dump(const std::string &filename, const DoubleCompressedImage &dexels)
+	{
+		std::ofstream out(filename);
+		if (!out) throw std::runtime_error("cannot write " + filename);
+		out << std::setprecision(17);
+		size_t v = 1;
+		std::ostringstream faces;
+		for (int x = 0; x < dexels.height(); ++x)
+			for (size_t i = 0; 2 * i + 1 < dexels.m_Rays[x].size(); ++i) {
+				const double y0 = dexels.m_Rays[x][2 * i], y1 = dexels.m_Rays[x][2 * i + 1];
+				out << "v " << x << ' ' << y0 << " 1\nv " << x + 1 << ' ' << y0 << " 1\nv " << x << ' ' << y1 << " 1\nv " << x + 1 << ' ' << y1 << " 1\n";
+				faces << "f " << v << ' ' << v + 1 << ' ' << v + 2 << ' ' << v + 3 << '\n';
+				v += 4;
+			}
+		out << faces.str();
 	}
 }
