@@ -26,5 +26,15 @@ img = synth.star_image(96, 96, 9)
 d = image2d.DoubleCompressedImage.from_image(img, ctx)
 d.dilate(3.0 / 96)
 ok &= d.bit_equal(orc.morph2d(img, "dilate", 3.0 / 96))
+# mesh -> dexels -> offset on the device, everything released explicitly so that --leak-check sees a clean exit
+from voroffset_b200.dexelize import dexelize_dev, grid_for
+V, F = synth.boxes_mesh(40)
+grid = grid_for(V, None, 2, 72)
+dv, _ = dexelize_dev(ctx, V, F, grid)
+ok &= dv.download(grid).bit_equal(orc.dexelize(V, F, grid))
+out, _, _ = morpho.make_operator("ours", ctx).morph_dev("closing", dv, 3.0)
+out.free(); dv.free(); d.free() if hasattr(d, "free") else None
+del d
+ctx.close()
 print("all equal:", ok)
 sys.exit(0 if ok else 1)

@@ -205,6 +205,7 @@ template <typename T> struct Tmp {
 std::mutex g_host_mu;
 std::unordered_map<void *, size_t> g_host_live;            // ptr -> capacity
 std::vector<std::pair<void *, size_t>> g_host_cache;       // released blocks kept for reuse
+int g_live_contexts = 0;                                   // the cache is emptied when the last context goes (guarded by g_host_mu)
 
 void *host_block(size_t bytes)
 {
@@ -1903,6 +1904,7 @@ int vo_create(int device, vo_ctx **out)
 		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) ctx->big_free_limit = total_b / 3;
 		else cudaGetLastError();
 	}
+	{ std::lock_guard<std::mutex> lk(g_host_mu); ++g_live_contexts; }
 	if (!ok) { cudaGetLastError(); vo_destroy(ctx); return VO_ERR_CUDA; }
 	*out = ctx;
 	return VO_OK;
@@ -1928,6 +1930,13 @@ void vo_destroy(vo_ctx *ctx)
 	if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
+	// pinned result blocks waiting for reuse (vo_free) are process-wide; the last context releases them
+	std::lock_guard<std::mutex> lk(g_host_mu);
+	if (--g_live_contexts <= 0) {
+		g_live_contexts = 0;
+		for (auto &blk : g_host_cache) cudaFreeHost(blk.first);
+		g_host_cache.clear();
+	}
 }
 
 const char *vo_last_error(const vo_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
