@@ -64,6 +64,38 @@ def main():
         path = os.path.join(HERE, f"img2d_{name}.npz")
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path) // 1024, "KiB")
+    ingest(ref)
+
+
+def ingest_curves():
+    """Seeded closed polygons for DoubleCompressedImage::fromImage: stars in a grid, a rectangle with vertices ON scan
+    lines and an edge along one, and a curve whose crossings go in front of the ray's content."""
+    import math
+    rng = np.random.default_rng(77)
+    w, h, curves = 120, 90, []
+    for k in range(12):
+        cx, cy = (k % 4 + 0.5) * h / 4 + rng.uniform(-1, 1), (k // 4 + 0.5) * w / 3 + rng.uniform(-1, 1)
+        n = int(rng.integers(3, 9))
+        a = np.linspace(0, 2 * math.pi, 2 * n, endpoint=False) + rng.uniform(0, 1)
+        rr = np.where(np.arange(2 * n) % 2 == 0, 9.0, 4.0)
+        curves.append(np.stack([cx + rr * np.cos(a), cy + rr * np.sin(a)], 1))
+    curves.append(np.array([[5, 5], [12, 5], [12, 9], [5, 9.5]], float))
+    curves.append(np.array([[30, 1.0], [30, 2.5], [33, 2.5], [36, 4], [36, 1.0]], float))
+    return w, h, curves
+
+
+def ingest(ref):
+    """2D ingestion fixture: fromImage (DoubleCompressedImage.cpp:25-111) and transposeInPlace (:478-584) outputs of
+    the reference."""
+    w, h, curves = ingest_curves()
+    img = ref.from_image(w, h, curves)
+    src = synth.random_image(37, 53, kmax=4, seed=4)
+    tr = ref.transposed(src)
+    path = os.path.join(HERE, "ingest2d.npz")
+    np.savez_compressed(path, w=w, h=h, curve_off=np.cumsum([0] + [len(c) for c in curves]), curve_pts=np.concatenate(curves),
+                        img_off=img.off, img_spans=img.spans, t_in_off=src.off, t_in_spans=src.spans, t_rows=src.rows,
+                        t_width=src.width, t_off=tr.off, t_spans=tr.spans)
+    print(path, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":

@@ -152,6 +152,23 @@ def test_svg_reader_units_viewbox_transforms_and_errors(tmp_path):
         assert rb.returncode == 1 and "not supported" in rb.stderr
 
 
+def test_offset2d_transpose_matches_the_reference_fixture(tmp_path):
+    """The same without oracle/_ref: tests/golden/ingest2d.npz holds the reference's transposeInPlace output."""
+    import util
+    z = np.load(os.path.join(util.GOLDEN, "ingest2d.npz"))
+    img = DexelImage(int(z["t_rows"]), int(z["t_width"]), z["t_in_off"], z["t_in_spans"])
+    src, out = tmp_path / "in.dex", tmp_path / "out.dex"
+    with open(src, "w") as f:
+        f.write(f"{img.width} {img.rows}\n")
+        for i in range(img.rows):
+            row = img.spans[int(img.off[i]):int(img.off[i + 1])].reshape(-1)
+            f.write(str(row.size) + "".join(f" {v!r}" for v in row.tolist()) + "\n")
+    r = _offset2d(src, "-o", out, "-t")
+    assert r.returncode == 0, r.stderr
+    got = _load_dex(out)
+    assert got.off.tolist() == z["t_off"].tolist() and (got.spans.view("u8") == z["t_spans"].view("u8")).all()
+
+
 @pytest.mark.parametrize("seed", [4, 5])
 def test_offset2d_transpose_matches_the_reference(reference, tmp_path, seed):
     """offset2d -t: DoubleCompressedImage::transposeInPlace (DoubleCompressedImage.cpp:478-584, events truncated to

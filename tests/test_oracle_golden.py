@@ -25,3 +25,15 @@ def test_oracle_matches_reference_outputs_2d(oracle, path):
 
 def test_golden_set_is_present():
     assert len(util.golden_3d()) >= 5 and len(util.golden_2d()) >= 2
+
+
+def test_oracle_from_image_matches_the_reference_fixture(oracle):
+    """fromImage of the reference (tests/golden/ingest2d.npz, written by make_golden.py from oracle/_ref)."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(util.GOLDEN, "ingest2d.npz"))
+    co = z["curve_off"]
+    curves = [z["curve_pts"][co[k]:co[k + 1]] for k in range(len(co) - 1)]
+    got = oracle.from_image(int(z["w"]), int(z["h"]), curves)
+    assert got.off.tolist() == z["img_off"].tolist() and int(got.off[-1]) > 100
+    assert (got.spans.view("u8") == z["img_spans"].view("u8")).all()
