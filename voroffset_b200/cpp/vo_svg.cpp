@@ -20,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <iomanip>
+#include <map>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -81,45 +82,40 @@ namespace voroffset
 		else a.insert(a.begin(), b.begin(), b.end());
 	}
 
-	// DoubleCompressedImage.cpp:478-584 (the #else branch that is compiled), restated literally: events are
-	// truncated to int (the routine comes from the integer-pixel CompressedImage), pixel (i, j) is covered when an
-	// odd number of events of ray j lie at or before i, and runs of covered pixels along j become the new rays.
-	// An image without events only swaps its dimensions (the reference indexes m_Rays[-1] there).
+	// Same result as DoubleCompressedImage::transposeInPlace (DoubleCompressedImage.cpp:478-584, the #else branch that
+	// is compiled), computed on a coverage vector instead of the reference's incremental run toggling. What that
+	// routine does: every event is truncated to int (it comes from the integer-pixel CompressedImage) and the (line,
+	// ray) pairs are de-duplicated in a std::set; going through the lines in ascending order, the rays that have an
+	// event on a line flip their coverage there; new ray ii, for every ii from one event line up to the next, lists
+	// the positions where the coverage (as a function of the old ray index) changes; the last event line only
+	// yields its own ray. An image without events just swaps its dimensions (the reference indexes m_Rays[-1]
+	// there); an event at or beyond the old ray length raises instead of writing out of bounds.
 	void DoubleCompressedImage::transposeInPlace()
 	{
-		std::set<std::pair<int, int>> allEvents;
-		for (int j = 0; j < (int)m_Rays.size(); ++j)
-			for (const auto &val : m_Rays[j]) allEvents.emplace((int)val, j);
-		{
-			const int tmp = m_XSize;
-			m_XSize = (int)m_Rays.size();
-			m_Rays.assign(tmp, {});
-		}
-		if (allEvents.empty()) return;
-		auto toggle = [](std::set<int> &s, int x) { if (s.count(x)) s.erase(x); else s.insert(x); };
-		int startCol = -1, endCol = -1, prevLine = -1;
-		std::set<int> currentLine;
-		for (const auto &ev : allEvents) {
-			const int i = ev.first, j = ev.second;
-			if (prevLine != i) {
-				toggle(currentLine, startCol);
-				toggle(currentLine, endCol);
-				startCol = endCol = j;
-				if (prevLine != -1)
-					for (int ii = prevLine; ii < i; ++ii)
-						for (int v : currentLine) m_Rays.at(ii).push_back(v);
+		const int old_rays = (int)m_Rays.size();
+		std::map<int, std::set<int>> flips;                    // line -> rays with an event on it
+		for (int j = 0; j < old_rays; ++j)
+			for (const Scalar val : m_Rays[j]) flips[(int)val].insert(j);
+		const int new_rays = m_XSize;
+		m_XSize = old_rays;
+		m_Rays.assign(new_rays, {});
+		if (flips.empty()) return;
+		std::vector<char> covered((size_t)old_rays + 1, 0);    // [old_rays] stays 0: closes a run that reaches the end
+		auto boundaries = [&](std::vector<Scalar> &dst) {
+			char prev = 0;
+			for (int j = 0; j <= old_rays; ++j) {
+				if (covered[j] != prev) dst.push_back((Scalar)j);
+				prev = covered[j];
 			}
-			if (j != endCol) {
-				toggle(currentLine, startCol);
-				toggle(currentLine, endCol);
-				startCol = j;
-			}
-			endCol = j + 1;
-			prevLine = i;
+		};
+		int prev_line = -1;
+		for (const auto &line : flips) {
+			if (prev_line != -1)
+				for (int ii = prev_line; ii < line.first; ++ii) boundaries(m_Rays.at(ii));
+			for (int j : line.second) covered[j] ^= 1;
+			prev_line = line.first;
 		}
-		toggle(currentLine, startCol);
-		toggle(currentLine, endCol);
-		m_Rays.at(prevLine).insert(m_Rays.at(prevLine).end(), currentLine.begin(), currentLine.end());
+		boundaries(m_Rays.at(prev_line));
 	}
 
 	// ---- a small SVG reader with nanosvg's conventions ----------------------------------------------
