@@ -41,33 +41,28 @@ namespace voroffset
 		}
 	}
 
-	// DoubleCompressedImage.cpp:43-86: crossings of the closed polygon with the line x = line_x (an integer
-	// abscissa); a run of vertices exactly on the line counts once, and only when the curve changes side there.
+	// DoubleCompressedImage.cpp:43-86: crossings of the closed polygon with the line x = line_x (an integer abscissa).
+	// From every vertex off the line, walk to the next vertex off the line; the polygon crosses when the two lie on
+	// different sides. A direct edge is cut with the reference's interpolation (weights from the END point:
+	// s = (x_next - line) / (x_next - x_i), y = s y_i + (1 - s) y_next); when vertices ON the line lie in between,
+	// the crossing is the y of the last of them.
 	void DoubleCompressedImage::scanLine(std::vector<Scalar> &out, int line_x, const Curve &curve)
 	{
 		out.clear();
 		const int n = (int)curve.size();
-		auto re = [&](int i) { return curve[i % n].real(); };
-		auto im = [&](int i) { return curve[i % n].imag(); };
+		auto side = [&](int i) { const Scalar x = curve[i % n].real(); return x < line_x ? -1 : (x > line_x ? 1 : 0); };
 		for (int i = 0; i < n; ++i) {
-			if (re(i) < line_x) {
-				if (re(i + 1) > line_x) {
-					const Scalar s = (re(i + 1) - line_x) / (re(i + 1) - re(i));
-					out.push_back(s * im(i) + (1 - s) * im(i + 1));
-				} else {
-					int j = 1;
-					while (re(i + j) == line_x) j++;
-					if (re(i + j) > line_x) out.push_back(im(i + j - 1));
-				}
-			} else if (re(i) > line_x) {
-				if (re(i + 1) < line_x) {
-					const Scalar s = (re(i + 1) - line_x) / (re(i + 1) - re(i));
-					out.push_back(s * im(i) + (1 - s) * im(i + 1));
-				} else {
-					int j = 1;
-					while (re(i + j) == line_x) j++;
-					if (re(i + j) < line_x) out.push_back(im(i + j - 1));
-				}
+			const int here = side(i);
+			if (here == 0) continue;
+			int k = i + 1;
+			while (side(k) == 0) ++k;              // (terminates: vertex i itself is off the line)
+			if (side(k) == here) continue;
+			if (k == i + 1) {
+				const PointF &p = curve[i], &q = curve[k % n];
+				const Scalar s = (q.real() - line_x) / (q.real() - p.real());
+				out.push_back(s * p.imag() + (1 - s) * q.imag());
+			} else {
+				out.push_back(curve[(k - 1) % n].imag());
 			}
 		}
 		std::sort(out.begin(), out.end());
