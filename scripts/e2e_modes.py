@@ -11,14 +11,13 @@ def call():
     ctx.check(ctx.lib.vo_morph3d(ctx.handle, 0, 0, vol.nx, vol.ny, vol.zmin, vol.zmax, off_pin.data_ptr(), sp_pin.data_ptr(), R,
                                  C.byref(poff), C.byref(pspans), C.byref(n), None, None))
     ctx.lib.vo_free(C.cast(poff, C.c_void_p)); ctx.lib.vo_free(C.cast(pspans, C.c_void_p))
-for ctas in ("1", "2", "4"):
-    for split in ("1", "2", "4"):
-        for bands in ("8", "12"):
-            ctx.set_option("tile_ctas", ctas); ctx.set_option("band_split", split); ctx.set_option("bands", bands)
-            for _ in range(3): call()
-            ts = []
-            for _ in range(3):
-                t = time.perf_counter()
-                for _ in range(5): call()
-                ts.append((time.perf_counter() - t) * 200)
-            print("tile_ctas", ctas, "band_split", split, "bands", bands, "e2e ms", round(min(ts), 3), flush=True)
+for free in ("0", "8", "16", "24", "32", "48"):
+    for split in ("1", "2"):
+        ctx.set_option("band_free", free); ctx.set_option("band_split", split)
+        for _ in range(3): call()
+        ts = []
+        for _ in range(4):
+            t = time.perf_counter()
+            for _ in range(5): call()
+            ts.append((time.perf_counter() - t) * 200)
+        print("band_free", free, "band_split", split, "e2e ms", round(min(ts), 3), "median", round(sorted(ts)[len(ts) // 2], 3), flush=True)

@@ -7,6 +7,9 @@ ctx = _lib.Context(0)
 vol = synth.torus_z(2048); R = 32.0
 off_pin = torch.from_numpy(vol.off.view(np.int32)).pin_memory(); sp_pin = torch.from_numpy(vol.spans).pin_memory()
 ctx.set_option("bands", sys.argv[1] if len(sys.argv) > 1 else "8")
+for kv in sys.argv[3:]:            # further options as key=value (band_free=32 band_split=1 ...)
+    k, v = kv.split("=")
+    ctx.set_option(k, v)
 for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     poff, pspans, n = _lib._u32p(), _lib._f64p(), C.c_uint64()
     ctx.check(ctx.lib.vo_morph3d(ctx.handle, 0, 0, vol.nx, vol.ny, vol.zmin, vol.zmax, off_pin.data_ptr(), sp_pin.data_ptr(), R,

@@ -134,7 +134,16 @@ struct ThreshArgs {
 	double clip_lo, clip_hi;             // the result is only read inside (clip_lo, clip_hi); -inf / +inf: everywhere
 	unsigned int *est = nullptr;         // optional, [ny * tiles_xw], zeroed by the host: estimated cost of every pass-1 tile
 	int tiles_xw = 0;                    //   (surviving pairs weighted by their classes; only the ORDER of the tiles uses it)
+	unsigned long long *zero_bank = nullptr;   // optional: the tile lists and cursors ([3] [5] [6] [7] [10]) of the launch set that
+	                                           //   follows on this stream are zeroed here instead of by three memsets of their own
 };
+
+__device__ __forceinline__ void thresh_zero_bank(const ThreshArgs &a)
+{
+	if (a.zero_bank && blockIdx.x == 0 && threadIdx.x == 0) {
+		a.zero_bank[3] = 0; a.zero_bank[5] = 0; a.zero_bank[6] = 0; a.zero_bank[7] = 0; a.zero_bank[10] = 0;
+	}
+}
 
 __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 {
@@ -142,6 +151,7 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	double *s_D = s_DE, *s_E = s_DE + a.J + 2;
 	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) { s_D[i] = a.Dmono[i]; s_E[i] = a.Emono[i]; }
 	__syncthreads();
+	thresh_zero_bank(a);
 	const unsigned long long c = a.c_begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = c < a.c_end;
 	if (!a.est && !in_range) return;
@@ -227,6 +237,7 @@ __global__ void __launch_bounds__(256) k_thresh_quad(ThreshArgs a)
 	double *s_D = s_DE, *s_E = s_DE + a.J + 2;
 	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) { s_D[i] = a.Dmono[i]; s_E[i] = a.Emono[i]; }
 	__syncthreads();
+	thresh_zero_bank(a);
 	const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const unsigned long long c = a.c_begin + t / TH_Q;
 	const int dir = (int)(threadIdx.x & (TH_Q - 1)), lane = (int)(threadIdx.x & 31);

@@ -54,6 +54,7 @@ struct vo_ctx {
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
 	int band_split = 2;               // vo_set_option("band_split", "N"): a band's pass-1 launch set takes 1/N of the SMs (host-buffer pipeline)
+	int band_free = 0;                // vo_set_option("band_free", "N"): SMs no pass-1 launch set of the pipeline takes (room for its small kernels and pass 2)
 	int pipe_bands = 8;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
 	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
@@ -1251,7 +1252,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	Tmp<unsigned int> est(ctx), order0(ctx), order1(ctx);
 	const bool ordered = ctx->tile_order;
 	if (ordered) {
-		VO_TRY(dalloc(ctx, &est.p, ntiles + 4 * P1_NBUCKET));
+		VO_TRY(dalloc(ctx, &est.p, ntiles + 2ull * P1_NBUCKET * nb));      // [nb][2 * P1_NBUCKET] bucket counters | cost estimate per tile
 		VO_TRY(dalloc(ctx, &order0.p, ntiles));
 		VO_TRY(dalloc(ctx, &order1.p, ntiles));
 	}
@@ -1298,7 +1299,9 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	if (std::getenv("VO_TRACE")) { cudaEventCreate(&ev_t0); cudaEventRecord(ev_t0, pr.s_in); }
 	std::vector<cudaEvent_t> ev_in(nb), ev_done(nb);
 	for (int b = 0; b < nb; ++b) {
-		const int y0 = ys[b], y1 = ys[b + 1];
+		// rows [ys[b] + 1, ys[b + 1] + 1): one row ahead of the band, so that pass 1 of band b (whose thresholds read the
+		// row below) can start as soon as ITS upload is done instead of waiting for the next one
+		const int y0 = b == 0 ? 0 : ys[b] + 1, y1 = std::min(ny, ys[b + 1] + 1);
 		const unsigned long long c0 = (unsigned long long)y0 * nx, c1 = (unsigned long long)y1 * nx;
 		cudaMemcpyAsync(in->off + c0, off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, pr.s_in);
 		if (off[c1] > off[c0])
@@ -1328,7 +1331,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	if (trace && ev_t0) marks.emplace_back("start 0", ev_t0);
 	cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), ctx->stream);
 	cudaMemsetAsync(m->tilemask, 0, 2ull * ny * tiles_x * sizeof(unsigned long long), ctx->stream);
-	if (ordered) cudaMemsetAsync(est.p, 0, (ntiles + 4 * P1_NBUCKET) * sizeof(unsigned int), ctx->stream);
+	if (ordered) cudaMemsetAsync(est.p, 0, (ntiles + 2ull * P1_NBUCKET * nb) * sizeof(unsigned int), ctx->stream);
 	cudaMemsetAsync(gb.p, 0, (3ull * nb + 1) * sizeof(unsigned long long), ctx->stream);
 	cudaEventRecord(ctx->ev[0], ctx->stream);
 	{
@@ -1360,29 +1363,26 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		const int y0 = ys[b], y1 = ys[b + 1], w = b & 1;
 		cudaStream_t sp = ctx->s_p[w];
 		unsigned long long *bank = w ? ctx->d_ctr + NCTR + 8 : ctx->d_ctr;
-		cudaStreamWaitEvent(sp, ev_in[std::min(b + 1, nb - 1)], 0);     // thresholds of a band's last row read the next band's first row
+		cudaStreamWaitEvent(sp, ev_in[b], 0);                // (the upload of a band includes the first row of the next: thresholds look one row down)
 		mark("pass1 begin", b, sp);
-		cudaMemsetAsync(bank + 3, 0, sizeof(unsigned long long), sp);
-		cudaMemsetAsync(bank + 5, 0, 3 * sizeof(unsigned long long), sp);
-		cudaMemsetAsync(bank + 10, 0, sizeof(unsigned long long), sp);
+		ta.zero_bank = bank;                                 // the lists and cursors of this launch set, zeroed by k_thresh itself
 		ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
 		const unsigned int t0 = (unsigned int)plan.tiles_xw * (unsigned int)y0, nt = (unsigned int)plan.tiles_xw * (unsigned int)(y1 - y0);
 		unsigned int *ord = nullptr;
 		if (ordered) {
-			unsigned int *scratch = est.p + 2 * P1_NBUCKET * w;
-			if (b >= 2) cudaMemsetAsync(scratch, 0, 2 * P1_NBUCKET * sizeof(unsigned int), sp);
-			ta.est = est.p + 4 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw;
+			ta.est = est.p + 2ull * P1_NBUCKET * nb; ta.tiles_xw = plan.tiles_xw;
 			ord = (w ? order1.p : order0.p) + t0;
 		}
 		launch_thresh(ta, k_in, sp);
 		ctx->launches++;
 		mark("  thresh end", b, sp);
-		if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p + 2 * P1_NBUCKET * w, ord, t0, nt, 0u, 0u, sp);
+		if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p + 2ull * P1_NBUCKET * b, ord, t0, nt, 0u, 0u, sp);
 		mark("  order end", b, sp);
 		g.redo = redo_of(b);
 		// (the two streams' launch sets may each take a share of the SMs, so that they run side by side instead of the
 		// second waiting for CTAs of the first to retire)
-		const int reserve = ctx->band_split > 1 ? plan.sms - plan.sms / ctx->band_split : 0;
+		const int usable = std::max(ctx->band_split, plan.sms - std::max(0, ctx->band_free));
+		const int reserve = plan.sms - usable / std::max(1, ctx->band_split);
 		plan.launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, reserve, bank, ord);
 		ev_p1[b] = pr.event();
 		cudaEventRecord(ev_p1[b], sp);
@@ -1973,6 +1973,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "bands") == 0) {
 		const int n = std::atoi(value);
 		if (n >= 3 && n <= 64) { ctx->pipe_bands = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "band_free") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 0 && n <= 96) { ctx->band_free = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "band_split") == 0) {
 		const int n = std::atoi(value);
