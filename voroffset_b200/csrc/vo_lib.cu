@@ -1248,7 +1248,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	VO_TRY(dalloc(ctx, &multi_tiles.p, ntiles));
 	VO_TRY(dalloc(ctx, &big_tiles1.p, ntiles));
 	VO_TRY(dalloc(ctx, &multi_tiles1.p, ntiles));
-	// tile order per band (expensive first): [per stream 2 * P1_NBUCKET counters | cost estimate per tile], permutations per stream
+	// tile order per band (expensive first): [per band 2 * P1_NBUCKET counters | cost estimate per tile], permutations per stream
 	Tmp<unsigned int> est(ctx), order0(ctx), order1(ctx);
 	const bool ordered = ctx->tile_order;
 	if (ordered) {
