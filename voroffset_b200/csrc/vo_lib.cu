@@ -54,6 +54,7 @@ struct vo_ctx {
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
 	int band_split = 2;               // vo_set_option("band_split", "N"): a band's pass-1 launch set takes 1/N of the SMs (host-buffer pipeline)
+	int pipe_warps = 64;              // vo_set_option("pipe_warps", "N"): warps per tile-kernel CTA in the host-buffer pipeline (default: as many as fit)
 	int band_free = 0;                // vo_set_option("band_free", "N"): SMs no pass-1 launch set of the pipeline takes (room for its small kernels and pass 2)
 	int pipe_bands = 8;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
 	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
@@ -606,7 +607,9 @@ struct TilePlan {
 	size_t smem_small = 0, smem_big = 0, smem_multi = 0;
 	static constexpr int CMAX = 2048;       // largest candidate buffer (11-bit candidate ids in the survivor lists)
 	static bool fits(int J, double k_in) { return J <= 63 && k_in * (P1_W + 2 * J) <= 0.75 * CMAX; }
-	int init(vo_ctx *ctx, int nx, int J_, double k_in)
+	// warps_cap: fewer warps per CTA than the registers allow (the host-buffer pipeline leaves room on every SM for the
+	// small kernels of the other bands, which otherwise wait for a persistent tile CTA to retire)
+	int init(vo_ctx *ctx, int nx, int J_, double k_in, int warps_cap = 64)
 	{
 		J = J_;
 		tiles_xw = (nx + P1_W - 1) / P1_W;
@@ -631,7 +634,7 @@ struct TilePlan {
 		auto warps = [&](int cmax, int lcap, int maxw) {
 			const size_t per = pass1_warp_smem(J, cmax, lcap), tab = pass1_table_smem(J) + 32;
 			if (budget < tab + per) return 1;
-			return (int)std::max<size_t>(1, std::min<size_t>(maxw / cps, (budget - tab) / per));
+			return (int)std::max<size_t>(1, std::min<size_t>(std::min(maxw, warps_cap) / cps, (budget - tab) / per));
 		};
 		nw_small = warps(cmax_small, P1_LCAP_S, P1_MAXWARPS); nw_big = warps(cmax_big, P1_LCAP_M, P1_MAXWARPS);
 		nw_multi = warps(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M);
@@ -1239,7 +1242,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	Tmp<uint4> thr(ctx);
 	VO_TRY(dalloc(ctx, &thr.p, nspans));
 	TilePlan plan;
-	VO_TRY(plan.init(ctx, nx, J, k_in));
+	VO_TRY(plan.init(ctx, nx, J, k_in, ctx->pipe_warps));
 	const int tiles_x = plan.tiles_x;
 	VO_TRY(dalloc(ctx, &m->tilemask, 2ull * ny * tiles_x));
 	const unsigned long long ntiles = (unsigned long long)plan.tiles_xw * ny;
@@ -1318,8 +1321,9 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	// VO_TRACE=1: device-side timeline of the call on stderr (development aid, scripts/e2e_bands.py)
 	static const bool trace = std::getenv("VO_TRACE") != nullptr;
 	std::vector<std::pair<std::string, cudaEvent_t>> marks;
+	static const bool trace_few = trace && std::getenv("VO_TRACE")[0] == '2';   // VO_TRACE=2: band 0 and the downloads only (perturbs less)
 	auto mark = [&](const char *name, int b, cudaStream_t st) {
-		if (!trace) return;
+		if (!trace || (trace_few && b != 0 && std::strncmp(name, "download", 8) != 0)) return;
 		cudaEvent_t ev;
 		cudaEventCreate(&ev);
 		cudaEventRecord(ev, st);
@@ -1973,6 +1977,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "bands") == 0) {
 		const int n = std::atoi(value);
 		if (n >= 3 && n <= 64) { ctx->pipe_bands = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "pipe_warps") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 1 && n <= 64) { ctx->pipe_warps = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "band_free") == 0) {
 		const int n = std::atoi(value);
