@@ -1213,6 +1213,13 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const int nb = (int)ys.size() - 1;
 	int BH = 0;                                              // the tallest band
 	for (int b = 0; b < nb; ++b) BH = std::max(BH, ys[b + 1] - ys[b]);
+	// The second half (pass 2 .. download) works on bands shifted UP by floor(R) rows: its rows [ys2[b], ys2[b+1]) only
+	// read mid rows below ys[b+1], i.e. pass 1 of the bands 0 .. b - a band's result no longer waits for pass 1 of the
+	// band behind it. (The last one takes the floor(R) rows that are left over.)
+	std::vector<int> ys2(ys);
+	for (int b = 1; b < nb; ++b) ys2[b] = ys[b] - J;
+	int BH2 = 0;
+	for (int b = 0; b < nb; ++b) BH2 = std::max(BH2, ys2[b + 1] - ys2[b]);
 	if (nb < 3 || ncols * (unsigned long long)(J + 1) < (48ull << 20) || !TilePlan::fits(J, k_in)) return PIPE_NA;
 	if (nspans && !spans) return PIPE_NA;
 
@@ -1277,10 +1284,10 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const unsigned long long dcap = hs_cap;
 	StageBuf sb(ctx);
 	VO_TRY(sb.alloc(ncols, 65536ull + ncols / 8));
-	const unsigned int rcap2 = (unsigned int)std::min<unsigned long long>((unsigned long long)nx * BH, 1ull << 22);
+	const unsigned int rcap2 = (unsigned int)std::min<unsigned long long>((unsigned long long)nx * BH2, 1ull << 22);
 	Tmp<unsigned long long> redo2(ctx), sums(ctx), gb(ctx);
 	VO_TRY(dalloc(ctx, &redo2.p, (unsigned long long)rcap2 * nb));
-	const unsigned int nt_max = blocks_for((unsigned long long)nx * BH, SCAN_TILE);
+	const unsigned int nt_max = blocks_for((unsigned long long)nx * BH2, SCAN_TILE);
 	VO_TRY(dalloc(ctx, &sums.p, ((unsigned long long)nt_max + 1) * nb));
 	VO_TRY(dalloc(ctx, &gb.p, 3ull * nb + 1));                // [nb + 1] running totals, [nb] redo counts of pass 2, [nb] of pass 1
 	vo_dvol *dout = nullptr;
@@ -1415,7 +1422,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 
 	std::vector<cudaEvent_t> ev_tot(nb);
 	auto second_half = [&](int b) {
-		const int y0 = ys[b], y1 = ys[b + 1];
+		const int y0 = ys2[b], y1 = ys2[b + 1];
 		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
 		const unsigned int nt = blocks_for(nlists, SCAN_TILE);
 		unsigned long long *sums_b = sums.p + (size_t)b * (nt_max + 1);
@@ -1423,7 +1430,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		st.cnt += c0; st.inl += c0 * STAGE_INLINE;
 		const Redo rd{redo2.p + (size_t)b * rcap2, reinterpret_cast<unsigned int *>(gb.p + nb + 1 + b), rcap2};
 		cudaStream_t sm = sh[b & 1];                        // consecutive bands overlap; only the running total is a chain
-		cudaStreamWaitEvent(sm, ev_r1[std::min(b + 1, nb - 1)], 0);     // pass 2 of band b reads the mid rows of band b+1
+		cudaStreamWaitEvent(sm, ev_r1[b], 0);                // rows [ys2[b], ys2[b+1]) read mid rows below ys[b+1]: pass 1 of the bands 0 .. b
 		mark("pass2 begin", b, sm);
 		Pass2Args a2;
 		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = y0; a2.y1 = y1;
@@ -1455,7 +1462,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	for (int b = 0; b < nb; ++b) second_half(b);
 	uint64_t base = 0;          // intervals of the bands downloaded so far
 	for (int b = 0; b < nb && rc == VO_OK; ++b) {
-		const int y0 = ys[b], y1 = ys[b + 1];
+		const int y0 = ys2[b], y1 = ys2[b + 1];
 		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
 		if (cudaEventSynchronize(ev_tot[b]) != cudaSuccess) { rc = PIPE_NA; break; }
 		const uint64_t tot = h_tot[b];
