@@ -68,8 +68,13 @@ void       *vo_stream(const vo_ctx *ctx);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches).                 */
 uint64_t    vo_launch_count(const vo_ctx *ctx);
 
-/* Tuning knobs. "pass1" = "auto" (default: tile kernel when it fits) | "tile" | "simple" (one thread per
- * (x, y, class); kept as the general fallback and as an independent implementation for the tests).     */
+/* Tuning knobs (none changes a result bit). "pass1" = "auto" (default: tile kernel when it fits) | "tile" | "simple"
+ * (one thread per (x, y, class); kept as the general fallback and as an independent implementation for the tests);
+ * "tile_order" = "on" | "off" (expensive pass-1 tiles first); "tile_ctas" = 1..8 (CTAs per SM of the tile kernel);
+ * "block_cache" = "on" | "off" (released scratch blocks >= 1 MiB kept whole for the next call);
+ * host-buffer call (vo_morph3d): "pipeline" = "on" | "off" (bands of rows uploaded, processed and downloaded
+ * concurrently), "bands" = 3..64, "band_split" = 1..4, "band_free" = 0..96 SMs, "pipe_warps" = 1..64;
+ * y-slab step: "slab" = "overlap" | "serial".                                                           */
 int         vo_set_option(vo_ctx *ctx, const char *key, const char *value);
 /* Timing on the context's own stream (torch.cuda.Event only sees torch's streams): vo_mark records event
  * `slot` (0..7); vo_elapsed_ms waits for slot_b and returns the device time between the two marks.     */
