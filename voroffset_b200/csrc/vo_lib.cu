@@ -1324,7 +1324,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	cudaEvent_t ev_up_done = nullptr;
 	if (std::getenv("VO_TRACE")) { cudaEventCreate(&ev_up_done); cudaEventRecord(ev_up_done, pr.s_in); }
 
-	cudaStream_t sh[2] = {ctx->s_hi[0], ctx->s_hi[1]}, s_redo = ctx->s_hi[2];
+	cudaStream_t sh[2] = {ctx->s_hi[0], ctx->s_hi[1]};
 	// VO_TRACE=1: device-side timeline of the call on stderr (development aid, scripts/e2e_bands.py)
 	static const bool trace = std::getenv("VO_TRACE") != nullptr;
 	std::vector<std::pair<std::string, cudaEvent_t>> marks;
@@ -1399,16 +1399,18 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaEventRecord(ev_p1[b], sp);
 		mark("pass1 end", b, sp);
 	};
-	// whatever outgrew the fast paths of band b is redone on a stream of its own, in band order: ev_r1[b] = pass 1 of
-	// the bands 0 .. b is complete
-	auto pass1_redo = [&](int b) {
-		cudaStreamWaitEvent(s_redo, ev_p1[b], 0);
+	// Whatever outgrew the fast paths of pass 1 in band b is redone at the head of that band's second half (normally an
+	// idle launch: no stream of its own, no extra hop between the streams). ev_r1[b] = pass 1 of the bands 0 .. b is
+	// complete, redone slots included.
+	auto pass1_redo = [&](int b, cudaStream_t st) {
+		cudaStreamWaitEvent(st, ev_p1[b], 0);
+		if (b > 0) cudaStreamWaitEvent(st, ev_r1[b - 1], 0);
 		a1.redo = redo_of(b);
 		a1.wk = Work{a1.redo.list, 0ull, a1.redo.count, a1.redo.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
-		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, s_redo>>>(a1);
+		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, st>>>(a1);
 		ctx->launches++;
 		ev_r1[b] = pr.event();
-		cudaEventRecord(ev_r1[b], s_redo);
+		cudaEventRecord(ev_r1[b], st);
 	};
 
 	// Second half of a band: pass 2 -> prefix sum -> compaction, enqueued WITHOUT a host round trip. The bands share
@@ -1430,7 +1432,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		st.cnt += c0; st.inl += c0 * STAGE_INLINE;
 		const Redo rd{redo2.p + (size_t)b * rcap2, reinterpret_cast<unsigned int *>(gb.p + nb + 1 + b), rcap2};
 		cudaStream_t sm = sh[b & 1];                        // consecutive bands overlap; only the running total is a chain
-		cudaStreamWaitEvent(sm, ev_r1[b], 0);                // rows [ys2[b], ys2[b+1]) read mid rows below ys[b+1]: pass 1 of the bands 0 .. b
+		pass1_redo(b, sm);                                   // rows [ys2[b], ys2[b+1]) read mid rows below ys[b+1]: pass 1 of the bands 0 .. b
 		mark("pass2 begin", b, sm);
 		Pass2Args a2;
 		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = y0; a2.y1 = y1;
@@ -1458,7 +1460,6 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	// Everything is enqueued up front: pass 1 of every band (it only waits for its upload), then the second halves
 	// (pass 2 of band b-1 needs pass 1 of band b). After that the host follows the bands and starts their downloads.
 	for (int b = 0; b < nb; ++b) pass1_band(b);
-	for (int b = 0; b < nb; ++b) pass1_redo(b);
 	for (int b = 0; b < nb; ++b) second_half(b);
 	uint64_t base = 0;          // intervals of the bands downloaded so far
 	for (int b = 0; b < nb && rc == VO_OK; ++b) {
