@@ -25,6 +25,10 @@
  *   xor (src/vor3d/Voronoi.cpp:91-111, MorphologyOperators.cpp:319-374).
  *   2D: DoubleCompressedImage::dilate/erode/open/close/negate (src/vor2d/DoubleCompressedImage.cpp:
  *     438-468,680-719; DoubleVoronoi.h:101-148; DoubleVoronoi.cpp:713-725).
+ *   Either side of the path (sections at the end of this file, each with its own header):
+ *     dexeliser   compute_sign and helpers (src/vor3d/Dexelize.cpp:56-225)         - PARITY UNPINNED (geogram absent)
+ *     2D ingest   DoubleCompressedImage::fromImage / scanLine / unionIntersections
+ *                 (src/vor2d/DoubleCompressedImage.cpp:25-111)                       - pinned against oracle/_ref
  *
  * Layout everywhere: column (x,y) of an nx*ny volume is list number c = x + nx*y; list c holds the
  * intervals ev[2*off[c]] .. ev[2*off[c+1]) as (z1,z2) pairs, ascending and disjoint.
