@@ -12,6 +12,8 @@ One JSON line on stdout (rank 0):
   value        whole-job columns/s with inputs resident in HBM (CUDA events on the library's stream)
   e2e          the same through the host-buffer C-ABI call (vo_morph3d): H2D of the CSR input from pinned
                memory, both passes, D2H of the CSR result, all inside the timed region
+               (N = 1: the banded pipeline of vo_morph3d; N > 1: vo_dvol_upload, the slab step with its halo
+               exchange, vo_dvol_download, one after the other)
   roofline     dominant kernel (k_pass1_tile): algorithmic bytes / its event-timed duration
   cpu_baseline the reference's own code (oracle/_ref) on a bounded sample with all host threads
 """
