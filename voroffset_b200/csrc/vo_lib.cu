@@ -1188,7 +1188,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const double k_in = (double)nspans / (double)ncols;
 	// Bands of rows: eight by default (vo_set_option("bands", N)) - enough to overlap the copies with the passes, few
 	// enough that a launch set of pass 1 still has many tiles per warp. (Small bands at both ends and large ones in
-	// between - early first download, short last stage - were tried and lose: the passes, not the copies, bound the call.)
+	// between, or a first band half as tall - early first download, short last stage - were tried and give nothing: a
+	// band's chain of stream-ordered launches costs the same whatever its height)
 	// Every band is at least 2 (floor(R) + 1) rows high (pass 2 of a band then only reaches into its two neighbours).
 	std::vector<int> ys;
 	{
