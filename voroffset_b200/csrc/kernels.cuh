@@ -160,6 +160,10 @@ struct Pass2Args {
 	const unsigned long long *tilemask;   // [2][ny * ceil(nx / 128)]: OR of the class windows (bit j = class j) of the
 	                        // columns of a pass-1 tile, consumers above ([0]) / below ([1]); NULL-free only for J <= 63
 	const double2 *pool;
+	unsigned long long pool_cap = ~0ull;   // entries of `pool`. The banded host-buffer call and the slab step run pass 2 before the
+	                        // host has seen pass 1's counters: a pass 1 that outgrew its pool leaves references beyond
+	                        // the end (the host then discards the result and repeats with a larger pool), which must
+	                        // not be followed
 	Stage st;
 	Redo redo;
 	Work wk;
@@ -169,13 +173,14 @@ struct Pass2Args {
 __device__ __forceinline__ bool flag_has(uint16_t w, int j) { return (int)(w & 0xffu) <= j && j < (int)(w >> 8); }
 
 template <int CAP>
-__device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot, const double2 *pool)
+__device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot, const double2 *pool, unsigned long long pool_cap)
 {
 	const double2 s = __ldg(slot);
 	if (s.x <= s.y) u.insert(s.x, s.y);
 	else if (slot_is_pool(s)) {
 		const unsigned long long base = slot_pool_base(s);
 		const unsigned int n = slot_pool_count(s);
+		if (base + n > pool_cap) return;
 		for (unsigned int k = 0; k < n; ++k) {
 			const double2 v = __ldg(pool + base + k);
 			u.insert(v.x, v.y);
@@ -191,7 +196,7 @@ __device__ __forceinline__ void pass2_gather(const Pass2Args &a, RunUnion<CAP> &
 {
 	const size_t nx = (size_t)a.nx, midrow = (size_t)(a.J + 1) * nx;
 	const double2 *self = a.mid + (size_t)y * midrow + x;
-	if (self_needed) pass2_take(u, self, a.pool);
+	if (self_needed) pass2_take(u, self, a.pool, a.pool_cap);
 	const size_t step_up = midrow - nx, step_dn = midrow + nx;     // slot (y-j, class j) = self - j*step_up, ...
 	while (m_up | m_dn) {
 		const double2 *p[4];
@@ -212,7 +217,8 @@ __device__ __forceinline__ void pass2_gather(const Pass2Args &a, RunUnion<CAP> &
 				else if (slot_is_pool(v[i])) {
 					const unsigned long long base = slot_pool_base(v[i]);
 					const unsigned int cnt = slot_pool_count(v[i]);
-					for (unsigned int k = 0; k < cnt; ++k) { const double2 w = __ldg(a.pool + base + k); u.insert(w.x, w.y); }
+					if (base + cnt <= a.pool_cap)
+						for (unsigned int k = 0; k < cnt; ++k) { const double2 w = __ldg(a.pool + base + k); u.insert(w.x, w.y); }
 				}
 			}
 		}
@@ -251,12 +257,12 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 		const uint16_t *f = f_dn + (size_t)(y - up) * nx + x;
 		const double2 *row = a.mid + (size_t)(y - up) * midrow + x;
 		for (int j = up; j >= 1; --j, f += nx, row += midrow)
-			if (flag_has(__ldg(f), j)) pass2_take(u, row + (size_t)j * nx, a.pool);
-		if (flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0)) pass2_take(u, self, a.pool);
+			if (flag_has(__ldg(f), j)) pass2_take(u, row + (size_t)j * nx, a.pool, a.pool_cap);
+		if (flag_has(__ldg(f_up + cc), 0) || flag_has(__ldg(f_dn + cc), 0)) pass2_take(u, self, a.pool, a.pool_cap);
 		f = f_up + (size_t)(y + 1) * nx + x;
 		row = a.mid + (size_t)(y + 1) * midrow + x;
 		for (int j = 1; j <= dn; ++j, f += nx, row += midrow)
-			if (flag_has(__ldg(f), j)) pass2_take(u, row + (size_t)j * nx, a.pool);
+			if (flag_has(__ldg(f), j)) pass2_take(u, row + (size_t)j * nx, a.pool, a.pool_cap);
 	}
 	if (u.overflow) { overflow_item(a.wk, a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);
@@ -614,6 +620,7 @@ __global__ void __launch_bounds__(256) k_compact(Stage st, unsigned long long nl
 		for (uint32_t k = 0; k < n; ++k) dst[k] = st.inl[c * STAGE_INLINE + k];
 	} else {
 		const unsigned long long base = slot_pool_base(st.inl[c * STAGE_INLINE]);
+		if (base + n > st.pool_cap) return;       // the staging pool overflowed (banded call: the host only learns afterwards and repeats)
 		for (uint32_t k = 0; k < n; ++k) dst[k] = st.pool[base + k];
 	}
 }

@@ -825,7 +825,7 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
 	if (y0 < 0 || y1 > m->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "pass 2 row range outside the mid volume");
 	Pass2Args a;
 	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = y0; a.y1 = y1;
-	a.mid = m->slots; a.flags = m->flags; a.tilemask = m->tilemask; a.pool = m->pool;
+	a.mid = m->slots; a.flags = m->flags; a.tilemask = m->tilemask; a.pool = m->pool; a.pool_cap = m->pool_cap;
 	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
@@ -1437,7 +1437,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		mark("pass2 begin", b, sm);
 		Pass2Args a2;
 		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = y0; a2.y1 = y1;
-		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.st = st; a2.redo = rd;
+		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.pool_cap = m->pool_cap; a2.st = st; a2.redo = rd;
 		a2.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
 		k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		a2.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
