@@ -192,3 +192,27 @@ def test_offset2d_transpose_matches_the_reference(reference, tmp_path, seed):
     want = reference.transposed(img)
     assert (got.rows, got.width) == (want.rows, want.width) == (img.width, img.rows)
     assert got.numSegments() > (20 if seed >= 0 else 3) and got.bit_equal(want)
+
+
+def test_svg_reader_survives_malformed_input(tmp_path):
+    """Seeded fragments glued together at random: the executable must finish with exit code 0 or 1 (error reported),
+    never crash or hang."""
+    import random
+    rnd = random.Random(5)
+    frags = ['<svg width="100" height="80">', '<svg viewBox="0 0 10 10" width="50mm" height="40mm">', '<svg>', '</svg>',
+             '<g transform="translate(3,4) rotate(30)">', '</g>', '<path d="M 1 1 L 5 1 L 5 5 Z"/>',
+             '<path d="m1,1 5,0 0,5z M 20 20 h 5 v 5 h -5 z"/>', '<path d="M 1 1 C 2 2 3 3 4 1 S 6 0 7 1 Q 8 8 9 1 T 10 10 Z"/>',
+             '<path d="M"/>', '<path d="L 1 1 2"/>', '<path d="M 1e400 1 L nan 2 Z"/>', '<polygon points="1,1 9,1 5,9"/>',
+             '<polygon points="1,1 9"/>', '<polyline points=""/>', '<rect x="1" y="1" width="30" height="20"/>',
+             '<rect width="-1" height="5"/>', '<circle cx="20" cy="20" r="10"/>', '<ellipse cx="5" cy="5" rx="3" ry="0"/>',
+             '<line x1="0" y1="0" x2="10" y2="10"/>', '<defs>', '</defs>', '<!-- c -->', '<?xml?>', '<svg width="abc">',
+             "<path d='M 1 1 L 2 2", '<g transform="matrix(1 0 0 1)">', '<g transform="scale(0)">',
+             '<path transform="skewX(89.999)" d="M0 0 L 1 1 L 0 1 z"/>', '<text>hi</text>', '<<<>>>']
+    svg, out = tmp_path / "f.svg", tmp_path / "f.dex"
+    for _ in range(40):
+        body = "".join(rnd.choice(frags) for _ in range(rnd.randint(1, 8)))
+        if rnd.random() < 0.7:
+            body = f'<svg width="{rnd.randint(1, 400)}" height="{rnd.randint(1, 400)}">' + body + "</svg>"
+        svg.write_text(body)
+        r = subprocess.run([os.path.join(BIN, "offset2d"), str(svg), "-o", str(out), "-f"], capture_output=True, text=True, timeout=30)
+        assert r.returncode in (0, 1), (r.returncode, body, r.stderr[-200:])
