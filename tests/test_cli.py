@@ -153,3 +153,15 @@ def test_offset2d_pipeline(tmp_path, ctx, oracle):
     assert load(tmp_path / "e.dex").bit_equal(oracle.morph2d(img, "erode", 3.0))
     assert run("offset2d", src, "-o", tmp_path / "n.dex", "-n").returncode == 0
     assert load(tmp_path / "n.dex").bit_equal(oracle.morph2d(img, "negate", 0.0))
+
+
+def test_mesh_reader_rejects_bad_indices(tmp_path):
+    """A facet that names a vertex outside the file is an error, not an out-of-bounds read (host loop and device path
+    share the reader)."""
+    _build()
+    for name, text in (("a.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 99\n"), ("b.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 -7\n"),
+                       ("c.off", "OFF\n3 1 0\n0 0 0\n1 0 0\n0 1 0\n3 0 1 5\n")):
+        mesh = tmp_path / name
+        mesh.write_text(text)
+        r = run("offset3d", mesh, "-n", 8, "-x", "noop")
+        assert r.returncode == 1 and "Invalid input mesh" in r.stderr, (name, r.stderr)

@@ -242,6 +242,9 @@ namespace voroffset3d
 			else if (endswith(f, ".stl")) m = load_stl(filename);
 			else throw std::runtime_error("Invalid input mesh.");
 			if (m.V.empty() || m.F.empty()) throw std::runtime_error("Invalid input mesh.");
+			for (const auto &t : m.F)
+				for (int k = 0; k < 3; ++k)
+					if (t[k] < 0 || (size_t)t[k] >= m.V.size()) throw std::runtime_error("Invalid input mesh (a facet names a vertex that does not exist).");
 			return m;
 		}
 
