@@ -401,6 +401,84 @@ def test_config5_dilation_2048_properties(ctx, oracle):
     assert np.all(co[cs > 0] >= 1)
 
 
+def test_config5_full_grid_matches_the_reference(ctx):
+    """BASELINE config 5 at full size against the reference's OWN result for all 4.19 M columns (tests/golden/
+    full_c5_*.npz: per-column interval counts + per-row checksums of the endpoint bits, generated by
+    tests/golden/make_golden_full.py from oracle/_ref, the reference's sources compiled in place)."""
+    z = util.golden_full("c5_torus_z_n2048_r32")
+    vol = synth.torus_z(2048)
+    util.assert_digest(vol, z, "in", what="synthetic input (generator drift?)")
+    op = morpho.make_operator("ours", ctx)
+    got, _, _ = op.dilation(vol, float(z["radius"]))                       # host-buffer call (banded pipeline)
+    util.assert_digest(got, z, "dilation", what="config 5, vo_morph3d")
+    d = morpho.DeviceVolume.upload(ctx, vol)
+    out, _, _ = op.morph_dev("dilation", d, float(z["radius"]))            # resident path (what bench.py times)
+    util.assert_digest(out.download(), z, "dilation", what="config 5, vo_morph3d_dev")
+    out.free(); d.free()
+
+
+def test_config4_full_grid_matches_the_reference(ctx):
+    """BASELINE config 4 (-n 1024 -p 18 -r 16): all four operations of 'ours' against the reference's own full-size
+    result. Primitives bit for bit, composites with exact topology and endpoint sums within util.COMPOSITE_TOL."""
+    z = util.golden_full("c4_torus_z_n1024_p18_r16")
+    vol = synth.torus_z(1024, padding=18)
+    util.assert_digest(vol, z, "in", what="synthetic input (generator drift?)")
+    op = morpho.make_operator("ours", ctx)
+    for name in ("dilation", "erosion", "opening", "closing"):
+        got, _, _ = morpho.apply_operation(op, name, vol, float(z["radius"]))
+        util.assert_digest(got, z, name, exact=name in ("dilation", "erosion"), what="config 4")
+
+
+LARGE_R = [(64.5, 44, 36), (100.0, 40, 33), (255.0, 37, 30), (256.0, 37, 30), (300.25, 30, 28)]
+
+
+@pytest.mark.parametrize("radius,nx,ny", LARGE_R, ids=[f"R{r:g}" for r, _, _ in LARGE_R])
+def test_large_radii(ctx, oracle, radius, nx, ny):
+    """floor(R) >= 64 takes the one-thread-per-slot pass 1 and the general pass 2; floor(R) + 1 >= 256 no longer fits the
+    8-bit class-window bound (kernels.cuh: FLAG_ALL). Both methods, dilation and erosion bit for bit against the oracle."""
+    vol = synth.random_volume(nx, ny, kmax=3, padding=2, seed=31, zrange=900.0)
+    for method in ("ours", "brute_force"):
+        op = morpho.make_operator(method, ctx)
+        for opn in ("dilation", "erosion"):
+            got, _, _ = morpho.apply_operation(op, opn, vol, radius)
+            util.assert_same(got, oracle.morph3d(vol, opn, radius, method), opn, method, f"R = {radius}")
+    assert got.numSegments() >= 0
+
+
+def test_unsorted_offsets_are_rejected(ctx):
+    """include/voroffset_b200.h promises VO_ERR_ARG for offsets that are not non-decreasing: the plain path checks on the
+    host (vo_lib.cu: upload), the banded host-buffer call on the device (k_thresh, ThreshArgs::bad) - and the context
+    stays usable."""
+    op = morpho.make_operator("ours", ctx)
+    small = synth.random_volume(40, 32, kmax=4, padding=2, seed=3)
+    big = synth.torus_z(1536)
+    for vol, c in ((small, small.nx * 5 + 7), (big, big.nx * 700 + 801), (big, big.nx * 192 + 3)):
+        good, _, _ = op.dilation(vol, 20.0 if vol is big else 3.0)
+        off = vol.off.copy()
+        nz = np.nonzero(np.diff(off.astype(np.int64)) > 0)[0]
+        k = int(nz[np.searchsorted(nz, c)])
+        off[k + 1] = off[k] - 1 if off[k] > 0 else off[k + 2] + 5            # decreasing inside a band / a row
+        bad = CompressedVolume(vol.nx, vol.ny, off, vol.spans)
+        with pytest.raises(_lib.VoroffsetError) as e:
+            op.dilation(bad, 20.0 if vol is big else 3.0)
+        assert e.value.code == 1 and "non-decreasing" in str(e.value)
+        again, _, _ = op.dilation(vol, 20.0 if vol is big else 3.0)
+        assert again.bit_equal(good)
+
+
+def test_2d_dilate_with_effective_radius_beyond_4096(ctx, oracle):
+    """dilate(r) sweeps with R = r * rows (DoubleCompressedImage.cpp:685-686): r = 2.5 on 2048 rows is R = 5120."""
+    img = synth.star_image(2048, 256, 12)
+    d = image2d.DoubleCompressedImage.from_image(img, ctx)
+    d.dilate(2.5)
+    assert d.bit_equal(oracle.morph2d(img, "dilate", 2.5))
+    small = synth.random_image(60, 90, kmax=4, seed=8)
+    for op, r in (("dilate", 80.0), ("erode", 70.5), ("erode", 5000.0)):
+        d = image2d.DoubleCompressedImage.from_image(small, ctx)
+        getattr(d, op)(r)
+        assert d.bit_equal(oracle.morph2d(small, op, r)), (op, r)
+
+
 def _rows(vol, y0, y1):
     c0, c1 = y0 * vol.nx, y1 * vol.nx
     off = vol.off[c0:c1 + 1].astype(np.int64)

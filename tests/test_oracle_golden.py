@@ -37,3 +37,21 @@ def test_oracle_from_image_matches_the_reference_fixture(oracle):
     got = oracle.from_image(int(z["w"]), int(z["h"]), curves)
     assert got.off.tolist() == z["img_off"].tolist() and int(got.off[-1]) > 100
     assert (got.spans.view("u8") == z["img_spans"].view("u8")).all()
+
+
+def test_oracle_matches_the_reference_at_config4_size(oracle):
+    """Full-size pin: the oracle's dilation of BASELINE config 4 (1060 x 1060 columns, R = 16) against the digest of the
+    reference's own result (tests/golden/full_c4_*.npz, written by tests/golden/make_golden_full.py from oracle/_ref);
+    also catches a drifting input generator. ~10 s with 8 threads."""
+    from voroffset_b200 import synth
+    z = util.golden_full("c4_torus_z_n1024_p18_r16")
+    vol = synth.torus_z(1024, padding=18)
+    util.assert_digest(vol, z, "in", what="synthetic input")
+    util.assert_digest(oracle.morph3d(vol, "dilation", float(z["radius"]), "ours"), z, "dilation", what="oracle vs reference digest")
+
+
+def test_full_size_inputs_are_reproducible():
+    from voroffset_b200 import synth
+    z = util.golden_full("c5_torus_z_n2048_r32")
+    util.assert_digest(synth.torus_z(2048), z, "in", what="synthetic input")
+    assert int(z["dilation__nseg"]) == 2790447

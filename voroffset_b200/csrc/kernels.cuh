@@ -169,8 +169,10 @@ struct Pass2Args {
 	Work wk;
 };
 
-// class window flag (lo | hi << 8): is class j needed?
-__device__ __forceinline__ bool flag_has(uint16_t w, int j) { return (int)(w & 0xffu) <= j && j < (int)(w >> 8); }
+// class window flag (lo | hi << 8): is class j needed? FLAG_ALL = every class (written by the one-thread-per-slot pass 1
+// when floor(R) + 1 does not fit the 8-bit window bound; lo = hi = 255 never occurs as a window, empty ones are 0).
+constexpr uint16_t FLAG_ALL = 0xFFFFu;
+__device__ __forceinline__ bool flag_has(uint16_t w, int j) { return w == FLAG_ALL || ((int)(w & 0xffu) <= j && j < (int)(w >> 8)); }
 
 template <int CAP>
 __device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot, const double2 *pool, unsigned long long pool_cap)

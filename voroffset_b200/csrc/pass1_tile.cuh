@@ -136,7 +136,18 @@ struct ThreshArgs {
 	int tiles_xw = 0;                    //   (surviving pairs weighted by their classes; only the ORDER of the tiles uses it)
 	unsigned long long *zero_bank = nullptr;   // optional: the tile lists and cursors ([3] [5] [6] [7] [10]) of the launch set that
 	                                           //   follows on this stream are zeroed here instead of by three memsets of their own
+	// optional (the banded host-buffer call, whose input nobody has validated yet): offsets that are not
+	// non-decreasing or point beyond `nspans` raise *bad and are read as empty columns; the tile kernel of the band
+	// then does nothing and the host reports VO_ERR_ARG
+	unsigned int *bad = nullptr;
+	uint32_t nspans = 0;
 };
+
+// offsets of one column as read from untrusted input (ThreshArgs::bad): an invalid pair becomes an empty column
+__device__ __forceinline__ void thresh_guard(const ThreshArgs &a, uint32_t &q0, uint32_t &q1)
+{
+	if (a.bad && (q1 < q0 || q1 > a.nspans)) { *a.bad = 1u; q0 = q1 = 0; }
+}
 
 __device__ __forceinline__ void thresh_zero_bank(const ThreshArgs &a)
 {
@@ -156,16 +167,16 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	const bool in_range = c < a.c_end;
 	if (!a.est && !in_range) return;
 	uint32_t o0 = 0, o1 = 0;
-	if (in_range) { o0 = __ldg(a.off + c); o1 = __ldg(a.off + c + 1); }
+	if (in_range) { o0 = __ldg(a.off + c); o1 = __ldg(a.off + c + 1); thresh_guard(a, o0, o1); }
 	if (!a.est && o0 == o1) return;
 	const int J = a.J, JP = J + 1;
 	const int x = in_range ? (int)(c % (unsigned)a.nx) : 0, y = in_range ? (int)(c / (unsigned)a.nx) : 0;
 	uint32_t l0 = 0, l1 = 0, r0 = 0, r1 = 0, u0 = 0, u1 = 0, d0 = 0, d1 = 0;
 	if (o0 != o1) {
-		if (x > 0) { l0 = __ldg(a.off + c - 1); l1 = o0; }
-		if (x < a.nx - 1) { r0 = o1; r1 = __ldg(a.off + c + 2); }
-		if (y > 0) { u0 = __ldg(a.off + c - a.nx); u1 = __ldg(a.off + c - a.nx + 1); }
-		if (y < a.ny - 1) { d0 = __ldg(a.off + c + a.nx); d1 = __ldg(a.off + c + a.nx + 1); }
+		if (x > 0) { l0 = __ldg(a.off + c - 1); l1 = o0; thresh_guard(a, l0, l1); }
+		if (x < a.nx - 1) { r0 = o1; r1 = __ldg(a.off + c + 2); thresh_guard(a, r0, r1); }
+		if (y > 0) { u0 = __ldg(a.off + c - a.nx); u1 = __ldg(a.off + c - a.nx + 1); thresh_guard(a, u0, u1); }
+		if (y < a.ny - 1) { d0 = __ldg(a.off + c + a.nx); d1 = __ldg(a.off + c + a.nx + 1); thresh_guard(a, d0, d1); }
 	}
 	unsigned int cost_l = 0, cost_s = 0, cost_r = 0;     // pairs of this column with outputs in the tile on the left / its own / on the right
 	const int xi = x & (P1_W - 1);
@@ -245,7 +256,7 @@ __global__ void __launch_bounds__(256) k_thresh_quad(ThreshArgs a)
 	const bool in_range = c < a.c_end;
 	if (!a.est && !in_range) return;
 	uint32_t o0 = 0, o1 = 0;
-	if (in_range) { o0 = __ldg(a.off + c); o1 = __ldg(a.off + c + 1); }
+	if (in_range) { o0 = __ldg(a.off + c); o1 = __ldg(a.off + c + 1); thresh_guard(a, o0, o1); }
 	if (!a.est && o0 == o1) return;
 	const int J = a.J, JP = J + 1;
 	const int x = in_range ? (int)(c % (unsigned)a.nx) : 0, y = in_range ? (int)(c / (unsigned)a.nx) : 0;
@@ -255,6 +266,7 @@ __global__ void __launch_bounds__(256) k_thresh_quad(ThreshArgs a)
 		else if (dir == 1) { if (x < a.nx - 1) { q0 = o1; q1 = __ldg(a.off + c + 2); } }
 		else if (dir == 2) { if (y > 0) { q0 = __ldg(a.off + c - a.nx); q1 = __ldg(a.off + c - a.nx + 1); } }
 		else { if (y < a.ny - 1) { q0 = __ldg(a.off + c + a.nx); q1 = __ldg(a.off + c + a.nx + 1); } }
+		thresh_guard(a, q0, q1);
 	}
 	unsigned int cost_l = 0, cost_s = 0, cost_r = 0;     // pairs of this column with outputs in the tile on the left / its own / on the right
 	const int xi = x & (P1_W - 1);
@@ -384,6 +396,8 @@ struct Pass1TileArgs {
 	unsigned long long *cursor;
 	unsigned long long pool_cap;
 	uint32_t *ovf;          // [CTAs * warps][P1_OVF][P1_W]: survivor entries beyond the shared-memory lists
+	const unsigned int *bad = nullptr;   // optional: raised by k_thresh when the (untrusted) offsets of the launch set's rows are
+	                                     //   invalid - the launch then does nothing (ThreshArgs::bad)
 	unsigned long long *dbg;   // development aid (NULL normally): per tile {cycles, candidates, survivor entries, cycles of phase 1}
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
 	// Device-side dispatch (no host round trip between the launches). Every launch is one resident wave of CTAs
@@ -897,6 +911,12 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const unsigned int n = LIST ? *a.tiles_count : a.ntiles;
 	if (n == 0) return;
+	if (a.bad) {                                            // invalid input offsets (banded host-buffer call): nothing is safe to read
+		__shared__ unsigned int s_bad;                      // (one read per CTA: another band's k_thresh may raise the flag meanwhile)
+		if (threadIdx.x == 0) s_bad = *a.bad;
+		__syncthreads();
+		if (s_bad) return;
+	}
 	const int J = a.J, JP = J + 1, SEG = P1_W + 2 * J, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned int FULL = 0xffffffffu;
 	const TableSmem tb(smem_raw, J);

@@ -369,6 +369,7 @@ struct RedoBuf {
 
 constexpr int NCTR = 16;  // pass 1: [0] mid-pool cursor [2] redo count [3] big-tile count [4] redo failures [5] multi-tile count
                           //         [6] [7] list cursors [10] tile cursor of the first launch; staged gathers (pass 2, ...): [1] stage-pool cursor [8] redo count [9] failures
+                          //         [11] invalid input offsets seen by k_thresh (banded host-buffer call)
 
 int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 {
@@ -785,7 +786,8 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			ctx->kev_valid[0] = true;
 		} else if (nslots) {
 			// every class of every column is computed: all class windows = [0, J + 1)
-			k_fill16<<<blocks_for(2 * ncols, 256), 256, 0, ctx->stream>>>(m->flags, 2 * ncols, (uint16_t)((t.J + 1) << 8));
+			// (an 8-bit window bound only reaches class 254: larger radii get the "every class" sentinel)
+			k_fill16<<<blocks_for(2 * ncols, 256), 256, 0, ctx->stream>>>(m->flags, 2 * ncols, t.J + 1 <= 255 ? (uint16_t)((t.J + 1) << 8) : FLAG_ALL);
 			cudaMemsetAsync(m->tilemask, 0xFF, nmask * sizeof(unsigned long long), ctx->stream);
 			ctx->launches++;
 			cudaEventRecord(ctx->kev[0], ctx->stream);
@@ -1003,8 +1005,11 @@ int morph3d_dev(vo_ctx *ctx, int op, int method, const vo_dvol *in, double zmin,
 // vor2d: rows live in a vo_dvol with nx = rows, ny = 1
 int dilate2d(vo_ctx *ctx, const vo_dvol *in, int width, double R, int complement, vo_dvol **out)
 {
-	VO_TRY(check_radius(ctx, R));
-	const int J = (int)std::floor(R);
+	// (R = r * rows for a dilation, DoubleCompressedImage.cpp:685-686: easily thousands of rows. Only rows of the image -
+	// and, for the erosion sweep, the two sentinel rows next to it - contribute: the table ends there, the radius itself
+	// is not limited like the 3D one)
+	if (!(R >= 0.0) || !(R < 1.0e9)) return fail(ctx, VO_ERR_ARG, "radius must be in [0, 1e9) rows");
+	const int J = (int)std::min<double>(std::floor(R), (double)in->nx + 1.0);
 	std::vector<double> h2((size_t)J + 1);
 	for (int di = 0; di <= J; ++di) {
 		const double d = (double)di;
@@ -1100,6 +1105,15 @@ int xor_dev(vo_ctx *ctx, const vo_dvol *A, const vo_dvol *B, double zmin, double
 	return VO_OK;
 }
 
+// CSR offsets must be non-decreasing (every kernel indexes spans[] with them). Branch-free so that it vectorises:
+// ~1.5 ms for the 4.2 M columns of a 2048^2 grid, hidden behind the upload it guards.
+bool offsets_sorted(const uint32_t *off, unsigned long long n)
+{
+	uint32_t bad = 0;
+	for (unsigned long long i = 0; i < n; ++i) bad |= (uint32_t)(off[i] > off[i + 1]);
+	return bad == 0;
+}
+
 int upload(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans, vo_dvol **out)
 {
 	VO_TRY(check_dims(ctx, nx, ny));
@@ -1113,9 +1127,16 @@ int upload(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans
 	int rc = dalloc(ctx, &v->spans, m);
 	if (rc) { free_dvol(ctx, v); return rc; }
 	v->nspans = m;
+	// (the copies only need off[n]: the check below runs on the host while they are in flight, and nothing is
+	// launched on the volume before it has passed)
 	cudaError_t e = cudaMemcpyAsync(v->off, off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
 	if (e == cudaSuccess && m) e = cudaMemcpyAsync(v->spans, spans, m * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream);
 	if (e != cudaSuccess) { free_dvol(ctx, v); cudaGetLastError(); return fail(ctx, VO_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e)); }
+	if (!offsets_sorted(off, n)) {
+		cudaStreamSynchronize(ctx->stream);
+		free_dvol(ctx, v);
+		return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
+	}
 	*out = v;
 	return VO_OK;
 }
@@ -1223,6 +1244,18 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	for (int b = 0; b < nb; ++b) BH2 = std::max(BH2, ys2[b + 1] - ys2[b]);
 	if (nb < 3 || ncols * (unsigned long long)(J + 1) < (48ull << 20) || !TilePlan::fits(J, k_in)) return PIPE_NA;
 	if (nspans && !spans) return PIPE_NA;
+	// The offsets have not been validated (upload() does that for the plain path): the band boundaries are checked here, so
+	// that every copy below stays inside the buffers; everything in between is checked on the device by k_thresh, which
+	// reads every offset anyway (ThreshArgs::bad) - a host loop over 4 M offsets would cost more than a band's upload.
+	for (int b = 0; b <= nb; ++b) {
+		const uint32_t o = off[(unsigned long long)ys[b] * nx];
+		if (o > nspans || (b > 0 && o < off[(unsigned long long)ys[b - 1] * nx])) return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
+	}
+	for (int b = 1; b < nb; ++b) {                           // (a band's upload ends one row below it)
+		const unsigned long long c = (unsigned long long)std::min(ny, ys[b] + 1) * nx;
+		if (off[c] > nspans || off[c] < off[(unsigned long long)ys[b] * nx] || off[c] > off[(unsigned long long)ys[b + 1] * nx])
+			return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
+	}
 
 	TableCache *tc = nullptr;
 	VO_TRY(get_tables(ctx, R, true, &tc));
@@ -1359,10 +1392,12 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	ta.nx = nx; ta.ny = ny; ta.J = J; ta.off = in->off; ta.spans = in->spans;
 	ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
 	ta.clip_lo = -std::numeric_limits<double>::infinity(); ta.clip_hi = std::numeric_limits<double>::infinity();
+	ta.bad = reinterpret_cast<unsigned int *>(ctx->d_ctr + 11); ta.nspans = (uint32_t)nspans;
 	Pass1TileArgs g;
 	g.nx = nx; g.ny = ny;
 	g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
 	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap;
+	g.bad = ta.bad;
 	Pass1Args a1;
 	a1.nx = nx; a1.ny = ny; a1.J = J; a1.off = in->off; a1.spans = in->spans; a1.H = dt.H; a1.reach = dt.reach;
 	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap;
@@ -1506,6 +1541,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaGetLastError();
 	}
 	if (rc == VO_OK && cudaGetLastError() != cudaSuccess) rc = PIPE_NA;
+	if (rc == VO_OK && h[11]) { drop_host(); return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing"); }
 	if (rc == VO_OK && (h[0] > m->pool_cap || h[4])) {
 		ctx->pool_hint = std::max<unsigned long long>(ctx->pool_hint, h[0] + h[0] / 4);
 		rc = PIPE_NA;                                           // let the plain path deal with it (it regrows / reports)
@@ -2007,10 +2043,12 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 		if (std::strcmp(value, "off") == 0) { ctx->tile_order = false; return VO_OK; }
 		if (std::strcmp(value, "on") == 0) { ctx->tile_order = true; return VO_OK; }
 	}
-	if (std::strcmp(key, "tile_debug") == 0) {           // development aid: scripts/tile_costs.py
+#ifdef VO_TILE_DEBUG                                     // development builds only (scripts/tile_costs.py): a raw device pointer
+	if (std::strcmp(key, "tile_debug") == 0) {
 		ctx->dbg_tiles = reinterpret_cast<unsigned long long *>(std::strtoull(value, nullptr, 0));
 		return VO_OK;
 	}
+#endif
 	if (std::strcmp(key, "pass1") == 0) {
 		if (std::strcmp(value, "simple") == 0) { ctx->force_simple_pass1 = true; ctx->force_tile_pass1 = false; return VO_OK; }
 		if (std::strcmp(value, "tile") == 0) { ctx->force_simple_pass1 = false; ctx->force_tile_pass1 = true; return VO_OK; }
