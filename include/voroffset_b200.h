@@ -16,6 +16,15 @@
  * Threading: a vo_ctx owns one CUDA device, one stream and its scratch memory; it is not
  * thread-safe. Use one context per calling thread / per GPU.
  *
+ * Limits the reference does not have (all reported, never silent):
+ *   - CSR offsets are uint32: at most 2^32 - 9 columns and 2^32 - 1 intervals per volume (VO_ERR_OVERFLOW beyond);
+ *   - 3D radii must be in [0, 4096) dexels (VO_ERR_ARG); the 2D radius is only bounded by 1e9 rows;
+ *   - while a column's result is being gathered it may pass through at most 512 disjoint intervals at a time
+ *     (the running union of the redo launch, csrc/kernels.cuh: CAP_BIG); a column that needs more fails the whole call
+ *     with VO_ERR_OVERFLOW. Lists of up to 32 intervals take the fast path;
+ *   - host CSR inputs are validated (off[0] = 0, offsets non-decreasing: VO_ERR_ARG); volumes that are ALREADY in device
+ *     memory (vo_dvol_from_device, the vo_*_dev entry points) are trusted.
+ *
  * Errors: every function returns VO_OK (0) or a VO_ERR_* code; vo_last_error(ctx) gives the text.
  * The C++ adapters (voroffset_b200/cpp) turn a non-zero code into std::runtime_error, which is what
  * the reference's vor_assert does (src/vor3d/Common.cpp:7-17).
@@ -68,7 +77,9 @@ void       *vo_stream(const vo_ctx *ctx);
 /* Number of kernel launches issued by this context so far (bench.py's gpu_launches).                 */
 uint64_t    vo_launch_count(const vo_ctx *ctx);
 
-/* Tuning knobs (none changes a result bit). "pass1" = "auto" (default: tile kernel when it fits) | "tile" | "simple"
+/* Tuning knobs (none changes a result bit). "scan" = "fused" (default: staged lists -> CSR and both complements in one
+ * single-pass look-back kernel each) | "classic"; "tile_dbuf" = "auto" | "on" | "off" (double-buffered candidate staging
+ * of the pass-1 tile kernel). "pass1" = "auto" (default: tile kernel when it fits) | "tile" | "simple"
  * (one thread per (x, y, class); kept as the general fallback and as an independent implementation for the tests);
  * "tile_order" = "on" | "off" (expensive pass-1 tiles first); "tile_ctas" = 1..8 (CTAs per SM of the tile kernel);
  * "block_cache" = "on" | "off" (released scratch blocks >= 1 MiB kept whole for the next call);
@@ -172,6 +183,41 @@ int  vo_slab_finish(vo_ctx *ctx, vo_slab *slab, const void *d_off_prev, const vo
                     const void *d_off_next, const void *d_spans_next, uint64_t n_next,
                     vo_dvol **out, double *ms_pass1, double *ms_pass2);
 void vo_slab_abort(vo_ctx *ctx, vo_slab *slab);
+
+/* ---- multi-GPU: one grid cut into y-slabs over several B200s, halo rows exchanged with NCCL ------------------------ */
+/* Replaces the same calls as vo_morph3d (Voronoi.h:18,29; offset3d.cpp:104-136) for a grid sharded the way the
+ * reference's dormant TBB regions cut it (VoronoiVorPower.cpp:41-63,70-92: tasks own disjoint slices). Slab g of G owns
+ * the rows [g ny/G, (g+1) ny/G) (remainder to the first slabs); before pass 1 every slab receives the floor(radius)
+ * boundary rows of its two neighbours (ncclSend / ncclRecv, csrc/vo_mg.cuh); erosion keeps the reference's one-line solid
+ * border (Voronoi.cpp:18-55) on the two edge slabs. All four operations and both methods; results are bit-identical to
+ * the single-GPU call. libnccl.so.2 is loaded at run time (the copy PyTorch has loaded, if any).
+ *   vo_mg_create        one process drives n_dev GPUs (device_ids NULL: 0 .. n_dev-1), one host thread per GPU while an
+ *                       operator runs. n_dev = 1 works without NCCL.
+ *   vo_mg_unique_id / vo_mg_create_rank   one process per GPU (torchrun): rank 0 makes the 128-byte id, every rank
+ *                       passes the same bytes; the group then has ONE local rank.                                        */
+typedef struct vo_mg vo_mg;
+int         vo_mg_create(const int *device_ids, int n_dev, vo_mg **out);
+int         vo_mg_unique_id(void *id128);
+int         vo_mg_create_rank(int device, int rank, int world, const void *id128, vo_mg **out);
+void        vo_mg_destroy(vo_mg *mg);
+int         vo_mg_world(const vo_mg *mg);                 /* slabs = GPUs of the whole group                              */
+int         vo_mg_local_count(const vo_mg *mg);           /* ranks driven by this process                                 */
+int         vo_mg_rank(const vo_mg *mg, int local);       /* global rank of a local one                                   */
+vo_ctx     *vo_mg_ctx(vo_mg *mg, int local);              /* its context (upload / download / free of its slab volumes)   */
+const char *vo_mg_last_error(const vo_mg *mg);
+/* Host buffers in, host buffers out (single-process groups): the drop-in call of offset3d --gpus N.                    */
+int vo_mg_morph3d(vo_mg *mg, int op, int method, int nx, int ny, double zmin, double zmax,
+                  const uint32_t *off, const double *spans, double radius,
+                  uint32_t **out_off, double **out_spans, uint64_t *out_nspans, double *ms_pass1, double *ms_pass2);
+/* Resident slabs: in[i] / out[i] belong to local rank i (uploaded through vo_mg_ctx(mg, i)); every slab but the thinnest
+ * grid needs at least floor(radius) rows. Collective: every process of the group calls it with the same op / radius.  */
+int vo_mg_morph3d_dev(vo_mg *mg, int op, int method, const vo_dvol *const *in, double zmin, double zmax, double radius,
+                      vo_dvol **out, double *ms_pass1, double *ms_pass2);
+/* Halo traffic of the last operator on a local rank: device time of the NCCL groups, host time blocked until the halos
+ * had landed (what the step stalls for beyond the overlapped pass 1), bytes sent, NCCL groups, primitives that took the
+ * overlapped slab step / the concatenate-then-dilate path.                                                             */
+int vo_mg_stats(const vo_mg *mg, int local, double *halo_ms, double *halo_wait_ms, uint64_t *halo_bytes,
+                int *messages, int *overlapped, int *plain);
 
 /* ---- the step before the path: mesh -> dexel volume --------------------------------------------- */
 /* Replaces the ray-marching loop of vor3d::create_dexels, compute_sign (src/vor3d/Dexelize.cpp:166-225, with

@@ -35,7 +35,15 @@ namespace
 namespace voroffset3d
 {
 	VoronoiMorphoB200::VoronoiMorphoB200(int method, int device) : m_ctx(make_ctx(device)), m_method(method) {}
-	VoronoiMorphoB200::~VoronoiMorphoB200() { vo_destroy(m_ctx); }
+	VoronoiMorphoB200::VoronoiMorphoB200(int method, int first_device, int n_gpus) : m_ctx(nullptr), m_method(method)
+	{
+		if (n_gpus <= 1) { m_ctx = make_ctx(first_device); return; }
+		std::vector<int> devs(n_gpus);
+		for (int i = 0; i < n_gpus; ++i) devs[i] = first_device + i;
+		if (vo_mg_create(devs.data(), n_gpus, &m_mg) != VO_OK)
+			throw std::runtime_error("voroffset_b200: cannot create the multi-GPU group (CUDA devices or libnccl.so.2 missing; there is no CPU fallback)");
+	}
+	VoronoiMorphoB200::~VoronoiMorphoB200() { if (m_mg) vo_mg_destroy(m_mg); else vo_destroy(m_ctx); }
 
 	void VoronoiMorphoB200::run(int op, CompressedVolume &input, CompressedVolume &result, double radius, double &time_1, double &time_2)
 	{
@@ -51,8 +59,12 @@ namespace voroffset3d
 		uint32_t *o_off = nullptr;
 		double *o_spans = nullptr;
 		uint64_t n = 0;
-		check(m_ctx, vo_morph3d(m_ctx, op, m_method, nx, ny, zmin, zmax, off.data(), spans.data(), radius,
-		                        &o_off, &o_spans, &n, &time_1, &time_2));
+		if (m_mg) {      // y-slabs over several GPUs, NCCL halo exchange inside the library
+			if (vo_mg_morph3d(m_mg, op, m_method, nx, ny, zmin, zmax, off.data(), spans.data(), radius, &o_off, &o_spans, &n, &time_1, &time_2) != VO_OK)
+				throw std::runtime_error(std::string("voroffset_b200: ") + vo_mg_last_error(m_mg));
+		} else
+			check(m_ctx, vo_morph3d(m_ctx, op, m_method, nx, ny, zmin, zmax, off.data(), spans.data(), radius,
+			                        &o_off, &o_spans, &n, &time_1, &time_2));
 		// result.reset(...) exactly like VoronoiVorPower.cpp:37 / VoronoiBruteForce.cpp:20
 		result.reset(input.origin(), input.extent(), input.spacing(), input.padding(), nx, ny);
 		for (int y = 0; y < ny; ++y)

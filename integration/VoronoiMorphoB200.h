@@ -18,6 +18,8 @@ namespace voroffset3d
 	{
 	public:
 		explicit VoronoiMorphoB200(int method, int device = 0);
+		// n_gpus > 1: the grid is cut into y-slabs over the GPUs first_device .. first_device + n_gpus - 1 (vo_mg_*)
+		VoronoiMorphoB200(int method, int first_device, int n_gpus);
 		~VoronoiMorphoB200() override;
 		VoronoiMorphoB200(const VoronoiMorphoB200 &) = delete;
 		VoronoiMorphoB200 &operator=(const VoronoiMorphoB200 &) = delete;
@@ -34,6 +36,7 @@ namespace voroffset3d
 	private:
 		void run(int op, CompressedVolume &input, CompressedVolume &result, double radius, double &time_1, double &time_2);
 		vo_ctx *m_ctx;
+		vo_mg *m_mg = nullptr;
 		int m_method;
 	};
 
@@ -42,11 +45,13 @@ namespace voroffset3d
 	{
 	public:
 		explicit VoronoiMorphoVorPowerB200(int device = 0) : VoronoiMorphoB200(VO_METHOD_OURS, device) {}
+		VoronoiMorphoVorPowerB200(int first_device, int n_gpus) : VoronoiMorphoB200(VO_METHOD_OURS, first_device, n_gpus) {}
 	};
 	class VoronoiMorphoBruteForceB200 : public VoronoiMorphoB200
 	{
 	public:
 		explicit VoronoiMorphoBruteForceB200(int device = 0) : VoronoiMorphoB200(VO_METHOD_BRUTE_FORCE, device) {}
+		VoronoiMorphoBruteForceB200(int first_device, int n_gpus) : VoronoiMorphoB200(VO_METHOD_BRUTE_FORCE, first_device, n_gpus) {}
 	};
 }
 

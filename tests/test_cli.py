@@ -39,7 +39,7 @@ def test_help_and_flag_validation():
     _build()
     r = run("offset3d", "--help")
     assert r.returncode == 0
-    for flag in ("-i", "-o", "-j", "-d", "-n", "-p", "-t", "-r", "-m", "-x", "-f", "-u"):   # offset3d.cpp:38-51
+    for flag in ("-i", "-o", "-j", "-d", "-n", "-p", "-t", "-r", "-m", "-x", "-f", "-u", "--gpus"):   # offset3d.cpp:38-51 (+ ours)
         assert flag in r.stderr
     assert run("offset3d").returncode == 1
     assert run("offset3d", "/nonexistent.obj").returncode == 1
@@ -99,8 +99,11 @@ def test_no_cpu_fallback_in_cli(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("method", ["ours", "brute_force"])
-def test_offset3d_pipeline_matches_python_mirror(tmp_path, ctx, method):
+def test_offset3d_pipeline_matches_the_oracle(tmp_path, ctx, oracle, method):
+    """The executable end to end (mesh -> device dexeliser -> operator -> .vol) against the ORACLE run on the dexelised
+    input the same executable wrote with -x noop (host loop), and against the Python mirror of the operator interface."""
     _build()
+    import util
     from voroffset_b200 import morpho
     from voroffset_b200.volume import CompressedVolume
     mesh = tmp_path / "torus.obj"
@@ -115,6 +118,7 @@ def test_offset3d_pipeline_matches_python_mirror(tmp_path, ctx, method):
         assert r.returncode == 0, r.stderr
         with open(out) as f:
             got = CompressedVolume.load(f)
+        util.assert_same(got, oracle.morph3d(vin, operation, 5.5, method), operation, method, "offset3d vs oracle")
         want, _, _ = morpho.apply_operation(op, operation, vin, 5.5)
         if operation in ("closing", "opening"):
             # the CLI composes two calls through the host (offset3d.cpp:124-133), the mirror composes on the device

@@ -170,3 +170,73 @@ def test_offset3d_dexelises_on_the_device(ctx, oracle, tmp_path):
     grid = grid_for(V, None, 6, 64)
     want, _, _ = morpho.make_operator("ours", ctx).dilation(oracle.dexelize(V, F, grid), 5.0)
     assert got.bit_equal(want)
+
+
+# ---- known answers (exact rational geometry, tests/golden/make_dexel_known.py) -------------------------------------
+def _known_cases():
+    z = np.load(os.path.join(util.GOLDEN, "dexel_known.npz"))
+    return z, [str(n) for n in z["names"]]
+
+
+def _check_known(z, name, vol):
+    """`vol` (the dexelisation of fixture `name`) against the hand-derived answer: exact crossing counts and heights for
+    every column strictly inside or outside the footprint - also where the centre lies on an edge or a vertex shared by
+    several facets (the simulation-of-simplicity ties of Dexelize.cpp:56-92) - and an even count out of the exact
+    heights on the silhouette."""
+    state, zoff, zs = z[f"{name}__state"], z[f"{name}__zoff"], z[f"{name}__z"]
+    assert vol.nx * vol.ny == state.size
+    seen = {-1: 0, 0: 0, 1: 0}
+    for c in range(state.size):
+        got = vol.spans[int(vol.off[c]):int(vol.off[c + 1])].reshape(-1)
+        want = zs[zoff[c]:zoff[c + 1]]
+        seen[int(state[c])] += 1
+        if state[c] < 0:
+            assert got.size == 0, (name, c, "crossings outside the footprint")
+        elif state[c] > 0:
+            assert got.size == want.size and np.allclose(got, want, rtol=0, atol=1e-12), (name, c, got, want)
+        else:
+            assert got.size % 2 == 0 and all(np.abs(want - g).min() <= 1e-12 for g in got), (name, c, got, want)
+    assert seen[1] > 0 and seen[0] > 0
+
+
+def _known_grid(z, name):
+    ox, oy, sp, nx, ny = z[f"{name}__grid"]
+    return CompressedVolume(int(nx), int(ny), np.zeros(int(nx) * int(ny) + 1, dtype=np.uint32), np.zeros((0, 2)),
+                            (float(ox), float(oy), 0.0), (float(nx * sp), float(ny * sp), 1.0), float(sp), 0)
+
+
+@pytest.mark.parametrize("name", _known_cases()[1])
+def test_oracle_dexeliser_known_answers(oracle, name):
+    z, _ = _known_cases()
+    _check_known(z, name, oracle.dexelize(z[f"{name}__V"], z[f"{name}__F"], _known_grid(z, name)))
+
+
+def test_host_loop_known_answers(tmp_path):
+    """The host loop of the re-hosted offset3d (-x noop) on a known-answer mesh: the grid that create_dexels derives
+    from the bounding box (Dexelize.cpp:255-272) puts the box's own faces on the silhouette, so only the interior and
+    the diagonals are pinned here."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "voroffset_b200", "cpp"), "-s"], check=True)
+    z, _ = _known_cases()
+    V, F = z["nested_boxes__V"], z["nested_boxes__F"]
+    mesh, out = tmp_path / "m.obj", tmp_path / "m.vol"
+    save_obj(str(mesh), V, F)
+    r = subprocess.run([os.path.join(BIN, "offset3d"), str(mesh), str(out), "-d", "0.25", "-n", "-1", "-p", "1", "-x", "noop"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    with open(out) as f:
+        got = CompressedVolume.load(f)
+    cnt = got.counts().reshape(got.ny, got.nx)
+    # outer box 2.5 x 2.5 at spacing 0.25 -> 10 x 10 columns (+1 of padding): two crossings everywhere, four over the inner box
+    assert (got.nx, got.ny) == (12, 12) and cnt[1:11, 1:11].min() >= 1 and cnt.max() == 2
+    assert cnt[0, :].sum() == 0 and cnt[:, 0].sum() == 0 and cnt[11, :].sum() == 0 and cnt[:, 11].sum() == 0
+    assert int((cnt == 2).sum()) in (12, 15, 16, 20)                # inner box 1.0 x 1.25: 4 x 5 columns, its silhouette either way
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", _known_cases()[1])
+def test_device_dexeliser_known_answers(ctx, name):
+    from voroffset_b200.dexelize import dexelize_dev
+    z, _ = _known_cases()
+    grid = _known_grid(z, name)
+    dv, _ = dexelize_dev(ctx, z[f"{name}__V"], z[f"{name}__F"], grid)
+    _check_known(z, name, dv.download(grid))

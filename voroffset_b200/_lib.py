@@ -31,6 +31,8 @@ EXPORTS = [
     "vo_pass1_dev", "vo_pass2_dev", "vo_dmid_free", "vo_dmid_info", "vo_morph2d_dev",
     "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device", "vo_set_option", "vo_dvol_rows_to",
     "vo_slab_begin", "vo_slab_finish", "vo_slab_abort", "vo_dexelize_dev",
+    "vo_mg_create", "vo_mg_unique_id", "vo_mg_create_rank", "vo_mg_destroy", "vo_mg_world", "vo_mg_local_count",
+    "vo_mg_rank", "vo_mg_ctx", "vo_mg_last_error", "vo_mg_morph3d", "vo_mg_morph3d_dev", "vo_mg_stats",
 ]
 
 _lib = None
@@ -99,6 +101,24 @@ def load() -> C.CDLL:
     L.vo_slab_finish.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, C.c_uint64, C.POINTER(_vp), _f64p, _f64p]
     L.vo_slab_abort.argtypes = [_vp, _vp]
     L.vo_slab_abort.restype = None
+    L.vo_mg_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]
+    L.vo_mg_unique_id.argtypes = [_vp]
+    L.vo_mg_create_rank.argtypes = [C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]
+    L.vo_mg_destroy.argtypes = [_vp]
+    L.vo_mg_destroy.restype = None
+    L.vo_mg_world.argtypes = [_vp]
+    L.vo_mg_local_count.argtypes = [_vp]
+    L.vo_mg_rank.argtypes = [_vp, C.c_int]
+    L.vo_mg_ctx.argtypes = [_vp, C.c_int]
+    L.vo_mg_ctx.restype = _vp
+    L.vo_mg_last_error.argtypes = [_vp]
+    L.vo_mg_last_error.restype = C.c_char_p
+    L.vo_mg_morph3d.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp,
+                                C.c_double, C.POINTER(_u32p), C.POINTER(_f64p), C.POINTER(C.c_uint64), _f64p, _f64p]
+    L.vo_mg_morph3d_dev.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.c_double, C.c_double, C.c_double,
+                                    C.POINTER(_vp), _f64p, _f64p]
+    L.vo_mg_stats.argtypes = [_vp, C.c_int, _f64p, _f64p, C.POINTER(C.c_uint64), C.POINTER(C.c_int),
+                              C.POINTER(C.c_int), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -106,8 +126,12 @@ def load() -> C.CDLL:
 class Context:
     """One vo_ctx: one device, one stream. Not thread-safe (include/voroffset_b200.h)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self.lib = load()
+        if _borrowed is not None:               # a context owned by a multi-GPU group (vo_mg_ctx): never destroyed here
+            self.handle, self.device, self._owned = _vp(_borrowed), int(device), False
+            return
+        self._owned = True
         h = _vp()
         rc = self.lib.vo_create(int(device), C.byref(h))
         if rc != VO_OK:
@@ -117,7 +141,8 @@ class Context:
 
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.vo_destroy(self.handle)
+            if getattr(self, "_owned", True):
+                self.lib.vo_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -30,7 +30,8 @@ static int usage(const char *msg)
 	             "  -m,--method {ours,brute_force}\n"
 	             "  -x,--apply {noop,dilation,erosion,closing,opening}\n"
 	             "  -f,--force                  Overwrite output file\n"
-	             "  -u,--radius_in_mm           Radius is given in mm instead\n";
+	             "  -u,--radius_in_mm           Radius is given in mm instead\n"
+	             "  -g,--gpus INT               Number of GPUs (default 1): the grid is cut into y-slabs, halo rows travel with NCCL\n";
 	return msg ? 1 : 0;
 }
 
@@ -39,7 +40,7 @@ int main(int argc, char *argv[])
 	struct {
 		std::string input, output_mesh = "output.obj", output_json = "", method = "ours", operation = "dilation";
 		double radius = 8, dexels_size = 1;
-		int padding = 0, num_dexels = 256;
+		int padding = 0, num_dexels = 256, gpus = 1;
 		unsigned int num_thread = std::max(1u, std::thread::hardware_concurrency());
 		bool force = false, radius_in_mm = false;
 	} args;
@@ -61,6 +62,7 @@ int main(int argc, char *argv[])
 		else if (a == "-x" || a == "--apply") args.operation = val("-x");
 		else if (a == "-f" || a == "--force") args.force = true;
 		else if (a == "-u" || a == "--radius_in_mm") args.radius_in_mm = true;
+		else if (a == "-g" || a == "--gpus") args.gpus = std::stoi(val("-g"));
 		else if (!a.empty() && a[0] == '-') return usage(("unknown option " + a).c_str());
 		else if (positional == 0) { args.input = a; ++positional; }
 		else if (positional == 1) { args.output_mesh = a; ++positional; }
@@ -96,8 +98,8 @@ int main(int argc, char *argv[])
 		// Create offset operator (offset3d.cpp:104-112)
 		std::unique_ptr<vor3d::VoronoiMorpho> op;
 		if (args.operation != "noop") {          // (the GPU context is only needed when something is computed)
-			if (args.method == "ours") op = std::make_unique<vor3d::VoronoiMorphoVorPower>();
-			else op = std::make_unique<vor3d::VoronoiMorphoBruteForce>();
+			if (args.method == "ours") op = std::make_unique<vor3d::VoronoiMorphoVorPower>(0, std::max(1, args.gpus));
+			else op = std::make_unique<vor3d::VoronoiMorphoBruteForce>(0, std::max(1, args.gpus));
 		}
 
 		// Apply operation (offset3d.cpp:116-136)
@@ -132,6 +134,7 @@ int main(int argc, char *argv[])
 				  << "    \"method\": \"" << args.method << "\",\n"
 				  << "    \"model_name\": \"" << args.input << "\",\n"
 				  << "    \"num_dexels\": " << args.num_dexels << ",\n"
+				  << "    \"num_gpus\": " << std::max(1, args.gpus) << ",\n"
 				  << "    \"num_segments\": " << num_segments << ",\n"
 				  << "    \"num_threads\": " << args.num_thread << ",\n"
 				  << "    \"operation\": \"" << args.operation << "\",\n"

@@ -77,7 +77,16 @@ namespace voroffset3d
 
 	// ---- VoronoiMorpho -----------------------------------------------------------------------------
 	VoronoiMorpho::VoronoiMorpho(int method, int device) : m_ctx(make_ctx(device)), m_method(method) {}
-	VoronoiMorpho::~VoronoiMorpho() { vo_destroy(m_ctx); }
+	VoronoiMorpho::VoronoiMorpho(int method, int first_device, int n_gpus) : m_ctx(nullptr), m_method(method)
+	{
+		if (n_gpus <= 1) { m_ctx = make_ctx(first_device); return; }
+		std::vector<int> devs(n_gpus);
+		for (int i = 0; i < n_gpus; ++i) devs[i] = first_device + i;
+		if (vo_mg_create(devs.data(), n_gpus, &m_mg) != VO_OK)
+			throw std::runtime_error("voroffset_b200: cannot create a " + std::to_string(n_gpus) + "-GPU group (CUDA devices or libnccl.so.2 missing; there is no CPU fallback)");
+		m_ctx = vo_mg_ctx(m_mg, 0);      // (owned by the group; used for xor)
+	}
+	VoronoiMorpho::~VoronoiMorpho() { if (m_mg) vo_mg_destroy(m_mg); else vo_destroy(m_ctx); }
 
 	void VoronoiMorpho::run(int op, const CompressedVolume &input, CompressedVolume &result, double radius, double &t1, double &t2)
 	{
@@ -88,8 +97,13 @@ namespace voroffset3d
 		uint32_t *o_off = nullptr;
 		double *o_spans = nullptr;
 		uint64_t n = 0;
-		check(m_ctx, vo_morph3d(m_ctx, op, m_method, nx, ny, input.zmin(), input.zmax(), off.data(), spans.data(), radius,
-		                        &o_off, &o_spans, &n, &t1, &t2));
+		if (m_mg) {
+			const int rc = vo_mg_morph3d(m_mg, op, m_method, nx, ny, input.zmin(), input.zmax(), off.data(), spans.data(), radius,
+			                             &o_off, &o_spans, &n, &t1, &t2);
+			if (rc != VO_OK) throw std::runtime_error(std::string("Assertion failed: ") + vo_mg_last_error(m_mg));
+		} else
+			check(m_ctx, vo_morph3d(m_ctx, op, m_method, nx, ny, input.zmin(), input.zmax(), off.data(), spans.data(), radius,
+			                        &o_off, &o_spans, &n, &t1, &t2));
 		result.reset(input.origin(), input.extent(), input.spacing(), input.padding(), nx, ny);   // VoronoiVorPower.cpp:37
 		result.from_csr(o_off, o_spans);
 		vo_free(o_off);

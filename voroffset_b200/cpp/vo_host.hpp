@@ -103,6 +103,9 @@ namespace voroffset3d
 	{
 	public:
 		explicit VoronoiMorpho(int method, int device = 0);
+		// n_gpus > 1: the grid is cut into y-slabs over the GPUs 0 .. n_gpus-1 (vo_mg_*: NCCL halo exchange inside the
+		// library); every operator below then runs on all of them
+		VoronoiMorpho(int method, int first_device, int n_gpus);
 		virtual ~VoronoiMorpho();
 		VoronoiMorpho(const VoronoiMorpho &) = delete;
 		VoronoiMorpho &operator=(const VoronoiMorpho &) = delete;
@@ -115,10 +118,21 @@ namespace voroffset3d
 	protected:
 		void run(int op, const CompressedVolume &input, CompressedVolume &result, double radius, double &t1, double &t2);
 		vo_ctx *m_ctx;
+		vo_mg *m_mg = nullptr;
 		int m_method;
 	};
-	class VoronoiMorphoVorPower : public VoronoiMorpho { public: explicit VoronoiMorphoVorPower(int device = 0) : VoronoiMorpho(VO_METHOD_OURS, device) {} };
-	class VoronoiMorphoBruteForce : public VoronoiMorpho { public: explicit VoronoiMorphoBruteForce(int device = 0) : VoronoiMorpho(VO_METHOD_BRUTE_FORCE, device) {} };
+	class VoronoiMorphoVorPower : public VoronoiMorpho
+	{
+	public:
+		explicit VoronoiMorphoVorPower(int device = 0) : VoronoiMorpho(VO_METHOD_OURS, device) {}
+		VoronoiMorphoVorPower(int first_device, int n_gpus) : VoronoiMorpho(VO_METHOD_OURS, first_device, n_gpus) {}
+	};
+	class VoronoiMorphoBruteForce : public VoronoiMorpho
+	{
+	public:
+		explicit VoronoiMorphoBruteForce(int device = 0) : VoronoiMorpho(VO_METHOD_BRUTE_FORCE, device) {}
+		VoronoiMorphoBruteForce(int first_device, int n_gpus) : VoronoiMorpho(VO_METHOD_BRUTE_FORCE, first_device, n_gpus) {}
+	};
 
 	// Geogram-free restatement of src/vor3d/Dexelize.cpp (mesh -> dexels, dexels -> hex mesh / points).
 	// device >= 0: the ray-marching loop runs on that GPU (vo_dexelize_dev); device < 0: host loop (offset3d -x noop,

@@ -10,6 +10,7 @@
 //                    reference's exact fp64 operation order, independent of GPU sqrt / FMA behaviour.
 #pragma once
 #include "run_union.cuh"
+#include "scan.cuh"
 
 namespace vo {
 
@@ -484,6 +485,10 @@ __global__ void __launch_bounds__(D2B_THREADS) k_dilate2d_block(Dil2dArgs a)
 	if (i >= a.rows) return;
 	const int nsrc = 2 * a.J + 1;
 	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	if (nsrc > 129) {                                      // more source rows than s_rowbase holds: one-thread-per-row kernel
+		if (tid == 0) { redo_push(a.redo, (unsigned long long)i); a.st.cnt[i] = 0; }
+		return;
+	}
 	// candidates per source row (complement rows have one more seed than intervals; sentinels have one)
 	if (tid == 0) {
 		int tot = 0;
@@ -501,7 +506,7 @@ __global__ void __launch_bounds__(D2B_THREADS) k_dilate2d_block(Dil2dArgs a)
 	}
 	__syncthreads();
 	const int total = s_total;
-	if (total > D2B_MAX || nsrc > 129) {                   // too long for shared memory: one-thread-per-row kernel
+	if (total > D2B_MAX) {                                 // too long for shared memory: one-thread-per-row kernel
 		if (tid == 0) { redo_push(a.redo, (unsigned long long)i); a.st.cnt[i] = 0; }
 		return;
 	}
@@ -627,6 +632,69 @@ __global__ void __launch_bounds__(256) k_compact(Stage st, unsigned long long nl
 	}
 }
 
+// Staged lists -> canonical CSR in ONE launch (scan.cuh: decoupled look-back): offsets of every list, off[nlists] and
+// *total_out = grand total, spans copied where the list ends inside `cap` intervals.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigned long long nlists, uint32_t *__restrict__ off,
+                                                               double2 *__restrict__ spans, unsigned long long cap,
+                                                               unsigned long long *state, unsigned long long *ticket,
+                                                               unsigned long long ticket_base, uint32_t epoch,
+                                                               unsigned long long *total_out)
+{
+	__shared__ uint32_t s_tile;
+	__shared__ unsigned long long s_prefix;
+	if (threadIdx.x == 0) s_tile = (uint32_t)(atomicAdd(ticket, 1ull) - ticket_base);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const unsigned long long base = (unsigned long long)tile * SCAN_TILE + (unsigned long long)threadIdx.x * SCAN_ITEMS;
+	uint32_t c[SCAN_ITEMS];
+	unsigned long long sum = 0;
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		const unsigned long long k = base + i;
+		c[i] = k < nlists ? st.cnt[k] : 0u;
+		sum += c[i];
+	}
+	unsigned long long tot;
+	unsigned long long ex = block_excl_scan(sum, &tot);
+	volatile unsigned long long *vstate = state;
+	if (threadIdx.x == 0) {
+		vstate[tile] = scan_word(tot, epoch, tile == 0 ? SCAN_INCL : SCAN_AGG);
+		if (tile == 0) s_prefix = 0;
+	}
+	if (tile > 0 && threadIdx.x < 32) {
+		const unsigned long long excl = scan_look_back(vstate, tile, epoch);
+		if (threadIdx.x == 0) {
+			vstate[tile] = scan_word(excl + tot, epoch, SCAN_INCL);
+			s_prefix = excl;
+		}
+	}
+	__syncthreads();
+	ex += s_prefix;
+	if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {          // the last ticket is the last tile: its end is the grand total
+		const unsigned long long total = ex + sum;
+		off[nlists] = (uint32_t)total;
+		*total_out = total;
+	}
+#pragma unroll
+	for (int i = 0; i < SCAN_ITEMS; ++i) {
+		const unsigned long long k = base + i;
+		if (k >= nlists) break;
+		off[k] = (uint32_t)ex;
+		const uint32_t n = c[i];
+		if (n && ex + n <= cap) {
+			double2 *dst = spans + ex;
+			if (n <= STAGE_INLINE) {
+				for (uint32_t q = 0; q < n; ++q) dst[q] = st.inl[k * STAGE_INLINE + q];
+			} else {
+				const unsigned long long pb = slot_pool_base(st.inl[k * STAGE_INLINE]);
+				if (pb + n <= st.pool_cap)
+					for (uint32_t q = 0; q < n; ++q) dst[q] = st.pool[pb + q];
+			}
+		}
+		ex += n;
+	}
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Complement kernels of the erosion composite (src/vor3d/Voronoi.cpp:18-89).
 // negate: output grid (nx+2*border)^2-ish with `border` empty lines added on every side, every column
@@ -634,7 +702,8 @@ __global__ void __launch_bounds__(256) k_compact(Stage st, unsigned long long nl
 // border = 1 for the 3D erosion, 0 for the vor2d negate() (DoubleCompressedImage.cpp:438-468).
 // ---------------------------------------------------------------------------------------------------
 struct NegArgs {
-	int nx, ny, border;     // source grid, border width
+	int nx, ny, border;     // source grid, border columns on either side in x
+	int by0, by1;           // border rows before / after (a y-slab of a sharded grid only has the rows of the global border it owns)
 	double lo, hi;
 	const uint32_t *off;
 	const double2 *spans;
@@ -649,7 +718,7 @@ __device__ __forceinline__ bool neg_src(const NegArgs &a, unsigned long long c, 
 {
 	const int mx = a.nx + 2 * a.border;
 	const int x = (int)(c % (unsigned)mx) - a.border;
-	const int y = (int)(c / (unsigned)mx) - a.border;
+	const int y = (int)(c / (unsigned)mx) - a.by0;
 	if (x < 0 || x >= a.nx || y < 0 || y >= a.ny) { o0 = o1 = 0; return false; }
 	const size_t s = (size_t)y * a.nx + x;
 	o0 = a.off[s];
@@ -657,25 +726,27 @@ __device__ __forceinline__ bool neg_src(const NegArgs &a, unsigned long long c, 
 	return true;
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(256) k_negate(NegArgs a, unsigned long long nlists)
+// one column of negate: number of intervals of its complement (and the "data outside [lo, hi]" flag)
+__device__ __forceinline__ uint32_t neg_count(const NegArgs &a, unsigned long long c)
 {
-	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= nlists) return;
 	uint32_t o0, o1;
 	neg_src(a, c, o0, o1);
 	const uint32_t k = o1 - o0;
-	if (k == 0) {
-		if (FILL) a.out_spans[a.out_off[c]] = make_double2(a.lo, a.hi);
-		else a.cnt[c] = 1;
-		return;
-	}
+	if (k == 0) return 1u;
 	const bool f = (a.spans[o0].x == a.lo);          // first event == lo: erased
 	const bool l = (a.spans[o1 - 1].y == a.hi);      // last event == hi: popped
-	if (!FILL && a.outside && (a.spans[o0].x < a.lo || a.spans[o1 - 1].y > a.hi)) *a.outside = 1u;
-	const uint32_t n = k + 1 - (f ? 1u : 0u) - (l ? 1u : 0u);
-	if (!FILL) { a.cnt[c] = n; return; }
-	double2 *dst = a.out_spans + a.out_off[c];
+	if (a.outside && (a.spans[o0].x < a.lo || a.spans[o1 - 1].y > a.hi)) *a.outside = 1u;
+	return k + 1 - (f ? 1u : 0u) - (l ? 1u : 0u);
+}
+
+// ... and the intervals themselves, written to dst[0 .. neg_count)
+__device__ __forceinline__ void neg_fill(const NegArgs &a, unsigned long long c, double2 *dst)
+{
+	uint32_t o0, o1;
+	neg_src(a, c, o0, o1);
+	if (o1 == o0) { dst[0] = make_double2(a.lo, a.hi); return; }
+	const bool f = (a.spans[o0].x == a.lo);
+	const bool l = (a.spans[o1 - 1].y == a.hi);
 	// event sequence: [lo if !f] z1_0? ... pairs re-formed from consecutive events
 	double start = f ? a.spans[o0].y : a.lo;
 	uint32_t w = 0;
@@ -688,11 +759,21 @@ __global__ void __launch_bounds__(256) k_negate(NegArgs a, unsigned long long nl
 	if (!l) dst[w++] = make_double2(start, a.hi);
 }
 
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_negate(NegArgs a, unsigned long long nlists)
+{
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nlists) return;
+	if (FILL) neg_fill(a, c, a.out_spans + a.out_off[c]);
+	else a.cnt[c] = neg_count(a, c);
+}
+
 // negateInv: strip `border` lines on every side, then negate_ray_range (MorphologyOperators.cpp:282-315):
 // leading events <= lo and trailing events >= hi are dropped; a bound is re-inserted when an even
 // number of events was dropped on that side; an empty column becomes [lo, hi].
 struct NegInvArgs {
-	int mx, my, border;     // source (bordered) grid
+	int mx, my, border;     // source (bordered) grid, border columns on either side in x
+	int by0;                // border rows stripped before the first row (the rows after the last are simply not visited)
 	double lo, hi;
 	const uint32_t *off;
 	const double2 *spans;
@@ -707,21 +788,19 @@ __device__ __forceinline__ double ev_at(const double2 *sp, uint32_t base, uint32
 	return (i & 1u) ? v.y : v.x;
 }
 
+// one column of negateInv: FILL = false returns the number of intervals, FILL = true also writes them to dst
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_negate_inv(NegInvArgs a, unsigned long long nlists)
+__device__ __forceinline__ uint32_t neg_inv_col(const NegInvArgs &a, unsigned long long c, double2 *dst)
 {
-	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= nlists) return;
 	const int nx = a.mx - 2 * a.border;
 	const int x = (int)(c % (unsigned)nx) + a.border;
-	const int y = (int)(c / (unsigned)nx) + a.border;
+	const int y = (int)(c / (unsigned)nx) + a.by0;
 	const size_t s = (size_t)y * a.mx + x;
 	const uint32_t o0 = a.off[s], o1 = a.off[s + 1];
 	const uint32_t n = 2 * (o1 - o0);               // events
 	if (n == 0) {
-		if (FILL) a.out_spans[a.out_off[c]] = make_double2(a.lo, a.hi);
-		else a.cnt[c] = 1;
-		return;
+		if (FILL) dst[0] = make_double2(a.lo, a.hi);
+		return 1u;
 	}
 	uint32_t cf = 0;
 	while (cf < n && ev_at(a.spans, o0, cf) <= a.lo) ++cf;
@@ -734,8 +813,7 @@ __global__ void __launch_bounds__(256) k_negate_inv(NegInvArgs a, unsigned long 
 	}
 	const uint32_t app = (cl % 2 == 0) ? 1u : 0u;    // hi re-appended
 	const uint32_t total = k + app;                  // events of the result
-	if (!FILL) { a.cnt[c] = total / 2; return; }
-	double2 *dst = a.out_spans + a.out_off[c];
+	if (!FILL) return total / 2;
 	// event t of the result: t < min(pre,k) -> lo ; t < k -> e[cf + t - pre] ; t == k (app) -> hi
 	const uint32_t npre = (pre < k) ? pre : k;
 	for (uint32_t t = 0; t + 1 < total + 0u; t += 2) {
@@ -745,6 +823,84 @@ __global__ void __launch_bounds__(256) k_negate_inv(NegInvArgs a, unsigned long 
 			v[q] = (tt < npre) ? a.lo : (tt < k) ? ev_at(a.spans, o0, cf + tt - pre) : a.hi;
 		}
 		dst[t >> 1] = make_double2(v[0], v[1]);
+	}
+	return total / 2;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_negate_inv(NegInvArgs a, unsigned long long nlists)
+{
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nlists) return;
+	if (FILL) neg_inv_col<true>(a, c, a.out_spans + a.out_off[c]);
+	else a.cnt[c] = neg_inv_col<false>(a, c, nullptr);
+}
+
+// Both complements in ONE launch each (count -> single-pass prefix sum with look-back -> fill, scan.cuh) instead of
+// count / reduce / scan / apply / fill with a host round trip in the middle. The output buffer holds `cap` intervals
+// (the caller passes the bound k + 1 per column, which both complements respect); *total_out = the exact total.
+struct NegOp {
+	typedef NegArgs Args;
+	static __device__ __forceinline__ uint32_t count(const Args &a, unsigned long long c) { return neg_count(a, c); }
+	static __device__ __forceinline__ void fill(const Args &a, unsigned long long c, double2 *dst) { neg_fill(a, c, dst); }
+};
+struct NegInvOp {
+	typedef NegInvArgs Args;
+	static __device__ __forceinline__ uint32_t count(const Args &a, unsigned long long c) { return neg_inv_col<false>(a, c, nullptr); }
+	static __device__ __forceinline__ void fill(const Args &a, unsigned long long c, double2 *dst) { neg_inv_col<true>(a, c, dst); }
+};
+
+constexpr int CF_ITEMS = 4;                             // columns per thread
+constexpr int CF_TILE = SCAN_THREADS * CF_ITEMS;
+
+template <typename Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_complement_fused(typename Op::Args a, unsigned long long nlists, uint32_t *__restrict__ off,
+                                                                   double2 *__restrict__ spans, unsigned long long cap,
+                                                                   unsigned long long *state, unsigned long long *ticket,
+                                                                   unsigned long long ticket_base, uint32_t epoch,
+                                                                   unsigned long long *total_out)
+{
+	__shared__ uint32_t s_tile;
+	__shared__ unsigned long long s_prefix;
+	if (threadIdx.x == 0) s_tile = (uint32_t)(atomicAdd(ticket, 1ull) - ticket_base);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const unsigned long long base = (unsigned long long)tile * CF_TILE + (unsigned long long)threadIdx.x * CF_ITEMS;
+	uint32_t n[CF_ITEMS];
+	unsigned long long sum = 0;
+#pragma unroll
+	for (int i = 0; i < CF_ITEMS; ++i) {
+		const unsigned long long c = base + i;
+		n[i] = c < nlists ? Op::count(a, c) : 0u;
+		sum += n[i];
+	}
+	unsigned long long tot;
+	unsigned long long ex = block_excl_scan(sum, &tot);
+	volatile unsigned long long *vstate = state;
+	if (threadIdx.x == 0) {
+		vstate[tile] = scan_word(tot, epoch, tile == 0 ? SCAN_INCL : SCAN_AGG);
+		if (tile == 0) s_prefix = 0;
+	}
+	if (tile > 0 && threadIdx.x < 32) {
+		const unsigned long long excl = scan_look_back(vstate, tile, epoch);
+		if (threadIdx.x == 0) {
+			vstate[tile] = scan_word(excl + tot, epoch, SCAN_INCL);
+			s_prefix = excl;
+		}
+	}
+	__syncthreads();
+	ex += s_prefix;
+	if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
+		off[nlists] = (uint32_t)(ex + sum);
+		*total_out = ex + sum;
+	}
+#pragma unroll
+	for (int i = 0; i < CF_ITEMS; ++i) {
+		const unsigned long long c = base + i;
+		if (c >= nlists) break;
+		off[c] = (uint32_t)ex;
+		if (n[i] && ex + n[i] <= cap) Op::fill(a, c, spans + ex);
+		ex += n[i];
 	}
 }
 

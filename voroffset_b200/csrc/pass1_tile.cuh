@@ -89,17 +89,24 @@ __device__ __forceinline__ int first_gt(const float *tab, int last, float v)
 // on that side a saturated q contains everything and nothing unsaturated contains a saturated p. Without this
 // the complement's intervals, which all share the endpoint zmin-1 or zmax+1, could never dominate each other
 // from farther away (the closer one always reaches lower), and every candidate up to the tangent point survived.
-__device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint32_t q0, uint32_t q1, double clo, double chi)
+// The intervals of a column are ascending and disjoint, so along q the first term (a_q - a_p) grows and the second
+// (b_p - b_q) falls: the minimum sits where they cross. `qs` (kept by the caller across the ascending p of one column,
+// initially q0) skips the q that lie entirely below p except the nearest, and the scan stops once the first term alone
+// reaches the best value - a column of k intervals costs O(k) per neighbour instead of O(k^2) (lattices: 10 x 10).
+// Any SUBSET of q gives a valid, merely more conservative value, so unsorted input only prunes less.
+__device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint32_t &qs, uint32_t q1, double clo, double chi)
 {
 	const double inf = __longlong_as_double(0x7FF0000000000000LL);
 	const bool plo = p.x <= clo, phi = p.y >= chi;
 	double r = inf;
-	for (uint32_t k = q0; k < q1; ++k) {
+	while (qs + 1 < q1 && __ldg(q + qs + 1).y < p.x) ++qs;
+	for (uint32_t k = qs; k < q1; ++k) {
 		const double2 v = __ldg(q + k);
 		if (!(v.x <= v.y)) continue;                       // (not an interval, see k_thresh)
 		const double ta = v.x <= clo ? -inf : (plo ? inf : v.x - p.x);
 		const double tb = v.y >= chi ? -inf : (phi ? inf : p.y - v.y);
 		r = fmin(r, fmax(ta, tb));
+		if (ta >= r) break;
 	}
 	return r;
 }
@@ -153,6 +160,7 @@ __device__ __forceinline__ void thresh_zero_bank(const ThreshArgs &a)
 {
 	if (a.zero_bank && blockIdx.x == 0 && threadIdx.x == 0) {
 		a.zero_bank[3] = 0; a.zero_bank[5] = 0; a.zero_bank[6] = 0; a.zero_bank[7] = 0; a.zero_bank[10] = 0;
+		a.zero_bank[12] = 0; a.zero_bank[13] = 0;
 	}
 }
 
@@ -188,6 +196,7 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 		// MorphologyOperators.cpp:241-248 - is sent to the unpruned kernel by erode() anyway.)
 		const bool proper = p.x <= p.y;
 		const double pinf = __longlong_as_double(0x7FF0000000000000LL);
+		// (l0, r0, u0, d0 advance with p: nn_of's scan start)
 		const double nnL = proper ? nn_of(p, a.spans, l0, l1, a.clip_lo, a.clip_hi) : pinf, nnR = proper ? nn_of(p, a.spans, r0, r1, a.clip_lo, a.clip_hi) : pinf;
 		const double nnU = proper ? nn_of(p, a.spans, u0, u1, a.clip_lo, a.clip_hi) : pinf, nnD = proper ? nn_of(p, a.spans, d0, d1, a.clip_lo, a.clip_hi) : pinf;
 		// an interval saturated on both sides covers the whole range: it yields to a CLOSER one of its kind (near
@@ -379,6 +388,7 @@ __global__ void __launch_bounds__(256) k_order_place(OrderArgs a)
 // ---- pass 1 ------------------------------------------------------------------------------------------
 struct Pass1TileArgs {
 	int nx, ny, J, cmax;
+	int dbuf = 1;           // candidates double-buffered (pass1_warp_smem)
 	int tiles_xw;           // tiles (P1_W columns) per row
 	int tiles_x;            // tile masks (P1_TX columns) per row
 	unsigned int tile0, ntiles;         // tiles [tile0, tile0 + ntiles0) and [tile0b, tile0b + ntiles - ntiles0) when `tiles` is NULL
@@ -427,23 +437,25 @@ __host__ __device__ inline size_t pass1_table_smem(int J)
 	b += (JP + 1 + 15) & ~(size_t)15;                       // jmax
 	return b;
 }
-__host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap)
+// dbuf: the candidates are double-buffered (the next tile is staged while the current one is in phase 2). Large buffers
+// (dense columns: lattices, erosion's complement) take one: 34 instead of 52 bytes per candidate, i.e. half again as many
+// warps per SM, against ~1.5 us of exposed copy latency per tile - tiles that large take tens of microseconds.
+__host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap, bool dbuf = true)
 {
-	const size_t SEG = (size_t)P1_W + 2 * J;
+	const size_t SEG = (size_t)P1_W + 2 * J, nb = dbuf ? 2 : 1;
 	size_t b = 0;
-	b += 2 * (size_t)cmax * sizeof(double2);                // candidates (double-buffered: the next tile is staged
-	b += (size_t)cmax * sizeof(uint4);                      // their thresholds    while the current one is processed); the
-	                                                        // thresholds are only read by phase 1: ONE buffer, refilled after it
-	b += 2 * ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);   // segment offsets (double-buffered)
+	b += nb * (size_t)cmax * sizeof(double2);               // candidates
+	b += (size_t)cmax * sizeof(uint4);                      // their thresholds: only read by phase 1, ONE buffer, refilled after it
+	b += 2 * ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);   // segment offsets (always double-buffered)
 	b += (size_t)P1_W * sizeof(uint32_t);                   // list lengths
 	b += (size_t)lcap * P1_W * sizeof(uint32_t);            // survivor lists [s][lane]
-	b += 4 * (((size_t)cmax + 15) & ~(size_t)15);           // segment column and layer of each candidate (double-buffered)
+	b += 2 * nb * (((size_t)cmax + 15) & ~(size_t)15);      // segment column and layer of each candidate
 	b += 2 * sizeof(unsigned long long);                    // mbarriers of the two staging buffers
 	return b;
 }
-__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap, int nwarps)
+__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap, int nwarps, bool dbuf = true)
 {
-	return pass1_table_smem(J) + (size_t)nwarps * pass1_warp_smem(J, cmax, lcap) + 32;
+	return pass1_table_smem(J) + (size_t)nwarps * pass1_warp_smem(J, cmax, lcap, dbuf) + 32;
 }
 
 // Pool space for `n` entries, one atomic per converged group of threads instead of one per thread.
@@ -489,21 +501,21 @@ struct WarpSmem {
 	uint32_t *off[2], *cnt, *list;
 	uint8_t *ci[2], *ly[2];
 	unsigned long long *mbar;      // [2]
-	__device__ __forceinline__ WarpSmem(unsigned char *raw, int J, int cmax, int lcap)
+	__device__ __forceinline__ WarpSmem(unsigned char *raw, int J, int cmax, int lcap, bool dbuf)
 	{
-		const int SEG = P1_W + 2 * J;
+		const int SEG = P1_W + 2 * J, c16 = (cmax + 15) & ~15;
 		cand[0] = reinterpret_cast<double2 *>(raw);
-		cand[1] = cand[0] + cmax;
+		cand[1] = dbuf ? cand[0] + cmax : cand[0];          // (single buffer: both names, one array)
 		thr = reinterpret_cast<uint4 *>(cand[1] + cmax);
 		off[0] = reinterpret_cast<uint32_t *>(thr + cmax);
 		off[1] = off[0] + ((SEG + 4) & ~3);
 		cnt = off[1] + ((SEG + 4) & ~3);
 		list = cnt + P1_W;
 		ci[0] = reinterpret_cast<uint8_t *>(list + (size_t)lcap * P1_W);
-		ci[1] = ci[0] + ((cmax + 15) & ~15);
-		ly[0] = ci[1] + ((cmax + 15) & ~15);
-		ly[1] = ly[0] + ((cmax + 15) & ~15);
-		mbar = reinterpret_cast<unsigned long long *>(ly[1] + ((cmax + 15) & ~15));
+		ci[1] = dbuf ? ci[0] + c16 : ci[0];
+		ly[0] = ci[1] + c16;
+		ly[1] = dbuf ? ly[0] + c16 : ly[0];
+		mbar = reinterpret_cast<unsigned long long *>(ly[1] + c16);
 	}
 };
 
@@ -923,7 +935,8 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 	for (int i = threadIdx.x; i < JP * pass1_jpp(J); i += blockDim.x) tb.Ht[i] = __ldg(a.Ht + i);
 	for (int i = threadIdx.x; i < JP * (JP + 1); i += blockDim.x) tb.Ef[i] = __ldg(a.Ef + i);
 	for (int i = threadIdx.x; i < JP + 1; i += blockDim.x) tb.jmax[i] = __ldg(a.jmax + i);
-	const WarpSmem sm(smem_raw + pass1_table_smem(J) + (size_t)warp * pass1_warp_smem(J, a.cmax, LCAP), J, a.cmax, LCAP);
+	const bool dbuf = a.dbuf != 0;
+	const WarpSmem sm(smem_raw + pass1_table_smem(J) + (size_t)warp * pass1_warp_smem(J, a.cmax, LCAP, dbuf), J, a.cmax, LCAP, dbuf);
 	sm.cnt[lane] = 0;
 	if (lane == 0) {
 		mbar_init(sm.mbar + 0, 1); mbar_init(sm.mbar + 1, 1);
@@ -1014,11 +1027,11 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 			for (int k = lane; k < cur.ncand; k += 32) tl.scatter(k, cur.txe);
 		} else tile_other<MULTI>(a, cur);
 
-		// ---- publish the next tile's offsets, start its staging ----
+		// ---- publish the next tile's offsets, start its staging (single candidate buffer: only after phase 2) ----
 		if (have_next) {
 			const bool nmulti = store_offsets(o, sm.off[buf ^ 1]);
 			classify(nxt, sm.off[buf ^ 1], nmulti);
-			if (nxt.kind == TK_NORMAL) stage(nxt, buf ^ 1);
+			if (dbuf && nxt.kind == TK_NORMAL) stage(nxt, buf ^ 1);
 		}
 		__syncwarp();                                       // phase 1 of the current tile is complete (lists visible)
 
@@ -1034,6 +1047,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 			d[3] = (unsigned long long)(dbg_t1 - dbg_t0);
 		}
 		if (!have_next) break;
+		if (!dbuf && nxt.kind == TK_NORMAL) { stage(nxt, buf ^ 1); __syncwarp(); }
 		cur = nxt;
 		buf ^= 1;
 	}

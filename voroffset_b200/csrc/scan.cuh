@@ -100,4 +100,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t *__r
 	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) off[n] = (uint32_t)tile_sum[gridDim.x];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Single-pass form ("decoupled look-back"): ONE launch turns the staged lists into canonical CSR - the exclusive
+// prefix sum of the counts AND the compaction of the spans - instead of reduce / scan / apply / compact with a host
+// round trip in between (the spans buffer is sized from the previous result; a result that outgrows it falls back to
+// k_compact with the offsets this kernel has already written).
+// Tiles take tickets in launch order, publish their own sum at once and then look back over their predecessors'
+// state words until they meet one that carries an inclusive prefix. A state word holds value, call epoch and flag
+// together, so one 64-bit load / store is the whole protocol and the array never has to be cleared between calls.
+// ---------------------------------------------------------------------------------------------------
+constexpr unsigned long long SCAN_AGG = 1ull, SCAN_INCL = 2ull;
+constexpr int SCAN_EPOCH_BITS = 22;
+__device__ __forceinline__ unsigned long long scan_word(unsigned long long value, uint32_t epoch, unsigned long long flag)
+{
+	return (value << (SCAN_EPOCH_BITS + 2)) | ((unsigned long long)epoch << 2) | flag;
+}
+
+// Prefix of everything before `tile` (warp 0 of the block calls this; every lane returns the same value).
+__device__ __forceinline__ unsigned long long scan_look_back(const volatile unsigned long long *state, uint32_t tile, uint32_t epoch)
+{
+	const int lane = threadIdx.x & 31;
+	unsigned long long excl = 0;
+	long long idx = (long long)tile - 1 - lane;
+	for (;;) {
+		const unsigned long long w = idx >= 0 ? state[idx] : scan_word(0ull, epoch, SCAN_INCL);
+		const bool ok = (uint32_t)((w >> 2) & ((1u << SCAN_EPOCH_BITS) - 1u)) == epoch && (w & 3ull) != 0ull;
+		if (!__all_sync(0xffffffffu, ok)) continue;          // a predecessor has not published yet
+		const unsigned int incl = __ballot_sync(0xffffffffu, (w & 3ull) == SCAN_INCL);
+		const int first = incl ? __ffs(incl) - 1 : 31;       // lanes 0 .. first contribute
+		unsigned long long v = lane <= first ? (w >> (SCAN_EPOCH_BITS + 2)) : 0ull;
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+		excl += v;
+		if (incl) return excl;
+		idx -= 32;
+	}
+}
+
 } // namespace vo

@@ -53,6 +53,7 @@ struct vo_ctx {
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
+	int tile_dbuf = -1;               // vo_set_option("tile_dbuf", "auto" | "on" | "off"): double-buffered candidate staging of the tile kernel
 	int band_split = 2;               // vo_set_option("band_split", "N"): a band's pass-1 launch set takes 1/N of the SMs (host-buffer pipeline)
 	int pipe_warps = 64;              // vo_set_option("pipe_warps", "N"): warps per tile-kernel CTA in the host-buffer pipeline (default: as many as fit)
 	int band_free = 0;                // vo_set_option("band_free", "N"): SMs no pass-1 launch set of the pipeline takes (room for its small kernels and pass 2)
@@ -63,6 +64,14 @@ struct vo_ctx {
 	cudaStream_t s_hi[3] = {nullptr, nullptr, nullptr};   // its second-half streams (highest priority): two for alternating bands, one for the pass-1 redo launches
 	cudaStream_t s_ctl = nullptr;                   // its control stream (band totals -> host)
 	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
+	// single-pass scan + compaction (k_scan_compact): tile state words, ticket counter (device) and their host mirrors
+	unsigned long long *scan_state = nullptr;   // [scan_cap] state words, then the ticket counter
+	size_t scan_cap = 0;
+	unsigned long long scan_ticket = 0;         // tickets handed out so far
+	uint32_t scan_epoch = 0;                    // epoch of the last call (1 .. 2^22 - 1)
+	unsigned long long out_cap_hint = 0;        // intervals the recent staged results needed (+12 %): sizes the spans buffer up front
+	bool fused_scan = true;                     // vo_set_option("scan", "fused" | "classic")
+	unsigned long long last_ctr[16] = {};   // the counters as the last read_counters saw them (a deferred pass 1 is judged after pass 2)
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
 	// Large scratch blocks (>= 1 MiB) released by dfree are kept WHOLE and handed to the next request they fit
@@ -90,6 +99,8 @@ struct vo_dmid {
 	uint16_t *flags = nullptr;      // [2][ny*nx]: class window (lo | hi << 8) needed by the consumer rows above / below each mid column
 	unsigned long long *tilemask = nullptr;   // [2][ny * ceil(nx / P1_TX)]: OR of the windows per pass-1 tile
 	uint64_t pool_cap = 0, pool_used = 0;
+	bool deferred = false;          // pass 1 returned without reading its counters: the caller checks them after pass 2
+	unsigned int redo_cap = 0;      // ... against these
 };
 static_assert(P1_TX == P2_TX, "pass 2 reads the tile masks of pass 1: same tile width");
 
@@ -375,6 +386,8 @@ int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 {
 	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, NCTR * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	static_assert(NCTR == 16, "vo_ctx::last_ctr");
+	std::memcpy(ctx->last_ctr, h, NCTR * sizeof(unsigned long long));
 	return VO_OK;
 }
 
@@ -384,6 +397,26 @@ int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 // The whole chain - gather, redo, prefix sum - is enqueued without a host round trip; the single
 // synchronisation at the end returns the counters and the grand total together.
 constexpr unsigned int REDO_GRID = 148 * 4;
+
+// tile state of k_scan_compact for `ntiles` tiles: grown when needed, cleared when grown and when the epoch wraps
+int scan_prepare(vo_ctx *ctx, unsigned int ntiles, uint32_t *epoch, unsigned long long *ticket_base)
+{
+	if (ctx->scan_cap < ntiles) {
+		if (ctx->scan_state) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->scan_state); ctx->scan_state = nullptr; }
+		const size_t cap = std::max<size_t>(2 * (size_t)ntiles, 4096);
+		VO_CUDA(cudaMalloc((void **)&ctx->scan_state, (cap + 1) * sizeof(unsigned long long)));
+		VO_CUDA(cudaMemsetAsync(ctx->scan_state, 0, (cap + 1) * sizeof(unsigned long long), ctx->stream));
+		ctx->scan_cap = cap; ctx->scan_ticket = 0; ctx->scan_epoch = 0;
+	}
+	if (++ctx->scan_epoch >= (1u << SCAN_EPOCH_BITS)) {
+		VO_CUDA(cudaMemsetAsync(ctx->scan_state, 0, ctx->scan_cap * sizeof(unsigned long long), ctx->stream));
+		ctx->scan_epoch = 1;
+	}
+	*epoch = ctx->scan_epoch;
+	*ticket_base = ctx->scan_ticket;
+	ctx->scan_ticket += ntiles;
+	return VO_OK;
+}
 
 template <typename Args, typename LaunchFast, typename LaunchBig>
 int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long long pool_guess,
@@ -401,6 +434,14 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	const unsigned int ntiles = blocks_for(nlists, SCAN_TILE);
 	Tmp<unsigned long long> sums(ctx);
 	VO_TRY(dalloc(ctx, &sums.p, (unsigned long long)ntiles + 1));
+	// fused: the spans buffer exists before the gather (sized from the recent results, at least one interval per list)
+	// and ONE kernel writes offsets and spans; a result that outgrows the buffer is compacted again into an exact one
+	const bool fused = ctx->fused_scan && nlists > 0;
+	unsigned long long out_cap = 0;
+	if (fused) {
+		out_cap = std::min<unsigned long long>(std::max(ctx->out_cap_hint, nlists + 65536ull), (1ull << 32) - 1);
+		VO_TRY(dalloc(ctx, &v->spans, out_cap));
+	}
 	for (int attempt = 0; attempt < 3; ++attempt) {
 		// only the counters of the staged gather: a pass 1 may be in flight on the same stream (pipelined path)
 		VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
@@ -413,10 +454,19 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 			launch_fast(args);
 			args.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
 			launch_big(args, REDO_GRID);
-			k_scan_reduce<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p);
-			k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(sums.p, ntiles);
-			k_scan_apply<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p, v->off);
-			ctx->launches += 5;
+			if (fused) {
+				uint32_t epoch = 0;
+				unsigned long long tbase = 0;
+				VO_TRY(scan_prepare(ctx, ntiles, &epoch, &tbase));
+				k_scan_compact<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
+				                                                         ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles);
+				ctx->launches += 3;
+			} else {
+				k_scan_reduce<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p);
+				k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(sums.p, ntiles);
+				k_scan_apply<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p, v->off);
+				ctx->launches += 5;
+			}
 			VO_CUDA(cudaGetLastError());
 			VO_CUDA(cudaMemcpyAsync(&total, sums.p + ntiles, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
 		} else {
@@ -428,13 +478,17 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 		ctx->stage_hint = next_hint(ctx->stage_hint, h[1]);
 		if (h[1] > sb.st.pool_cap) { VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024)); continue; }
 		if (total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
-		VO_TRY(dalloc(ctx, &v->spans, total));
-		v->nspans = total;
-		if (nlists) {
-			k_compact<<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans);
-			ctx->launches++;
-			VO_CUDA(cudaGetLastError());
+		if (fused) ctx->out_cap_hint = next_hint(ctx->out_cap_hint, total + total / 8 + 1024);
+		if (!fused || total > out_cap) {
+			if (v->spans) { dfree(ctx, v->spans); v->spans = nullptr; }
+			VO_TRY(dalloc(ctx, &v->spans, total));
+			if (nlists) {
+				k_compact<<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans);
+				ctx->launches++;
+				VO_CUDA(cudaGetLastError());
+			}
 		}
+		v->nspans = total;
 		*out = v;
 		v = nullptr;          // released from the guard
 		return VO_OK;
@@ -604,7 +658,9 @@ inline void launch_thresh(const ThreshArgs &ta, double k_in, cudaStream_t s)
 struct TilePlan {
 	int J = 0, tiles_xw = 0, tiles_x = 0, sms = 148, cps = 1;
 	int cmax_small = 0, cmax_big = 0, cmax_multi = 0;
-	int nw_small = 1, nw_big = 1, nw_multi = 1;
+	int nw_small = 1, nw_big = 1, nw_multi = 1, nw_bigmulti = 1;
+	bool db_small = true, db_big = true, db_multi = true, db_bigmulti = false;   // candidates double-buffered (pass1_warp_smem)
+	size_t smem_bigmulti = 0;
 	size_t smem_small = 0, smem_big = 0, smem_multi = 0;
 	static constexpr int CMAX = 2048;       // largest candidate buffer (11-bit candidate ids in the survivor lists)
 	static bool fits(int J, double k_in) { return J <= 63 && k_in * (P1_W + 2 * J) <= 0.75 * CMAX; }
@@ -626,37 +682,45 @@ struct TilePlan {
 		// launch 1 only sees single-interval columns: at most SEG candidates
 		cmax_small = std::min(pick(k_in * SEG * 1.5), (SEG + 15) & ~15);
 		cmax_big = CMAX;
-		cmax_multi = std::max(pick(k_in * SEG * 1.5), 128);
+		// launch 3 (multi-interval columns): a quarter above the mean fill, in steps of 32 (shared memory per warp is what
+		// bounds the warps per SM of this launch; the few tiles beyond it go to the redo list)
+		cmax_multi = std::min(CMAX, std::max(128, ((int)std::ceil(k_in * SEG * 1.25) + 31) & ~31));
 		// `cps` CTAs per SM share its shared memory (228 KB, 1 KB of it reserved per CTA) and its 16 warps' worth of
 		// registers: several small CTAs give an SM back piecewise when a launch runs out of tiles, one large CTA only
 		// when its last warp is done
 		cps = std::max(1, std::min(ctx->tile_ctas, 8));
 		const size_t budget = std::min<size_t>(220 * 1024, 228 * 1024 / cps - 1024 - 256);
-		auto warps = [&](int cmax, int lcap, int maxw) {
-			const size_t per = pass1_warp_smem(J, cmax, lcap), tab = pass1_table_smem(J) + 32;
+		auto warps = [&](int cmax, int lcap, int maxw, bool dbuf) {
+			const size_t per = pass1_warp_smem(J, cmax, lcap, dbuf), tab = pass1_table_smem(J) + 32;
 			if (budget < tab + per) return 1;
 			return (int)std::max<size_t>(1, std::min<size_t>(std::min(maxw, warps_cap) / cps, (budget - tab) / per));
 		};
-		nw_small = warps(cmax_small, P1_LCAP_S, P1_MAXWARPS); nw_big = warps(cmax_big, P1_LCAP_M, P1_MAXWARPS);
-		nw_multi = warps(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M);
-		smem_small = pass1_tile_smem(J, cmax_small, P1_LCAP_S, nw_small);
-		smem_big = pass1_tile_smem(J, cmax_big, P1_LCAP_M, nw_big);
-		smem_multi = pass1_tile_smem(J, cmax_multi, P1_LCAP_M, nw_multi);
+		// double-buffered candidates where that still leaves room for every warp the registers allow, one buffer otherwise
+		auto plan = [&](int cmax, int lcap, int maxw, int &nw, bool &db, size_t &smem) {
+			const int want = std::max(1, std::min(maxw, warps_cap) / cps);
+			db = ctx->tile_dbuf > 0 || (ctx->tile_dbuf < 0 && warps(cmax, lcap, maxw, true) >= want);
+			nw = warps(cmax, lcap, maxw, db);
+			smem = pass1_tile_smem(J, cmax, lcap, nw, db);
+		};
+		plan(cmax_small, P1_LCAP_S, P1_MAXWARPS, nw_small, db_small, smem_small);
+		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS, nw_big, db_big, smem_big);
+		plan(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M, nw_multi, db_multi, smem_multi);
+		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS_M, nw_bigmulti, db_bigmulti, smem_bigmulti);   // launch 4: the multi-interval tiles beyond cmax_multi
 		cudaError_t e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
-		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_multi, smem_bigmulti));
 		if (e != cudaSuccess) return fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e));
 		return VO_OK;
 	}
-	// The three launches over the tiles [tile0, tile0 + ntiles). `g` holds the data pointers; the lists and cursors
-	// ([3] big count, [5] multi count, [6] [7] [10] cursors of d_ctr) must be zero.
+	// The four launches over the tiles [tile0, tile0 + ntiles). `g` holds the data pointers; the lists and cursors
+	// ([3] big count, [5] multi count, [12] big multi count, [6] [7] [10] [13] cursors of d_ctr) must be zero.
 	// A second range [tile0b, tile0b + ntilesb) may follow the first; reserve_sms CTAs fewer are launched (room for the
 	// NCCL kernels of a halo exchange in flight).
 	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles0, unsigned int *big_tiles, unsigned int *multi_tiles,
 	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0,
 	            unsigned long long *bank = nullptr, const unsigned int *order = nullptr) const
 	{
-		if (!bank) bank = ctx->d_ctr;                       // ([3] [5] [6] [7] [10] of `bank`: the lists and cursors of this launch set)
+		if (!bank) bank = ctx->d_ctr;                       // ([3] [5] [6] [7] [10] [12] [13] of `bank`: the lists and cursors of this launch set)
 		const unsigned int ntiles = ntiles0 + ntilesb;
 		const int sms = std::max(1, this->sms - reserve_sms);
 		g.J = J; g.tiles_xw = tiles_xw; g.tiles_x = tiles_x; g.tile0 = tile0; g.ntiles = ntiles; g.tile0b = tile0b; g.ntiles0 = ntiles0;
@@ -669,22 +733,32 @@ struct TilePlan {
 		// the tile counter does not mind)
 		auto grid = [&](int nw) { return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)(sms * cps), (ntiles + nw - 1) / nw)); };
 		// launch 1: single-interval tiles, small candidate buffer
-		g.cmax = cmax_small; g.tiles = nullptr; g.tiles_count = nullptr; g.order = order;
+		g.cmax = cmax_small; g.dbuf = db_small; g.tiles = nullptr; g.tiles_count = nullptr; g.order = order;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 10);
 		g.big_tiles = cmax_small < cmax_big ? big_tiles : nullptr;
 		k_pass1_tile<CAP_FAST, false, false><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
 		ctx->launches++;
 		if (cmax_small < cmax_big) {    // launch 2: the single-interval tiles that need the large buffer
-			g.cmax = cmax_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
+			g.cmax = cmax_big; g.dbuf = db_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 6);
 			k_pass1_tile<CAP_FAST, false, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
 			ctx->launches++;
 		}
-		// launch 3: tiles with multi-interval columns (two hulls per class); oversized ones go to the redo list
-		g.cmax = cmax_multi; g.tiles = multi_tiles; g.tiles_count = multi_count; g.big_tiles = nullptr;
+		// launch 3: tiles with multi-interval columns (two hulls per class), candidate buffer a quarter above the mean fill;
+		// the tiles beyond it are collected again (in big_tiles, which launch 2 is done with) for launch 4
+		unsigned int *bigmulti_count = reinterpret_cast<unsigned int *>(bank + 12);
+		const bool four = cmax_multi < cmax_big;
+		g.cmax = cmax_multi; g.dbuf = db_multi; g.tiles = multi_tiles; g.tiles_count = multi_count;
+		g.big_tiles = four ? big_tiles : nullptr; g.big_count = bigmulti_count;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 7);
 		k_pass1_tile<CAP_FAST, true, true><<<grid(nw_multi), 32 * nw_multi, smem_multi, s>>>(g);
 		ctx->launches++;
+		if (four) {                     // launch 4: the largest buffer; whatever exceeds that goes to the redo list
+			g.cmax = cmax_big; g.dbuf = db_bigmulti; g.tiles = big_tiles; g.tiles_count = bigmulti_count; g.big_tiles = nullptr;
+			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 13);
+			k_pass1_tile<CAP_FAST, true, true><<<grid(nw_bigmulti), 32 * nw_bigmulti, smem_bigmulti, s>>>(g);
+			ctx->launches++;
+		}
 	}
 	// Expensive tiles first: `est` (k_thresh, per tile) -> `order`, a permutation of the positions of the same two
 	// ranges launch() takes; scratch = [2 * P1_NBUCKET] zeroed counters.
@@ -704,8 +778,12 @@ struct TilePlan {
 // ---- 'ours' pass 1 ------------------------------------------------------------------------------------
 // clip_lo / clip_hi: the caller only reads the dilation inside (clip_lo, clip_hi) (erosion); the pruning of the tile
 // kernel may then ignore what happens outside. -inf / +inf: the exact dilation everywhere.
+// defer: enqueue only - no host round trip; the counters that say whether the pools were large enough are read by the
+// caller together with those of pass 2 (which never follows a reference beyond a pool), and a pass 1 that fell short is
+// repeated without `defer`. Saves one synchronisation per dilation.
 int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
-          double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity())
+          double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity(),
+          bool defer = false)
 {
 	VO_TRY(check_radius(ctx, R));
 	const int J0 = (int)std::floor(R);
@@ -804,6 +882,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 		}
 		e = cudaGetLastError();
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1: ") + cudaGetErrorString(e)));
+		if (defer) { m->deferred = true; m->redo_cap = redo_cap; *out = m; return VO_OK; }
 		unsigned long long h[NCTR];
 		rc = read_counters(ctx, h);
 		if (rc) return bail(rc);
@@ -871,12 +950,30 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 	float t1 = 0, t2 = 0;
 	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 	if (method == VO_METHOD_OURS) {
-		vo_dmid *mid = nullptr;
-		VO_TRY(pass1(ctx, in, R, &mid, clip_lo, clip_hi));
-		cudaEventRecord(ctx->ev[1], ctx->stream);
-		int rc = pass2(ctx, mid, 0, mid->ny, out);
-		vo_dmid_free(ctx, mid);
-		VO_TRY(rc);
+		for (int attempt = 0;; ++attempt) {
+			vo_dmid *mid = nullptr;
+			VO_TRY(pass1(ctx, in, R, &mid, clip_lo, clip_hi, attempt == 0));
+			cudaEventRecord(ctx->ev[1], ctx->stream);
+			const bool deferred = mid->deferred;
+			const uint64_t pool_cap = mid->pool_cap;
+			const unsigned int redo_cap = mid->redo_cap;
+			int rc = pass2(ctx, mid, 0, mid->ny, out);
+			vo_dmid_free(ctx, mid);
+			if (deferred) {
+				// pass 2's synchronisation has read every counter: was the deferred pass 1 complete?
+				const unsigned long long *h = ctx->last_ctr;
+				const bool short1 = h[0] > pool_cap || h[2] > redo_cap || h[4] != 0;
+				if (rc == VO_OK && !short1) { ctx->pool_hint = next_hint(ctx->pool_hint, h[0]); break; }
+				if (rc == VO_OK) { free_dvol(ctx, *out); *out = nullptr; }
+				else if (!short1) return rc;
+				// repeat, synchronously this time (it regrows its pool / reports what cannot be done)
+				if (h[0] > pool_cap) ctx->pool_hint = std::max<unsigned long long>(ctx->pool_hint, h[0] + h[0] / 4);
+				ctx->err.clear();
+				continue;
+			}
+			VO_TRY(rc);
+			break;
+		}
 		VO_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
 		VO_CUDA(cudaEventSynchronize(ctx->ev[2]));
 		cudaEventElapsedTime(&t1, ctx->ev[0], ctx->ev[1]);
@@ -893,21 +990,59 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 	return VO_OK;
 }
 
-// negate (Voronoi.cpp:18-55) / negateInv (Voronoi.cpp:57-89) / vor2d negate, all count -> scan -> fill
-int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out, unsigned int *outside = nullptr)
+// negate (Voronoi.cpp:18-55) / negateInv (Voronoi.cpp:57-89) / vor2d negate. Fused (default): ONE launch (count ->
+// look-back prefix sum -> fill, k_complement_fused) into a buffer sized by the bound "intervals + 1 per column", one
+// synchronisation for the exact total. Classic: count -> scan -> fill.
+template <typename Op>
+int complement_fused(vo_ctx *ctx, typename Op::Args &a, unsigned long long nlists, unsigned long long cap, vo_dvol *v,
+                     unsigned int *d_flag, unsigned int *h_flag)
 {
-	const int mx = in->nx + 2 * border, my = in->ny + 2 * border;
+	VO_TRY(dalloc(ctx, &v->spans, cap));
+	const unsigned int ntiles = blocks_for(nlists, CF_TILE);
+	Tmp<unsigned long long> tot(ctx);
+	VO_TRY(dalloc(ctx, &tot.p, 1));
+	uint32_t epoch = 0;
+	unsigned long long tbase = 0, total = 0;
+	VO_TRY(scan_prepare(ctx, ntiles, &epoch, &tbase));
+	k_complement_fused<Op><<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(a, nlists, v->off, v->spans, cap, ctx->scan_state,
+	                                                                 ctx->scan_state + ctx->scan_cap, tbase, epoch, tot.p);
+	ctx->launches++;
+	VO_CUDA(cudaGetLastError());
+	VO_CUDA(cudaMemcpyAsync(&total, tot.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+	if (d_flag && h_flag) VO_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (total > cap) return fail(ctx, VO_ERR_OVERFLOW, "complement larger than its bound");
+	v->nspans = total;
+	return VO_OK;
+}
+
+// by0 / by1: border rows before / after (default: `border` on every side; a y-slab of a sharded grid passes the rows of
+// the global border it owns). h_outside (optional): receives the "data outside [lo, hi]" flag of `outside`.
+int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out, unsigned int *outside = nullptr,
+           int by0 = -1, int by1 = -1, unsigned int *h_outside = nullptr)
+{
+	if (by0 < 0) by0 = border;
+	if (by1 < 0) by1 = border;
+	const int mx = in->nx + 2 * border, my = in->ny + by0 + by1;
 	VO_TRY(check_dims(ctx, mx, my));
 	const unsigned long long nlists = (unsigned long long)mx * my;
 	vo_dvol *v = nullptr;
 	VO_TRY(new_dvol(ctx, mx, my, &v));
+	NegArgs a;
+	a.nx = in->nx; a.ny = in->ny; a.border = border; a.by0 = by0; a.by1 = by1; a.lo = lo; a.hi = hi;
+	a.off = in->off; a.spans = in->spans; a.cnt = nullptr; a.out_off = nullptr; a.out_spans = nullptr; a.outside = outside;
+	if (outside) cudaMemsetAsync(outside, 0, sizeof(unsigned int), ctx->stream);
+	if (h_outside) *h_outside = 0;
+	if (ctx->fused_scan && nlists && in->nspans + nlists < (1ull << 32)) {
+		const int rc = complement_fused<NegOp>(ctx, a, nlists, in->nspans + nlists, v, outside, h_outside);
+		if (rc) { free_dvol(ctx, v); return rc; }
+		*out = v;
+		return VO_OK;
+	}
 	Tmp<uint32_t> cnt(ctx);
 	int rc = dalloc(ctx, &cnt.p, nlists);
 	if (rc) { free_dvol(ctx, v); return rc; }
-	NegArgs a;
-	a.nx = in->nx; a.ny = in->ny; a.border = border; a.lo = lo; a.hi = hi;
-	a.off = in->off; a.spans = in->spans; a.cnt = cnt.p; a.out_off = nullptr; a.out_spans = nullptr; a.outside = outside;
-	if (outside) cudaMemsetAsync(outside, 0, sizeof(unsigned int), ctx->stream);
+	a.cnt = cnt.p;
 	if (nlists) { k_negate<false><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
 	unsigned long long total = 0;
 	rc = scan_counts(ctx, cnt.p, nlists, v->off, &total);
@@ -917,24 +1052,37 @@ int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_
 	a.out_off = v->off; a.out_spans = v->spans;
 	if (nlists) { k_negate<true><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
 	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess && outside && h_outside) {
+		e = cudaMemcpyAsync(h_outside, outside, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	}
 	if (e != cudaSuccess) { free_dvol(ctx, v); return fail(ctx, VO_ERR_CUDA, std::string("k_negate: ") + cudaGetErrorString(e)); }
 	*out = v;
 	return VO_OK;
 }
 
-int negate_inv(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out)
+int negate_inv(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_dvol **out, int by0 = -1, int by1 = -1)
 {
-	const int nx = in->nx - 2 * border, ny = in->ny - 2 * border;
+	if (by0 < 0) by0 = border;
+	if (by1 < 0) by1 = border;
+	const int nx = in->nx - 2 * border, ny = in->ny - by0 - by1;
 	if (nx < 0 || ny < 0) return fail(ctx, VO_ERR_ARG, "negateInv on a grid smaller than its border");
 	const unsigned long long nlists = (unsigned long long)nx * ny;
 	vo_dvol *v = nullptr;
 	VO_TRY(new_dvol(ctx, nx, ny, &v));
+	NegInvArgs a;
+	a.mx = in->nx; a.my = in->ny; a.border = border; a.by0 = by0; a.lo = lo; a.hi = hi;
+	a.off = in->off; a.spans = in->spans; a.cnt = nullptr; a.out_off = nullptr; a.out_spans = nullptr;
+	if (ctx->fused_scan && nlists && in->nspans + nlists < (1ull << 32)) {
+		const int rc = complement_fused<NegInvOp>(ctx, a, nlists, in->nspans + nlists, v, nullptr, nullptr);
+		if (rc) { free_dvol(ctx, v); return rc; }
+		*out = v;
+		return VO_OK;
+	}
 	Tmp<uint32_t> cnt(ctx);
 	int rc = dalloc(ctx, &cnt.p, nlists);
 	if (rc) { free_dvol(ctx, v); return rc; }
-	NegInvArgs a;
-	a.mx = in->nx; a.my = in->ny; a.border = border; a.lo = lo; a.hi = hi;
-	a.off = in->off; a.spans = in->spans; a.cnt = cnt.p; a.out_off = nullptr; a.out_spans = nullptr;
+	a.cnt = cnt.p;
 	if (nlists) { k_negate_inv<false><<<blocks_for(nlists, 256), 256, 0, ctx->stream>>>(a, nlists); ctx->launches++; }
 	unsigned long long total = 0;
 	rc = scan_counts(ctx, cnt.p, nlists, v->off, &total);
@@ -949,32 +1097,40 @@ int negate_inv(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi,
 	return VO_OK;
 }
 
-// erosion = negate, dilation, negateInv (Voronoi.cpp:8-17)
-int erode(vo_ctx *ctx, int method, const vo_dvol *in, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt)
+// erosion = negate, dilation, negateInv (Voronoi.cpp:8-17). `dil(neg, clip_lo, clip_hi, unpruned, &out)` dilates the
+// complement; by0 / by1 = rows of the one-line border this volume owns (1 / 1 for a whole grid; a y-slab of a sharded grid
+// only has the border rows at the ends of the global grid).
+template <typename DilateFn>
+int erode_with(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, int by0, int by1, DilateFn dil, vo_dvol **out)
 {
 	const double z_min = zmin - 1, z_max = zmax + 1;
-	vo_dvol *neg = nullptr, *dil = nullptr;
+	vo_dvol *neg = nullptr, *dl = nullptr;
 	unsigned int *outside = reinterpret_cast<unsigned int *>(ctx->d_ctr + NCTR);
-	VO_TRY(negate(ctx, in, 1, z_min, z_max, &neg, outside));
+	unsigned int h_outside = 0;
+	VO_TRY(negate(ctx, in, 1, z_min, z_max, &neg, outside, by0, by1, &h_outside));
 	// negateInv only reads the dilated complement inside (z_min + 1, z_max - 1): everything at or beyond those bounds
 	// is dropped (MorphologyOperators.cpp:292-312), so 'ours' may prune with that clip range (pass1_tile.cuh: nn_of)
 	// Data outside [z_min, z_max] (no head-room: offset3d's -p) turns the complement into something that is not a
 	// set of intervals (negate_ray prepends / appends the bounds without looking); the reference still computes with
 	// it. k_negate raises a flag then, and that dilation takes the unpruned one-thread-per-slot kernel, which folds
 	// whatever it is given exactly like the reference's unions do.
-	unsigned int h_outside = 0;
-	cudaError_t ec = cudaMemcpyAsync(&h_outside, outside, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream);
-	if (ec == cudaSuccess) ec = cudaStreamSynchronize(ctx->stream);
-	if (ec != cudaSuccess) { free_dvol(ctx, neg); return fail(ctx, VO_ERR_CUDA, std::string("erode: ") + cudaGetErrorString(ec)); }
-	const bool saved_simple = ctx->force_simple_pass1;
-	if (h_outside) ctx->force_simple_pass1 = true;
-	int rc = dilate(ctx, method, neg, R, &dil, pt, z_min + 1, z_max - 1);
-	ctx->force_simple_pass1 = saved_simple;
+	int rc = dil(neg, z_min + 1, z_max - 1, h_outside != 0, &dl);
 	free_dvol(ctx, neg);
 	VO_TRY(rc);
-	rc = negate_inv(ctx, dil, 1, z_min + 1, z_max - 1, out);
-	free_dvol(ctx, dil);
+	rc = negate_inv(ctx, dl, 1, z_min + 1, z_max - 1, out, by0, by1);
+	free_dvol(ctx, dl);
 	return rc;
+}
+
+int erode(vo_ctx *ctx, int method, const vo_dvol *in, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt)
+{
+	return erode_with(ctx, in, zmin, zmax, 1, 1, [&](const vo_dvol *neg, double clo, double chi, bool unpruned, vo_dvol **o) {
+		const bool saved_simple = ctx->force_simple_pass1;
+		if (unpruned) ctx->force_simple_pass1 = true;
+		const int rc = dilate(ctx, method, neg, R, o, pt, clo, chi);
+		ctx->force_simple_pass1 = saved_simple;
+		return rc;
+	}, out);
 }
 
 int morph3d_dev(vo_ctx *ctx, int op, int method, const vo_dvol *in, double zmin, double zmax, double R,
@@ -1575,6 +1731,7 @@ struct vo_slab {
 	int nx = 0, ny = 0, J = 0, jp = 0, jn = 0;      // own rows; halo rows before / after (0 or J)
 	uint64_t cap_prev = 0, cap_next = 0, n_own = 0;
 	double R = 0;
+	double clip_lo = -std::numeric_limits<double>::infinity(), clip_hi = std::numeric_limits<double>::infinity();   // erosion: the result is only read inside
 	TilePlan plan;
 	uint4 *thr = nullptr;
 	unsigned int *big_tiles = nullptr, *multi_tiles = nullptr;
@@ -1621,10 +1778,11 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	cudaMemsetAsync(bank + 3, 0, sizeof(unsigned long long), sm);
 	cudaMemsetAsync(bank + 5, 0, 3 * sizeof(unsigned long long), sm);
 	cudaMemsetAsync(bank + 10, 0, sizeof(unsigned long long), sm);
+	cudaMemsetAsync(bank + 12, 0, 2 * sizeof(unsigned long long), sm);
 	ThreshArgs ta;
 	ta.nx = nx; ta.ny = S->ext->ny; ta.J = J; ta.off = S->ext->off; ta.spans = S->ext->spans;
 	ta.Dmono = tc->tt.Dmono; ta.Emono = tc->tt.Emono; ta.G = tc->tt.G; ta.reach = tc->dt.reach; ta.thr = S->thr;
-	ta.clip_lo = -std::numeric_limits<double>::infinity(); ta.clip_hi = std::numeric_limits<double>::infinity();
+	ta.clip_lo = S->clip_lo; ta.clip_hi = S->clip_hi;
 	ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
 	if (S->est) { ta.est = S->est + 4 * P1_NBUCKET; ta.tiles_xw = S->plan.tiles_xw; }
 	launch_thresh(ta, S->k_in, sm);
@@ -1680,7 +1838,8 @@ void slab_redo(vo_slab *S)
 struct HaloOut { void *d_off; void *d_spans; uint64_t cap; };   // send buffer of one neighbour (d_off == NULL: none)
 
 int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_next, uint64_t cap_prev, uint64_t cap_next,
-               HaloOut to_prev, HaloOut to_next, void *wait_stream, vo_slab **out)
+               HaloOut to_prev, HaloOut to_next, void *wait_stream, vo_slab **out,
+               double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity())
 {
 	VO_TRY(check_radius(ctx, R));
 	const int J = (int)std::floor(R), nx = own->nx, ny = own->ny;
@@ -1700,7 +1859,7 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	vo_slab *S = new (std::nothrow) vo_slab();
 	if (!S) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
 	S->ctx = ctx; S->nx = nx; S->ny = ny; S->J = J; S->jp = jp; S->jn = jn; S->R = R;
-	S->cap_prev = cap_prev; S->cap_next = cap_next; S->n_own = own->nspans;
+	S->cap_prev = cap_prev; S->cap_next = cap_next; S->n_own = own->nspans; S->clip_lo = clip_lo; S->clip_hi = clip_hi;
 	auto bail = [&](int rc) { free_slab(S); return rc; };
 	int rc = new_dvol(ctx, nx, ey, &S->ext);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->ext->spans, total);
@@ -1908,6 +2067,8 @@ int dexelize_dev(vo_ctx *ctx, uint64_t nv, const double *verts, uint64_t nf, con
 	return VO_OK;
 }
 
+int concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const vo_dvol *c, vo_dvol **out);
+
 struct DeviceGuard {
 	int prev = -1;
 	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
@@ -1968,6 +2129,7 @@ void vo_destroy(vo_ctx *ctx)
 	if (ctx->stream) { release_big_free(ctx, 0); cudaStreamSynchronize(ctx->stream); }
 	if (ctx->d_ctr) cudaFree(ctx->d_ctr);
 	if (ctx->ovf) cudaFree(ctx->ovf);
+	if (ctx->scan_state) cudaFree(ctx->scan_state);
 	for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->mark) if (e) cudaEventDestroy(e);
 	for (auto &e : ctx->kev) if (e) cudaEventDestroy(e);
@@ -2038,6 +2200,15 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "tile_ctas") == 0) {
 		const int n = std::atoi(value);
 		if (n >= 1 && n <= 8) { ctx->tile_ctas = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "scan") == 0) {
+		if (std::strcmp(value, "fused") == 0) { ctx->fused_scan = true; return VO_OK; }
+		if (std::strcmp(value, "classic") == 0) { ctx->fused_scan = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "tile_dbuf") == 0) {
+		if (std::strcmp(value, "auto") == 0) { ctx->tile_dbuf = -1; return VO_OK; }
+		if (std::strcmp(value, "on") == 0) { ctx->tile_dbuf = 1; return VO_OK; }
+		if (std::strcmp(value, "off") == 0) { ctx->tile_dbuf = 0; return VO_OK; }
 	}
 	if (std::strcmp(key, "tile_order") == 0) {
 		if (std::strcmp(value, "off") == 0) { ctx->tile_order = false; return VO_OK; }
@@ -2218,6 +2389,14 @@ int vo_dvol_concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const v
 	if (!ctx || !out) return VO_ERR_ARG;
 	ctx->err.clear();
 	DeviceGuard g(ctx->device);
+	return concat_rows(ctx, a, b, c, out);
+}
+
+} // extern "C"
+
+namespace {
+int concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const vo_dvol *c, vo_dvol **out)
+{
 	const vo_dvol *parts[3] = {a, b, c};
 	int nx = -1, ny = 0;
 	uint64_t total = 0;
@@ -2251,6 +2430,9 @@ int vo_dvol_concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const v
 	*out = r;
 	return VO_OK;
 }
+} // namespace
+
+extern "C" {
 
 int vo_morph3d_dev(vo_ctx *ctx, int op, int method, const vo_dvol *in, double zmin, double zmax, double radius,
                    vo_dvol **out, double *ms_pass1, double *ms_pass2)
@@ -2465,3 +2647,5 @@ int vo_xor3d(vo_ctx *ctx, int nx, int ny, double zmin, double zmax, double spaci
 }
 
 } // extern "C"
+
+#include "vo_mg.cuh"

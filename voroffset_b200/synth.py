@@ -48,6 +48,27 @@ def torus_z(n: int, padding: int = 0, major: float = 1.0, minor: float = 0.35) -
     return _single_interval_volume(vol, (zc - half) / sp, (zc + half) / sp, mask)
 
 
+def torus_z_rows(n: int, y0: int, y1: int, padding: int = 0, major: float = 1.0, minor: float = 0.35) -> CompressedVolume:
+    """Rows [y0, y1) of `torus_z(n, padding)` (a y-slab of a grid sharded over GPUs) without building the whole grid:
+    the same elementwise arithmetic, hence the same bits."""
+    ext = (2 * (major + minor), 2 * (major + minor), 2 * minor)
+    corner = (-(major + minor), -(major + minor), -minor)
+    vol, xs, ys, sp = _grid(ext, n, padding, corner)
+    y0, y1 = max(0, y0), min(vol.ny, y1)
+    X, Y = np.meshgrid(xs + _JX * sp, ys[y0:y1] + _JY * sp)
+    rho = np.sqrt(X * X + Y * Y)
+    d2 = minor * minor - (rho - major) ** 2
+    mask = d2 > 0
+    half = np.sqrt(np.where(mask, d2, 0.0))
+    zc = _JZ * sp
+    cnt = mask.reshape(-1).astype(np.int64)
+    off = np.zeros(cnt.size + 1, dtype=np.int64)
+    np.cumsum(cnt, out=off[1:])
+    lo, hi = (zc - half) / sp, (zc + half) / sp
+    spans = np.stack([lo.reshape(-1)[mask.reshape(-1)], hi.reshape(-1)[mask.reshape(-1)]], axis=1)
+    return vol.like(vol.nx, y1 - y0, off, spans)
+
+
 def torus_x(n: int, padding: int = 0, major: float = 1.0, minor: float = 0.35) -> CompressedVolume:
     """Torus with axis x (up to two intervals per column): config C1 (grid 67 x 256 at n=256)."""
     ext = (2 * minor, 2 * (major + minor), 2 * (major + minor))
