@@ -638,14 +638,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
                                                                double2 *__restrict__ spans, unsigned long long cap,
                                                                unsigned long long *state, unsigned long long *ticket,
                                                                unsigned long long ticket_base, uint32_t epoch,
-                                                               unsigned long long *total_out)
+                                                               unsigned long long *total_out,
+                                                               const unsigned long long *base_in = nullptr)
 {
+	// base_in (optional): the offsets start from *base_in instead of 0 (a band of rows of a larger volume: `spans` and
+	// `cap` are the whole volume's, *total_out = the running total after this band)
 	__shared__ uint32_t s_tile;
 	__shared__ unsigned long long s_prefix;
+	__shared__ uint32_t s_rel[SCAN_TILE + 1];              // offsets of the tile's lists relative to the tile's first
 	if (threadIdx.x == 0) s_tile = (uint32_t)(atomicAdd(ticket, 1ull) - ticket_base);
 	__syncthreads();
 	const uint32_t tile = s_tile;
-	const unsigned long long base = (unsigned long long)tile * SCAN_TILE + (unsigned long long)threadIdx.x * SCAN_ITEMS;
+	const unsigned long long tbase = (unsigned long long)tile * SCAN_TILE, base = tbase + (unsigned long long)threadIdx.x * SCAN_ITEMS;
 	uint32_t c[SCAN_ITEMS];
 	unsigned long long sum = 0;
 #pragma unroll
@@ -655,11 +659,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
 		sum += c[i];
 	}
 	unsigned long long tot;
-	unsigned long long ex = block_excl_scan(sum, &tot);
+	const unsigned long long exl = block_excl_scan(sum, &tot);
 	volatile unsigned long long *vstate = state;
 	if (threadIdx.x == 0) {
 		vstate[tile] = scan_word(tot, epoch, tile == 0 ? SCAN_INCL : SCAN_AGG);
 		if (tile == 0) s_prefix = 0;
+	}
+	{
+		uint32_t r = (uint32_t)exl;
+#pragma unroll
+		for (int i = 0; i < SCAN_ITEMS; ++i) { s_rel[threadIdx.x * SCAN_ITEMS + i] = r; r += c[i]; }
+		if (threadIdx.x == blockDim.x - 1) s_rel[SCAN_TILE] = r;
 	}
 	if (tile > 0 && threadIdx.x < 32) {
 		const unsigned long long excl = scan_look_back(vstate, tile, epoch);
@@ -669,18 +679,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
 		}
 	}
 	__syncthreads();
-	ex += s_prefix;
-	if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {          // the last ticket is the last tile: its end is the grand total
-		const unsigned long long total = ex + sum;
-		off[nlists] = (uint32_t)total;
-		*total_out = total;
+	const unsigned long long first = s_prefix + (base_in ? *base_in : 0ull);    // global offset of the tile's first list
+	if (tile == gridDim.x - 1 && threadIdx.x == 0) {          // the last ticket is the last tile: its end is the grand total
+		off[nlists] = (uint32_t)(first + tot);
+		*total_out = first + tot;
 	}
+	// lists of the tile by stride: neighbouring threads take neighbouring lists (coalesced, SCAN_ITEMS independent copies
+	// in flight per thread)
 #pragma unroll
 	for (int i = 0; i < SCAN_ITEMS; ++i) {
-		const unsigned long long k = base + i;
+		const int j = i * SCAN_THREADS + (int)threadIdx.x;
+		const unsigned long long k = tbase + j;
 		if (k >= nlists) break;
+		const unsigned long long ex = first + s_rel[j];
+		const uint32_t n = s_rel[j + 1] - s_rel[j];
 		off[k] = (uint32_t)ex;
-		const uint32_t n = c[i];
 		if (n && ex + n <= cap) {
 			double2 *dst = spans + ex;
 			if (n <= STAGE_INLINE) {
@@ -691,7 +704,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
 					for (uint32_t q = 0; q < n; ++q) dst[q] = st.pool[pb + q];
 			}
 		}
-		ex += n;
 	}
 }
 
@@ -862,24 +874,34 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_complement_fused(typename Op::
 {
 	__shared__ uint32_t s_tile;
 	__shared__ unsigned long long s_prefix;
+	__shared__ uint32_t s_n[CF_TILE];                       // counts, then offsets relative to the tile's first column
 	if (threadIdx.x == 0) s_tile = (uint32_t)(atomicAdd(ticket, 1ull) - ticket_base);
 	__syncthreads();
 	const uint32_t tile = s_tile;
-	const unsigned long long base = (unsigned long long)tile * CF_TILE + (unsigned long long)threadIdx.x * CF_ITEMS;
+	const unsigned long long tbase = (unsigned long long)tile * CF_TILE;
+	// counts by stride (neighbouring threads read neighbouring columns), scanned in column order
+#pragma unroll
+	for (int i = 0; i < CF_ITEMS; ++i) {
+		const int j = i * SCAN_THREADS + (int)threadIdx.x;
+		const unsigned long long c = tbase + j;
+		s_n[j] = c < nlists ? Op::count(a, c) : 0u;
+	}
+	__syncthreads();
 	uint32_t n[CF_ITEMS];
 	unsigned long long sum = 0;
 #pragma unroll
-	for (int i = 0; i < CF_ITEMS; ++i) {
-		const unsigned long long c = base + i;
-		n[i] = c < nlists ? Op::count(a, c) : 0u;
-		sum += n[i];
-	}
+	for (int i = 0; i < CF_ITEMS; ++i) { n[i] = s_n[threadIdx.x * CF_ITEMS + i]; sum += n[i]; }
 	unsigned long long tot;
-	unsigned long long ex = block_excl_scan(sum, &tot);
+	const unsigned long long exl = block_excl_scan(sum, &tot);
 	volatile unsigned long long *vstate = state;
 	if (threadIdx.x == 0) {
 		vstate[tile] = scan_word(tot, epoch, tile == 0 ? SCAN_INCL : SCAN_AGG);
 		if (tile == 0) s_prefix = 0;
+	}
+	{
+		uint32_t r = (uint32_t)exl;
+#pragma unroll
+		for (int i = 0; i < CF_ITEMS; ++i) { s_n[threadIdx.x * CF_ITEMS + i] = r; r += n[i]; }
 	}
 	if (tile > 0 && threadIdx.x < 32) {
 		const unsigned long long excl = scan_look_back(vstate, tile, epoch);
@@ -889,18 +911,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_complement_fused(typename Op::
 		}
 	}
 	__syncthreads();
-	ex += s_prefix;
-	if (tile == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
-		off[nlists] = (uint32_t)(ex + sum);
-		*total_out = ex + sum;
+	const unsigned long long first = s_prefix;
+	if (tile == gridDim.x - 1 && threadIdx.x == 0) {
+		off[nlists] = (uint32_t)(first + tot);
+		*total_out = first + tot;
 	}
 #pragma unroll
 	for (int i = 0; i < CF_ITEMS; ++i) {
-		const unsigned long long c = base + i;
+		const int j = i * SCAN_THREADS + (int)threadIdx.x;
+		const unsigned long long c = tbase + j;
 		if (c >= nlists) break;
+		const unsigned long long ex = first + s_n[j];
+		const uint32_t cnt = (j + 1 < CF_TILE ? s_n[j + 1] : (uint32_t)tot) - s_n[j];
 		off[c] = (uint32_t)ex;
-		if (n[i] && ex + n[i] <= cap) Op::fill(a, c, spans + ex);
-		ex += n[i];
+		if (cnt && ex + cnt <= cap) Op::fill(a, c, spans + ex);
 	}
 }
 

@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(256) k_order_place(OrderArgs a)
 struct Pass1TileArgs {
 	int nx, ny, J, cmax;
 	int dbuf = 1;           // candidates double-buffered (pass1_warp_smem)
+	int lean = 0;           // candidates and thresholds stay in global memory (pass1_warp_smem)
 	int tiles_xw;           // tiles (P1_W columns) per row
 	int tiles_x;            // tile masks (P1_TX columns) per row
 	unsigned int tile0, ntiles;         // tiles [tile0, tile0 + ntiles0) and [tile0b, tile0b + ntiles - ntiles0) when `tiles` is NULL
@@ -438,14 +439,20 @@ __host__ __device__ inline size_t pass1_table_smem(int J)
 	return b;
 }
 // dbuf: the candidates are double-buffered (the next tile is staged while the current one is in phase 2). Large buffers
-// (dense columns: lattices, erosion's complement) take one: 34 instead of 52 bytes per candidate, i.e. half again as many
+// (dense columns: erosion's complement) take one: 34 instead of 52 bytes per candidate, i.e. half again as many
 // warps per SM, against ~1.5 us of exposed copy latency per tile - tiles that large take tens of microseconds.
-__host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap, bool dbuf = true)
+// lean: nothing but the segment column and the layer of a candidate (2 bytes) lives in shared memory; phase 1 reads the
+// thresholds from global memory (coalesced, one batch ahead), phase 2 reads the few surviving candidates through L1.
+// Used where the buffers would otherwise leave room for a few warps only (lattices with ten intervals per column: 430
+// candidates per tile on average, far more in some): 2048 candidates cost 4 KB per warp instead of 70-106 KB.
+__host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap, bool dbuf = true, bool lean = false)
 {
-	const size_t SEG = (size_t)P1_W + 2 * J, nb = dbuf ? 2 : 1;
+	const size_t SEG = (size_t)P1_W + 2 * J, nb = (dbuf && !lean) ? 2 : 1;
 	size_t b = 0;
-	b += nb * (size_t)cmax * sizeof(double2);               // candidates
-	b += (size_t)cmax * sizeof(uint4);                      // their thresholds: only read by phase 1, ONE buffer, refilled after it
+	if (!lean) {
+		b += nb * (size_t)cmax * sizeof(double2);           // candidates
+		b += (size_t)cmax * sizeof(uint4);                  // their thresholds: only read by phase 1, ONE buffer, refilled after it
+	}
 	b += 2 * ((SEG + 4) & ~(size_t)3) * sizeof(uint32_t);   // segment offsets (always double-buffered)
 	b += (size_t)P1_W * sizeof(uint32_t);                   // list lengths
 	b += (size_t)lcap * P1_W * sizeof(uint32_t);            // survivor lists [s][lane]
@@ -453,9 +460,9 @@ __host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap, boo
 	b += 2 * sizeof(unsigned long long);                    // mbarriers of the two staging buffers
 	return b;
 }
-__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap, int nwarps, bool dbuf = true)
+__host__ __device__ inline size_t pass1_tile_smem(int J, int cmax, int lcap, int nwarps, bool dbuf = true, bool lean = false)
 {
-	return pass1_table_smem(J) + (size_t)nwarps * pass1_warp_smem(J, cmax, lcap, dbuf) + 32;
+	return pass1_table_smem(J) + (size_t)nwarps * pass1_warp_smem(J, cmax, lcap, dbuf, lean) + 32;
 }
 
 // Pool space for `n` entries, one atomic per converged group of threads instead of one per thread.
@@ -501,13 +508,13 @@ struct WarpSmem {
 	uint32_t *off[2], *cnt, *list;
 	uint8_t *ci[2], *ly[2];
 	unsigned long long *mbar;      // [2]
-	__device__ __forceinline__ WarpSmem(unsigned char *raw, int J, int cmax, int lcap, bool dbuf)
+	__device__ __forceinline__ WarpSmem(unsigned char *raw, int J, int cmax, int lcap, bool dbuf, bool lean)
 	{
 		const int SEG = P1_W + 2 * J, c16 = (cmax + 15) & ~15;
 		cand[0] = reinterpret_cast<double2 *>(raw);
 		cand[1] = dbuf ? cand[0] + cmax : cand[0];          // (single buffer: both names, one array)
 		thr = reinterpret_cast<uint4 *>(cand[1] + cmax);
-		off[0] = reinterpret_cast<uint32_t *>(thr + cmax);
+		off[0] = lean ? reinterpret_cast<uint32_t *>(raw) : reinterpret_cast<uint32_t *>(thr + cmax);   // (lean: no candidate / threshold arrays)
 		off[1] = off[0] + ((SEG + 4) & ~3);
 		cnt = off[1] + ((SEG + 4) & ~3);
 		list = cnt + P1_W;
@@ -586,9 +593,8 @@ struct Tile {
 	}
 
 	// Phase 1: candidate k appends itself to the lists of the output columns it survives for.
-	__device__ __forceinline__ void scatter(int k, int txe) const
+	__device__ __forceinline__ void scatter(const uint4 th, int k, int txe) const
 	{
-		const uint4 th = thr[k];
 		const int i = (int)ci[k];
 		const int tyu = (int)(th.y & 0xffu) + 1, tyd = (int)((th.y >> 8) & 0xffu) + 1, T = max(tyu, tyd), rx = (int)(th.y >> 24);
 		const float vu = __uint_as_float(th.z), vd = __uint_as_float(th.w);
@@ -935,8 +941,8 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 	for (int i = threadIdx.x; i < JP * pass1_jpp(J); i += blockDim.x) tb.Ht[i] = __ldg(a.Ht + i);
 	for (int i = threadIdx.x; i < JP * (JP + 1); i += blockDim.x) tb.Ef[i] = __ldg(a.Ef + i);
 	for (int i = threadIdx.x; i < JP + 1; i += blockDim.x) tb.jmax[i] = __ldg(a.jmax + i);
-	const bool dbuf = a.dbuf != 0;
-	const WarpSmem sm(smem_raw + pass1_table_smem(J) + (size_t)warp * pass1_warp_smem(J, a.cmax, LCAP, dbuf), J, a.cmax, LCAP, dbuf);
+	const bool lean = LIST && a.lean != 0, dbuf = a.dbuf != 0 && !lean;
+	const WarpSmem sm(smem_raw + pass1_table_smem(J) + (size_t)warp * pass1_warp_smem(J, a.cmax, LCAP, dbuf, lean), J, a.cmax, LCAP, dbuf, lean);
 	sm.cnt[lane] = 0;
 	if (lane == 0) {
 		mbar_init(sm.mbar + 0, 1); mbar_init(sm.mbar + 1, 1);
@@ -984,7 +990,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 	};
 	// start the staging of a NORMAL tile into buffer b: bulk copies by one lane, the column map by all
 	auto stage = [&](const TileHead &h, int b) {
-		if (lane == 0) {
+		if (lane == 0 && !lean) {
 			const unsigned int bytes = (unsigned int)h.ncand * 16u;
 			mbar_expect_tx(sm.mbar + b, 2u * bytes);
 			bulk_g2s(sm.cand[b], a.spans + h.base, bytes, sm.mbar + b);
@@ -1021,10 +1027,22 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 		// ---- current tile, phase 1 ----
 		const long long dbg_t0 = a.dbg ? clock64() : 0;
 		if (cur.kind == TK_NORMAL) {
-			mbar_wait(sm.mbar + buf, phase[buf]);            // candidates and thresholds have landed
-			phase[buf] ^= 1u;
-			tl.cand = sm.cand[buf]; tl.thr = sm.thr; tl.gthr = a.thr + cur.base; tl.ci = sm.ci[buf]; tl.ly = sm.ly[buf];
-			for (int k = lane; k < cur.ncand; k += 32) tl.scatter(k, cur.txe);
+			tl.gthr = a.thr + cur.base; tl.ci = sm.ci[buf]; tl.ly = sm.ly[buf];
+			if (!lean) {
+				mbar_wait(sm.mbar + buf, phase[buf]);        // candidates and thresholds have landed
+				phase[buf] ^= 1u;
+				tl.cand = sm.cand[buf]; tl.thr = sm.thr;
+				for (int k = lane; k < cur.ncand; k += 32) tl.scatter(sm.thr[k], k, cur.txe);
+			} else {
+				__syncwarp();                                // (the column map of this tile, written by all lanes)
+				tl.cand = a.spans + cur.base; tl.thr = tl.gthr;
+				uint4 th = lane < cur.ncand ? __ldg(tl.gthr + lane) : make_uint4(0u, 0u, 0u, 0u);
+				for (int k = lane; k < cur.ncand; k += 32) {     // thresholds one batch ahead of their use
+					const uint4 nx4 = k + 32 < cur.ncand ? __ldg(tl.gthr + k + 32) : make_uint4(0u, 0u, 0u, 0u);
+					tl.scatter(th, k, cur.txe);
+					th = nx4;
+				}
+			}
 		} else tile_other<MULTI>(a, cur);
 
 		// ---- publish the next tile's offsets, start its staging (single candidate buffer: only after phase 2) ----

@@ -54,6 +54,7 @@ struct vo_ctx {
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
 	int tile_dbuf = -1;               // vo_set_option("tile_dbuf", "auto" | "on" | "off"): double-buffered candidate staging of the tile kernel
+	int tile_lean = -1;               // vo_set_option("tile_lean", "auto" | "on" | "off"): candidates of the list launches left in global memory
 	int band_split = 2;               // vo_set_option("band_split", "N"): a band's pass-1 launch set takes 1/N of the SMs (host-buffer pipeline)
 	int pipe_warps = 64;              // vo_set_option("pipe_warps", "N"): warps per tile-kernel CTA in the host-buffer pipeline (default: as many as fit)
 	int band_free = 0;                // vo_set_option("band_free", "N"): SMs no pass-1 launch set of the pipeline takes (room for its small kernels and pass 2)
@@ -399,17 +400,26 @@ int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
 constexpr unsigned int REDO_GRID = 148 * 4;
 
 // tile state of k_scan_compact for `ntiles` tiles: grown when needed, cleared when grown and when the epoch wraps
+// (growing and the epoch wrap clear the array and wait for that: rare, and other streams may use it next)
+int scan_reserve(vo_ctx *ctx, unsigned int ntiles)
+{
+	if (ctx->scan_cap >= ntiles) return VO_OK;
+	if (ctx->scan_state) { cudaDeviceSynchronize(); cudaFree(ctx->scan_state); ctx->scan_state = nullptr; ctx->scan_cap = 0; }
+	const size_t cap = std::max<size_t>(2 * (size_t)ntiles, 4096);
+	VO_CUDA(cudaMalloc((void **)&ctx->scan_state, (cap + 1) * sizeof(unsigned long long)));
+	VO_CUDA(cudaMemsetAsync(ctx->scan_state, 0, (cap + 1) * sizeof(unsigned long long), ctx->stream));
+	VO_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->scan_cap = cap; ctx->scan_ticket = 0; ctx->scan_epoch = 0;
+	return VO_OK;
+}
+
 int scan_prepare(vo_ctx *ctx, unsigned int ntiles, uint32_t *epoch, unsigned long long *ticket_base)
 {
-	if (ctx->scan_cap < ntiles) {
-		if (ctx->scan_state) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->scan_state); ctx->scan_state = nullptr; }
-		const size_t cap = std::max<size_t>(2 * (size_t)ntiles, 4096);
-		VO_CUDA(cudaMalloc((void **)&ctx->scan_state, (cap + 1) * sizeof(unsigned long long)));
-		VO_CUDA(cudaMemsetAsync(ctx->scan_state, 0, (cap + 1) * sizeof(unsigned long long), ctx->stream));
-		ctx->scan_cap = cap; ctx->scan_ticket = 0; ctx->scan_epoch = 0;
-	}
+	if (ntiles == 0) { *epoch = 0; *ticket_base = ctx->scan_ticket; return VO_OK; }
+	VO_TRY(scan_reserve(ctx, ntiles));
 	if (++ctx->scan_epoch >= (1u << SCAN_EPOCH_BITS)) {
 		VO_CUDA(cudaMemsetAsync(ctx->scan_state, 0, ctx->scan_cap * sizeof(unsigned long long), ctx->stream));
+		VO_CUDA(cudaStreamSynchronize(ctx->stream));
 		ctx->scan_epoch = 1;
 	}
 	*epoch = ctx->scan_epoch;
@@ -425,7 +435,9 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	StageBuf sb(ctx);
 	RedoBuf rb(ctx);
 	// (the last call's need is the best guess for repeated calls on similar data: no second gather)
-	VO_TRY(sb.alloc(nlists, std::max(pool_guess, std::min(ctx->stage_hint, 4 * nlists + 65536ull))));
+	// (bounded by what the lists can need at most - CAP_BIG intervals each - not by a guess: dense volumes, ten intervals
+	// per column, used to run every gather three times because the hint was cut to four per list)
+	VO_TRY(sb.alloc(nlists, std::max(pool_guess, std::min(ctx->stage_hint, (unsigned long long)CAP_BIG * nlists + 65536ull))));
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nlists, 1ull), 1ull << 22);
 	VO_TRY(rb.alloc(redo_cap, 8));
 	vo_dvol *v = nullptr;
@@ -660,6 +672,7 @@ struct TilePlan {
 	int cmax_small = 0, cmax_big = 0, cmax_multi = 0;
 	int nw_small = 1, nw_big = 1, nw_multi = 1, nw_bigmulti = 1;
 	bool db_small = true, db_big = true, db_multi = true, db_bigmulti = false;   // candidates double-buffered (pass1_warp_smem)
+	bool lean_big = false, lean_multi = false, lean_bigmulti = false;             // ... or left in global memory
 	size_t smem_bigmulti = 0;
 	size_t smem_small = 0, smem_big = 0, smem_multi = 0;
 	static constexpr int CMAX = 2048;       // largest candidate buffer (11-bit candidate ids in the survivor lists)
@@ -690,22 +703,31 @@ struct TilePlan {
 		// when its last warp is done
 		cps = std::max(1, std::min(ctx->tile_ctas, 8));
 		const size_t budget = std::min<size_t>(220 * 1024, 228 * 1024 / cps - 1024 - 256);
-		auto warps = [&](int cmax, int lcap, int maxw, bool dbuf) {
-			const size_t per = pass1_warp_smem(J, cmax, lcap, dbuf), tab = pass1_table_smem(J) + 32;
+		auto warps = [&](int cmax, int lcap, int maxw, bool dbuf, bool lean) {
+			const size_t per = pass1_warp_smem(J, cmax, lcap, dbuf, lean), tab = pass1_table_smem(J) + 32;
 			if (budget < tab + per) return 1;
 			return (int)std::max<size_t>(1, std::min<size_t>(std::min(maxw, warps_cap) / cps, (budget - tab) / per));
 		};
-		// double-buffered candidates where that still leaves room for every warp the registers allow, one buffer otherwise
-		auto plan = [&](int cmax, int lcap, int maxw, int &nw, bool &db, size_t &smem) {
+		// The staging of a launch, in order of preference: double-buffered candidates in shared memory where that still
+		// leaves room for every warp the registers allow, one buffer otherwise, and for the launches that pull tiles from a
+		// list (may_lean) nothing but the column map when even that costs warps.
+		auto plan = [&](int cmax, int lcap, int maxw, bool may_lean, int &nw, bool &db, bool &lean, size_t &smem) {
 			const int want = std::max(1, std::min(maxw, warps_cap) / cps);
-			db = ctx->tile_dbuf > 0 || (ctx->tile_dbuf < 0 && warps(cmax, lcap, maxw, true) >= want);
-			nw = warps(cmax, lcap, maxw, db);
-			smem = pass1_tile_smem(J, cmax, lcap, nw, db);
+			lean = false;
+			db = ctx->tile_dbuf > 0 || (ctx->tile_dbuf < 0 && warps(cmax, lcap, maxw, true, false) >= want);
+			if (!db && may_lean && ctx->tile_lean != 0 && (ctx->tile_lean > 0 || warps(cmax, lcap, maxw, false, false) < want)) lean = true;
+			nw = warps(cmax, lcap, maxw, db, lean);
+			smem = pass1_tile_smem(J, cmax, lcap, nw, db, lean);
 		};
-		plan(cmax_small, P1_LCAP_S, P1_MAXWARPS, nw_small, db_small, smem_small);
-		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS, nw_big, db_big, smem_big);
-		plan(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M, nw_multi, db_multi, smem_multi);
-		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS_M, nw_bigmulti, db_bigmulti, smem_bigmulti);   // launch 4: the multi-interval tiles beyond cmax_multi
+		bool dummy = false;
+		plan(cmax_small, P1_LCAP_S, P1_MAXWARPS, false, nw_small, db_small, dummy, smem_small);
+		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS, true, nw_big, db_big, lean_big, smem_big);
+		plan(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M, true, nw_multi, db_multi, lean_multi, smem_multi);
+		if (lean_multi) {                // lean costs the same whatever the capacity: one launch for every multi-interval tile
+			cmax_multi = cmax_big;
+			plan(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M, true, nw_multi, db_multi, lean_multi, smem_multi);
+		}
+		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS_M, true, nw_bigmulti, db_bigmulti, lean_bigmulti, smem_bigmulti);   // launch 4: the multi-interval tiles beyond cmax_multi
 		cudaError_t e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_multi, smem_bigmulti));
@@ -733,13 +755,13 @@ struct TilePlan {
 		// the tile counter does not mind)
 		auto grid = [&](int nw) { return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)(sms * cps), (ntiles + nw - 1) / nw)); };
 		// launch 1: single-interval tiles, small candidate buffer
-		g.cmax = cmax_small; g.dbuf = db_small; g.tiles = nullptr; g.tiles_count = nullptr; g.order = order;
+		g.cmax = cmax_small; g.dbuf = db_small; g.lean = 0; g.tiles = nullptr; g.tiles_count = nullptr; g.order = order;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 10);
 		g.big_tiles = cmax_small < cmax_big ? big_tiles : nullptr;
 		k_pass1_tile<CAP_FAST, false, false><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
 		ctx->launches++;
 		if (cmax_small < cmax_big) {    // launch 2: the single-interval tiles that need the large buffer
-			g.cmax = cmax_big; g.dbuf = db_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
+			g.cmax = cmax_big; g.dbuf = db_big; g.lean = lean_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 6);
 			k_pass1_tile<CAP_FAST, false, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
 			ctx->launches++;
@@ -748,13 +770,13 @@ struct TilePlan {
 		// the tiles beyond it are collected again (in big_tiles, which launch 2 is done with) for launch 4
 		unsigned int *bigmulti_count = reinterpret_cast<unsigned int *>(bank + 12);
 		const bool four = cmax_multi < cmax_big;
-		g.cmax = cmax_multi; g.dbuf = db_multi; g.tiles = multi_tiles; g.tiles_count = multi_count;
+		g.cmax = cmax_multi; g.dbuf = db_multi; g.lean = lean_multi; g.tiles = multi_tiles; g.tiles_count = multi_count;
 		g.big_tiles = four ? big_tiles : nullptr; g.big_count = bigmulti_count;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 7);
 		k_pass1_tile<CAP_FAST, true, true><<<grid(nw_multi), 32 * nw_multi, smem_multi, s>>>(g);
 		ctx->launches++;
 		if (four) {                     // launch 4: the largest buffer; whatever exceeds that goes to the redo list
-			g.cmax = cmax_big; g.dbuf = db_bigmulti; g.tiles = big_tiles; g.tiles_count = bigmulti_count; g.big_tiles = nullptr;
+			g.cmax = cmax_big; g.dbuf = db_bigmulti; g.lean = lean_bigmulti; g.tiles = big_tiles; g.tiles_count = bigmulti_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 13);
 			k_pass1_tile<CAP_FAST, true, true><<<grid(nw_bigmulti), 32 * nw_bigmulti, smem_bigmulti, s>>>(g);
 			ctx->launches++;
@@ -1615,6 +1637,19 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	struct Join { vo_ctx *c; ~Join() { for (auto st : c->s_hi) cudaStreamSynchronize(st); cudaStreamSynchronize(c->s_ctl); for (auto st : c->s_p) cudaStreamSynchronize(st); } } join{ctx};
 
 	std::vector<cudaEvent_t> ev_tot(nb);
+	// single-pass scan + compaction per band: tile state reserved up front (no allocation between the launches)
+	const bool fused = ctx->fused_scan;
+	std::vector<uint32_t> scan_epoch(nb, 0u);
+	std::vector<unsigned long long> scan_tbase(nb, 0ull);
+	if (fused) {
+		unsigned int most = 1;
+		for (int b = 0; b < nb; ++b) most = std::max(most, blocks_for((unsigned long long)nx * (ys2[b + 1] - ys2[b]), SCAN_TILE));
+		VO_TRY(scan_reserve(ctx, most));
+		for (int b = 0; b < nb; ++b) {
+			const unsigned int nt = blocks_for((unsigned long long)nx * (ys2[b + 1] - ys2[b]), SCAN_TILE);
+			VO_TRY(scan_prepare(ctx, nt, &scan_epoch[b], &scan_tbase[b]));
+		}
+	}
 	auto second_half = [&](int b) {
 		const int y0 = ys2[b], y1 = ys2[b + 1];
 		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
@@ -1633,14 +1668,25 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		a2.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
 		k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
-		k_scan_reduce<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b);
-		if (b > 0) cudaStreamWaitEvent(sm, ev_scan[b - 1], 0);
-		k_scan_tiles<<<1, 1024, 0, sm>>>(sums_b, nt, gb.p + b, gb.p + b + 1);
-		ev_scan[b] = pr.event();
-		cudaEventRecord(ev_scan[b], sm);
-		k_scan_apply<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b, dout->off + c0);
-		k_compact<<<blocks_for(nlists, 256), 256, 0, sm>>>(st, nlists, dout->off + c0, dout->spans, dcap);
-		ctx->launches += 6;
+		if (fused) {
+			// ONE kernel: offsets (from the running total gb[b] of the bands before) and spans of the band; the bands'
+			// kernels follow one another (the running total is a chain anyway, and each takes a few microseconds)
+			if (b > 0) cudaStreamWaitEvent(sm, ev_scan[b - 1], 0);
+			k_scan_compact<<<nt, SCAN_THREADS, 0, sm>>>(st, nlists, dout->off + c0, dout->spans, dcap, ctx->scan_state,
+			                                            ctx->scan_state + ctx->scan_cap, scan_tbase[b], scan_epoch[b], gb.p + b + 1, gb.p + b);
+			ev_scan[b] = pr.event();
+			cudaEventRecord(ev_scan[b], sm);
+			ctx->launches += 3;
+		} else {
+			k_scan_reduce<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b);
+			if (b > 0) cudaStreamWaitEvent(sm, ev_scan[b - 1], 0);
+			k_scan_tiles<<<1, 1024, 0, sm>>>(sums_b, nt, gb.p + b, gb.p + b + 1);
+			ev_scan[b] = pr.event();
+			cudaEventRecord(ev_scan[b], sm);
+			k_scan_apply<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b, dout->off + c0);
+			k_compact<<<blocks_for(nlists, 256), 256, 0, sm>>>(st, nlists, dout->off + c0, dout->spans, dcap);
+			ctx->launches += 6;
+		}
 		cudaEventRecord(ev_done[b], sm);
 		mark("pass2 end", b, sm);
 		cudaStreamWaitEvent(ctx->s_ctl, ev_done[b], 0);
@@ -2204,6 +2250,11 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "scan") == 0) {
 		if (std::strcmp(value, "fused") == 0) { ctx->fused_scan = true; return VO_OK; }
 		if (std::strcmp(value, "classic") == 0) { ctx->fused_scan = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "tile_lean") == 0) {
+		if (std::strcmp(value, "auto") == 0) { ctx->tile_lean = -1; return VO_OK; }
+		if (std::strcmp(value, "on") == 0) { ctx->tile_lean = 1; return VO_OK; }
+		if (std::strcmp(value, "off") == 0) { ctx->tile_lean = 0; return VO_OK; }
 	}
 	if (std::strcmp(key, "tile_dbuf") == 0) {
 		if (std::strcmp(value, "auto") == 0) { ctx->tile_dbuf = -1; return VO_OK; }
