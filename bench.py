@@ -404,9 +404,15 @@ def main():
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
     nseg = w["nseg"]
 
+    def drop_scratch_cache():
+        """Scratch blocks the library keeps for reuse: drop them between workloads of very different size,
+        so that the multi-GB blocks of the 8192^2 grid are not released in the middle of a later timed step."""
+        ctx.set_option("block_cache", "off")
+        ctx.set_option("block_cache", "on")
+
     extras = {}
     if not a.no_extras:
-        xs, xw = max(3, a.steps // 2), 2
+        xs, xw = max(3, a.steps // 2), 3
         # ---- strong: BASELINE config 5 as written - ONE n x n grid over the N GPUs --------------------------------
         if world > 1 and a.n // world >= J:
             y0, y1 = slab.slab_bounds(a.n, world)[rank]
@@ -450,6 +456,7 @@ def main():
                 extras["strong_large"]["slab_parity"] = parity["strong_large"]
             d_own.free()
             del own
+            drop_scratch_cache()
         # ---- the other operations of the target on the config-5 grid (padding 34 = head-room for the composites) ----
         pad = J + 2
         full = synth.torus_z(a.n, padding=pad)

@@ -7,7 +7,8 @@ import csv, io, os, re, subprocess, sys, tempfile, collections
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "voroffset_b200", "libvoroffset_b200.so")
+so = os.environ.get("VO_SO", os.path.join(root, "voroffset_b200", "libvoroffset_b200.so"))     # the build the capture was taken with
+srcdir = os.environ.get("VO_SRC", os.path.join(root, "voroffset_b200", "csrc"))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -32,6 +33,8 @@ rows = list(csv.reader(io.StringIO(raw)))
 want = os.environ.get("NCU_KERNEL", "")
 starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
 pick = next((i for i in starts if want in rows[i][1]), starts[0])
+if os.environ.get("NCU_INDEX"):          # ... or the n-th profiled launch of the capture (template arguments are not in the name)
+    pick = starts[int(os.environ["NCU_INDEX"])]
 nxt = next((i for i in starts if i > pick), len(rows))
 rows = rows[pick:nxt]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
@@ -50,7 +53,7 @@ src = {}
 print(f"total: samples {tot[0]}  warp-inst {tot[1]}  thread-inst {tot[2]}")
 print(f"{'file:line':28s} {'samples%':>8s} {'inst%':>7s} {'thr/warp':>8s}  source")
 for loc, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    f = os.path.join(root, "voroffset_b200", "csrc", loc[0])
+    f = os.path.join(srcdir, loc[0])
     if loc[0] not in src:
         try: src[loc[0]] = open(f).read().splitlines()
         except Exception: src[loc[0]] = []

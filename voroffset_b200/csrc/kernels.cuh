@@ -59,7 +59,7 @@ __device__ __forceinline__ void stage_emit(const Stage &st, size_t c, const RunU
 	} else {
 		unsigned long long base = atomicAdd(st.cursor, (unsigned long long)u.n);
 		if (base + u.n <= st.pool_cap)
-			for (int k = 0; k < u.n; ++k) st.pool[base + k] = u.L[k];
+			for (int k = 0; k < u.n; ++k) st.pool[base + k] = u.get(k);
 		st.inl[c * STAGE_INLINE] = slot_pool(base, (unsigned int)u.n);
 	}
 }
@@ -132,7 +132,7 @@ __device__ __forceinline__ void pass1_item(const Pass1Args &a, unsigned long lon
 	else {
 		unsigned long long base = atomicAdd(a.cursor, (unsigned long long)u.n);
 		if (base + u.n <= a.pool_cap)
-			for (int k = 0; k < u.n; ++k) a.pool[base + k] = u.L[k];
+			for (int k = 0; k < u.n; ++k) a.pool[base + k] = u.get(k);
 		out = slot_pool(base, (unsigned int)u.n);
 	}
 	a.mid[slot] = out;
@@ -634,6 +634,7 @@ __global__ void __launch_bounds__(256) k_compact(Stage st, unsigned long long nl
 
 // Staged lists -> canonical CSR in ONE launch (scan.cuh: decoupled look-back): offsets of every list, off[nlists] and
 // *total_out = grand total, spans copied where the list ends inside `cap` intervals.
+template <int ITEMS>                                    // lists per thread: 8 for millions of lists, 2 when that would leave SMs without a tile
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigned long long nlists, uint32_t *__restrict__ off,
                                                                double2 *__restrict__ spans, unsigned long long cap,
                                                                unsigned long long *state, unsigned long long *ticket,
@@ -643,17 +644,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
 {
 	// base_in (optional): the offsets start from *base_in instead of 0 (a band of rows of a larger volume: `spans` and
 	// `cap` are the whole volume's, *total_out = the running total after this band)
+	constexpr int TILE = SCAN_THREADS * ITEMS;
 	__shared__ uint32_t s_tile;
 	__shared__ unsigned long long s_prefix;
-	__shared__ uint32_t s_rel[SCAN_TILE + 1];              // offsets of the tile's lists relative to the tile's first
+	__shared__ uint32_t s_rel[TILE + 1];              // offsets of the tile's lists relative to the tile's first
 	if (threadIdx.x == 0) s_tile = (uint32_t)(atomicAdd(ticket, 1ull) - ticket_base);
 	__syncthreads();
 	const uint32_t tile = s_tile;
-	const unsigned long long tbase = (unsigned long long)tile * SCAN_TILE, base = tbase + (unsigned long long)threadIdx.x * SCAN_ITEMS;
-	uint32_t c[SCAN_ITEMS];
+	const unsigned long long tbase = (unsigned long long)tile * TILE, base = tbase + (unsigned long long)threadIdx.x * ITEMS;
+	uint32_t c[ITEMS];
 	unsigned long long sum = 0;
 #pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; ++i) {
+	for (int i = 0; i < ITEMS; ++i) {
 		const unsigned long long k = base + i;
 		c[i] = k < nlists ? st.cnt[k] : 0u;
 		sum += c[i];
@@ -668,8 +670,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
 	{
 		uint32_t r = (uint32_t)exl;
 #pragma unroll
-		for (int i = 0; i < SCAN_ITEMS; ++i) { s_rel[threadIdx.x * SCAN_ITEMS + i] = r; r += c[i]; }
-		if (threadIdx.x == blockDim.x - 1) s_rel[SCAN_TILE] = r;
+		for (int i = 0; i < ITEMS; ++i) { s_rel[threadIdx.x * ITEMS + i] = r; r += c[i]; }
+		if (threadIdx.x == blockDim.x - 1) s_rel[TILE] = r;
 	}
 	if (tile > 0 && threadIdx.x < 32) {
 		const unsigned long long excl = scan_look_back(vstate, tile, epoch);
@@ -684,10 +686,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
 		off[nlists] = (uint32_t)(first + tot);
 		*total_out = first + tot;
 	}
-	// lists of the tile by stride: neighbouring threads take neighbouring lists (coalesced, SCAN_ITEMS independent copies
+	// lists of the tile by stride: neighbouring threads take neighbouring lists (coalesced, ITEMS independent copies
 	// in flight per thread)
 #pragma unroll
-	for (int i = 0; i < SCAN_ITEMS; ++i) {
+	for (int i = 0; i < ITEMS; ++i) {
 		const int j = i * SCAN_THREADS + (int)threadIdx.x;
 		const unsigned long long k = tbase + j;
 		if (k >= nlists) break;

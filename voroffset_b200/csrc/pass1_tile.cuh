@@ -714,7 +714,7 @@ __device__ __noinline__ double2 class_general(const Pass1TileArgs &a, const Tile
 	if (u.n == 1) return make_double2(u.s0, u.e0);
 	const unsigned long long pb = atomicAdd(a.cursor, (unsigned long long)u.n);
 	if (pb + u.n <= a.pool_cap)
-		for (int q = 0; q < u.n; ++q) a.pool[pb + q] = u.L[q];
+		for (int q = 0; q < u.n; ++q) a.pool[pb + q] = u.get(q);
 	return slot_pool(pb, (unsigned int)u.n);
 }
 

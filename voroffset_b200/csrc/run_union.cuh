@@ -37,7 +37,7 @@ __device__ __forceinline__ unsigned int slot_pool_count(double2 s)
 	return (unsigned int)__double_as_longlong(s.y);
 }
 
-// Slow path of the running union: insert [s, e] into the sorted disjoint list L[0..n) (n >= 2).
+// Slow path of the running union: insert [s, e] into the sorted disjoint list L[0..n) (n >= 3).
 // Returns the new length, or -1 when the list would outgrow CAP. Kept out of line (and free of any
 // reference to the caller's scalar state) so that the fast-path state stays in registers.
 template <int CAP>
@@ -68,21 +68,26 @@ __device__ __noinline__ int run_union_insert_list(double2 *L, int n, double s, d
 	return n;
 }
 
-// Sorted disjoint closed intervals. One interval lives in registers (the overwhelmingly common case for
-// smooth solids); from two on the list lives in the caller-provided array L (local memory). The struct
-// only holds scalars and a pointer, so it is scalar-replaced into registers.
+// Sorted disjoint closed intervals. Up to TWO intervals live in registers - one is the overwhelmingly common case
+// for smooth solids, two is what every column of an erosion's complement holds (a part below and a part above the
+// solid) and what shells give; from three on the list lives in the caller-provided array L (local memory). The
+// struct only holds scalars and a pointer, so it is scalar-replaced into registers.
 template <int CAP>
 struct RunUnion {
-	double s0, e0;
+	double s0, e0, s1, e1;          // n == 1: (s0, e0); n == 2: (s0, e0) < (s1, e1)
 	int n;
 	bool overflow;
-	double2 *L;
+	double2 *L;                     // valid for n >= 3 only: read through get()
 
-	__device__ __forceinline__ explicit RunUnion(double2 *list) : s0(0), e0(0), n(0), overflow(false), L(list) {}
+	__device__ __forceinline__ explicit RunUnion(double2 *list) : s0(0), e0(0), s1(0), e1(0), n(0), overflow(false), L(list) {}
 
 	__device__ __forceinline__ void init() { n = 0; overflow = false; }
 
-	__device__ __forceinline__ double2 get(int k) const { return n == 1 ? make_double2(s0, e0) : L[k]; }
+	__device__ __forceinline__ double2 get(int k) const
+	{
+		if (n <= 2) return k == 0 ? make_double2(s0, e0) : make_double2(s1, e1);
+		return L[k];
+	}
 
 	__device__ __forceinline__ void insert(double s, double e)
 	{
@@ -93,17 +98,32 @@ struct RunUnion {
 				return;
 			}
 			if (CAP < 2) { overflow = true; return; }
-			if (e < s0) { L[0] = make_double2(s, e); L[1] = make_double2(s0, e0); }
-			else        { L[0] = make_double2(s0, e0); L[1] = make_double2(s, e); }
+			if (e < s0) { s1 = s0; e1 = e0; s0 = s; e0 = e; }
+			else        { s1 = s; e1 = e; }
 			n = 2;
 			return;
 		}
 		if (n == 0) { s0 = s; e0 = e; n = 1; return; }
+		if (n == 2 && s <= e) {            // (an entry with s > e is not an interval: the list path below folds it the way it always has)
+			const bool t0 = s <= e0 && e >= s0, t1 = s <= e1 && e >= s1;
+			if (t0 && t1) { s0 = (s < s0) ? s : s0; e0 = (e > e1) ? e : e1; n = 1; return; }   // bridges the gap
+			if (t0) { s0 = (s < s0) ? s : s0; e0 = (e > e0) ? e : e0; return; }
+			if (t1) { s1 = (s < s1) ? s : s1; e1 = (e > e1) ? e : e1; return; }
+			if (CAP < 3) { overflow = true; return; }
+			// a third component: the list moves to L, sorted
+			const double2 a = make_double2(s0, e0), b = make_double2(s1, e1), c = make_double2(s, e);
+			if (e < s0) { L[0] = c; L[1] = a; L[2] = b; }
+			else if (e < s1) { L[0] = a; L[1] = c; L[2] = b; }
+			else { L[0] = a; L[1] = b; L[2] = c; }
+			n = 3;
+			return;
+		}
 		if (overflow) return;
+		if (n == 2) { L[0] = make_double2(s0, e0); L[1] = make_double2(s1, e1); }
 		const int r = run_union_insert_list<CAP>(L, n, s, e);
 		if (r < 0) { overflow = true; return; }
 		n = r;
-		if (n == 1) { s0 = L[0].x; e0 = L[0].y; }
+		if (n <= 2) { s0 = L[0].x; e0 = L[0].y; if (n == 2) { s1 = L[1].x; e1 = L[1].y; } }
 	}
 };
 

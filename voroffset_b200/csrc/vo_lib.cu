@@ -443,12 +443,14 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	vo_dvol *v = nullptr;
 	VO_TRY(new_dvol(ctx, nx, ny, &v));
 	struct Guard { vo_ctx *c; vo_dvol *&p; ~Guard() { if (p) free_dvol(c, p); } } guard{ctx, v};
-	const unsigned int ntiles = blocks_for(nlists, SCAN_TILE);
+	const bool fused = ctx->fused_scan && nlists > 0;
+	// (small grids: tiles of 512 lists instead of 2048, so that every SM gets some)
+	const bool small_tiles = fused && blocks_for(nlists, SCAN_TILE) < 4 * 148;
+	const unsigned int ntiles = blocks_for(nlists, small_tiles ? SCAN_THREADS * 2 : SCAN_TILE);
 	Tmp<unsigned long long> sums(ctx);
 	VO_TRY(dalloc(ctx, &sums.p, (unsigned long long)ntiles + 1));
 	// fused: the spans buffer exists before the gather (sized from the recent results, at least one interval per list)
 	// and ONE kernel writes offsets and spans; a result that outgrows the buffer is compacted again into an exact one
-	const bool fused = ctx->fused_scan && nlists > 0;
 	unsigned long long out_cap = 0;
 	if (fused) {
 		out_cap = std::min<unsigned long long>(std::max(ctx->out_cap_hint, nlists + 65536ull), (1ull << 32) - 1);
@@ -470,8 +472,12 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 				uint32_t epoch = 0;
 				unsigned long long tbase = 0;
 				VO_TRY(scan_prepare(ctx, ntiles, &epoch, &tbase));
-				k_scan_compact<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
-				                                                         ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles);
+				if (small_tiles)
+					k_scan_compact<2><<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
+					                                                            ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles);
+				else
+					k_scan_compact<SCAN_ITEMS><<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
+					                                                                     ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles);
 				ctx->launches += 3;
 			} else {
 				k_scan_reduce<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p);
@@ -1672,7 +1678,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			// ONE kernel: offsets (from the running total gb[b] of the bands before) and spans of the band; the bands'
 			// kernels follow one another (the running total is a chain anyway, and each takes a few microseconds)
 			if (b > 0) cudaStreamWaitEvent(sm, ev_scan[b - 1], 0);
-			k_scan_compact<<<nt, SCAN_THREADS, 0, sm>>>(st, nlists, dout->off + c0, dout->spans, dcap, ctx->scan_state,
+			k_scan_compact<SCAN_ITEMS><<<nt, SCAN_THREADS, 0, sm>>>(st, nlists, dout->off + c0, dout->spans, dcap, ctx->scan_state,
 			                                            ctx->scan_state + ctx->scan_cap, scan_tbase[b], scan_epoch[b], gb.p + b + 1, gb.p + b);
 			ev_scan[b] = pr.event();
 			cudaEventRecord(ev_scan[b], sm);
