@@ -328,6 +328,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_min(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
     def all_ok(flag):
         t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -366,7 +372,10 @@ def main():
         total = all_max(sum(ms))
         return {"total_ms": total, "ms_per_step": total / steps, "k1": statistics.mean(k1s), "k2": statistics.mean(k2s),
                 "p1": statistics.mean(p1s), "p2": statistics.mean(p2s), "nseg": nseg,
-                "halo_wait_ms": all_max(statistics.mean(hw)) if hw else 0.0, "halo_ms": all_max(statistics.mean(hm)) if hm else 0.0}
+                # (the ranks are not re-synchronised between steps: a rank with one neighbour runs ahead and then waits for
+                # the slower ones, so the MAX over ranks mostly shows that skew and the MIN what the exchange itself costs)
+                "halo_wait_ms": all_max(statistics.mean(hw)) if hw else 0.0, "halo_ms": all_max(statistics.mean(hm)) if hm else 0.0,
+                "halo_wait_ms_min": all_min(statistics.mean(hw)) if hw else 0.0}
 
     def parity_rows(got_dev, ext_host, y_lo, y_hi, opn="dilation"):
         """This rank's multi-GPU rows against the single-GPU operator on `ext_host`, rows [y_lo, y_hi), bit for bit."""
@@ -427,8 +436,8 @@ def main():
             s = timed("dilation", d_own, own, a.steps, a.warmup)
             extras["strong"] = {"grid": [a.n, a.n], "slabs": world, "rows_per_gpu": a.n // world, "ms_per_step": s["ms_per_step"],
                                 "value": a.n * a.n * a.steps / (s["total_ms"] * 1e-3), "unit": UNIT, "steps": a.steps,
-                                "halo_wait_ms": s["halo_wait_ms"], "halo_ms": s["halo_ms"], "pass_ms": {"pass1": s["p1"], "pass2": s["p2"]},
-                                "slab_parity": parity["strong"]}
+                                "halo_wait_ms": s["halo_wait_ms"], "halo_wait_ms_min": s["halo_wait_ms_min"], "halo_ms": s["halo_ms"],
+                                "pass_ms": {"pass1": s["p1"], "pass2": s["p2"]}, "slab_parity": parity["strong"]}
             d_own.free()
         elif world == 1:
             extras["strong"] = {"grid": [a.n, a.n], "slabs": 1, "rows_per_gpu": a.n, "ms_per_step": w["ms_per_step"],
@@ -451,7 +460,8 @@ def main():
             s = timed("dilation", d_own, own, xs, xw)
             extras["strong_large"] = {"grid": [nl, nl], "slabs": world, "rows_per_gpu": nl // world, "ms_per_step": s["ms_per_step"],
                                       "value": nl * nl * xs / (s["total_ms"] * 1e-3), "unit": UNIT, "steps": xs, "warmup": xw,
-                                      "halo_wait_ms": s["halo_wait_ms"], "halo_ms": s["halo_ms"], "pass_ms": {"pass1": s["p1"], "pass2": s["p2"]}}
+                                      "halo_wait_ms": s["halo_wait_ms"], "halo_wait_ms_min": s["halo_wait_ms_min"], "halo_ms": s["halo_ms"],
+                                      "pass_ms": {"pass1": s["p1"], "pass2": s["p2"]}}
             if world > 1:
                 extras["strong_large"]["slab_parity"] = parity["strong_large"]
             d_own.free()
@@ -554,7 +564,8 @@ def main():
                        "timing": "CUDA events on the library stream around each step, summed, max over ranks"},
             "e2e": e2e, "gpu_launches": int(launches),
             "pass_ms": {"pass1": w["p1"], "pass2": w["p2"], "k_pass1": k1, "k_pass2": w["k2"]},
-            "halo": {"halo_wait_ms": w["halo_wait_ms"], "halo_ms": w["halo_ms"]},
+            "halo": {"halo_wait_ms": w["halo_wait_ms"], "halo_wait_ms_min": w["halo_wait_ms_min"], "halo_ms": w["halo_ms"],
+                     "note": "per step: max / min over ranks of the host time stalled until the halos had landed, max of the device time of the NCCL groups"},
             "slab_parity": (all(parity.values()) if parity else None), "slab_parity_checks": parity,
             **extras,
             "roofline": {"bound": "hbm", "kernel": "k_pass1_tile (the three tile launches of pass 1)", "achieved": ach, "peak": peak, "unit": "GB/s",

@@ -13,13 +13,24 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 mg = multigpu.MultiGpu.from_torch_distributed(local)
 ctx = mg.contexts[0]
-full = synth.torus_z(n, padding=int(R) + 2)
-y0, y1 = slab.slab_bounds(full.ny, world)[rank]
-c0, c1 = y0 * full.nx, y1 * full.nx
-off = full.off[c0:c1 + 1].astype("int64")
-own = full.like(full.nx, y1 - y0, (off - off[0]).astype("uint32"), full.spans[off[0]:off[-1]])
+if os.environ.get("VO_SLAB_RESERVE"):
+    ctx.set_option("slab_reserve", os.environ["VO_SLAB_RESERVE"])
+OPS = os.environ.get("VO_OPS", "dilation,erosion,opening,closing").split(",")
+full = synth.torus_z(n, padding=int(R) + 2) if n <= 4096 else None
+if full is None:      # large grids: only this rank's rows are generated
+    import types
+    b = slab.slab_bounds(n, world)[rank]
+    own_rows = synth.torus_z_rows(n, b[0], b[1])
+    full = types.SimpleNamespace(nx=own_rows.nx, ny=n, zmin=own_rows.zmin, zmax=own_rows.zmax)
+if n <= 4096:
+    y0, y1 = slab.slab_bounds(full.ny, world)[rank]
+    c0, c1 = y0 * full.nx, y1 * full.nx
+    off = full.off[c0:c1 + 1].astype("int64")
+    own = full.like(full.nx, y1 - y0, (off - off[0]).astype("uint32"), full.spans[off[0]:off[-1]])
+else:
+    own = own_rows
 d = morpho.DeviceVolume.upload(ctx, own)
-for opn in ("dilation", "erosion", "opening", "closing"):
+for opn in OPS:
     for i in range(steps):
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         t = time.perf_counter()

@@ -60,6 +60,7 @@ struct vo_ctx {
 	int band_free = 0;                // vo_set_option("band_free", "N"): SMs no pass-1 launch set of the pipeline takes (room for its small kernels and pass 2)
 	int pipe_bands = 8;               // vo_set_option("bands", "N"): row bands of the pipelined host-buffer path
 	bool slab_overlap = true;         // vo_set_option("slab", "overlap" | "serial"): pass 1 of the halo-independent rows while the halos travel
+	int slab_reserve = 8;             // vo_set_option("slab_reserve", "N"): SMs the interior launch of a slab step leaves to the NCCL kernels
 	cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-buffer path
 	cudaStream_t s_p[2] = {nullptr, nullptr};       // its two pass-1 streams (consecutive bands overlap)
 	cudaStream_t s_hi[3] = {nullptr, nullptr, nullptr};   // its second-half streams (highest priority): two for alternating bands, one for the pass-1 redo launches
@@ -1978,7 +1979,7 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	// step against 1.39 ms overlapped; a single GPU takes 1.26 ms for the same rows).
 	S->overlapped = ctx->slab_overlap;
 	cudaEventRecord(S->ev_setup, sm);                       // (the side stream of vo_slab_finish starts from here)
-	if (S->overlapped) slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0), 0, 0, 8);
+	if (S->overlapped) slab_pass1_rows(S, jp + (jp ? 1 : 0), jp + ny - (jn ? 1 : 0), 0, 0, std::max(1, ctx->slab_reserve));
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("slab_begin: ") + cudaGetErrorString(e)));
 	*out = S;
@@ -2232,6 +2233,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "slab") == 0) {
 		if (std::strcmp(value, "overlap") == 0) { ctx->slab_overlap = true; return VO_OK; }
 		if (std::strcmp(value, "serial") == 0) { ctx->slab_overlap = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "slab_reserve") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 1 && n <= 96) { ctx->slab_reserve = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "bands") == 0) {
 		const int n = std::atoi(value);
