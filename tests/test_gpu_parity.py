@@ -3,6 +3,8 @@
 Bit-exact for dilation / erosion (both methods) and for every brute_force composite; opening / closing
 of 'ours' are compared with identical topology and |dz| <= util.COMPOSITE_TOL (see tests/util.py).
 """
+import math
+
 import numpy as np
 import pytest
 
@@ -84,6 +86,95 @@ def test_tile_kernel_forced_3d(ctx, oracle, name, gen, radius):
             got, _, _ = morpho.apply_operation(op, opn, vol, radius)
             util.assert_same(got, oracle.morph3d(vol, opn, radius, "ours"), opn, "ours", f"tile kernel vs oracle [{name}]")
     finally:
+        ctx.set_option("pass1", "auto")
+
+
+def _height_field(nx, ny, seed, padding, holes=0.03, thick=(0.4, 30.0), rough=3.0):
+    """One interval per column (a few columns empty): rough lower and upper surfaces, so that the eroded intervals
+    [a + h, b - h] of neighbouring columns cut each other in every way (U <= L, clamping, pinched-off columns)."""
+    rng = np.random.RandomState(seed)
+    p = padding
+    gx, gy = nx + 2 * p, ny + 2 * p
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    base = 6.0 + 4.0 * np.sin(xx / 7.0) * np.cos(yy / 5.0) + rng.uniform(0, rough, (ny, nx))
+    top = base + rng.uniform(thick[0], thick[1], (ny, nx))
+    keep = rng.uniform(size=(ny, nx)) >= holes
+    lists = []
+    for j in range(gy):
+        for i in range(gx):
+            inner = p <= i < gx - p and p <= j < gy - p and keep[j - p, i - p]
+            lists.append((base[j - p, i - p], top[j - p, i - p]) if inner else ())
+    zhi = math.ceil(float(top.max())) + 1.0
+    return CompressedVolume.from_lists(gx, gy, lists, origin=(-float(p), -float(p), -float(p)), extent=(float(nx), float(ny), zhi),
+                                       spacing=1.0, padding=p)
+
+
+DUAL_CASES = [
+    ("torus_z_n160_p12", lambda: synth.torus_z(160, padding=12), 10.0),
+    ("torus_z_n96_R0.75", lambda: synth.torus_z(96, padding=3), 0.75),
+    ("torus_z_n128_R6", lambda: synth.torus_z(128, padding=8), 6.0),
+    ("height_field_rough", lambda: _height_field(90, 60, 1, 6), 3.7),
+    ("height_field_thin", lambda: _height_field(75, 44, 2, 9, holes=0.0, thick=(0.1, 9.0)), 8.0),
+    ("height_field_no_padding", lambda: _height_field(64, 64, 3, 0, holes=0.002), 2.2),
+    ("height_field_wide", lambda: _height_field(300, 40, 4, 5, holes=0.001, thick=(20.0, 40.0), rough=1.0), 12.5),
+]
+
+
+@pytest.mark.parametrize("name,gen,radius", DUAL_CASES, ids=[c[0] for c in DUAL_CASES])
+def test_erosion_dual_form(ctx, oracle, name, gen, radius):
+    """Volumes with at most one interval per column take the erosion in DUAL form (vo_lib.cu: erode_dual - the hull of
+    the mirrored intervals through the tile kernel, no complement volumes). "erosion" = "dual" makes the library fail
+    instead of falling back, so this really is that path: bit for bit against the oracle and against the general
+    complement - dilate - complement path; the composites (which chain it) against the oracle."""
+    vol = gen()
+    op = morpho.make_operator("ours", ctx)
+    want = oracle.morph3d(vol, "erosion", radius, "ours")
+    ctx.set_option("pass1", "tile")
+    try:
+        ctx.set_option("erosion", "dual")
+        got, t1, t2 = morpho.apply_operation(op, "erosion", vol, radius)
+        util.assert_same(got, want, "erosion", "ours", f"dual erosion vs oracle [{name}]")
+        assert t1 >= 0 and t2 >= 0
+        ctx.set_option("erosion", "general")
+        gen_, _, _ = morpho.apply_operation(op, "erosion", vol, radius)
+        assert got.bit_equal(gen_), f"dual and general erosion differ [{name}]"
+        ctx.set_option("erosion", "auto")
+        for opn in ("opening", "closing"):
+            r, _, _ = morpho.apply_operation(op, opn, vol, radius)
+            util.assert_same(r, oracle.morph3d(vol, opn, radius, "ours"), opn, "ours", f"{opn} with dual erosion [{name}]")
+    finally:
+        ctx.set_option("erosion", "auto")
+        ctx.set_option("pass1", "auto")
+
+
+def test_erosion_dual_form_declines_what_does_not_qualify(ctx, oracle):
+    """A second interval in ONE column, an interval starting exactly at zmin - 1 ... the dual form must notice while it
+    runs (k_thresh) and the call must fall back to the general path: same result as the oracle; with "erosion" = "dual"
+    the call fails instead."""
+    base = _height_field(80, 50, 7, 6, holes=0.2)
+    # (a) one column with two intervals (the total still fits "at most one per column on average")
+    lists = [tuple(base.at(x, y)) for y in range(base.ny) for x in range(base.nx)]
+    c = 20 + base.nx * 25
+    a0, b0 = lists[c] if lists[c] else (5.0, 9.0)
+    lists[c] = (a0, a0 + 0.25 * (b0 - a0), a0 + 0.5 * (b0 - a0), b0)
+    meta = dict(origin=base.origin, extent=base.extent, spacing=base.spacing, padding=base.padding)
+    two = CompressedVolume.from_lists(base.nx, base.ny, lists, **meta)
+    # (b) an interval that starts exactly at the lower bound of the complement (zmin - 1): negate_ray erases that event
+    sp = base.spans.copy()
+    sp[3, 0] = base.zmin - 1.0
+    low = CompressedVolume(base.nx, base.ny, base.off, sp, **meta)
+    op = morpho.make_operator("ours", ctx)
+    ctx.set_option("pass1", "tile")
+    try:
+        for what, vol in (("two intervals in a column", two), ("interval at the bound", low)):
+            ctx.set_option("erosion", "auto")
+            got, _, _ = morpho.apply_operation(op, "erosion", vol, 4.4)
+            util.assert_same(got, oracle.morph3d(vol, "erosion", 4.4, "ours"), "erosion", "ours", what)
+            ctx.set_option("erosion", "dual")
+            with pytest.raises(_lib.VoroffsetError):
+                morpho.apply_operation(op, "erosion", vol, 4.4)
+    finally:
+        ctx.set_option("erosion", "auto")
         ctx.set_option("pass1", "auto")
 
 

@@ -168,6 +168,11 @@ struct Pass2Args {
 	Stage st;
 	Redo redo;
 	Work wk;
+	// dual form only (k_pass2_rows_dual): distance of every column to the nearest EMPTY column of its row (k_empty_dist),
+	// the reach of every class, and the range negateInv keeps (zmin, zmax of the erosion)
+	const uint8_t *dist = nullptr;
+	const int *reach = nullptr;
+	double lo = 0, hi = 0;
 };
 
 // class window flag (lo | hi << 8): is class j needed? FLAG_ALL = every class (written by the one-thread-per-slot pass 1
@@ -337,6 +342,158 @@ __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 	const unsigned long long c = (unsigned long long)(y - a.y0) * nx + x;
 	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Erosion in DUAL form, for volumes with at most one interval [a, b] per column strictly inside the bounds
+// (vo_lib.cu: erode_dual). The reference erodes by dilating the complement (Voronoi.cpp:8-17): the column's complement
+// is [zmin-1, a] and [b, zmax+1] (negate_ray, MorphologyOperators.cpp:230-259), an empty column's - and the one-line
+// border's - is everything. In the dilated complement of an output column all lower parts share the point zmin-1
+// and all upper parts zmax+1, so it is [.., L] u [U, ..] with L = max (a_q + h_q), U = min (b_q - h_q) over the same
+// (column, cap) pairs a dilation visits, ONE interval when U <= L or when an empty column lies in reach; negateInv
+// (negate_ray_range, MorphologyOperators.cpp:282-315) then keeps [L, U] clamped to [lo, hi]. Pass 1 (the tile kernel,
+// DUAL) has computed, per class, the hull of the MIRRORED contributions [-a_q - h_q, -b_q + h_q]: the same table
+// values and the same IEEE operations up to sign, so L and U carry the reference's bits. Nothing is complemented,
+// no border is added, no list is ever built.
+//
+// k_empty_dist: per row, the distance (0 .. 255) of every column to the nearest empty column, the two virtual
+// columns x = -1 and x = nx (the border) counting as empty. One CTA per row: occupancy bit mask of the row in shared
+// memory, then a word-wise search to either side.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ED_THREADS = 256;
+__global__ void __launch_bounds__(ED_THREADS) k_empty_dist(const uint32_t *__restrict__ off, int nx, uint8_t *__restrict__ dist)
+{
+	extern __shared__ uint32_t s_occ[];                     // bit x = column x is EMPTY
+	const int y = blockIdx.x, nwords = (nx + 31) >> 5;
+	const uint32_t *row = off + (size_t)y * nx;
+	for (int x0 = 0; x0 < nwords * 32; x0 += ED_THREADS) {
+		const int x = x0 + (int)threadIdx.x;
+		const bool empty = x < nx && __ldg(row + x + 1) == __ldg(row + x);
+		const unsigned int b = __ballot_sync(0xffffffffu, empty);
+		if ((threadIdx.x & 31) == 0 && (x >> 5) < nwords) s_occ[x >> 5] = b;
+	}
+	__syncthreads();
+	for (int x = threadIdx.x; x < nx; x += ED_THREADS) {
+		int best = min(min(x + 1, nx - x), 255);
+		// nearest empty column at or below x
+		int wi = x >> 5;
+		uint32_t bits = s_occ[wi] & (0xffffffffu >> (31 - (x & 31)));
+		while (true) {
+			if (bits) { best = min(best, x - (wi * 32 + 31 - __clz(bits))); break; }
+			if (wi == 0 || x - (wi * 32 - 1) >= best) break;
+			bits = s_occ[--wi];
+		}
+		// ... above x
+		wi = x >> 5;
+		bits = s_occ[wi] & (0xffffffffu << (x & 31));
+		while (true) {
+			if (bits) { best = min(best, wi * 32 + __ffs(bits) - 1 - x); break; }
+			if (wi + 1 >= nwords || (wi + 1) * 32 - x >= best) break;
+			bits = s_occ[++wi];
+		}
+		dist[(size_t)y * nx + x] = (uint8_t)best;
+	}
+}
+
+// Pass 2 of the dual form: same segment / tile-mask logic as k_pass2_rows; the fold is a hull (no running union), an
+// output column with an empty column (or the border) in reach is empty, the rest goes through negateInv's clamping.
+__global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows_dual(Pass2Args a)
+{
+	__shared__ int s_reach[64];
+	if (threadIdx.x <= (unsigned)a.J) s_reach[threadIdx.x] = __ldg(a.reach + threadIdx.x);
+	__syncthreads();
+	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
+	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);
+	const int y = a.y0 + (int)(blockIdx.x / (unsigned)tiles_x);
+	const int x = tile * P2_TX + (int)threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const size_t nx = (size_t)a.nx;
+	const unsigned long long *t_up = a.tilemask, *t_dn = a.tilemask + (size_t)a.ny * tiles_x;
+	unsigned long long c_up = 0, c_dn = 0;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const int j = lane + 1 + 32 * h;
+		bool pu = false, pd = false;
+		if (j <= a.J) {
+			if (y - j >= 0) pu = (__ldg(t_dn + (size_t)(y - j) * tiles_x + tile) >> j) & 1ull;
+			if (y + j < a.ny) pd = (__ldg(t_up + (size_t)(y + j) * tiles_x + tile) >> j) & 1ull;
+		}
+		c_up |= (unsigned long long)__ballot_sync(0xffffffffu, pu) << (32 * h);
+		c_dn |= (unsigned long long)__ballot_sync(0xffffffffu, pd) << (32 * h);
+	}
+	if (x >= a.nx) return;
+	const size_t cc = (size_t)y * nx + x;
+	const unsigned long long c = (unsigned long long)(y - a.y0) * nx + x;
+	// an empty column within reach[|dy|] of x in row y + dy, |dy| <= J (rows outside the grid are the border: empty)
+	bool killed = y < a.J || a.ny - 1 - y < a.J;
+	if (!killed) {
+		const uint8_t *d = a.dist + cc;
+		killed = (int)__ldg(d) <= s_reach[0];
+		for (int j0 = 1; j0 <= a.J && !killed; j0 += 4) {
+			uint8_t v[8];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int j = min(j0 + i, a.J);
+				v[2 * i] = __ldg(d - (size_t)j * nx); v[2 * i + 1] = __ldg(d + (size_t)j * nx);
+			}
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int r = s_reach[min(j0 + i, a.J)];
+				killed |= (int)v[2 * i] <= r || (int)v[2 * i + 1] <= r;
+			}
+		}
+	}
+	if (killed) { a.st.cnt[c] = 0; return; }
+	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
+	unsigned long long m_up = 0, m_dn = 0;
+	const uint16_t w_up = __ldg(f_up + cc), w_dn = __ldg(f_dn + cc);
+	while (c_up | c_dn) {
+		int jj[4];
+		const uint16_t *p[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			jj[i] = 0; p[i] = f_up + cc;
+			if (c_up) { const int j = __ffsll((long long)c_up); c_up &= c_up - 1; jj[i] = -j; p[i] = f_dn + cc - (size_t)j * nx; }
+			else if (c_dn) { const int j = __ffsll((long long)c_dn); c_dn &= c_dn - 1; jj[i] = j; p[i] = f_up + cc + (size_t)j * nx; }
+		}
+		uint16_t w[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) w[i] = __ldg(p[i]);
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			if (jj[i] < 0) m_up |= (unsigned long long)flag_has(w[i], -jj[i]) << (-jj[i] - 1);
+			else if (jj[i] > 0) m_dn |= (unsigned long long)flag_has(w[i], jj[i]) << (jj[i] - 1);
+		}
+	}
+	// hull of the mirrored slots: X = min (-a - h) = -L, Y = max (-b + h) = -U
+	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	double X = inf, Y = -inf;
+	const size_t midrow = (size_t)(a.J + 1) * nx;
+	const double2 *self = a.mid + (size_t)y * midrow + x;
+	if (flag_has(w_up, 0) || flag_has(w_dn, 0)) { const double2 v = __ldg(self); X = v.x < X ? v.x : X; Y = v.y > Y ? v.y : Y; }
+	const size_t step_up = midrow - nx, step_dn = midrow + nx;
+	while (m_up | m_dn) {
+		const double2 *p[4];
+		int n = 0;
+#pragma unroll
+		for (int i = 0; i < 4; ++i) {
+			p[i] = self;
+			if (m_up) { const int j = __ffsll((long long)m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
+			else if (m_dn) { const int j = __ffsll((long long)m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
+		}
+		double2 v[4];
+#pragma unroll
+		for (int i = 0; i < 4; ++i) v[i] = __ldg(p[i]);
+#pragma unroll
+		for (int i = 0; i < 4; ++i)
+			if (i < n) { X = v[i].x < X ? v[i].x : X; Y = v[i].y > Y ? v[i].y : Y; }
+	}
+	const double L = -X, U = -Y;
+	// the dilated complement is [.., L] u [U, ..] (one interval when they touch); negate_ray_range drops the leading
+	// events <= lo and the trailing ones >= hi and re-inserts a bound where an even number went
+	if (U <= L || U <= a.lo || L >= a.hi) { a.st.cnt[c] = 0; return; }
+	a.st.cnt[c] = 1u;
+	a.st.inl[c * STAGE_INLINE] = make_double2(L <= a.lo ? a.lo : L, U >= a.hi ? a.hi : U);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -94,15 +94,19 @@ __device__ __forceinline__ int first_gt(const float *tab, int last, float v)
 // initially q0) skips the q that lie entirely below p except the nearest, and the scan stops once the first term alone
 // reaches the best value - a column of k intervals costs O(k) per neighbour instead of O(k^2) (lattices: 10 x 10).
 // Any SUBSET of q gives a valid, merely more conservative value, so unsorted input only prunes less.
-__device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint32_t &qs, uint32_t q1, double clo, double chi)
+// dual (ThreshArgs::dual): p and the q are mirrored intervals (-z1, -z2) - the formula is the same, only the
+// "is an interval" test and the scan start, which rely on z1 <= z2 and on the order inside a column, are dropped
+// (dual columns hold one interval).
+__device__ __forceinline__ double nn_of(const double2 p, const double2 *q, uint32_t &qs, uint32_t q1, double clo, double chi, bool dual = false)
 {
 	const double inf = __longlong_as_double(0x7FF0000000000000LL);
 	const bool plo = p.x <= clo, phi = p.y >= chi;
 	double r = inf;
-	while (qs + 1 < q1 && __ldg(q + qs + 1).y < p.x) ++qs;
+	while (!dual && qs + 1 < q1 && __ldg(q + qs + 1).y < p.x) ++qs;
 	for (uint32_t k = qs; k < q1; ++k) {
-		const double2 v = __ldg(q + k);
-		if (!(v.x <= v.y)) continue;                       // (not an interval, see k_thresh)
+		double2 v = __ldg(q + k);
+		if (dual) v = make_double2(-v.x, -v.y);
+		else if (!(v.x <= v.y)) continue;                  // (not an interval, see k_thresh)
 		const double ta = v.x <= clo ? -inf : (plo ? inf : v.x - p.x);
 		const double tb = v.y >= chi ? -inf : (phi ? inf : p.y - v.y);
 		r = fmin(r, fmax(ta, tb));
@@ -148,6 +152,12 @@ struct ThreshArgs {
 	// then does nothing and the host reports VO_ERR_ARG
 	unsigned int *bad = nullptr;
 	uint32_t nspans = 0;
+	// Dual form (erosion of a volume with at most one interval per column, vo_lib.cu: erode_dual): the thresholds of the
+	// MIRRORED intervals (-z1, -z2), whose "dilation" hull is the erosion's intersection. Columns that do not qualify -
+	// several intervals, an interval that is not strictly inside (dual_lo, dual_hi) or has z1 > z2 - raise *dual_bad.
+	int dual = 0;
+	double dual_lo = 0, dual_hi = 0;
+	unsigned int *dual_bad = nullptr;
 };
 
 // offsets of one column as read from untrusted input (ThreshArgs::bad): an invalid pair becomes an empty column
@@ -188,17 +198,23 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	}
 	unsigned int cost_l = 0, cost_s = 0, cost_r = 0;     // pairs of this column with outputs in the tile on the left / its own / on the right
 	const int xi = x & (P1_W - 1);
+	const bool dual = a.dual != 0;
+	if (dual && o1 - o0 > 1u) *a.dual_bad = 1u;
 	for (uint32_t k = o0; k < o1; ++k) {
-		const double2 p = __ldg(a.spans + k);
+		double2 p = __ldg(a.spans + k);
+		if (dual) {
+			if (!(p.x > a.dual_lo && p.x <= p.y && p.y < a.dual_hi)) *a.dual_bad = 1u;
+			p = make_double2(-p.x, -p.y);
+		}
 		const double m = 1e-9 + 1e-13 * (fabs(p.x) + fabs(p.y));
 		// An entry with z1 > z2 is not an interval; it is never pruned and never prunes. (The one known source - the
 		// erosion of data outside [zmin, zmax], where negate_ray prepends the bound without looking,
 		// MorphologyOperators.cpp:241-248 - is sent to the unpruned kernel by erode() anyway.)
-		const bool proper = p.x <= p.y;
+		const bool proper = dual || p.x <= p.y;
 		const double pinf = __longlong_as_double(0x7FF0000000000000LL);
 		// (l0, r0, u0, d0 advance with p: nn_of's scan start)
-		const double nnL = proper ? nn_of(p, a.spans, l0, l1, a.clip_lo, a.clip_hi) : pinf, nnR = proper ? nn_of(p, a.spans, r0, r1, a.clip_lo, a.clip_hi) : pinf;
-		const double nnU = proper ? nn_of(p, a.spans, u0, u1, a.clip_lo, a.clip_hi) : pinf, nnD = proper ? nn_of(p, a.spans, d0, d1, a.clip_lo, a.clip_hi) : pinf;
+		const double nnL = proper ? nn_of(p, a.spans, l0, l1, a.clip_lo, a.clip_hi, dual) : pinf, nnR = proper ? nn_of(p, a.spans, r0, r1, a.clip_lo, a.clip_hi, dual) : pinf;
+		const double nnU = proper ? nn_of(p, a.spans, u0, u1, a.clip_lo, a.clip_hi, dual) : pinf, nnD = proper ? nn_of(p, a.spans, d0, d1, a.clip_lo, a.clip_hi, dual) : pinf;
 		// an interval saturated on both sides covers the whole range: it yields to a CLOSER one of its kind (near
 		// tests) but never to a farther one - otherwise two of them could drop each other
 		const bool whole = p.x <= a.clip_lo && p.y >= a.clip_hi;
@@ -723,7 +739,10 @@ __device__ __noinline__ double2 class_general(const Pass1TileArgs &a, const Tile
 // (erosion) each such layer unions to ONE interval, so a class costs NL (lo, hi) pairs and no list. A
 // survivor that misses the running hull of its layer makes the class "complex" (general path).
 // `need` = the classes of the block some consumer reads (bit q = class cb + q).
-template <int CB, int NL, int CAP, int LCAP>
+// DUAL (erosion in dual form, vo_lib.cu: erode_dual): the candidates are read as the mirrored intervals (-z1, -z2);
+// the hull (min, max) IS the result then - the intersection of the eroded intervals, mirrored - so no class is ever
+// "complex".
+template <int CB, int NL, int CAP, int LCAP, bool DUAL = false>
 __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThread<LCAP> &t, int cb, unsigned int need)
 {
 	const double inf = __longlong_as_double(0x7FF0000000000000LL);
@@ -742,7 +761,8 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 		if (!t.survivor(s, k, d, w)) continue;
 		const unsigned int valid = window_mask<CB>(w, cb);
 		if (!valid) continue;
-		const double2 ab = t.t.cand[k];
+		double2 ab = t.t.cand[k];
+		if (DUAL) ab = make_double2(-ab.x, -ab.y);
 		const double *hp = t.t.Ht + (size_t)d * t.t.JPP + cb;
 		double h[CB];
 #pragma unroll
@@ -758,7 +778,7 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 				for (int q = 0; q < CB; ++q) {
 					const double hq = ((valid >> q) & 1u) ? h[q] : -inf;
 					const double cs = ab.x - hq, ce = ab.y + hq;
-					miss |= (cs <= hi[l][q] && ce >= lo[l][q]) ? 0u : (1u << q);
+					if (!DUAL) miss |= (cs <= hi[l][q] && ce >= lo[l][q]) ? 0u : (1u << q);
 					lo[l][q] = cs < lo[l][q] ? cs : lo[l][q];
 					hi[l][q] = ce > hi[l][q] ? ce : hi[l][q];
 				}
@@ -804,14 +824,14 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 }
 
 // every class of the two windows [UL, UH) u [DL, DH), CB at a time, blocks starting at a needed class
-template <int CB, int NL, int CAP, int LCAP>
+template <int CB, int NL, int CAP, int LCAP, bool DUAL = false>
 __device__ __forceinline__ void eval_classes(const Pass1TileArgs &a, const TileThread<LCAP> &t, int UL, int UH, int DL, int DH)
 {
 	const int jend = max(UH, DH);
 	int cb = UH > UL ? (DH > DL ? min(UL, DL) : UL) : DL;
 	while (cb < jend) {
 		const unsigned int need = range_mask<CB>(UL, UH, cb) | range_mask<CB>(DL, DH, cb);
-		eval_block<CB, NL, CAP, LCAP>(a, t, cb, need);
+		eval_block<CB, NL, CAP, LCAP, DUAL>(a, t, cb, need);
 		cb += CB;
 		// next needed class at or after cb
 		const bool in_u = cb >= UL && cb < UH, in_d = cb >= DL && cb < DH;
@@ -834,7 +854,7 @@ struct TileHead {
 };
 
 // Phase 2 of a staged tile: lane per output column (the whole warp enters; `active` = owns a column).
-template <int CAP, bool MULTI, int LCAP>
+template <int CAP, bool MULTI, int LCAP, bool DUAL = false>
 __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHead &h, const Tile<LCAP> &tl, const uint32_t *s_off)
 {
 	const int J = a.J, lane = threadIdx.x & 31;
@@ -878,7 +898,7 @@ __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHe
 		}
 	}
 	if (!active || (UH == 0 && DH == 0)) return;
-	if (!MULTI || maxlayer == 0) eval_classes<P1_CB, 1, CAP, LCAP>(a, t, UL, UH, DL, DH);   // every survivor is the first interval of its column
+	if (!MULTI || maxlayer == 0) eval_classes<P1_CB, 1, CAP, LCAP, DUAL>(a, t, UL, UH, DL, DH);   // every survivor is the first interval of its column
 	else eval_classes<P1_CB, 2, CAP, LCAP>(a, t, UL, UH, DL, DH);                           // two hulls per class
 }
 
@@ -921,7 +941,7 @@ __device__ __forceinline__ void tile_other(const Pass1TileArgs &a, const TileHea
 //   - right after that one lane starts the bulk copies (TMA, cp.async.bulk) of the next tile's candidates and
 //     thresholds into the other staging buffer; they land during phase 2 of the current tile and are awaited
 //     (mbarrier) at the top of the next iteration.
-template <int CAP, bool MULTI, bool LIST>
+template <int CAP, bool MULTI, bool LIST, bool DUAL = false>
 __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1) k_pass1_tile(Pass1TileArgs a)
 {
 	constexpr int LCAP = (MULTI || LIST) ? P1_LCAP_M : P1_LCAP_S;
@@ -1057,7 +1077,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 		unsigned int dbg_entries = 0;
 		const long long dbg_t1 = a.dbg ? clock64() : 0;
 		if (a.dbg && cur.kind == TK_NORMAL) { __syncwarp(); dbg_entries = __reduce_add_sync(FULL, sm.cnt[lane]); }
-		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP>(a, cur, tl, sm.off[buf]);
+		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP, DUAL>(a, cur, tl, sm.off[buf]);
 		__syncwarp();                                       // lists, counters and the staging buffer are free again
 		if (a.dbg && lane == 0 && cur.kind == TK_NORMAL) {     // (scripts/tile_costs.py)
 			unsigned long long *d = a.dbg + 4ull * cur.tile;

@@ -84,6 +84,9 @@ struct vo_ctx {
 	std::vector<std::pair<void *, size_t>> big_free;        // released blocks, oldest first
 	size_t big_free_bytes = 0, big_free_limit = (size_t)48 << 30;   // vo_create sets the limit to a third of the device memory
 	bool block_cache = true;          // vo_set_option("block_cache", "off")
+	int erosion_mode = 0;             // vo_set_option("erosion", "auto" | "dual" | "general"): 0 = dual form where the input qualifies
+	                                  // (erode_dual), 1 = dual form or VO_ERR_ARG (tests), 2 = always complement - dilate - complement
+	uint64_t dual_erosions = 0;       // erosions that ran in dual form
 };
 
 struct vo_dvol {
@@ -91,6 +94,7 @@ struct vo_dvol {
 	uint64_t nspans = 0;
 	uint32_t *off = nullptr;
 	double2 *spans = nullptr;
+	mutable int dual_state = 0;     // erode_dual: 0 = not tried, 1 = qualified, 2 = did not (several intervals in a column, data at the bounds)
 };
 
 struct vo_dmid {
@@ -738,6 +742,8 @@ struct TilePlan {
 		cudaError_t e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_multi, smem_bigmulti));
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 		if (e != cudaSuccess) return fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e));
 		return VO_OK;
 	}
@@ -747,7 +753,7 @@ struct TilePlan {
 	// NCCL kernels of a halo exchange in flight).
 	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles0, unsigned int *big_tiles, unsigned int *multi_tiles,
 	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0,
-	            unsigned long long *bank = nullptr, const unsigned int *order = nullptr) const
+	            unsigned long long *bank = nullptr, const unsigned int *order = nullptr, bool dual = false) const
 	{
 		if (!bank) bank = ctx->d_ctr;                       // ([3] [5] [6] [7] [10] [12] [13] of `bank`: the lists and cursors of this launch set)
 		const unsigned int ntiles = ntiles0 + ntilesb;
@@ -765,14 +771,19 @@ struct TilePlan {
 		g.cmax = cmax_small; g.dbuf = db_small; g.lean = 0; g.tiles = nullptr; g.tiles_count = nullptr; g.order = order;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 10);
 		g.big_tiles = cmax_small < cmax_big ? big_tiles : nullptr;
-		k_pass1_tile<CAP_FAST, false, false><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
+		if (dual) k_pass1_tile<CAP_FAST, false, false, true><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
+		else k_pass1_tile<CAP_FAST, false, false><<<grid(nw_small), 32 * nw_small, smem_small, s>>>(g);
 		ctx->launches++;
 		if (cmax_small < cmax_big) {    // launch 2: the single-interval tiles that need the large buffer
 			g.cmax = cmax_big; g.dbuf = db_big; g.lean = lean_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 6);
-			k_pass1_tile<CAP_FAST, false, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
+			if (dual) k_pass1_tile<CAP_FAST, false, true, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
+			else k_pass1_tile<CAP_FAST, false, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
 			ctx->launches++;
 		}
+		// (dual form: every column holds one interval; a tile that says otherwise is only counted, [5], and the caller
+		// falls back to the general erosion)
+		if (dual) return;
 		// launch 3: tiles with multi-interval columns (two hulls per class), candidate buffer a quarter above the mean fill;
 		// the tiles beyond it are collected again (in big_tiles, which launch 2 is done with) for launch 4
 		unsigned int *bigmulti_count = reinterpret_cast<unsigned int *>(bank + 12);
@@ -810,9 +821,25 @@ struct TilePlan {
 // defer: enqueue only - no host round trip; the counters that say whether the pools were large enough are read by the
 // caller together with those of pass 2 (which never follows a reference beyond a pool), and a pass 1 that fell short is
 // repeated without `defer`. Saves one synchronisation per dilation.
+// Would pass 1 of this volume take the tile kernel?
+bool pass1_uses_tile(const vo_ctx *ctx, const vo_dvol *in, double R)
+{
+	const int J0 = (int)std::floor(R);
+	const unsigned long long ncols = (unsigned long long)in->nx * in->ny;
+	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
+	// (small problems do not fill the machine with one lane per column: the simple kernel has J+1 times more threads;
+	// dense columns tip the balance earlier - the tile kernel's class windows also spare pass 2 most of its reads)
+	const bool big = (double)ncols * (J0 + 1) * std::max(1.0, k_in) >= (double)(2ull << 20) || ctx->force_tile_pass1;
+	return ncols > 0 && TilePlan::fits(J0, k_in) && big && !ctx->force_simple_pass1;
+}
+
+// dual: the mid volume of the MIRRORED intervals (erode_dual; tile kernel only, always deferred). [dual_lo, dual_hi] =
+// the bounds of the erosion's complement (zmin - 1, zmax + 1): every interval must lie strictly inside.
+struct DualSpec { double lo, hi; };
+
 int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
           double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity(),
-          bool defer = false)
+          bool defer = false, const DualSpec *dual = nullptr)
 {
 	VO_TRY(check_radius(ctx, R));
 	const int J0 = (int)std::floor(R);
@@ -821,10 +848,8 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	// candidates are expected to fit; otherwise the one-thread-per-(x,y,j) kernel does everything
 	const int TX = P1_TX;
 	const double k_in = ncols ? (double)in->nspans / (double)ncols : 0.0;
-	// (small problems do not fill the machine with one lane per column: the simple kernel has J+1 times more threads;
-	// dense columns tip the balance earlier - the tile kernel's class windows also spare pass 2 most of its reads)
-	const bool big = (double)ncols * (J0 + 1) * std::max(1.0, k_in) >= (double)(2ull << 20) || ctx->force_tile_pass1;
-	const bool use_tile = ncols > 0 && TilePlan::fits(J0, k_in) && big && !ctx->force_simple_pass1;
+	const bool use_tile = pass1_uses_tile(ctx, in, R);
+	if (dual && (!use_tile || !defer)) return fail(ctx, VO_ERR_ARG, "dual pass 1 needs the tile kernel");
 	TableCache *tc = nullptr;
 	VO_TRY(get_tables(ctx, R, use_tile, &tc));
 	const Tables &t = tc->t;
@@ -876,6 +901,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			ta.nx = in->nx; ta.ny = in->ny; ta.J = t.J; ta.off = in->off; ta.spans = in->spans;
 			ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
 			ta.c_begin = 0; ta.c_end = ncols; ta.clip_lo = clip_lo; ta.clip_hi = clip_hi;
+			if (dual) { ta.dual = 1; ta.dual_lo = dual->lo; ta.dual_hi = dual->hi; ta.dual_bad = reinterpret_cast<unsigned int *>(ctx->d_ctr + 14); }
 			if (ordered) {
 				cudaMemsetAsync(est.p, 0, (ntiles + 2 * P1_NBUCKET) * sizeof(unsigned int), ctx->stream);
 				ta.est = est.p + 2 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw;
@@ -888,7 +914,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
 			g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			cudaEventRecord(ctx->kev[0], ctx->stream);
-			plan.launch(ctx, g, 0u, (unsigned int)ntiles, big_tiles.p, multi_tiles.p, ctx->stream, 0u, 0u, 0, nullptr, ordered ? order.p : nullptr);
+			plan.launch(ctx, g, 0u, (unsigned int)ntiles, big_tiles.p, multi_tiles.p, ctx->stream, 0u, 0u, 0, nullptr, ordered ? order.p : nullptr, dual != nullptr);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
 		} else if (nslots) {
@@ -903,7 +929,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			ctx->kev_valid[0] = true;
 			ctx->launches++;
 		}
-		if (nslots) {
+		if (nslots && !dual) {
 			// redo launch over the device-side list (fixed grid, reads the count itself)
 			a.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
 			k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, ctx->stream>>>(a);
@@ -950,6 +976,26 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
 		},
 		[&](Pass2Args &g, unsigned int grid) { k_pass2<CAP_BIG><<<grid, 128, 0, s>>>(g); },
 		m->nx, y1 - y0, out);
+}
+
+// pass 2 of the dual form (k_pass2_rows_dual): hull of the mirrored slots, empty columns in reach, negateInv's clamping
+int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *reach, double lo, double hi, vo_dvol **out)
+{
+	Pass2Args a;
+	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = 0; a.y1 = m->ny;
+	a.mid = m->slots; a.flags = m->flags; a.tilemask = m->tilemask; a.pool = m->pool; a.pool_cap = m->pool_cap;
+	a.dist = dist; a.reach = reach; a.lo = lo; a.hi = hi;
+	const unsigned long long nlists = (unsigned long long)m->nx * m->ny;
+	cudaStream_t s = ctx->stream;
+	return run_staged(ctx, a, nlists, 65536ull,
+		[&](Pass2Args &g) {
+			cudaEventRecord(ctx->kev[2], s);
+			k_pass2_rows_dual<<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+			cudaEventRecord(ctx->kev[3], s);
+			ctx->kev_valid[1] = true;
+		},
+		[&](Pass2Args &, unsigned int) { ctx->launches--; },     // (no list can outgrow anything: at most one interval per column)
+		m->nx, m->ny, out);
 }
 
 int brute(vo_ctx *ctx, const vo_dvol *in, double R, vo_dvol **out)
@@ -1151,8 +1197,63 @@ int erode_with(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, int by0
 	return rc;
 }
 
+// Erosion in DUAL form ('ours'; kernels.cuh: k_pass2_rows_dual has the derivation): for a volume whose columns hold at
+// most one interval, strictly inside (zmin - 1, zmax + 1), the reference's complement - dilate - complement
+// (Voronoi.cpp:8-17) is, column by column, the intersection of the eroded intervals [a_q + h_q, b_q - h_q] over the
+// pairs a dilation visits, and empty where an empty column (or the one-line border) lies in reach. The tile kernel
+// computes that intersection as the hull of the mirrored intervals with the same tables and the same pruning, so the
+// erosion costs one dilation-sized pass instead of a dilation of the (denser, two-layer) complement between two
+// complement kernels. Whether the input qualifies is checked by k_thresh while it runs (no separate pass, no
+// synchronisation): DUAL_NA = it did not (or cannot be known to), the caller takes the general path.
+constexpr int DUAL_NA = -2;
+int erode_dual(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt)
+{
+	const unsigned long long ncols = (unsigned long long)in->nx * in->ny;
+	if (in->dual_state == 2 || ncols == 0 || in->nspans > ncols || ctx->force_simple_pass1) return DUAL_NA;
+	if (check_radius(ctx, R) != VO_OK || !pass1_uses_tile(ctx, in, R)) { ctx->err.clear(); return DUAL_NA; }
+	float t1 = 0, t2 = 0;
+	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	Tmp<uint8_t> dist(ctx);
+	VO_TRY(dalloc(ctx, &dist.p, ncols));
+	k_empty_dist<<<(unsigned int)in->ny, ED_THREADS, (size_t)((in->nx + 31) / 32) * sizeof(uint32_t), ctx->stream>>>(in->off, in->nx, dist.p);
+	ctx->launches++;
+	vo_dmid *mid = nullptr;
+	const DualSpec ds{zmin - 1, zmax + 1};
+	const double inf = std::numeric_limits<double>::infinity();
+	VO_TRY(pass1(ctx, in, R, &mid, -inf, inf, true, &ds));
+	cudaEventRecord(ctx->ev[1], ctx->stream);
+	const unsigned int redo_cap = mid->redo_cap;
+	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);    // (pass 1 has just made these the current tables)
+	int rc = pass2_dual(ctx, mid, dist.p, tc->dt.reach, zmin, zmax, out);
+	vo_dmid_free(ctx, mid);
+	VO_TRY(rc);
+	// pass 2's synchronisation has read every counter: [14] a column did not qualify, [5] a tile saw a multi-interval
+	// column, [2] anything was left to the (non-dual) redo kernel
+	const unsigned long long *h = ctx->last_ctr;
+	(void)redo_cap;
+	if (h[14] != 0 || h[5] != 0 || h[2] != 0 || h[4] != 0) {
+		free_dvol(ctx, *out);
+		*out = nullptr;
+		in->dual_state = 2;
+		return DUAL_NA;
+	}
+	in->dual_state = 1;
+	ctx->dual_erosions++;
+	VO_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+	VO_CUDA(cudaEventSynchronize(ctx->ev[2]));
+	cudaEventElapsedTime(&t1, ctx->ev[0], ctx->ev[1]);
+	cudaEventElapsedTime(&t2, ctx->ev[1], ctx->ev[2]);
+	if (pt) { pt->ms1 = t1; pt->ms2 = t2; }
+	return VO_OK;
+}
+
 int erode(vo_ctx *ctx, int method, const vo_dvol *in, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt)
 {
+	if (method == VO_METHOD_OURS && ctx->erosion_mode != 2) {
+		const int rc = erode_dual(ctx, in, zmin, zmax, R, out, pt);
+		if (rc != DUAL_NA) return rc;
+		if (ctx->erosion_mode == 1) return fail(ctx, VO_ERR_ARG, "erosion = dual: the input does not qualify for the dual form");
+	}
 	return erode_with(ctx, in, zmin, zmax, 1, 1, [&](const vo_dvol *neg, double clo, double chi, bool unpruned, vo_dvol **o) {
 		const bool saved_simple = ctx->force_simple_pass1;
 		if (unpruned) ctx->force_simple_pass1 = true;
@@ -2213,6 +2314,11 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "pipeline") == 0) {
 		if (std::strcmp(value, "off") == 0) { ctx->no_pipeline = true; return VO_OK; }
 		if (std::strcmp(value, "on") == 0 || std::strcmp(value, "auto") == 0) { ctx->no_pipeline = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "erosion") == 0) {
+		if (std::strcmp(value, "auto") == 0) { ctx->erosion_mode = 0; return VO_OK; }
+		if (std::strcmp(value, "dual") == 0) { ctx->erosion_mode = 1; return VO_OK; }
+		if (std::strcmp(value, "general") == 0) { ctx->erosion_mode = 2; return VO_OK; }
 	}
 	if (std::strcmp(key, "block_cache") == 0) {
 		if (std::strcmp(value, "on") == 0) {
