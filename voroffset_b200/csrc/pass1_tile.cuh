@@ -433,6 +433,9 @@ struct Pass1TileArgs {
 	//             multi_tiles, tiles with more than cmax candidates to big_tiles.
 	//   launch 2  <MULTI=false>, large buffer, tiles = big_tiles.
 	//   launch 3  <MULTI=true> (two hulls per class), tiles = multi_tiles.
+	int quota = 0;                    // > 0: a warp takes at most this many tiles and leaves (launch 1 of the host-buffer pipeline: a
+	                                  //      grid of short-lived CTAs, so that the small kernels of the other bands get SM slots all
+	                                  //      the time instead of waiting for a resident wave to retire); 0: warps stay until the tiles run out
 	const unsigned int *tiles;        // NULL: all tiles of [tile0, tile0 + ntiles)
 	const unsigned int *order;        // with tiles == NULL, optional: the same tiles as a permutation (k_order_place), expensive ones first
 	const unsigned int *tiles_count;  // length of `tiles` (device side)
@@ -1020,7 +1023,12 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 		for (int i = lane; i < SEG; i += 32)
 			for (uint32_t k0 = s_off[i] - h.base, k = k0; k < s_off[i + 1] - h.base; ++k) { sm.ci[b][k] = (uint8_t)i; sm.ly[b][k] = (uint8_t)min(k - k0, 3u); }
 	};
-	auto fetch_pos = [&]() -> unsigned int { return lane == 0 ? atomicAdd(a.tiles_next, 1u) : 0u; };
+	int claims = 0;                                         // tiles this warp has asked for (a.quota)
+	auto fetch_pos = [&]() -> unsigned int {
+		if (a.quota > 0 && claims >= a.quota) return 0xffffffffu;
+		++claims;
+		return lane == 0 ? atomicAdd(a.tiles_next, 1u) : 0u;
+	};
 
 	// prologue: the first tile is loaded synchronously, the positions of the next two are in flight
 	unsigned int pos = __shfl_sync(FULL, fetch_pos(), 0);
