@@ -797,8 +797,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
                                                                unsigned long long *state, unsigned long long *ticket,
                                                                unsigned long long ticket_base, uint32_t epoch,
                                                                unsigned long long *total_out,
-                                                               const unsigned long long *base_in = nullptr)
+                                                               const unsigned long long *base_in = nullptr,
+                                                               unsigned long long *max_word = nullptr, uint32_t max_tag = 0)
 {
+	// max_word (optional): receives max_tag << 32 | the largest list length seen (atomicMax: a word left by an earlier
+	// call carries a smaller tag, so nobody has to clear it)
 	// base_in (optional): the offsets start from *base_in instead of 0 (a band of rows of a larger volume: `spans` and
 	// `cap` are the whole volume's, *total_out = the running total after this band)
 	constexpr int TILE = SCAN_THREADS * ITEMS;
@@ -823,6 +826,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
 	if (threadIdx.x == 0) {
 		vstate[tile] = scan_word(tot, epoch, tile == 0 ? SCAN_INCL : SCAN_AGG);
 		if (tile == 0) s_prefix = 0;
+	}
+	if (max_word) {
+		uint32_t mx = 0;
+#pragma unroll
+		for (int i = 0; i < ITEMS; ++i) mx = c[i] > mx ? c[i] : mx;
+		mx = __reduce_max_sync(0xffffffffu, mx);
+		if ((threadIdx.x & 31) == 0 && mx) {
+			const unsigned long long w = ((unsigned long long)max_tag << 32) | mx;
+			if (*(volatile unsigned long long *)max_word < w) atomicMax(max_word, w);   // (nearly every warp finds its value there already)
+		}
 	}
 	{
 		uint32_t r = (uint32_t)exl;

@@ -93,6 +93,9 @@ struct vo_ctx {
 	std::vector<std::pair<void *, size_t>> big_free;        // released blocks, oldest first
 	size_t big_free_bytes = 0, big_free_limit = (size_t)48 << 30;   // vo_create sets the limit to a third of the device memory
 	bool block_cache = true;          // vo_set_option("block_cache", "off")
+	int redo_recent = 0;              // > 0: a recent call needed a redo launch (lists beyond the fast capacities) - the next calls
+	                                  // enqueue the redo launches up front again instead of finding out at the end
+	uint32_t max_epoch = 0;           // tags the "largest list" word ([15] of d_ctr) of a staged gather
 	int erosion_mode = 0;             // vo_set_option("erosion", "auto" | "dual" | "general"): 0 = dual form where the input qualifies
 	                                  // (erode_dual), 1 = dual form or VO_ERR_ARG (tests), 2 = always complement - dilate - complement
 	uint64_t dual_erosions = 0;       // erosions that ran in dual form
@@ -103,6 +106,8 @@ struct vo_dvol {
 	uint64_t nspans = 0;
 	uint32_t *off = nullptr;
 	double2 *spans = nullptr;
+	long long max_cnt = -1;         // upper bound on the intervals of any column where one is known (-1: unknown): a volume known to
+	                                // hold at most one per column skips the multi-interval launches of pass 1
 	mutable int dual_state = 0;     // erode_dual: 0 = not tried, 1 = qualified, 2 = did not (several intervals in a column, data at the bounds)
 };
 
@@ -114,6 +119,7 @@ struct vo_dmid {
 	uint16_t *flags = nullptr;      // [2][ny*nx]: class window (lo | hi << 8) needed by the consumer rows above / below each mid column
 	unsigned long long *tilemask = nullptr;   // [2][ny * ceil(nx / P1_TX)]: OR of the windows per pass-1 tile
 	uint64_t pool_cap = 0, pool_used = 0;
+	bool redo_skipped = false;      // ... and without its redo launch: any entry in the redo list means "repeat"
 	bool deferred = false;          // pass 1 returned without reading its counters: the caller checks them after pass 2
 	unsigned int redo_cap = 0;      // ... against these
 };
@@ -470,7 +476,11 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 		out_cap = std::min<unsigned long long>(std::max(ctx->out_cap_hint, nlists + 65536ull), (1ull << 32) - 1);
 		VO_TRY(dalloc(ctx, &v->spans, out_cap));
 	}
-	for (int attempt = 0; attempt < 3; ++attempt) {
+	// The redo launch is normally idle (no list outgrows the fast capacity): it is left out, and the call repeats with it
+	// when the counters say that a list did (and keeps launching it for the calls that follow).
+	bool skip_redo = ctx->redo_recent == 0;
+	if (ctx->redo_recent > 0) --ctx->redo_recent;
+	for (int attempt = 0; attempt < 4; ++attempt) {
 		// only the counters of the staged gather: a pass 1 may be in flight on the same stream (pipelined path)
 		VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
 		VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -481,23 +491,29 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 			args.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
 			launch_fast(args);
 			args.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
-			launch_big(args, REDO_GRID);
+			if (!skip_redo) launch_big(args, REDO_GRID);
 			if (fused) {
 				uint32_t epoch = 0;
 				unsigned long long tbase = 0;
 				VO_TRY(scan_prepare(ctx, ntiles, &epoch, &tbase));
+				if (++ctx->max_epoch == 0) {                     // (the tag wrapped: start over from a cleared word)
+					VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 15, 0, sizeof(unsigned long long), ctx->stream));
+					ctx->max_epoch = 1;
+				}
 				if (small_tiles)
 					k_scan_compact<2><<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
-					                                                            ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles);
+					                                                            ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles,
+					                                                            nullptr, ctx->d_ctr + 15, ctx->max_epoch);
 				else
 					k_scan_compact<SCAN_ITEMS><<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
-					                                                                     ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles);
-				ctx->launches += 3;
+					                                                                     ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles,
+					                                                                     nullptr, ctx->d_ctr + 15, ctx->max_epoch);
+				ctx->launches += skip_redo ? 2 : 3;
 			} else {
 				k_scan_reduce<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p);
 				k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(sums.p, ntiles);
 				k_scan_apply<<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st.cnt, nlists, sums.p, v->off);
-				ctx->launches += 5;
+				ctx->launches += skip_redo ? 4 : 5;
 			}
 			VO_CUDA(cudaGetLastError());
 			VO_CUDA(cudaMemcpyAsync(&total, sums.p + ntiles, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
@@ -505,6 +521,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 			VO_CUDA(cudaMemsetAsync(v->off, 0, sizeof(uint32_t), ctx->stream));
 		}
 		VO_TRY(read_counters(ctx, h));
+		if (skip_redo && h[8] > 0) { skip_redo = false; ctx->redo_recent = 16; continue; }
 		if (h[8] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
 		if (h[9]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
 		ctx->stage_hint = next_hint(ctx->stage_hint, h[1]);
@@ -521,6 +538,8 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 			}
 		}
 		v->nspans = total;
+		if (nlists == 0) v->max_cnt = 0;
+		else if (fused) v->max_cnt = (uint32_t)(h[15] >> 32) == ctx->max_epoch ? (long long)(uint32_t)h[15] : 0;
 		*out = v;
 		v = nullptr;          // released from the guard
 		return VO_OK;
@@ -777,8 +796,12 @@ struct TilePlan {
 	// NCCL kernels of a halo exchange in flight).
 	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles0, unsigned int *big_tiles, unsigned int *multi_tiles,
 	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0,
-	            unsigned long long *bank = nullptr, const unsigned int *order = nullptr, bool dual = false, int ovf_bank = -1) const
+	            unsigned long long *bank = nullptr, const unsigned int *order = nullptr, bool dual = false, int ovf_bank = -1,
+	            bool single = false) const
 	{
+		// single: every column is KNOWN to hold at most one interval (vo_dvol::max_cnt) - no tile can be a multi-interval
+		// one, and none can hold more candidates than its segment has columns: the list launches that could only find
+		// empty lists are not made
 		if (!bank) bank = ctx->d_ctr;                       // ([3] [5] [6] [7] [10] [12] [13] of `bank`: the lists and cursors of this launch set)
 		const unsigned int ntiles = ntiles0 + ntilesb;
 		const int sms = std::max(1, this->sms - reserve_sms);
@@ -801,7 +824,7 @@ struct TilePlan {
 		else k_pass1_tile<CAP_FAST, false, false><<<grid_small(ntiles, sms), 32 * nw_small, smem_small, s>>>(g);
 		g.quota = 0;
 		ctx->launches++;
-		if (cmax_small < cmax_big) {    // launch 2: the single-interval tiles that need the large buffer
+		if (cmax_small < cmax_big && !(single && cmax_small >= P1_W + 2 * J)) {    // launch 2: the single-interval tiles that need the large buffer
 			g.cmax = cmax_big; g.dbuf = db_big; g.lean = lean_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 6);
 			if (dual) k_pass1_tile<CAP_FAST, false, true, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
@@ -810,7 +833,7 @@ struct TilePlan {
 		}
 		// (dual form: every column holds one interval; a tile that says otherwise is only counted, [5], and the caller
 		// falls back to the general erosion)
-		if (dual) return;
+		if (dual || single) return;
 		// launch 3: tiles with multi-interval columns (two hulls per class), candidate buffer a quarter above the mean fill;
 		// the tiles beyond it are collected again (in big_tiles, which launch 2 is done with) for launch 4
 		unsigned int *bigmulti_count = reinterpret_cast<unsigned int *>(bank + 12);
@@ -941,7 +964,8 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
 			g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap; g.redo = rb.rd;
 			cudaEventRecord(ctx->kev[0], ctx->stream);
-			plan.launch(ctx, g, 0u, (unsigned int)ntiles, big_tiles.p, multi_tiles.p, ctx->stream, 0u, 0u, 0, nullptr, ordered ? order.p : nullptr, dual != nullptr);
+			plan.launch(ctx, g, 0u, (unsigned int)ntiles, big_tiles.p, multi_tiles.p, ctx->stream, 0u, 0u, 0, nullptr, ordered ? order.p : nullptr, dual != nullptr,
+			            -1, in->max_cnt >= 0 && in->max_cnt <= 1);
 			cudaEventRecord(ctx->kev[1], ctx->stream);
 			ctx->kev_valid[0] = true;
 		} else if (nslots) {
@@ -956,7 +980,11 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			ctx->kev_valid[0] = true;
 			ctx->launches++;
 		}
-		if (nslots && !dual) {
+		// (deferred: the redo launch - normally idle - is left out like run_staged's; the caller, who reads the counters
+		// after pass 2, repeats the dilation without `defer` when a list did outgrow the fast capacity)
+		const bool skip_redo = defer && ctx->redo_recent == 0 && attempt == 0;
+		m->redo_skipped = skip_redo;
+		if (nslots && !dual && !skip_redo) {
 			// redo launch over the device-side list (fixed grid, reads the count itself)
 			a.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
 			k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, ctx->stream>>>(a);
@@ -1021,7 +1049,7 @@ int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *re
 			cudaEventRecord(ctx->kev[3], s);
 			ctx->kev_valid[1] = true;
 		},
-		[&](Pass2Args &, unsigned int) { ctx->launches--; },     // (no list can outgrow anything: at most one interval per column)
+		[&](Pass2Args &, unsigned int) {},                       // (never needed: at most one interval per column)
 		m->nx, m->ny, out);
 }
 
@@ -1056,7 +1084,7 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 			vo_dmid *mid = nullptr;
 			VO_TRY(pass1(ctx, in, R, &mid, clip_lo, clip_hi, attempt == 0));
 			cudaEventRecord(ctx->ev[1], ctx->stream);
-			const bool deferred = mid->deferred;
+			const bool deferred = mid->deferred, redo_skipped = mid->redo_skipped;
 			const uint64_t pool_cap = mid->pool_cap;
 			const unsigned int redo_cap = mid->redo_cap;
 			int rc = pass2(ctx, mid, 0, mid->ny, out);
@@ -1064,7 +1092,8 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 			if (deferred) {
 				// pass 2's synchronisation has read every counter: was the deferred pass 1 complete?
 				const unsigned long long *h = ctx->last_ctr;
-				const bool short1 = h[0] > pool_cap || h[2] > redo_cap || h[4] != 0;
+				const bool short1 = h[0] > pool_cap || h[2] > redo_cap || h[4] != 0 || (redo_skipped && h[2] != 0);
+				if (redo_skipped && h[2] != 0) ctx->redo_recent = 16;
 				if (rc == VO_OK && !short1) { ctx->pool_hint = next_hint(ctx->pool_hint, h[0]); break; }
 				if (rc == VO_OK) { free_dvol(ctx, *out); *out = nullptr; }
 				else if (!short1) return rc;
@@ -1138,6 +1167,7 @@ int negate(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi, vo_
 	if (ctx->fused_scan && nlists && in->nspans + nlists < (1ull << 32)) {
 		const int rc = complement_fused<NegOp>(ctx, a, nlists, in->nspans + nlists, v, outside, h_outside);
 		if (rc) { free_dvol(ctx, v); return rc; }
+		v->max_cnt = in->max_cnt < 0 ? -1 : in->max_cnt + 1;
 		*out = v;
 		return VO_OK;
 	}
@@ -1178,6 +1208,7 @@ int negate_inv(vo_ctx *ctx, const vo_dvol *in, int border, double lo, double hi,
 	if (ctx->fused_scan && nlists && in->nspans + nlists < (1ull << 32)) {
 		const int rc = complement_fused<NegInvOp>(ctx, a, nlists, in->nspans + nlists, v, nullptr, nullptr);
 		if (rc) { free_dvol(ctx, v); return rc; }
+		v->max_cnt = in->max_cnt < 0 ? -1 : in->max_cnt + 1;
 		*out = v;
 		return VO_OK;
 	}
@@ -1420,10 +1451,15 @@ int xor_dev(vo_ctx *ctx, const vo_dvol *A, const vo_dvol *B, double zmin, double
 
 // CSR offsets must be non-decreasing (every kernel indexes spans[] with them). Branch-free so that it vectorises:
 // ~1.5 ms for the 4.2 M columns of a 2048^2 grid, hidden behind the upload it guards.
-bool offsets_sorted(const uint32_t *off, unsigned long long n)
+bool offsets_sorted(const uint32_t *off, unsigned long long n, uint32_t *max_count = nullptr)
 {
-	uint32_t bad = 0;
-	for (unsigned long long i = 0; i < n; ++i) bad |= (uint32_t)(off[i] > off[i + 1]);
+	uint32_t bad = 0, mx = 0;
+	for (unsigned long long i = 0; i < n; ++i) {
+		bad |= (uint32_t)(off[i] > off[i + 1]);
+		const uint32_t c = off[i + 1] - off[i];
+		mx = c > mx ? c : mx;
+	}
+	if (max_count) *max_count = mx;
 	return bad == 0;
 }
 
@@ -1445,11 +1481,13 @@ int upload(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans
 	cudaError_t e = cudaMemcpyAsync(v->off, off, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
 	if (e == cudaSuccess && m) e = cudaMemcpyAsync(v->spans, spans, m * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream);
 	if (e != cudaSuccess) { free_dvol(ctx, v); cudaGetLastError(); return fail(ctx, VO_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e)); }
-	if (!offsets_sorted(off, n)) {
+	uint32_t max_count = 0;
+	if (!offsets_sorted(off, n, &max_count)) {
 		cudaStreamSynchronize(ctx->stream);
 		free_dvol(ctx, v);
 		return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
 	}
+	v->max_cnt = max_count;
 	*out = v;
 	return VO_OK;
 }
@@ -2599,6 +2637,7 @@ int vo_dvol_rows(vo_ctx *ctx, const vo_dvol *v, int y0, int y1, vo_dvol **out)
 	vo_dvol *r = nullptr;
 	VO_TRY(new_dvol(ctx, v->nx, y1 - y0, &r));
 	r->nspans = ends[1] - ends[0];
+	r->max_cnt = v->max_cnt;
 	int rc = dalloc(ctx, &r->spans, r->nspans);
 	if (rc) { free_dvol(ctx, r); return rc; }
 	cudaMemcpyAsync(r->off, v->off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream);
@@ -2663,6 +2702,8 @@ int concat_rows(vo_ctx *ctx, const vo_dvol *a, const vo_dvol *b, const vo_dvol *
 	vo_dvol *r = nullptr;
 	VO_TRY(new_dvol(ctx, nx, ny, &r));
 	r->nspans = total;
+	r->max_cnt = 0;
+	for (auto p : parts) if (p) r->max_cnt = (r->max_cnt < 0 || p->max_cnt < 0) ? -1 : std::max(r->max_cnt, p->max_cnt);
 	int rc = dalloc(ctx, &r->spans, total);
 	if (rc) { free_dvol(ctx, r); return rc; }
 	unsigned long long col = 0;
