@@ -82,7 +82,8 @@ struct vo_ctx {
 	uint32_t scan_epoch = 0;                    // epoch of the last call (1 .. 2^22 - 1)
 	unsigned long long out_cap_hint = 0;        // intervals the recent staged results needed (+12 %): sizes the spans buffer up front
 	bool fused_scan = true;                     // vo_set_option("scan", "fused" | "classic")
-	unsigned long long last_ctr[16] = {};   // the counters as the last read_counters saw them (a deferred pass 1 is judged after pass 2)
+	unsigned long long last_ctr[18] = {};
+	bool staged_ctr_clean = false;    // pass 1 has just zeroed every counter: the staged gather that follows need not zero its own again   // the counters as the last read_counters saw them (a deferred pass 1 is judged after pass 2)
 	bool force_tile_pass1 = false;
 	bool force_simple_pass1 = false;  // vo_set_option("pass1", "simple"): always use the one-thread-per-(x,y,j) kernel
 	// Large scratch blocks (>= 1 MiB) released by dfree are kept WHOLE and handed to the next request they fit
@@ -403,12 +404,14 @@ constexpr int NCTR = 16;  // pass 1: [0] mid-pool cursor [2] redo count [3] big-
                           //         [6] [7] list cursors [10] tile cursor of the first launch; staged gathers (pass 2, ...): [1] stage-pool cursor [8] redo count [9] failures
                           //         [11] invalid input offsets seen by k_thresh (banded host-buffer call)
 
-int read_counters(vo_ctx *ctx, unsigned long long h[NCTR])
+constexpr int NREAD = NCTR + 2;   // ... what read_counters brings back: the counters, [NCTR] erosion's "data outside the z range" flag,
+                                  // [NCTR + 1] the grand total of the last fused scan + compaction (written, not accumulated)
+int read_counters(vo_ctx *ctx, unsigned long long h[NREAD])
 {
-	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, NCTR * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+	VO_CUDA(cudaMemcpyAsync(h, ctx->d_ctr, NREAD * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
 	VO_CUDA(cudaStreamSynchronize(ctx->stream));
-	static_assert(NCTR == 16, "vo_ctx::last_ctr");
-	std::memcpy(ctx->last_ctr, h, NCTR * sizeof(unsigned long long));
+	static_assert(NREAD == 18, "vo_ctx::last_ctr");
+	std::memcpy(ctx->last_ctr, h, NREAD * sizeof(unsigned long long));
 	return VO_OK;
 }
 
@@ -448,9 +451,10 @@ int scan_prepare(vo_ctx *ctx, unsigned int ntiles, uint32_t *epoch, unsigned lon
 	return VO_OK;
 }
 
+// done_ev (optional): recorded behind the last kernel, before the counters travel back
 template <typename Args, typename LaunchFast, typename LaunchBig>
 int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long long pool_guess,
-               LaunchFast launch_fast, LaunchBig launch_big, int nx, int ny, vo_dvol **out)
+               LaunchFast launch_fast, LaunchBig launch_big, int nx, int ny, vo_dvol **out, cudaEvent_t done_ev = nullptr)
 {
 	StageBuf sb(ctx);
 	RedoBuf rb(ctx);
@@ -468,7 +472,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	const bool small_tiles = fused && blocks_for(nlists, SCAN_TILE) < 4 * 148;
 	const unsigned int ntiles = blocks_for(nlists, small_tiles ? SCAN_THREADS * 2 : SCAN_TILE);
 	Tmp<unsigned long long> sums(ctx);
-	VO_TRY(dalloc(ctx, &sums.p, (unsigned long long)ntiles + 1));
+	if (!fused) VO_TRY(dalloc(ctx, &sums.p, (unsigned long long)ntiles + 1));
 	// fused: the spans buffer exists before the gather (sized from the recent results, at least one interval per list)
 	// and ONE kernel writes offsets and spans; a result that outgrows the buffer is compacted again into an exact one
 	unsigned long long out_cap = 0;
@@ -482,9 +486,12 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	if (ctx->redo_recent > 0) --ctx->redo_recent;
 	for (int attempt = 0; attempt < 4; ++attempt) {
 		// only the counters of the staged gather: a pass 1 may be in flight on the same stream (pipelined path)
-		VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
-		VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
-		unsigned long long h[NCTR] = {0}, total = 0;
+		if (!ctx->staged_ctr_clean) {
+			VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 1, 0, sizeof(unsigned long long), ctx->stream));
+			VO_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, 2 * sizeof(unsigned long long), ctx->stream));
+		}
+		ctx->staged_ctr_clean = false;
+		unsigned long long h[NREAD] = {0}, total = 0;
 		if (nlists) {
 			args.st = sb.st;
 			args.redo = rb.rd;
@@ -502,11 +509,11 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 				}
 				if (small_tiles)
 					k_scan_compact<2><<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
-					                                                            ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles,
+					                                                            ctx->scan_state + ctx->scan_cap, tbase, epoch, ctx->d_ctr + NCTR + 1,
 					                                                            nullptr, ctx->d_ctr + 15, ctx->max_epoch);
 				else
 					k_scan_compact<SCAN_ITEMS><<<ntiles, SCAN_THREADS, 0, ctx->stream>>>(sb.st, nlists, v->off, v->spans, out_cap, ctx->scan_state,
-					                                                                     ctx->scan_state + ctx->scan_cap, tbase, epoch, sums.p + ntiles,
+					                                                                     ctx->scan_state + ctx->scan_cap, tbase, epoch, ctx->d_ctr + NCTR + 1,
 					                                                                     nullptr, ctx->d_ctr + 15, ctx->max_epoch);
 				ctx->launches += skip_redo ? 2 : 3;
 			} else {
@@ -516,11 +523,13 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 				ctx->launches += skip_redo ? 4 : 5;
 			}
 			VO_CUDA(cudaGetLastError());
-			VO_CUDA(cudaMemcpyAsync(&total, sums.p + ntiles, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+			if (!fused) VO_CUDA(cudaMemcpyAsync(&total, sums.p + ntiles, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
 		} else {
 			VO_CUDA(cudaMemsetAsync(v->off, 0, sizeof(uint32_t), ctx->stream));
 		}
+		if (done_ev) cudaEventRecord(done_ev, ctx->stream);
 		VO_TRY(read_counters(ctx, h));
+		if (fused) total = h[NCTR + 1];
 		if (skip_redo && h[8] > 0) { skip_redo = false; ctx->redo_recent = 16; continue; }
 		if (h[8] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
 		if (h[9]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
@@ -915,7 +924,11 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	if (rc == VO_OK) rc = dalloc(ctx, &m->pool, pool_cap);
 	if (rc == VO_OK) rc = dalloc(ctx, &m->flags, 2 * ncols);
 	const unsigned long long nmask = 2ull * in->ny * ((in->nx + TX - 1) / TX);
-	if (rc == VO_OK) rc = dalloc(ctx, &m->tilemask, nmask);
+	// (the tile order's counters and cost estimates sit behind the tile masks: one block, one memset)
+	const unsigned long long ntiles_pre = (unsigned long long)((in->nx + P1_W - 1) / P1_W) * in->ny;
+	const bool ordered_pre = use_tile && ctx->tile_order && ntiles_pre >= 4096;
+	const unsigned long long nest = ordered_pre ? (ntiles_pre + 2 * P1_NBUCKET + 1) / 2 : 0;
+	if (rc == VO_OK) rc = dalloc(ctx, &m->tilemask, nmask + nest);
 	Tmp<uint4> thr(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &thr.p, in->nspans);
 	TilePlan plan;
@@ -925,9 +938,9 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, ntiles);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &multi_tiles.p, ntiles);
 	// tile order (expensive first): [2 * P1_NBUCKET counters | cost estimate per tile], and the permutation
-	Tmp<unsigned int> est(ctx), order(ctx);
-	const bool ordered = use_tile && ctx->tile_order && ntiles >= 4096;
-	if (rc == VO_OK && ordered) rc = dalloc(ctx, &est.p, ntiles + 2 * P1_NBUCKET);
+	Tmp<unsigned int> order(ctx);
+	const bool ordered = ordered_pre;
+	struct { unsigned int *p; } est{rc == VO_OK && ordered ? reinterpret_cast<unsigned int *>(m->tilemask + nmask) : nullptr};
 	if (rc == VO_OK && ordered) rc = dalloc(ctx, &order.p, ntiles);
 	RedoBuf rb(ctx);
 	const unsigned int redo_cap = (unsigned int)std::min<unsigned long long>(std::max<unsigned long long>(nslots, 1ull), 1ull << 22);
@@ -939,6 +952,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	for (int attempt = 0; attempt < 4; ++attempt) {
 		cudaError_t e = cudaMemsetAsync(ctx->d_ctr, 0, NCTR * sizeof(unsigned long long), ctx->stream);
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, cudaGetErrorString(e)));
+		ctx->staged_ctr_clean = defer;                       // (pass 2 follows at once and need not zero its counters again)
 		Pass1Args a;
 		a.nx = in->nx; a.ny = in->ny; a.J = t.J;
 		a.off = in->off; a.spans = in->spans; a.H = dt.H; a.reach = dt.reach;
@@ -946,16 +960,13 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 		a.redo = rb.rd;
 		a.wk = Work{nullptr, nslots, nullptr, 0u, nullptr};
 		if (nslots && tile_now) {
-			cudaMemsetAsync(m->tilemask, 0, nmask * sizeof(unsigned long long), ctx->stream);
+			cudaMemsetAsync(m->tilemask, 0, (nmask + nest) * sizeof(unsigned long long), ctx->stream);
 			ThreshArgs ta;
 			ta.nx = in->nx; ta.ny = in->ny; ta.J = t.J; ta.off = in->off; ta.spans = in->spans;
 			ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
 			ta.c_begin = 0; ta.c_end = ncols; ta.clip_lo = clip_lo; ta.clip_hi = clip_hi;
 			if (dual) { ta.dual = 1; ta.dual_lo = dual->lo; ta.dual_hi = dual->hi; ta.dual_bad = reinterpret_cast<unsigned int *>(ctx->d_ctr + 14); }
-			if (ordered) {
-				cudaMemsetAsync(est.p, 0, (ntiles + 2 * P1_NBUCKET) * sizeof(unsigned int), ctx->stream);
-				ta.est = est.p + 2 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw;
-			}
+			if (ordered) { ta.est = est.p + 2 * P1_NBUCKET; ta.tiles_xw = plan.tiles_xw; }
 			launch_thresh(ta, k_in, ctx->stream);
 			ctx->launches++;
 			if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p, order.p, 0u, (unsigned int)ntiles, 0u, 0u, ctx->stream);
@@ -993,7 +1004,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 		e = cudaGetLastError();
 		if (e != cudaSuccess) return bail(fail(ctx, VO_ERR_CUDA, std::string("k_pass1: ") + cudaGetErrorString(e)));
 		if (defer) { m->deferred = true; m->redo_cap = redo_cap; *out = m; return VO_OK; }
-		unsigned long long h[NCTR];
+		unsigned long long h[NREAD];
 		rc = read_counters(ctx, h);
 		if (rc) return bail(rc);
 		if (h[2] > redo_cap) {
@@ -1011,7 +1022,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	return bail(fail(ctx, VO_ERR_OVERFLOW, "mid pool did not converge"));
 }
 
-int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
+int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEvent_t done_ev = nullptr)
 {
 	if (y0 < 0 || y1 > m->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "pass 2 row range outside the mid volume");
 	Pass2Args a;
@@ -1030,11 +1041,11 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out)
 			ctx->kev_valid[1] = true;
 		},
 		[&](Pass2Args &g, unsigned int grid) { k_pass2<CAP_BIG><<<grid, 128, 0, s>>>(g); },
-		m->nx, y1 - y0, out);
+		m->nx, y1 - y0, out, done_ev);
 }
 
 // pass 2 of the dual form (k_pass2_rows_dual): hull of the mirrored slots, empty columns in reach, negateInv's clamping
-int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *reach, double lo, double hi, vo_dvol **out)
+int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *reach, double lo, double hi, vo_dvol **out, cudaEvent_t done_ev = nullptr)
 {
 	Pass2Args a;
 	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = 0; a.y1 = m->ny;
@@ -1050,7 +1061,7 @@ int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *re
 			ctx->kev_valid[1] = true;
 		},
 		[&](Pass2Args &, unsigned int) {},                       // (never needed: at most one interval per column)
-		m->nx, m->ny, out);
+		m->nx, m->ny, out, done_ev);
 }
 
 int brute(vo_ctx *ctx, const vo_dvol *in, double R, vo_dvol **out)
@@ -1087,7 +1098,7 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 			const bool deferred = mid->deferred, redo_skipped = mid->redo_skipped;
 			const uint64_t pool_cap = mid->pool_cap;
 			const unsigned int redo_cap = mid->redo_cap;
-			int rc = pass2(ctx, mid, 0, mid->ny, out);
+			int rc = pass2(ctx, mid, 0, mid->ny, out, ctx->ev[2]);   // (ev[2] behind the last kernel: run_staged has synchronised past it)
 			vo_dmid_free(ctx, mid);
 			if (deferred) {
 				// pass 2's synchronisation has read every counter: was the deferred pass 1 complete?
@@ -1105,8 +1116,6 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 			VO_TRY(rc);
 			break;
 		}
-		VO_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-		VO_CUDA(cudaEventSynchronize(ctx->ev[2]));
 		cudaEventElapsedTime(&t1, ctx->ev[0], ctx->ev[1]);
 		cudaEventElapsedTime(&t2, ctx->ev[1], ctx->ev[2]);
 	} else if (method == VO_METHOD_BRUTE_FORCE) {
@@ -1282,7 +1291,7 @@ int erode_dual(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, double 
 	cudaEventRecord(ctx->ev[1], ctx->stream);
 	const unsigned int redo_cap = mid->redo_cap;
 	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);    // (pass 1 has just made these the current tables)
-	int rc = pass2_dual(ctx, mid, dist.p, tc->dt.reach, zmin, zmax, out);
+	int rc = pass2_dual(ctx, mid, dist.p, tc->dt.reach, zmin, zmax, out, ctx->ev[2]);
 	vo_dmid_free(ctx, mid);
 	VO_TRY(rc);
 	// pass 2's synchronisation has read every counter: [14] a column did not qualify, [5] a tile saw a multi-interval
@@ -1297,8 +1306,6 @@ int erode_dual(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, double 
 	}
 	in->dual_state = 1;
 	ctx->dual_erosions++;
-	VO_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-	VO_CUDA(cudaEventSynchronize(ctx->ev[2]));
 	cudaEventElapsedTime(&t1, ctx->ev[0], ctx->ev[1]);
 	cudaEventElapsedTime(&t2, ctx->ev[1], ctx->ev[2]);
 	if (pt) { pt->ms1 = t1; pt->ms2 = t2; }
@@ -1917,7 +1924,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		for (auto st : ctx->s_hi) { cudaEvent_t e = pr.event(); cudaEventRecord(e, st); cudaStreamWaitEvent(ctx->stream, e, 0); }
 	}
 	cudaEventRecord(ctx->ev[2], ctx->stream);
-	unsigned long long h[NCTR];
+	unsigned long long h[NREAD];
 	std::vector<unsigned long long> hgb(3 * (size_t)nb + 1, 0ull);
 	if (rc == VO_OK && cudaMemcpyAsync(hgb.data(), gb.p, hgb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = PIPE_NA;
 	if (rc == VO_OK) rc = read_counters(ctx, h);
@@ -2210,7 +2217,7 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 		slab_redo(S);                                       // (whatever either launch set left on the redo list)
 	} else slab_pass1_rows(S, 0, jp + ny + jn, 0, 0, -1);
 	cudaEventRecord(S->ev1, sm);
-	unsigned long long h[NCTR];
+	unsigned long long h[NREAD];
 	VO_TRY(read_counters(ctx, h));
 	VO_CUDA(cudaGetLastError());
 	if (h[0] > S->mid->pool_cap) { ctx->pool_hint = h[0] + h[0] / 4; return fail(ctx, VO_ERR_OVERFLOW, "mid pool too small"); }
