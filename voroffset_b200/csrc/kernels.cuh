@@ -9,6 +9,8 @@
 //   cap tables     : host-computed doubles (vo_lib.cu: make_tables) so that every cap height carries the
 //                    reference's exact fp64 operation order, independent of GPU sqrt / FMA behaviour.
 #pragma once
+#include <type_traits>
+
 #include "run_union.cuh"
 #include "scan.cuh"
 
@@ -198,9 +200,12 @@ __device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot
 
 // The slots of output column (x, y) named by two bit masks (bit j-1 of m_up: class j of row y-j, of m_dn: class j
 // of row y+j; self: class 0 of the own row), fetched four at a time (independent loads) and folded into the union.
-template <int CAP>
-__device__ __forceinline__ void pass2_gather(const Pass2Args &a, RunUnion<CAP> &u, int x, int y,
-                                             unsigned long long m_up, unsigned long long m_dn, bool self_needed)
+// bit scans of the class masks: 32-bit words where floor(R) <= 32 (half the instructions of the 64-bit ones)
+__device__ __forceinline__ int mask_ffs(unsigned int m) { return __ffs((int)m); }
+__device__ __forceinline__ int mask_ffs(unsigned long long m) { return __ffsll((long long)m); }
+
+template <int CAP, typename M = unsigned long long>
+__device__ __forceinline__ void pass2_gather(const Pass2Args &a, RunUnion<CAP> &u, int x, int y, M m_up, M m_dn, bool self_needed)
 {
 	const size_t nx = (size_t)a.nx, midrow = (size_t)(a.J + 1) * nx;
 	const double2 *self = a.mid + (size_t)y * midrow + x;
@@ -212,8 +217,8 @@ __device__ __forceinline__ void pass2_gather(const Pass2Args &a, RunUnion<CAP> &
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			p[i] = self;
-			if (m_up) { const int j = __ffsll((long long)m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
-			else if (m_dn) { const int j = __ffsll((long long)m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
+			if (m_up) { const int j = mask_ffs(m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
+			else if (m_dn) { const int j = mask_ffs(m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
 		}
 		double2 v[4];
 #pragma unroll
@@ -289,9 +294,11 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 // those are the per-column windows read - instead of 2J+1 flags per consumer.
 constexpr int P2_TX = 128;
 
-template <int CAP>
+// WIDE = false: floor(R) <= 32, the class masks are 32-bit words.
+template <int CAP, bool WIDE = true>
 __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 {
+	typedef typename std::conditional<WIDE, unsigned long long, unsigned int>::type M;
 	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
 	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);
 	const int y = a.y0 + (int)(blockIdx.x / (unsigned)tiles_x);
@@ -300,23 +307,23 @@ __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 	const size_t nx = (size_t)a.nx;
 	const unsigned long long *t_up = a.tilemask, *t_dn = a.tilemask + (size_t)a.ny * tiles_x;
 	// coarse: bit j-1 of c_up = the tile of row y-j holds a column whose "dn" window has class j, ...
-	unsigned long long c_up = 0, c_dn = 0;
+	M c_up = 0, c_dn = 0;
 #pragma unroll
-	for (int h = 0; h < 2; ++h) {
+	for (int h = 0; h < (WIDE ? 2 : 1); ++h) {
 		const int j = lane + 1 + 32 * h;
 		bool pu = false, pd = false;
 		if (j <= a.J) {
 			if (y - j >= 0) pu = (__ldg(t_dn + (size_t)(y - j) * tiles_x + tile) >> j) & 1ull;
 			if (y + j < a.ny) pd = (__ldg(t_up + (size_t)(y + j) * tiles_x + tile) >> j) & 1ull;
 		}
-		c_up |= (unsigned long long)__ballot_sync(0xffffffffu, pu) << (32 * h);
-		c_dn |= (unsigned long long)__ballot_sync(0xffffffffu, pd) << (32 * h);
+		c_up |= (M)__ballot_sync(0xffffffffu, pu) << (32 * h);
+		c_dn |= (M)__ballot_sync(0xffffffffu, pd) << (32 * h);
 	}
 	if (x >= a.nx) return;
 	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
 	const size_t cc = (size_t)y * nx + x;
 	// windows of the candidate rows, four independent loads at a time (the masks are warp-uniform)
-	unsigned long long m_up = 0, m_dn = 0;
+	M m_up = 0, m_dn = 0;
 	const uint16_t w_up = __ldg(f_up + cc), w_dn = __ldg(f_dn + cc);
 	while (c_up | c_dn) {
 		int jj[4];
@@ -324,21 +331,21 @@ __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			jj[i] = 0; p[i] = f_up + cc;
-			if (c_up) { const int j = __ffsll((long long)c_up); c_up &= c_up - 1; jj[i] = -j; p[i] = f_dn + cc - (size_t)j * nx; }
-			else if (c_dn) { const int j = __ffsll((long long)c_dn); c_dn &= c_dn - 1; jj[i] = j; p[i] = f_up + cc + (size_t)j * nx; }
+			if (c_up) { const int j = mask_ffs(c_up); c_up &= c_up - 1; jj[i] = -j; p[i] = f_dn + cc - (size_t)j * nx; }
+			else if (c_dn) { const int j = mask_ffs(c_dn); c_dn &= c_dn - 1; jj[i] = j; p[i] = f_up + cc + (size_t)j * nx; }
 		}
 		uint16_t w[4];
 #pragma unroll
 		for (int i = 0; i < 4; ++i) w[i] = __ldg(p[i]);
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			if (jj[i] < 0) m_up |= (unsigned long long)flag_has(w[i], -jj[i]) << (-jj[i] - 1);
-			else if (jj[i] > 0) m_dn |= (unsigned long long)flag_has(w[i], jj[i]) << (jj[i] - 1);
+			if (jj[i] < 0) m_up |= (M)flag_has(w[i], -jj[i]) << (-jj[i] - 1);
+			else if (jj[i] > 0) m_dn |= (M)flag_has(w[i], jj[i]) << (jj[i] - 1);
 		}
 	}
 	double2 ulist[CAP];
 	RunUnion<CAP> u(ulist);
-	pass2_gather(a, u, x, y, m_up, m_dn, flag_has(w_up, 0) || flag_has(w_dn, 0));
+	pass2_gather<CAP, M>(a, u, x, y, m_up, m_dn, flag_has(w_up, 0) || flag_has(w_dn, 0));
 	const unsigned long long c = (unsigned long long)(y - a.y0) * nx + x;
 	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);

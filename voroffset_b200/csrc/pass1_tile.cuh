@@ -249,7 +249,10 @@ __global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
 	if (a.est) {
 		// one atomic per warp and tile (lanes are consecutive columns: usually a single tile)
 		const unsigned int tile = in_range ? (unsigned int)y * (unsigned int)a.tiles_xw + (unsigned int)(x / P1_W) : 0xffffffffu;
-		const unsigned int grp = __match_any_sync(0xffffffffu, tile);
+		// (a warp usually lies inside one tile - always when the row length is a multiple of the tile width: one plain
+		// reduction then, instead of grouping the lanes by tile first)
+		const bool one_tile = __all_sync(0xffffffffu, tile == __shfl_sync(0xffffffffu, tile, 0));
+		const unsigned int grp = one_tile ? 0xffffffffu : __match_any_sync(0xffffffffu, tile);
 		const unsigned int sl = __reduce_add_sync(grp, cost_l), ss = __reduce_add_sync(grp, cost_s), sr = __reduce_add_sync(grp, cost_r);
 		if (in_range && (threadIdx.x & 31) == __ffs(grp) - 1) {
 			const int tx = x / P1_W;
@@ -341,7 +344,8 @@ __global__ void __launch_bounds__(256) k_thresh_quad(ThreshArgs a)
 	if (a.est) {
 		// one atomic per warp and tile (a warp holds eight consecutive columns: usually a single tile)
 		const unsigned int tile = in_range ? (unsigned int)y * (unsigned int)a.tiles_xw + (unsigned int)(x / P1_W) : 0xffffffffu;
-		const unsigned int grp = __match_any_sync(0xffffffffu, tile);
+		const bool one_tile = __all_sync(0xffffffffu, tile == __shfl_sync(0xffffffffu, tile, 0));
+		const unsigned int grp = one_tile ? 0xffffffffu : __match_any_sync(0xffffffffu, tile);
 		const unsigned int sl = __reduce_add_sync(grp, cost_l), ss = __reduce_add_sync(grp, cost_s), sr = __reduce_add_sync(grp, cost_r);
 		if (in_range && lane == __ffs(grp) - 1) {
 			const int tx = x / P1_W;

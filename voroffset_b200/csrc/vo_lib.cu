@@ -1033,7 +1033,9 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEven
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
 		[&](Pass2Args &g) {
 			cudaEventRecord(ctx->kev[2], s);
-			if (g.J <= 63)
+			if (g.J <= 32)
+				k_pass2_rows<CAP_FAST, false><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+			else if (g.J <= 63)
 				k_pass2_rows<CAP_FAST><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
 			else
 				k_pass2<CAP_FAST><<<blocks_for(g.wk.n, 128), 128, 0, s>>>(g);
@@ -1861,7 +1863,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = y0; a2.y1 = y1;
 		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.pool_cap = m->pool_cap; a2.st = st; a2.redo = rd;
 		a2.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
-		k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		if (J <= 32) k_pass2_rows<CAP_FAST, false><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		else k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		a2.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
 		k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
 		if (fused) {
