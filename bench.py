@@ -19,7 +19,8 @@ One JSON line on stdout (rank 0):
   halo         per step: device time of the NCCL groups and host time stalled waiting for the halos (max over ranks)
   e2e          the same metric through the host-buffer C-ABI call: H2D of the CSR input from pinned memory, both passes,
                D2H of the CSR result, all inside the timed region (N = 1: the banded pipeline of vo_morph3d; N > 1:
-               upload, the slab step with its halo exchange, download on every rank)
+               vo_morph3d_rows on every rank - its slab with the floor(R) ghost rows of its neighbours cut from host
+               memory, the same banded pipeline, the slab's rows back; checked against the resident multi-GPU rows)
   roofline     dominant kernel (k_pass1_tile): algorithmic bytes / its event-timed duration
   cpu_baseline the reference's own code (oracle/_ref) on a bounded sample with all host threads
 """
@@ -502,35 +503,43 @@ def main():
     # ---- e2e: host buffers in, host buffers out, through the drop-in call ------------------------
     e2e = None
     if not a.no_e2e:
-        off_pin = torch.from_numpy(vol.off.view(np.int32)).pin_memory()
-        sp_pin = torch.from_numpy(vol.spans).pin_memory()
+        # N = 1: the grid as it is. N > 1: this rank's slab WITH the floor(R) ghost rows of its neighbours in the host buffer
+        # (the host-side halo of vo_morph3d_rows: a host application that holds the grid has them anyway), rows of the slab back
+        jp, jn = (J if rank > 0 else 0), (J if rank + 1 < world else 0)
+        ext = vol if world == 1 else _stack([_rows(vol, vol.ny - J, vol.ny) if jp else None, vol, _rows(vol, 0, J) if jn else None])
+        off_pin = torch.from_numpy(ext.off.view(np.int32)).pin_memory()
+        sp_pin = torch.from_numpy(ext.spans).pin_memory()
         h2d = off_pin.numel() * 4 + sp_pin.numel() * 8
         d2h = 0
-        # pinned result buffers of the N > 1 path (the single-GPU call returns library-owned pinned blocks)
-        out_pin = [torch.empty(ncols + 1, dtype=torch.int32).pin_memory(), torch.empty(4 * sp_pin.numel(), dtype=torch.float64).pin_memory()]
+        e2e_first = []
 
         def step_e2e():
             nonlocal d2h
             poff, pspans, n = _lib._u32p(), _lib._f64p(), C.c_uint64()
-            if mg is None:
+            if world == 1:
                 ctx.check(ctx.lib.vo_morph3d(ctx.handle, 0, 0, vol.nx, vol.ny, vol.zmin, vol.zmax, off_pin.data_ptr(),
                                              sp_pin.data_ptr(), R, C.byref(poff), C.byref(pspans), C.byref(n), None, None))
-                d2h = (ncols + 1) * 4 + int(n.value) * 16
-                ctx.lib.vo_free(C.cast(poff, C.c_void_p)); ctx.lib.vo_free(C.cast(pspans, C.c_void_p))
             else:
-                h = C.c_void_p()
-                ctx.check(ctx.lib.vo_dvol_upload(ctx.handle, vol.nx, vol.ny, off_pin.data_ptr(), sp_pin.data_ptr(), C.byref(h)))
-                d = morpho.DeviceVolume(ctx, h, vol)
-                out, _, _ = run_op("dilation", d, vol)
-                nseg_out = out.info()[2]
-                if out_pin[1].numel() < 2 * nseg_out:
-                    out_pin[1] = torch.empty(int(2.2 * nseg_out), dtype=torch.float64).pin_memory()
-                ctx.check(ctx.lib.vo_dvol_download(ctx.handle, out.handle, out_pin[0].data_ptr(), out_pin[1].data_ptr()))
-                d2h = (ncols + 1) * 4 + nseg_out * 16
-                out.free(); d.free()
+                ctx.check(ctx.lib.vo_morph3d_rows(ctx.handle, 0, 0, ext.nx, ext.ny, vol.zmin, vol.zmax, off_pin.data_ptr(),
+                                                  sp_pin.data_ptr(), R, jp, jp + vol.ny, C.byref(poff), C.byref(pspans), C.byref(n), None, None))
+            d2h = (ncols + 1) * 4 + int(n.value) * 16
+            if not e2e_first:                                  # checksum of the first result: the same rows as the resident arm's
+                o = np.ctypeslib.as_array(poff, shape=(ncols + 1,)).copy()
+                sp = np.ctypeslib.as_array(pspans, shape=(max(int(n.value), 1) * 2,))[:2 * int(n.value)].copy()
+                e2e_first.append((o, sp))
+            ctx.lib.vo_free(C.cast(poff, C.c_void_p)); ctx.lib.vo_free(C.cast(pspans, C.c_void_p))
 
         for _ in range(max(1, min(a.warmup, 2))):
             step_e2e()
+        if world > 1:
+            # the rows of the host-buffer call against the resident multi-GPU rows of the same slab, bit for bit
+            r0, _, _ = run_op("dilation", d_in, vol)
+            want = r0.download()
+            r0.free()
+            same = np.array_equal(want.off, e2e_first[0][0]) and np.array_equal(want.spans.reshape(-1).view(np.uint64), e2e_first[0][1].view(np.uint64))
+            parity["e2e_rows"] = all_ok(same)
+            if not parity["e2e_rows"]:
+                raise SystemExit("slab parity FAILED (host-buffer call with ghost rows)")
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):
@@ -539,7 +548,10 @@ def main():
         e2e_s = all_max(time.perf_counter() - t0)
         e2e = {"value": ncols * world * a.steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3 / a.steps,
-               "timing": "wall clock around the synchronous call(s) with pinned host buffers, max over ranks", "numa_node": numa}
+               "timing": "wall clock around the synchronous call(s) with pinned host buffers, max over ranks", "numa_node": numa,
+               "call": "vo_morph3d (banded pipeline)" if world == 1 else
+                       "vo_morph3d_rows per rank: the slab with its floor(R) ghost rows cut from host memory (no device-to-device exchange), "
+                       "banded pipeline, the slab's rows back"}
 
     if rank == 0:
         peak, peak_src = peaks()

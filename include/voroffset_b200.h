@@ -111,6 +111,21 @@ int vo_morph3d(vo_ctx *ctx, int op, int method, int nx, int ny, double zmin, dou
                uint32_t **out_off, double **out_spans, uint64_t *out_nspans,
                double *ms_pass1, double *ms_pass2);
 
+/* The same call on a WINDOW of rows: the operator runs on the grid (nx, ny) that is passed, but only the rows
+ * [row0, row1) of its result are computed to the end and returned (offsets starting at 0). Meant for a y-slab of a
+ * larger grid handed over together with its ghost rows - the decomposition of VoronoiVorPower.cpp:41-63,70-92 with the
+ * halo cut from HOST memory, where a caller that holds the whole grid has it anyway (no device-to-device exchange):
+ * `off` may point into the middle of the larger CSR (ny*nx+1 entries, off[0] != 0 allowed) and `spans` stays the
+ * base of the larger span array (span k of the window is spans[2k], k counted like the offsets). The ends of the
+ * passed grid are treated as the ends of the volume (erosion's border), so pass as many ghost rows as the operator
+ * reaches: floor(radius) for a dilation or an erosion, twice that for an opening or a closing; none at the true ends
+ * of the volume. A large 'ours' dilation runs as the banded pipeline of vo_morph3d (upload, passes and download
+ * overlap), every other case as upload - operator - rows - download.                                           */
+int vo_morph3d_rows(vo_ctx *ctx, int op, int method, int nx, int ny, double zmin, double zmax,
+                    const uint32_t *off, const double *spans, double radius, int row0, int row1,
+                    uint32_t **out_off, double **out_spans, uint64_t *out_nspans,
+                    double *ms_pass1, double *ms_pass2);
+
 /* Replaces  DoubleCompressedImage::dilate / erode / open / close / negate
  * (src/vor2d/DoubleCompressedImage.cpp:438-468,680-719). `r` is the argument of the member function,
  * untouched: dilate sweeps with R = r*rows, erode with R = r (DoubleCompressedImage.cpp:685-686,698-699). */

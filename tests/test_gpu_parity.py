@@ -178,6 +178,35 @@ def test_erosion_dual_form_declines_what_does_not_qualify(ctx, oracle):
         ctx.set_option("pass1", "auto")
 
 
+def test_row_window_call_matches_the_rows_of_the_whole_grid(ctx):
+    """vo_morph3d_rows: a y-slab handed over with its ghost rows (a window of the host CSR, offsets not starting at 0)
+    must give, bit for bit, the rows the call on the whole grid gives - through the banded pipeline (config-5 size) and
+    through the plain path (small grids, the other operations)."""
+    op = morpho.make_operator("ours", ctx)
+    big, R = synth.torus_z(2048), 32.0
+    J = int(R)
+    whole, _, _ = op.dilation(big, R)
+    for y0, y1 in ((0, 700), (700, 1500), (1500, 2048), (1017, 1091)):
+        e0, e1 = max(0, y0 - J), min(big.ny, y1 + J)
+        got, t1, t2 = op.morph_rows("dilation", big, R, e0, e1, y0 - e0, y1 - e0)
+        want = _rows_of(whole, y0, y1)
+        assert got.bit_equal(want), f"window [{y0}, {y1}) of the config-5 dilation differs from the whole-grid rows"
+    small, r = synth.torus_z(160, padding=12), 5.5
+    j = int(r)
+    for opn, ghost in (("dilation", j), ("erosion", j), ("opening", 2 * j), ("closing", 2 * j)):
+        whole, _, _ = morpho.apply_operation(op, opn, small, r)
+        for y0, y1 in ((0, 60), (60, 130), (130, small.ny)):
+            e0, e1 = max(0, y0 - ghost), min(small.ny, y1 + ghost)
+            got, _, _ = op.morph_rows(opn, small, r, e0, e1, y0 - e0, y1 - e0)
+            assert got.bit_equal(_rows_of(whole, y0, y1)), f"{opn}: window [{y0}, {y1}) differs"
+
+
+def _rows_of(vol, y0, y1):
+    c0, c1 = y0 * vol.nx, y1 * vol.nx
+    off = vol.off[c0:c1 + 1].astype(np.int64)
+    return vol.like(vol.nx, y1 - y0, (off - off[0]).astype(np.uint32), vol.spans[off[0]:off[-1]])
+
+
 def test_erosion_with_data_touching_the_z_bounds(ctx, oracle):
     """Erosion of 'ours' prunes with the clip range of negateInv (pass1_tile.cuh: saturated endpoints). A tight
     bounding box makes the lowest interval start EXACTLY at zmin and the highest end exactly at zmax

@@ -104,6 +104,45 @@ def test_config5_on_all_gpus_bit_identical_and_overlapped(ctx):
     mg.close()
 
 
+def test_erosion_in_dual_form_on_all_gpus(ctx):
+    """Volumes with one interval per column erode in dual form on every slab (the ranks agree first: one all-reduced
+    word). "erosion" = "dual" on every context makes a fallback an error, so this is that path - and a grid in which
+    only ONE slab holds a column with two intervals must make the whole group take the general path, same result."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    mg = multigpu.MultiGpu.single_process(list(range(n)))
+    op = morpho.make_operator("ours", ctx)
+    vol = synth.torus_z(512, padding=20)
+    want, _, _ = op.erosion(vol, 14.0)
+    for c in mg.contexts:
+        c.set_option("erosion", "dual")
+    for attempt in range(2):
+        got, _, _ = mg.morph("erosion", vol, 14.0)
+        assert got.bit_equal(want), f"dual erosion on {n} GPUs differs from one GPU (call {attempt})"
+    for c in mg.contexts:
+        c.set_option("erosion", "auto")
+    for opn in ("opening", "closing"):
+        want, _, _ = morpho.apply_operation(op, opn, vol, 14.0)
+        got, _, _ = mg.morph(opn, vol, 14.0)
+        assert got.bit_equal(want), f"{opn} on {n} GPUs"
+    # one column of the LAST slab gets a second interval
+    from voroffset_b200.volume import CompressedVolume
+    lists = [tuple(vol.at(x, y)) for y in range(vol.ny) for x in range(vol.nx)]
+    c = vol.nx // 2 + vol.nx * (vol.ny - 60)
+    a0, b0 = lists[c]
+    lists[c] = (a0, a0 + 0.3 * (b0 - a0), a0 + 0.6 * (b0 - a0), b0)
+    mixed = CompressedVolume.from_lists(vol.nx, vol.ny, lists, origin=vol.origin, extent=vol.extent, spacing=vol.spacing, padding=vol.padding)
+    want, _, _ = op.erosion(mixed, 14.0)
+    got, _, _ = mg.morph("erosion", mixed, 14.0)
+    assert got.bit_equal(want), "mixed grid: the group must agree on the general path"
+    for c in mg.contexts:
+        c.set_option("erosion", "dual")
+    with pytest.raises(_lib.VoroffsetError):
+        mg.morph("erosion", mixed, 14.0)
+    mg.close()
+
+
 def test_halo_capacity_overflow_falls_back(ctx):
     n = _ngpu()
     if n < 2:

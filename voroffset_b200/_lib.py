@@ -26,7 +26,7 @@ _vp = C.c_void_p
 # every symbol include/voroffset_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "vo_create", "vo_destroy", "vo_last_error", "vo_version", "vo_span_bytes", "vo_free", "vo_stream",
-    "vo_launch_count", "vo_morph3d", "vo_morph2d", "vo_xor3d", "vo_dvol_upload", "vo_dvol_download",
+    "vo_launch_count", "vo_morph3d", "vo_morph3d_rows", "vo_morph2d", "vo_xor3d", "vo_dvol_upload", "vo_dvol_download",
     "vo_dvol_info", "vo_dvol_free", "vo_dvol_rows", "vo_dvol_concat_rows", "vo_morph3d_dev", "vo_xor3d_dev",
     "vo_pass1_dev", "vo_pass2_dev", "vo_dmid_free", "vo_dmid_info", "vo_morph2d_dev",
     "vo_mark", "vo_elapsed_ms", "vo_last_profile", "vo_dvol_from_device", "vo_set_option", "vo_dvol_rows_to",
@@ -67,6 +67,9 @@ def load() -> C.CDLL:
     L.vo_launch_count.restype = C.c_uint64
     L.vo_morph3d.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp,
                              C.c_double, C.POINTER(_u32p), C.POINTER(_f64p), C.POINTER(C.c_uint64), _f64p, _f64p]
+    L.vo_morph3d_rows.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp,
+                                  C.c_double, C.c_int, C.c_int, C.POINTER(_u32p), C.POINTER(_f64p), C.POINTER(C.c_uint64),
+                                  _f64p, _f64p]
     L.vo_morph2d.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_double,
                              C.POINTER(_u32p), C.POINTER(_f64p), C.POINTER(C.c_uint64), _f64p]
     L.vo_xor3d.argtypes = [_vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _vp, _vp, _vp, _vp,

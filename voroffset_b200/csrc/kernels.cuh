@@ -402,6 +402,22 @@ __global__ void __launch_bounds__(ED_THREADS) k_empty_dist(const uint32_t *__res
 	}
 }
 
+// Does a volume qualify for the dual form? *flag is raised when a column holds several intervals or an interval is not
+// strictly inside (lo, hi) (or when the host already knows a reason, init_bad). The single-GPU path lets k_thresh find
+// out while it runs; the ranks of a multi-GPU group have to AGREE before they exchange anything, so they check first.
+__global__ void __launch_bounds__(256) k_dual_check(const uint32_t *__restrict__ off, const double2 *__restrict__ spans, unsigned long long ncols,
+                                                    double lo, double hi, unsigned int init_bad, unsigned int *flag)
+{
+	const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c == 0 && init_bad) *flag = 1u;
+	if (c >= ncols) return;
+	const uint32_t o0 = __ldg(off + c), o1 = __ldg(off + c + 1);
+	if (o1 == o0) return;
+	bool bad = o1 - o0 > 1u;
+	if (!bad) { const double2 p = __ldg(spans + o0); bad = !(p.x > lo && p.x <= p.y && p.y < hi); }
+	if (bad) *flag = 1u;
+}
+
 // Pass 2 of the dual form: same segment / tile-mask logic as k_pass2_rows; the fold is a hull (no running union), an
 // output column with an empty column (or the border) in reach is empty, the rest goes through negateInv's clamping.
 __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows_dual(Pass2Args a)

@@ -151,7 +151,7 @@ struct ThreshArgs {
 	// non-decreasing or point beyond `nspans` raise *bad and are read as empty columns; the tile kernel of the band
 	// then does nothing and the host reports VO_ERR_ARG
 	unsigned int *bad = nullptr;
-	uint32_t nspans = 0;
+	uint32_t nspans = 0, nspans_lo = 0;                  // valid offsets: [nspans_lo, nspans] (a row window of a larger CSR starts above 0)
 	// Dual form (erosion of a volume with at most one interval per column, vo_lib.cu: erode_dual): the thresholds of the
 	// MIRRORED intervals (-z1, -z2), whose "dilation" hull is the erosion's intersection. Columns that do not qualify -
 	// several intervals, an interval that is not strictly inside (dual_lo, dual_hi) or has z1 > z2 - raise *dual_bad.
@@ -163,7 +163,7 @@ struct ThreshArgs {
 // offsets of one column as read from untrusted input (ThreshArgs::bad): an invalid pair becomes an empty column
 __device__ __forceinline__ void thresh_guard(const ThreshArgs &a, uint32_t &q0, uint32_t &q1)
 {
-	if (a.bad && (q1 < q0 || q1 > a.nspans)) { *a.bad = 1u; q0 = q1 = 0; }
+	if (a.bad && (q1 < q0 || q1 > a.nspans || q0 < a.nspans_lo)) { *a.bad = 1u; q0 = q1 = a.nspans_lo; }
 }
 
 __device__ __forceinline__ void thresh_zero_bank(const ThreshArgs &a)
@@ -174,7 +174,7 @@ __device__ __forceinline__ void thresh_zero_bank(const ThreshArgs &a)
 	}
 }
 
-__global__ void __launch_bounds__(256) k_thresh(ThreshArgs a)
+__global__ void __launch_bounds__(256, 6) k_thresh(ThreshArgs a)
 {
 	extern __shared__ double s_DE[];
 	double *s_D = s_DE, *s_E = s_DE + a.J + 2;

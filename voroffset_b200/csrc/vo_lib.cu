@@ -1047,13 +1047,16 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEven
 }
 
 // pass 2 of the dual form (k_pass2_rows_dual): hull of the mirrored slots, empty columns in reach, negateInv's clamping
-int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *reach, double lo, double hi, vo_dvol **out, cudaEvent_t done_ev = nullptr)
+int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *reach, double lo, double hi, vo_dvol **out, cudaEvent_t done_ev = nullptr,
+               int y0 = 0, int y1 = -1)
 {
+	if (y1 < 0) y1 = m->ny;
+	if (y0 < 0 || y1 > m->ny || y0 > y1) return fail(ctx, VO_ERR_ARG, "pass 2 row range outside the mid volume");
 	Pass2Args a;
-	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = 0; a.y1 = m->ny;
+	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = y0; a.y1 = y1;
 	a.mid = m->slots; a.flags = m->flags; a.tilemask = m->tilemask; a.pool = m->pool; a.pool_cap = m->pool_cap;
 	a.dist = dist; a.reach = reach; a.lo = lo; a.hi = hi;
-	const unsigned long long nlists = (unsigned long long)m->nx * m->ny;
+	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull,
 		[&](Pass2Args &g) {
@@ -1063,7 +1066,7 @@ int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *re
 			ctx->kev_valid[1] = true;
 		},
 		[&](Pass2Args &, unsigned int) {},                       // (never needed: at most one interval per column)
-		m->nx, m->ny, out, done_ev);
+		m->nx, y1 - y0, out, done_ev);
 }
 
 int brute(vo_ctx *ctx, const vo_dvol *in, double R, vo_dvol **out)
@@ -1275,10 +1278,11 @@ int erode_with(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, int by0
 // complement kernels. Whether the input qualifies is checked by k_thresh while it runs (no separate pass, no
 // synchronisation): DUAL_NA = it did not (or cannot be known to), the caller takes the general path.
 constexpr int DUAL_NA = -2;
-int erode_dual(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt)
+// (y0, y1: only these rows of the result - a y-slab that was handed its halo rows; default: all)
+int erode_dual(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt, int y0 = 0, int y1 = -1)
 {
 	const unsigned long long ncols = (unsigned long long)in->nx * in->ny;
-	if (in->dual_state == 2 || ncols == 0 || in->nspans > ncols || ctx->force_simple_pass1) return DUAL_NA;
+	if (in->dual_state == 2 || ncols == 0 || in->nspans > ncols || ctx->force_simple_pass1 || (in->max_cnt > 1)) return DUAL_NA;
 	if (check_radius(ctx, R) != VO_OK || !pass1_uses_tile(ctx, in, R)) { ctx->err.clear(); return DUAL_NA; }
 	float t1 = 0, t2 = 0;
 	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1293,7 +1297,7 @@ int erode_dual(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, double 
 	cudaEventRecord(ctx->ev[1], ctx->stream);
 	const unsigned int redo_cap = mid->redo_cap;
 	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);    // (pass 1 has just made these the current tables)
-	int rc = pass2_dual(ctx, mid, dist.p, tc->dt.reach, zmin, zmax, out, ctx->ev[2]);
+	int rc = pass2_dual(ctx, mid, dist.p, tc->dt.reach, zmin, zmax, out, ctx->ev[2], y0, y1);
 	vo_dmid_free(ctx, mid);
 	VO_TRY(rc);
 	// pass 2's synchronisation has read every counter: [14] a column did not qualify, [5] a tile saw a multi-interval
@@ -1557,15 +1561,25 @@ struct PipeRes {
 	}
 };
 
+// Row window (keep0, keep1; default: everything): only the rows [keep0, keep1) of the result are produced and returned
+// (offsets starting at 0) - a y-slab of a larger grid passed WITH its floor(R) ghost rows on either side, cut from host
+// memory (vo_morph3d_rows: the multi-GPU host-buffer call, where the host holds every slab's neighbours anyway, so the
+// halo needs no device-to-device exchange). `off` may then point into the middle of a larger CSR: the offsets are taken
+// as they are (off[0] != 0) and `spans` is the base of the whole span array.
 int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, const double *spans, double R,
-                          uint32_t **out_off, double **out_spans, uint64_t *out_nspans, PassTimes *pt)
+                          uint32_t **out_off, double **out_spans, uint64_t *out_nspans, PassTimes *pt, int keep0 = 0, int keep1 = -1)
 {
 	if (ctx->force_simple_pass1 || ctx->no_pipeline) return PIPE_NA;
 	if (check_radius(ctx, R) != VO_OK) return PIPE_NA;             // let the plain path report it
 	const int J = (int)std::floor(R);
 	const unsigned long long ncols = (unsigned long long)nx * ny;
-	if (nx <= 0 || ny <= 0 || !off || off[0] != 0 || ncols >= (1ull << 32) - 8) return PIPE_NA;
-	const uint64_t nspans = off[ncols];
+	if (keep1 < 0) keep1 = ny;
+	if (nx <= 0 || ny <= 0 || !off || ncols >= (1ull << 32) - 8 || keep0 < 0 || keep1 > ny || keep0 >= keep1) return PIPE_NA;
+	const bool whole = keep0 == 0 && keep1 == ny;
+	if (whole && off[0] != 0) return PIPE_NA;
+	const uint32_t obase = off[0];                                 // the device arrays are indexed by the offsets as they are: pointers shifted by this
+	if (off[ncols] < obase) return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
+	const uint64_t nspans = off[ncols] - obase;
 	const double k_in = (double)nspans / (double)ncols;
 	// Bands of rows: eight by default (vo_set_option("bands", N)) - enough to overlap the copies with the passes, few
 	// enough that a launch set of pass 1 still has many tiles per warp. (Small bands at both ends and large ones in
@@ -1610,11 +1624,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	// reads every offset anyway (ThreshArgs::bad) - a host loop over 4 M offsets would cost more than a band's upload.
 	for (int b = 0; b <= nb; ++b) {
 		const uint32_t o = off[(unsigned long long)ys[b] * nx];
-		if (o > nspans || (b > 0 && o < off[(unsigned long long)ys[b - 1] * nx])) return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
+		if (o < obase || o - obase > nspans || (b > 0 && o < off[(unsigned long long)ys[b - 1] * nx])) return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
 	}
 	for (int b = 1; b < nb; ++b) {                           // (a band's upload ends one row below it)
 		const unsigned long long c = (unsigned long long)std::min(ny, ys[b] + 1) * nx;
-		if (off[c] > nspans || off[c] < off[(unsigned long long)ys[b] * nx] || off[c] > off[(unsigned long long)ys[b + 1] * nx])
+		if (off[c] - obase > nspans || off[c] < off[(unsigned long long)ys[b] * nx] || off[c] > off[(unsigned long long)ys[b + 1] * nx])
 			return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
 	}
 
@@ -1643,6 +1657,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	VO_TRY(dalloc(ctx, &m->flags, 2 * ncols));
 	Tmp<uint4> thr(ctx);
 	VO_TRY(dalloc(ctx, &thr.p, nspans));
+	double2 *const d_sp = in->spans - obase;                // indexed by the host's offsets as they are
+	uint4 *const d_thr = thr.p - obase;
 	TilePlan plan;
 	VO_TRY(plan.init(ctx, nx, J, k_in, ctx->pipe_warps, ctx->pipe_ctas, ctx->pipe_quota,
 	                 (unsigned int)(((nx + P1_W - 1) / P1_W) * (unsigned int)BH)));
@@ -1703,7 +1719,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	if (!ctx->s_ctl && cudaStreamCreateWithFlags(&ctx->s_ctl, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
 
 	// result buffers (pinned): offsets are exact, the span buffer is sized from the last result
-	uint32_t *ho = (uint32_t *)host_block((ncols + 1) * sizeof(uint32_t));
+	const unsigned long long ckeep0 = (unsigned long long)keep0 * nx, nkeep = (unsigned long long)(keep1 - keep0) * nx;
+	uint32_t *ho = (uint32_t *)host_block((nkeep + 1) * sizeof(uint32_t));
 	double *hs = (double *)host_block(hs_cap * sizeof(double2));
 	unsigned long long *h_tot = (unsigned long long *)host_block((size_t)nb * sizeof(unsigned long long));
 	auto drop_host = [&]() { vo_free(ho); vo_free(hs); };
@@ -1721,7 +1738,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		const unsigned long long c0 = (unsigned long long)y0 * nx, c1 = (unsigned long long)y1 * nx;
 		cudaMemcpyAsync(in->off + c0, off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, pr.s_in);
 		if (off[c1] > off[c0])
-			cudaMemcpyAsync(in->spans + off[c0], spans + 2 * (size_t)off[c0], (size_t)(off[c1] - off[c0]) * sizeof(double2), cudaMemcpyHostToDevice, pr.s_in);
+			cudaMemcpyAsync(d_sp + off[c0], spans + 2 * (size_t)off[c0], (size_t)(off[c1] - off[c0]) * sizeof(double2), cudaMemcpyHostToDevice, pr.s_in);
 		ev_in[b] = pr.event();
 		ev_done[b] = pr.event();
 		cudaEventRecord(ev_in[b], pr.s_in);
@@ -1763,17 +1780,17 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 
 	// launch parameters shared by all bands
 	ThreshArgs ta;
-	ta.nx = nx; ta.ny = ny; ta.J = J; ta.off = in->off; ta.spans = in->spans;
-	ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = thr.p;
+	ta.nx = nx; ta.ny = ny; ta.J = J; ta.off = in->off; ta.spans = d_sp;
+	ta.Dmono = tt.Dmono; ta.Emono = tt.Emono; ta.G = tt.G; ta.reach = dt.reach; ta.thr = d_thr;
 	ta.clip_lo = -std::numeric_limits<double>::infinity(); ta.clip_hi = std::numeric_limits<double>::infinity();
-	ta.bad = reinterpret_cast<unsigned int *>(ctx->d_ctr + 11); ta.nspans = (uint32_t)nspans;
+	ta.bad = reinterpret_cast<unsigned int *>(ctx->d_ctr + 11); ta.nspans = (uint32_t)(obase + nspans); ta.nspans_lo = obase;
 	Pass1TileArgs g;
 	g.nx = nx; g.ny = ny;
-	g.off = in->off; g.spans = in->spans; g.thr = thr.p; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
+	g.off = in->off; g.spans = d_sp; g.thr = d_thr; g.Ht = tt.Ht; g.Ef = tt.Ef; g.jmax = tt.jmax;
 	g.mid = m->slots; g.flags = m->flags; g.tilemask = m->tilemask; g.pool = m->pool; g.cursor = ctx->d_ctr; g.pool_cap = m->pool_cap;
 	g.bad = ta.bad;
 	Pass1Args a1;
-	a1.nx = nx; a1.ny = ny; a1.J = J; a1.off = in->off; a1.spans = in->spans; a1.H = dt.H; a1.reach = dt.reach;
+	a1.nx = nx; a1.ny = ny; a1.J = J; a1.off = in->off; a1.spans = d_sp; a1.H = dt.H; a1.reach = dt.reach;
 	a1.mid = m->slots; a1.pool = m->pool; a1.cursor = ctx->d_ctr; a1.pool_cap = m->pool_cap;
 	auto redo_of = [&](int b) { return Redo{redo1.p + (size_t)b * rcap1, reinterpret_cast<unsigned int *>(gb.p + 2 * nb + 1 + b), rcap1}; };
 
@@ -1839,17 +1856,34 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const bool fused = ctx->fused_scan;
 	std::vector<uint32_t> scan_epoch(nb, 0u);
 	std::vector<unsigned long long> scan_tbase(nb, 0ull);
+	// (row window: a band's second half covers its rows inside [keep0, keep1); bands with none only take part in pass 1.
+	// prev_act = the last band before b with rows to produce: the running total and the scan chain skip the others.)
+	std::vector<int> prev_act(nb, -1);
+	std::vector<char> act(nb, 0);
+	int last_act = -1;
+	for (int b = 0, pa = -1; b < nb; ++b) {
+		prev_act[b] = pa;
+		act[b] = std::max(ys2[b], keep0) < std::min(ys2[b + 1], keep1);
+		if (act[b]) { pa = b; last_act = b; }
+	}
+	auto rows2 = [&](int b) { return std::max(0, std::min(ys2[b + 1], keep1) - std::max(ys2[b], keep0)); };
 	if (fused) {
 		unsigned int most = 1;
-		for (int b = 0; b < nb; ++b) most = std::max(most, blocks_for((unsigned long long)nx * (ys2[b + 1] - ys2[b]), SCAN_TILE));
+		for (int b = 0; b < nb; ++b) most = std::max(most, blocks_for((unsigned long long)nx * rows2(b), SCAN_TILE));
 		VO_TRY(scan_reserve(ctx, most));
 		for (int b = 0; b < nb; ++b) {
-			const unsigned int nt = blocks_for((unsigned long long)nx * (ys2[b + 1] - ys2[b]), SCAN_TILE);
+			if (!act[b]) continue;
+			const unsigned int nt = blocks_for((unsigned long long)nx * rows2(b), SCAN_TILE);
 			VO_TRY(scan_prepare(ctx, nt, &scan_epoch[b], &scan_tbase[b]));
 		}
 	}
 	auto second_half = [&](int b) {
-		const int y0 = ys2[b], y1 = ys2[b + 1];
+		const int y0 = std::max(ys2[b], keep0), y1 = std::min(ys2[b + 1], keep1);
+		if (!act[b]) {                                      // pass 1's redo launch still has to run (and keep the ev_r1 chain whole)
+			pass1_redo(b, sh[b & 1]);
+			return;
+		}
+		const int pb = prev_act[b];
 		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
 		const unsigned int nt = blocks_for(nlists, SCAN_TILE);
 		unsigned long long *sums_b = sums.p + (size_t)b * (nt_max + 1);
@@ -1870,16 +1904,16 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		if (fused) {
 			// ONE kernel: offsets (from the running total gb[b] of the bands before) and spans of the band; the bands'
 			// kernels follow one another (the running total is a chain anyway, and each takes a few microseconds)
-			if (b > 0) cudaStreamWaitEvent(sm, ev_scan[b - 1], 0);
+			if (pb >= 0) cudaStreamWaitEvent(sm, ev_scan[pb], 0);
 			k_scan_compact<SCAN_ITEMS><<<nt, SCAN_THREADS, 0, sm>>>(st, nlists, dout->off + c0, dout->spans, dcap, ctx->scan_state,
-			                                            ctx->scan_state + ctx->scan_cap, scan_tbase[b], scan_epoch[b], gb.p + b + 1, gb.p + b);
+			                                            ctx->scan_state + ctx->scan_cap, scan_tbase[b], scan_epoch[b], gb.p + b + 1, gb.p + pb + 1);
 			ev_scan[b] = pr.event();
 			cudaEventRecord(ev_scan[b], sm);
 			ctx->launches += 3;
 		} else {
 			k_scan_reduce<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b);
-			if (b > 0) cudaStreamWaitEvent(sm, ev_scan[b - 1], 0);
-			k_scan_tiles<<<1, 1024, 0, sm>>>(sums_b, nt, gb.p + b, gb.p + b + 1);
+			if (pb >= 0) cudaStreamWaitEvent(sm, ev_scan[pb], 0);
+			k_scan_tiles<<<1, 1024, 0, sm>>>(sums_b, nt, gb.p + pb + 1, gb.p + b + 1);
 			ev_scan[b] = pr.event();
 			cudaEventRecord(ev_scan[b], sm);
 			k_scan_apply<<<nt, SCAN_THREADS, 0, sm>>>(st.cnt, nlists, sums_b, dout->off + c0);
@@ -1907,7 +1941,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	}
 	uint64_t base = 0;          // intervals of the bands downloaded so far
 	for (int b = 0; b < nb && rc == VO_OK; ++b) {
-		const int y0 = ys2[b], y1 = ys2[b + 1];
+		if (!act[b]) continue;
+		const int y0 = std::max(ys2[b], keep0), y1 = std::min(ys2[b + 1], keep1);
 		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
 		if (cudaEventSynchronize(ev_tot[b]) != cudaSuccess) { rc = PIPE_NA; break; }
 		const uint64_t tot = h_tot[b];
@@ -1917,7 +1952,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			break;
 		}
 		mark("download begin", b, pr.s_out);
-		cudaMemcpyAsync(ho + c0, dout->off + c0, (nlists + (b == nb - 1 ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+		cudaMemcpyAsync(ho + (c0 - ckeep0), dout->off + c0, (nlists + (b == last_act ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
 		if (tot > base) cudaMemcpyAsync(hs + 2 * base, dout->spans + base, (tot - base) * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
 		mark("download end", b, pr.s_out);
 		base = tot;
@@ -1996,6 +2031,8 @@ struct vo_slab {
 	unsigned int redo_cap = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 	bool overlapped = false;
+	bool dual = false;                              // erosion in dual form (erode_dual): mirrored intervals through pass 1, k_pass2_rows_dual
+	double dual_zmin = 0, dual_zmax = 0;            // ... the z range of the erosion
 };
 
 namespace {
@@ -2035,6 +2072,7 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	ta.nx = nx; ta.ny = S->ext->ny; ta.J = J; ta.off = S->ext->off; ta.spans = S->ext->spans;
 	ta.Dmono = tc->tt.Dmono; ta.Emono = tc->tt.Emono; ta.G = tc->tt.G; ta.reach = tc->dt.reach; ta.thr = S->thr;
 	ta.clip_lo = S->clip_lo; ta.clip_hi = S->clip_hi;
+	if (S->dual) { ta.dual = 1; ta.dual_lo = S->dual_zmin - 1; ta.dual_hi = S->dual_zmax + 1; ta.dual_bad = reinterpret_cast<unsigned int *>(ctx->d_ctr + 14); }
 	ta.c_begin = (unsigned long long)y0 * nx; ta.c_end = (unsigned long long)y1 * nx;
 	if (S->est) { ta.est = S->est + 4 * P1_NBUCKET; ta.tiles_xw = S->plan.tiles_xw; }
 	launch_thresh(ta, S->k_in, sm);
@@ -2064,7 +2102,7 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	S->plan.launch(ctx, g, (unsigned int)S->plan.tiles_xw * (unsigned int)y0, (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0),
 	               side ? S->big_tiles_b : S->big_tiles, side ? S->multi_tiles_b : S->multi_tiles, sm,
 	               (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
-	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms, bank, order);
+	               (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), reserve_sms, bank, order, S->dual);
 	if (interior) { cudaEventRecord(ctx->kev[1], sm); ctx->kev_valid[0] = true; }
 	if (side) return;
 	slab_redo(S);
@@ -2073,6 +2111,7 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 // lists that outgrew the fast capacity, and oversized tiles: one strided launch over the redo list (idempotent)
 void slab_redo(vo_slab *S)
 {
+	if (S->dual) return;                                    // (nothing can land on the redo list; slab_finish checks that nothing did)
 	vo_ctx *ctx = S->ctx;
 	cudaStream_t sm = ctx->stream;
 	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
@@ -2091,7 +2130,8 @@ struct HaloOut { void *d_off; void *d_spans; uint64_t cap; };   // send buffer o
 
 int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_next, uint64_t cap_prev, uint64_t cap_next,
                HaloOut to_prev, HaloOut to_next, void *wait_stream, vo_slab **out,
-               double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity())
+               double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity(),
+               bool dual = false, double dual_zmin = 0, double dual_zmax = 0)
 {
 	VO_TRY(check_radius(ctx, R));
 	const int J = (int)std::floor(R), nx = own->nx, ny = own->ny;
@@ -2112,6 +2152,7 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	if (!S) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
 	S->ctx = ctx; S->nx = nx; S->ny = ny; S->J = J; S->jp = jp; S->jn = jn; S->R = R;
 	S->cap_prev = cap_prev; S->cap_next = cap_next; S->n_own = own->nspans; S->clip_lo = clip_lo; S->clip_hi = clip_hi;
+	S->dual = dual; S->dual_zmin = dual_zmin; S->dual_zmax = dual_zmax;
 	auto bail = [&](int rc) { free_slab(S); return rc; };
 	int rc = new_dvol(ctx, nx, ey, &S->ext);
 	if (rc == VO_OK) rc = dalloc(ctx, &S->ext->spans, total);
@@ -2227,6 +2268,16 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 	if (h[2] > S->redo_cap || h[4]) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
 	S->mid->pool_used = h[0];
 	ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
+	if (S->dual) {
+		// (the ranks agreed beforehand that every slab qualifies: k_dual_check in vo_mg.cuh)
+		if (h[14] || h[5] || h[2]) return fail(ctx, VO_ERR_OVERFLOW, "dual erosion: a column did not qualify after all");
+		Tmp<uint8_t> dist(ctx);
+		VO_TRY(dalloc(ctx, &dist.p, (unsigned long long)nx * S->ext->ny));
+		k_empty_dist<<<(unsigned int)S->ext->ny, ED_THREADS, (size_t)((nx + 31) / 32) * sizeof(uint32_t), sm>>>(S->ext->off, nx, dist.p);
+		ctx->launches++;
+		TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
+		VO_TRY(pass2_dual(ctx, S->mid, dist.p, tc->dt.reach, S->dual_zmin, S->dual_zmax, out, nullptr, jp, jp + ny));
+	} else
 	VO_TRY(pass2(ctx, S->mid, jp, jp + ny, out));
 	VO_CUDA(cudaEventRecord(S->ev2, sm));
 	VO_CUDA(cudaEventSynchronize(S->ev2));
@@ -2900,6 +2951,56 @@ int vo_morph3d(vo_ctx *ctx, int op, int method, int nx, int ny, double zmin, dou
 	VO_TRY(rc);
 	rc = download_new(ctx, res, out_off, out_spans, out_nspans);
 	free_dvol(ctx, res);
+	VO_TRY(rc);
+	if (ms_pass1) *ms_pass1 = pt.ms1;
+	if (ms_pass2) *ms_pass2 = pt.ms2;
+	return VO_OK;
+}
+
+int vo_morph3d_rows(vo_ctx *ctx, int op, int method, int nx, int ny, double zmin, double zmax,
+                    const uint32_t *off, const double *spans, double radius, int row0, int row1,
+                    uint32_t **out_off, double **out_spans, uint64_t *out_nspans, double *ms_pass1, double *ms_pass2)
+{
+	if (!ctx || !out_off || !out_spans) return VO_ERR_ARG;
+	ctx->err.clear();
+	DeviceGuard g(ctx->device);
+	if (nx < 0 || ny < 0 || !off) return fail(ctx, VO_ERR_ARG, "bad grid / offsets");
+	if (row0 < 0 || row1 > ny || row0 > row1) return fail(ctx, VO_ERR_ARG, "row window outside the grid");
+	PassTimes pt;
+	if (op == VO_OP_DILATION && method == VO_METHOD_OURS && row0 < row1) {
+		const int prc = dilate_ours_pipelined(ctx, nx, ny, off, spans, radius, out_off, out_spans, out_nspans, &pt, row0, row1);
+		if (prc == VO_OK) {
+			if (ms_pass1) *ms_pass1 = pt.ms1;
+			if (ms_pass2) *ms_pass2 = pt.ms2;
+			return VO_OK;
+		}
+		if (prc != PIPE_NA) return prc;
+		ctx->err.clear();
+	}
+	// plain path: the window as a volume of its own (offsets rebased on the host), the operator, the rows asked for
+	VO_TRY(check_dims(ctx, nx, ny));
+	const unsigned long long n = (unsigned long long)nx * ny;
+	const uint32_t obase = off[0];
+	std::vector<uint32_t> rel;
+	const uint32_t *o = off;
+	if (obase) {
+		rel.resize(n + 1);
+		for (unsigned long long i = 0; i <= n; ++i) {
+			if (off[i] < obase) return fail(ctx, VO_ERR_ARG, "offsets must be non-decreasing");
+			rel[i] = off[i] - obase;
+		}
+		o = rel.data();
+	}
+	vo_dvol *in = nullptr, *res = nullptr, *rows = nullptr;
+	VO_TRY(upload(ctx, nx, ny, o, spans ? spans + 2 * (size_t)obase : nullptr, &in));
+	int rc = morph3d_dev(ctx, op, method, in, zmin, zmax, radius, &res, &pt);
+	free_dvol(ctx, in);
+	VO_TRY(rc);
+	rc = vo_dvol_rows(ctx, res, row0, row1, &rows);
+	free_dvol(ctx, res);
+	VO_TRY(rc);
+	rc = download_new(ctx, rows, out_off, out_spans, out_nspans);
+	free_dvol(ctx, rows);
 	VO_TRY(rc);
 	if (ms_pass1) *ms_pass1 = pt.ms1;
 	if (ms_pass2) *ms_pass2 = pt.ms2;

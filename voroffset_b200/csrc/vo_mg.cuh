@@ -41,6 +41,7 @@ struct NcclApi {
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
 	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
 	ncclResult_t (*GroupEnd)() = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -67,6 +68,7 @@ NcclApi *nccl_api()
 		api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
 		api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
 		api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+		api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
 		api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
 		api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
 		api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
@@ -103,7 +105,8 @@ struct MgRank {
 	ncclComm_t comm = nullptr;
 	cudaStream_t cs = nullptr;                              // communication stream
 	cudaEvent_t ev_pack = nullptr, ev_c0 = nullptr, ev_c1 = nullptr;
-	uint32_t *h_hdr = nullptr;                              // pinned: [link][in count, in flag, out count, out flag]
+	uint32_t *h_hdr = nullptr;                              // pinned: [link][in count, in flag, out count, out flag], [8] the agreement word
+	unsigned int *d_agree = nullptr;                        // device word of mg_all_agree
 	int rank = 0, world = 1;
 	MgLink prev, next;
 	MgStats stats;
@@ -147,14 +150,22 @@ void mg_free_link(MgLink &l)
 
 // One dilation of this rank's slab. world_act: ranks [0, world_act) take part (a grid with fewer rows than ranks x halo
 // leaves the last ranks idle). clip_lo / clip_hi / unpruned: see erode_with.
+// dual (mg_erode_dual): not a dilation but the erosion of `own` in dual form (vo_lib.cu: erode_dual) - the same halo of
+// input rows, the mirrored intervals through pass 1, k_pass2_rows_dual on the rows this rank owns.
+struct MgDual { double zmin, zmax; };
+
 int mg_dilate(MgRank &r, int world_act, int method, const vo_dvol *own, double R, double clip_lo, double clip_hi, bool unpruned,
-              vo_dvol **out, PassTimes *pt)
+              vo_dvol **out, PassTimes *pt, const MgDual *dual = nullptr)
 {
 	vo_ctx *ctx = r.ctx;
 	VO_TRY(check_radius(ctx, R));
 	const int J = (int)std::floor(R), nx = own->nx, ny = own->ny;
 	const bool has_prev = r.rank > 0, has_next = r.rank + 1 < world_act;
 	auto local = [&](const vo_dvol *v, vo_dvol **o) {
+		if (dual) {                                         // (the group has agreed that every slab qualifies)
+			const int rc = erode_dual(ctx, v, dual->zmin, dual->zmax, R, o, pt);
+			return rc == DUAL_NA ? fail(ctx, VO_ERR_OVERFLOW, "dual erosion: a slab did not qualify after all") : rc;
+		}
 		const bool saved = ctx->force_simple_pass1;
 		if (unpruned) ctx->force_simple_pass1 = true;
 		const int rc = dilate(ctx, method, v, R, o, pt, clip_lo, clip_hi);
@@ -200,7 +211,8 @@ int mg_dilate(MgRank &r, int world_act, int method, const vo_dvol *own, double R
 	vo_slab *S = nullptr;
 	if (all_fast && method == VO_METHOD_OURS && !unpruned && !ctx->force_simple_pass1) {
 		const int rc = slab_begin(ctx, own, R, has_prev, has_next, has_prev ? caps[0].in : 0, has_next ? caps[1].in : 0,
-		                          HaloOut{nullptr, nullptr, 0}, HaloOut{nullptr, nullptr, 0}, nullptr, &S, clip_lo, clip_hi);
+		                          HaloOut{nullptr, nullptr, 0}, HaloOut{nullptr, nullptr, 0}, nullptr, &S, clip_lo, clip_hi,
+		                          dual != nullptr, dual ? dual->zmin : 0.0, dual ? dual->zmax : 0.0);
 		if (rc != VO_OK && rc != VO_ERR_ARG) return rc;     // (VO_ERR_ARG: not a case for the overlapped path)
 		if (rc != VO_OK) { S = nullptr; ctx->err.clear(); }
 	}
@@ -301,7 +313,10 @@ int mg_dilate(MgRank &r, int world_act, int method, const vo_dvol *own, double R
 	VO_TRY(concat_rows(ctx, has_prev ? &hp : nullptr, own, has_next ? &hn : nullptr, &ext));
 	const int y0 = has_prev ? J : 0;
 	int rc;
-	if (method == VO_METHOD_OURS) {
+	if (dual) {
+		rc = erode_dual(ctx, ext, dual->zmin, dual->zmax, R, out, pt, y0, y0 + ny);
+		if (rc == DUAL_NA) rc = fail(ctx, VO_ERR_OVERFLOW, "dual erosion: a slab did not qualify after all");
+	} else if (method == VO_METHOD_OURS) {
 		float t1 = 0, t2 = 0;
 		cudaEventRecord(ctx->ev[0], sm);
 		vo_dmid *mid = nullptr;
@@ -333,6 +348,44 @@ int mg_dilate(MgRank &r, int world_act, int method, const vo_dvol *own, double R
 	return rc;
 }
 
+// Does every slab of the group qualify for the dual form of the erosion? Host-side conditions (the tile kernel must be
+// the one that runs) and the data (k_dual_check) go into one device word, the group takes the maximum.
+int mg_dual_agree(MgRank &r, int world_act, const vo_dvol *own, double zmin, double zmax, double R, bool *all)
+{
+	vo_ctx *ctx = r.ctx;
+	*all = false;
+	const int J = (int)std::floor(R);
+	const unsigned long long ncols = (unsigned long long)own->nx * own->ny;
+	const double k_in = ncols ? (double)own->nspans / (double)ncols : 0.0;
+	bool cand = check_radius(ctx, R) == VO_OK && ncols > 0 && own->nspans <= ncols && own->max_cnt <= 1 && own->dual_state != 2 &&
+	            !ctx->force_simple_pass1 && TilePlan::fits(J, k_in) &&
+	            ((double)ncols * (J + 1) * std::max(1.0, k_in) >= (double)(2ull << 20) || ctx->force_tile_pass1);
+	ctx->err.clear();
+	if (world_act <= 1 || J == 0) {                         // no neighbour to agree with: erode_dual finds out by itself
+		*all = cand;
+		return VO_OK;
+	}
+	if (world_act != r.world) return VO_OK;                 // (idle ranks do not take part in a collective: the general path)
+	NcclApi *nc = nccl_api();
+	if (!nc) return mg_fail(r, VO_ERR_CUDA, "NCCL is not available");
+	if (!r.d_agree) VO_CUDA(cudaMalloc((void **)&r.d_agree, sizeof(unsigned int)));
+	cudaStream_t sm = ctx->stream;
+	VO_CUDA(cudaMemsetAsync(r.d_agree, 0, sizeof(unsigned int), sm));
+	k_dual_check<<<blocks_for(std::max<unsigned long long>(ncols, 1), 256), 256, 0, sm>>>(own->off, own->spans, cand ? ncols : 0ull, zmin - 1, zmax + 1,
+	                                                                                   cand ? 0u : 1u, r.d_agree);
+	ctx->launches++;
+	VO_CUDA(cudaEventRecord(r.ev_pack, sm));
+	VO_CUDA(cudaStreamWaitEvent(r.cs, r.ev_pack, 0));
+	VO_NCCL(r, nc->AllReduce(r.d_agree, r.d_agree, 1, ncclUint32, ncclMax, r.comm, r.cs));
+	VO_CUDA(cudaMemcpyAsync(r.h_hdr + 8, r.d_agree, sizeof(unsigned int), cudaMemcpyDeviceToHost, r.cs));
+	const auto t0 = std::chrono::steady_clock::now();
+	VO_CUDA(cudaStreamSynchronize(r.cs));
+	r.stats.halo_wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	r.stats.messages++;
+	*all = r.h_hdr[8] == 0;
+	return VO_OK;
+}
+
 // One operator on this rank's slab (the -x switch of offset3d.cpp:116-136 per slab).
 int mg_morph(MgRank &r, int world_act, int op, int method, const vo_dvol *own, double zmin, double zmax, double R, vo_dvol **out, PassTimes *pt)
 {
@@ -340,6 +393,19 @@ int mg_morph(MgRank &r, int world_act, int op, int method, const vo_dvol *own, d
 	const double ninf = -std::numeric_limits<double>::infinity(), pinf = std::numeric_limits<double>::infinity();
 	auto dil = [&](const vo_dvol *v, vo_dvol **o) { return mg_dilate(r, world_act, method, v, R, ninf, pinf, false, o, pt); };
 	auto ero = [&](const vo_dvol *v, vo_dvol **o) {
+		// Dual form (vo_lib.cu: erode_dual) when EVERY slab qualifies: the ranks exchange input rows instead of
+		// complement rows then, so they have to agree before anything travels - one word, all-reduced.
+		if (method == VO_METHOD_OURS && ctx->erosion_mode != 2) {
+			bool all = false;
+			VO_TRY(mg_dual_agree(r, world_act, v, zmin, zmax, R, &all));
+			if (all) {
+				const MgDual md{zmin, zmax};
+				const int rc = mg_dilate(r, world_act, method, v, R, ninf, pinf, false, o, pt, &md);
+				if (rc == VO_OK) ctx->dual_erosions++;
+				return rc;
+			}
+			if (ctx->erosion_mode == 1) return fail(ctx, VO_ERR_ARG, "erosion = dual: the input does not qualify for the dual form");
+		}
 		// Voronoi.cpp:18-55: one line of solid border around the GLOBAL grid - the first and the last slab own its rows
 		return erode_with(ctx, v, zmin, zmax, r.rank == 0 ? 1 : 0, r.rank == world_act - 1 ? 1 : 0,
 			[&](const vo_dvol *neg, double clo, double chi, bool unpruned, vo_dvol **d) { return mg_dilate(r, world_act, method, neg, R, clo, chi, unpruned, d, pt); }, o);
@@ -376,7 +442,7 @@ int mg_init_rank(MgRank &r, int device, int rank, int world)
 	bool ok = cudaStreamCreateWithFlags(&r.cs, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&r.ev_pack, cudaEventDisableTiming) == cudaSuccess;
 	ok = ok && cudaEventCreate(&r.ev_c0) == cudaSuccess && cudaEventCreate(&r.ev_c1) == cudaSuccess;
-	ok = ok && cudaMallocHost((void **)&r.h_hdr, 8 * sizeof(uint32_t)) == cudaSuccess;
+	ok = ok && cudaMallocHost((void **)&r.h_hdr, 16 * sizeof(uint32_t)) == cudaSuccess;
 	if (!ok) { cudaGetLastError(); return VO_ERR_CUDA; }
 	return VO_OK;
 }
@@ -390,6 +456,7 @@ void mg_destroy_rank(MgRank &r)
 	if (r.comm && nccl_api()) nccl_api()->CommDestroy(r.comm);
 	mg_free_link(r.prev); mg_free_link(r.next);
 	if (r.h_hdr) cudaFreeHost(r.h_hdr);
+	if (r.d_agree) cudaFree(r.d_agree);
 	for (cudaEvent_t e : {r.ev_pack, r.ev_c0, r.ev_c1}) if (e) cudaEventDestroy(e);
 	if (r.cs) cudaStreamDestroy(r.cs);
 	vo_destroy(r.ctx);

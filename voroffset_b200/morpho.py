@@ -94,6 +94,21 @@ class VoronoiMorpho:
         off, sp = ctx.take_host(poff, pspans, input.nx * input.ny, int(n.value))
         return input.like(input.nx, input.ny, off, sp), t1.value, t2.value
 
+    def morph_rows(self, op: str, input: CompressedVolume, radius: float, y0: int, y1: int, row0: int, row1: int):
+        """vo_morph3d_rows on the rows [y0, y1) of `input` (a y-slab with its ghost rows, cut from the host CSR without
+        copying): the operator on those rows, rows [row0, row1) of that window returned. -> (result, time_1, time_2)"""
+        ctx = self.ctx
+        poff, pspans = _lib._u32p(), _lib._f64p()
+        n = C.c_uint64()
+        t1, t2 = C.c_double(0), C.c_double(0)
+        spans = input.spans if input.spans.size else np.zeros((1, 2))
+        off = input.off[y0 * input.nx:y1 * input.nx + 1]
+        ctx.check(ctx.lib.vo_morph3d_rows(ctx.handle, _lib.OPS3D[op], _lib.METHODS[self.method], input.nx, y1 - y0,
+                                          input.zmin, input.zmax, _lib.ptr(off), _lib.ptr(spans), float(radius), row0, row1,
+                                          C.byref(poff), C.byref(pspans), C.byref(n), C.byref(t1), C.byref(t2)))
+        o, sp = ctx.take_host(poff, pspans, input.nx * (row1 - row0), int(n.value))
+        return input.like(input.nx, row1 - row0, o, sp), t1.value, t2.value
+
     def dilation(self, input: CompressedVolume, radius: float):
         """Voronoi.h:18. Returns (result, time_1, time_2) with the times in ms."""
         return self._morph("dilation", input, radius)
