@@ -295,13 +295,12 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 constexpr int P2_TX = 128;
 
 // WIDE = false: floor(R) <= 32, the class masks are 32-bit words.
-template <int CAP, bool WIDE = true>
-__global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
+// The union of output column (tile * P2_TX + threadIdx.x, y) into `u`; every thread of the CTA calls it (warp ballots),
+// false = no such column (beyond the end of the row).
+template <int CAP, bool WIDE>
+__device__ __forceinline__ bool pass2_rows_union(const Pass2Args &a, int tiles_x, int tile, int y, RunUnion<CAP> &u)
 {
 	typedef typename std::conditional<WIDE, unsigned long long, unsigned int>::type M;
-	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
-	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);
-	const int y = a.y0 + (int)(blockIdx.x / (unsigned)tiles_x);
 	const int x = tile * P2_TX + (int)threadIdx.x;
 	const int lane = threadIdx.x & 31;
 	const size_t nx = (size_t)a.nx;
@@ -319,7 +318,7 @@ __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 		c_up |= (M)__ballot_sync(0xffffffffu, pu) << (32 * h);
 		c_dn |= (M)__ballot_sync(0xffffffffu, pd) << (32 * h);
 	}
-	if (x >= a.nx) return;
+	if (x >= a.nx) return false;
 	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
 	const size_t cc = (size_t)y * nx + x;
 	// windows of the candidate rows, four independent loads at a time (the masks are warp-uniform)
@@ -343,13 +342,28 @@ __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 			else if (jj[i] > 0) m_dn |= (M)flag_has(w[i], jj[i]) << (jj[i] - 1);
 		}
 	}
+	pass2_gather<CAP, M>(a, u, x, y, m_up, m_dn, flag_has(w_up, 0) || flag_has(w_dn, 0));
+	return true;
+}
+
+template <int CAP, bool WIDE = true>
+__global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
+{
+	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
+	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);
+	const int y = a.y0 + (int)(blockIdx.x / (unsigned)tiles_x);
 	double2 ulist[CAP];
 	RunUnion<CAP> u(ulist);
-	pass2_gather<CAP, M>(a, u, x, y, m_up, m_dn, flag_has(w_up, 0) || flag_has(w_dn, 0));
-	const unsigned long long c = (unsigned long long)(y - a.y0) * nx + x;
+	if (!pass2_rows_union<CAP, WIDE>(a, tiles_x, tile, y, u)) return;
+	const unsigned long long c = (unsigned long long)(y - a.y0) * a.nx + tile * P2_TX + threadIdx.x;
 	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
 	stage_emit(a.st, (size_t)c, u);
 }
+
+// (Tried in round 2 and dropped: the same pass writing canonical CSR itself - CTAs taking tickets in list order and the
+// prefix sum of their interval counts running across them as a decoupled look-back while the unions are still in
+// registers. Bit-identical, but 32768 small tiles of very unequal cost wait for each other in ticket order: 0.575 ms
+// against 0.199 + 0.040 ms for this kernel plus k_scan_compact at C5.)
 
 // ---------------------------------------------------------------------------------------------------
 // Erosion in DUAL form, for volumes with at most one interval [a, b] per column strictly inside the bounds
