@@ -587,6 +587,10 @@ def main():
                                        "column of the REFERENCE's mid volume; our kernel never materialises those pieces "
                                        "(`traffic` = what it really moves, from ncu), so this fraction measures speed against the "
                                        "reference's data flow, not DRAM utilisation",
+                         "dram": (None if not ncu_traffic(a.n, R) or k1 <= 0 else
+                                  {"gbs": ncu_traffic(a.n, R) / (k1 * 1e-3) / 1e9, "frac": ncu_traffic(a.n, R) / (k1 * 1e-3) / 1e9 / peak,
+                                   "note": "what the kernel physically moves (ncu dram bytes of the committed capture / its live duration): "
+                                           "it is bound by instruction issue, not by HBM"}),
                          "whole_dilation": {"bytes_per_column": b1 + b2,
                                             "achieved": (b1 + b2) * ncols / ((total_ms / a.steps) * 1e-3) / 1e9,
                                             "frac": (b1 + b2) * ncols / ((total_ms / a.steps) * 1e-3) / 1e9 / peak}},

@@ -62,6 +62,8 @@ struct vo_ctx {
 	std::vector<int> pipe_wts;        // vo_set_option("band_weights", "1,2,3,4,..."): relative heights of the bands (empty: equal bands)
 	bool pipe_first_full = true;      // vo_set_option("pipe_first_full", "on"): the first band's tile launches take every SM
 	bool pipe_interleave = false;     // vo_set_option("pipe_interleave", "on"): enqueue order pass 1 (b + 1), second half (b), ...
+	int pipe_warps0 = 0;              // vo_set_option("pipe_warps0", "N"): warps per tile-kernel CTA for the FIRST band only (0: as the others) - few
+	                                  // warps per SM run their tiles faster, which is what the time to the first result needs
 	int pipe_quota = 0;               // vo_set_option("pipe_quota", "N"): tiles per warp of the pipeline's first tile launch (0: persistent CTAs)
 	int pipe_ctas = 0;                // vo_set_option("pipe_ctas", "N"): CTAs per SM of the pipeline's tile launches (0: as tile_ctas)
 	bool pipe_mid = false;            // vo_set_option("pipe_mid", "on"): thresholds and tile order of every band on a stream of their own, one
@@ -1659,9 +1661,12 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	VO_TRY(dalloc(ctx, &thr.p, nspans));
 	double2 *const d_sp = in->spans - obase;                // indexed by the host's offsets as they are
 	uint4 *const d_thr = thr.p - obase;
-	TilePlan plan;
+	TilePlan plan, plan0;
+	// (the first band's plan first: init() leaves the kernels' shared-memory limit at what the LAST call asked for, the larger one)
+	if (ctx->pipe_warps0 > 0) VO_TRY(plan0.init(ctx, nx, J, k_in, ctx->pipe_warps0, ctx->pipe_ctas, 0, 0));
 	VO_TRY(plan.init(ctx, nx, J, k_in, ctx->pipe_warps, ctx->pipe_ctas, ctx->pipe_quota,
 	                 (unsigned int)(((nx + P1_W - 1) / P1_W) * (unsigned int)BH)));
+	if (ctx->pipe_warps0 <= 0) plan0 = plan;
 	const int tiles_x = plan.tiles_x;
 	VO_TRY(dalloc(ctx, &m->tilemask, 2ull * ny * tiles_x));
 	const unsigned long long ntiles = (unsigned long long)plan.tiles_xw * ny;
@@ -1823,7 +1828,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		// second waiting for CTAs of the first to retire)
 		const int usable = std::max(ctx->band_split, plan.sms - std::max(0, ctx->band_free));
 		const int reserve = (b == 0 && ctx->pipe_first_full) ? 0 : plan.sms - usable / std::max(1, ctx->band_split);
-		plan.launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, reserve, bank, ord, false, w);
+		(b == 0 ? plan0 : plan).launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, reserve, bank, ord, false, w);
 		ev_p1[b] = pr.event();
 		cudaEventRecord(ev_p1[b], sp);
 		mark("pass1 end", b, sp);
@@ -2529,6 +2534,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "pipe_mid") == 0) {
 		if (std::strcmp(value, "on") == 0) { ctx->pipe_mid = true; return VO_OK; }
 		if (std::strcmp(value, "off") == 0) { ctx->pipe_mid = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "pipe_warps0") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 0 && n <= 64) { ctx->pipe_warps0 = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "pipe_warps") == 0) {
 		const int n = std::atoi(value);
