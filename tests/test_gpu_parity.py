@@ -663,3 +663,43 @@ def test_pipelined_host_path_edge_cases(ctx):
             piped, _, _ = op.dilation(vol, R)
             assert piped.bit_equal(plain), f"{name}, call {attempt}"
     assert plain.numSegments() > 0
+
+
+def _with_extra_intervals(vol, rows, cols, extra, gap):
+    """`vol` (at most one interval per column) with `extra` further intervals stacked above the first one, `gap` apart,
+    in the columns of the given row / column ranges that hold one."""
+    nx, ny = vol.nx, vol.ny
+    cnt = np.diff(vol.off.astype(np.int64))
+    assert cnt.max() <= 1
+    region = np.zeros((ny, nx), dtype=bool)
+    region[rows[0]:rows[1], cols[0]:cols[1]] = True
+    sel = (cnt == 1) & region.reshape(-1)
+    new_cnt = cnt + extra * sel
+    off = np.concatenate(([0], np.cumsum(new_cnt))).astype(np.uint32)
+    spans = np.empty((int(off[-1]), 2))
+    has = cnt >= 1
+    spans[off[:-1][has]] = vol.spans.reshape(-1, 2)[vol.off[:-1][has]]
+    base = vol.spans.reshape(-1, 2)[vol.off[:-1][sel]]
+    for k in range(1, extra + 1):
+        spans[off[:-1][sel] + k] = np.stack((base[:, 1] + k * gap, base[:, 1] + k * gap + 0.4 * gap), axis=1)
+    return CompressedVolume(nx, ny, off, spans), int(sel.sum())
+
+
+def test_pipelined_host_path_with_launches_left_out(ctx):
+    """The bands of the host-buffer call leave out the launches that are idle for height-field-like input (the tile
+    kernel's list launches, the redo launches of both passes; vo_ctx::pipe_lean). Input that needs them - columns with
+    several intervals, a running union beyond the fast capacity - must be noticed, done on the plain path, and the
+    following calls (which make those launches) must give the same bits."""
+    base = synth.torus_z(1536, padding=0)
+    op = morpho.make_operator("ours", ctx)
+    for name, (vol, n) in (("two layers", _with_extra_intervals(base, (500, 620), (0, base.nx), 1, 90.0)),
+                           ("forty layers", _with_extra_intervals(base, (300, 303), (200, 204), 40, 70.0))):
+        assert n > 0, name
+        ctx.set_option("pipe_lean", "on")            # (forgets what an earlier call learnt)
+        ctx.set_option("pipeline", "off")
+        plain, _, _ = op.dilation(vol, 31.5)
+        ctx.set_option("pipeline", "on")
+        for attempt in range(3):
+            piped, _, _ = op.dilation(vol, 31.5)
+            assert piped.bit_equal(plain), f"{name}, call {attempt}"
+    ctx.set_option("pipe_lean", "on")

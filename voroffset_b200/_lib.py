@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libvoroffset_b200.so")
+LIB_PATH = os.environ.get("VO_LIB") or os.path.join(_PKG, "libvoroffset_b200.so")   # (VO_LIB: A/B builds, scripts/ only)
 
 VO_OK = 0
 ERRORS = {1: "VO_ERR_ARG", 2: "VO_ERR_CUDA", 3: "VO_ERR_NOMEM", 4: "VO_ERR_OVERFLOW"}

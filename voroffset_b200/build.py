@@ -47,19 +47,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines=()) -> str:
+    """out / defines: a variant build next to the library (A/B runs of compile-time knobs, scripts/ only)."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + sources()
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + [
+        "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out or LIB] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libvoroffset_b200.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # build.py [--force] [-v] [--out path -DNAME=value ...]
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out,
+                defines=[a[2:] for a in sys.argv if a.startswith("-D")]))

@@ -143,6 +143,7 @@ __device__ __forceinline__ void pass1_item(const Pass1Args &a, unsigned long lon
 template <int CAP>
 __global__ void __launch_bounds__(128) k_pass1(Pass1Args a)
 {
+	KT_SCOPE(KT_PASS1, 0, threadIdx.x == 0);
 	VO_FOR_WORK(CAP, a.wk, slot) pass1_item<CAP>(a, slot);
 }
 
@@ -284,6 +285,7 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 template <int CAP>
 __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 {
+	KT_SCOPE(KT_PASS2, a.y0, threadIdx.x == 0);
 	VO_FOR_WORK(CAP, a.wk, c) pass2_item<CAP>(a, c);
 }
 
@@ -349,6 +351,7 @@ __device__ __forceinline__ bool pass2_rows_union(const Pass2Args &a, int tiles_x
 template <int CAP, bool WIDE = true>
 __global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
 {
+	KT_SCOPE(KT_PASS2_ROWS, a.y0, threadIdx.x == 0);
 	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
 	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);
 	const int y = a.y0 + (int)(blockIdx.x / (unsigned)tiles_x);
@@ -837,6 +840,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_compact(Stage st, unsigne
                                                                const unsigned long long *base_in = nullptr,
                                                                unsigned long long *max_word = nullptr, uint32_t max_tag = 0)
 {
+	KT_SCOPE(KT_SCAN_COMPACT, 0, threadIdx.x == 0);
 	// max_word (optional): receives max_tag << 32 | the largest list length seen (atomicMax: a word left by an earlier
 	// call carries a smaller tag, so nobody has to clear it)
 	// base_in (optional): the offsets start from *base_in instead of 0 (a band of rows of a larger volume: `spans` and
@@ -1188,6 +1192,25 @@ __global__ void __launch_bounds__(256) k_xor(XorArgs a, unsigned long long nlist
 	}
 	if (have && !(cur_e - cur_s < 1e-10)) { if (FILL) dst[w] = make_double2(cur_s, cur_e); len += cur_e - cur_s; ++w; }
 	if (FILL) a.col_len[c] = len; else a.cnt[c] = w;
+}
+
+// Intervals [*begin, min(*end, cap)) of a result volume to the caller's pinned host buffer through the SMs (16-byte
+// stores over PCIe, four in flight per thread): the range is only known on the device, so a copy-engine download
+// would need a host round trip per band of the host-buffer call first (vo_lib.cu: dilate_ours_pipelined).
+constexpr int COPY_OUT_THREADS = 256;
+__global__ void __launch_bounds__(COPY_OUT_THREADS) k_copy_out(const double2 *__restrict__ src, double2 *__restrict__ dst_host,
+                                                               const unsigned long long *begin, const unsigned long long *end,
+                                                               unsigned long long cap)
+{
+	KT_SCOPE(KT_COPY_OUT, 0, threadIdx.x == 0);
+	const unsigned long long i0 = *begin, i1 = min(*end, cap);
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	unsigned long long i = i0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	for (; i + 3 * stride < i1; i += 4 * stride) {
+		const double2 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+		dst_host[i] = a; dst_host[i + stride] = b; dst_host[i + 2 * stride] = c; dst_host[i + 3 * stride] = d;
+	}
+	for (; i < i1; i += stride) dst_host[i] = src[i];
 }
 
 // Rebase a copied slice of offsets so that it starts at zero.

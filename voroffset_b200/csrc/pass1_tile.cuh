@@ -176,6 +176,7 @@ __device__ __forceinline__ void thresh_zero_bank(const ThreshArgs &a)
 
 __global__ void __launch_bounds__(256, 6) k_thresh(ThreshArgs a)
 {
+	KT_SCOPE(KT_THRESH, a.c_begin / (unsigned)a.nx, threadIdx.x == 0);
 	extern __shared__ double s_DE[];
 	double *s_D = s_DE, *s_E = s_DE + a.J + 2;
 	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) { s_D[i] = a.Dmono[i]; s_E[i] = a.Emono[i]; }
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(256, 6) k_thresh(ThreshArgs a)
 constexpr int TH_Q = 4;
 __global__ void __launch_bounds__(256) k_thresh_quad(ThreshArgs a)
 {
+	KT_SCOPE(KT_THRESH, a.c_begin / (unsigned)a.nx, threadIdx.x == 0);
 	extern __shared__ double s_DE[];
 	double *s_D = s_DE, *s_E = s_DE + a.J + 2;
 	for (int i = threadIdx.x; i < a.J + 2; i += blockDim.x) { s_D[i] = a.Dmono[i]; s_E[i] = a.Emono[i]; }
@@ -370,6 +372,7 @@ __device__ __forceinline__ int order_bucket(unsigned int est) { return P1_NBUCKE
 
 __global__ void __launch_bounds__(256) k_order_count(OrderArgs a)
 {
+	KT_SCOPE(KT_ORDER_COUNT, a.tile0, threadIdx.x == 0);
 	__shared__ unsigned int h[P1_NBUCKET];
 	if (threadIdx.x < P1_NBUCKET) h[threadIdx.x] = 0;
 	__syncthreads();
@@ -384,6 +387,7 @@ __global__ void __launch_bounds__(256) k_order_count(OrderArgs a)
 
 __global__ void __launch_bounds__(256) k_order_place(OrderArgs a)
 {
+	KT_SCOPE(KT_ORDER_PLACE, a.tile0, threadIdx.x == 0);
 	__shared__ unsigned int base[P1_NBUCKET], h[P1_NBUCKET], start[P1_NBUCKET];
 	if (threadIdx.x < P1_NBUCKET) h[threadIdx.x] = 0;
 	if (threadIdx.x == 0) {
@@ -403,6 +407,31 @@ __global__ void __launch_bounds__(256) k_order_place(OrderArgs a)
 	if (threadIdx.x < P1_NBUCKET && h[threadIdx.x]) start[threadIdx.x] = atomicAdd(a.hist + P1_NBUCKET + threadIdx.x, h[threadIdx.x]);
 	__syncthreads();
 	if (b >= 0) a.order[base[b] + start[b] + rank] = tile;
+}
+
+// The same permutation by ONE CTA (count, bucket starts and placement between CTA barriers): for the launch sets of a
+// band of the host-buffer call, where two dependent launches cost more than the few microseconds this takes.
+constexpr unsigned int P1_ORDER_ONE_MAX = 1u << 15;
+__global__ void __launch_bounds__(1024) k_order_one(OrderArgs a)
+{
+	KT_SCOPE(KT_ORDER_COUNT, a.tile0, threadIdx.x == 0);
+	__shared__ unsigned int h[P1_NBUCKET], base[P1_NBUCKET];
+	if (threadIdx.x < P1_NBUCKET) h[threadIdx.x] = 0;
+	__syncthreads();
+	for (unsigned int pos = threadIdx.x; pos < a.ntiles; pos += blockDim.x) {
+		const unsigned int tile = pos < a.ntiles0 ? a.tile0 + pos : a.tile0b + (pos - a.ntiles0);
+		atomicAdd(&h[order_bucket(__ldg(a.est + tile))], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned int acc = 0;
+		for (int b = 0; b < P1_NBUCKET; ++b) { base[b] = acc; acc += h[b]; }
+	}
+	__syncthreads();
+	for (unsigned int pos = threadIdx.x; pos < a.ntiles; pos += blockDim.x) {
+		const unsigned int tile = pos < a.ntiles0 ? a.tile0 + pos : a.tile0b + (pos - a.ntiles0);
+		a.order[atomicAdd(&base[order_bucket(__ldg(a.est + tile))], 1u)] = tile;
+	}
 }
 
 // ---- pass 1 ------------------------------------------------------------------------------------------
@@ -429,6 +458,9 @@ struct Pass1TileArgs {
 	uint32_t *ovf;          // [CTAs * warps][P1_OVF][P1_W]: survivor entries beyond the shared-memory lists
 	const unsigned int *bad = nullptr;   // optional: raised by k_thresh when the (untrusted) offsets of the launch set's rows are
 	                                     //   invalid - the launch then does nothing (ThreshArgs::bad)
+	unsigned int *sticky_multi = nullptr, *sticky_big = nullptr;   // optional: count the tiles handed to a list (multi_tiles / big_tiles)
+	                                     //   whose launch the caller has left out (never zeroed by a launch set: the banded host-buffer call
+	                                     //   reads it once at the end and repeats with the list launches when it is not 0)
 	unsigned long long *dbg;   // development aid (NULL normally): per tile {cycles, candidates, survivor entries, cycles of phase 1}
 	Redo redo;              // slot ids to be (re)done by k_pass1: list overflow and oversized tiles
 	// Device-side dispatch (no host round trip between the launches). Every launch is one resident wave of CTAs
@@ -918,9 +950,9 @@ __device__ __forceinline__ void tile_other(const Pass1TileArgs &a, const TileHea
 	if (h.kind == TK_EMPTY) {                               // nothing in reach: no slot of the tile is needed
 		if (lane < h.txe) { a.flags[rowbase + h.x0 + lane] = 0; a.flags[ncols_all + rowbase + h.x0 + lane] = 0; }
 	} else if (h.kind == TK_MULTI) {                        // -> two-hull variant, launch 3
-		if (lane == 0) a.multi_tiles[atomicAdd(a.multi_count, 1u)] = h.tile;
+		if (lane == 0) { a.multi_tiles[atomicAdd(a.multi_count, 1u)] = h.tile; if (a.sticky_multi) atomicAdd(a.sticky_multi, 1u); }
 	} else if (h.kind == TK_BIG) {                          // -> launch 2, larger candidate buffer
-		if (lane == 0) a.big_tiles[atomicAdd(a.big_count, 1u)] = h.tile;
+		if (lane == 0) { a.big_tiles[atomicAdd(a.big_count, 1u)] = h.tile; if (a.sticky_big) atomicAdd(a.sticky_big, 1u); }
 	} else {                                                // TK_REDO: leave every slot of the tile to k_pass1
 		const uint16_t full = (uint16_t)(JP << 8);         // window [0, J+1)
 		if (lane < h.txe) { a.flags[rowbase + h.x0 + lane] = full; a.flags[ncols_all + rowbase + h.x0 + lane] = full; }
@@ -954,6 +986,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 	constexpr int LCAP = (MULTI || LIST) ? P1_LCAP_M : P1_LCAP_S;
 	constexpr int NR = 5;                                   // segment offsets per lane: P1_W + 2 * 63 + 1 <= 32 * NR
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+	KT_SCOPE(LIST ? KT_TILE_LIST : KT_TILE, a.tile0 / (unsigned)a.tiles_xw, (threadIdx.x & 31) == 0);     // (per warp: warps leave on their own)
 	const unsigned int n = LIST ? *a.tiles_count : a.ntiles;
 	if (n == 0) return;
 	if (a.bad) {                                            // invalid input offsets (banded host-buffer call): nothing is safe to read

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ktrace.cuh"
+
 namespace vo {
 
 // Slot encoding shared by the intermediate volume and the staging buffers:

@@ -62,6 +62,14 @@ struct vo_ctx {
 	std::vector<int> pipe_wts;        // vo_set_option("band_weights", "1,2,3,4,..."): relative heights of the bands (empty: equal bands)
 	bool pipe_first_full = true;      // vo_set_option("pipe_first_full", "on"): the first band's tile launches take every SM
 	bool pipe_interleave = false;     // vo_set_option("pipe_interleave", "on"): enqueue order pass 1 (b + 1), second half (b), ...
+	bool pipe_lean = true;            // vo_set_option("pipe_lean", "on"): the bands of the host-buffer call leave out the launches that are normally idle
+	                                  // (the tile kernel's list launches, the redo launches of both passes); a call that did need one is
+	                                  // repeated on the plain path and the context remembers which (pipe_lists, pipe_redo)
+	bool pipe_lists = false, pipe_redo = false;
+	unsigned long long pipe_dry = 0;             // (-DVO_KTRACE builds) vo_set_option("pipe_dry", "<intervals>"): the host-buffer call without its kernels - copies, events
+	                                  // and host round trips only, downloads sized from the previous result: the floor its transfer pattern sets
+	bool pipe_ahead = true;           // vo_set_option("pipe_ahead", "on"): a band's offsets download is enqueued before the host knows the band's total
+	bool pipe_order_one = true;       // vo_set_option("pipe_order_one", "on"): a band's tile order by one CTA in one launch
 	int pipe_warps0 = 0;              // vo_set_option("pipe_warps0", "N"): warps per tile-kernel CTA for the FIRST band only (0: as the others) - few
 	                                  // warps per SM run their tiles faster, which is what the time to the first result needs
 	int pipe_quota = 0;               // vo_set_option("pipe_quota", "N"): tiles per warp of the pipeline's first tile launch (0: persistent CTAs)
@@ -76,6 +84,9 @@ struct vo_ctx {
 	cudaStream_t s_p[2] = {nullptr, nullptr};       // its two pass-1 streams (consecutive bands overlap)
 	cudaStream_t s_hi[3] = {nullptr, nullptr, nullptr};   // its second-half streams (highest priority): two for alternating bands, one for the pass-1 redo launches
 	cudaStream_t s_ctl = nullptr;                   // its control stream (band totals -> host)
+	cudaStream_t s_out2 = nullptr;                  // the stream of its SM-driven span downloads (k_copy_out)
+	int copy_out_ctas = 0;                          // vo_set_option("copy_out", "N"): CTAs of k_copy_out; 0 (default): the spans leave through the copy
+	                                                // engine, which needs a host round trip per band for their size
 	std::vector<cudaEvent_t> pipe_ev;               // its (reused) events
 	// single-pass scan + compaction (k_scan_compact): tile state words, ticket counter (device) and their host mirrors
 	unsigned long long *scan_state = nullptr;   // [scan_cap] state words, then the ticket counter
@@ -808,8 +819,9 @@ struct TilePlan {
 	void launch(vo_ctx *ctx, Pass1TileArgs g, unsigned int tile0, unsigned int ntiles0, unsigned int *big_tiles, unsigned int *multi_tiles,
 	            cudaStream_t s, unsigned int tile0b = 0, unsigned int ntilesb = 0, int reserve_sms = 0,
 	            unsigned long long *bank = nullptr, const unsigned int *order = nullptr, bool dual = false, int ovf_bank = -1,
-	            bool single = false) const
+	            bool single = false, unsigned int *sticky = nullptr) const
 	{
+		// sticky: with `single`, counts the tiles that would have needed a launch that is not made (the caller repeats with them)
 		// single: every column is KNOWN to hold at most one interval (vo_dvol::max_cnt) - no tile can be a multi-interval
 		// one, and none can hold more candidates than its segment has columns: the list launches that could only find
 		// empty lists are not made
@@ -831,11 +843,14 @@ struct TilePlan {
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 10);
 		g.big_tiles = cmax_small < cmax_big ? big_tiles : nullptr;
 		g.quota = quota;
+		const bool launch2 = cmax_small < cmax_big && !(single && cmax_small >= P1_W + 2 * J);
+		g.sticky_multi = single ? sticky : nullptr; g.sticky_big = (single && !launch2) ? sticky : nullptr;
 		if (dual) k_pass1_tile<CAP_FAST, false, false, true><<<grid_small(ntiles, sms), 32 * nw_small, smem_small, s>>>(g);
 		else k_pass1_tile<CAP_FAST, false, false><<<grid_small(ntiles, sms), 32 * nw_small, smem_small, s>>>(g);
 		g.quota = 0;
 		ctx->launches++;
-		if (cmax_small < cmax_big && !(single && cmax_small >= P1_W + 2 * J)) {    // launch 2: the single-interval tiles that need the large buffer
+		g.sticky_multi = g.sticky_big = nullptr;
+		if (launch2) {                  // launch 2: the single-interval tiles that need the large buffer
 			g.cmax = cmax_big; g.dbuf = db_big; g.lean = lean_big; g.tiles = big_tiles; g.tiles_count = big_count; g.big_tiles = nullptr;
 			g.tiles_next = reinterpret_cast<unsigned int *>(bank + 6);
 			if (dual) k_pass1_tile<CAP_FAST, false, true, true><<<grid(nw_big), 32 * nw_big, smem_big, s>>>(g);
@@ -864,12 +879,17 @@ struct TilePlan {
 	// Expensive tiles first: `est` (k_thresh, per tile) -> `order`, a permutation of the positions of the same two
 	// ranges launch() takes; scratch = [2 * P1_NBUCKET] zeroed counters.
 	static void order_tiles(vo_ctx *ctx, const unsigned int *est, unsigned int *scratch, unsigned int *order, unsigned int tile0,
-	                        unsigned int ntiles0, unsigned int tile0b, unsigned int ntilesb, cudaStream_t s)
+	                        unsigned int ntiles0, unsigned int tile0b, unsigned int ntilesb, cudaStream_t s, bool one_cta = false)
 	{
 		OrderArgs oa;
 		oa.est = est; oa.tile0 = tile0; oa.ntiles0 = ntiles0; oa.tile0b = tile0b; oa.ntiles = ntiles0 + ntilesb;
 		oa.hist = scratch; oa.order = order;
 		if (!oa.ntiles) return;
+		if (one_cta && oa.ntiles <= P1_ORDER_ONE_MAX) {
+			k_order_one<<<1, 1024, 0, s>>>(oa);
+			ctx->launches++;
+			return;
+		}
 		k_order_count<<<blocks_for(oa.ntiles, 256), 256, 0, s>>>(oa);
 		k_order_place<<<blocks_for(oa.ntiles, 256), 256, 0, s>>>(oa);
 		ctx->launches += 2;
@@ -1722,6 +1742,15 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	struct OutGuard { vo_ctx *c; vo_dvol *p; ~OutGuard() { free_dvol(c, p); } } out_guard{ctx, dout};
 	VO_TRY(dalloc(ctx, &dout->spans, dcap));
 	if (!ctx->s_ctl && cudaStreamCreateWithFlags(&ctx->s_ctl, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
+	if (!ctx->s_out2) {
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		if (cudaStreamCreateWithPriority(&ctx->s_out2, cudaStreamNonBlocking, greatest) != cudaSuccess) { cudaGetLastError(); return PIPE_NA; }
+	}
+	// Downloads: the offsets of a band have a size the host knows (copy engine, enqueued up front behind the band's
+	// event); the spans do not - the SMs copy them (k_copy_out reads the range on the device), or the host waits for
+	// every band's total and enqueues a copy of that size (copy_out = 0; a round trip per band, ~0.2 ms per call)
+	const bool sm_out = ctx->copy_out_ctas > 0;
 
 	// result buffers (pinned): offsets are exact, the span buffer is sized from the last result
 	const unsigned long long ckeep0 = (unsigned long long)keep0 * nx, nkeep = (unsigned long long)(keep1 - keep0) * nx;
@@ -1747,6 +1776,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		ev_in[b] = pr.event();
 		ev_done[b] = pr.event();
 		cudaEventRecord(ev_in[b], pr.s_in);
+		KT_MARK_STREAM(1000 + b, pr.s_in);
 	}
 	if (cudaGetLastError() != cudaSuccess) { drop_host(); return PIPE_NA; }
 	cudaEvent_t ev_up_done = nullptr;
@@ -1802,6 +1832,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	// Pass 1 of band b runs on one of two streams, with that stream's own tile lists and cursors: the launch set of
 	// band b+1 starts while the last heavy tiles of band b are still being worked on (every launch of the tile kernel
 	// ends with such a tail), its CTAs taking over the SMs as those of band b retire.
+	// (normally idle launches left out: see vo_ctx::pipe_lean)
+	const bool no_lists = ctx->pipe_lean && !ctx->pipe_lists, no_redo = ctx->pipe_lean && !ctx->pipe_redo;
 	auto pass1_band = [&](int b) {
 		const int y0 = ys[b], y1 = ys[b + 1], w = b & 1;
 		cudaStream_t sp = ctx->s_p[w];
@@ -1817,10 +1849,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			ta.est = est.p + 2ull * P1_NBUCKET * nb; ta.tiles_xw = plan.tiles_xw;
 			ord = (w ? order1.p : order0.p) + t0;
 		}
+		if (ctx->pipe_dry) { ev_p1[b] = pr.event(); cudaEventRecord(ev_p1[b], sp); return; }
 		launch_thresh(ta, k_in, st);
 		ctx->launches++;
 		mark("  thresh end", b, st);
-		if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p + 2ull * P1_NBUCKET * b, ord, t0, nt, 0u, 0u, st);
+		if (ordered) TilePlan::order_tiles(ctx, ta.est, est.p + 2ull * P1_NBUCKET * b, ord, t0, nt, 0u, 0u, st, ctx->pipe_order_one);
 		mark("  order end", b, st);
 		if (mid) { cudaEvent_t e = pr.event(); cudaEventRecord(e, st); cudaStreamWaitEvent(sp, e, 0); }
 		g.redo = redo_of(b);
@@ -1828,7 +1861,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		// second waiting for CTAs of the first to retire)
 		const int usable = std::max(ctx->band_split, plan.sms - std::max(0, ctx->band_free));
 		const int reserve = (b == 0 && ctx->pipe_first_full) ? 0 : plan.sms - usable / std::max(1, ctx->band_split);
-		(b == 0 ? plan0 : plan).launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, reserve, bank, ord, false, w);
+		(b == 0 ? plan0 : plan).launch(ctx, g, t0, nt, w ? big_tiles1.p : big_tiles.p, w ? multi_tiles1.p : multi_tiles.p, sp, 0u, 0u, reserve, bank, ord, false, w,
+		                               no_lists, reinterpret_cast<unsigned int *>(ctx->d_ctr + 14));
 		ev_p1[b] = pr.event();
 		cudaEventRecord(ev_p1[b], sp);
 		mark("pass1 end", b, sp);
@@ -1841,8 +1875,10 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		if (b > 0) cudaStreamWaitEvent(st, ev_r1[b - 1], 0);
 		a1.redo = redo_of(b);
 		a1.wk = Work{a1.redo.list, 0ull, a1.redo.count, a1.redo.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
-		k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, st>>>(a1);
-		ctx->launches++;
+		if (!no_redo) {
+			k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, st>>>(a1);
+			ctx->launches++;
+		}
 		ev_r1[b] = pr.event();
 		cudaEventRecord(ev_r1[b], st);
 	};
@@ -1854,7 +1890,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	int rc = VO_OK;
 	// declared last, hence destroyed first: on every way out the side streams are drained BEFORE the temporaries above
 	// go back to the pool of the context stream (stream-ordered frees only order against that stream)
-	struct Join { vo_ctx *c; ~Join() { for (auto st : c->s_hi) cudaStreamSynchronize(st); cudaStreamSynchronize(c->s_ctl); for (auto st : c->s_p) cudaStreamSynchronize(st); if (c->s_mid) cudaStreamSynchronize(c->s_mid); } } join{ctx};
+	struct Join { vo_ctx *c; ~Join() { for (auto st : c->s_hi) cudaStreamSynchronize(st); cudaStreamSynchronize(c->s_ctl); for (auto st : c->s_p) cudaStreamSynchronize(st); if (c->s_mid) cudaStreamSynchronize(c->s_mid); if (c->s_out2) cudaStreamSynchronize(c->s_out2); } } join{ctx};
 
 	std::vector<cudaEvent_t> ev_tot(nb);
 	// single-pass scan + compaction per band: tile state reserved up front (no allocation between the launches)
@@ -1902,10 +1938,18 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		a2.nx = nx; a2.ny = ny; a2.J = J; a2.y0 = y0; a2.y1 = y1;
 		a2.mid = m->slots; a2.flags = m->flags; a2.tilemask = m->tilemask; a2.pool = m->pool; a2.pool_cap = m->pool_cap; a2.st = st; a2.redo = rd;
 		a2.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
+		if (ctx->pipe_dry) {
+			cudaEventRecord(ev_done[b], sm);
+			cudaStreamWaitEvent(ctx->s_ctl, ev_done[b], 0);
+			cudaMemcpyAsync(h_tot + b, gb.p + b + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_ctl);
+			ev_tot[b] = pr.event();
+			cudaEventRecord(ev_tot[b], ctx->s_ctl);
+			return;
+		}
 		if (J <= 32) k_pass2_rows<CAP_FAST, false><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		else k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		a2.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
-		k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
+		if (!no_redo) k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
 		if (fused) {
 			// ONE kernel: offsets (from the running total gb[b] of the bands before) and spans of the band; the bands'
 			// kernels follow one another (the running total is a chain anyway, and each takes a few microseconds)
@@ -1927,6 +1971,16 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		}
 		cudaEventRecord(ev_done[b], sm);
 		mark("pass2 end", b, sm);
+		if (sm_out) {
+			cudaStreamWaitEvent(pr.s_out, ev_done[b], 0);
+			cudaMemcpyAsync(ho + (c0 - ckeep0), dout->off + c0, (nlists + (b == last_act ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+			cudaStreamWaitEvent(ctx->s_out2, ev_done[b], 0);
+			mark("download begin", b, ctx->s_out2);
+			k_copy_out<<<ctx->copy_out_ctas, COPY_OUT_THREADS, 0, ctx->s_out2>>>(dout->spans, reinterpret_cast<double2 *>(hs), gb.p + pb + 1, gb.p + b + 1, dcap);
+			ctx->launches++;
+			mark("download end", b, ctx->s_out2);
+			return;
+		}
 		cudaStreamWaitEvent(ctx->s_ctl, ev_done[b], 0);
 		cudaMemcpyAsync(h_tot + b, gb.p + b + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_ctl);
 		ev_tot[b] = pr.event();
@@ -1945,22 +1999,39 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		for (int b = 0; b < nb; ++b) second_half(b);
 	}
 	uint64_t base = 0;          // intervals of the bands downloaded so far
-	for (int b = 0; b < nb && rc == VO_OK; ++b) {
-		if (!act[b]) continue;
+	// The offsets of a band have a size the host knows: their copy is enqueued AHEAD, behind the band's event, and runs
+	// while the host is still waiting for the band's total - the round trip (total -> host -> enqueue) hides behind it.
+	// (Not all of them up front: a stream runs in enqueue order, and the spans of band b must not queue behind the
+	// offsets of the bands after it.)
+	auto offsets_ahead = [&](int b, bool now = false) {
+		if (!ctx->pipe_ahead && !now) return;
+		while (!now && b < nb && !act[b]) ++b;
+		if (b >= nb) return;
 		const int y0 = std::max(ys2[b], keep0), y1 = std::min(ys2[b + 1], keep1);
 		const unsigned long long c0 = (unsigned long long)y0 * nx, nlists = (unsigned long long)nx * (y1 - y0);
+		cudaStreamWaitEvent(pr.s_out, ev_done[b], 0);
+		mark("download begin", b, pr.s_out);
+		KT_MARK_STREAM(2000 + b, pr.s_out);
+		cudaMemcpyAsync(ho + (c0 - ckeep0), dout->off + c0, (nlists + (b == last_act ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+	};
+	const bool host_driven = !(sm_out && !ctx->pipe_dry);
+	if (host_driven) offsets_ahead(0);
+	for (int b = 0; b < nb && rc == VO_OK && host_driven; ++b) {
+		if (!act[b]) continue;
 		if (cudaEventSynchronize(ev_tot[b]) != cudaSuccess) { rc = PIPE_NA; break; }
-		const uint64_t tot = h_tot[b];
+		uint64_t tot = h_tot[b];
+		if (ctx->pipe_dry) tot = (uint64_t)ctx->pipe_dry * (uint64_t)(b + 1) / (uint64_t)nb;
 		if (tot > dcap) {                                   // result buffers too small (first call, or a much larger result): plain path
 			ctx->out_hint = std::max<uint64_t>(ctx->out_hint, 2 * tot);
 			rc = PIPE_NA;
 			break;
 		}
-		mark("download begin", b, pr.s_out);
-		cudaMemcpyAsync(ho + (c0 - ckeep0), dout->off + c0, (nlists + (b == last_act ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+		if (!ctx->pipe_ahead) offsets_ahead(b, true);
 		if (tot > base) cudaMemcpyAsync(hs + 2 * base, dout->spans + base, (tot - base) * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
 		mark("download end", b, pr.s_out);
+		KT_MARK_STREAM(3000 + b, pr.s_out);
 		base = tot;
+		offsets_ahead(b + 1);
 	}
 	{
 		for (auto st : ctx->s_p) { cudaEvent_t e = pr.event(); cudaEventRecord(e, st); cudaStreamWaitEvent(ctx->stream, e, 0); }
@@ -1972,11 +2043,21 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	if (rc == VO_OK && cudaMemcpyAsync(hgb.data(), gb.p, hgb.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = PIPE_NA;
 	if (rc == VO_OK) rc = read_counters(ctx, h);
 	cudaStreamSynchronize(pr.s_out);
+	cudaStreamSynchronize(ctx->s_out2);
 	cudaStreamSynchronize(pr.s_in);
+	if (rc == VO_OK && sm_out && !ctx->pipe_dry) {              // the total the device arrived at (k_copy_out stopped at the buffer's end)
+		base = last_act >= 0 ? hgb[(size_t)last_act + 1] : 0;
+		if (base > dcap) { ctx->out_hint = std::max<uint64_t>(ctx->out_hint, 2 * base); rc = PIPE_NA; }
+	}
 	vo_free(h_tot);
 	if (rc == VO_OK) {
 		bool redo = h[9] != 0 || h[1] > sb.st.pool_cap;         // rare: the plain path regrows / reports
 		for (int b = 0; b < nb; ++b) redo = redo || (unsigned int)hgb[nb + 1 + b] > rcap2 || (unsigned int)hgb[2 * nb + 1 + b] > rcap1;
+		// launches that were left out and turned out to be needed: the plain path does this call, the next ones make them
+		if (no_redo)
+			for (int b = 0; b < nb; ++b)
+				if ((unsigned int)hgb[nb + 1 + b] || (unsigned int)hgb[2 * nb + 1 + b]) { ctx->pipe_redo = true; redo = true; }
+		if (no_lists && h[14]) { ctx->pipe_lists = true; redo = true; }
 		if (redo) rc = PIPE_NA;
 	}
 	if (trace && !marks.empty()) {
@@ -2445,6 +2526,7 @@ void vo_destroy(vo_ctx *ctx)
 	for (auto &st : ctx->s_p) if (st) cudaStreamDestroy(st);
 	for (auto &st : ctx->s_hi) if (st) cudaStreamDestroy(st);
 	if (ctx->s_ctl) cudaStreamDestroy(ctx->s_ctl);
+	if (ctx->s_out2) cudaStreamDestroy(ctx->s_out2);
 	if (ctx->s_mid) cudaStreamDestroy(ctx->s_mid);
 	if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
 	if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
@@ -2535,6 +2617,22 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 		if (std::strcmp(value, "on") == 0) { ctx->pipe_mid = true; return VO_OK; }
 		if (std::strcmp(value, "off") == 0) { ctx->pipe_mid = false; return VO_OK; }
 	}
+	if (std::strcmp(key, "copy_out") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 0 && n <= 1024) { ctx->copy_out_ctas = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "pipe_lean") == 0) {
+		if (std::strcmp(value, "on") == 0) { ctx->pipe_lean = true; ctx->pipe_lists = ctx->pipe_redo = false; return VO_OK; }
+		if (std::strcmp(value, "off") == 0) { ctx->pipe_lean = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "pipe_ahead") == 0) {
+		if (std::strcmp(value, "on") == 0) { ctx->pipe_ahead = true; return VO_OK; }
+		if (std::strcmp(value, "off") == 0) { ctx->pipe_ahead = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "pipe_order_one") == 0) {
+		if (std::strcmp(value, "on") == 0) { ctx->pipe_order_one = true; return VO_OK; }
+		if (std::strcmp(value, "off") == 0) { ctx->pipe_order_one = false; return VO_OK; }
+	}
 	if (std::strcmp(key, "pipe_warps0") == 0) {
 		const int n = std::atoi(value);
 		if (n >= 0 && n <= 64) { ctx->pipe_warps0 = n; return VO_OK; }
@@ -2573,6 +2671,42 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 		if (std::strcmp(value, "off") == 0) { ctx->tile_order = false; return VO_OK; }
 		if (std::strcmp(value, "on") == 0) { ctx->tile_order = true; return VO_OK; }
 	}
+#ifdef VO_KTRACE                                         // development builds only (ktrace.cuh, scripts/ktrace_view.py)
+	if (std::strcmp(key, "pipe_dry") == 0) { ctx->pipe_dry = std::strtoull(value, nullptr, 0); return VO_OK; }
+	if (std::strcmp(key, "ktrace") == 0) {
+		DeviceGuard g(ctx->device);
+		const unsigned int cap = (unsigned int)std::strtoul(value, nullptr, 0);
+		KTraceBuf kb{nullptr, nullptr, cap};
+		if (cap) {
+			VO_CUDA(cudaMalloc(&kb.rec, 32ull * cap));
+			VO_CUDA(cudaMalloc(&kb.count, sizeof(unsigned int)));
+			VO_CUDA(cudaMemset(kb.count, 0, sizeof(unsigned int)));
+		}
+		VO_CUDA(cudaMemcpyToSymbol(c_kt, &kb, sizeof kb));
+		return VO_OK;
+	}
+	if (std::strcmp(key, "ktrace_dump") == 0) {
+		DeviceGuard g(ctx->device);
+		VO_CUDA(cudaDeviceSynchronize());
+		KTraceBuf kb;
+		VO_CUDA(cudaMemcpyFromSymbol(&kb, c_kt, sizeof kb));
+		if (!kb.rec) return fail(ctx, VO_ERR_ARG, "ktrace is off");
+		unsigned int n = 0;
+		VO_CUDA(cudaMemcpy(&n, kb.count, sizeof n, cudaMemcpyDeviceToHost));
+		n = std::min(n, kb.cap);
+		std::vector<unsigned long long> rec(4ull * n);
+		if (n) VO_CUDA(cudaMemcpy(rec.data(), kb.rec, 32ull * n, cudaMemcpyDeviceToHost));
+		VO_CUDA(cudaMemset(kb.count, 0, sizeof(unsigned int)));
+		FILE *f = std::fopen(value, "w");
+		if (!f) return fail(ctx, VO_ERR_ARG, "ktrace_dump: cannot open the file");
+		std::fprintf(f, "id,sm,aux,block,t0,t1\n");
+		for (unsigned int i = 0; i < n; ++i)
+			std::fprintf(f, "%llu,%llu,%llu,%llu,%llu,%llu\n", rec[4ull * i] & 0xffffffffull, rec[4ull * i] >> 32, rec[4ull * i + 1] & 0xffffffffull,
+			             rec[4ull * i + 1] >> 32, rec[4ull * i + 2], rec[4ull * i + 3]);
+		std::fclose(f);
+		return VO_OK;
+	}
+#endif
 #ifdef VO_TILE_DEBUG                                     // development builds only (scripts/tile_costs.py): a raw device pointer
 	if (std::strcmp(key, "tile_debug") == 0) {
 		ctx->dbg_tiles = reinterpret_cast<unsigned long long *>(std::strtoull(value, nullptr, 0));
