@@ -68,6 +68,10 @@ struct vo_ctx {
 	bool pipe_lists = false, pipe_redo = false;
 	unsigned long long pipe_dry = 0;             // (-DVO_KTRACE builds) vo_set_option("pipe_dry", "<intervals>"): the host-buffer call without its kernels - copies, events
 	                                  // and host round trips only, downloads sized from the previous result: the floor its transfer pattern sets
+	int copy_align = 256;             // vo_set_option("copy_align", "N"): the band copies of the host-buffer call start and end on N-byte boundaries
+	                                  // (0: exactly the band's bytes). The copy engines run a copy whose ends are only 16-byte aligned a fifth
+	                                  // slower when both directions are busy (profiles/r2ah_pcie_probe6.txt); the few bytes of the
+	                                  // neighbouring band that travel along are the same bytes, or are overwritten by that band's own copy
 	bool pipe_ahead = true;           // vo_set_option("pipe_ahead", "on"): a band's offsets download is enqueued before the host knows the band's total
 	bool pipe_order_one = true;       // vo_set_option("pipe_order_one", "on"): a band's tile order by one CTA in one launch
 	int pipe_warps0 = 0;              // vo_set_option("pipe_warps0", "N"): warps per tile-kernel CTA for the FIRST band only (0: as the others) - few
@@ -1760,6 +1764,19 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	auto drop_host = [&]() { vo_free(ho); vo_free(hs); };
 	if (!ho || !hs || !h_tot) { drop_host(); vo_free(h_tot); return fail(ctx, VO_ERR_NOMEM, "pinned host allocation failed"); }
 
+	// copy boundaries in elements (vo_ctx::copy_align): only where source and destination are aligned alike
+	const unsigned long long al_bytes = ctx->copy_align >= 16 && (ctx->copy_align & (ctx->copy_align - 1)) == 0 ? (unsigned long long)ctx->copy_align : 0ull;
+	auto aligned_ptr = [&](const void *p) { return al_bytes && (reinterpret_cast<uintptr_t>(p) & (al_bytes - 1)) == 0; };
+	const unsigned long long al_off = aligned_ptr(off) && aligned_ptr(in->off) ? al_bytes / sizeof(uint32_t) : 0ull;
+	const unsigned long long al_sp = aligned_ptr(spans) && aligned_ptr(in->spans) && obase % (al_bytes ? al_bytes / sizeof(double2) : 1) == 0 ? al_bytes / sizeof(double2) : 0ull;
+	const unsigned long long al_off_out = aligned_ptr(ho) && aligned_ptr(dout->off) && ckeep0 % (al_bytes ? al_bytes / sizeof(uint32_t) : 1) == 0 ? al_bytes / sizeof(uint32_t) : 0ull;
+	const unsigned long long al_sp_out = aligned_ptr(hs) && aligned_ptr(dout->spans) ? al_bytes / sizeof(double2) : 0ull;
+	// offsets of the lists [c0, c0 + n) of the result (+ the closing one for the last band) to the host
+	auto download_offsets = [&](unsigned long long c0, unsigned long long n, bool last) {
+		unsigned long long a0 = c0, a1 = c0 + n + (last ? 1 : 0);
+		if (al_off_out) { a0 &= ~(al_off_out - 1); if (!last) a1 = (a1 + al_off_out - 1) & ~(al_off_out - 1); }
+		cudaMemcpyAsync(ho + (a0 - ckeep0), dout->off + a0, (a1 - a0) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+	};
 	// stage 0: all uploads are enqueued up front, one event per band
 	const auto host_t0 = std::chrono::steady_clock::now();
 	cudaEvent_t ev_t0 = nullptr;
@@ -1770,9 +1787,16 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		// row below) can start as soon as ITS upload is done instead of waiting for the next one
 		const int y0 = b == 0 ? 0 : ys[b] + 1, y1 = std::min(ny, ys[b + 1] + 1);
 		const unsigned long long c0 = (unsigned long long)y0 * nx, c1 = (unsigned long long)y1 * nx;
-		cudaMemcpyAsync(in->off + c0, off + c0, (c1 - c0 + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, pr.s_in);
-		if (off[c1] > off[c0])
-			cudaMemcpyAsync(d_sp + off[c0], spans + 2 * (size_t)off[c0], (size_t)(off[c1] - off[c0]) * sizeof(double2), cudaMemcpyHostToDevice, pr.s_in);
+		{
+			unsigned long long a0 = c0, a1 = c1 + 1;            // offsets [a0, a1)
+			if (al_off) { a0 = c0 & ~(al_off - 1); a1 = std::min<unsigned long long>(ncols + 1, (c1 + 1 + al_off - 1) & ~(al_off - 1)); }
+			cudaMemcpyAsync(in->off + a0, off + a0, (a1 - a0) * sizeof(uint32_t), cudaMemcpyHostToDevice, pr.s_in);
+		}
+		if (off[c1] > off[c0]) {
+			unsigned long long i0 = off[c0], i1 = off[c1];
+			if (al_sp) { i0 &= ~(al_sp - 1); i1 = std::min<unsigned long long>((unsigned long long)obase + nspans, (i1 + al_sp - 1) & ~(al_sp - 1)); }
+			cudaMemcpyAsync(d_sp + i0, spans + 2 * (size_t)i0, (size_t)(i1 - i0) * sizeof(double2), cudaMemcpyHostToDevice, pr.s_in);
+		}
 		ev_in[b] = pr.event();
 		ev_done[b] = pr.event();
 		cudaEventRecord(ev_in[b], pr.s_in);
@@ -1973,7 +1997,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		mark("pass2 end", b, sm);
 		if (sm_out) {
 			cudaStreamWaitEvent(pr.s_out, ev_done[b], 0);
-			cudaMemcpyAsync(ho + (c0 - ckeep0), dout->off + c0, (nlists + (b == last_act ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+			download_offsets(c0, nlists, b == last_act);
 			cudaStreamWaitEvent(ctx->s_out2, ev_done[b], 0);
 			mark("download begin", b, ctx->s_out2);
 			k_copy_out<<<ctx->copy_out_ctas, COPY_OUT_THREADS, 0, ctx->s_out2>>>(dout->spans, reinterpret_cast<double2 *>(hs), gb.p + pb + 1, gb.p + b + 1, dcap);
@@ -2012,7 +2036,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		cudaStreamWaitEvent(pr.s_out, ev_done[b], 0);
 		mark("download begin", b, pr.s_out);
 		KT_MARK_STREAM(2000 + b, pr.s_out);
-		cudaMemcpyAsync(ho + (c0 - ckeep0), dout->off + c0, (nlists + (b == last_act ? 1 : 0)) * sizeof(uint32_t), cudaMemcpyDeviceToHost, pr.s_out);
+		download_offsets(c0, nlists, b == last_act);
 	};
 	const bool host_driven = !(sm_out && !ctx->pipe_dry);
 	if (host_driven) offsets_ahead(0);
@@ -2027,7 +2051,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			break;
 		}
 		if (!ctx->pipe_ahead) offsets_ahead(b, true);
-		if (tot > base) cudaMemcpyAsync(hs + 2 * base, dout->spans + base, (tot - base) * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
+		if (tot > base) {
+			unsigned long long j0 = base, j1 = tot;
+			if (al_sp_out) { j0 &= ~(al_sp_out - 1); j1 = std::min<unsigned long long>(dcap, (j1 + al_sp_out - 1) & ~(al_sp_out - 1)); }
+			cudaMemcpyAsync(hs + 2 * j0, dout->spans + j0, (j1 - j0) * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
+		}
 		mark("download end", b, pr.s_out);
 		KT_MARK_STREAM(3000 + b, pr.s_out);
 		base = tot;
@@ -2624,6 +2652,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "pipe_lean") == 0) {
 		if (std::strcmp(value, "on") == 0) { ctx->pipe_lean = true; ctx->pipe_lists = ctx->pipe_redo = false; return VO_OK; }
 		if (std::strcmp(value, "off") == 0) { ctx->pipe_lean = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "copy_align") == 0) {
+		const int n = std::atoi(value);
+		if (n == 0 || (n >= 16 && n <= 65536 && (n & (n - 1)) == 0)) { ctx->copy_align = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "pipe_ahead") == 0) {
 		if (std::strcmp(value, "on") == 0) { ctx->pipe_ahead = true; return VO_OK; }
