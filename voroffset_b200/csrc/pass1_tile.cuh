@@ -938,7 +938,16 @@ __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHe
 	}
 	if (!active || (UH == 0 && DH == 0)) return;
 	if (!MULTI || maxlayer == 0) eval_classes<P1_CB, 1, CAP, LCAP, DUAL>(a, t, UL, UH, DL, DH);   // every survivor is the first interval of its column
-	else eval_classes<P1_CB, 2, CAP, LCAP>(a, t, UL, UH, DL, DH);                           // two hulls per class
+	else if (maxlayer == 1) eval_classes<P1_CB, 2, CAP, LCAP>(a, t, UL, UH, DL, DH);        // two hulls per class
+	else {
+		// three layers and more (lattices, stacks of plates): two hulls per class would come out "complex" for nearly
+		// every class - straight to the sorted-list union
+		for (int j = min(UH > UL ? UL : DL, DH > DL ? DL : UL); j < max(UH, DH); ++j) {
+			if (!((j >= UL && j < UH) || (j >= DL && j < DH))) continue;
+			const unsigned long long slot = ((unsigned long long)t.y * (J + 1) + j) * a.nx + t.x0 + t.xi;
+			a.mid[slot] = class_general<CAP, LCAP>(a, t, j, slot);
+		}
+	}
 }
 
 // Tiles that are not processed here: empty ones, ones for another launch, ones left to k_pass1.

@@ -42,11 +42,23 @@ __device__ __forceinline__ unsigned int slot_pool_count(double2 s)
 // Slow path of the running union: insert [s, e] into the sorted disjoint list L[0..n) (n >= 3).
 // Returns the new length, or -1 when the list would outgrow CAP. Kept out of line (and free of any
 // reference to the caller's scalar state) so that the fast-path state stays in registers.
+// proper: every entry that ever went into the list had s <= e, so the upper ends ascend and the first interval that is
+// not entirely below the candidate can be found by looking at the last one (candidates tend to arrive in ascending
+// runs: the intervals of one input column after the other) and then by bisection, instead of walking up from the
+// bottom - the walk was a third of the tile kernel's time on lattices with ~26 intervals per column. (An entry with
+// s > e - not an interval; the reference carries those through its unions - can leave the list unsorted: the walk then.)
 template <int CAP>
-__device__ __noinline__ int run_union_insert_list(double2 *L, int n, double s, double e)
+__device__ __noinline__ int run_union_insert_list(double2 *L, int n, double s, double e, bool proper = false)
 {
 	int i = 0;
-	while (i < n && L[i].y < s) ++i;              // intervals entirely below the candidate
+	if (proper) {
+		if (L[n - 1].y < s) i = n;
+		else {
+			int hi = n - 1;                            // invariant: L[hi].y >= s, everything below i is < s
+			while (i < hi) { const int mid = (i + hi) >> 1; if (L[mid].y < s) i = mid + 1; else hi = mid; }
+		}
+	} else
+		while (i < n && L[i].y < s) ++i;          // intervals entirely below the candidate
 	if (i == n) {                                  // append
 		if (n == CAP) return -1;
 		L[n] = make_double2(s, e);
@@ -79,11 +91,12 @@ struct RunUnion {
 	double s0, e0, s1, e1;          // n == 1: (s0, e0); n == 2: (s0, e0) < (s1, e1)
 	int n;
 	bool overflow;
+	bool proper;                    // n >= 3: every entry of L came from candidates with s <= e (run_union_insert_list)
 	double2 *L;                     // valid for n >= 3 only: read through get()
 
-	__device__ __forceinline__ explicit RunUnion(double2 *list) : s0(0), e0(0), s1(0), e1(0), n(0), overflow(false), L(list) {}
+	__device__ __forceinline__ explicit RunUnion(double2 *list) : s0(0), e0(0), s1(0), e1(0), n(0), overflow(false), proper(false), L(list) {}
 
-	__device__ __forceinline__ void init() { n = 0; overflow = false; }
+	__device__ __forceinline__ void init() { n = 0; overflow = false; proper = false; }
 
 	__device__ __forceinline__ double2 get(int k) const
 	{
@@ -118,11 +131,13 @@ struct RunUnion {
 			else if (e < s1) { L[0] = a; L[1] = c; L[2] = b; }
 			else { L[0] = a; L[1] = b; L[2] = c; }
 			n = 3;
+			proper = s0 <= e0 && s1 <= e1;
 			return;
 		}
 		if (overflow) return;
-		if (n == 2) { L[0] = make_double2(s0, e0); L[1] = make_double2(s1, e1); }
-		const int r = run_union_insert_list<CAP>(L, n, s, e);
+		if (n == 2) { L[0] = make_double2(s0, e0); L[1] = make_double2(s1, e1); proper = false; }
+		proper = proper && s <= e;
+		const int r = run_union_insert_list<CAP>(L, n, s, e, proper);
 		if (r < 0) { overflow = true; return; }
 		n = r;
 		if (n <= 2) { s0 = L[0].x; e0 = L[0].y; if (n == 2) { s1 = L[1].x; e1 = L[1].y; } }

@@ -1670,7 +1670,10 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	vo_dvol *in = nullptr;
 	VO_TRY(new_dvol(ctx, nx, ny, &in));
 	struct InGuard { vo_ctx *c; vo_dvol *p; ~InGuard() { free_dvol(c, p); } } in_guard{ctx, in};
-	VO_TRY(dalloc(ctx, &in->spans, nspans));
+	// (a row window starts at some interval obase of the caller's array: the device copy starts obase % 16 entries into its
+	// block, so that host and device addresses of an interval are aligned alike - vo_ctx::copy_align)
+	const uint32_t in_pad = obase % 16u;
+	VO_TRY(dalloc(ctx, &in->spans, nspans + 16));
 	in->nspans = nspans;
 	vo_dmid *m = new (std::nothrow) vo_dmid();
 	if (!m) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
@@ -1683,7 +1686,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	VO_TRY(dalloc(ctx, &m->flags, 2 * ncols));
 	Tmp<uint4> thr(ctx);
 	VO_TRY(dalloc(ctx, &thr.p, nspans));
-	double2 *const d_sp = in->spans - obase;                // indexed by the host's offsets as they are
+	double2 *const d_sp = in->spans + in_pad - obase;       // indexed by the host's offsets as they are
 	uint4 *const d_thr = thr.p - obase;
 	TilePlan plan, plan0;
 	// (the first band's plan first: init() leaves the kernels' shared-memory limit at what the LAST call asked for, the larger one)
@@ -1768,7 +1771,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const unsigned long long al_bytes = ctx->copy_align >= 16 && (ctx->copy_align & (ctx->copy_align - 1)) == 0 ? (unsigned long long)ctx->copy_align : 0ull;
 	auto aligned_ptr = [&](const void *p) { return al_bytes && (reinterpret_cast<uintptr_t>(p) & (al_bytes - 1)) == 0; };
 	const unsigned long long al_off = aligned_ptr(off) && aligned_ptr(in->off) ? al_bytes / sizeof(uint32_t) : 0ull;
-	const unsigned long long al_sp = aligned_ptr(spans) && aligned_ptr(in->spans) && obase % (al_bytes ? al_bytes / sizeof(double2) : 1) == 0 ? al_bytes / sizeof(double2) : 0ull;
+	const unsigned long long al_sp = aligned_ptr(spans) && aligned_ptr(in->spans) && al_bytes <= 16 * sizeof(double2) ? al_bytes / sizeof(double2) : 0ull;
 	const unsigned long long al_off_out = aligned_ptr(ho) && aligned_ptr(dout->off) && ckeep0 % (al_bytes ? al_bytes / sizeof(uint32_t) : 1) == 0 ? al_bytes / sizeof(uint32_t) : 0ull;
 	const unsigned long long al_sp_out = aligned_ptr(hs) && aligned_ptr(dout->spans) ? al_bytes / sizeof(double2) : 0ull;
 	// offsets of the lists [c0, c0 + n) of the result (+ the closing one for the last band) to the host
