@@ -62,7 +62,10 @@ constexpr int P1_LCAP_S = 24;   // survivors listed per output column, single-in
 constexpr int P1_LCAP_M = 32;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
 constexpr int P1_MAXWARPS = 16; // warps per CTA (one CTA per SM; fewer when the per-warp buffers are large). (20 warps at 96
                                 // registers were tried: the spills cost more than the extra warps give, 0.71 vs 0.65 ms on C5.)
-constexpr int P1_MAXWARPS_M = 16; // ... of the two-hull variant
+#ifndef P1_MAXWARPS_M_V
+#define P1_MAXWARPS_M_V 16
+#endif
+constexpr int P1_MAXWARPS_M = P1_MAXWARPS_M_V; // ... of the two-hull variant
 constexpr int P1_OVF = 224;     // further survivors per output column kept in a global-memory spill area of the warp
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)

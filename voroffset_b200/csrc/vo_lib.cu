@@ -52,6 +52,12 @@ struct vo_ctx {
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
+	int multi_warps = 0;              // vo_set_option("multi_warps", "N"): warps per CTA of the tile kernel's multi-interval launches (0: 12 when the
+	                                  // last dilation of multi-interval columns left long lists in the mid pool, else 16). Long lists are folded by
+	                                  // the sorted-list union, whose lists live in local memory: 16 warps x 32 lanes x ~26 intervals outgrow the L1
+	                                  // and every insertion waits for the L2 (C3 lattice, R = 5: 1.75 ms with 16 warps, 1.50 with 14, 1.46-1.54 with
+	                                  // 10-12, 1.97 with 8; the same lattice with R = 12, whose unions merge to a few intervals: 0.76 with 16, 0.99 with 12)
+	double pooled_per_column = -1;    // mid-pool entries per column the last tile-kernel pass 1 with multi-interval tiles needed (-1: none yet)
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
 	int tile_dbuf = -1;               // vo_set_option("tile_dbuf", "auto" | "on" | "off"): double-buffered candidate staging of the tile kernel
 	int tile_lean = -1;               // vo_set_option("tile_lean", "auto" | "on" | "off"): candidates of the list launches left in global memory
@@ -800,12 +806,13 @@ struct TilePlan {
 		bool dummy = false;
 		plan(cmax_small, P1_LCAP_S, P1_MAXWARPS, false, nw_small, db_small, dummy, smem_small);
 		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS, true, nw_big, db_big, lean_big, smem_big);
-		plan(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M, true, nw_multi, db_multi, lean_multi, smem_multi);
+		const int mw = std::min(P1_MAXWARPS_M, ctx->multi_warps > 0 ? ctx->multi_warps : ctx->pooled_per_column >= 8.0 ? 12 : P1_MAXWARPS_M);   // (vo_ctx::multi_warps)
+		plan(cmax_multi, P1_LCAP_M, mw, true, nw_multi, db_multi, lean_multi, smem_multi);
 		if (lean_multi) {                // lean costs the same whatever the capacity: one launch for every multi-interval tile
 			cmax_multi = cmax_big;
-			plan(cmax_multi, P1_LCAP_M, P1_MAXWARPS_M, true, nw_multi, db_multi, lean_multi, smem_multi);
+			plan(cmax_multi, P1_LCAP_M, mw, true, nw_multi, db_multi, lean_multi, smem_multi);
 		}
-		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS_M, true, nw_bigmulti, db_bigmulti, lean_bigmulti, smem_bigmulti);   // launch 4: the multi-interval tiles beyond cmax_multi
+		plan(cmax_big, P1_LCAP_M, mw, true, nw_bigmulti, db_bigmulti, lean_bigmulti, smem_bigmulti);   // launch 4: the multi-interval tiles beyond cmax_multi
 		cudaError_t e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_multi, smem_bigmulti));
@@ -1038,7 +1045,12 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
 		}
 		if (h[4]) return bail(fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union"));
-		if (h[0] <= m->pool_cap) { m->pool_used = h[0]; ctx->pool_hint = next_hint(ctx->pool_hint, h[0]); *out = m; return VO_OK; }
+		if (h[0] <= m->pool_cap) {
+			m->pool_used = h[0]; ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
+			if (tile_now && h[5]) ctx->pooled_per_column = (double)h[0] / (double)std::max<unsigned long long>(1, (unsigned long long)in->nx * in->ny);
+			*out = m;
+			return VO_OK;
+		}
 		dfree(ctx, m->pool);
 		m->pool = nullptr;
 		m->pool_cap = h[0] + h[0] / 8 + 1024;
@@ -1136,7 +1148,12 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 				const unsigned long long *h = ctx->last_ctr;
 				const bool short1 = h[0] > pool_cap || h[2] > redo_cap || h[4] != 0 || (redo_skipped && h[2] != 0);
 				if (redo_skipped && h[2] != 0) ctx->redo_recent = 16;
-				if (rc == VO_OK && !short1) { ctx->pool_hint = next_hint(ctx->pool_hint, h[0]); break; }
+				if (rc == VO_OK && !short1) {
+					ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
+					if (h[5]) ctx->pooled_per_column = (double)h[0] / (double)std::max<unsigned long long>(1, (unsigned long long)in->nx * in->ny);
+					if (h[5] && std::getenv("VO_TRACE")) std::fprintf(stderr, "[vo trace] mid-pool entries per column %.2f\n", ctx->pooled_per_column);
+					break;
+				}
 				if (rc == VO_OK) { free_dvol(ctx, *out); *out = nullptr; }
 				else if (!short1) return rc;
 				// repeat, synchronously this time (it regrows its pool / reports what cannot be done)
@@ -2655,6 +2672,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "pipe_lean") == 0) {
 		if (std::strcmp(value, "on") == 0) { ctx->pipe_lean = true; ctx->pipe_lists = ctx->pipe_redo = false; return VO_OK; }
 		if (std::strcmp(value, "off") == 0) { ctx->pipe_lean = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "multi_warps") == 0) {
+		const int n = std::atoi(value);
+		if (n >= 0 && n <= 64) { ctx->multi_warps = n; return VO_OK; }
 	}
 	if (std::strcmp(key, "copy_align") == 0) {
 		const int n = std::atoi(value);
