@@ -84,8 +84,14 @@ uint64_t    vo_launch_count(const vo_ctx *ctx);
  * "tile_order" = "on" | "off" (expensive pass-1 tiles first); "tile_ctas" = 1..8 (CTAs per SM of the tile kernel);
  * "block_cache" = "on" | "off" (released scratch blocks >= 1 MiB kept whole for the next call);
  * host-buffer call (vo_morph3d): "pipeline" = "on" | "off" (bands of rows uploaded, processed and downloaded
- * concurrently), "bands" = 3..64, "band_split" = 1..4, "band_free" = 0..96 SMs, "pipe_warps" = 1..64;
- * y-slab step: "slab" = "overlap" | "serial".                                                           */
+ * concurrently), "bands" = 3..64, "band_split" = 1..4, "band_free" = 0..96 SMs, "pipe_warps" = 1..64,
+ * "copy_align" = 0 | 16..65536 (band copies start and end on such a boundary; default 256), "pipe_lean" = "on" | "off"
+ * (bands leave out the launches that are idle for height-field-like input; a call that needed one is redone on the plain
+ * path and the context remembers), "pipe_ahead" = "on" | "off" (a band's offsets download enqueued before its total is
+ * known), "pipe_order_one" = "on" | "off", "copy_out" = 0 (default: span downloads by the copy engine) | 1..1024 (CTAs of an
+ * SM-driven span download that needs no host round trip), "erosion" = "auto" | "dual" | "general", "multi_warps" = 0
+ * (auto) | 1..16 (warps per CTA of the tile kernel's multi-interval launches);
+ * y-slab step: "slab" = "overlap" | "serial". (DESIGN.md 4.1-4.3 say what each is for and what it measured.)     */
 int         vo_set_option(vo_ctx *ctx, const char *key, const char *value);
 /* Timing on the context's own stream (torch.cuda.Event only sees torch's streams): vo_mark records event
  * `slot` (0..7); vo_elapsed_ms waits for slot_b and returns the device time between the two marks.     */
