@@ -8,6 +8,14 @@ from voroffset_b200 import synth, morpho, image2d, _lib
 
 ctx = _lib.Context(0)
 out = []
+# pieces per column of the REFERENCE's mid volume for these exact volumes (its own first pass, oracle/_ref
+# ref3d_mid_count = VoronoiVorPower.cpp:50-65, run once on the CPU): SURVEY.md 8(d)'s k_mid
+K_MID = {"C1 torus_x -n 256 -r 8": 24.139, "C3 lattice -n 512 -p 10 -r 5": 23.590, "C4 torus_z -n 1024 -p 18 -r 16": 18.461,
+         "C5 torus_z -n 2048 -r 32": 38.825}
+try:
+    PEAK = float(json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"])
+except Exception:
+    PEAK = 6548.2
 
 def timed3d(name, vol, R, opn, method, reps=5):
     op = morpho.make_operator(method, ctx)
@@ -18,6 +26,7 @@ def timed3d(name, vol, R, opn, method, reps=5):
         r, t1, t2 = op.morph_dev(opn, d, R)
         ctx.mark(1)
         if i >= 2: ms.append(ctx.elapsed_ms(0, 1))
+        k1, k2 = ctx.last_profile()
         nseg = r.info()[2]
         r.free()
     ncols = vol.nx * vol.ny
@@ -25,6 +34,14 @@ def timed3d(name, vol, R, opn, method, reps=5):
     rec = {"config": name, "grid": [vol.nx, vol.ny], "radius": R, "operation": opn, "method": method,
            "k_in": round(vol.numSegments() / ncols, 3), "k_out": round(nseg / ncols, 3),
            "ms": round(float(np.median(ms)), 4), "Mcolumns_per_s": round(ncols * prim / np.median(ms) / 1e3, 1)}
+    if method == "ours" and opn == "dilation" and name in K_MID and k1 > 0:
+        # the contract's roofline (bench.py: roofline) for the dominant kernel of pass 1 and for the whole dilation
+        k_in, k_out, k_mid = vol.numSegments() / ncols, nseg / ncols, K_MID[name]
+        b1, b2 = (4 + 16 * k_in) + (4 + 24 * k_mid), (4 + 24 * k_mid) + (4 + 16 * k_out)
+        rec["roofline"] = {"bound": "hbm", "k_mid": k_mid, "algorithmic_bytes_per_column": round(b1, 1), "k_pass1_ms": round(k1, 4),
+                           "achieved": round(b1 * ncols / (k1 * 1e-3) / 1e9, 1), "peak": PEAK, "unit": "GB/s",
+                           "frac": round(b1 * ncols / (k1 * 1e-3) / 1e9 / PEAK, 3),
+                           "whole_dilation_frac": round((b1 + b2) * ncols / (float(np.median(ms)) * 1e-3) / 1e9 / PEAK, 3)}
     print(json.dumps(rec), flush=True)
     out.append(rec)
     d.free()

@@ -703,3 +703,35 @@ def test_pipelined_host_path_with_launches_left_out(ctx):
             piped, _, _ = op.dilation(vol, 31.5)
             assert piped.bit_equal(plain), f"{name}, call {attempt}"
     ctx.set_option("pipe_lean", "on")
+
+
+def test_pipelined_host_path_copy_boundaries_and_sm_download(ctx):
+    """The band copies of the host-buffer call start and end on 256-byte boundaries (vo_ctx::copy_align) and take a few
+    bytes of the neighbouring band along; a grid width that is not a multiple of anything puts every band boundary at an
+    odd offset, a volume without intervals in its first rows puts the first span copies at the very start of the
+    array. Same bits as the exact copies and as the plain path - also with the spans downloaded by the SMs
+    (copy_out: k_copy_out reads the band's range on the device, no host round trip)."""
+    nx, ny, R = 1531, 1099, 32.0                     # odd on purpose; large enough for the banded path
+    rng = np.random.RandomState(11)
+    cnt = (rng.uniform(size=nx * ny) < 0.55).astype(np.int64)
+    cnt[: nx * 150] = 0                              # empty first rows
+    off = np.concatenate(([0], np.cumsum(cnt))).astype(np.uint32)
+    n = int(off[-1])
+    yy, xx = np.divmod(np.nonzero(cnt)[0], nx)
+    a = 200.0 + 40.0 * np.sin(xx * 0.011) * np.cos(yy * 0.013) + rng.uniform(0.0, 0.3, size=n)
+    spans = np.stack((a, a + 3.0 + rng.uniform(0.0, 2.0, size=n)), axis=1)
+    vol = CompressedVolume(nx, ny, off, spans)
+    op = morpho.make_operator("ours", ctx)
+    ctx.set_option("pipeline", "off")
+    plain, _, _ = op.dilation(vol, R)
+    ctx.set_option("pipeline", "on")
+    try:
+        for opts in ({"copy_align": "256"}, {"copy_align": "0"}, {"copy_align": "4096"}, {"copy_align": "256", "copy_out": "32"}):
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            for attempt in range(2):
+                piped, _, _ = op.dilation(vol, R)
+                assert piped.bit_equal(plain), f"{opts}, call {attempt}"
+    finally:
+        ctx.set_option("copy_align", "256")
+        ctx.set_option("copy_out", "0")

@@ -60,7 +60,10 @@ constexpr int P1_TX = 128;      // columns per tile mask (the unit pass 2 skips 
 constexpr int P1_CB = 4;        // classes evaluated together in registers
 constexpr int P1_LCAP_S = 24;   // survivors listed per output column, single-interval launch
 constexpr int P1_LCAP_M = 32;   // ... multi-interval / large-buffer launches (more: the range is re-scanned)
-constexpr int P1_MAXWARPS = 16; // warps per CTA (one CTA per SM; fewer when the per-warp buffers are large). (20 warps at 96
+#ifndef P1_MAXWARPS_V
+#define P1_MAXWARPS_V 16
+#endif
+constexpr int P1_MAXWARPS = P1_MAXWARPS_V; // warps per CTA (one CTA per SM; fewer when the per-warp buffers are large). (20 warps at 96
                                 // registers were tried: the spills cost more than the extra warps give, 0.71 vs 0.65 ms on C5.)
 #ifndef P1_MAXWARPS_M_V
 #define P1_MAXWARPS_M_V 16
