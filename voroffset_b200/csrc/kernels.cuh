@@ -295,6 +295,11 @@ __global__ void __launch_bounds__(128) k_pass2(Pass2Args a)
 // test the 2J tile masks in parallel (two rows per lane), the ballots name the ~10 candidate rows, and only for
 // those are the per-column windows read - instead of 2J+1 flags per consumer.
 constexpr int P2_TX = 128;
+// Resident CTAs per SM the row-segment kernels are compiled for: 8 (64 registers) where the running unions may grow
+// lists (the spills of a tighter budget cost more than the warps give: C3 pass 2 0.225 -> 0.255 ms), P2_SHALLOW = 12
+// (40 registers, ~230 bytes of spills) where the mid slots hold one interval each - height-field-like input, the dual
+// form: the gather is bound by memory latency, C5 k_pass2_rows 0.197 -> 0.174 ms, 14 and 16 give no more.
+constexpr int P2_DEEP = 8, P2_SHALLOW = 12;
 
 // WIDE = false: floor(R) <= 32, the class masks are 32-bit words.
 // The union of output column (tile * P2_TX + threadIdx.x, y) into `u`; every thread of the CTA calls it (warp ballots),
@@ -348,8 +353,8 @@ __device__ __forceinline__ bool pass2_rows_union(const Pass2Args &a, int tiles_x
 	return true;
 }
 
-template <int CAP, bool WIDE = true>
-__global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows(Pass2Args a)
+template <int CAP, bool WIDE = true, int MINB = P2_DEEP>
+__global__ void __launch_bounds__(P2_TX, MINB) k_pass2_rows(Pass2Args a)
 {
 	KT_SCOPE(KT_PASS2_ROWS, a.y0, threadIdx.x == 0);
 	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
@@ -437,7 +442,7 @@ __global__ void __launch_bounds__(256) k_dual_check(const uint32_t *__restrict__
 
 // Pass 2 of the dual form: same segment / tile-mask logic as k_pass2_rows; the fold is a hull (no running union), an
 // output column with an empty column (or the border) in reach is empty, the rest goes through negateInv's clamping.
-__global__ void __launch_bounds__(P2_TX, 8) k_pass2_rows_dual(Pass2Args a)
+__global__ void __launch_bounds__(P2_TX, P2_SHALLOW) k_pass2_rows_dual(Pass2Args a)
 {
 	__shared__ int s_reach[64];
 	if (threadIdx.x <= (unsigned)a.J) s_reach[threadIdx.x] = __ldg(a.reach + threadIdx.x);

@@ -180,7 +180,10 @@ __device__ __forceinline__ void thresh_zero_bank(const ThreshArgs &a)
 	}
 }
 
-__global__ void __launch_bounds__(256, 6) k_thresh(ThreshArgs a)
+#ifndef TH_MINB
+#define TH_MINB 8
+#endif
+__global__ void __launch_bounds__(256, TH_MINB) k_thresh(ThreshArgs a)
 {
 	KT_SCOPE(KT_THRESH, a.c_begin / (unsigned)a.nx, threadIdx.x == 0);
 	extern __shared__ double s_DE[];

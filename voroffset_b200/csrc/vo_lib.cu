@@ -143,6 +143,7 @@ struct vo_dmid {
 	uint16_t *flags = nullptr;      // [2][ny*nx]: class window (lo | hi << 8) needed by the consumer rows above / below each mid column
 	unsigned long long *tilemask = nullptr;   // [2][ny * ceil(nx / P1_TX)]: OR of the windows per pass-1 tile
 	uint64_t pool_cap = 0, pool_used = 0;
+	bool shallow = false;           // pass 1 ran on input known to hold at most one interval per column: pass 2 with more CTAs per SM (P2_SHALLOW)
 	bool redo_skipped = false;      // ... and without its redo launch: any entry in the redo list means "repeat"
 	bool deferred = false;          // pass 1 returned without reading its counters: the caller checks them after pass 2
 	unsigned int redo_cap = 0;      // ... against these
@@ -951,6 +952,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	vo_dmid *m = new (std::nothrow) vo_dmid();
 	if (!m) return fail(ctx, VO_ERR_NOMEM, "out of host memory");
 	m->nx = in->nx; m->ny = in->ny; m->J = t.J; m->R = R;
+	m->shallow = in->max_cnt >= 0 && in->max_cnt <= 1;
 	const unsigned long long nslots = ncols * (t.J + 1);
 	int rc = dalloc(ctx, &m->slots, nslots);
 	unsigned long long pool_cap = std::max(65536ull + (unsigned long long)(t.J + 1) * (in->nspans / 4), ctx->pool_hint);
@@ -1071,7 +1073,9 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEven
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
 		[&](Pass2Args &g) {
 			cudaEventRecord(ctx->kev[2], s);
-			if (g.J <= 32)
+			if (g.J <= 32 && m->shallow)
+				k_pass2_rows<CAP_FAST, false, P2_SHALLOW><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+			else if (g.J <= 32)
 				k_pass2_rows<CAP_FAST, false><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
 			else if (g.J <= 63)
 				k_pass2_rows<CAP_FAST><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
@@ -1990,7 +1994,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			cudaEventRecord(ev_tot[b], ctx->s_ctl);
 			return;
 		}
-		if (J <= 32) k_pass2_rows<CAP_FAST, false><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		if (J <= 32 && no_lists) k_pass2_rows<CAP_FAST, false, P2_SHALLOW><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		else if (J <= 32) k_pass2_rows<CAP_FAST, false><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		else k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		a2.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
 		if (!no_redo) k_pass2<CAP_BIG><<<REDO_GRID, 128, 0, sm>>>(a2);
@@ -2296,6 +2301,7 @@ int slab_begin(vo_ctx *ctx, const vo_dvol *own, double R, int has_prev, int has_
 	if (!m) return bail(fail(ctx, VO_ERR_NOMEM, "out of host memory"));
 	S->mid = m;
 	m->nx = nx; m->ny = ey; m->J = J; m->R = R;
+	m->shallow = own->max_cnt >= 0 && own->max_cnt <= 1;     // (a hint: the halo rows usually look like the rows next to them)
 	const unsigned long long nslots = ncols * (J + 1);
 	m->pool_cap = std::max(65536ull + (unsigned long long)(J + 1) * (total / 4), ctx->pool_hint);
 	rc = dalloc(ctx, &m->slots, nslots);
