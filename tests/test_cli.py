@@ -84,6 +84,28 @@ def test_dexeliser_and_export_without_gpu(tmp_path):
     assert nv % 8 == 0 and nf == 6 * nv // 8 and nv > 0
     assert run("offset3d", mesh, tmp_path / "pts.xyz", "-n", 24, "-x", "noop").returncode == 0
     assert len(open(tmp_path / "pts.xyz").read().splitlines()) == 2 * nv // 8
+    # the reference's hex mesh (Dexelize.cpp:312-351) in Medit format: eight vertices, six border quads and one cell per
+    # interval; every cell has positive volume in Medit's corner order and its quads are the faces of its own box
+    assert run("offset3d", mesh, tmp_path / "hex.mesh", "-n", 24, "-x", "noop").returncode == 0
+    tok = open(tmp_path / "hex.mesh").read().split()
+    iv, iq, ih = tok.index("Vertices"), tok.index("Quadrilaterals"), tok.index("Hexahedra")
+    n_v, n_q, n_h = int(tok[iv + 1]), int(tok[iq + 1]), int(tok[ih + 1])
+    assert n_v == nv and n_q == 6 * n_h and n_v == 8 * n_h and tok[-1] == "End"
+    V = np.array(tok[iv + 2: iv + 2 + 4 * n_v], dtype=float).reshape(-1, 4)[:, :3]
+    H = np.array(tok[ih + 2: ih + 2 + 9 * n_h], dtype=int).reshape(-1, 9)[:, :8] - 1
+    Q = np.array(tok[iq + 2: iq + 2 + 5 * n_q], dtype=int).reshape(-1, 5)[:, :4] - 1
+    for h in H[:: max(1, n_h // 50)]:
+        p = V[h]
+        e1, e2, e3 = p[1] - p[0], p[3] - p[0], p[4] - p[0]          # Medit: 0-1-2-3 bottom, 4-7 above them
+        assert np.dot(np.cross(e1, e2), e3) > 0
+        assert np.allclose(p[2], p[0] + e1 + e2) and np.allclose(p[6], p[0] + e1 + e2 + e3)
+    c = 0
+    box = V[8 * c: 8 * c + 8]
+    centre = box.mean(axis=0)
+    for q in Q[6 * c: 6 * c + 6]:
+        assert set(q) <= set(range(8 * c, 8 * c + 8))
+        a, b, d = V[q[0]], V[q[1]], V[q[3]]
+        assert np.dot(np.cross(b - a, d - a), V[q].mean(axis=0) - centre) > 0      # outward
 
 
 def test_no_cpu_fallback_in_cli(tmp_path):

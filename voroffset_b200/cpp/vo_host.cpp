@@ -365,9 +365,44 @@ namespace voroffset3d
 		return dexels;
 	}
 
-	// dexels -> one box per interval (Dexelize.cpp:312-351) written as an OBJ quad mesh, or the interval
-	// end points as an .xyz point list (Dexelize.cpp:289-310). A ".vol" / ".txt" name writes the
-	// reference's own text format (CompressedVolume::save).
+	// The hex mesh the reference builds (Dexelize.cpp:312-351): one hexahedron with eight vertices of its own per interval;
+	// since no two cells share a vertex, geogram's compute_borders() makes every face of every cell a border facet and
+	// remove_isolated() removes nothing. Written in the Medit text format (what GEO::mesh_save writes for a ".mesh"
+	// name): Vertices, Quadrilaterals (the border), Hexahedra (Medit corner order: bottom face counter-clockwise, then
+	// the top face).
+	static void hex_mesh_dump(std::ostream &out, const CompressedVolume &dexels)
+	{
+		const double sp = dexels.spacing();
+		size_t n = 0;
+		for (int y = 0; y < dexels.gridSize()[1]; ++y)
+			for (int x = 0; x < dexels.gridSize()[0]; ++x) n += dexels.at(x, y).size() / 2;
+		out << "MeshVersionFormatted 2\nDimension 3\nVertices\n" << 8 * n << "\n";
+		for (int y = 0; y < dexels.gridSize()[1]; ++y)
+			for (int x = 0; x < dexels.gridSize()[0]; ++x)
+				for (size_t i = 0; 2 * i + 1 < dexels.at(x, y).size(); ++i) {
+					const double z0 = dexels.at(x, y)[2 * i] * sp, z1 = dexels.at(x, y)[2 * i + 1] * sp;
+					const double x0 = dexels.origin()[0] + x * sp, x1 = dexels.origin()[0] + (x + 1) * sp;
+					const double y0 = dexels.origin()[1] + y * sp, y1 = dexels.origin()[1] + (y + 1) * sp;
+					// (the reference's corner order, Dexelize.cpp:326-329)
+					const double P[8][3] = {{x0, y0, z1}, {x1, y0, z1}, {x0, y1, z1}, {x1, y1, z1}, {x0, y0, z0}, {x1, y0, z0}, {x0, y1, z0}, {x1, y1, z0}};
+					for (auto &p : P) out << p[0] << ' ' << p[1] << ' ' << p[2] << " 0\n";
+				}
+		out << "Quadrilaterals\n" << 6 * n << "\n";
+		const int Q[6][4] = {{1, 2, 4, 3}, {5, 7, 8, 6}, {1, 5, 6, 2}, {3, 4, 8, 7}, {1, 3, 7, 5}, {2, 6, 8, 4}};   // outward normals
+		for (size_t c = 0; c < n; ++c)
+			for (auto &q : Q) out << 8 * c + q[0] << ' ' << 8 * c + q[1] << ' ' << 8 * c + q[2] << ' ' << 8 * c + q[3] << " 0\n";
+		out << "Hexahedra\n" << n << "\n";
+		const int H[8] = {5, 6, 8, 7, 1, 2, 4, 3};
+		for (size_t c = 0; c < n; ++c) {
+			for (int k : H) out << 8 * c + k << ' ';
+			out << "0\n";
+		}
+		out << "End\n";
+	}
+
+	// dexels -> one box per interval (Dexelize.cpp:312-351) written as a Medit hex mesh (".mesh": cells + border facets,
+	// see above) or as an OBJ quad mesh (the border facets alone), or the interval end points as an .xyz point list
+	// (Dexelize.cpp:289-310). A ".vol" / ".txt" name writes the reference's own text format (CompressedVolume::save).
 	void dexel_dump(const std::string &filename, const CompressedVolume &dexels)
 	{
 		std::ofstream out(filename);
@@ -375,6 +410,7 @@ namespace voroffset3d
 		out << std::setprecision(17);
 		const std::string f = lower(filename);
 		if (endswith(f, ".vol") || endswith(f, ".txt")) { dexels.save(out); return; }
+		if (endswith(f, ".mesh")) { hex_mesh_dump(out, dexels); return; }
 		const double sp = dexels.spacing();
 		const bool points = endswith(f, ".xyz");
 		size_t v = 0;
