@@ -2203,11 +2203,8 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	unsigned long long *bank = side ? ctx->d_ctr + NCTR + 8 : ctx->d_ctr;
 	TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
 	const int nx = S->nx, J = S->J;
-	cudaMemsetAsync(bank + 3, 0, sizeof(unsigned long long), sm);
-	cudaMemsetAsync(bank + 5, 0, 3 * sizeof(unsigned long long), sm);
-	cudaMemsetAsync(bank + 10, 0, sizeof(unsigned long long), sm);
-	cudaMemsetAsync(bank + 12, 0, 2 * sizeof(unsigned long long), sm);
 	ThreshArgs ta;
+	ta.zero_bank = bank;                                    // the lists and cursors of this launch set, zeroed by k_thresh (no memsets of their own)
 	ta.nx = nx; ta.ny = S->ext->ny; ta.J = J; ta.off = S->ext->off; ta.spans = S->ext->spans;
 	ta.Dmono = tc->tt.Dmono; ta.Emono = tc->tt.Emono; ta.G = tc->tt.G; ta.reach = tc->dt.reach; ta.thr = S->thr;
 	ta.clip_lo = S->clip_lo; ta.clip_hi = S->clip_hi;
@@ -2217,6 +2214,7 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 	launch_thresh(ta, S->k_in, sm);
 	ctx->launches++;
 	if (y1b > y0b) {
+		ta.zero_bank = nullptr;
 		ta.c_begin = (unsigned long long)y0b * nx; ta.c_end = (unsigned long long)y1b * nx;
 		launch_thresh(ta, S->k_in, sm);
 		ctx->launches++;
@@ -2226,7 +2224,7 @@ void slab_pass1_rows(vo_slab *S, int y0, int y1, int y0b = 0, int y1b = 0, int r
 		unsigned int *ord = S->order + (side ? S->ntiles : 0ull);
 		TilePlan::order_tiles(ctx, ta.est, S->est + (side ? 2 * P1_NBUCKET : 0), ord, (unsigned int)S->plan.tiles_xw * (unsigned int)y0,
 		                      (unsigned int)S->plan.tiles_xw * (unsigned int)(y1 - y0), (unsigned int)S->plan.tiles_xw * (unsigned int)y0b,
-		                      (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), sm);
+		                      (unsigned int)S->plan.tiles_xw * (unsigned int)std::max(0, y1b - y0b), sm, true);   // (one CTA where the set is small: the boundary rows)
 		order = ord;
 	}
 	vo_dmid *m = S->mid;
