@@ -84,8 +84,7 @@ __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
 __device__ __forceinline__ int first_gt(const float *tab, int last, float v)
 {
 	if (!(tab[1] <= v)) return 1;                 // the common case: no far dominance at all
-	if (last >= 2 && !(tab[2] <= v)) return 2;    // ... and the next most common: one class
-	int lo = min(3, last), hi = last;
+	int lo = 2, hi = last;
 	while (lo < hi) { const int mid = (lo + hi) >> 1; if (tab[mid] > v) hi = mid; else lo = mid + 1; }
 	return lo;
 }
@@ -1077,10 +1076,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 		}
 		const uint32_t *s_off = sm.off[b];
 		for (int i = lane; i < SEG; i += 32)
-			for (uint32_t k0 = s_off[i] - h.base, k = k0; k < s_off[i + 1] - h.base; ++k) {
-				sm.ci[b][k] = (uint8_t)i;
-				if (MULTI) sm.ly[b][k] = (uint8_t)min(k - k0, 3u);   // (only the two-hull variant reads the layers)
-			}
+			for (uint32_t k0 = s_off[i] - h.base, k = k0; k < s_off[i + 1] - h.base; ++k) { sm.ci[b][k] = (uint8_t)i; sm.ly[b][k] = (uint8_t)min(k - k0, 3u); }
 	};
 	int claims = 0;                                         // tiles this warp has asked for (a.quota)
 	auto fetch_pos = [&]() -> unsigned int {
