@@ -88,7 +88,8 @@ uint64_t    vo_launch_count(const vo_ctx *ctx);
  * "copy_align" = 0 | 16..65536 (band copies start and end on such a boundary; default 256), "pipe_lean" = "on" | "off"
  * (bands leave out the launches that are idle for height-field-like input; a call that needed one is redone on the plain
  * path and the context remembers), "pipe_ahead" = "on" | "off" (a band's offsets download enqueued before its total is
- * known), "pipe_order_one" = "on" | "off", "copy_out" = 0 (default: span downloads by the copy engine) | 1..1024 (CTAs of an
+ * known), "pipe_order_one" = "on" | "off", "copy_batch" = "on" | "off" (the two copies of a band and direction as one
+ * cudaMemcpyBatchAsync), "copy_out" = 0 (default: span downloads by the copy engine) | 1..1024 (CTAs of an
  * SM-driven span download that needs no host round trip), "erosion" = "auto" | "dual" | "general", "multi_warps" = 0
  * (auto) | 1..16 (warps per CTA of the tile kernel's multi-interval launches);
  * y-slab step: "slab" = "overlap" | "serial". (DESIGN.md 4.1-4.3 say what each is for and what it measured.)     */

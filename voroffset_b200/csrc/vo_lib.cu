@@ -78,7 +78,12 @@ struct vo_ctx {
 	                                  // (0: exactly the band's bytes). The copy engines run a copy whose ends are only 16-byte aligned a fifth
 	                                  // slower when both directions are busy (profiles/r2ah_pcie_probe6.txt); the few bytes of the
 	                                  // neighbouring band that travel along are the same bytes, or are overwritten by that band's own copy
-	bool pipe_ahead = true;           // vo_set_option("pipe_ahead", "on"): a band's offsets download is enqueued before the host knows the band's total
+	bool copy_batch = true;           // vo_set_option("copy_batch", "on"): the two copies of a band and direction (offsets, spans) as ONE
+	                                  // cudaMemcpyBatchAsync: the copy engine takes them without the gap between two stream operations
+	                                  // (bare pattern, 8 / 16 bands: 1.46 -> 1.39 / 1.64 -> 1.46 ms, scripts/probes/pcie_probe7.cu)
+	bool pipe_ahead = false;          // vo_set_option("pipe_ahead", "on"): a band's offsets download is enqueued before the host knows the band's total
+	                                  // ("off", the default since copy_batch: offsets and spans of a band leave together as one batch once the
+	                                  // total is known - 1.98 against 2.01 ms)
 	bool pipe_order_one = true;       // vo_set_option("pipe_order_one", "on"): a band's tile order by one CTA in one launch
 	int pipe_warps0 = 0;              // vo_set_option("pipe_warps0", "N"): warps per tile-kernel CTA for the FIRST band only (0: as the others) - few
 	                                  // warps per SM run their tiles faster, which is what the time to the first result needs
@@ -1795,6 +1800,20 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	const unsigned long long al_sp = aligned_ptr(spans) && aligned_ptr(in->spans) && al_bytes <= 16 * sizeof(double2) ? al_bytes / sizeof(double2) : 0ull;
 	const unsigned long long al_off_out = aligned_ptr(ho) && aligned_ptr(dout->off) && ckeep0 % (al_bytes ? al_bytes / sizeof(uint32_t) : 1) == 0 ? al_bytes / sizeof(uint32_t) : 0ull;
 	const unsigned long long al_sp_out = aligned_ptr(hs) && aligned_ptr(dout->spans) ? al_bytes / sizeof(double2) : 0ull;
+	// two copies of one direction: one batch where the runtime has it (vo_ctx::copy_batch), else one after the other
+	auto copy_pair = [&](void *d0, const void *s0, size_t n0, void *d1, const void *s1, size_t n1, cudaMemcpyKind kind, cudaStream_t st) {
+		if (ctx->copy_batch && n0 && n1) {
+			void *dsts[2] = {d0, d1}, *srcs[2] = {const_cast<void *>(s0), const_cast<void *>(s1)};
+			size_t sizes[2] = {n0, n1}, idx[1] = {0}, fail_idx = 0;
+			cudaMemcpyAttributes attr{};
+			attr.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+			if (cudaMemcpyBatchAsync(dsts, srcs, sizes, 2, &attr, idx, 1, &fail_idx, st) == cudaSuccess) return;
+			cudaGetLastError();
+			ctx->copy_batch = false;                            // (a driver without it: plain copies from now on)
+		}
+		if (n0) cudaMemcpyAsync(d0, s0, n0, kind, st);
+		if (n1) cudaMemcpyAsync(d1, s1, n1, kind, st);
+	};
 	// offsets of the lists [c0, c0 + n) of the result (+ the closing one for the last band) to the host
 	auto download_offsets = [&](unsigned long long c0, unsigned long long n, bool last) {
 		unsigned long long a0 = c0, a1 = c0 + n + (last ? 1 : 0);
@@ -1814,12 +1833,10 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		{
 			unsigned long long a0 = c0, a1 = c1 + 1;            // offsets [a0, a1)
 			if (al_off) { a0 = c0 & ~(al_off - 1); a1 = std::min<unsigned long long>(ncols + 1, (c1 + 1 + al_off - 1) & ~(al_off - 1)); }
-			cudaMemcpyAsync(in->off + a0, off + a0, (a1 - a0) * sizeof(uint32_t), cudaMemcpyHostToDevice, pr.s_in);
-		}
-		if (off[c1] > off[c0]) {
-			unsigned long long i0 = off[c0], i1 = off[c1];
-			if (al_sp) { i0 &= ~(al_sp - 1); i1 = std::min<unsigned long long>((unsigned long long)obase + nspans, (i1 + al_sp - 1) & ~(al_sp - 1)); }
-			cudaMemcpyAsync(d_sp + i0, spans + 2 * (size_t)i0, (size_t)(i1 - i0) * sizeof(double2), cudaMemcpyHostToDevice, pr.s_in);
+			unsigned long long i0 = off[c0], i1 = off[c1];      // spans [i0, i1)
+			if (i1 > i0 && al_sp) { i0 &= ~(al_sp - 1); i1 = std::min<unsigned long long>((unsigned long long)obase + nspans, (i1 + al_sp - 1) & ~(al_sp - 1)); }
+			copy_pair(in->off + a0, off + a0, (a1 - a0) * sizeof(uint32_t), d_sp + i0, spans + 2 * (size_t)i0, (size_t)(i1 > i0 ? i1 - i0 : 0) * sizeof(double2),
+			          cudaMemcpyHostToDevice, pr.s_in);
 		}
 		ev_in[b] = pr.event();
 		ev_done[b] = pr.event();
@@ -2075,11 +2092,20 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			rc = PIPE_NA;
 			break;
 		}
-		if (!ctx->pipe_ahead) offsets_ahead(b, true);
-		if (tot > base) {
+		{
 			unsigned long long j0 = base, j1 = tot;
-			if (al_sp_out) { j0 &= ~(al_sp_out - 1); j1 = std::min<unsigned long long>(dcap, (j1 + al_sp_out - 1) & ~(al_sp_out - 1)); }
-			cudaMemcpyAsync(hs + 2 * j0, dout->spans + j0, (j1 - j0) * sizeof(double2), cudaMemcpyDeviceToHost, pr.s_out);
+			if (j1 > j0 && al_sp_out) { j0 &= ~(al_sp_out - 1); j1 = std::min<unsigned long long>(dcap, (j1 + al_sp_out - 1) & ~(al_sp_out - 1)); }
+			const size_t nsp = (size_t)(j1 > j0 ? j1 - j0 : 0) * sizeof(double2);
+			if (!ctx->pipe_ahead) {                             // offsets and spans of the band in one go
+				const int y0 = std::max(ys2[b], keep0), y1 = std::min(ys2[b + 1], keep1);
+				const unsigned long long c0 = (unsigned long long)y0 * nx, n = (unsigned long long)nx * (y1 - y0);
+				unsigned long long a0 = c0, a1 = c0 + n + (b == last_act ? 1 : 0);
+				if (al_off_out) { a0 &= ~(al_off_out - 1); if (b != last_act) a1 = (a1 + al_off_out - 1) & ~(al_off_out - 1); }
+				cudaStreamWaitEvent(pr.s_out, ev_done[b], 0);
+				mark("download begin", b, pr.s_out);
+				KT_MARK_STREAM(2000 + b, pr.s_out);
+				copy_pair(ho + (a0 - ckeep0), dout->off + a0, (a1 - a0) * sizeof(uint32_t), hs + 2 * j0, dout->spans + j0, nsp, cudaMemcpyDeviceToHost, pr.s_out);
+			} else if (nsp) cudaMemcpyAsync(hs + 2 * j0, dout->spans + j0, nsp, cudaMemcpyDeviceToHost, pr.s_out);
 		}
 		mark("download end", b, pr.s_out);
 		KT_MARK_STREAM(3000 + b, pr.s_out);
@@ -2684,6 +2710,10 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "copy_align") == 0) {
 		const int n = std::atoi(value);
 		if (n == 0 || (n >= 16 && n <= 65536 && (n & (n - 1)) == 0)) { ctx->copy_align = n; return VO_OK; }
+	}
+	if (std::strcmp(key, "copy_batch") == 0) {
+		if (std::strcmp(value, "on") == 0) { ctx->copy_batch = true; return VO_OK; }
+		if (std::strcmp(value, "off") == 0) { ctx->copy_batch = false; return VO_OK; }
 	}
 	if (std::strcmp(key, "pipe_ahead") == 0) {
 		if (std::strcmp(value, "on") == 0) { ctx->pipe_ahead = true; return VO_OK; }
