@@ -478,6 +478,8 @@ struct Pass1TileArgs {
 	//             multi_tiles, tiles with more than cmax candidates to big_tiles.
 	//   launch 2  <MULTI=false>, large buffer, tiles = big_tiles.
 	//   launch 3  <MULTI=true> (two hulls per class), tiles = multi_tiles.
+	int layer_major = -1;             // lean multi-interval launches, order in which phase 1 walks the candidates of a tile: -1 layer-major for tiles
+	                                  //      with three layers and more (see `stage` in k_pass1_tile), 0 column-major, 1 layer-major (vo_set_option("cand_order", ...))
 	int quota = 0;                    // > 0: a warp takes at most this many tiles and leaves (launch 1 of the host-buffer pipeline: a
 	                                  //      grid of short-lived CTAs, so that the small kernels of the other bands get SM slots all
 	                                  //      the time instead of waiting for a resident wave to retire); 0: warps stay until the tiles run out
@@ -521,6 +523,7 @@ __host__ __device__ inline size_t pass1_warp_smem(int J, int cmax, int lcap, boo
 	b += (size_t)P1_W * sizeof(uint32_t);                   // list lengths
 	b += (size_t)lcap * P1_W * sizeof(uint32_t);            // survivor lists [s][lane]
 	b += 2 * nb * (((size_t)cmax + 15) & ~(size_t)15);      // segment column and layer of each candidate
+	if (lean) b += 2 * (((size_t)cmax + 15) & ~(size_t)15); // layer-major order of the candidates (uint16, Tile::perm)
 	b += 2 * sizeof(unsigned long long);                    // mbarriers of the two staging buffers
 	return b;
 }
@@ -571,6 +574,7 @@ struct WarpSmem {
 	uint4 *thr;
 	uint32_t *off[2], *cnt, *list;
 	uint8_t *ci[2], *ly[2];
+	uint16_t *perm;                // lean only: the candidates in layer-major order (see `stage` in k_pass1_tile)
 	unsigned long long *mbar;      // [2]
 	__device__ __forceinline__ WarpSmem(unsigned char *raw, int J, int cmax, int lcap, bool dbuf, bool lean)
 	{
@@ -586,7 +590,8 @@ struct WarpSmem {
 		ci[1] = dbuf ? ci[0] + c16 : ci[0];
 		ly[0] = ci[1] + c16;
 		ly[1] = dbuf ? ly[0] + c16 : ly[0];
-		mbar = reinterpret_cast<unsigned long long *>(ly[1] + c16);
+		perm = reinterpret_cast<uint16_t *>(ly[1] + c16);
+		mbar = reinterpret_cast<unsigned long long *>(ly[1] + c16 + (lean ? 2 * c16 : 0));
 	}
 };
 
@@ -986,6 +991,46 @@ __device__ __forceinline__ void tile_other(const Pass1TileArgs &a, const TileHea
 	}
 }
 
+// Layer-major order of a tile's candidates (every column's first interval, then every column's second, ...): phase 1 of
+// the lean multi-interval launches walks them in this order, so the survivors of an output column reach its list - and
+// later the sorted-list union of class_general - roughly in ascending z (neighbouring columns cut the same features),
+// where an insertion is an append or a merge with the tail. In column-major order every column after the first inserted
+// its intervals into the middle of the list: shifts, bisections and merge scans on four lanes of 32 were a third of that
+// launch on a lattice with ten intervals per column. Only the order changes, never the result. mode: -1 = for tiles
+// with three layers and more (below that every class is two hulls, which no order changes), 0 never, 1 always.
+// Called by the whole warp; returns whether `perm` now holds the order. (Out of line: the tile kernel sits at its
+// register limit.)
+__device__ __noinline__ bool layer_major_order(const uint32_t *s_off, uint32_t base, int SEG, uint16_t *perm, int mode)
+{
+	constexpr int NR = 5;                                   // SEG <= 32 + 2 * 63
+	const int lane = threadIdx.x & 31;
+	uint32_t cn[NR], kf[NR];
+	uint32_t maxc = 0;
+#pragma unroll
+	for (int r = 0; r < NR; ++r) {
+		const int i = lane + r * 32;
+		cn[r] = i < SEG ? s_off[i + 1] - s_off[i] : 0u;
+		kf[r] = i < SEG ? s_off[i] - base : 0u;
+		maxc = max(maxc, cn[r]);
+	}
+	maxc = __reduce_max_sync(0xffffffffu, maxc);
+	if (!(mode > 0 || (mode < 0 && maxc >= 3u))) return false;
+	const unsigned int lt = (1u << lane) - 1u;
+	uint32_t at = 0;
+	for (uint32_t l = 0; l < maxc; ++l) {
+#pragma unroll
+		for (int r = 0; r < NR; ++r) {
+			if (r * 32 < SEG) {
+				const bool has = cn[r] > l;
+				const unsigned int bal = __ballot_sync(0xffffffffu, has);
+				if (has) perm[at + __popc(bal & lt)] = (uint16_t)(kf[r] + l);
+				at += __popc(bal);
+			}
+		}
+	}
+	return true;
+}
+
 // One CTA per SM; the cap tables are staged once per CTA, then every WARP works on its own: it pulls tiles
 // (P1_W output columns of one row) with an atomic counter and never meets a CTA barrier again - tile costs vary
 // a lot (steep walls), and a warp that lags only delays itself.
@@ -1067,6 +1112,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 		h.kind = multi ? TK_MULTI : h.ncand > a.cmax ? (a.big_tiles ? TK_BIG : TK_REDO) : h.ncand == 0 ? TK_EMPTY : TK_NORMAL;
 	};
 	// start the staging of a NORMAL tile into buffer b: bulk copies by one lane, the column map by all
+	bool perm_on = false;                                   // lean multi-interval launches: the tile staged last is walked in layer-major order
 	auto stage = [&](const TileHead &h, int b) {
 		if (lane == 0 && !lean) {
 			const unsigned int bytes = (unsigned int)h.ncand * 16u;
@@ -1077,6 +1123,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 		const uint32_t *s_off = sm.off[b];
 		for (int i = lane; i < SEG; i += 32)
 			for (uint32_t k0 = s_off[i] - h.base, k = k0; k < s_off[i + 1] - h.base; ++k) { sm.ci[b][k] = (uint8_t)i; sm.ly[b][k] = (uint8_t)min(k - k0, 3u); }
+		if (MULTI && lean) perm_on = layer_major_order(s_off, h.base, SEG, sm.perm, a.layer_major);
 	};
 	int claims = 0;                                         // tiles this warp has asked for (a.quota)
 	auto fetch_pos = [&]() -> unsigned int {
@@ -1119,11 +1166,15 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 			} else {
 				__syncwarp();                                // (the column map of this tile, written by all lanes)
 				tl.cand = a.spans + cur.base; tl.thr = tl.gthr;
-				uint4 th = lane < cur.ncand ? __ldg(tl.gthr + lane) : make_uint4(0u, 0u, 0u, 0u);
+				// (MULTI: candidates in layer-major order, see `stage`)
+				auto cand_at = [&](int q) -> int { return (MULTI && perm_on) ? (int)sm.perm[q] : q; };
+				int kc = lane < cur.ncand ? cand_at(lane) : 0;
+				uint4 th = lane < cur.ncand ? __ldg(tl.gthr + kc) : make_uint4(0u, 0u, 0u, 0u);
 				for (int k = lane; k < cur.ncand; k += 32) {     // thresholds one batch ahead of their use
-					const uint4 nx4 = k + 32 < cur.ncand ? __ldg(tl.gthr + k + 32) : make_uint4(0u, 0u, 0u, 0u);
-					tl.scatter(th, k, cur.txe);
-					th = nx4;
+					const int kn = k + 32 < cur.ncand ? cand_at(k + 32) : 0;
+					const uint4 nx4 = k + 32 < cur.ncand ? __ldg(tl.gthr + kn) : make_uint4(0u, 0u, 0u, 0u);
+					tl.scatter(th, kc, cur.txe);
+					th = nx4; kc = kn;
 				}
 			}
 		} else tile_other<MULTI>(a, cur);

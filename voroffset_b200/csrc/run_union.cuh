@@ -53,8 +53,9 @@ __device__ __noinline__ int run_union_insert_list(double2 *L, int n, double s, d
 	int i = 0;
 	if (proper) {
 		if (L[n - 1].y < s) i = n;
+		else if (L[n - 2].y < s) i = n - 1;            // (n >= 3) lands on the last interval: the other common case
 		else {
-			int hi = n - 1;                            // invariant: L[hi].y >= s, everything below i is < s
+			int hi = n - 2;                            // invariant: L[hi].y >= s, everything below i is < s
 			while (i < hi) { const int mid = (i + hi) >> 1; if (L[mid].y < s) i = mid + 1; else hi = mid; }
 		}
 	} else

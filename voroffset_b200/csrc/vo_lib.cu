@@ -52,14 +52,13 @@ struct vo_ctx {
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
-	int multi_warps = 0;              // vo_set_option("multi_warps", "N"): warps per CTA of the tile kernel's multi-interval launches (0: 12 when the
-	                                  // last dilation of multi-interval columns left long lists in the mid pool, else 16). Long lists are folded by
-	                                  // the sorted-list union, whose lists live in local memory: 16 warps x 32 lanes x ~26 intervals outgrow the L1
-	                                  // and every insertion waits for the L2 (C3 lattice, R = 5: 1.75 ms with 16 warps, 1.50 with 14, 1.46-1.54 with
-	                                  // 10-12, 1.97 with 8; the same lattice with R = 12, whose unions merge to a few intervals: 0.76 with 16, 0.99 with 12)
+	int multi_warps = 0;              // vo_set_option("multi_warps", "N"): warps per CTA of the tile kernel's multi-interval launches (0: chosen by
+	                                  // TilePlan::init - fewer than 16 for deep columns, whose sorted-list unions keep their lists in local memory:
+	                                  // 16 warps x 32 lanes x ~26 intervals outgrow the L1 and every insertion waits for the L2)
 	double pooled_per_column = -1;    // mid-pool entries per column the last tile-kernel pass 1 with multi-interval tiles needed (-1: none yet)
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
 	int tile_dbuf = -1;               // vo_set_option("tile_dbuf", "auto" | "on" | "off"): double-buffered candidate staging of the tile kernel
+	int cand_order = -1;              // vo_set_option("cand_order", "auto" | "column" | "layer"): order in which the lean multi-interval launches walk a tile's candidates (Pass1TileArgs::layer_major)
 	int tile_lean = -1;               // vo_set_option("tile_lean", "auto" | "on" | "off"): candidates of the list launches left in global memory
 	int band_split = 2;               // vo_set_option("band_split", "N"): a band's pass-1 launch set takes 1/N of the SMs (host-buffer pipeline)
 	int pipe_warps = 64;              // vo_set_option("pipe_warps", "N"): warps per tile-kernel CTA in the host-buffer pipeline (default: as many as fit)
@@ -749,6 +748,7 @@ struct TilePlan {
 	int cmax_small = 0, cmax_big = 0, cmax_multi = 0;
 	int nw_small = 1, nw_big = 1, nw_multi = 1, nw_bigmulti = 1;
 	bool db_small = true, db_big = true, db_multi = true, db_bigmulti = false;   // candidates double-buffered (pass1_warp_smem)
+	bool multi_bounded = false;
 	bool lean_big = false, lean_multi = false, lean_bigmulti = false;             // ... or left in global memory
 	size_t smem_bigmulti = 0;
 	size_t smem_small = 0, smem_big = 0, smem_multi = 0;
@@ -773,7 +773,7 @@ struct TilePlan {
 		if (quota > 0) return std::max(1u, (ntiles + (unsigned int)(nw_small * quota) - 1) / (unsigned int)(nw_small * quota));
 		return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)(sms_avail * cps), (ntiles + nw_small - 1) / nw_small));
 	}
-	int init(vo_ctx *ctx, int nx, int J_, double k_in, int warps_cap = 64, int cps_override = 0, int quota_ = 0, unsigned int ntiles_max = 0)
+	int init(vo_ctx *ctx, int nx, int J_, double k_in, int warps_cap = 64, int cps_override = 0, int quota_ = 0, unsigned int ntiles_max = 0, long long max_cnt = -1, int ny_hint = 0)
 	{
 		J = J_;
 		quota = quota_;
@@ -812,10 +812,19 @@ struct TilePlan {
 		bool dummy = false;
 		plan(cmax_small, P1_LCAP_S, P1_MAXWARPS, false, nw_small, db_small, dummy, smem_small);
 		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS, true, nw_big, db_big, lean_big, smem_big);
-		const int mw = std::min(P1_MAXWARPS_M, ctx->multi_warps > 0 ? ctx->multi_warps : ctx->pooled_per_column >= 8.0 ? 12 : P1_MAXWARPS_M);   // (vo_ctx::multi_warps)
+		// (vo_ctx::multi_warps) deep columns - known from the volume, or seen in the last mid pool - go through the sorted-list
+		// union, whose local-memory lists want the L1 to themselves: 16 warps thrash it (profiles/r2be_ab.txt: lattice 512,
+		// R = 5 / 8 / 12: 1.30 / 2.05 / 2.55 ms with 16 warps, 1.23 / 1.87 / 2.12 with 14, 1.29 / 1.83 / 1.96 with 12)
+		// - unless the grid has about one tile per warp anyway (lattice 256, R = 12: 0.76 ms with 16 warps, 0.99 with 12)
+		const bool few_tiles = ny_hint > 0 && (long long)tiles_xw * ny_hint < 2ll * sms * P1_MAXWARPS_M;
+		const bool deep = (max_cnt >= 3 || ctx->pooled_per_column >= 8.0) && !few_tiles;
+		const int mw = std::min(P1_MAXWARPS_M, ctx->multi_warps > 0 ? ctx->multi_warps : deep ? (J <= 6 ? 14 : 12) : P1_MAXWARPS_M);
 		plan(cmax_multi, P1_LCAP_M, mw, true, nw_multi, db_multi, lean_multi, smem_multi);
-		if (lean_multi) {                // lean costs the same whatever the capacity: one launch for every multi-interval tile
+		if (lean_multi) {                // lean is cheap per candidate (4 bytes): one launch for every multi-interval tile, sized by what
+			// a tile can hold at most where the deepest column is known (vo_dvol::max_cnt) - shared memory that is not asked
+			// for stays L1, which the local-memory lists of the sorted-list union live in
 			cmax_multi = cmax_big;
+			if (max_cnt > 0 && max_cnt * SEG < (long long)cmax_big) { cmax_multi = std::max(128, ((int)(max_cnt * SEG) + 15) & ~15); multi_bounded = true; }
 			plan(cmax_multi, P1_LCAP_M, mw, true, nw_multi, db_multi, lean_multi, smem_multi);
 		}
 		plan(cmax_big, P1_LCAP_M, mw, true, nw_bigmulti, db_bigmulti, lean_bigmulti, smem_bigmulti);   // launch 4: the multi-interval tiles beyond cmax_multi
@@ -849,6 +858,7 @@ struct TilePlan {
 		if (ovf_bank < 0) ovf_bank = bank == ctx->d_ctr ? 0 : 1;
 		g.ovf = ctx->ovf + (size_t)ovf_bank * ctx->ovf_areas * P1_OVF * P1_W;
 		g.dbg = ctx->dbg_tiles;
+		g.layer_major = ctx->cand_order;
 		unsigned int *big_count = reinterpret_cast<unsigned int *>(bank + 3);
 		unsigned int *multi_count = reinterpret_cast<unsigned int *>(bank + 5);
 		g.big_count = big_count; g.multi_tiles = multi_tiles; g.multi_count = multi_count;
@@ -880,7 +890,7 @@ struct TilePlan {
 		// launch 3: tiles with multi-interval columns (two hulls per class), candidate buffer a quarter above the mean fill;
 		// the tiles beyond it are collected again (in big_tiles, which launch 2 is done with) for launch 4
 		unsigned int *bigmulti_count = reinterpret_cast<unsigned int *>(bank + 12);
-		const bool four = cmax_multi < cmax_big;
+		const bool four = cmax_multi < cmax_big && !multi_bounded;   // (bounded: no tile can hold more than cmax_multi candidates)
 		g.cmax = cmax_multi; g.dbuf = db_multi; g.lean = lean_multi; g.tiles = multi_tiles; g.tiles_count = multi_count;
 		g.big_tiles = four ? big_tiles : nullptr; g.big_count = bigmulti_count;
 		g.tiles_next = reinterpret_cast<unsigned int *>(bank + 7);
@@ -972,7 +982,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 	Tmp<uint4> thr(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &thr.p, in->nspans);
 	TilePlan plan;
-	if (rc == VO_OK && use_tile) rc = plan.init(ctx, in->nx, t.J, k_in);
+	if (rc == VO_OK && use_tile) rc = plan.init(ctx, in->nx, t.J, k_in, 64, 0, 0, 0, in->max_cnt, in->ny);
 	const unsigned long long ntiles = (unsigned long long)plan.tiles_xw * in->ny;
 	Tmp<unsigned int> big_tiles(ctx), multi_tiles(ctx);
 	if (rc == VO_OK && use_tile) rc = dalloc(ctx, &big_tiles.p, ntiles);
@@ -2746,6 +2756,11 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "scan") == 0) {
 		if (std::strcmp(value, "fused") == 0) { ctx->fused_scan = true; return VO_OK; }
 		if (std::strcmp(value, "classic") == 0) { ctx->fused_scan = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "cand_order") == 0) {
+		if (std::strcmp(value, "auto") == 0) { ctx->cand_order = -1; return VO_OK; }
+		if (std::strcmp(value, "column") == 0) { ctx->cand_order = 0; return VO_OK; }
+		if (std::strcmp(value, "layer") == 0) { ctx->cand_order = 1; return VO_OK; }
 	}
 	if (std::strcmp(key, "tile_lean") == 0) {
 		if (std::strcmp(value, "auto") == 0) { ctx->tile_lean = -1; return VO_OK; }
