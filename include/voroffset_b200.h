@@ -19,9 +19,11 @@
  * Limits the reference does not have (all reported, never silent):
  *   - CSR offsets are uint32: at most 2^32 - 9 columns and 2^32 - 1 intervals per volume (VO_ERR_OVERFLOW beyond);
  *   - 3D radii must be in [0, 4096) dexels (VO_ERR_ARG); the 2D radius is only bounded by 1e9 rows;
- *   - while a column's result is being gathered it may pass through at most 512 disjoint intervals at a time
- *     (the running union of the redo launch, csrc/kernels.cuh: CAP_BIG); a column that needs more fails the whole call
- *     with VO_ERR_OVERFLOW. Lists of up to 32 intervals take the fast path;
+ *   - while a column's result is being gathered its running union may hold at most 32768 disjoint intervals at a time
+ *     (VO_ERR_OVERFLOW beyond). Lists of up to 32 intervals take the fast path, up to 512 the redo launch; a dilation that
+ *     meets a longer one is repeated once with the redo launches in their last-resort form (csrc/kernels.cuh: CAP_HUGE,
+ *     lists in 4.6 GiB of global-memory scratch that only lives for that repeat; VO_ERR_NOMEM if it cannot be had).
+ *     The y-slab step (vo_slab_*, vo_mg_*) and the split passes (vo_pass1_dev / vo_pass2_dev) stop at 512;
  *   - host CSR inputs are validated (off[0] = 0, offsets non-decreasing: VO_ERR_ARG); volumes that are ALREADY in device
  *     memory (vo_dvol_from_device, the vo_*_dev entry points) are trusted.
  *

@@ -279,6 +279,50 @@ def test_many_layers_use_the_redo_path(ctx, oracle):
         assert got.bit_equal(oracle.morph3d(vol, "dilation", 1.3, method))
 
 
+def test_lists_beyond_the_redo_capacity_take_the_last_resort_launch(ctx, oracle):
+    # columns of 700 and 1500 thin layers: the running union outgrows CAP_BIG = 512 as well; the primitive is repeated with the
+    # redo launches in their CAP_HUGE form (lists in global memory) instead of failing with VO_ERR_OVERFLOW (round 1 did)
+    rng = np.random.RandomState(5)
+    lists = []
+    for c in range(6 * 5):
+        n = 1500 if c == 7 else 700 if c == 20 else 40
+        z = np.cumsum(rng.uniform(0.7, 0.9, size=2 * n)) + rng.uniform(0, 0.3)
+        lists.append(z.tolist())
+    dense = CompressedVolume.from_lists(6, 5, lists, origin=(0, 0, -5.0), extent=(6.0, 5.0, 2700.0), spacing=1.0, padding=0)
+    # ... and a mostly empty grid with one such column, which the tile kernel accepts (its sorted-list union hands the slot to
+    # the redo launch of the one-thread-per-slot kernel)
+    lists = []
+    for c in range(64 * 4):
+        n = 700 if c == 64 * 2 + 10 else 3 if c % 7 == 0 else 0
+        lists.append((np.cumsum(rng.uniform(0.7, 0.9, size=2 * n)) + rng.uniform(0, 0.3)).tolist())
+    sparse = CompressedVolume.from_lists(64, 4, lists, origin=(0, 0, -5.0), extent=(64.0, 4.0, 1300.0), spacing=1.0, padding=0)
+    for vol, mode in ((dense, "auto"), (sparse, "auto"), (sparse, "tile")):
+        ctx.set_option("pass1", mode)
+        try:
+            for method in ("ours", "brute_force"):
+                for radius in (0.3, 1.3):
+                    got, _, _ = morpho.make_operator(method, ctx).dilation(vol, radius)
+                    assert got.bit_equal(oracle.morph3d(vol, "dilation", radius, method)), (mode, method, radius)
+                    if radius < 1:
+                        assert got.counts().max() > 512
+        finally:
+            ctx.set_option("pass1", "auto")
+    # the calls that follow are back on the normal launches
+    small = synth.blobs(32, padding=2, seed=4)
+    got, _, _ = morpho.make_operator("ours", ctx).dilation(small, 3.0)
+    assert got.bit_equal(oracle.morph3d(small, "dilation", 3.0, "ours"))
+    # 2D rows
+    rows = []
+    for i in range(8):
+        n = 700 if i == 3 else 20
+        rows.append((np.cumsum(rng.uniform(2.0, 3.0, size=2 * n)) + 1.0).tolist())
+    img = DexelImage.from_lists(5000, rows)
+    d = image2d.DoubleCompressedImage.from_image(img, ctx)
+    d.dilate(0.3 / 8)
+    want = oracle.morph2d(img, "dilate", 0.3 / 8)
+    assert d.bit_equal(want) and int(np.diff(want.off.astype(np.int64)).max()) > 512
+
+
 def test_zero_radius_is_identity(ctx):
     vol = synth.blobs(32, padding=2, seed=4)
     got, _, _ = morpho.make_operator("ours", ctx).dilation(vol, 0.0)

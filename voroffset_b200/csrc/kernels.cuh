@@ -18,6 +18,8 @@ namespace vo {
 
 constexpr int CAP_FAST = 32;    // running-union capacity of the first launch
 constexpr int CAP_BIG = 512;    // capacity of the redo launch for lists that outgrew CAP_FAST
+constexpr int CAP_HUGE = 32768; // ... of the last-resort redo launch (a call that met a list beyond CAP_BIG is repeated with it): the
+                                // lists live in a global-memory scratch, one slice per thread of a small fixed grid (HUGE_GRID)
 constexpr int STAGE_INLINE = 2; // inline slots per staged list
 
 struct Stage {
@@ -43,6 +45,19 @@ struct Work {
 	const unsigned int *count;     // device-side length of `list` (redo launch), capped by cap
 	unsigned int cap;
 	unsigned int *fail;            // redo launch: incremented when an item outgrows CAP_BIG as well
+	double2 *huge = nullptr;       // last-resort redo launch (CAP_HUGE): CAP_HUGE entries per thread of the grid
+};
+
+// Where the running union of a gather item keeps its list from the third interval on: local memory, or - last-resort
+// launch - this thread's slice of the global scratch.
+template <int CAP>
+struct ListStore {
+	double2 a[CAP];
+	__device__ __forceinline__ double2 *ptr(const Work &) { return a; }
+};
+template <>
+struct ListStore<CAP_HUGE> {
+	__device__ __forceinline__ double2 *ptr(const Work &wk) { return wk.huge + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * CAP_HUGE; }
 };
 
 // CAP == CAP_FAST is the first launch (one id per thread, no loop); CAP == CAP_BIG is the redo launch.
@@ -109,8 +124,8 @@ __device__ __forceinline__ void pass1_item(const Pass1Args &a, unsigned long lon
 	const int j = (int)(rest % (unsigned)(a.J + 1));
 	const int y = (int)(rest / (unsigned)(a.J + 1));
 
-	double2 ulist[CAP];
-	RunUnion<CAP> u(ulist);
+	ListStore<CAP> ulist;
+	RunUnion<CAP> u(ulist.ptr(a.wk));
 	const int X = a.reach[j];
 	const int lo = max(-X, -x), hi = min(X, a.nx - 1 - x);
 	const double *Hrow = a.H + (size_t)j * (a.J + 1);
@@ -245,8 +260,8 @@ __device__ __forceinline__ void pass2_item(const Pass2Args &a, unsigned long lon
 	const int x = (int)(c % (unsigned)a.nx);
 	const int y = a.y0 + (int)(c / (unsigned)a.nx);
 
-	double2 ulist[CAP];
-	RunUnion<CAP> u(ulist);
+	ListStore<CAP> ulist;
+	RunUnion<CAP> u(ulist.ptr(a.wk));
 	const int up = min(a.J, y), dn = min(a.J, a.ny - 1 - y);    // rows available above / below
 	const size_t nx = (size_t)a.nx, midrow = (size_t)(a.J + 1) * nx;
 	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
@@ -360,8 +375,8 @@ __global__ void __launch_bounds__(P2_TX, MINB) k_pass2_rows(Pass2Args a)
 	const int tiles_x = (a.nx + P2_TX - 1) / P2_TX;
 	const int tile = (int)(blockIdx.x % (unsigned)tiles_x);
 	const int y = a.y0 + (int)(blockIdx.x / (unsigned)tiles_x);
-	double2 ulist[CAP];
-	RunUnion<CAP> u(ulist);
+	ListStore<CAP> ulist;
+	RunUnion<CAP> u(ulist.ptr(a.wk));
 	if (!pass2_rows_union<CAP, WIDE>(a, tiles_x, tile, y, u)) return;
 	const unsigned long long c = (unsigned long long)(y - a.y0) * a.nx + tile * P2_TX + threadIdx.x;
 	if (u.overflow) { redo_push(a.redo, c); a.st.cnt[c] = 0; return; }
@@ -561,8 +576,8 @@ __device__ __forceinline__ void brute_item(const BruteArgs &a, unsigned long lon
 	const int x = (int)(c % (unsigned)a.nx);
 	const int y = (int)(c / (unsigned)a.nx);
 
-	double2 ulist[CAP];
-	RunUnion<CAP> u(ulist);
+	ListStore<CAP> ulist;
+	RunUnion<CAP> u(ulist.ptr(a.wk));
 	const int ylo = max(-a.J, -y), yhi = min(a.J, a.ny - 1 - y);
 	const int xlo = max(-a.J, -x), xhi = min(a.J, a.nx - 1 - x);
 	for (int dy = ylo; dy <= yhi; ++dy) {
@@ -622,8 +637,8 @@ template <int CAP>
 __device__ __forceinline__ void dilate2d_item(const Dil2dArgs &a, unsigned long long c)
 {
 	const int i = (int)c;
-	double2 ulist[CAP];
-	RunUnion<CAP> u(ulist);
+	ListStore<CAP> ulist;
+	RunUnion<CAP> u(ulist.ptr(a.wk));
 	for (int di = -a.J; di <= a.J; ++di) {
 		const int r = i + di;
 		const double h = __ldg(a.h2 + abs(di));

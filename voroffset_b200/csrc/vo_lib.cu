@@ -51,6 +51,9 @@ struct vo_ctx {
 	uint32_t *ovf = nullptr;          // spill area of the tile kernel's survivor lists (pass1_tile.cuh), allocated on first use
 	uint64_t out_hint = 0;            // intervals of the last pipelined result (+12 %): sizes the pinned span buffer
 	bool no_pipeline = false;         // vo_set_option("pipeline", "off")
+	// last resort for lists beyond CAP_BIG (with_huge_lists): the redo launches run with CAP_HUGE and lists in `huge_scratch`
+	bool huge = false, list_overflow = false;
+	double2 *huge_scratch = nullptr;
 	bool tile_order = true;           // vo_set_option("tile_order", "off"): pass-1 tiles in row-major order instead of expensive first
 	int multi_warps = 0;              // vo_set_option("multi_warps", "N"): warps per CTA of the tile kernel's multi-interval launches (0: chosen by
 	                                  // TilePlan::init - fewer than 16 for deep columns, whose sorted-list unions keep their lists in local memory:
@@ -449,6 +452,41 @@ int read_counters(vo_ctx *ctx, unsigned long long h[NREAD])
 // The whole chain - gather, redo, prefix sum - is enqueued without a host round trip; the single
 // synchronisation at the end returns the counters and the grand total together.
 constexpr unsigned int REDO_GRID = 148 * 4;
+constexpr unsigned int HUGE_GRID = 74;      // last-resort redo launch: 74 x 128 threads x CAP_HUGE x 16 bytes = 4.6 GiB of scratch
+
+// "a list outgrew the redo capacity": remembered, so that the primitive can be repeated with the last-resort launch
+int fail_list_overflow(vo_ctx *ctx)
+{
+	ctx->list_overflow = true;
+	return fail(ctx, VO_ERR_OVERFLOW, ctx->huge ? "a dexel list needs more than 32768 disjoint intervals in its running union"
+	                                           : "a dexel list needs more than 512 disjoint intervals in its running union");
+}
+
+// Runs a primitive (a dilation: both passes, brute force, the 2D rows); if it fails because a running union outgrew
+// CAP_BIG, runs it once more with the redo launches in their last-resort form (CAP_HUGE, lists in global memory: slow,
+// but the reference has no such limit at all). The scratch only lives for that second run.
+template <typename F>
+int with_huge_lists(vo_ctx *ctx, F f)
+{
+	if (ctx->huge) return f();
+	ctx->list_overflow = false;
+	int rc = f();
+	if (rc != VO_ERR_OVERFLOW || !ctx->list_overflow) return rc;
+	const size_t bytes = (size_t)HUGE_GRID * 128 * CAP_HUGE * sizeof(double2);
+	if (cudaMalloc((void **)&ctx->huge_scratch, bytes) != cudaSuccess) {
+		cudaGetLastError();
+		ctx->huge_scratch = nullptr;
+		return fail(ctx, VO_ERR_NOMEM, "scratch of the last-resort launch (a dexel list needs more than 512 disjoint intervals in its running union)");
+	}
+	ctx->huge = true;
+	ctx->err.clear();
+	rc = f();
+	ctx->huge = false;
+	cudaStreamSynchronize(ctx->stream);
+	cudaFree(ctx->huge_scratch);
+	ctx->huge_scratch = nullptr;
+	return rc;
+}
 
 // tile state of k_scan_compact for `ntiles` tiles: grown when needed, cleared when grown and when the epoch wraps
 // (growing and the epoch wrap clear the array and wait for that: rare, and other streams may use it next)
@@ -510,7 +548,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 	}
 	// The redo launch is normally idle (no list outgrows the fast capacity): it is left out, and the call repeats with it
 	// when the counters say that a list did (and keeps launching it for the calls that follow).
-	bool skip_redo = ctx->redo_recent == 0;
+	bool skip_redo = ctx->redo_recent == 0 && !ctx->huge;
 	if (ctx->redo_recent > 0) --ctx->redo_recent;
 	for (int attempt = 0; attempt < 4; ++attempt) {
 		// only the counters of the staged gather: a pass 1 may be in flight on the same stream (pipelined path)
@@ -526,6 +564,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 			args.wk = Work{nullptr, nlists, nullptr, 0u, nullptr};
 			launch_fast(args);
 			args.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
+			args.wk.huge = ctx->huge_scratch;                    // (ctx->huge: the launch_big of every caller launches its CAP_HUGE form)
 			if (!skip_redo) launch_big(args, REDO_GRID);
 			if (fused) {
 				uint32_t epoch = 0;
@@ -560,7 +599,7 @@ int run_staged(vo_ctx *ctx, Args &args, unsigned long long nlists, unsigned long
 		if (fused) total = h[NCTR + 1];
 		if (skip_redo && h[8] > 0) { skip_redo = false; ctx->redo_recent = 16; continue; }
 		if (h[8] > redo_cap) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
-		if (h[9]) return fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union");
+		if (h[9]) return fail_list_overflow(ctx);
 		ctx->stage_hint = next_hint(ctx->stage_hint, h[1]);
 		if (h[1] > sb.st.pool_cap) { VO_TRY(sb.regrow(h[1] + h[1] / 8 + 1024)); continue; }
 		if (total >= (1ull << 32)) return fail(ctx, VO_ERR_OVERFLOW, "result has more than 2^32-1 intervals");
@@ -1043,12 +1082,14 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 		}
 		// (deferred: the redo launch - normally idle - is left out like run_staged's; the caller, who reads the counters
 		// after pass 2, repeats the dilation without `defer` when a list did outgrow the fast capacity)
-		const bool skip_redo = defer && ctx->redo_recent == 0 && attempt == 0;
+		const bool skip_redo = defer && ctx->redo_recent == 0 && attempt == 0 && !ctx->huge;
 		m->redo_skipped = skip_redo;
 		if (nslots && !dual && !skip_redo) {
 			// redo launch over the device-side list (fixed grid, reads the count itself)
 			a.wk = Work{rb.rd.list, 0ull, rb.rd.count, rb.rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 4)};
-			k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, ctx->stream>>>(a);
+			a.wk.huge = ctx->huge_scratch;
+			if (ctx->huge) k_pass1<CAP_HUGE><<<HUGE_GRID, 128, 0, ctx->stream>>>(a);
+			else k_pass1<CAP_BIG><<<REDO_GRID, 128, 0, ctx->stream>>>(a);
 			ctx->launches++;
 		}
 		e = cudaGetLastError();
@@ -1061,7 +1102,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 			if (tile_now) { tile_now = false; continue; }       // too many oversized tiles: simple kernel for everything
 			return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
 		}
-		if (h[4]) return bail(fail(ctx, VO_ERR_OVERFLOW, "a dexel list needs more than 512 disjoint intervals in its running union"));
+		if (h[4]) return bail(fail_list_overflow(ctx));
 		if (h[0] <= m->pool_cap) {
 			m->pool_used = h[0]; ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
 			if (tile_now && h[5]) ctx->pooled_per_column = (double)h[0] / (double)std::max<unsigned long long>(1, (unsigned long long)in->nx * in->ny);
@@ -1099,7 +1140,10 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEven
 			cudaEventRecord(ctx->kev[3], s);
 			ctx->kev_valid[1] = true;
 		},
-		[&](Pass2Args &g, unsigned int grid) { k_pass2<CAP_BIG><<<grid, 128, 0, s>>>(g); },
+		[&](Pass2Args &g, unsigned int grid) {
+			if (ctx->huge) k_pass2<CAP_HUGE><<<HUGE_GRID, 128, 0, s>>>(g);
+			else k_pass2<CAP_BIG><<<grid, 128, 0, s>>>(g);
+		},
 		m->nx, y1 - y0, out, done_ev);
 }
 
@@ -1140,22 +1184,24 @@ int brute(vo_ctx *ctx, const vo_dvol *in, double R, vo_dvol **out)
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
 		[&](BruteArgs &g) { k_brute<CAP_FAST><<<blocks_for(g.wk.n, 128), 128, 0, s>>>(g); },
-		[&](BruteArgs &g, unsigned int grid) { k_brute<CAP_BIG><<<grid, 128, 0, s>>>(g); },
+		[&](BruteArgs &g, unsigned int grid) {
+			if (ctx->huge) k_brute<CAP_HUGE><<<HUGE_GRID, 128, 0, s>>>(g);
+			else k_brute<CAP_BIG><<<grid, 128, 0, s>>>(g);
+		},
 		in->nx, in->ny, out);
 }
 
 struct PassTimes { double ms1 = 0, ms2 = 0; };
 
 // dilation of a resident volume; fills the per-pass device times
-int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, PassTimes *pt,
-           double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity())
+int dilate_once(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, PassTimes *pt, double clip_lo, double clip_hi)
 {
 	float t1 = 0, t2 = 0;
 	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 	if (method == VO_METHOD_OURS) {
 		for (int attempt = 0;; ++attempt) {
 			vo_dmid *mid = nullptr;
-			VO_TRY(pass1(ctx, in, R, &mid, clip_lo, clip_hi, attempt == 0));
+			VO_TRY(pass1(ctx, in, R, &mid, clip_lo, clip_hi, attempt == 0 && !ctx->huge));
 			cudaEventRecord(ctx->ev[1], ctx->stream);
 			const bool deferred = mid->deferred, redo_skipped = mid->redo_skipped;
 			const uint64_t pool_cap = mid->pool_cap;
@@ -1195,6 +1241,12 @@ int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, 
 	}
 	if (pt) { pt->ms1 = t1; pt->ms2 = t2; }
 	return VO_OK;
+}
+
+int dilate(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **out, PassTimes *pt,
+           double clip_lo = -std::numeric_limits<double>::infinity(), double clip_hi = std::numeric_limits<double>::infinity())
+{
+	return with_huge_lists(ctx, [&] { return dilate_once(ctx, method, in, R, out, pt, clip_lo, clip_hi); });
 }
 
 // negate (Voronoi.cpp:18-55) / negateInv (Voronoi.cpp:57-89) / vor2d negate. Fused (default): ONE launch (count ->
@@ -1446,10 +1498,13 @@ int dilate2d(vo_ctx *ctx, const vo_dvol *in, int width, double R, int complement
 	a.off = in->off; a.spans = in->spans; a.h2 = dh.p;
 	const unsigned long long nlists = (unsigned long long)in->nx;
 	cudaStream_t s = ctx->stream;
-	return run_staged(ctx, a, nlists, 65536ull + 4 * in->nspans,
+	return with_huge_lists(ctx, [&] { return run_staged(ctx, a, nlists, 65536ull + 4 * in->nspans,
 		[&](Dil2dArgs &g) { k_dilate2d_block<<<(unsigned int)g.wk.n, D2B_THREADS, 0, s>>>(g); },   // CTA per row; overflow -> redo
-		[&](Dil2dArgs &g, unsigned int grid) { k_dilate2d<CAP_BIG><<<grid, 64, 0, s>>>(g); },
-		in->nx, 1, out);
+		[&](Dil2dArgs &g, unsigned int grid) {
+			if (ctx->huge) k_dilate2d<CAP_HUGE><<<2 * HUGE_GRID, 64, 0, s>>>(g);
+			else k_dilate2d<CAP_BIG><<<grid, 64, 0, s>>>(g);
+		},
+		in->nx, 1, out); });
 }
 
 int morph2d_dev(vo_ctx *ctx, int op, const vo_dvol *in, int width, double r, vo_dvol **out)
