@@ -11,4 +11,4 @@ for spec in "lattice 512 10 5 dilation" "lattice 256 14 12 dilation" "lattice 51
   echo -n "new col  "; run $NEW $spec 20 $extra cand_order=column
   echo -n "notail2  "; run $NT $spec 20 $extra
 done
-done 2>&1 | tee gpurun_out/r2bc_ab.txt
+done 2>&1 | tee gpurun_out/r2cc_ab.txt

@@ -10,5 +10,5 @@ for spec in "lattice 512 10 5 dilation" "lattice 256 14 12 dilation" "lattice 51
   echo -n "new auto "; run $NEW $spec 20 $extra
   echo -n "new col  "; run $NEW $spec 20 $extra cand_order=column
 done
-done 2>&1 | tee gpurun_out/r2bd_ab.txt
-for w in 10 12 14 16; do echo -n "new auto multi_warps=$w "; run $NEW lattice 512 10 5 dilation 20 multi_warps=$w; done 2>&1 | tee -a gpurun_out/r2bd_ab.txt
+done 2>&1 | tee gpurun_out/r2cd_ab.txt
+for w in 10 12 14 16; do echo -n "new auto multi_warps=$w "; run $NEW lattice 512 10 5 dilation 20 multi_warps=$w; done 2>&1 | tee -a gpurun_out/r2cd_ab.txt

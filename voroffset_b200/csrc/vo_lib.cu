@@ -852,7 +852,7 @@ struct TilePlan {
 		plan(cmax_small, P1_LCAP_S, P1_MAXWARPS, false, nw_small, db_small, dummy, smem_small);
 		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS, true, nw_big, db_big, lean_big, smem_big);
 		// (vo_ctx::multi_warps) deep columns - known from the volume, or seen in the last mid pool - go through the sorted-list
-		// union, whose local-memory lists want the L1 to themselves: 16 warps thrash it (profiles/r2be_ab.txt: lattice 512,
+		// union, whose local-memory lists want the L1 to themselves: 16 warps thrash it (profiles/r2ce_layer_major_ab.txt: lattice 512,
 		// R = 5 / 8 / 12: 1.30 / 2.05 / 2.55 ms with 16 warps, 1.23 / 1.87 / 2.12 with 14, 1.29 / 1.83 / 1.96 with 12)
 		// - unless the grid has about one tile per warp anyway (lattice 256, R = 12: 0.76 ms with 16 warps, 0.99 with 12)
 		const bool few_tiles = ny_hint > 0 && (long long)tiles_xw * ny_hint < 2ll * sms * P1_MAXWARPS_M;
