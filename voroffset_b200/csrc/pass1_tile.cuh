@@ -768,16 +768,37 @@ __device__ __noinline__ double2 class_general(const Pass1TileArgs &a, const Tile
 {
 	double2 ulist[CAP];
 	RunUnion<CAP> u(ulist);
-	for (int s = 0; s < t.niter; ++s) {
+	// (list launches - LCAP == P1_LCAP_M - one survivor ahead: the candidate and its cap are loaded before the previous
+	// survivor goes into the list; an insertion from the third interval on is a call, which no load is moved across. Lattices
+	// 2 - 3 % of the launch. The first launch keeps the plain loop: there the function is all but idle, and the longer live
+	// ranges cost the kernel around it 5 % - C5 k_pass1_tile 0.764 -> 0.803 ms, profiles/r2ch_ab.txt)
+	if (LCAP != P1_LCAP_M) {
+		for (int s = 0; s < t.niter; ++s) {
+			int k, d;
+			uint32_t w;
+			if (!t.survivor(s, k, d, w)) continue;
+			if (window_mask<1>(w, j)) {
+				const double2 ab = t.t.cand[k];
+				const double hh = t.t.Ht[(size_t)d * t.t.JPP + j];
+				u.insert(ab.x - hh, ab.y + hh);
+			}
+		}
+	}
+	bool have = false;
+	double2 ab_p = make_double2(0.0, 0.0);
+	double hh_p = 0.0;
+	for (int s = 0; LCAP == P1_LCAP_M && s < t.niter; ++s) {
 		int k, d;
 		uint32_t w;
 		if (!t.survivor(s, k, d, w)) continue;
 		if (window_mask<1>(w, j)) {
 			const double2 ab = t.t.cand[k];
 			const double hh = t.t.Ht[(size_t)d * t.t.JPP + j];
-			u.insert(ab.x - hh, ab.y + hh);
+			if (have) u.insert(ab_p.x - hh_p, ab_p.y + hh_p);
+			ab_p = ab; hh_p = hh; have = true;
 		}
 	}
+	if (have) u.insert(ab_p.x - hh_p, ab_p.y + hh_p);
 	if (u.overflow) { redo_push(a.redo, slot); return slot_empty(); }
 	if (u.n == 0) return slot_empty();
 	if (u.n == 1) return make_double2(u.s0, u.e0);
