@@ -94,7 +94,9 @@ uint64_t    vo_launch_count(const vo_ctx *ctx);
  * cudaMemcpyBatchAsync), "copy_out" = 0 (default: span downloads by the copy engine) | 1..1024 (CTAs of an
  * SM-driven span download that needs no host round trip), "erosion" = "auto" | "dual" | "general", "multi_warps" = 0
  * (auto) | 1..16 (warps per CTA of the tile kernel's multi-interval launches), "cand_order" = "auto" | "column" | "layer"
- * (order in which those launches walk a tile's candidates; a speed knob, the result never depends on it);
+ * (order in which those launches walk a tile's candidates; a speed knob, the result never depends on it), "tile_general" =
+ * "auto" | "redo" | "inline" (first tile launch: classes that need the sorted-list union go to the redo launch - 20 warps
+ * per SM - or are folded inline - 16 warps; auto switches to inline for a while when a call met such classes);
  * y-slab step: "slab" = "overlap" | "serial". (DESIGN.md 4.1-4.3 say what each is for and what it measured.)     */
 int         vo_set_option(vo_ctx *ctx, const char *key, const char *value);
 /* Timing on the context's own stream (torch.cuda.Event only sees torch's streams): vo_mark records event

@@ -89,6 +89,28 @@ def test_tile_kernel_forced_3d(ctx, oracle, name, gen, radius):
         ctx.set_option("pass1", "auto")
 
 
+def test_complex_classes_in_single_interval_tiles(ctx, oracle):
+    """One interval per column at unrelated heights: most classes of the first tile launch are 'complex' (their survivors do
+    not union to one interval). The 20-warp variant hands them to the redo launch, the 16-warp variant folds them inline, and
+    'auto' moves from the first to the second after the first call: same bits every way."""
+    vol = synth.random_volume(150, 40, kmax=1, padding=3, seed=21)
+    want = oracle.morph3d(vol, "dilation", 6.4, "ours")
+    op = morpho.make_operator("ours", ctx)
+    ctx.set_option("pass1", "tile")
+    try:
+        for mode in ("redo", "inline", "auto", "auto", "redo"):
+            ctx.set_option("tile_general", mode)
+            got, _, _ = op.dilation(vol, 6.4)
+            assert got.bit_equal(want), mode
+            d = morpho.DeviceVolume.upload(ctx, vol)
+            out, _, _ = op.morph_dev("dilation", d, 6.4)
+            assert out.download().bit_equal(want), mode
+            out.free(); d.free()
+    finally:
+        ctx.set_option("pass1", "auto")
+        ctx.set_option("tile_general", "auto")
+
+
 def _height_field(nx, ny, seed, padding, holes=0.03, thick=(0.4, 30.0), rough=3.0):
     """One interval per column (a few columns empty): rough lower and upper surfaces, so that the eroded intervals
     [a + h, b - h] of neighbouring columns cut each other in every way (U <= L, clamping, pinched-off columns)."""

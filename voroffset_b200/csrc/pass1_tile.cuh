@@ -69,6 +69,11 @@ constexpr int P1_MAXWARPS = P1_MAXWARPS_V; // warps per CTA (one CTA per SM; few
 #define P1_MAXWARPS_M_V 16
 #endif
 constexpr int P1_MAXWARPS_M = P1_MAXWARPS_M_V; // ... of the two-hull variant
+#ifndef P1_MAXWARPS_LEAN_V
+#define P1_MAXWARPS_LEAN_V 20
+#endif
+constexpr int P1_MAXWARPS_LEAN = P1_MAXWARPS_LEAN_V; // ... of the first launch without the inline sorted-list union (k_pass1_tile<..., GEN = false>: 88
+                                // registers; 22 / 23 warps at 80 registers were no faster than 20, profiles/r2ci_defer_general_ab.txt)
 constexpr int P1_OVF = 224;     // further survivors per output column kept in a global-memory spill area of the warp
 
 __device__ __forceinline__ int first_ge(const double *tab, int J, double need)
@@ -816,7 +821,7 @@ __device__ __noinline__ double2 class_general(const Pass1TileArgs &a, const Tile
 // DUAL (erosion in dual form, vo_lib.cu: erode_dual): the candidates are read as the mirrored intervals (-z1, -z2);
 // the hull (min, max) IS the result then - the intersection of the eroded intervals, mirrored - so no class is ever
 // "complex".
-template <int CB, int NL, int CAP, int LCAP, bool DUAL = false>
+template <int CB, int NL, int CAP, int LCAP, bool DUAL = false, bool GEN = true>
 __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThread<LCAP> &t, int cb, unsigned int need)
 {
 	const double inf = __longlong_as_double(0x7FF0000000000000LL);
@@ -879,7 +884,10 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 		const int j = cb + q;
 		const unsigned long long slot = ((unsigned long long)t.y * (t.t.J + 1) + j) * a.nx + t.x0 + t.xi;
 		double2 out;
-		if ((complex_mask >> q) & 1u) out = class_general<CAP, LCAP>(a, t, j, slot);
+		if ((complex_mask >> q) & 1u) {
+			if (GEN) out = class_general<CAP, LCAP>(a, t, j, slot);
+			else { redo_push(a.redo, slot); out = slot_empty(); }     // (the redo launch computes the slot from scratch)
+		}
 		else if (NL == 1) out = make_double2(lo[0][q], hi[0][q]);          // (+inf, -inf) is the empty slot
 		else if ((two_mask >> q) & 1u) {
 			const bool first0 = lo[0][q] < lo[NL - 1][q];
@@ -898,14 +906,14 @@ __device__ __forceinline__ void eval_block(const Pass1TileArgs &a, const TileThr
 }
 
 // every class of the two windows [UL, UH) u [DL, DH), CB at a time, blocks starting at a needed class
-template <int CB, int NL, int CAP, int LCAP, bool DUAL = false>
+template <int CB, int NL, int CAP, int LCAP, bool DUAL = false, bool GEN = true>
 __device__ __forceinline__ void eval_classes(const Pass1TileArgs &a, const TileThread<LCAP> &t, int UL, int UH, int DL, int DH)
 {
 	const int jend = max(UH, DH);
 	int cb = UH > UL ? (DH > DL ? min(UL, DL) : UL) : DL;
 	while (cb < jend) {
 		const unsigned int need = range_mask<CB>(UL, UH, cb) | range_mask<CB>(DL, DH, cb);
-		eval_block<CB, NL, CAP, LCAP, DUAL>(a, t, cb, need);
+		eval_block<CB, NL, CAP, LCAP, DUAL, GEN>(a, t, cb, need);
 		cb += CB;
 		// next needed class at or after cb
 		const bool in_u = cb >= UL && cb < UH, in_d = cb >= DL && cb < DH;
@@ -928,7 +936,7 @@ struct TileHead {
 };
 
 // Phase 2 of a staged tile: lane per output column (the whole warp enters; `active` = owns a column).
-template <int CAP, bool MULTI, int LCAP, bool DUAL = false>
+template <int CAP, bool MULTI, int LCAP, bool DUAL = false, bool GEN = true>
 __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHead &h, const Tile<LCAP> &tl, const uint32_t *s_off)
 {
 	const int J = a.J, lane = threadIdx.x & 31;
@@ -972,7 +980,7 @@ __device__ __forceinline__ void tile_phase2(const Pass1TileArgs &a, const TileHe
 		}
 	}
 	if (!active || (UH == 0 && DH == 0)) return;
-	if (!MULTI || maxlayer == 0) eval_classes<P1_CB, 1, CAP, LCAP, DUAL>(a, t, UL, UH, DL, DH);   // every survivor is the first interval of its column
+	if (!MULTI || maxlayer == 0) eval_classes<P1_CB, 1, CAP, LCAP, DUAL, GEN>(a, t, UL, UH, DL, DH);   // every survivor is the first interval of its column
 	else if (maxlayer == 1) eval_classes<P1_CB, 2, CAP, LCAP>(a, t, UL, UH, DL, DH);        // two hulls per class
 	else {
 		// three layers and more (lattices, stacks of plates): two hulls per class would come out "complex" for nearly
@@ -1064,8 +1072,13 @@ __device__ __noinline__ bool layer_major_order(const uint32_t *s_off, uint32_t b
 //   - right after that one lane starts the bulk copies (TMA, cp.async.bulk) of the next tile's candidates and
 //     thresholds into the other staging buffer; they land during phase 2 of the current tile and are awaited
 //     (mbarrier) at the top of the next iteration.
-template <int CAP, bool MULTI, bool LIST, bool DUAL = false>
-__global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1) k_pass1_tile(Pass1TileArgs a)
+// GEN = false (first launch only): a class whose hull turns out "complex" is handed to the redo launch instead of being
+// folded here by class_general. The call - and the registers the ABI keeps free around it - is what held this kernel at 128
+// registers with spills; without it 88 registers and no spill, i.e. 20 warps per SM instead of 16 (C5 k_pass1_tile
+// 0.645 -> 0.565 ms). Complex classes are rare in height-field-like input; a context that meets them falls back to the
+// inline variant for its next calls (vo_ctx::gen_inline_calls).
+template <int CAP, bool MULTI, bool LIST, bool DUAL = false, bool GEN = true>
+__global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : GEN ? P1_MAXWARPS : P1_MAXWARPS_LEAN), 1) k_pass1_tile(Pass1TileArgs a)
 {
 	constexpr int LCAP = (MULTI || LIST) ? P1_LCAP_M : P1_LCAP_S;
 	constexpr int NR = 5;                                   // segment offsets per lane: P1_W + 2 * 63 + 1 <= 32 * NR
@@ -1212,7 +1225,7 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : P1_MAXWARPS), 1)
 		unsigned int dbg_entries = 0;
 		const long long dbg_t1 = a.dbg ? clock64() : 0;
 		if (a.dbg && cur.kind == TK_NORMAL) { __syncwarp(); dbg_entries = __reduce_add_sync(FULL, sm.cnt[lane]); }
-		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP, DUAL>(a, cur, tl, sm.off[buf]);
+		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP, DUAL, GEN>(a, cur, tl, sm.off[buf]);
 		__syncwarp();                                       // lists, counters and the staging buffer are free again
 		if (a.dbg && lane == 0 && cur.kind == TK_NORMAL) {     // (scripts/tile_costs.py)
 			unsigned long long *d = a.dbg + 4ull * cur.tile;

@@ -58,6 +58,10 @@ struct vo_ctx {
 	int multi_warps = 0;              // vo_set_option("multi_warps", "N"): warps per CTA of the tile kernel's multi-interval launches (0: chosen by
 	                                  // TilePlan::init - fewer than 16 for deep columns, whose sorted-list unions keep their lists in local memory:
 	                                  // 16 warps x 32 lanes x ~26 intervals outgrow the L1 and every insertion waits for the L2)
+	int gen_mode = -1;                // vo_set_option("tile_general", "auto" | "redo" | "inline"): -1 as described below, 0 never inline, 1 always
+	bool last_lean1 = false;          // the last tile launch set started with the 20-warp variant (note_pass1_redo)
+	int gen_inline_calls = 0;         // > 0: the first tile launch keeps its inline sorted-list union for this many more calls (k_pass1_tile<..., GEN>:
+	                                  // a pass 1 that handed slots to the redo launch probably met "complex" classes; 0: the 20-warp variant without it)
 	double pooled_per_column = -1;    // mid-pool entries per column the last tile-kernel pass 1 with multi-interval tiles needed (-1: none yet)
 	int tile_ctas = 1;                // vo_set_option("tile_ctas", "N"): CTAs per SM of the pass-1 tile kernel
 	int tile_dbuf = -1;               // vo_set_option("tile_dbuf", "auto" | "on" | "off"): double-buffered candidate staging of the tile kernel
@@ -785,12 +789,14 @@ inline void launch_thresh(const ThreshArgs &ta, double k_in, cudaStream_t s)
 struct TilePlan {
 	int J = 0, tiles_xw = 0, tiles_x = 0, sms = 148, cps = 1, quota = 0;
 	int cmax_small = 0, cmax_big = 0, cmax_multi = 0;
-	int nw_small = 1, nw_big = 1, nw_multi = 1, nw_bigmulti = 1;
+	int nw_small = 1, nw_big = 1, nw_multi = 1, nw_bigmulti = 1, nw_small_dual = 1;
 	bool db_small = true, db_big = true, db_multi = true, db_bigmulti = false;   // candidates double-buffered (pass1_warp_smem)
 	bool multi_bounded = false;
+	bool lean1 = true;                // first launch without the inline sorted-list union (20 warps; vo_ctx::gen_inline_calls)
 	bool lean_big = false, lean_multi = false, lean_bigmulti = false;             // ... or left in global memory
 	size_t smem_bigmulti = 0;
-	size_t smem_small = 0, smem_big = 0, smem_multi = 0;
+	size_t smem_small = 0, smem_big = 0, smem_multi = 0, smem_small_dual = 0;
+	bool db_small_dual = true;
 	static constexpr int CMAX = 2048;       // largest candidate buffer (11-bit candidate ids in the survivor lists)
 	static bool fits(int J, double k_in) { return J <= 63 && k_in * (P1_W + 2 * J) <= 0.75 * CMAX; }
 	// warps_cap: fewer warps per CTA than the registers allow (the host-buffer pipeline leaves room on every SM for the
@@ -807,10 +813,11 @@ struct TilePlan {
 		return VO_OK;
 	}
 	// first-launch grid over `ntiles` tiles
-	unsigned int grid_small(unsigned int ntiles, int sms_avail) const
+	unsigned int grid_small(unsigned int ntiles, int sms_avail, int nw = 0) const
 	{
-		if (quota > 0) return std::max(1u, (ntiles + (unsigned int)(nw_small * quota) - 1) / (unsigned int)(nw_small * quota));
-		return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)(sms_avail * cps), (ntiles + nw_small - 1) / nw_small));
+		if (nw <= 0) nw = nw_small;
+		if (quota > 0) return std::max(1u, (ntiles + (unsigned int)(nw * quota) - 1) / (unsigned int)(nw * quota));
+		return (unsigned int)std::max(1u, std::min<unsigned int>((unsigned int)(sms_avail * cps), (ntiles + nw - 1) / nw));
 	}
 	int init(vo_ctx *ctx, int nx, int J_, double k_in, int warps_cap = 64, int cps_override = 0, int quota_ = 0, unsigned int ntiles_max = 0, long long max_cnt = -1, int ny_hint = 0)
 	{
@@ -849,7 +856,14 @@ struct TilePlan {
 			smem = pass1_tile_smem(J, cmax, lcap, nw, db, lean);
 		};
 		bool dummy = false;
-		plan(cmax_small, P1_LCAP_S, P1_MAXWARPS, false, nw_small, db_small, dummy, smem_small);
+		lean1 = ctx->gen_mode == 0 || (ctx->gen_mode < 0 && ctx->gen_inline_calls == 0);
+		if (!lean1 && ctx->gen_inline_calls > 0) --ctx->gen_inline_calls;
+		plan(cmax_small, P1_LCAP_S, lean1 ? P1_MAXWARPS_LEAN : P1_MAXWARPS, false, nw_small, db_small, dummy, smem_small);
+		{   // (the dual form's first launch never meets a complex class: always the 20-warp variant)
+			bool db = true, ln = false;
+			plan(cmax_small, P1_LCAP_S, P1_MAXWARPS_LEAN, false, nw_small_dual, db, ln, smem_small_dual);
+			db_small_dual = db;
+		}
 		plan(cmax_big, P1_LCAP_M, P1_MAXWARPS, true, nw_big, db_big, lean_big, smem_big);
 		// (vo_ctx::multi_warps) deep columns - known from the volume, or seen in the last mid pool - go through the sorted-list
 		// union, whose local-memory lists want the L1 to themselves: 16 warps thrash it (profiles/r2ce_layer_major_ab.txt: lattice 512,
@@ -870,11 +884,12 @@ struct TilePlan {
 		cudaError_t e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem_multi, smem_bigmulti));
-		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small_dual);
 		if (e == cudaSuccess) e = cudaFuncSetAttribute(k_pass1_tile<CAP_FAST, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big);
 		if (e != cudaSuccess) return fail(ctx, VO_ERR_CUDA, std::string("k_pass1_tile smem: ") + cudaGetErrorString(e));
-		size_t areas = (size_t)sms * P1_MAXWARPS;
-		if (quota > 0) areas = std::max(areas, (size_t)grid_small(ntiles_max, sms) * nw_small);
+		size_t areas = (size_t)sms * std::max(P1_MAXWARPS, P1_MAXWARPS_LEAN);
+		if (quota > 0) areas = std::max(areas, (size_t)grid_small(ntiles_max, sms) * std::max(nw_small, nw_small_dual));
 		return reserve_ovf(ctx, areas);
 	}
 	// The four launches over the tiles [tile0, tile0 + ntiles). `g` holds the data pointers; the lists and cursors
@@ -911,8 +926,12 @@ struct TilePlan {
 		g.quota = quota;
 		const bool launch2 = cmax_small < cmax_big && !(single && cmax_small >= P1_W + 2 * J);
 		g.sticky_multi = single ? sticky : nullptr; g.sticky_big = (single && !launch2) ? sticky : nullptr;
-		if (dual) k_pass1_tile<CAP_FAST, false, false, true><<<grid_small(ntiles, sms), 32 * nw_small, smem_small, s>>>(g);
+		if (dual) {
+			g.dbuf = db_small_dual;
+			k_pass1_tile<CAP_FAST, false, false, true, false><<<grid_small(ntiles, sms, nw_small_dual), 32 * nw_small_dual, smem_small_dual, s>>>(g);
+		} else if (lean1) k_pass1_tile<CAP_FAST, false, false, false, false><<<grid_small(ntiles, sms), 32 * nw_small, smem_small, s>>>(g);
 		else k_pass1_tile<CAP_FAST, false, false><<<grid_small(ntiles, sms), 32 * nw_small, smem_small, s>>>(g);
+		ctx->last_lean1 = !dual && lean1;
 		g.quota = 0;
 		ctx->launches++;
 		g.sticky_multi = g.sticky_big = nullptr;
@@ -968,6 +987,14 @@ struct TilePlan {
 // defer: enqueue only - no host round trip; the counters that say whether the pools were large enough are read by the
 // caller together with those of pass 2 (which never follows a reference beyond a pool), and a pass 1 that fell short is
 // repeated without `defer`. Saves one synchronisation per dilation.
+// A pass 1 whose first tile launch ran without the inline sorted-list union (TilePlan::lean1) and that handed slots to the
+// redo launch has probably met "complex" classes: the next calls of this context take the inline variant again.
+inline void note_pass1_redo(vo_ctx *ctx, unsigned long long redo_count)
+{
+	if (ctx->last_lean1 && redo_count != 0) ctx->gen_inline_calls = 64;
+	ctx->last_lean1 = false;
+}
+
 // Would pass 1 of this volume take the tile kernel?
 bool pass1_uses_tile(const vo_ctx *ctx, const vo_dvol *in, double R)
 {
@@ -1098,6 +1125,7 @@ int pass1(vo_ctx *ctx, const vo_dvol *in, double R, vo_dmid **out,
 		unsigned long long h[NREAD];
 		rc = read_counters(ctx, h);
 		if (rc) return bail(rc);
+		note_pass1_redo(ctx, h[2]);
 		if (h[2] > redo_cap) {
 			if (tile_now) { tile_now = false; continue; }       // too many oversized tiles: simple kernel for everything
 			return bail(fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity"));
@@ -1213,6 +1241,7 @@ int dilate_once(vo_ctx *ctx, int method, const vo_dvol *in, double R, vo_dvol **
 				const unsigned long long *h = ctx->last_ctr;
 				const bool short1 = h[0] > pool_cap || h[2] > redo_cap || h[4] != 0 || (redo_skipped && h[2] != 0);
 				if (redo_skipped && h[2] != 0) ctx->redo_recent = 16;
+				note_pass1_redo(ctx, h[2]);
 				if (rc == VO_OK && !short1) {
 					ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
 					if (h[5]) ctx->pooled_per_column = (double)h[0] / (double)std::max<unsigned long long>(1, (unsigned long long)in->nx * in->ny);
@@ -2198,6 +2227,9 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		bool redo = h[9] != 0 || h[1] > sb.st.pool_cap;         // rare: the plain path regrows / reports
 		for (int b = 0; b < nb; ++b) redo = redo || (unsigned int)hgb[nb + 1 + b] > rcap2 || (unsigned int)hgb[2 * nb + 1 + b] > rcap1;
 		// launches that were left out and turned out to be needed: the plain path does this call, the next ones make them
+		unsigned long long redo1_count = 0;
+		for (int b = 0; b < nb; ++b) redo1_count += (unsigned int)hgb[2 * nb + 1 + b];
+		note_pass1_redo(ctx, redo1_count);                           // (slots handed over by the 20-warp first launch: see there)
 		if (no_redo)
 			for (int b = 0; b < nb; ++b)
 				if ((unsigned int)hgb[nb + 1 + b] || (unsigned int)hgb[2 * nb + 1 + b]) { ctx->pipe_redo = true; redo = true; }
@@ -2494,6 +2526,7 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 	VO_TRY(read_counters(ctx, h));
 	VO_CUDA(cudaGetLastError());
 	if (h[0] > S->mid->pool_cap) { ctx->pool_hint = h[0] + h[0] / 4; return fail(ctx, VO_ERR_OVERFLOW, "mid pool too small"); }
+	note_pass1_redo(ctx, h[2]);
 	if (h[2] > S->redo_cap || h[4]) return fail(ctx, VO_ERR_OVERFLOW, "too many lists outgrew the fast running-union capacity");
 	S->mid->pool_used = h[0];
 	ctx->pool_hint = next_hint(ctx->pool_hint, h[0]);
@@ -2811,6 +2844,11 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "scan") == 0) {
 		if (std::strcmp(value, "fused") == 0) { ctx->fused_scan = true; return VO_OK; }
 		if (std::strcmp(value, "classic") == 0) { ctx->fused_scan = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "tile_general") == 0) {
+		if (std::strcmp(value, "auto") == 0) { ctx->gen_mode = -1; ctx->gen_inline_calls = 0; return VO_OK; }
+		if (std::strcmp(value, "redo") == 0) { ctx->gen_mode = 0; return VO_OK; }
+		if (std::strcmp(value, "inline") == 0) { ctx->gen_mode = 1; return VO_OK; }
 	}
 	if (std::strcmp(key, "cand_order") == 0) {
 		if (std::strcmp(value, "auto") == 0) { ctx->cand_order = -1; return VO_OK; }
