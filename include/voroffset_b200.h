@@ -96,7 +96,9 @@ uint64_t    vo_launch_count(const vo_ctx *ctx);
  * (auto) | 1..16 (warps per CTA of the tile kernel's multi-interval launches), "cand_order" = "auto" | "column" | "layer"
  * (order in which those launches walk a tile's candidates; a speed knob, the result never depends on it), "tile_general" =
  * "auto" | "redo" | "inline" (first tile launch: classes that need the sorted-list union go to the redo launch - 20 warps
- * per SM - or are folded inline - 16 warps; auto switches to inline for a while when a call met such classes);
+ * per SM - or are folded inline - 16 warps; auto switches to inline for a while when a call met such classes), "pass2_union" =
+ * "auto" | "registers" | "lists" (pass 2 on one-interval-per-column input: running union of capacity 2 in registers, a
+ * third interval goes to the redo launch; auto falls back to the list-capable kernel when many columns needed it);
  * y-slab step: "slab" = "overlap" | "serial". (DESIGN.md 4.1-4.3 say what each is for and what it measured.)     */
 int         vo_set_option(vo_ctx *ctx, const char *key, const char *value);
 /* Timing on the context's own stream (torch.cuda.Event only sees torch's streams): vo_mark records event

@@ -106,9 +106,21 @@ def test_complex_classes_in_single_interval_tiles(ctx, oracle):
             out, _, _ = op.morph_dev("dilation", d, 6.4)
             assert out.download().bit_equal(want), mode
             out.free(); d.free()
+        # the same input leaves one output column in sixty with three intervals and more: pass 2's register-only union (capacity 2) hands
+        # them to the redo launch, the list-capable kernel folds them itself, 'auto' goes from one to the other
+        assert want.counts().max() >= 3
+        for mode in ("registers", "lists", "auto", "auto", "registers"):
+            ctx.set_option("pass2_union", mode)
+            got, _, _ = op.dilation(vol, 6.4)
+            assert got.bit_equal(want), mode
+            d = morpho.DeviceVolume.upload(ctx, vol)
+            out, _, _ = op.morph_dev("dilation", d, 6.4)
+            assert out.download().bit_equal(want), mode
+            out.free(); d.free()
     finally:
         ctx.set_option("pass1", "auto")
         ctx.set_option("tile_general", "auto")
+        ctx.set_option("pass2_union", "auto")
 
 
 def _height_field(nx, ny, seed, padding, holes=0.03, thick=(0.4, 30.0), rough=3.0):

@@ -56,6 +56,10 @@ struct ListStore {
 	__device__ __forceinline__ double2 *ptr(const Work &) { return a; }
 };
 template <>
+struct ListStore<2> {           // (a running union of capacity 2 lives in registers: no list at all)
+	__device__ __forceinline__ double2 *ptr(const Work &) { return nullptr; }
+};
+template <>
 struct ListStore<CAP_HUGE> {
 	__device__ __forceinline__ double2 *ptr(const Work &wk) { return wk.huge + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * CAP_HUGE; }
 };

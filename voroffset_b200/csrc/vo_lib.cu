@@ -58,6 +58,8 @@ struct vo_ctx {
 	int multi_warps = 0;              // vo_set_option("multi_warps", "N"): warps per CTA of the tile kernel's multi-interval launches (0: chosen by
 	                                  // TilePlan::init - fewer than 16 for deep columns, whose sorted-list unions keep their lists in local memory:
 	                                  // 16 warps x 32 lanes x ~26 intervals outgrow the L1 and every insertion waits for the L2)
+	int p2_mode = -1;                 // vo_set_option("pass2_union", "auto" | "registers" | "lists"): running union of pass 2 on shallow input, see pass2()
+	int p2_list_calls = 0;            // > 0: pass 2 keeps its list-capable union for this many more calls
 	int gen_mode = -1;                // vo_set_option("tile_general", "auto" | "redo" | "inline"): -1 as described below, 0 never inline, 1 always
 	bool last_lean1 = false;          // the last tile launch set started with the 20-warp variant (note_pass1_redo)
 	int gen_inline_calls = 0;         // > 0: the first tile launch keeps its inline sorted-list union for this many more calls (k_pass1_tile<..., GEN>:
@@ -1154,10 +1156,18 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEven
 	a.mid = m->slots; a.flags = m->flags; a.tilemask = m->tilemask; a.pool = m->pool; a.pool_cap = m->pool_cap;
 	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
 	cudaStream_t s = ctx->stream;
-	return run_staged(ctx, a, nlists, 65536ull + nlists / 8,
+	// Shallow input (one interval per column): nearly every output column is one or two intervals, which the running union
+	// keeps in registers. The kernel instantiated with capacity 2 has no list, no call into the list code and no local
+	// memory (C5 k_pass2_rows 0.175 -> 0.155 ms); a third interval sends the column to the redo launch. A call that sent
+	// more than one column in 128 there goes back to the list-capable kernel for the next 64 calls.
+	const bool regonly = a.J <= 32 && m->shallow && (ctx->p2_mode == 0 || (ctx->p2_mode < 0 && ctx->p2_list_calls == 0));
+	if (!regonly && ctx->p2_list_calls > 0) --ctx->p2_list_calls;
+	const int rc2 = run_staged(ctx, a, nlists, 65536ull + nlists / 8,
 		[&](Pass2Args &g) {
 			cudaEventRecord(ctx->kev[2], s);
-			if (g.J <= 32 && m->shallow)
+			if (regonly)
+				k_pass2_rows<2, false, P2_SHALLOW><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+			else if (g.J <= 32 && m->shallow)
 				k_pass2_rows<CAP_FAST, false, P2_SHALLOW><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
 			else if (g.J <= 32)
 				k_pass2_rows<CAP_FAST, false><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
@@ -1173,6 +1183,8 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEven
 			else k_pass2<CAP_BIG><<<grid, 128, 0, s>>>(g);
 		},
 		m->nx, y1 - y0, out, done_ev);
+	if (regonly && ctx->last_ctr[8] > std::max<unsigned long long>(64, nlists / 128)) ctx->p2_list_calls = 64;
+	return rc2;
 }
 
 // pass 2 of the dual form (k_pass2_rows_dual): hull of the mirrored slots, empty columns in reach, negateInv's clamping
@@ -1993,6 +2005,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 	// ends with such a tail), its CTAs taking over the SMs as those of band b retire.
 	// (normally idle launches left out: see vo_ctx::pipe_lean)
 	const bool no_lists = ctx->pipe_lean && !ctx->pipe_lists, no_redo = ctx->pipe_lean && !ctx->pipe_redo;
+	const bool p2_regonly = no_lists && (ctx->p2_mode == 0 || (ctx->p2_mode < 0 && ctx->p2_list_calls == 0));   // (see pass2())
+	if (!p2_regonly && ctx->p2_list_calls > 0) --ctx->p2_list_calls;
 	auto pass1_band = [&](int b) {
 		const int y0 = ys[b], y1 = ys[b + 1], w = b & 1;
 		cudaStream_t sp = ctx->s_p[w];
@@ -2105,7 +2119,8 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			cudaEventRecord(ev_tot[b], ctx->s_ctl);
 			return;
 		}
-		if (J <= 32 && no_lists) k_pass2_rows<CAP_FAST, false, P2_SHALLOW><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		if (J <= 32 && no_lists && p2_regonly) k_pass2_rows<2, false, P2_SHALLOW><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		else if (J <= 32 && no_lists) k_pass2_rows<CAP_FAST, false, P2_SHALLOW><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		else if (J <= 32) k_pass2_rows<CAP_FAST, false><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		else k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		a2.wk = Work{rd.list, 0ull, rd.count, rd.cap, reinterpret_cast<unsigned int *>(ctx->d_ctr + 9)};
@@ -2227,6 +2242,11 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 		bool redo = h[9] != 0 || h[1] > sb.st.pool_cap;         // rare: the plain path regrows / reports
 		for (int b = 0; b < nb; ++b) redo = redo || (unsigned int)hgb[nb + 1 + b] > rcap2 || (unsigned int)hgb[2 * nb + 1 + b] > rcap1;
 		// launches that were left out and turned out to be needed: the plain path does this call, the next ones make them
+		if (p2_regonly) {                                        // (as pass2(): columns with a third interval)
+			unsigned long long redo2_count = 0;
+			for (int b = 0; b < nb; ++b) redo2_count += (unsigned int)hgb[nb + 1 + b];
+			if (redo2_count) ctx->p2_list_calls = 64;
+		}
 		unsigned long long redo1_count = 0;
 		for (int b = 0; b < nb; ++b) redo1_count += (unsigned int)hgb[2 * nb + 1 + b];
 		note_pass1_redo(ctx, redo1_count);                           // (slots handed over by the 20-warp first launch: see there)
@@ -2844,6 +2864,11 @@ int vo_set_option(vo_ctx *ctx, const char *key, const char *value)
 	if (std::strcmp(key, "scan") == 0) {
 		if (std::strcmp(value, "fused") == 0) { ctx->fused_scan = true; return VO_OK; }
 		if (std::strcmp(value, "classic") == 0) { ctx->fused_scan = false; return VO_OK; }
+	}
+	if (std::strcmp(key, "pass2_union") == 0) {
+		if (std::strcmp(value, "auto") == 0) { ctx->p2_mode = -1; ctx->p2_list_calls = 0; return VO_OK; }
+		if (std::strcmp(value, "registers") == 0) { ctx->p2_mode = 0; return VO_OK; }
+		if (std::strcmp(value, "lists") == 0) { ctx->p2_mode = 1; return VO_OK; }
 	}
 	if (std::strcmp(key, "tile_general") == 0) {
 		if (std::strcmp(value, "auto") == 0) { ctx->gen_mode = -1; ctx->gen_inline_calls = 0; return VO_OK; }
