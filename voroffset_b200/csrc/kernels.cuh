@@ -319,6 +319,10 @@ constexpr int P2_TX = 128;
 // (40 registers, ~230 bytes of spills) where the mid slots hold one interval each - height-field-like input, the dual
 // form: the gather is bound by memory latency, C5 k_pass2_rows 0.197 -> 0.174 ms, 14 and 16 give no more.
 constexpr int P2_DEEP = 8, P2_SHALLOW = 12;
+#ifndef P2_REGONLY_V
+#define P2_REGONLY_V 12
+#endif
+constexpr int P2_REGONLY = P2_REGONLY_V;   // CTAs per SM of the register-only variant (running union of capacity 2, vo_lib.cu: pass2())
 
 // WIDE = false: floor(R) <= 32, the class masks are 32-bit words.
 // The union of output column (tile * P2_TX + threadIdx.x, y) into `u`; every thread of the CTA calls it (warp ballots),

@@ -1189,7 +1189,9 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : GEN ? P1_MAXWARP
 		if (have_next) load_offsets(npos, o, nxt);
 
 		// ---- current tile, phase 1 ----
+#ifdef VO_TILE_DEBUG
 		const long long dbg_t0 = a.dbg ? clock64() : 0;
+#endif
 		if (cur.kind == TK_NORMAL) {
 			tl.gthr = a.thr + cur.base; tl.ci = sm.ci[buf]; tl.ly = sm.ly[buf];
 			if (!lean) {
@@ -1222,16 +1224,20 @@ __global__ void __launch_bounds__(32 * (MULTI ? P1_MAXWARPS_M : GEN ? P1_MAXWARP
 		__syncwarp();                                       // phase 1 of the current tile is complete (lists visible)
 
 		// ---- current tile, phase 2 ----
+#ifdef VO_TILE_DEBUG                                     // (development builds: per-tile statistics for scripts/tile_costs.py)
 		unsigned int dbg_entries = 0;
 		const long long dbg_t1 = a.dbg ? clock64() : 0;
 		if (a.dbg && cur.kind == TK_NORMAL) { __syncwarp(); dbg_entries = __reduce_add_sync(FULL, sm.cnt[lane]); }
+#endif
 		if (cur.kind == TK_NORMAL) tile_phase2<CAP, MULTI, LCAP, DUAL, GEN>(a, cur, tl, sm.off[buf]);
 		__syncwarp();                                       // lists, counters and the staging buffer are free again
+#ifdef VO_TILE_DEBUG
 		if (a.dbg && lane == 0 && cur.kind == TK_NORMAL) {     // (scripts/tile_costs.py)
 			unsigned long long *d = a.dbg + 4ull * cur.tile;
 			d[0] = (unsigned long long)(clock64() - dbg_t0); d[1] = (unsigned long long)cur.ncand; d[2] = dbg_entries;
 			d[3] = (unsigned long long)(dbg_t1 - dbg_t0);
 		}
+#endif
 		if (!have_next) break;
 		if (!dbuf && nxt.kind == TK_NORMAL) { stage(nxt, buf ^ 1); __syncwarp(); }
 		cur = nxt;

@@ -1166,7 +1166,7 @@ int pass2(vo_ctx *ctx, const vo_dmid *m, int y0, int y1, vo_dvol **out, cudaEven
 		[&](Pass2Args &g) {
 			cudaEventRecord(ctx->kev[2], s);
 			if (regonly)
-				k_pass2_rows<2, false, P2_SHALLOW><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+				k_pass2_rows<2, false, P2_REGONLY><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
 			else if (g.J <= 32 && m->shallow)
 				k_pass2_rows<CAP_FAST, false, P2_SHALLOW><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
 			else if (g.J <= 32)
@@ -2119,7 +2119,7 @@ int dilate_ours_pipelined(vo_ctx *ctx, int nx, int ny, const uint32_t *off, cons
 			cudaEventRecord(ev_tot[b], ctx->s_ctl);
 			return;
 		}
-		if (J <= 32 && no_lists && p2_regonly) k_pass2_rows<2, false, P2_SHALLOW><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
+		if (J <= 32 && no_lists && p2_regonly) k_pass2_rows<2, false, P2_REGONLY><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		else if (J <= 32 && no_lists) k_pass2_rows<CAP_FAST, false, P2_SHALLOW><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		else if (J <= 32) k_pass2_rows<CAP_FAST, false><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
 		else k_pass2_rows<CAP_FAST><<<(unsigned int)((nx + P2_TX - 1) / P2_TX) * (unsigned int)(y1 - y0), P2_TX, 0, sm>>>(a2);
