@@ -193,6 +193,7 @@ struct Pass2Args {
 	// dual form only (k_pass2_rows_dual): distance of every column to the nearest EMPTY column of its row (k_empty_dist),
 	// the reach of every class, and the range negateInv keeps (zmin, zmax of the erosion)
 	const uint8_t *dist = nullptr;
+	const uint8_t *dist_tmin = nullptr;   // ... and the smallest of them per pass-2 tile and row (k_empty_dist)
 	const int *reach = nullptr;
 	double lo = 0, hi = 0;
 };
@@ -201,6 +202,8 @@ struct Pass2Args {
 // when floor(R) + 1 does not fit the 8-bit window bound; lo = hi = 255 never occurs as a window, empty ones are 0).
 constexpr uint16_t FLAG_ALL = 0xFFFFu;
 __device__ __forceinline__ bool flag_has(uint16_t w, int j) { return w == FLAG_ALL || ((int)(w & 0xffu) <= j && j < (int)(w >> 8)); }
+// ... where the sentinel cannot occur (the row kernels: floor(R) <= 63): lo <= j < hi as one unsigned compare
+__device__ __forceinline__ bool flag_in(uint16_t w, int j) { const unsigned int lo = w & 0xffu; return (unsigned int)j - lo < (unsigned int)(w >> 8) - lo; }
 
 template <int CAP>
 __device__ __forceinline__ void pass2_take(RunUnion<CAP> &u, const double2 *slot, const double2 *pool, unsigned long long pool_cap)
@@ -368,11 +371,11 @@ __device__ __forceinline__ bool pass2_rows_union(const Pass2Args &a, int tiles_x
 		for (int i = 0; i < 4; ++i) w[i] = __ldg(p[i]);
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			if (jj[i] < 0) m_up |= (M)flag_has(w[i], -jj[i]) << (-jj[i] - 1);
-			else if (jj[i] > 0) m_dn |= (M)flag_has(w[i], jj[i]) << (jj[i] - 1);
+			if (jj[i] < 0) m_up |= (M)flag_in(w[i], -jj[i]) << (-jj[i] - 1);
+			else if (jj[i] > 0) m_dn |= (M)flag_in(w[i], jj[i]) << (jj[i] - 1);
 		}
 	}
-	pass2_gather<CAP, M>(a, u, x, y, m_up, m_dn, flag_has(w_up, 0) || flag_has(w_dn, 0));
+	pass2_gather<CAP, M>(a, u, x, y, m_up, m_dn, flag_in(w_up, 0) || flag_in(w_dn, 0));
 	return true;
 }
 
@@ -413,11 +416,16 @@ __global__ void __launch_bounds__(P2_TX, MINB) k_pass2_rows(Pass2Args a)
 // memory, then a word-wise search to either side.
 // ---------------------------------------------------------------------------------------------------
 constexpr int ED_THREADS = 256;
-__global__ void __launch_bounds__(ED_THREADS) k_empty_dist(const uint32_t *__restrict__ off, int nx, uint8_t *__restrict__ dist)
+// tmin [ny * ceil(nx / P2_TX)]: the smallest distance inside every pass-2 tile of the row - k_pass2_rows_dual skips its
+// per-column scan of the 2 floor(R) + 1 rows when no tile above or below comes within reach (the inside of a solid)
+// (shared memory: ceil(nx / 32) occupancy words + ceil(nx / P2_TX) tile minima)
+__global__ void __launch_bounds__(ED_THREADS) k_empty_dist(const uint32_t *__restrict__ off, int nx, uint8_t *__restrict__ dist, uint8_t *__restrict__ tmin)
 {
 	extern __shared__ uint32_t s_occ[];                     // bit x = column x is EMPTY
-	const int y = blockIdx.x, nwords = (nx + 31) >> 5;
+	const int y = blockIdx.x, nwords = (nx + 31) >> 5, ntx = (nx + P2_TX - 1) / P2_TX;
+	uint32_t *s_tmin = s_occ + nwords;
 	const uint32_t *row = off + (size_t)y * nx;
+	for (int i = threadIdx.x; i < ntx; i += ED_THREADS) s_tmin[i] = 255u;
 	for (int x0 = 0; x0 < nwords * 32; x0 += ED_THREADS) {
 		const int x = x0 + (int)threadIdx.x;
 		const bool empty = x < nx && __ldg(row + x + 1) == __ldg(row + x);
@@ -425,26 +433,35 @@ __global__ void __launch_bounds__(ED_THREADS) k_empty_dist(const uint32_t *__res
 		if ((threadIdx.x & 31) == 0 && (x >> 5) < nwords) s_occ[x >> 5] = b;
 	}
 	__syncthreads();
-	for (int x = threadIdx.x; x < nx; x += ED_THREADS) {
-		int best = min(min(x + 1, nx - x), 255);
-		// nearest empty column at or below x
-		int wi = x >> 5;
-		uint32_t bits = s_occ[wi] & (0xffffffffu >> (31 - (x & 31)));
-		while (true) {
-			if (bits) { best = min(best, x - (wi * 32 + 31 - __clz(bits))); break; }
-			if (wi == 0 || x - (wi * 32 - 1) >= best) break;
-			bits = s_occ[--wi];
+	for (int x0 = 0; x0 < nx; x0 += ED_THREADS) {           // (whole warps stay in the loop: the tile minimum is a warp reduction)
+		const int x = x0 + (int)threadIdx.x;
+		int best = 255;
+		if (x < nx) {
+			best = min(min(x + 1, nx - x), 255);
+			// nearest empty column at or below x
+			int wi = x >> 5;
+			uint32_t bits = s_occ[wi] & (0xffffffffu >> (31 - (x & 31)));
+			while (true) {
+				if (bits) { best = min(best, x - (wi * 32 + 31 - __clz(bits))); break; }
+				if (wi == 0 || x - (wi * 32 - 1) >= best) break;
+				bits = s_occ[--wi];
+			}
+			// ... above x
+			wi = x >> 5;
+			bits = s_occ[wi] & (0xffffffffu << (x & 31));
+			while (true) {
+				if (bits) { best = min(best, wi * 32 + __ffs(bits) - 1 - x); break; }
+				if (wi + 1 >= nwords || (wi + 1) * 32 - x >= best) break;
+				bits = s_occ[++wi];
+			}
+			dist[(size_t)y * nx + x] = (uint8_t)best;
 		}
-		// ... above x
-		wi = x >> 5;
-		bits = s_occ[wi] & (0xffffffffu << (x & 31));
-		while (true) {
-			if (bits) { best = min(best, wi * 32 + __ffs(bits) - 1 - x); break; }
-			if (wi + 1 >= nwords || (wi + 1) * 32 - x >= best) break;
-			bits = s_occ[++wi];
-		}
-		dist[(size_t)y * nx + x] = (uint8_t)best;
+		// (a warp's 32 consecutive columns start at a multiple of 32: one tile)
+		const unsigned int wmin = __reduce_min_sync(0xffffffffu, (unsigned int)best);
+		if ((threadIdx.x & 31) == 0 && (x0 + (int)(threadIdx.x & ~31u)) < nx) atomicMin(s_tmin + (x0 + (int)(threadIdx.x & ~31u)) / P2_TX, wmin);
 	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < ntx; i += ED_THREADS) tmin[(size_t)y * ntx + i] = (uint8_t)s_tmin[i];
 }
 
 // Does a volume qualify for the dual form? *flag is raised when a column holds several intervals or an interval is not
@@ -465,8 +482,10 @@ __global__ void __launch_bounds__(256) k_dual_check(const uint32_t *__restrict__
 
 // Pass 2 of the dual form: same segment / tile-mask logic as k_pass2_rows; the fold is a hull (no running union), an
 // output column with an empty column (or the border) in reach is empty, the rest goes through negateInv's clamping.
+template <bool WIDE = true>                             // WIDE = false: floor(R) <= 32, class masks in 32-bit words (as k_pass2_rows)
 __global__ void __launch_bounds__(P2_TX, P2_SHALLOW) k_pass2_rows_dual(Pass2Args a)
 {
+	typedef typename std::conditional<WIDE, unsigned long long, unsigned int>::type M;
 	__shared__ int s_reach[64];
 	if (threadIdx.x <= (unsigned)a.J) s_reach[threadIdx.x] = __ldg(a.reach + threadIdx.x);
 	__syncthreads();
@@ -477,24 +496,34 @@ __global__ void __launch_bounds__(P2_TX, P2_SHALLOW) k_pass2_rows_dual(Pass2Args
 	const int lane = threadIdx.x & 31;
 	const size_t nx = (size_t)a.nx;
 	const unsigned long long *t_up = a.tilemask, *t_dn = a.tilemask + (size_t)a.ny * tiles_x;
-	unsigned long long c_up = 0, c_dn = 0;
+	M c_up = 0, c_dn = 0;
 #pragma unroll
-	for (int h = 0; h < 2; ++h) {
+	for (int h = 0; h < (WIDE ? 2 : 1); ++h) {
 		const int j = lane + 1 + 32 * h;
 		bool pu = false, pd = false;
 		if (j <= a.J) {
 			if (y - j >= 0) pu = (__ldg(t_dn + (size_t)(y - j) * tiles_x + tile) >> j) & 1ull;
 			if (y + j < a.ny) pd = (__ldg(t_up + (size_t)(y + j) * tiles_x + tile) >> j) & 1ull;
 		}
-		c_up |= (unsigned long long)__ballot_sync(0xffffffffu, pu) << (32 * h);
-		c_dn |= (unsigned long long)__ballot_sync(0xffffffffu, pd) << (32 * h);
+		c_up |= (M)__ballot_sync(0xffffffffu, pu) << (32 * h);
+		c_dn |= (M)__ballot_sync(0xffffffffu, pd) << (32 * h);
+	}
+	// an empty column within reach[|dy|] of x in row y + dy, |dy| <= J (rows outside the grid are the border: empty)
+	bool killed = y < a.J || a.ny - 1 - y < a.J;
+	// (tile minima of the distances: can anything in the 2J + 1 rows of this tile come within reach at all? - whole warps)
+	bool near_empty = true;
+	if (a.dist_tmin && !killed) {
+		near_empty = false;
+		for (int j = lane; j <= a.J; j += 32) {
+			const int r = s_reach[j];
+			near_empty |= (int)__ldg(a.dist_tmin + (size_t)(y - j) * tiles_x + tile) <= r || (int)__ldg(a.dist_tmin + (size_t)(y + j) * tiles_x + tile) <= r;
+		}
+		near_empty = __any_sync(0xffffffffu, near_empty);
 	}
 	if (x >= a.nx) return;
 	const size_t cc = (size_t)y * nx + x;
 	const unsigned long long c = (unsigned long long)(y - a.y0) * nx + x;
-	// an empty column within reach[|dy|] of x in row y + dy, |dy| <= J (rows outside the grid are the border: empty)
-	bool killed = y < a.J || a.ny - 1 - y < a.J;
-	if (!killed) {
+	if (!killed && near_empty) {
 		const uint8_t *d = a.dist + cc;
 		killed = (int)__ldg(d) <= s_reach[0];
 		for (int j0 = 1; j0 <= a.J && !killed; j0 += 4) {
@@ -513,7 +542,7 @@ __global__ void __launch_bounds__(P2_TX, P2_SHALLOW) k_pass2_rows_dual(Pass2Args
 	}
 	if (killed) { a.st.cnt[c] = 0; return; }
 	const uint16_t *f_up = a.flags, *f_dn = a.flags + (size_t)a.ny * nx;
-	unsigned long long m_up = 0, m_dn = 0;
+	M m_up = 0, m_dn = 0;
 	const uint16_t w_up = __ldg(f_up + cc), w_dn = __ldg(f_dn + cc);
 	while (c_up | c_dn) {
 		int jj[4];
@@ -521,16 +550,16 @@ __global__ void __launch_bounds__(P2_TX, P2_SHALLOW) k_pass2_rows_dual(Pass2Args
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			jj[i] = 0; p[i] = f_up + cc;
-			if (c_up) { const int j = __ffsll((long long)c_up); c_up &= c_up - 1; jj[i] = -j; p[i] = f_dn + cc - (size_t)j * nx; }
-			else if (c_dn) { const int j = __ffsll((long long)c_dn); c_dn &= c_dn - 1; jj[i] = j; p[i] = f_up + cc + (size_t)j * nx; }
+			if (c_up) { const int j = mask_ffs(c_up); c_up &= c_up - 1; jj[i] = -j; p[i] = f_dn + cc - (size_t)j * nx; }
+			else if (c_dn) { const int j = mask_ffs(c_dn); c_dn &= c_dn - 1; jj[i] = j; p[i] = f_up + cc + (size_t)j * nx; }
 		}
 		uint16_t w[4];
 #pragma unroll
 		for (int i = 0; i < 4; ++i) w[i] = __ldg(p[i]);
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			if (jj[i] < 0) m_up |= (unsigned long long)flag_has(w[i], -jj[i]) << (-jj[i] - 1);
-			else if (jj[i] > 0) m_dn |= (unsigned long long)flag_has(w[i], jj[i]) << (jj[i] - 1);
+			if (jj[i] < 0) m_up |= (M)flag_in(w[i], -jj[i]) << (-jj[i] - 1);
+			else if (jj[i] > 0) m_dn |= (M)flag_in(w[i], jj[i]) << (jj[i] - 1);
 		}
 	}
 	// hull of the mirrored slots: X = min (-a - h) = -L, Y = max (-b + h) = -U
@@ -538,7 +567,7 @@ __global__ void __launch_bounds__(P2_TX, P2_SHALLOW) k_pass2_rows_dual(Pass2Args
 	double X = inf, Y = -inf;
 	const size_t midrow = (size_t)(a.J + 1) * nx;
 	const double2 *self = a.mid + (size_t)y * midrow + x;
-	if (flag_has(w_up, 0) || flag_has(w_dn, 0)) { const double2 v = __ldg(self); X = v.x < X ? v.x : X; Y = v.y > Y ? v.y : Y; }
+	if (flag_in(w_up, 0) || flag_in(w_dn, 0)) { const double2 v = __ldg(self); X = v.x < X ? v.x : X; Y = v.y > Y ? v.y : Y; }
 	const size_t step_up = midrow - nx, step_dn = midrow + nx;
 	while (m_up | m_dn) {
 		const double2 *p[4];
@@ -546,8 +575,8 @@ __global__ void __launch_bounds__(P2_TX, P2_SHALLOW) k_pass2_rows_dual(Pass2Args
 #pragma unroll
 		for (int i = 0; i < 4; ++i) {
 			p[i] = self;
-			if (m_up) { const int j = __ffsll((long long)m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
-			else if (m_dn) { const int j = __ffsll((long long)m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
+			if (m_up) { const int j = mask_ffs(m_up); m_up &= m_up - 1; p[i] = self - (size_t)j * step_up; n = i + 1; }
+			else if (m_dn) { const int j = mask_ffs(m_dn); m_dn &= m_dn - 1; p[i] = self + (size_t)j * step_dn; n = i + 1; }
 		}
 		double2 v[4];
 #pragma unroll

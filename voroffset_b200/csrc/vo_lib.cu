@@ -1197,12 +1197,14 @@ int pass2_dual(vo_ctx *ctx, const vo_dmid *m, const uint8_t *dist, const int *re
 	a.nx = m->nx; a.ny = m->ny; a.J = m->J; a.y0 = y0; a.y1 = y1;
 	a.mid = m->slots; a.flags = m->flags; a.tilemask = m->tilemask; a.pool = m->pool; a.pool_cap = m->pool_cap;
 	a.dist = dist; a.reach = reach; a.lo = lo; a.hi = hi;
+	a.dist_tmin = dist + (size_t)m->nx * m->ny;                 // (k_empty_dist leaves the tile minima behind the distances)
 	const unsigned long long nlists = (unsigned long long)m->nx * (y1 - y0);
 	cudaStream_t s = ctx->stream;
 	return run_staged(ctx, a, nlists, 65536ull,
 		[&](Pass2Args &g) {
 			cudaEventRecord(ctx->kev[2], s);
-			k_pass2_rows_dual<<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+			if (g.J <= 32) k_pass2_rows_dual<false><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
+			else k_pass2_rows_dual<true><<<(unsigned int)((g.nx + P2_TX - 1) / P2_TX) * (unsigned int)(g.y1 - g.y0), P2_TX, 0, s>>>(g);
 			cudaEventRecord(ctx->kev[3], s);
 			ctx->kev_valid[1] = true;
 		},
@@ -1442,8 +1444,9 @@ int erode_dual(vo_ctx *ctx, const vo_dvol *in, double zmin, double zmax, double 
 	float t1 = 0, t2 = 0;
 	VO_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 	Tmp<uint8_t> dist(ctx);
-	VO_TRY(dalloc(ctx, &dist.p, ncols));
-	k_empty_dist<<<(unsigned int)in->ny, ED_THREADS, (size_t)((in->nx + 31) / 32) * sizeof(uint32_t), ctx->stream>>>(in->off, in->nx, dist.p);
+	const unsigned long long ntmin = (unsigned long long)in->ny * ((in->nx + P2_TX - 1) / P2_TX);     // (tile minima behind the distances)
+	VO_TRY(dalloc(ctx, &dist.p, ncols + ntmin));
+	k_empty_dist<<<(unsigned int)in->ny, ED_THREADS, (size_t)((in->nx + 31) / 32 + (in->nx + P2_TX - 1) / P2_TX) * sizeof(uint32_t), ctx->stream>>>(in->off, in->nx, dist.p, dist.p + ncols);
 	ctx->launches++;
 	vo_dmid *mid = nullptr;
 	const DualSpec ds{zmin - 1, zmax + 1};
@@ -2554,8 +2557,9 @@ int slab_finish(vo_slab *S, const void *d_off_prev, const void *d_spans_prev, ui
 		// (the ranks agreed beforehand that every slab qualifies: k_dual_check in vo_mg.cuh)
 		if (h[14] || h[5] || h[2]) return fail(ctx, VO_ERR_OVERFLOW, "dual erosion: a column did not qualify after all");
 		Tmp<uint8_t> dist(ctx);
-		VO_TRY(dalloc(ctx, &dist.p, (unsigned long long)nx * S->ext->ny));
-		k_empty_dist<<<(unsigned int)S->ext->ny, ED_THREADS, (size_t)((nx + 31) / 32) * sizeof(uint32_t), sm>>>(S->ext->off, nx, dist.p);
+		const unsigned long long ncols_ext = (unsigned long long)nx * S->ext->ny, ntmin = (unsigned long long)S->ext->ny * ((nx + P2_TX - 1) / P2_TX);
+		VO_TRY(dalloc(ctx, &dist.p, ncols_ext + ntmin));
+		k_empty_dist<<<(unsigned int)S->ext->ny, ED_THREADS, (size_t)((nx + 31) / 32 + (nx + P2_TX - 1) / P2_TX) * sizeof(uint32_t), sm>>>(S->ext->off, nx, dist.p, dist.p + ncols_ext);
 		ctx->launches++;
 		TableCache *tc = static_cast<TableCache *>(ctx->table_cache);
 		VO_TRY(pass2_dual(ctx, S->mid, dist.p, tc->dt.reach, S->dual_zmin, S->dual_zmax, out, nullptr, jp, jp + ny));
