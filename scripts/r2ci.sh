@@ -1,3 +1,4 @@
+# (the libvo_defer*.so variants were built with -DVO_DEFER_GENERAL [-DP1_MAXWARPS_V=N], a switch that existed for this run only: the result is the GEN template parameter of k_pass1_tile)
 # first launch of the tile kernel without the inline sorted-list union (complex classes -> redo list): 110 / 88 / 80 registers
 # instead of 128 + spills, so 16 / 20 / 22 / 23 warps per CTA. A/B against the current build + parity of the 20-warp variant
 mkdir -p gpurun_out

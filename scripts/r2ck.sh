@@ -1,3 +1,4 @@
+# (the VO_P2REG environment switch existed for this run only; the variant it selected is now the pass2_union option, default on shallow input)
 # pass 2 with a register-only running union (capacity 2, third interval -> redo launch): 12 and 16 CTAs per SM against the current kernel
 mkdir -p gpurun_out
 for rep in 1 2; do
