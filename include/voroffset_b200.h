@@ -99,7 +99,12 @@ uint64_t    vo_launch_count(const vo_ctx *ctx);
  * per SM - or are folded inline - 16 warps; auto switches to inline for a while when a call met such classes), "pass2_union" =
  * "auto" | "registers" | "lists" (pass 2 on one-interval-per-column input: running union of capacity 2 in registers, a
  * third interval goes to the redo launch; auto falls back to the list-capable kernel when many columns needed it);
- * y-slab step: "slab" = "overlap" | "serial". (DESIGN.md 4.1-4.3 say what each is for and what it measured.)     */
+ * "tile_lean" = "auto" | "on" | "off" (candidates of the tile kernel's list launches left in global memory);
+ * y-slab step: "slab" = "overlap" | "serial", "slab_reserve" = SMs the interior launch leaves to the NCCL kernels (8).
+ * Experiment switches of the host-buffer pipeline, all measured and left at their defaults:
+ * "band_weights" = "1,2,..." (relative band heights), "pipe_ctas", "pipe_quota", "pipe_warps0", "pipe_first_full",
+ * "pipe_interleave", "pipe_mid"; development builds only: "pipe_dry", "ktrace", "ktrace_dump" (-DVO_KTRACE),
+ * "tile_debug" (-DVO_TILE_DEBUG). (DESIGN.md 4.1-4.3 say what each is for and what it measured.)     */
 int         vo_set_option(vo_ctx *ctx, const char *key, const char *value);
 /* Timing on the context's own stream (torch.cuda.Event only sees torch's streams): vo_mark records event
  * `slot` (0..7); vo_elapsed_ms waits for slot_b and returns the device time between the two marks.     */

@@ -57,3 +57,15 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
                 assert "libvoroffset_ref" not in src, f
+
+
+def test_every_option_of_the_library_is_listed_in_the_header():
+    """vo_set_option takes free-form keys: the header is the only place a caller of the C ABI can learn them from."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "voroffset_b200", "csrc", "vo_lib.cu")).read()
+    hdr = open(os.path.join(root, "include", "voroffset_b200.h")).read()
+    keys = sorted(set(re.findall(r'strcmp\(key, "([a-z0-9_]+)"\)', src)))
+    assert len(keys) > 20
+    missing = [k for k in keys if f'"{k}"' not in hdr]
+    assert not missing, missing
