@@ -23,7 +23,8 @@
  *     (VO_ERR_OVERFLOW beyond). Lists of up to 32 intervals take the fast path, up to 512 the redo launch; a dilation that
  *     meets a longer one is repeated once with the redo launches in their last-resort form (csrc/kernels.cuh: CAP_HUGE,
  *     lists in 4.6 GiB of global-memory scratch that only lives for that repeat; VO_ERR_NOMEM if it cannot be had).
- *     The y-slab step (vo_slab_*, vo_mg_*) and the split passes (vo_pass1_dev / vo_pass2_dev) stop at 512;
+ *     The raw y-slab step (vo_slab_*) and the split passes (vo_pass1_dev / vo_pass2_dev) stop at 512; the multi-GPU
+ *     operators (vo_mg_*) leave their overlapped slab step for the plain passes then, which repeat in the same way;
  *   - host CSR inputs are validated (off[0] = 0, offsets non-decreasing: VO_ERR_ARG); volumes that are ALREADY in device
  *     memory (vo_dvol_from_device, the vo_*_dev entry points) are trusted.
  *

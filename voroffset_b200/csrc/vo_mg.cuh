@@ -318,17 +318,21 @@ int mg_dilate(MgRank &r, int world_act, int method, const vo_dvol *own, double R
 		if (rc == DUAL_NA) rc = fail(ctx, VO_ERR_OVERFLOW, "dual erosion: a slab did not qualify after all");
 	} else if (method == VO_METHOD_OURS) {
 		float t1 = 0, t2 = 0;
-		cudaEventRecord(ctx->ev[0], sm);
-		vo_dmid *mid = nullptr;
-		const bool saved = ctx->force_simple_pass1;
-		if (unpruned) ctx->force_simple_pass1 = true;
-		rc = pass1(ctx, ext, R, &mid, clip_lo, clip_hi);
-		ctx->force_simple_pass1 = saved;
-		if (rc == VO_OK) {
-			cudaEventRecord(ctx->ev[1], sm);
-			rc = pass2(ctx, mid, y0, y0 + ny, out);
-			vo_dmid_free(ctx, mid);
-		}
+		// (a list beyond the redo capacity: once more with the last-resort launches, like dilate() - the ranks do not talk here)
+		rc = with_huge_lists(ctx, [&] {
+			cudaEventRecord(ctx->ev[0], sm);
+			vo_dmid *mid = nullptr;
+			const bool saved = ctx->force_simple_pass1;
+			if (unpruned) ctx->force_simple_pass1 = true;
+			int rc1 = pass1(ctx, ext, R, &mid, clip_lo, clip_hi);
+			ctx->force_simple_pass1 = saved;
+			if (rc1 == VO_OK) {
+				cudaEventRecord(ctx->ev[1], sm);
+				rc1 = pass2(ctx, mid, y0, y0 + ny, out);
+				vo_dmid_free(ctx, mid);
+			}
+			return rc1;
+		});
 		if (rc == VO_OK) {
 			cudaEventRecord(ctx->ev[2], sm);
 			cudaEventSynchronize(ctx->ev[2]);
